@@ -1,0 +1,239 @@
+/*
+ * kolibrie_b200.h — C ABI of libkolibrie_b200.so: the B200-native (sm_100a) replacement for the
+ * data-parallel hot path of Kolibrie (dictionary-encoded triple scan + filter, multi-way hash join,
+ * GROUP BY aggregate, Datalog semi-naive fixpoint).
+ *
+ * Plain C, no C++/torch types. All ids are the reference's u32 dictionary term ids
+ * (shared/src/dictionary.rs:32-48; quoted-triple ids carry bit 31, shared/src/quoted_triple_store.rs:17-55).
+ * Variables exist only on the host: a "slot" is a small integer the caller assigns to each variable name.
+ *
+ * Threading: a kb_ctx is NOT re-entrant (one call in flight at a time, any thread) — the reference holds
+ * `&mut SparqlDatabase` (kolibrie/src/streamertail_optimizer/execution/engine.rs:54) or the R2R mutex
+ * (kolibrie/src/rsp_engine.rs:92) around every call. Distinct contexts may run concurrently.
+ *
+ * Ownership: inputs are borrowed for the duration of the call only (the reference passes slices,
+ * kolibrie/src/cuda/cuda_join.rs:41-46). Outputs (kb_rel / kb_groups) are library-owned until *_free.
+ *
+ * Errors: every call returns kb_status; message via kb_last_error(). KB_E_UNSUPPORTED means "shape not
+ * handled on the device — run the reference CPU path" (the `#[cfg(not(feature = "cuda"))]` fallback at
+ * kolibrie/src/execute_query.rs:598-602). There is no CPU fallback inside this library.
+ */
+#ifndef KOLIBRIE_B200_H
+#define KOLIBRIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_API __attribute__((visibility("default")))
+
+typedef int32_t kb_status;
+#define KB_OK 0
+#define KB_E_INVALID (-1)     /* bad argument */
+#define KB_E_CUDA (-2)        /* CUDA runtime error (message has the cudaError string) */
+#define KB_E_OOM (-3)         /* device or host allocation failed */
+#define KB_E_UNSUPPORTED (-4) /* shape not supported on the device: caller falls back to its CPU path */
+#define KB_E_NOT_FOUND (-5)
+#define KB_E_LIMIT (-6)       /* a documented limit was exceeded (rows >= 2^32, > KB_MAX_* ...) */
+
+/* Reserved id. The reference reserves the same value as RuleIndex WILDCARD (shared/src/rule_index.rs:16);
+ * it is never a dictionary id (< 0x8000_0000) and is used here as "no such term" / empty hash slot. */
+#define KB_ID_NONE 0xFFFFFFFFu
+
+#define KB_MAX_PATTERNS 8   /* patterns fused in one scan / one star join */
+#define KB_MAX_COLS 16      /* columns (variables) per relation */
+#define KB_MAX_FILTER_OPS 32
+#define KB_MAX_PREMISES 6
+#define KB_MAX_CONCLUSIONS 4
+#define KB_MAX_RULE_FILTERS 4
+
+typedef struct kb_ctx kb_ctx;
+typedef struct kb_rel kb_rel;       /* device-resident columnar bag of binding rows (reference `Bindings`, shared/src/terms.rs:23) */
+typedef struct kb_groups kb_groups; /* host-resident GROUP BY result */
+
+/* Term of a triple pattern — reference `Term::{Variable,Constant}` (shared/src/terms.rs:14-21).
+ * QuotedTriple terms are resolved on the host before reaching the device (engine.rs:59-70). */
+typedef struct kb_term {
+    uint32_t is_var; /* 1: `value` is a variable slot; 0: `value` is a constant term id */
+    uint32_t value;
+} kb_term;
+
+/* reference `TriplePattern = (Term, Term, Term)` (shared/src/terms.rs:22) */
+typedef struct kb_pattern {
+    kb_term s, p, o;
+} kb_pattern;
+
+/* ---- FILTER programs: postfix encoding of `FilterExpression` (shared/src/query.rs:15-22) with the
+ *      semantics of `Condition::evaluate_with_ids` (kolibrie/src/streamertail_optimizer/types.rs:110-186) ---- */
+enum kb_filter_opcode {
+    KB_F_CMP_NUM = 1, /* push ( num_or0[row[slot]] <cmp> value )          types.rs:133-148: parse::<f64>().unwrap_or(0.0) */
+    KB_F_EQ_ID = 2,   /* push ( row[slot] == id ); id==KB_ID_NONE -> false types.rs:131  (literal not in dictionary) */
+    KB_F_NE_ID = 3,   /* push ( row[slot] != id ); id==KB_ID_NONE -> true  types.rs:132 */
+    KB_F_AND = 4,
+    KB_F_OR = 5,
+    KB_F_NOT = 6,
+    KB_F_PUSH_VAR = 7,   /* arithmetic operand: numeric value of row[slot]; invalid if the term is not numeric (types.rs:163-167) */
+    KB_F_PUSH_CONST = 8, /* arithmetic operand: `value` */
+    KB_F_ADD = 9,
+    KB_F_SUB = 10,
+    KB_F_MUL = 11,
+    KB_F_DIV = 12,      /* divisor == 0.0 -> whole expression invalid (shared/src/query.rs:47-53) */
+    KB_F_TRUTHY = 13,   /* pop number, push ( valid && v != 0.0 )            types.rs:168 */
+    KB_F_IS_TRIPLE = 14 /* push ( row[slot] has bit 31 )                      types.rs:170-183 */
+};
+enum kb_cmp { KB_CMP_GT = 1, KB_CMP_GE = 2, KB_CMP_LT = 3, KB_CMP_LE = 4, KB_CMP_EQ = 5, KB_CMP_NE = 6 };
+
+typedef struct kb_filter_op {
+    uint32_t op;   /* kb_filter_opcode */
+    uint32_t slot; /* variable slot (operand ops) */
+    uint32_t cmp;  /* kb_cmp for KB_F_CMP_NUM */
+    uint32_t id;   /* term id for KB_F_EQ_ID / KB_F_NE_ID */
+    double value;  /* constant for KB_F_CMP_NUM / KB_F_PUSH_CONST */
+} kb_filter_op;
+
+/* ---- aggregates: `group_and_aggregate_results` (kolibrie/src/execute_query.rs:1150-1227) ---- */
+enum kb_agg_kind { KB_AGG_COUNT = 0, KB_AGG_SUM = 1, KB_AGG_MIN = 2, KB_AGG_MAX = 3, KB_AGG_AVG = 4 };
+typedef struct kb_agg {
+    uint32_t kind; /* kb_agg_kind; COUNT ignores slot (rows per group — advertised README.md:415, not parsed by the reference) */
+    uint32_t slot; /* variable aggregated: value = num_or0[row[slot]] (non-numeric -> 0.0, execute_query.rs:1171-1175,1184) */
+} kb_agg;
+
+/* ---- Datalog: `Rule{premise,filters,conclusion}` (shared/src/rule.rs:14-25) ---- */
+typedef struct kb_rule_filter { /* `FilterCondition{variable,operator,value}` with `evaluate_filters` semantics (datalog/src/reasoning/rules.rs:133-165) */
+    uint32_t lhs_slot;
+    uint32_t cmp;        /* kb_cmp; 0 = operator the reference ignores (e.g. "OR:>"): no-op */
+    uint32_t rhs_is_var; /* 1: compare ids of two bound variables (only = and != have an effect, rules.rs:141-146) */
+    uint32_t rhs_slot;
+    double rhs_value;    /* rhs_is_var==0: value.parse::<f64>().unwrap_or(0.0); = / != use f64::EPSILON (rules.rs:157-158) */
+} kb_rule_filter;
+
+typedef struct kb_rule {
+    const kb_pattern* premise;
+    uint32_t n_premise;
+    const kb_rule_filter* filters;
+    uint32_t n_filters;
+    const kb_pattern* conclusion;
+    uint32_t n_conclusion;
+} kb_rule;
+
+enum kb_strategy {
+    KB_SEMI_NAIVE = 0, /* datalog/src/reasoning/materialisation/semi_naive.rs:53-91 */
+    KB_NAIVE = 1       /* datalog/src/reasoning/materialisation/my_naive.rs:10-71 */
+};
+
+typedef struct kb_fixpoint_stats {
+    uint32_t rounds;            /* infer_round calls that produced facts (infer_generic.rs:33-50) */
+    uint64_t inferred;          /* facts appended to the store */
+    uint64_t derivations;       /* candidate head instances before dedup */
+    uint64_t round_new[64];     /* new facts per round (first 64 rounds) */
+    double device_ms;           /* CUDA-event time of the whole fixpoint */
+} kb_fixpoint_stats;
+
+/* per-call device timings (CUDA events on the library's stream); enabled by kb_set_timing(ctx,1) */
+typedef struct kb_stats {
+    double scan_ms, build_ms, probe_ms, filter_ms, group_ms, other_ms, total_ms;
+    uint64_t scan_launches, build_launches, probe_launches, filter_launches, group_launches, other_launches;
+    uint64_t rows_scanned;   /* triples read by scan kernels */
+    uint64_t rows_built;     /* rows inserted in hash tables */
+    uint64_t rows_probed;    /* probe-side rows */
+    uint64_t rows_out;       /* rows of the last result */
+    uint64_t h2d_bytes, d2h_bytes;
+} kb_stats;
+
+/* ------------------------------------------------------------------ context */
+KB_API const char* kb_version(void);
+KB_API kb_status kb_ctx_create(int device, kb_ctx** out);
+KB_API void kb_ctx_destroy(kb_ctx* ctx);
+KB_API const char* kb_last_error(const kb_ctx* ctx); /* ctx may be NULL: last error of a failed kb_ctx_create */
+KB_API kb_status kb_set_timing(kb_ctx* ctx, int enabled);
+KB_API kb_status kb_get_stats(kb_ctx* ctx, kb_stats* out, int reset);
+KB_API kb_status kb_synchronize(kb_ctx* ctx);
+
+/* ------------------------------------------------------------------ triple store (device cache of `SparqlDatabase.triples`,
+ * kolibrie/src/sparql_database.rs:50; segments = RSP window slides, kolibrie/src/rsp_engine.rs:94-104) */
+KB_API kb_status kb_store_load(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n);
+/* same, columns already in device memory of ctx's device (copied device-to-device) */
+KB_API kb_status kb_store_load_device(kb_ctx* ctx, const uint32_t* d_s, const uint32_t* d_p, const uint32_t* d_o, uint64_t n);
+KB_API kb_status kb_store_append(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint64_t segment_tag);
+KB_API kb_status kb_store_evict(kb_ctx* ctx, uint64_t segment_tag);
+/* set-difference by value (SparqlDatabase::delete_triple, sparql_database.rs:229-242) */
+KB_API kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n);
+KB_API kb_status kb_store_clear(kb_ctx* ctx);
+KB_API kb_status kb_store_size(kb_ctx* ctx, uint64_t* n_triples, uint32_t* n_segments);
+/* id -> f64 side table computed by the host with Rust `str::parse::<f64>` acceptance:
+ * num_or0[id] = parse().unwrap_or(0.0); is_num[id] = parse().is_ok(). ids >= n_ids read as (0.0, not numeric). */
+KB_API kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t* is_num, uint32_t n_ids);
+
+/* ------------------------------------------------------------------ relations */
+KB_API kb_status kb_rel_info(const kb_rel* r, uint64_t* n_rows, uint32_t* n_cols, uint32_t* slots /* [KB_MAX_COLS] or NULL */);
+KB_API kb_status kb_rel_download(kb_ctx* ctx, const kb_rel* r, uint32_t col, uint32_t* host_dst /* n_rows */);
+KB_API kb_status kb_rel_device_col(const kb_rel* r, uint32_t col, const uint32_t** d_ptr);
+/* `PhysicalOperator::InMemoryBuffer` / VALUES (operators/physical.rs:16-76; engine.rs:128-130) */
+KB_API kb_status kb_rel_from_host(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* cols, uint64_t n_rows, kb_rel** out);
+KB_API void kb_rel_free(kb_ctx* ctx, kb_rel* r);
+
+/* ------------------------------------------------------------------ operators (mirror `PhysicalOperator`, operators/physical.rs:16-76) */
+/* TableScan/IndexScan (engine.rs:510-584, 1192-1245): ONE fused pass over the store evaluates n_pats patterns.
+ * out[k] has one column per distinct variable of pattern k in s,p,o order. A repeated variable inside one
+ * pattern is enforced as equality (the reference's index scans do not — documented divergence).
+ * pushdown[k] (nullable) is a filter program over pattern k's own variables applied while scanning. */
+KB_API kb_status kb_scan(kb_ctx* ctx, const kb_pattern* pats, uint32_t n_pats,
+                         const kb_filter_op* const* pushdown, const uint32_t* pushdown_len, kb_rel** out);
+/* Filter (engine.rs:73-85) */
+KB_API kb_status kb_filter(kb_ctx* ctx, const kb_rel* in, const kb_filter_op* prog, uint32_t n_ops, kb_rel** out);
+/* Projection — bag semantics, duplicates kept (engine.rs:86-106); zero-copy */
+KB_API kb_status kb_project(kb_ctx* ctx, const kb_rel* in, const uint32_t* slots, uint32_t n_slots, kb_rel** out);
+/* OptimizedHashJoin / HashJoin / merge join / NestedLoopJoin (engine.rs:710-837, 970-1039): natural join on the
+ * common slots; no common slot -> cartesian product (engine.rs:1054-1071, limited to 2^28 output rows). */
+KB_API kb_status kb_hash_join(kb_ctx* ctx, const kb_rel* left, const kb_rel* right, kb_rel** out);
+/* StarJoin (engine.rs:587-691) and bind-join chains on one variable (engine.rs:840-885): fused scan + build + probe.
+ * Every pattern must contain join_slot. `filter` (nullable) is applied to the joined rows (engine.rs:73-85);
+ * conjuncts that touch one pattern only are pushed into the scan. Result caps of the reference (quirk Q1) are NOT applied. */
+KB_API kb_status kb_star_join(kb_ctx* ctx, uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats,
+                              const kb_filter_op* filter, uint32_t n_filter_ops, kb_rel** out);
+/* whole BGP: patterns joined left-deep in the given order (build_logical_plan, utils.rs:101-191), star-fused when
+ * all patterns share one variable (optimizer.rs:84-152); then FILTER, then projection (NULL = all variables). */
+KB_API kb_status kb_bgp_execute(kb_ctx* ctx, const kb_pattern* pats, uint32_t n_pats,
+                                const kb_filter_op* filter, uint32_t n_filter_ops,
+                                const uint32_t* project_slots, uint32_t n_project, kb_rel** out);
+/* GROUP BY + aggregates (execute_query.rs:1150-1227) */
+KB_API kb_status kb_group_aggregate(kb_ctx* ctx, const kb_rel* in, const uint32_t* group_slots, uint32_t n_group,
+                                    const kb_agg* aggs, uint32_t n_aggs, kb_groups** out);
+KB_API kb_status kb_groups_info(const kb_groups* g, uint64_t* n_groups, uint32_t* n_group_cols, uint32_t* n_aggs);
+KB_API kb_status kb_groups_keys(const kb_groups* g, uint32_t col, const uint32_t** keys);   /* host pointer, n_groups */
+KB_API kb_status kb_groups_values(const kb_groups* g, uint32_t agg, const double** values); /* host pointer, n_groups */
+KB_API kb_status kb_groups_counts(const kb_groups* g, const uint64_t** counts);            /* rows per group */
+KB_API void kb_groups_free(kb_groups* g);
+
+/* ------------------------------------------------------------------ Datalog (Reasoner::infer_with_strategy, infer_generic.rs:27-53)
+ * Facts = the ctx store. Inferred facts are appended to the store (segment tag KB_TAG_INFERRED), exactly as the
+ * reference inserts them into its index (infer_generic.rs:46), and returned as a 3-column relation (slots 0,1,2 = s,p,o).
+ * Unsupported rule shapes (variable predicate in a premise, unbound head variable — SURVEY quirks Q6/Q8) -> KB_E_UNSUPPORTED. */
+#define KB_TAG_INFERRED 0xFFFFFFFFFFFFFFF0ull
+KB_API kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy,
+                                     kb_rel** inferred, kb_fixpoint_stats* stats);
+
+/* ------------------------------------------------------------------ multi-GPU helpers (one process per GPU; the host layer
+ * runs the NCCL all-to-all between kb_partition and kb_rel_from_device) */
+KB_API uint32_t kb_shard_of(uint32_t key, uint32_t n_shards); /* mix32(key) % n_shards — same function the device uses */
+/* split `in` by kb_shard_of(row[key_slot]) into n_parts contiguous ranges of ONE output relation;
+ * part_offsets[n_parts+1] (host) receives the row offsets. */
+KB_API kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, kb_rel** out, uint64_t* part_offsets);
+KB_API kb_status kb_rel_from_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out);
+KB_API kb_status kb_store_download(kb_ctx* ctx, uint32_t* s, uint32_t* p, uint32_t* o, uint64_t cap, uint64_t* n);
+
+/* ------------------------------------------------------------------ one-shot host-buffer entry (end-to-end measurement and the
+ * reference's per-call GPU usage, sparql_database.rs:3193-3353): upload (chunked, overlapped with the scan),
+ * star-join, download. Result columns are malloc'd by the callee and owned by the caller (free()). */
+KB_API kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n,
+                                   uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats,
+                                   const kb_filter_op* filter, uint32_t n_filter_ops,
+                                   uint32_t* n_cols, uint32_t* slots /* [KB_MAX_COLS] */, uint32_t** cols /* [KB_MAX_COLS] */, uint64_t* n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KOLIBRIE_B200_H */

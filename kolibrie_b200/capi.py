@@ -1,0 +1,501 @@
+"""ctypes binding of libkolibrie_b200.so (include/kolibrie_b200.h).
+
+This is the Python stand-in for the Rust shim described in INTEGRATION.md: the reference is a Rust workspace and there is no
+Rust toolchain in this image, so tests, bench.py and the multi-GPU plumbing drive the C ABI from Python. There is no CPU
+fallback: if the library (or a GPU) is missing, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkolibrie_b200.so")
+LEGACY_LIB_PATH = os.path.join(_HERE, "libcudajoin.so")
+
+KB_OK = 0
+KB_E_INVALID, KB_E_CUDA, KB_E_OOM, KB_E_UNSUPPORTED, KB_E_NOT_FOUND, KB_E_LIMIT = -1, -2, -3, -4, -5, -6
+KB_ID_NONE = 0xFFFFFFFF
+KB_MAX_COLS = 16
+KB_TAG_INFERRED = 0xFFFFFFFFFFFFFFF0
+
+# filter opcodes / comparisons / aggregates (mirror the header)
+F_CMP_NUM, F_EQ_ID, F_NE_ID, F_AND, F_OR, F_NOT, F_PUSH_VAR, F_PUSH_CONST, F_ADD, F_SUB, F_MUL, F_DIV, F_TRUTHY, F_IS_TRIPLE = range(1, 15)
+CMP_GT, CMP_GE, CMP_LT, CMP_LE, CMP_EQ, CMP_NE = range(1, 7)
+AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_AVG = range(5)
+SEMI_NAIVE, NAIVE = 0, 1
+
+
+class KbTerm(C.Structure):
+    _fields_ = [("is_var", C.c_uint32), ("value", C.c_uint32)]
+
+
+class KbPattern(C.Structure):
+    _fields_ = [("s", KbTerm), ("p", KbTerm), ("o", KbTerm)]
+
+
+class KbFilterOp(C.Structure):
+    _fields_ = [("op", C.c_uint32), ("slot", C.c_uint32), ("cmp", C.c_uint32), ("id", C.c_uint32), ("value", C.c_double)]
+
+
+class KbAgg(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("slot", C.c_uint32)]
+
+
+class KbRuleFilter(C.Structure):
+    _fields_ = [("lhs_slot", C.c_uint32), ("cmp", C.c_uint32), ("rhs_is_var", C.c_uint32), ("rhs_slot", C.c_uint32), ("rhs_value", C.c_double)]
+
+
+class KbRule(C.Structure):
+    _fields_ = [
+        ("premise", C.POINTER(KbPattern)), ("n_premise", C.c_uint32),
+        ("filters", C.POINTER(KbRuleFilter)), ("n_filters", C.c_uint32),
+        ("conclusion", C.POINTER(KbPattern)), ("n_conclusion", C.c_uint32),
+    ]
+
+
+class KbFixpointStats(C.Structure):
+    _fields_ = [("rounds", C.c_uint32), ("inferred", C.c_uint64), ("derivations", C.c_uint64), ("round_new", C.c_uint64 * 64), ("device_ms", C.c_double)]
+
+
+class KbStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("scan_ms", "build_ms", "probe_ms", "filter_ms", "group_ms", "other_ms", "total_ms")] + [
+        (n, C.c_uint64)
+        for n in ("scan_launches", "build_launches", "probe_launches", "filter_launches", "group_launches", "other_launches",
+                  "rows_scanned", "rows_built", "rows_probed", "rows_out", "h2d_bytes", "d2h_bytes")
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def V(slot: int) -> KbTerm:
+    """variable term"""
+    return KbTerm(1, slot)
+
+
+def K(term_id: int) -> KbTerm:
+    """constant term"""
+    return KbTerm(0, term_id)
+
+
+def pattern(s: KbTerm, p: KbTerm, o: KbTerm) -> KbPattern:
+    return KbPattern(s, p, o)
+
+
+def patterns(pats: Sequence[KbPattern]):
+    arr = (KbPattern * max(len(pats), 1))()
+    for i, p in enumerate(pats):
+        arr[i] = p
+    return arr
+
+
+def fop(op, slot=0, cmp=0, id=0, value=0.0) -> KbFilterOp:
+    return KbFilterOp(op, slot, cmp, id, value)
+
+
+def filter_prog(ops: Optional[Sequence[KbFilterOp]]):
+    ops = list(ops or [])
+    arr = (KbFilterOp * max(len(ops), 1))()
+    for i, o in enumerate(ops):
+        arr[i] = o
+    return arr, len(ops)
+
+
+class KolibrieError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"kb_status {status}: {message}")
+        self.status = status
+        self.message = message
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the shared library; fail loudly when it is missing (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                          "kolibrie_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    P = C.POINTER
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+    sig = {
+        "kb_version": (C.c_char_p, []),
+        "kb_ctx_create": (i32, [C.c_int, P(vp)]),
+        "kb_ctx_destroy": (None, [vp]),
+        "kb_last_error": (C.c_char_p, [vp]),
+        "kb_set_timing": (i32, [vp, C.c_int]),
+        "kb_get_stats": (i32, [vp, P(KbStats), C.c_int]),
+        "kb_synchronize": (i32, [vp]),
+        "kb_store_load": (i32, [vp, vp, vp, vp, u64]),
+        "kb_store_load_device": (i32, [vp, vp, vp, vp, u64]),
+        "kb_store_append": (i32, [vp, vp, vp, vp, u64, u64]),
+        "kb_store_evict": (i32, [vp, u64]),
+        "kb_store_delete": (i32, [vp, vp, vp, vp, u64]),
+        "kb_store_clear": (i32, [vp]),
+        "kb_store_size": (i32, [vp, P(u64), P(u32)]),
+        "kb_store_download": (i32, [vp, vp, vp, vp, u64, P(u64)]),
+        "kb_dict_numeric_load": (i32, [vp, vp, vp, u32]),
+        "kb_rel_info": (i32, [vp, P(u64), P(u32), P(u32)]),
+        "kb_rel_download": (i32, [vp, vp, u32, vp]),
+        "kb_rel_device_col": (i32, [vp, u32, P(vp)]),
+        "kb_rel_from_host": (i32, [vp, P(u32), u32, P(vp), u64, P(vp)]),
+        "kb_rel_from_device": (i32, [vp, P(u32), u32, P(vp), u64, P(vp)]),
+        "kb_rel_free": (None, [vp, vp]),
+        "kb_scan": (i32, [vp, P(KbPattern), u32, P(P(KbFilterOp)), P(u32), P(vp)]),
+        "kb_filter": (i32, [vp, vp, P(KbFilterOp), u32, P(vp)]),
+        "kb_project": (i32, [vp, vp, P(u32), u32, P(vp)]),
+        "kb_hash_join": (i32, [vp, vp, vp, P(vp)]),
+        "kb_star_join": (i32, [vp, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(vp)]),
+        "kb_bgp_execute": (i32, [vp, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), u32, P(vp)]),
+        "kb_group_aggregate": (i32, [vp, vp, P(u32), u32, P(KbAgg), u32, P(vp)]),
+        "kb_groups_info": (i32, [vp, P(u64), P(u32), P(u32)]),
+        "kb_groups_keys": (i32, [vp, u32, P(P(u32))]),
+        "kb_groups_values": (i32, [vp, u32, P(P(C.c_double))]),
+        "kb_groups_counts": (i32, [vp, P(P(u64))]),
+        "kb_groups_free": (None, [vp]),
+        "kb_datalog_fixpoint": (i32, [vp, P(KbRule), u32, u32, P(vp), P(KbFixpointStats)]),
+        "kb_shard_of": (u32, [u32, u32]),
+        "kb_partition": (i32, [vp, vp, u32, u32, P(vp), P(u64)]),
+        "kb_star_join_host": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), P(u64)]),
+        "perform_hash_join_cuda": (None, [vp, vp, vp, u32, u32, P(u32), P(P(u32)), P(u32)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = [
+    "kb_version", "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_set_timing", "kb_get_stats", "kb_synchronize",
+    "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_size",
+    "kb_store_download", "kb_dict_numeric_load", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
+    "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
+    "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free",
+    "kb_datalog_fixpoint", "kb_shard_of", "kb_partition", "kb_star_join_host", "perform_hash_join_cuda",
+]
+
+
+def _u32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+class Relation:
+    """Device-resident columnar bag of binding rows (kb_rel)."""
+
+    def __init__(self, ctx: "Context", handle):
+        self.ctx = ctx
+        self.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+
+    def info(self):
+        n, nc = C.c_uint64(), C.c_uint32()
+        slots = (C.c_uint32 * KB_MAX_COLS)()
+        self.ctx._check(lib().kb_rel_info(self.h, C.byref(n), C.byref(nc), slots))
+        return n.value, [slots[i] for i in range(nc.value)]
+
+    @property
+    def n_rows(self) -> int:
+        return self.info()[0]
+
+    @property
+    def slots(self):
+        return self.info()[1]
+
+    def column(self, col: int) -> np.ndarray:
+        n, _ = self.info()
+        out = np.empty(n, dtype=np.uint32)
+        self.ctx._check(lib().kb_rel_download(self.ctx.h, self.h, col, _ptr(out)))
+        return out
+
+    def device_ptr(self, col: int) -> int:
+        p = C.c_void_p()
+        self.ctx._check(lib().kb_rel_device_col(self.h, col, C.byref(p)))
+        return p.value or 0
+
+    def to_numpy(self, slot_order: Optional[Sequence[int]] = None) -> np.ndarray:
+        """rows x cols uint32 array, columns ordered by `slot_order` (default: the relation's own order)"""
+        n, slots = self.info()
+        order = list(slot_order) if slot_order is not None else slots
+        out = np.empty((n, len(order)), dtype=np.uint32)
+        for j, s in enumerate(order):
+            out[:, j] = self.column(slots.index(s))
+        return out
+
+    def free(self):
+        if self.h:
+            lib().kb_rel_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One device context = one GPU (multi-GPU = one process per GPU, see kolibrie_b200.dist)."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        rc = lib().kb_ctx_create(device, C.byref(h))
+        if rc != KB_OK:
+            raise KolibrieError(rc, (lib().kb_last_error(None) or b"").decode())
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().kb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != KB_OK:
+            raise KolibrieError(rc, (lib().kb_last_error(self.h) or b"").decode())
+
+    # ---- store
+    def store_load(self, s, p, o):
+        s, p, o = _u32(s), _u32(p), _u32(o)
+        self._check(lib().kb_store_load(self.h, _ptr(s), _ptr(p), _ptr(o), len(s)))
+
+    def store_load_device(self, d_s: int, d_p: int, d_o: int, n: int):
+        self._check(lib().kb_store_load_device(self.h, C.c_void_p(d_s), C.c_void_p(d_p), C.c_void_p(d_o), n))
+
+    def store_append(self, s, p, o, tag: int):
+        s, p, o = _u32(s), _u32(p), _u32(o)
+        self._check(lib().kb_store_append(self.h, _ptr(s), _ptr(p), _ptr(o), len(s), tag))
+
+    def store_evict(self, tag: int):
+        self._check(lib().kb_store_evict(self.h, tag))
+
+    def store_delete(self, s, p, o):
+        s, p, o = _u32(s), _u32(p), _u32(o)
+        self._check(lib().kb_store_delete(self.h, _ptr(s), _ptr(p), _ptr(o), len(s)))
+
+    def store_clear(self):
+        self._check(lib().kb_store_clear(self.h))
+
+    def store_size(self):
+        n, ns = C.c_uint64(), C.c_uint32()
+        self._check(lib().kb_store_size(self.h, C.byref(n), C.byref(ns)))
+        return n.value, ns.value
+
+    def store_download(self):
+        n, _ = self.store_size()
+        s, p, o = (np.empty(n, dtype=np.uint32) for _ in range(3))
+        got = C.c_uint64()
+        self._check(lib().kb_store_download(self.h, _ptr(s), _ptr(p), _ptr(o), n, C.byref(got)))
+        return s, p, o
+
+    def dict_numeric_load(self, num_or0, is_num):
+        num = np.ascontiguousarray(num_or0, dtype=np.float64)
+        isn = np.ascontiguousarray(is_num, dtype=np.uint8)
+        assert len(num) == len(isn)
+        self._check(lib().kb_dict_numeric_load(self.h, _ptr(num), _ptr(isn), len(num)))
+
+    # ---- operators
+    def scan(self, pats: Sequence[KbPattern], pushdown: Optional[Sequence[Optional[Sequence[KbFilterOp]]]] = None):
+        arr = patterns(pats)
+        k = len(pats)
+        out = (C.c_void_p * k)()
+        if pushdown:
+            progs, keep = (C.POINTER(KbFilterOp) * k)(), []
+            lens = (C.c_uint32 * k)()
+            for i in range(k):
+                a, n = filter_prog(pushdown[i] if i < len(pushdown) else None)
+                keep.append(a)
+                progs[i] = C.cast(a, C.POINTER(KbFilterOp))
+                lens[i] = n
+            self._check(lib().kb_scan(self.h, arr, k, progs, lens, out))
+        else:
+            self._check(lib().kb_scan(self.h, arr, k, None, None, out))
+        return [Relation(self, out[i]) for i in range(k)]
+
+    def filter(self, rel: Relation, ops: Sequence[KbFilterOp]) -> Relation:
+        a, n = filter_prog(ops)
+        out = C.c_void_p()
+        self._check(lib().kb_filter(self.h, rel.h, a, n, C.byref(out)))
+        return Relation(self, out)
+
+    def project(self, rel: Relation, slots: Sequence[int]) -> Relation:
+        a = (C.c_uint32 * max(len(slots), 1))(*slots)
+        out = C.c_void_p()
+        self._check(lib().kb_project(self.h, rel.h, a, len(slots), C.byref(out)))
+        return Relation(self, out)
+
+    def hash_join(self, left: Relation, right: Relation) -> Relation:
+        out = C.c_void_p()
+        self._check(lib().kb_hash_join(self.h, left.h, right.h, C.byref(out)))
+        return Relation(self, out)
+
+    def star_join(self, join_slot: int, pats: Sequence[KbPattern], filt: Optional[Sequence[KbFilterOp]] = None) -> Relation:
+        a, n = filter_prog(filt)
+        out = C.c_void_p()
+        self._check(lib().kb_star_join(self.h, join_slot, patterns(pats), len(pats), a, n, C.byref(out)))
+        return Relation(self, out)
+
+    def bgp_execute(self, pats: Sequence[KbPattern], filt: Optional[Sequence[KbFilterOp]] = None, project: Optional[Sequence[int]] = None) -> Relation:
+        a, n = filter_prog(filt)
+        out = C.c_void_p()
+        if project is not None:
+            pr = (C.c_uint32 * max(len(project), 1))(*project)
+            self._check(lib().kb_bgp_execute(self.h, patterns(pats), len(pats), a, n, pr, len(project), C.byref(out)))
+        else:
+            self._check(lib().kb_bgp_execute(self.h, patterns(pats), len(pats), a, n, None, 0, C.byref(out)))
+        return Relation(self, out)
+
+    def rel_from_host(self, slots: Sequence[int], cols: Sequence[np.ndarray]) -> Relation:
+        cols = [_u32(c) for c in cols]
+        n = len(cols[0]) if cols else 0
+        sl = (C.c_uint32 * max(len(slots), 1))(*slots)
+        ptrs = (C.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+        out = C.c_void_p()
+        self._check(lib().kb_rel_from_host(self.h, sl, len(slots), ptrs, n, C.byref(out)))
+        return Relation(self, out)
+
+    def rel_from_device(self, slots: Sequence[int], ptrs_: Sequence[int], n: int) -> Relation:
+        sl = (C.c_uint32 * max(len(slots), 1))(*slots)
+        ptrs = (C.c_void_p * max(len(ptrs_), 1))(*ptrs_)
+        out = C.c_void_p()
+        self._check(lib().kb_rel_from_device(self.h, sl, len(slots), ptrs, n, C.byref(out)))
+        return Relation(self, out)
+
+    def group_aggregate(self, rel: Relation, group_slots: Sequence[int], aggs: Sequence[tuple]):
+        """aggs: [(kind, slot)] -> dict(keys=[cols], values=[cols], counts=array)"""
+        gs = (C.c_uint32 * max(len(group_slots), 1))(*group_slots)
+        ag = (KbAgg * max(len(aggs), 1))()
+        for i, (k, s) in enumerate(aggs):
+            ag[i] = KbAgg(k, s)
+        g = C.c_void_p()
+        self._check(lib().kb_group_aggregate(self.h, rel.h, gs, len(group_slots), ag, len(aggs), C.byref(g)))
+        try:
+            n, ng, na = C.c_uint64(), C.c_uint32(), C.c_uint32()
+            self._check(lib().kb_groups_info(g, C.byref(n), C.byref(ng), C.byref(na)))
+            keys, vals = [], []
+            for c in range(ng.value):
+                p = C.POINTER(C.c_uint32)()
+                self._check(lib().kb_groups_keys(g, c, C.byref(p)))
+                keys.append(np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.empty(0, np.uint32))
+            for a in range(na.value):
+                p = C.POINTER(C.c_double)()
+                self._check(lib().kb_groups_values(g, a, C.byref(p)))
+                vals.append(np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.empty(0, np.float64))
+            pc = C.POINTER(C.c_uint64)()
+            self._check(lib().kb_groups_counts(g, C.byref(pc)))
+            counts = np.ctypeslib.as_array(pc, shape=(n.value,)).copy() if n.value else np.empty(0, np.uint64)
+            return {"keys": keys, "values": vals, "counts": counts}
+        finally:
+            lib().kb_groups_free(g)
+
+    def datalog_fixpoint(self, rules: Sequence[dict], strategy: int = SEMI_NAIVE):
+        """rules: [{'premise': [KbPattern], 'conclusion': [KbPattern], 'filters': [KbRuleFilter]}]"""
+        arr, keep = make_rules(rules)
+        out = C.c_void_p()
+        st = KbFixpointStats()
+        self._check(lib().kb_datalog_fixpoint(self.h, arr, len(rules), strategy, C.byref(out), C.byref(st)))
+        return Relation(self, out), st
+
+    def partition(self, rel: Relation, key_slot: int, n_parts: int):
+        out = C.c_void_p()
+        offs = (C.c_uint64 * (n_parts + 1))()
+        self._check(lib().kb_partition(self.h, rel.h, key_slot, n_parts, C.byref(out), offs))
+        return Relation(self, out), [offs[i] for i in range(n_parts + 1)]
+
+    def star_join_host(self, s, p, o, join_slot: int, pats: Sequence[KbPattern], filt=None):
+        """One-shot host-buffer call (kb_star_join_host): upload + star join + download; result columns are malloc'd by the
+        library and copied into numpy arrays here. Returns (rows x cols uint32 array, slots)."""
+        s, p, o = _u32(s), _u32(p), _u32(o)
+        a, nf = filter_prog(filt)
+        n_cols, n_rows = C.c_uint32(), C.c_uint64(0)
+        slots = (C.c_uint32 * KB_MAX_COLS)()
+        cols = (C.c_void_p * KB_MAX_COLS)()
+        self._check(lib().kb_star_join_host(self.h, _ptr(s), _ptr(p), _ptr(o), len(s), join_slot, patterns(pats), len(pats), a, nf,
+                                            C.byref(n_cols), slots, cols, C.byref(n_rows)))
+        libc = C.CDLL(None)
+        libc.free.argtypes = [C.c_void_p]
+        out = np.empty((n_rows.value, n_cols.value), dtype=np.uint32)
+        for c in range(n_cols.value):
+            if n_rows.value:
+                out[:, c] = np.ctypeslib.as_array(C.cast(cols[c], C.POINTER(C.c_uint32)), shape=(n_rows.value,))
+            libc.free(cols[c])
+        return out, [slots[i] for i in range(n_cols.value)]
+
+    # ---- stats
+    def set_timing(self, on: bool):
+        self._check(lib().kb_set_timing(self.h, 1 if on else 0))
+
+    def get_stats(self, reset: bool = False) -> dict:
+        st = KbStats()
+        self._check(lib().kb_get_stats(self.h, C.byref(st), 1 if reset else 0))
+        return st.as_dict()
+
+    def synchronize(self):
+        self._check(lib().kb_synchronize(self.h))
+
+
+def star_join_host_raw(ctx: Context, s_ptr: int, p_ptr: int, o_ptr: int, n: int, join_slot: int, pats, filt, out_ptrs: Sequence[int], out_cap: int):
+    """kb_star_join_host with raw host pointers (pinned torch / numpy memory). Returns (n_rows, slots)."""
+    a, nf = filter_prog(filt)
+    n_cols, n_rows = C.c_uint32(), C.c_uint64(out_cap)
+    slots = (C.c_uint32 * KB_MAX_COLS)()
+    cols = (C.c_void_p * KB_MAX_COLS)()
+    for i, ptr in enumerate(out_ptrs):
+        cols[i] = ptr
+    ctx._check(lib().kb_star_join_host(ctx.h, C.c_void_p(s_ptr), C.c_void_p(p_ptr), C.c_void_p(o_ptr), n, join_slot, patterns(pats), len(pats),
+                                       a, nf, C.byref(n_cols), slots, cols, C.byref(n_rows)))
+    return n_rows.value, [slots[i] for i in range(n_cols.value)]
+
+
+def make_rules(rules: Sequence[dict]):
+    arr = (KbRule * max(len(rules), 1))()
+    keep = []
+    for i, r in enumerate(rules):
+        prem = patterns(r["premise"])
+        conc = patterns(r["conclusion"])
+        fl = r.get("filters", [])
+        farr = (KbRuleFilter * max(len(fl), 1))()
+        for j, f in enumerate(fl):
+            farr[j] = f
+        keep += [prem, conc, farr]
+        arr[i] = KbRule(C.cast(prem, C.POINTER(KbPattern)), len(r["premise"]), C.cast(farr, C.POINTER(KbRuleFilter)), len(fl),
+                        C.cast(conc, C.POINTER(KbPattern)), len(r["conclusion"]))
+    arr._keep = keep  # keep the nested arrays alive as long as the rule array
+    return arr, keep
+
+
+def legacy_hash_join_cuda(subjects, predicates, objects, predicate_filter: int, literal_filter: Optional[int] = None, libpath: Optional[str] = None) -> np.ndarray:
+    """Replays exactly what Kolibrie's `hash_join_cuda` does (kolibrie/src/cuda/cuda_join.rs:28-60) against the legacy symbol."""
+    L = lib() if libpath is None else C.CDLL(libpath)
+    fn = L.perform_hash_join_cuda
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_uint32)]
+    s, p, o = _u32(subjects), _u32(predicates), _u32(objects)
+    lit = C.c_uint32(literal_filter) if literal_filter is not None else None
+    idx = C.POINTER(C.c_uint32)()
+    cnt = C.c_uint32(0)
+    fn(_ptr(s), _ptr(p), _ptr(o), len(s), predicate_filter, C.byref(lit) if lit is not None else None, C.byref(idx), C.byref(cnt))
+    out = np.ctypeslib.as_array(idx, shape=(cnt.value,)).copy() if cnt.value else np.empty(0, np.uint32)
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    if idx:
+        libc.free(C.cast(idx, C.c_void_p))  # the Rust side frees it through Vec's drop = libc free
+    return out

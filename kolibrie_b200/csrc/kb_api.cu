@@ -1,0 +1,1416 @@
+// kb_api.cu — C ABI of libkolibrie_b200.so: context, device triple store, relations and the operator entry points.
+// Host code only orchestrates: every data-touching step is one of the sm_100a kernels in kb_kernels.cu.
+#include <cstdarg>
+#include <cstdlib>
+#include <algorithm>
+#include <mutex>
+
+#include "kb_internal.hpp"
+
+using namespace kb;
+
+namespace kb {
+
+static std::string g_create_err;
+
+kb_status fail(kb_ctx* ctx, kb_status code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static inline size_t round256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+kb_status alloc_buf(kb_ctx* ctx, size_t bytes, Buf* out) {
+    auto b = std::make_shared<DevBuf>();
+    b->bytes = round256(bytes) + 256;  // every column can be over-read to the next 16-byte boundary by the TMA tile loads
+    b->st = ctx->st;
+    cudaError_t e = cudaMallocAsync(&b->p, b->bytes, ctx->st);
+    if (e != cudaSuccess) {
+        b->p = nullptr;
+        cudaGetLastError();
+        return fail(ctx, KB_E_OOM, "device allocation of %zu bytes failed: %s", b->bytes, cudaGetErrorString(e));
+    }
+    *out = b;
+    return KB_OK;
+}
+
+kb_status alloc_col(kb_ctx* ctx, u64 rows, Col* out) {
+    Buf b;
+    KB_TRY(alloc_buf(ctx, (size_t)rows * sizeof(u32), &b));
+    out->buf = b;
+    out->ptr = static_cast<u32*>(b->p);
+    return KB_OK;
+}
+
+kb_status begin_call(kb_ctx* ctx) {
+    ctx->err.clear();
+    ctx->ctrl_used = 0;
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl, 0, kb_ctx::CTRL_WORDS * sizeof(u32), ctx->st));
+    return KB_OK;
+}
+
+u32 ctrl_alloc(kb_ctx* ctx, u32 words) {
+    u32 off = ctx->ctrl_used;
+    ctx->ctrl_used += (words + 3u) & ~3u;
+    if (ctx->ctrl_used > kb_ctx::CTRL_WORDS) {  // wrap: callers never keep more than a few hundred words live per call
+        off = 0;
+        ctx->ctrl_used = (words + 3u) & ~3u;
+    }
+    return off;
+}
+
+kb_status ctrl_read(kb_ctx* ctx) {
+    const u32 words = kb_ctx::CTRL_WORDS;  // whole arena: allocations may have wrapped
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl, words * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->stats.d2h_bytes += words * sizeof(u32);
+    timers_flush(ctx);
+    return KB_OK;
+}
+
+kb_status ensure_tile_state(kb_ctx* ctx, u64 tiles) {
+    if (tiles <= ctx->tile_state_tiles) return KB_OK;
+    u64 want = std::max<u64>(tiles, 1024) * 2;
+    Buf b;
+    KB_TRY(alloc_buf(ctx, want * MAXP * sizeof(u64), &b));
+    KB_CUDA(ctx, cudaMemsetAsync(b->p, 0, want * MAXP * sizeof(u64), ctx->st));  // epoch 0 is never used by a launch
+    ctx->tile_state = b;
+    ctx->tile_state_tiles = want;
+    return KB_OK;
+}
+
+NumTab numtab(const kb_ctx* ctx) {
+    NumTab nt;
+    nt.num_or0 = ctx->num ? static_cast<const double*>(ctx->num->p) : nullptr;
+    nt.is_num = ctx->isnum ? static_cast<const u8*>(ctx->isnum->p) : nullptr;
+    nt.n_ids = ctx->n_ids;
+    return nt;
+}
+
+static cudaEvent_t get_event(kb_ctx* ctx) {
+    if (!ctx->ev_pool.empty()) {
+        cudaEvent_t e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void timer_begin(kb_ctx* ctx, int fam) {
+    switch (fam) {
+        case F_SCAN: ctx->stats.scan_launches++; break;
+        case F_BUILD: ctx->stats.build_launches++; break;
+        case F_PROBE: ctx->stats.probe_launches++; break;
+        case F_FILTER: ctx->stats.filter_launches++; break;
+        case F_GROUP: ctx->stats.group_launches++; break;
+        default: ctx->stats.other_launches++; break;
+    }
+    if (!ctx->timing) return;
+    PendingTimer t;
+    t.a = get_event(ctx);
+    t.b = get_event(ctx);
+    t.fam = fam;
+    cudaEventRecord(t.a, ctx->st);
+    ctx->timers.push_back(t);
+}
+void timer_end(kb_ctx* ctx) {
+    if (!ctx->timing || ctx->timers.empty()) return;
+    cudaEventRecord(ctx->timers.back().b, ctx->st);
+}
+void timers_flush(kb_ctx* ctx) {
+    for (auto& t : ctx->timers) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            switch (t.fam) {
+                case F_SCAN: ctx->stats.scan_ms += ms; break;
+                case F_BUILD: ctx->stats.build_ms += ms; break;
+                case F_PROBE: ctx->stats.probe_ms += ms; break;
+                case F_FILTER: ctx->stats.filter_ms += ms; break;
+                case F_GROUP: ctx->stats.group_ms += ms; break;
+                default: ctx->stats.other_ms += ms; break;
+            }
+            ctx->stats.total_ms += ms;
+        } else {
+            cudaGetLastError();
+        }
+        ctx->ev_pool.push_back(t.a);
+        ctx->ev_pool.push_back(t.b);
+    }
+    ctx->timers.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FILTER program helpers
+static int op_arity(u32 op) {
+    switch (op) {
+        case KB_F_CMP_NUM: case KB_F_EQ_ID: case KB_F_NE_ID: case KB_F_PUSH_VAR: case KB_F_PUSH_CONST: case KB_F_IS_TRIPLE: return 0;
+        case KB_F_NOT: case KB_F_TRUTHY: return 1;
+        case KB_F_AND: case KB_F_OR: case KB_F_ADD: case KB_F_SUB: case KB_F_MUL: case KB_F_DIV: return 2;
+        default: return -1;
+    }
+}
+static bool op_has_slot(u32 op) {
+    return op == KB_F_CMP_NUM || op == KB_F_EQ_ID || op == KB_F_NE_ID || op == KB_F_PUSH_VAR || op == KB_F_IS_TRIPLE;
+}
+
+kb_status validate_filter(kb_ctx* ctx, const kb_filter_op* ops, u32 n) {
+    if (n == 0) return KB_OK;
+    if (!ops) return fail(ctx, KB_E_INVALID, "filter program is NULL");
+    if (n > KB_MAX_FILTER_OPS) return fail(ctx, KB_E_LIMIT, "filter program longer than %d ops", KB_MAX_FILTER_OPS);
+    int depth = 0;
+    for (u32 i = 0; i < n; i++) {
+        int a = op_arity(ops[i].op);
+        if (a < 0) return fail(ctx, KB_E_INVALID, "filter op %u: unknown opcode %u", i, ops[i].op);
+        if (depth < a) return fail(ctx, KB_E_INVALID, "filter op %u: stack underflow", i);
+        depth += 1 - a;
+        if (depth > 10) return fail(ctx, KB_E_LIMIT, "filter expression too deep");
+    }
+    if (depth != 1) return fail(ctx, KB_E_INVALID, "filter program leaves %d values on the stack", depth);
+    return KB_OK;
+}
+
+static void split_rec(const kb_filter_op* ops, const std::vector<u32>& begin, u32 b, u32 e, std::vector<FilterProg>* out) {
+    if (ops[e - 1].op == KB_F_AND) {
+        const u32 right_b = begin[e - 2];
+        split_rec(ops, begin, b, right_b, out);
+        split_rec(ops, begin, right_b, e - 1, out);
+        return;
+    }
+    FilterProg f;
+    f.ops.assign(ops + b, ops + e);
+    out->push_back(std::move(f));
+}
+
+bool split_conjuncts(const kb_filter_op* ops, u32 n, std::vector<FilterProg>* out) {
+    out->clear();
+    if (n == 0) return true;
+    std::vector<u32> begin(n), stack;
+    for (u32 i = 0; i < n; i++) {
+        int a = op_arity(ops[i].op);
+        if (a < 0 || (int)stack.size() < a) return false;
+        u32 b = i;
+        for (int k = 0; k < a; k++) { b = stack.back(); stack.pop_back(); }
+        begin[i] = b;
+        stack.push_back(b);
+    }
+    if (stack.size() != 1) return false;
+    split_rec(ops, begin, 0, n, out);
+    return true;
+}
+
+std::set<u32> filter_slots(const FilterProg& f) {
+    std::set<u32> s;
+    for (auto& op : f.ops) if (op_has_slot(op.op)) s.insert(op.slot);
+    return s;
+}
+
+// append `f` (slots remapped through `remap`) to the device op array, AND-ing it with what is already there
+static bool append_prog(std::vector<FilterOp>* dst, const FilterProg& f, const std::map<u32, u32>& remap) {
+    const bool had = !dst->empty();
+    for (auto& op : f.ops) {
+        FilterOp d;
+        d.op = op.op; d.slot = op.slot; d.cmp = op.cmp; d.id = op.id; d.value = op.value;
+        if (op_has_slot(op.op)) {
+            auto it = remap.find(op.slot);
+            if (it == remap.end()) return false;
+            d.slot = it->second;
+        }
+        dst->push_back(d);
+    }
+    if (had) {
+        FilterOp a{};
+        a.op = KB_F_AND;
+        dst->push_back(a);
+    }
+    return true;
+}
+
+void pattern_vars(const kb_pattern& pt, std::vector<u32>* slots, std::vector<u32>* src) {
+    const kb_term* ts[3] = {&pt.s, &pt.p, &pt.o};
+    for (u32 i = 0; i < 3; i++) {
+        if (!ts[i]->is_var) continue;
+        if (std::find(slots->begin(), slots->end(), ts[i]->value) == slots->end()) {
+            slots->push_back(ts[i]->value);
+            src->push_back(i);
+        }
+    }
+}
+
+static kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt) {
+    const kb_term* ts[3] = {&pt.s, &pt.p, &pt.o};
+    for (auto* t : ts) {
+        if (t->is_var > 1) return fail(ctx, KB_E_INVALID, "kb_term.is_var must be 0 or 1");
+        if (!t->is_var && t->value == KB_ID_NONE) return fail(ctx, KB_E_INVALID, "constant id 0xFFFFFFFF is reserved (KB_ID_NONE)");
+        if (t->is_var && t->value >= 4096) return fail(ctx, KB_E_LIMIT, "variable slot %u too large (max 4095)", t->value);
+    }
+    return KB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// scan
+kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vector<FilterProg>& pushdown, const int* stat_slot, bool want_index,
+                    std::vector<std::unique_ptr<kb_rel>>* out, std::vector<u32>* kmin, std::vector<u32>* kmax) {
+    if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a fused scan takes 1..%d patterns (got %u)", MAXP, K);
+    const u64 N = ctx->n_triples;
+    if (N >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "store holds %llu triples; row positions are 32-bit", (unsigned long long)N);
+    ScanParams P{};
+    P.K = K;
+    P.nt = numtab(ctx);
+    std::vector<FilterOp> ops;
+    out->clear();
+    for (u32 k = 0; k < K; k++) {
+        KB_TRY(check_pattern(ctx, pats[k]));
+        const kb_pattern& pt = pats[k];
+        ScanPat& sp = P.pat[k];
+        sp.flags = 0;
+        if (!pt.s.is_var) { sp.flags |= SP_HAS_S; sp.cs = pt.s.value; }
+        if (!pt.p.is_var) { sp.flags |= SP_HAS_P; sp.cp = pt.p.value; }
+        if (!pt.o.is_var) { sp.flags |= SP_HAS_O; sp.co = pt.o.value; }
+        if (pt.s.is_var && pt.p.is_var && pt.s.value == pt.p.value) sp.flags |= SP_EQ_SP;
+        if (pt.s.is_var && pt.o.is_var && pt.s.value == pt.o.value) sp.flags |= SP_EQ_SO;
+        if (pt.p.is_var && pt.o.is_var && pt.p.value == pt.o.value) sp.flags |= SP_EQ_PO;
+        std::vector<u32> slots, src;
+        pattern_vars(pt, &slots, &src);
+        auto rel = std::make_unique<kb_rel>();
+        if (want_index) {
+            slots.assign(1, 0u);
+            src.assign(1, 3u);
+        }
+        rel->slots = slots;
+        sp.n_out = (u32)slots.size();
+        for (u32 c = 0; c < sp.n_out; c++) {
+            Col col;
+            KB_TRY(alloc_col(ctx, N, &col));
+            rel->cols.push_back(col);
+            sp.out[c] = col.ptr;
+            sp.out_src[c] = src[c];
+        }
+        sp.f_begin = (u32)ops.size();
+        sp.f_len = 0;
+        if (k < pushdown.size() && !pushdown[k].ops.empty()) {
+            std::map<u32, u32> remap;
+            std::vector<u32> vs, vsrc;
+            pattern_vars(pt, &vs, &vsrc);
+            for (size_t i = 0; i < vs.size(); i++) remap[vs[i]] = vsrc[i];
+            std::vector<FilterOp> local;
+            if (!append_prog(&local, pushdown[k], remap)) return fail(ctx, KB_E_INVALID, "pushed-down filter of pattern %u uses a variable the pattern does not bind", k);
+            if (ops.size() + local.size() > KB_MAX_FILTER_OPS) return fail(ctx, KB_E_LIMIT, "pushed-down filters exceed %d ops", KB_MAX_FILTER_OPS);
+            ops.insert(ops.end(), local.begin(), local.end());
+            sp.f_len = (u32)local.size();
+        }
+        sp.stat_src = 3;
+        if (stat_slot && stat_slot[k] >= 0) {
+            std::vector<u32> vs, vsrc;
+            pattern_vars(pt, &vs, &vsrc);
+            for (size_t i = 0; i < vs.size(); i++) if ((int)vs[i] == stat_slot[k]) sp.stat_src = vsrc[i];
+        }
+        out->push_back(std::move(rel));
+    }
+    for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
+
+    const u32 n_seg = (u32)ctx->segs.size();
+    const u32 off_tot = ctrl_alloc(ctx, MAXP), off_min = ctrl_alloc(ctx, MAXP), off_max = ctrl_alloc(ctx, MAXP);
+    const u32 off_ticket = ctrl_alloc(ctx, std::max(n_seg, 1u));
+    if (ctx->ctrl_used > kb_ctx::CTRL_WORDS - 64) return fail(ctx, KB_E_LIMIT, "too many store segments (%u)", n_seg);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_min, 0xFF, MAXP * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_tot, 0, MAXP * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_max, 0, MAXP * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_ticket, 0, std::max(n_seg, 1u) * sizeof(u32), ctx->st));
+    P.totals = ctx->ctrl + off_tot;
+    P.kmin = ctx->ctrl + off_min;
+    P.kmax = ctx->ctrl + off_max;
+    u64 max_tiles = 0;
+    for (auto& sg : ctx->segs) max_tiles = std::max<u64>(max_tiles, (sg.n + SCAN_TILE - 1) / SCAN_TILE);
+    KB_TRY(ensure_tile_state(ctx, max_tiles));
+    P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+    u64 index_base = 0;
+    for (u32 g = 0; g < n_seg; g++) {
+        const Segment& sg = ctx->segs[g];
+        if (sg.n == 0) continue;
+        P.s = sg.s.ptr; P.p = sg.p.ptr; P.o = sg.o.ptr;
+        P.n = (u32)sg.n;
+        P.n_tiles = (u32)((sg.n + SCAN_TILE - 1) / SCAN_TILE);
+        P.index_base = (u32)index_base;
+        P.ticket = ctx->ctrl + off_ticket + g;
+        P.epoch = ctx->epoch++;
+        if (ctx->epoch >= (1ull << 30)) ctx->epoch = 1;
+        if (sg.ready) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st, sg.ready, 0));  // chunked upload: start as soon as this chunk landed
+        timer_begin(ctx, F_SCAN);
+        launch_scan(P, ctx->n_sms, ctx->st);
+        timer_end(ctx);
+        index_base += sg.n;
+    }
+    KB_CUDA(ctx, cudaGetLastError());
+    ctx->stats.rows_scanned += N;
+    KB_TRY(ctrl_read(ctx));
+    if (kmin) kmin->assign(K, 0);
+    if (kmax) kmax->assign(K, 0);
+    for (u32 k = 0; k < K; k++) {
+        (*out)[k]->n = ctx->h_ctrl[off_tot + k];
+        if (kmin) (*kmin)[k] = ctx->h_ctrl[off_min + k];
+        if (kmax) (*kmax)[k] = ctx->h_ctrl[off_max + k];
+    }
+    return KB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// filter (= probe kernel with zero tables)
+kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out) {
+    auto rel = std::make_unique<kb_rel>();
+    rel->slots = in.slots;
+    if (in.n == 0 || f.ops.empty()) {
+        rel->cols = in.cols;
+        rel->n = in.n;
+        *out = std::move(rel);
+        return KB_OK;
+    }
+    if (in.n >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "relation too large");
+    ProbeDParams P{};
+    P.n_pcols = (u32)in.cols.size();
+    if (P.n_pcols == 0) return fail(ctx, KB_E_UNSUPPORTED, "filter on a relation without columns");
+    P.key_col = 0;
+    P.n = (u32)in.n;
+    P.n_tiles = (u32)((in.n + PROBE_TILE - 1) / PROBE_TILE);
+    P.T = 0;
+    P.n_out = P.n_pcols;
+    std::map<u32, u32> remap;
+    for (u32 c = 0; c < P.n_pcols; c++) {
+        P.pcol[c] = in.cols[c].ptr;
+        P.oc[c] = OutCol{OUT_PROBE, c, 0};
+        Col col;
+        KB_TRY(alloc_col(ctx, in.n, &col));
+        rel->cols.push_back(col);
+        P.out[c] = col.ptr;
+        remap[in.slots[c]] = c;
+    }
+    std::vector<FilterOp> ops;
+    if (!append_prog(&ops, f, remap)) return fail(ctx, KB_E_INVALID, "filter uses a variable that is not a column of the relation");
+    P.n_ops = (u32)ops.size();
+    for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
+    P.cap = (u32)in.n;
+    P.nt = numtab(ctx);
+    KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+    P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+    const u32 off = ctrl_alloc(ctx, 4);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+    P.ticket = ctx->ctrl + off;
+    P.total = ctx->ctrl + off + 1;
+    P.epoch = ctx->epoch++;
+    P.abort_flag = nullptr;
+    timer_begin(ctx, F_FILTER);
+    launch_probe_direct(P, ctx->n_sms, ctx->st);
+    timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    KB_TRY(ctrl_read(ctx));
+    rel->n = ctx->h_ctrl[off + 1];
+    *out = std::move(rel);
+    return KB_OK;
+}
+
+static u32 pow2_at_least(u64 x) {
+    u64 p = 1024;
+    while (p < x) p <<= 1;
+    return (u32)std::min<u64>(p, 1ull << 31);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// general natural join (chained multimap)
+kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const FilterProg* post, std::unique_ptr<kb_rel>* out) {
+    auto rel = std::make_unique<kb_rel>();
+    rel->slots = L.slots;
+    std::vector<u32> common;
+    for (u32 s : R.slots) {
+        if (L.col_of(s) >= 0) common.push_back(s);
+        else rel->slots.push_back(s);
+    }
+    if (rel->slots.size() > KB_MAX_COLS) return fail(ctx, KB_E_LIMIT, "join result has more than %d columns", KB_MAX_COLS);
+    if (L.n == 0 || R.n == 0) {  // engine.rs:714-716
+        rel->n = 0;
+        for (size_t c = 0; c < rel->slots.size(); c++) { Col col; KB_TRY(alloc_col(ctx, 0, &col)); rel->cols.push_back(col); }
+        *out = std::move(rel);
+        return KB_OK;
+    }
+    if (L.n >= 0xFFFFFFF0ull || R.n >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "relation too large");
+    if (common.empty()) {  // cartesian product (engine.rs:1054-1071)
+        const u64 total = L.n * R.n;
+        if (total > (1ull << 28)) return fail(ctx, KB_E_LIMIT, "cartesian product of %llu x %llu rows exceeds 2^28", (unsigned long long)L.n, (unsigned long long)R.n);
+        std::vector<const u32*> lc, rc;
+        std::vector<u32*> oc;
+        for (auto& c : L.cols) lc.push_back(c.ptr);
+        for (auto& c : R.cols) rc.push_back(c.ptr);
+        for (size_t c = 0; c < rel->slots.size(); c++) { Col col; KB_TRY(alloc_col(ctx, total, &col)); rel->cols.push_back(col); oc.push_back(col.ptr); }
+        timer_begin(ctx, F_PROBE);
+        launch_cartesian(lc.data(), (u32)L.n, (u32)lc.size(), rc.data(), (u32)R.n, (u32)rc.size(), oc.data(), ctx->st);
+        timer_end(ctx);
+        KB_CUDA(ctx, cudaGetLastError());
+        rel->n = total;
+        if (post && !post->ops.empty()) {
+            std::unique_ptr<kb_rel> f;
+            KB_TRY(filter_impl(ctx, *rel, *post, &f));
+            rel = std::move(f);
+        }
+        *out = std::move(rel);
+        return KB_OK;
+    }
+    if (common.size() > 4) return fail(ctx, KB_E_LIMIT, "join on more than 4 common variables");
+    const bool build_left = L.n <= R.n;  // engine.rs:729-733: build on the smaller side
+    const kb_rel& B = build_left ? L : R;
+    const kb_rel& Pr = build_left ? R : L;
+
+    ChainTab T{};
+    T.n_slots = pow2_at_least(B.n * 2);
+    T.n_keys = (u32)common.size();
+    Buf slots_buf, next_buf;
+    KB_TRY(alloc_buf(ctx, (size_t)T.n_slots * sizeof(u64), &slots_buf));
+    KB_TRY(alloc_buf(ctx, (size_t)B.n * sizeof(u32), &next_buf));
+    T.slots = static_cast<u64*>(slots_buf->p);
+    T.next = static_cast<u32*>(next_buf->p);
+    for (u32 q = 0; q < T.n_keys; q++) T.bkey[q] = B.cols[B.col_of(common[q])].ptr;
+    timer_begin(ctx, F_BUILD);
+    KB_CUDA(ctx, cudaMemsetAsync(T.slots, 0xFF, (size_t)T.n_slots * sizeof(u64), ctx->st));
+    launch_build_chained(T, (u32)B.n, ctx->n_sms, ctx->st);
+    timer_end(ctx);
+    ctx->stats.rows_built += B.n;
+
+    ProbeCParams P{};
+    P.tab = T;
+    P.n_pcols = (u32)Pr.cols.size();
+    P.n = (u32)Pr.n;
+    P.n_tiles = (u32)((Pr.n + PROBEC_TILE - 1) / PROBEC_TILE);
+    for (u32 c = 0; c < P.n_pcols; c++) P.pcol[c] = Pr.cols[c].ptr;
+    for (u32 q = 0; q < T.n_keys; q++) P.pkey[q] = (u32)Pr.col_of(common[q]);
+    std::vector<u32> kernel_slots = Pr.slots;  // kernel output order: probe columns, then build payload columns
+    P.n_bpay = 0;
+    for (size_t c = 0; c < B.slots.size(); c++) {
+        if (std::find(common.begin(), common.end(), B.slots[c]) != common.end()) continue;
+        P.bpay[P.n_bpay++] = B.cols[c].ptr;
+        kernel_slots.push_back(B.slots[c]);
+    }
+    P.n_out = (u32)kernel_slots.size();
+    if (post && !post->ops.empty()) {
+        std::map<u32, u32> remap;
+        for (u32 c = 0; c < P.n_out; c++) remap[kernel_slots[c]] = c;
+        std::vector<FilterOp> ops;
+        if (!append_prog(&ops, *post, remap)) return fail(ctx, KB_E_INVALID, "join filter uses a variable that neither side binds");
+        P.n_ops = (u32)ops.size();
+        for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
+    }
+    P.nt = numtab(ctx);
+    KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+    P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+    const u32 off = ctrl_alloc(ctx, 4);
+    P.total = ctx->ctrl + off + 1;
+    u64 cap = std::max(Pr.n, B.n);
+    ctx->stats.rows_probed += Pr.n;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        rel->cols.clear();
+        rel->cols.resize(rel->slots.size());
+        for (u32 c = 0; c < P.n_out; c++) {
+            Col col;
+            KB_TRY(alloc_col(ctx, cap, &col));
+            rel->cols[rel->col_of(kernel_slots[c])] = col;
+            P.out[c] = col.ptr;
+        }
+        P.cap = (u32)std::min<u64>(cap, 0xFFFFFFF0ull);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+        P.ticket = ctx->ctrl + off;
+        P.epoch = ctx->epoch++;
+        timer_begin(ctx, F_PROBE);
+        launch_probe_chained(P, ctx->n_sms, ctx->st);
+        timer_end(ctx);
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(ctrl_read(ctx));
+        const u64 total = ctx->h_ctrl[off + 1];
+        rel->n = total;
+        if (total <= cap) break;
+        if (attempt == 1) return fail(ctx, KB_E_LIMIT, "join output did not fit after resizing");
+        cap = total;  // the first pass doubled as the exact count
+    }
+    *out = std::move(rel);
+    return KB_OK;
+}
+
+// reorder / select columns (zero-copy)
+static std::unique_ptr<kb_rel> select_cols(const kb_rel& in, const std::vector<u32>& slots) {
+    auto r = std::make_unique<kb_rel>();
+    r->n = in.n;
+    for (u32 s : slots) {
+        int c = in.col_of(s);
+        if (c < 0) continue;
+        r->slots.push_back(s);
+        r->cols.push_back(in.cols[c]);
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// star join: fused scan -> direct builds -> fused multiway probe; falls back to chained binary joins on 1:N keys
+kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 K, const kb_filter_op* filter, u32 n_ops,
+                         std::unique_ptr<kb_rel>* out) {
+    if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a star join takes 1..%d patterns (got %u)", MAXP, K);
+    KB_TRY(validate_filter(ctx, filter, n_ops));
+    std::vector<std::vector<u32>> pv(K), psrc(K);
+    std::vector<u32> all_slots;
+    for (u32 k = 0; k < K; k++) {
+        KB_TRY(check_pattern(ctx, pats[k]));
+        pattern_vars(pats[k], &pv[k], &psrc[k]);
+        if (std::find(pv[k].begin(), pv[k].end(), join_slot) == pv[k].end())
+            return fail(ctx, KB_E_INVALID, "star join: pattern %u does not contain the join variable (slot %u)", k, join_slot);
+        for (u32 s : pv[k]) if (std::find(all_slots.begin(), all_slots.end(), s) == all_slots.end()) all_slots.push_back(s);
+    }
+    if (all_slots.size() > KB_MAX_COLS) return fail(ctx, KB_E_LIMIT, "more than %d variables", KB_MAX_COLS);
+    // FILTER: conjuncts over one pattern's variables are evaluated while scanning that pattern
+    std::vector<FilterProg> conj, pushdown(K);
+    FilterProg post;
+    if (!split_conjuncts(filter, n_ops, &conj)) return fail(ctx, KB_E_INVALID, "malformed filter program");
+    for (auto& c : conj) {
+        std::set<u32> fs = filter_slots(c);
+        for (u32 s : fs) if (std::find(all_slots.begin(), all_slots.end(), s) == all_slots.end())
+            return fail(ctx, KB_E_UNSUPPORTED, "filter references slot %u which no pattern binds (the reference evaluates it to false, types.rs:149-151)", s);
+        int target = -1;
+        for (u32 k = 0; k < K && target < 0; k++) {
+            bool all = true;
+            for (u32 s : fs) if (std::find(pv[k].begin(), pv[k].end(), s) == pv[k].end()) all = false;
+            if (all) target = (int)k;
+        }
+        FilterProg* dst = target >= 0 ? &pushdown[target] : &post;
+        const bool had = !dst->ops.empty();
+        dst->ops.insert(dst->ops.end(), c.ops.begin(), c.ops.end());
+        if (had) { kb_filter_op a{}; a.op = KB_F_AND; dst->ops.push_back(a); }
+    }
+    std::vector<int> stat(K, (int)join_slot);
+    std::vector<std::unique_ptr<kb_rel>> rels;
+    std::vector<u32> kmin, kmax;
+    KB_TRY(scan_impl(ctx, pats, K, pushdown, stat.data(), false, &rels, &kmin, &kmax));
+
+    auto empty_result = [&]() -> kb_status {
+        auto r = std::make_unique<kb_rel>();
+        r->slots = all_slots;
+        for (size_t c = 0; c < all_slots.size(); c++) { Col col; KB_TRY(alloc_col(ctx, 0, &col)); r->cols.push_back(col); }
+        *out = std::move(r);
+        return KB_OK;
+    };
+    for (u32 k = 0; k < K; k++) if (rels[k]->n == 0) return empty_result();
+
+    if (K == 1) {
+        std::unique_ptr<kb_rel> r = std::move(rels[0]);
+        if (!post.ops.empty()) { std::unique_ptr<kb_rel> f; KB_TRY(filter_impl(ctx, *r, post, &f)); r = std::move(f); }
+        *out = std::move(r);
+        return KB_OK;
+    }
+    // probe side = largest relation (ties: first)
+    u32 probe = 0;
+    for (u32 k = 1; k < K; k++) if (rels[k]->n > rels[probe]->n) probe = k;
+    std::vector<u32> builds;
+    for (u32 k = 0; k < K; k++) if (k != probe) builds.push_back(k);
+
+    // the fused path needs: patterns share only the join variable (quirk Q3: the reference never checks the others — we must,
+    // so such shapes take the natural-join chain), dense key ranges, and single-valued keys
+    bool fused_ok = true;
+    for (u32 a = 0; a < K && fused_ok; a++)
+        for (u32 b = a + 1; b < K && fused_ok; b++)
+            for (u32 s : pv[a]) if (s != join_slot && std::find(pv[b].begin(), pv[b].end(), s) != pv[b].end()) fused_ok = false;
+    auto key_pos = [&](u32 k) { for (size_t i = 0; i < pv[k].size(); i++) if (pv[k][i] == join_slot) return psrc[k][i]; return 0u; };
+    for (u32 k : builds) {
+        const u64 range = (u64)kmax[k] - kmin[k] + 1;
+        if (range > std::max<u64>(8 * rels[k]->n, 1ull << 16) || range > (1ull << 31)) fused_ok = false;
+        if (!pats[k].p.is_var && ctx->multi_valued.count({pats[k].p.value, key_pos(k)})) fused_ok = false;
+        if (pv[k].size() > 3) fused_ok = false;
+    }
+
+    if (fused_ok) {
+        std::unique_ptr<kb_rel> cur = std::move(rels[probe]);
+        bool dup_seen = false;
+        size_t done = 0;
+        while (done < builds.size() && !dup_seen) {
+            const size_t nb = std::min<size_t>(MAXT, builds.size() - done);
+            const bool last = done + nb == builds.size();
+            ProbeDParams P{};
+            P.n_pcols = (u32)cur->cols.size();
+            for (u32 c = 0; c < P.n_pcols; c++) P.pcol[c] = cur->cols[c].ptr;
+            P.key_col = (u32)cur->col_of(join_slot);
+            P.n = (u32)cur->n;
+            P.n_tiles = (u32)((cur->n + PROBE_TILE - 1) / PROBE_TILE);
+            P.T = (u32)nb;
+            const u32 off = ctrl_alloc(ctx, 8 + MAXT);
+            KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, (8 + MAXT) * sizeof(u32), ctx->st));
+            std::vector<Buf> tables(nb);
+            std::vector<u32> out_slots = cur->slots;
+            std::vector<OutCol> ocs;
+            for (u32 c = 0; c < P.n_pcols; c++) ocs.push_back(OutCol{OUT_PROBE, c, 0});
+            timer_begin(ctx, F_BUILD);
+            for (size_t t = 0; t < nb; t++) {
+                const u32 k = builds[done + t];
+                const kb_rel& B = *rels[k];
+                const u32 range = kmax[k] - kmin[k] + 1;
+                KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &tables[t]));
+                u32* tab = static_cast<u32*>(tables[t]->p);
+                KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), ctx->st));
+                const int kc = B.col_of(join_slot);
+                DirectTab& D = P.tab[t];
+                D.tab = tab; D.kmin = kmin[k]; D.range = range;
+                const u32* vals = nullptr;
+                if (B.cols.size() == 1) { D.mode = 2; D.n_pay = 0; }
+                else if (B.cols.size() == 2) {
+                    D.mode = 0; D.n_pay = 0;
+                    const int vc = kc == 0 ? 1 : 0;
+                    vals = B.cols[vc].ptr;
+                    out_slots.push_back(B.slots[vc]);
+                    ocs.push_back(OutCol{OUT_TABVAL, (u32)t, 0});
+                } else {
+                    D.mode = 1; D.n_pay = 0;
+                    for (size_t c = 0; c < B.cols.size(); c++) if ((int)c != kc) {
+                        D.pay[D.n_pay] = B.cols[c].ptr;
+                        out_slots.push_back(B.slots[c]);
+                        ocs.push_back(OutCol{OUT_TABPAY, (u32)t, D.n_pay});
+                        D.n_pay++;
+                    }
+                }
+                launch_build_direct(B.cols[kc].ptr, vals, (u32)B.n, tab, D.kmin, D.range, ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, ctx->st);
+                ctx->stats.rows_built += B.n;
+            }
+            timer_end(ctx);
+            auto res = std::make_unique<kb_rel>();
+            res->slots = out_slots;
+            P.n_out = (u32)out_slots.size();
+            for (u32 c = 0; c < P.n_out; c++) {
+                P.oc[c] = ocs[c];
+                Col col;
+                KB_TRY(alloc_col(ctx, cur->n, &col));
+                res->cols.push_back(col);
+                P.out[c] = col.ptr;
+            }
+            P.cap = (u32)cur->n;
+            P.n_ops = 0;
+            if (last && !post.ops.empty()) {
+                std::map<u32, u32> remap;
+                for (u32 c = 0; c < P.n_out; c++) remap[out_slots[c]] = c;
+                std::vector<FilterOp> ops;
+                if (!append_prog(&ops, post, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
+                P.n_ops = (u32)ops.size();
+                for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
+            }
+            P.nt = numtab(ctx);
+            KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+            P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+            P.ticket = ctx->ctrl + off;
+            P.total = ctx->ctrl + off + 1;
+            P.abort_flag = ctx->ctrl + off + 8;  // MAXT consecutive duplicate flags
+            P.epoch = ctx->epoch++;
+            timer_begin(ctx, F_PROBE);
+            launch_probe_direct(P, ctx->n_sms, ctx->st);
+            timer_end(ctx);
+            KB_CUDA(ctx, cudaGetLastError());
+            ctx->stats.rows_probed += cur->n;
+            KB_TRY(ctrl_read(ctx));
+            for (size_t t = 0; t < nb; t++) if (ctx->h_ctrl[off + 8 + t]) {
+                dup_seen = true;
+                const u32 k = builds[done + t];
+                if (!pats[k].p.is_var) ctx->multi_valued.insert({pats[k].p.value, key_pos(k)});
+            }
+            if (dup_seen) {
+                // `cur` may already hold the result of an earlier batch; restart the chain from the scan outputs that remain
+                // joinable: earlier batches consumed builds[0..done) — keep cur and join the rest with the general operator
+                break;
+            }
+            res->n = ctx->h_ctrl[off + 1];
+            cur = std::move(res);
+            done += nb;
+            if (cur->n == 0) return empty_result();
+        }
+        if (!dup_seen) {
+            *out = select_cols(*cur, all_slots);
+            return KB_OK;
+        }
+        // fall through: join the remaining build relations with the chained operator
+        std::vector<u32> rest(builds.begin() + done, builds.end());
+        std::sort(rest.begin(), rest.end(), [&](u32 a, u32 b) { return rels[a]->n < rels[b]->n; });
+        for (size_t i = 0; i < rest.size(); i++) {
+            std::unique_ptr<kb_rel> j;
+            KB_TRY(hash_join_impl(ctx, *cur, *rels[rest[i]], (i + 1 == rest.size() && !post.ops.empty()) ? &post : nullptr, &j));
+            cur = std::move(j);
+        }
+        *out = select_cols(*cur, all_slots);
+        return KB_OK;
+    }
+    // general chain: natural joins, smallest build sides first
+    std::unique_ptr<kb_rel> cur = std::move(rels[probe]);
+    std::sort(builds.begin(), builds.end(), [&](u32 a, u32 b) { return rels[a]->n < rels[b]->n; });
+    for (size_t i = 0; i < builds.size(); i++) {
+        std::unique_ptr<kb_rel> j;
+        KB_TRY(hash_join_impl(ctx, *cur, *rels[builds[i]], (i + 1 == builds.size() && !post.ops.empty()) ? &post : nullptr, &j));
+        cur = std::move(j);
+    }
+    *out = select_cols(*cur, all_slots);
+    return KB_OK;
+}
+
+}  // namespace kb
+
+// =================================================================================================================
+// C ABI
+#define KB_ENTER(ctx)                                         \
+    if (!(ctx)) return KB_E_INVALID;                          \
+    kb::DeviceGuard _guard((ctx)->device);                    \
+    KB_TRY(kb::begin_call(ctx))
+
+extern "C" {
+
+const char* kb_version(void) { return "kolibrie_b200 0.1.0 (sm_100a)"; }
+
+kb_status kb_ctx_create(int device, kb_ctx** out) {
+    if (!out) return KB_E_INVALID;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return kb::fail(nullptr, KB_E_CUDA, "no CUDA device available (%s): this library has no CPU fallback", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n_dev) return kb::fail(nullptr, KB_E_INVALID, "device %d out of range (0..%d)", device, n_dev - 1);
+    kb::DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return kb::fail(nullptr, KB_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10) return kb::fail(nullptr, KB_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    kb_ctx* ctx = new kb_ctx;
+    ctx->device = device;
+    ctx->n_sms = prop.multiProcessorCount;
+    auto bail = [&](const char* what, cudaError_t err) {
+        kb::fail(nullptr, KB_E_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        delete ctx;
+        return KB_E_CUDA;
+    };
+    if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;  // keep freed blocks cached: steady-state queries never hit cudaMalloc
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    if ((e = cudaMalloc(&ctx->ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMalloc(ctrl)", e);
+    if ((e = cudaMallocHost(&ctx->h_ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMallocHost(ctrl)", e);
+    *out = ctx;
+    return KB_OK;
+}
+
+void kb_ctx_destroy(kb_ctx* ctx) {
+    if (!ctx) return;
+    kb::DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    cudaStreamSynchronize(ctx->st_copy);
+    kb::timers_flush(ctx);
+    ctx->segs.clear();
+    ctx->num.reset();
+    ctx->isnum.reset();
+    ctx->tile_state.reset();
+    cudaStreamSynchronize(ctx->st);
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    if (ctx->ctrl) cudaFree(ctx->ctrl);
+    if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev_copy);
+    cudaStreamDestroy(ctx->st);
+    cudaStreamDestroy(ctx->st_copy);
+    delete ctx;
+}
+
+const char* kb_last_error(const kb_ctx* ctx) { return ctx ? ctx->err.c_str() : kb::g_create_err.c_str(); }
+
+kb_status kb_set_timing(kb_ctx* ctx, int enabled) {
+    if (!ctx) return KB_E_INVALID;
+    ctx->timing = enabled != 0;
+    return KB_OK;
+}
+kb_status kb_get_stats(kb_ctx* ctx, kb_stats* out, int reset) {
+    if (!ctx || !out) return KB_E_INVALID;
+    kb::DeviceGuard guard(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    kb::timers_flush(ctx);
+    *out = ctx->stats;
+    if (reset) ctx->stats = kb_stats{};
+    return KB_OK;
+}
+kb_status kb_synchronize(kb_ctx* ctx) {
+    if (!ctx) return KB_E_INVALID;
+    kb::DeviceGuard guard(ctx->device);
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st_copy));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    kb::timers_flush(ctx);
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------ store
+static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, const u32* o, u64 n, u64 tag, cudaMemcpyKind kind) {
+    if (n && (!s || !p || !o)) return kb::fail(ctx, KB_E_INVALID, "NULL column pointer");
+    if (ctx->n_triples + n >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "store would exceed 2^32-16 triples");
+    kb::Segment sg;
+    sg.tag = tag;
+    sg.n = n;
+    KB_TRY(kb::alloc_col(ctx, n, &sg.s));
+    KB_TRY(kb::alloc_col(ctx, n, &sg.p));
+    KB_TRY(kb::alloc_col(ctx, n, &sg.o));
+    if (n) {
+        KB_CUDA(ctx, cudaMemcpyAsync(sg.s.ptr, s, n * sizeof(u32), kind, ctx->st));
+        KB_CUDA(ctx, cudaMemcpyAsync(sg.p.ptr, p, n * sizeof(u32), kind, ctx->st));
+        KB_CUDA(ctx, cudaMemcpyAsync(sg.o.ptr, o, n * sizeof(u32), kind, ctx->st));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));  // the caller's buffers are borrowed for this call only
+        if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += 3 * n * sizeof(u32);
+    }
+    ctx->segs.push_back(sg);
+    ctx->n_triples += n;
+    ctx->store_version++;
+    ctx->multi_valued.clear();
+    return KB_OK;
+}
+
+kb_status kb_store_clear(kb_ctx* ctx) {
+    KB_ENTER(ctx);
+    ctx->segs.clear();
+    ctx->n_triples = 0;
+    ctx->store_version++;
+    ctx->multi_valued.clear();
+    return KB_OK;
+}
+kb_status kb_store_load(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n) {
+    KB_ENTER(ctx);
+    ctx->segs.clear();
+    ctx->n_triples = 0;
+    return store_add_segment(ctx, s, p, o, n, 0, cudaMemcpyHostToDevice);
+}
+kb_status kb_store_load_device(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n) {
+    KB_ENTER(ctx);
+    ctx->segs.clear();
+    ctx->n_triples = 0;
+    return store_add_segment(ctx, s, p, o, n, 0, cudaMemcpyDeviceToDevice);
+}
+kb_status kb_store_append(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint64_t tag) {
+    KB_ENTER(ctx);
+    return store_add_segment(ctx, s, p, o, n, tag, cudaMemcpyHostToDevice);
+}
+kb_status kb_store_evict(kb_ctx* ctx, uint64_t tag) {
+    KB_ENTER(ctx);
+    bool found = false;
+    for (size_t i = 0; i < ctx->segs.size();) {
+        if (ctx->segs[i].tag == tag) {
+            ctx->n_triples -= ctx->segs[i].n;
+            ctx->segs.erase(ctx->segs.begin() + i);
+            found = true;
+        } else i++;
+    }
+    ctx->store_version++;
+    ctx->multi_valued.clear();
+    return found ? KB_OK : kb::fail(ctx, KB_E_NOT_FOUND, "no segment with tag %llu", (unsigned long long)tag);
+}
+kb_status kb_store_size(kb_ctx* ctx, uint64_t* n, uint32_t* n_seg) {
+    if (!ctx) return KB_E_INVALID;
+    if (n) *n = ctx->n_triples;
+    if (n_seg) *n_seg = (uint32_t)ctx->segs.size();
+    return KB_OK;
+}
+
+kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n) {
+    KB_ENTER(ctx);
+    if (n == 0 || ctx->n_triples == 0) return KB_OK;
+    if (!s || !p || !o) return kb::fail(ctx, KB_E_INVALID, "NULL column pointer");
+    // 1. the delete set (96-bit keys), 2. mark matching triples by overwriting a copy of the predicate column with KB_ID_NONE,
+    // 3. rescan every segment with (?s ?p ?o) — a row whose predicate is KB_ID_NONE can never equal a real constant, and the
+    //    pattern's pushed-down filter NE_ID drops it.
+    const u32 set_slots = kb::pow2_at_least(n * 2);
+    kb::Buf set, ds, dp, dob;
+    KB_TRY(kb::alloc_buf(ctx, (size_t)set_slots * sizeof(uint4), &set));
+    KB_TRY(kb::alloc_buf(ctx, n * sizeof(u32), &ds));
+    KB_TRY(kb::alloc_buf(ctx, n * sizeof(u32), &dp));
+    KB_TRY(kb::alloc_buf(ctx, n * sizeof(u32), &dob));
+    KB_CUDA(ctx, cudaMemsetAsync(set->p, 0, (size_t)set_slots * sizeof(uint4), ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(ds->p, s, n * sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dp->p, p, n * sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(dob->p, o, n * sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
+    const u32 off = kb::ctrl_alloc(ctx, 4);
+    kb::launch_set_insert(static_cast<uint4*>(set->p), set_slots, (const u32*)ds->p, (const u32*)dp->p, 0u, (const u32*)dob->p, (u32)n,
+                          ctx->ctrl + off, ctx->n_sms, ctx->st);
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    std::vector<kb::Segment> old;
+    old.swap(ctx->segs);
+    ctx->n_triples = 0;
+    kb_status rc = KB_OK;
+    for (auto& sg : old) {
+        kb::Segment marked = sg;
+        if (sg.n) {
+            KB_TRY(kb::alloc_col(ctx, sg.n, &marked.p));
+            kb::launch_delete_mark(sg.s.ptr, sg.p.ptr, sg.o.ptr, (u32)sg.n, static_cast<const uint4*>(set->p), set_slots, marked.p.ptr,
+                                   ctx->n_sms, ctx->st);
+        }
+        // rescan this one segment
+        std::vector<kb::Segment> one{marked};
+        ctx->segs.swap(one);
+        const kb::u64 saved = ctx->n_triples;
+        ctx->n_triples = sg.n;
+        kb_pattern pt{{1, 0}, {1, 1}, {1, 2}};
+        kb::FilterProg keep;
+        kb_filter_op tr{};
+        tr.op = KB_F_IS_TRIPLE; tr.slot = 1;  // marked predicates (0xFFFFFFFF) have bit 31 set; real predicate ids never do
+        kb_filter_op nt{};
+        nt.op = KB_F_NOT;
+        keep.ops.push_back(tr);
+        keep.ops.push_back(nt);
+        std::vector<kb::FilterProg> pd{keep};
+        std::vector<std::unique_ptr<kb_rel>> rels;
+        rc = kb::scan_impl(ctx, &pt, 1, pd, nullptr, false, &rels, nullptr, nullptr);
+        ctx->segs.swap(one);
+        ctx->n_triples = saved;
+        if (rc != KB_OK) break;
+        kb::Segment ns;
+        ns.tag = sg.tag;
+        ns.n = rels[0]->n;
+        ns.s = rels[0]->cols[0]; ns.p = rels[0]->cols[1]; ns.o = rels[0]->cols[2];
+        ctx->segs.push_back(ns);
+        ctx->n_triples += ns.n;
+    }
+    if (rc != KB_OK) { ctx->segs.swap(old); ctx->n_triples = 0; for (auto& g : ctx->segs) ctx->n_triples += g.n; return rc; }
+    ctx->store_version++;
+    ctx->multi_valued.clear();
+    return KB_OK;
+}
+
+kb_status kb_store_download(kb_ctx* ctx, uint32_t* s, uint32_t* p, uint32_t* o, uint64_t cap, uint64_t* n) {
+    KB_ENTER(ctx);
+    if (n) *n = ctx->n_triples;
+    if (cap < ctx->n_triples) return kb::fail(ctx, KB_E_LIMIT, "buffer holds %llu triples, store has %llu", (unsigned long long)cap, (unsigned long long)ctx->n_triples);
+    u64 off = 0;
+    for (auto& sg : ctx->segs) {
+        if (!sg.n) continue;
+        KB_CUDA(ctx, cudaMemcpyAsync(s + off, sg.s.ptr, sg.n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+        KB_CUDA(ctx, cudaMemcpyAsync(p + off, sg.p.ptr, sg.n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+        KB_CUDA(ctx, cudaMemcpyAsync(o + off, sg.o.ptr, sg.n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+        off += sg.n;
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    return KB_OK;
+}
+
+kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t* is_num, uint32_t n_ids) {
+    KB_ENTER(ctx);
+    ctx->num.reset();
+    ctx->isnum.reset();
+    ctx->n_ids = 0;
+    if (n_ids == 0) return KB_OK;
+    if (!num_or0 || !is_num) return kb::fail(ctx, KB_E_INVALID, "NULL numeric table");
+    KB_TRY(kb::alloc_buf(ctx, (size_t)n_ids * sizeof(double), &ctx->num));
+    KB_TRY(kb::alloc_buf(ctx, (size_t)n_ids, &ctx->isnum));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->num->p, num_or0, (size_t)n_ids * sizeof(double), cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->isnum->p, is_num, (size_t)n_ids, cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->n_ids = n_ids;
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------ relations
+kb_status kb_rel_info(const kb_rel* r, uint64_t* n_rows, uint32_t* n_cols, uint32_t* slots) {
+    if (!r) return KB_E_INVALID;
+    if (n_rows) *n_rows = r->n;
+    if (n_cols) *n_cols = (uint32_t)r->slots.size();
+    if (slots) for (size_t i = 0; i < r->slots.size() && i < KB_MAX_COLS; i++) slots[i] = r->slots[i];
+    return KB_OK;
+}
+kb_status kb_rel_download(kb_ctx* ctx, const kb_rel* r, uint32_t col, uint32_t* dst) {
+    if (!ctx || !r) return KB_E_INVALID;
+    kb::DeviceGuard guard(ctx->device);
+    if (col >= r->cols.size()) return kb::fail(ctx, KB_E_INVALID, "column %u out of range", col);
+    if (r->n == 0) return KB_OK;
+    if (!dst) return kb::fail(ctx, KB_E_INVALID, "NULL destination");
+    KB_CUDA(ctx, cudaMemcpyAsync(dst, r->cols[col].ptr, r->n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->stats.d2h_bytes += r->n * sizeof(u32);
+    return KB_OK;
+}
+kb_status kb_rel_device_col(const kb_rel* r, uint32_t col, const uint32_t** d_ptr) {
+    if (!r || !d_ptr || col >= r->cols.size()) return KB_E_INVALID;
+    *d_ptr = r->cols[col].ptr;
+    return KB_OK;
+}
+static kb_status rel_from(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* cols, uint64_t n_rows, cudaMemcpyKind kind, kb_rel** out) {
+    if (!out || (n_cols && (!slots || !cols))) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n_cols > KB_MAX_COLS) return kb::fail(ctx, KB_E_LIMIT, "more than %d columns", KB_MAX_COLS);
+    if (n_rows >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
+    auto r = std::make_unique<kb_rel>();
+    r->n = n_rows;
+    for (u32 c = 0; c < n_cols; c++) {
+        for (u32 d = 0; d < c; d++) if (slots[d] == slots[c]) return kb::fail(ctx, KB_E_INVALID, "duplicate slot %u", slots[c]);
+        kb::Col col;
+        KB_TRY(kb::alloc_col(ctx, n_rows, &col));
+        if (n_rows) KB_CUDA(ctx, cudaMemcpyAsync(col.ptr, cols[c], n_rows * sizeof(u32), kind, ctx->st));
+        r->slots.push_back(slots[c]);
+        r->cols.push_back(col);
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += (u64)n_cols * n_rows * sizeof(u32);
+    *out = r.release();
+    return KB_OK;
+}
+kb_status kb_rel_from_host(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* cols, uint64_t n_rows, kb_rel** out) {
+    KB_ENTER(ctx);
+    return rel_from(ctx, slots, n_cols, cols, n_rows, cudaMemcpyHostToDevice, out);
+}
+kb_status kb_rel_from_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* cols, uint64_t n_rows, kb_rel** out) {
+    KB_ENTER(ctx);
+    return rel_from(ctx, slots, n_cols, cols, n_rows, cudaMemcpyDeviceToDevice, out);
+}
+void kb_rel_free(kb_ctx* ctx, kb_rel* r) {
+    if (!r) return;
+    if (ctx) {
+        kb::DeviceGuard guard(ctx->device);
+        delete r;
+    } else delete r;
+}
+
+// ------------------------------------------------------------------ operators
+kb_status kb_scan(kb_ctx* ctx, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* const* pushdown, const uint32_t* pushdown_len, kb_rel** out) {
+    KB_ENTER(ctx);
+    if (!pats || !out) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    std::vector<kb::FilterProg> pd(n_pats);
+    if (pushdown && pushdown_len)
+        for (u32 k = 0; k < n_pats; k++) if (pushdown[k] && pushdown_len[k]) {
+            KB_TRY(kb::validate_filter(ctx, pushdown[k], pushdown_len[k]));
+            pd[k].ops.assign(pushdown[k], pushdown[k] + pushdown_len[k]);
+        }
+    std::vector<std::unique_ptr<kb_rel>> rels;
+    KB_TRY(kb::scan_impl(ctx, pats, n_pats, pd, nullptr, false, &rels, nullptr, nullptr));
+    for (u32 k = 0; k < n_pats; k++) out[k] = rels[k].release();
+    if (n_pats) ctx->stats.rows_out = out[n_pats - 1]->n;
+    return KB_OK;
+}
+
+kb_status kb_filter(kb_ctx* ctx, const kb_rel* in, const kb_filter_op* prog, uint32_t n_ops, kb_rel** out) {
+    KB_ENTER(ctx);
+    if (!in || !out) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    KB_TRY(kb::validate_filter(ctx, prog, n_ops));
+    kb::FilterProg f;
+    if (n_ops) f.ops.assign(prog, prog + n_ops);
+    for (u32 s : kb::filter_slots(f)) if (in->col_of(s) < 0)
+        return kb::fail(ctx, KB_E_UNSUPPORTED, "filter references slot %u which is not bound (the reference evaluates it to false, types.rs:149-151)", s);
+    std::unique_ptr<kb_rel> r;
+    KB_TRY(kb::filter_impl(ctx, *in, f, &r));
+    ctx->stats.rows_out = r->n;
+    *out = r.release();
+    return KB_OK;
+}
+
+kb_status kb_project(kb_ctx* ctx, const kb_rel* in, const uint32_t* slots, uint32_t n_slots, kb_rel** out) {
+    if (!ctx || !in || !out || (n_slots && !slots)) return KB_E_INVALID;
+    std::vector<u32> v(slots, slots + n_slots);
+    *out = kb::select_cols(*in, v).release();
+    return KB_OK;
+}
+
+kb_status kb_hash_join(kb_ctx* ctx, const kb_rel* left, const kb_rel* right, kb_rel** out) {
+    KB_ENTER(ctx);
+    if (!left || !right || !out) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    std::unique_ptr<kb_rel> r;
+    KB_TRY(kb::hash_join_impl(ctx, *left, *right, nullptr, &r));
+    ctx->stats.rows_out = r->n;
+    *out = r.release();
+    return KB_OK;
+}
+
+kb_status kb_star_join(kb_ctx* ctx, uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops, kb_rel** out) {
+    KB_ENTER(ctx);
+    if (!pats || !out) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    std::unique_ptr<kb_rel> r;
+    KB_TRY(kb::star_join_impl(ctx, join_slot, pats, n_pats, filter, n_ops, &r));
+    ctx->stats.rows_out = r->n;
+    *out = r.release();
+    return KB_OK;
+}
+
+kb_status kb_bgp_execute(kb_ctx* ctx, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops,
+                         const uint32_t* project, uint32_t n_project, kb_rel** out) {
+    KB_ENTER(ctx);
+    if (!pats || !out || n_pats == 0) return kb::fail(ctx, KB_E_INVALID, "NULL or empty BGP");
+    if (n_pats > (u32)kb::MAXP) return kb::fail(ctx, KB_E_LIMIT, "more than %d patterns", kb::MAXP);
+    KB_TRY(kb::validate_filter(ctx, filter, n_ops));
+    std::vector<std::vector<u32>> pv(n_pats), ps(n_pats);
+    std::vector<u32> all_slots;
+    for (u32 k = 0; k < n_pats; k++) {
+        kb::pattern_vars(pats[k], &pv[k], &ps[k]);
+        for (u32 s : pv[k]) if (std::find(all_slots.begin(), all_slots.end(), s) == all_slots.end()) all_slots.push_back(s);
+    }
+    // a variable shared by every pattern -> star join (optimizer.rs:84-152); prefer the subject position
+    int star = -1;
+    for (size_t i = 0; i < pv[0].size() && star < 0; i++) {
+        bool all = true;
+        for (u32 k = 1; k < n_pats; k++) if (std::find(pv[k].begin(), pv[k].end(), pv[0][i]) == pv[k].end()) all = false;
+        if (all) star = (int)pv[0][i];
+    }
+    std::unique_ptr<kb_rel> cur;
+    if (star >= 0) {
+        KB_TRY(kb::star_join_impl(ctx, (u32)star, pats, n_pats, filter, n_ops, &cur));
+    } else {
+        // left-deep natural joins in textual order (build_logical_plan, utils.rs:101-191)
+        std::vector<kb::FilterProg> conj, pushdown(n_pats);
+        kb::FilterProg post;
+        if (!kb::split_conjuncts(filter, n_ops, &conj)) return kb::fail(ctx, KB_E_INVALID, "malformed filter program");
+        for (auto& c : conj) {
+            std::set<u32> fs = kb::filter_slots(c);
+            for (u32 s : fs) if (std::find(all_slots.begin(), all_slots.end(), s) == all_slots.end())
+                return kb::fail(ctx, KB_E_UNSUPPORTED, "filter references slot %u which no pattern binds", s);
+            int target = -1;
+            for (u32 k = 0; k < n_pats && target < 0; k++) {
+                bool all = true;
+                for (u32 s : fs) if (std::find(pv[k].begin(), pv[k].end(), s) == pv[k].end()) all = false;
+                if (all) target = (int)k;
+            }
+            kb::FilterProg* dst = target >= 0 ? &pushdown[target] : &post;
+            const bool had = !dst->ops.empty();
+            dst->ops.insert(dst->ops.end(), c.ops.begin(), c.ops.end());
+            if (had) { kb_filter_op a{}; a.op = KB_F_AND; dst->ops.push_back(a); }
+        }
+        std::vector<std::unique_ptr<kb_rel>> rels;
+        KB_TRY(kb::scan_impl(ctx, pats, n_pats, pushdown, nullptr, false, &rels, nullptr, nullptr));
+        cur = std::move(rels[0]);
+        for (u32 k = 1; k < n_pats; k++) {
+            std::unique_ptr<kb_rel> j;
+            KB_TRY(kb::hash_join_impl(ctx, *cur, *rels[k], (k + 1 == n_pats && !post.ops.empty()) ? &post : nullptr, &j));
+            cur = std::move(j);
+        }
+        if (n_pats == 1 && !post.ops.empty()) { std::unique_ptr<kb_rel> f; KB_TRY(kb::filter_impl(ctx, *cur, post, &f)); cur = std::move(f); }
+        cur = kb::select_cols(*cur, all_slots);
+    }
+    if (project) {
+        std::vector<u32> v(project, project + n_project);
+        cur = kb::select_cols(*cur, v);
+    }
+    ctx->stats.rows_out = cur->n;
+    *out = cur.release();
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------ GROUP BY
+kb_status kb_group_aggregate(kb_ctx* ctx, const kb_rel* in, const uint32_t* group_slots, uint32_t n_group, const kb_agg* aggs, uint32_t n_aggs, kb_groups** out) {
+    KB_ENTER(ctx);
+    if (!in || !out || (n_group && !group_slots) || (n_aggs && !aggs)) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n_group == 0 || n_group > 4) return kb::fail(ctx, KB_E_LIMIT, "GROUP BY takes 1..4 variables");
+    if (n_aggs > 8) return kb::fail(ctx, KB_E_LIMIT, "at most 8 aggregates");
+    if (in->n >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
+    kb::GroupParams P{};
+    P.n_gcols = n_group;
+    for (u32 c = 0; c < n_group; c++) {
+        int ci = in->col_of(group_slots[c]);
+        if (ci < 0) return kb::fail(ctx, KB_E_INVALID, "GROUP BY slot %u is not a column", group_slots[c]);
+        P.gcol[c] = in->cols[ci].ptr;
+    }
+    P.n_aggs = n_aggs;
+    for (u32 a = 0; a < n_aggs; a++) {
+        P.akind[a] = aggs[a].kind;
+        P.acol[a] = nullptr;
+        if (aggs[a].kind > KB_AGG_AVG) return kb::fail(ctx, KB_E_INVALID, "unknown aggregate kind %u", aggs[a].kind);
+        if (aggs[a].kind != KB_AGG_COUNT) {
+            int ci = in->col_of(aggs[a].slot);
+            if (ci < 0) return kb::fail(ctx, KB_E_INVALID, "aggregate slot %u is not a column", aggs[a].slot);
+            P.acol[a] = in->cols[ci].ptr;
+        }
+    }
+    P.n = (u32)in->n;
+    P.nt = kb::numtab(ctx);
+    auto g = std::make_unique<kb_groups>();
+    g->keys.resize(n_group);
+    g->vals.resize(n_aggs);
+    if (in->n == 0) { *out = g.release(); return KB_OK; }
+    u64 slots = 1u << 16;
+    for (;;) {
+        P.n_slots = (u32)slots;
+        kb::Buf keys, state, val, cnt;
+        KB_TRY(kb::alloc_buf(ctx, slots * 4 * sizeof(u32), &keys));
+        KB_TRY(kb::alloc_buf(ctx, slots * sizeof(u32), &state));
+        KB_TRY(kb::alloc_buf(ctx, slots * 8 * sizeof(double), &val));
+        KB_TRY(kb::alloc_buf(ctx, slots * sizeof(unsigned long long), &cnt));
+        P.gkeys = (u32*)keys->p; P.gstate = (u32*)state->p; P.gval = (double*)val->p; P.gcnt = (unsigned long long*)cnt->p;
+        const u32 off = kb::ctrl_alloc(ctx, 4);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+        P.overflow = ctx->ctrl + off;
+        kb::timer_begin(ctx, kb::F_GROUP);
+        kb::launch_group_init(P, ctx->st);
+        kb::launch_group(P, ctx->n_sms, ctx->st);
+        kb::timer_end(ctx);
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(kb::ctrl_read(ctx));
+        if (ctx->h_ctrl[off] == 0) {
+            std::vector<u32> hstate(slots), hkeys(slots * 4);
+            std::vector<double> hval(slots * 8);
+            std::vector<unsigned long long> hcnt(slots);
+            KB_CUDA(ctx, cudaMemcpyAsync(hstate.data(), P.gstate, slots * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+            KB_CUDA(ctx, cudaMemcpyAsync(hkeys.data(), P.gkeys, slots * 4 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+            KB_CUDA(ctx, cudaMemcpyAsync(hval.data(), P.gval, slots * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
+            KB_CUDA(ctx, cudaMemcpyAsync(hcnt.data(), P.gcnt, slots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+            KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+            for (u64 i = 0; i < slots; i++) {
+                if (hstate[i] != 2u) continue;
+                for (u32 c = 0; c < n_group; c++) g->keys[c].push_back(hkeys[i * 4 + c]);
+                g->counts.push_back(hcnt[i]);
+                for (u32 a = 0; a < n_aggs; a++) {
+                    double v = hval[i * 8 + a];
+                    if (aggs[a].kind == KB_AGG_AVG) v = v / (double)hcnt[i];   // execute_query.rs:1216
+                    if (aggs[a].kind == KB_AGG_COUNT) v = (double)hcnt[i];
+                    g->vals[a].push_back(v);
+                }
+            }
+            break;
+        }
+        if (slots >= 2 * in->n && slots >= (1u << 20)) return kb::fail(ctx, KB_E_LIMIT, "group table overflow");
+        slots *= 16;
+        if (slots > (1ull << 30)) slots = 1ull << 30;
+    }
+    *out = g.release();
+    return KB_OK;
+}
+kb_status kb_groups_info(const kb_groups* g, uint64_t* n_groups, uint32_t* n_group_cols, uint32_t* n_aggs) {
+    if (!g) return KB_E_INVALID;
+    if (n_groups) *n_groups = g->counts.size();
+    if (n_group_cols) *n_group_cols = (uint32_t)g->keys.size();
+    if (n_aggs) *n_aggs = (uint32_t)g->vals.size();
+    return KB_OK;
+}
+kb_status kb_groups_keys(const kb_groups* g, uint32_t col, const uint32_t** keys) {
+    if (!g || !keys || col >= g->keys.size()) return KB_E_INVALID;
+    *keys = g->keys[col].data();
+    return KB_OK;
+}
+kb_status kb_groups_values(const kb_groups* g, uint32_t agg, const double** values) {
+    if (!g || !values || agg >= g->vals.size()) return KB_E_INVALID;
+    *values = g->vals[agg].data();
+    return KB_OK;
+}
+kb_status kb_groups_counts(const kb_groups* g, const uint64_t** counts) {
+    if (!g || !counts) return KB_E_INVALID;
+    *counts = g->counts.data();
+    return KB_OK;
+}
+void kb_groups_free(kb_groups* g) { delete g; }
+
+// ------------------------------------------------------------------ multi-GPU helpers
+uint32_t kb_shard_of(uint32_t key, uint32_t n_shards) { return n_shards ? kb::mix32(key) % n_shards : 0; }
+
+kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, kb_rel** out, uint64_t* part_offsets) {
+    KB_ENTER(ctx);
+    if (!in || !out || !part_offsets) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n_parts == 0 || n_parts > 64) return kb::fail(ctx, KB_E_LIMIT, "1..64 partitions");
+    const int kc = in->col_of(key_slot);
+    if (kc < 0) return kb::fail(ctx, KB_E_INVALID, "partition key slot %u is not a column", key_slot);
+    if (in->n >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
+    auto r = std::make_unique<kb_rel>();
+    r->slots = in->slots;
+    r->n = in->n;
+    const u32 off = kb::ctrl_alloc(ctx, 128);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 128 * sizeof(u32), ctx->st));
+    kb::timer_begin(ctx, kb::F_OTHER);
+    kb::launch_part_count(in->cols[kc].ptr, (u32)in->n, n_parts, ctx->ctrl + off, ctx->n_sms, ctx->st);
+    kb::timer_end(ctx);
+    KB_TRY(kb::ctrl_read(ctx));
+    u64 run = 0;
+    std::vector<u32> cursors(n_parts);
+    for (u32 i = 0; i < n_parts; i++) { part_offsets[i] = run; cursors[i] = (u32)run; run += ctx->h_ctrl[off + i]; }
+    part_offsets[n_parts] = run;
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->ctrl + off + 64, cursors.data(), n_parts * sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
+    std::vector<const u32*> ic;
+    std::vector<u32*> oc;
+    for (auto& c : in->cols) {
+        kb::Col col;
+        KB_TRY(kb::alloc_col(ctx, in->n, &col));
+        r->cols.push_back(col);
+        ic.push_back(c.ptr);
+        oc.push_back(col.ptr);
+    }
+    kb::timer_begin(ctx, kb::F_OTHER);
+    kb::launch_part_scatter(in->cols[kc].ptr, (u32)in->n, n_parts, ctx->ctrl + off + 64, ic.data(), oc.data(), (u32)ic.size(), ctx->n_sms, ctx->st);
+    kb::timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    kb::timers_flush(ctx);
+    *out = r.release();
+    return KB_OK;
+}
+
+// ------------------------------------------------------------------ one-shot host-buffer star join
+kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint32_t join_slot,
+                            const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops, uint32_t* n_cols,
+                            uint32_t* slots, uint32_t** cols, uint64_t* n_rows) {
+    KB_ENTER(ctx);
+    if (!pats || !n_cols || !slots || !cols || !n_rows) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n && (!s || !p || !o)) return kb::fail(ctx, KB_E_INVALID, "NULL column pointer");
+    if (n >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "too many triples");
+    const bool caller_bufs = cols[0] != nullptr;
+    const u64 caller_cap = caller_bufs ? *n_rows : 0;
+    // upload in chunks on the copy stream; each chunk is a store segment the scan starts on as soon as its copy has landed
+    ctx->segs.clear();
+    ctx->n_triples = 0;
+    kb::Col cs, cp, co;
+    KB_TRY(kb::alloc_col(ctx, n, &cs));
+    KB_TRY(kb::alloc_col(ctx, n, &cp));
+    KB_TRY(kb::alloc_col(ctx, n, &co));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));  // allocations are stream-ordered on st; the copy stream must see them
+    const u64 chunk = (u64)kb::SCAN_TILE * 4096;   // 8 Mi triples = 32 MiB per column
+    std::vector<cudaEvent_t> evs;
+    for (u64 b = 0; b < n; b += chunk) {
+        const u64 m = std::min(chunk, n - b);
+        KB_CUDA(ctx, cudaMemcpyAsync(cs.ptr + b, s + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
+        KB_CUDA(ctx, cudaMemcpyAsync(cp.ptr + b, p + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
+        KB_CUDA(ctx, cudaMemcpyAsync(co.ptr + b, o + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
+        cudaEvent_t ev;
+        KB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        KB_CUDA(ctx, cudaEventRecord(ev, ctx->st_copy));
+        evs.push_back(ev);
+        kb::Segment sg;
+        sg.tag = 0; sg.n = m;
+        sg.ready = ev;
+        sg.s.buf = cs.buf; sg.s.ptr = cs.ptr + b;
+        sg.p.buf = cp.buf; sg.p.ptr = cp.ptr + b;
+        sg.o.buf = co.buf; sg.o.ptr = co.ptr + b;
+        ctx->segs.push_back(sg);
+        ctx->n_triples += m;
+    }
+    ctx->stats.h2d_bytes += 3 * n * sizeof(u32);
+    ctx->store_version++;
+    ctx->multi_valued.clear();
+    // scan_impl makes st wait on each segment's `ready` event right before that segment's scan kernel: copy i+1 overlaps scan i
+    std::unique_ptr<kb_rel> r;
+    kb_status rc = kb::star_join_impl(ctx, join_slot, pats, n_pats, filter, n_ops, &r);
+    for (auto& sg : ctx->segs) sg.ready = nullptr;
+    for (auto ev : evs) cudaEventDestroy(ev);
+    if (rc != KB_OK) return rc;
+    *n_cols = (u32)r->slots.size();
+    *n_rows = r->n;
+    for (size_t c = 0; c < r->slots.size(); c++) slots[c] = r->slots[c];
+    if (caller_bufs && caller_cap < r->n) return kb::fail(ctx, KB_E_LIMIT, "caller buffers hold %llu rows, result has %llu", (unsigned long long)caller_cap, (unsigned long long)r->n);
+    for (size_t c = 0; c < r->slots.size(); c++) {
+        if (!caller_bufs) {
+            cols[c] = (uint32_t*)malloc(std::max<size_t>(r->n * sizeof(u32), 4));
+            if (!cols[c]) return kb::fail(ctx, KB_E_OOM, "malloc failed");
+        } else if (!cols[c]) return kb::fail(ctx, KB_E_INVALID, "caller-provided column buffer %zu is NULL", c);
+        if (r->n) KB_CUDA(ctx, cudaMemcpyAsync(cols[c], r->cols[c].ptr, r->n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->stats.d2h_bytes += r->slots.size() * r->n * sizeof(u32);
+    ctx->stats.rows_out = r->n;
+    return KB_OK;
+}
+
+}  // extern "C"

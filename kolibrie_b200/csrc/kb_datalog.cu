@@ -1,0 +1,389 @@
+// kb_datalog.cu — semi-naive / naive Datalog materialisation on the device.
+// Replaces Reasoner::infer_with_strategy (datalog/src/reasoning/materialisation/infer_generic.rs:27-53) driving
+// SemiNaiveStrategy (semi_naive.rs:17-85) or NaiveStrategy (my_naive.rs:18-69), whose join is
+// perform_hash_join_for_rules (shared/src/join_algorithm.rs:499-677).
+//
+// Layout: one (s,o) column pair per predicate that occurs in a rule, append-only, exactly like the reference's
+// `all_facts: Vec<Triple>` with its delta suffix (semi_naive.rs:57-59) but partitioned by predicate once instead of
+// re-filtered by predicate for every premise of every rule of every round (join_algorithm.rs:528-534).
+// known_facts (infer_generic.rs:30) is a device hash set of 96-bit (s,p,o) keys; a derived fact is new iff its insert wins.
+// Round structure is the reference's: every rule of a round sees the same snapshot; new facts become visible (and become the
+// next delta) only after the round (infer_generic.rs:42-48) — so round counts and per-round fact counts match the oracle.
+#include <algorithm>
+
+#include "kb_internal.hpp"
+
+using namespace kb;
+
+namespace {
+
+struct PredRel {
+    u32 pred = 0;
+    Col s, o;
+    u64 n = 0, cap = 0;
+    u64 base_n = 0;       // facts present before inference
+    u64 delta_start = 0;  // facts [delta_start, snapshot) were added by the previous round
+    u64 snapshot = 0;
+    bool is_head = false;
+};
+
+struct Premise {
+    int s_var, o_var;  // variable slots (real or synthetic, quirk Q6)
+    bool pred_const;
+    u32 pred;
+};
+struct RulePlan {
+    std::vector<Premise> prem;
+    u32 n_vars = 0;
+};
+
+struct Pending {  // facts derived in the current round, not yet visible to the joins
+    u32 pred;
+    Col s, o;
+    u64 count;
+};
+
+struct Fix {
+    kb_ctx* ctx;
+    std::map<u32, PredRel> rels;
+    std::vector<Pending> pend;
+    Buf set;
+    u32 set_slots = 0;
+    u64 set_count = 0;  // keys in the set (exact: every derive reports how many inserts won)
+};
+
+kb_status grow_rel(kb_ctx* ctx, PredRel& r, u64 need) {
+    if (need <= r.cap) return KB_OK;
+    u64 cap = std::max<u64>(need, r.cap * 2);
+    cap = std::max<u64>(cap, 1024);
+    Col ns, no;
+    KB_TRY(alloc_col(ctx, cap, &ns));
+    KB_TRY(alloc_col(ctx, cap, &no));
+    if (r.n) {
+        KB_CUDA(ctx, cudaMemcpyAsync(ns.ptr, r.s.ptr, r.n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+        KB_CUDA(ctx, cudaMemcpyAsync(no.ptr, r.o.ptr, r.n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+    }
+    r.s = ns; r.o = no; r.cap = cap;
+    return KB_OK;
+}
+
+// (re)build the known-fact set so that it can take `extra` more keys at load <= 0.5
+kb_status ensure_set(Fix& fx, u64 extra) {
+    kb_ctx* ctx = fx.ctx;
+    const u64 need = (fx.set_count + extra) * 2;
+    if (fx.set && need <= fx.set_slots) return KB_OK;
+    u64 slots = 1024;
+    while (slots < need * 2) slots <<= 1;
+    if (slots > (1ull << 31)) return fail(ctx, KB_E_LIMIT, "known-fact set would need %llu slots", (unsigned long long)slots);
+    Buf nb;
+    KB_TRY(alloc_buf(ctx, slots * sizeof(uint4), &nb));
+    KB_CUDA(ctx, cudaMemsetAsync(nb->p, 0, slots * sizeof(uint4), ctx->st));
+    const u32 off = ctrl_alloc(ctx, 4);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+    u64 count = 0;
+    timer_begin(ctx, F_BUILD);
+    for (auto& kv : fx.rels) {
+        PredRel& r = kv.second;
+        if (!r.is_head || r.n == 0) continue;
+        launch_set_insert(static_cast<uint4*>(nb->p), (u32)slots, r.s.ptr, nullptr, r.pred, r.o.ptr, (u32)r.n, ctx->ctrl + off, ctx->n_sms, ctx->st);
+        count += r.n;
+    }
+    for (auto& pd : fx.pend) {  // a rebuild in the middle of a round must keep this round's facts
+        launch_set_insert(static_cast<uint4*>(nb->p), (u32)slots, pd.s.ptr, nullptr, pd.pred, pd.o.ptr, (u32)pd.count, ctx->ctrl + off, ctx->n_sms, ctx->st);
+        count += pd.count;
+    }
+    timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    fx.set = nb;
+    fx.set_slots = (u32)slots;
+    fx.set_count = count;
+    return KB_OK;
+}
+
+// a relation view over rows [start, start+n) of a predicate's columns; the probe kernels TMA-load their inputs, which needs
+// 16-byte aligned column starts, so a misaligned suffix (the delta) is copied
+kb_status make_view(kb_ctx* ctx, const PredRel& r, u64 start, u64 n, u32 s_slot, u32 o_slot, std::unique_ptr<kb_rel>* out) {
+    auto v = std::make_unique<kb_rel>();
+    v->slots = {s_slot, o_slot};
+    v->n = n;
+    const Col* src[2] = {&r.s, &r.o};
+    for (int c = 0; c < 2; c++) {
+        Col col;
+        if ((start & 3ull) == 0) {
+            col.buf = src[c]->buf;
+            col.ptr = src[c]->ptr + start;
+        } else {
+            KB_TRY(alloc_col(ctx, n, &col));
+            if (n) KB_CUDA(ctx, cudaMemcpyAsync(col.ptr, src[c]->ptr + start, n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+        }
+        v->cols.push_back(col);
+    }
+    *out = std::move(v);
+    return KB_OK;
+}
+
+}  // namespace
+
+extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy, kb_rel** inferred,
+                                         kb_fixpoint_stats* stats) {
+    if (!ctx) return KB_E_INVALID;
+    int prev_dev = -1;
+    cudaGetDevice(&prev_dev);
+    cudaSetDevice(ctx->device);
+    struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
+    KB_TRY(begin_call(ctx));
+    if ((n_rules && !rules) || !inferred) return fail(ctx, KB_E_INVALID, "NULL argument");
+    if (strategy != KB_SEMI_NAIVE && strategy != KB_NAIVE) return fail(ctx, KB_E_INVALID, "unknown strategy %u", strategy);
+    kb_fixpoint_stats st{};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, ctx->st);
+
+    // ---- compile the rules (host): variable slots, synthetic variables for constants in s/o (quirk Q6), safety checks
+    std::vector<RulePlan> plans(n_rules);
+    Fix fx;
+    fx.ctx = ctx;
+    for (u32 r = 0; r < n_rules; r++) {
+        const kb_rule& rule = rules[r];
+        if (rule.n_premise > KB_MAX_PREMISES || rule.n_conclusion > KB_MAX_CONCLUSIONS || rule.n_filters > KB_MAX_RULE_FILTERS)
+            return fail(ctx, KB_E_LIMIT, "rule %u exceeds the premise/conclusion/filter limits", r);
+        u32 mx = 0;
+        auto upd = [&](const kb_term& t) { if (t.is_var) mx = std::max(mx, t.value + 1); };
+        for (u32 i = 0; i < rule.n_premise; i++) { upd(rule.premise[i].s); upd(rule.premise[i].p); upd(rule.premise[i].o); }
+        for (u32 i = 0; i < rule.n_conclusion; i++) { upd(rule.conclusion[i].s); upd(rule.conclusion[i].p); upd(rule.conclusion[i].o); }
+        u32 next = mx;
+        std::map<std::pair<u32, u32>, u32> synth;  // (position, constant) -> synthetic slot: "__const_subj_{c}" / "__const_obj_{c}"
+        auto syn = [&](u32 pos, u32 c) {
+            auto it = synth.find({pos, c});
+            if (it != synth.end()) return it->second;
+            synth[{pos, c}] = next;
+            return next++;
+        };
+        std::set<u32> bound;
+        for (u32 i = 0; i < rule.n_premise; i++) {
+            const kb_pattern& p = rule.premise[i];
+            Premise pr;
+            pr.s_var = (int)(p.s.is_var ? p.s.value : syn(0, p.s.value));
+            pr.o_var = (int)(p.o.is_var ? p.o.value : syn(2, p.o.value));
+            pr.pred_const = !p.p.is_var;
+            pr.pred = p.p.value;
+            if (pr.s_var == pr.o_var)
+                return fail(ctx, KB_E_UNSUPPORTED, "rule %u premise %u repeats one variable in subject and object", r, i);
+            if (pr.pred_const) { fx.rels[pr.pred].pred = pr.pred; bound.insert((u32)pr.s_var); bound.insert((u32)pr.o_var); }
+            plans[r].prem.push_back(pr);
+        }
+        plans[r].n_vars = next;
+        if (next > KB_MAX_COLS) return fail(ctx, KB_E_LIMIT, "rule %u uses more than %d variables", r, KB_MAX_COLS);
+        for (u32 c = 0; c < rule.n_conclusion; c++) {
+            const kb_pattern& h = rule.conclusion[c];
+            if (h.p.is_var) return fail(ctx, KB_E_UNSUPPORTED, "rule %u: variable predicate in a conclusion", r);
+            const kb_term* ts[2] = {&h.s, &h.o};
+            for (auto* t : ts) if (t->is_var && !bound.count(t->value))
+                return fail(ctx, KB_E_UNSUPPORTED, "rule %u: head variable (slot %u) is not bound by the premises (quirk Q8: the reference invents ml_output_placeholder terms / id 0)", r, t->value);
+            fx.rels[h.p.value].pred = h.p.value;
+            fx.rels[h.p.value].is_head = true;
+        }
+        for (u32 f = 0; f < rule.n_filters; f++) {
+            if (rule.filters[f].cmp > KB_CMP_NE) return fail(ctx, KB_E_INVALID, "rule %u filter %u: bad comparison", r, f);
+        }
+    }
+
+    // ---- split the store by predicate: one fused scan per 8 predicates
+    {
+        std::vector<u32> preds;
+        for (auto& kv : fx.rels) preds.push_back(kv.first);
+        for (size_t b = 0; b < preds.size(); b += MAXP) {
+            const u32 k = (u32)std::min<size_t>(MAXP, preds.size() - b);
+            kb_pattern pats[MAXP];
+            for (u32 i = 0; i < k; i++) { pats[i].s = kb_term{1, 0}; pats[i].p = kb_term{0, preds[b + i]}; pats[i].o = kb_term{1, 1}; }
+            std::vector<std::unique_ptr<kb_rel>> out;
+            std::vector<FilterProg> none;
+            KB_TRY(scan_impl(ctx, pats, k, none, nullptr, false, &out, nullptr, nullptr));
+            for (u32 i = 0; i < k; i++) {
+                PredRel& r = fx.rels[preds[b + i]];
+                r.s = out[i]->cols[0];
+                r.o = out[i]->cols[1];
+                r.n = r.base_n = out[i]->n;
+                r.cap = ctx->n_triples;
+                if (r.n * 4 < r.cap) {  // shrink: the scan allocates for the worst case
+                    r.cap = 0;
+                    Col os = r.s, oo = r.o;
+                    u64 n = r.n;
+                    r.n = 0;
+                    KB_TRY(grow_rel(ctx, r, std::max<u64>(n * 2, 1024)));
+                    if (n) {
+                        KB_CUDA(ctx, cudaMemcpyAsync(r.s.ptr, os.ptr, n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+                        KB_CUDA(ctx, cudaMemcpyAsync(r.o.ptr, oo.ptr, n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+                    }
+                    r.n = n;
+                }
+            }
+        }
+    }
+    u64 head_base = 0;
+    for (auto& kv : fx.rels) if (kv.second.is_head) head_base += kv.second.n;
+    KB_TRY(ensure_set(fx, head_base + 1024));
+
+    // ---- rounds
+    for (u32 round = 0;; round++) {
+        for (auto& kv : fx.rels) kv.second.snapshot = kv.second.n;
+        fx.pend.clear();
+        for (u32 r = 0; r < n_rules; r++) {
+            const kb_rule& rule = rules[r];
+            const RulePlan& pl = plans[r];
+            const u32 np = (u32)pl.prem.size();
+            if (np == 0) continue;
+            bool dead = false;
+            for (auto& pr : pl.prem) if (!pr.pred_const) dead = true;  // a variable predicate never matches (join_algorithm.rs:515-521)
+            if (dead) continue;
+            const u32 n_start = strategy == KB_NAIVE ? 1 : np;
+            for (u32 i = 0; i < n_start; i++) {
+                // premise i over the delta (semi-naive) or over all facts (naive), then the others over all facts
+                std::unique_ptr<kb_rel> cur;
+                {
+                    const PredRel& pr = fx.rels[pl.prem[i].pred];
+                    const u64 a = strategy == KB_NAIVE ? 0 : pr.delta_start;
+                    const u64 n = pr.snapshot - a;
+                    if (n == 0) continue;
+                    KB_TRY(make_view(ctx, pr, a, n, (u32)pl.prem[i].s_var, (u32)pl.prem[i].o_var, &cur));
+                }
+                for (u32 j = 0; j < np && cur->n; j++) {
+                    if (j == i) continue;
+                    const PredRel& pr = fx.rels[pl.prem[j].pred];
+                    if (pr.snapshot == 0) { cur->n = 0; break; }
+                    std::unique_ptr<kb_rel> all, joined;
+                    KB_TRY(make_view(ctx, pr, 0, pr.snapshot, (u32)pl.prem[j].s_var, (u32)pl.prem[j].o_var, &all));
+                    KB_TRY(hash_join_impl(ctx, *cur, *all, nullptr, &joined));
+                    cur = std::move(joined);
+                }
+                if (cur->n == 0) continue;
+                // heads: filters + instantiate + dedup against known facts + append
+                for (u32 c = 0; c < rule.n_conclusion; c++) {
+                    const kb_pattern& h = rule.conclusion[c];
+                    DeriveParams D{};
+                    for (size_t k = 0; k < cur->cols.size(); k++) D.bcol[k] = cur->cols[k].ptr;
+                    D.n = (u32)cur->n;
+                    D.n_heads = 1;
+                    auto term = [&](const kb_term& t) {
+                        HeadTerm ht;
+                        ht.is_var = t.is_var;
+                        ht.value = t.is_var ? (u32)cur->col_of(t.value) : t.value;
+                        return ht;
+                    };
+                    D.head[0][0] = term(h.s);
+                    D.head[0][1] = HeadTerm{0, h.p.value};
+                    D.head[0][2] = term(h.o);
+                    D.n_filt = 0;
+                    for (u32 f = 0; f < rule.n_filters; f++) {
+                        const kb_rule_filter& rf = rule.filters[f];
+                        const int lc = cur->col_of(rf.lhs_slot);
+                        if (lc < 0 || rf.cmp == 0) continue;  // unbound lhs: the reference skips the filter (rules.rs:139)
+                        RuleFilterDev d;
+                        d.lhs_col = (u32)lc;
+                        d.cmp = rf.cmp;
+                        d.rhs_value = rf.rhs_value;
+                        d.rhs_is_var = 0; d.rhs_col = 0;
+                        if (rf.rhs_is_var) {
+                            const int rc = cur->col_of(rf.rhs_slot);
+                            if (rc >= 0) { d.rhs_is_var = 1; d.rhs_col = (u32)rc; }
+                            // rhs names an unbound variable: the reference falls to the numeric branch with value.parse() (rules.rs:148-151)
+                        }
+                        D.filt[D.n_filt++] = d;
+                    }
+                    D.nt = numtab(ctx);
+                    KB_TRY(ensure_set(fx, cur->n));
+                    D.set = static_cast<uint4*>(fx.set->p);
+                    D.set_slots = fx.set_slots;
+                    Pending pd;
+                    pd.pred = h.p.value;
+                    pd.count = 0;
+                    KB_TRY(alloc_col(ctx, cur->n, &pd.s));
+                    KB_TRY(alloc_col(ctx, cur->n, &pd.o));
+                    Col scratch_p;
+                    KB_TRY(alloc_col(ctx, cur->n, &scratch_p));
+                    const u32 coff = ctrl_alloc(ctx, 8);
+                    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff, 0, 8 * sizeof(u32), ctx->st));
+                    D.out_s = pd.s.ptr; D.out_p = scratch_p.ptr; D.out_o = pd.o.ptr;
+                    D.out_cap = (u32)cur->n;
+                    D.out_count = ctx->ctrl + coff;
+                    D.overflow = ctx->ctrl + coff + 1;
+                    D.n_deriv = reinterpret_cast<unsigned long long*>(ctx->ctrl + coff + 4);
+                    timer_begin(ctx, F_OTHER);
+                    launch_derive(D, ctx->n_sms, ctx->st);
+                    timer_end(ctx);
+                    KB_CUDA(ctx, cudaGetLastError());
+                    // counts are read immediately: the control arena may be recycled by later joins of this round
+                    KB_TRY(ctrl_read(ctx));
+                    if (ctx->h_ctrl[coff + 1]) return fail(ctx, KB_E_LIMIT, "known-fact set overflow");
+                    pd.count = ctx->h_ctrl[coff];
+                    unsigned long long nd;
+                    memcpy(&nd, ctx->h_ctrl + coff + 4, sizeof nd);
+                    st.derivations += nd;
+                    fx.set_count += pd.count;
+                    if (pd.count) fx.pend.push_back(pd);
+                }
+            }
+        }
+        // ---- end of round: the facts that were new become visible (infer_generic.rs:42-48)
+        u64 round_new = 0;
+        for (auto& kv : fx.rels) kv.second.delta_start = kv.second.snapshot;
+        for (auto& pd : fx.pend) {
+            PredRel& r = fx.rels[pd.pred];
+            const u64 cnt = pd.count;
+            KB_TRY(grow_rel(ctx, r, r.n + cnt));
+            KB_CUDA(ctx, cudaMemcpyAsync(r.s.ptr + r.n, pd.s.ptr, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            KB_CUDA(ctx, cudaMemcpyAsync(r.o.ptr + r.n, pd.o.ptr, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            r.n += cnt;
+            round_new += cnt;
+        }
+        fx.pend.clear();
+        if (round_new == 0) break;
+        if (st.rounds < 64) st.round_new[st.rounds] = round_new;
+        st.rounds++;
+        st.inferred += round_new;
+        if (round > 100000) return fail(ctx, KB_E_LIMIT, "fixpoint did not converge");
+    }
+
+    // ---- result: inferred facts as (s,p,o) columns; also appended to the store (infer_generic.rs:46 index_manager.insert)
+    auto res = std::make_unique<kb_rel>();
+    res->slots = {0, 1, 2};
+    res->n = st.inferred;
+    Col cs, cp, co;
+    KB_TRY(alloc_col(ctx, st.inferred, &cs));
+    KB_TRY(alloc_col(ctx, st.inferred, &cp));
+    KB_TRY(alloc_col(ctx, st.inferred, &co));
+    u64 off = 0;
+    for (auto& kv : fx.rels) {
+        PredRel& r = kv.second;
+        const u64 cnt = r.n - r.base_n;
+        if (!cnt) continue;
+        KB_CUDA(ctx, cudaMemcpyAsync(cs.ptr + off, r.s.ptr + r.base_n, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+        KB_CUDA(ctx, cudaMemcpyAsync(co.ptr + off, r.o.ptr + r.base_n, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+        launch_fill_u32(cp.ptr + off, r.pred, cnt, ctx->st);
+        off += cnt;
+    }
+    res->cols = {cs, cp, co};
+    if (st.inferred) {
+        Segment sg;
+        sg.tag = KB_TAG_INFERRED;
+        sg.n = st.inferred;
+        sg.s = cs; sg.p = cp; sg.o = co;
+        ctx->segs.push_back(sg);
+        ctx->n_triples += st.inferred;
+        ctx->store_version++;
+        ctx->multi_valued.clear();
+    }
+    cudaEventRecord(ev1, ctx->st);
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    timers_flush(ctx);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    st.device_ms = ms;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    if (stats) *stats = st;
+    ctx->stats.rows_out = st.inferred;
+    *inferred = res.release();
+    return KB_OK;
+}

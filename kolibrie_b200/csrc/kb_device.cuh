@@ -1,0 +1,195 @@
+// kb_device.cuh — sm_100a device helpers shared by all kernels: TMA bulk copies + mbarrier, the single-pass
+// "decoupled look-back" tile prefix that gives every compaction kernel a deterministic, store-ordered output,
+// hashing, and the FILTER evaluator (semantics: kolibrie/src/streamertail_optimizer/types.rs:110-186).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/kolibrie_b200.h"
+
+namespace kb {
+
+using u8 = uint8_t;
+using u32 = uint32_t;
+using u64 = uint64_t;
+
+constexpr u32 EMPTY32 = 0xFFFFFFFFu;  // == KB_ID_NONE: reserved id, never a dictionary / quoted-triple id
+constexpr u64 EMPTY64 = ~0ull;
+constexpr int MAXP = KB_MAX_PATTERNS;
+
+__host__ __device__ __forceinline__ u32 mix32(u32 x) {  // murmur3 finaliser; also the shard function (kb_shard_of)
+    x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// mbarrier + TMA (cp.async.bulk, 1-D: no tensor map needed for flat u32 columns). SASS: UBLKCP / SYNCS.
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "KB_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra KB_WAIT_DONE;\n\t"
+        "bra KB_WAIT_LOOP;\n\t"
+        "KB_WAIT_DONE:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16; completion counted on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// relaxed gpu-scope 64-bit accesses for the tile-state words
+__device__ __forceinline__ u64 ld_relaxed(const u64* p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u64* p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+
+__device__ __forceinline__ u32 warp_sum(u32 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Single-pass ordered prefix across tiles ("decoupled look-back"). One state word per (tile, counter):
+//   [63:34] launch epoch (so the buffer never needs clearing)  [33:32] status 1=A(ggregate) 2=P(refix)  [31:0] value.
+// Tiles take tickets from an atomic counter, so a tile only ever waits on tiles that are already running.
+// Called by ALL 32 lanes of one warp once counts[0..K) (shared memory) are final; writes the exclusive prefix of this tile
+// to excl[0..K). base[k] (global, may be null) is added to tile 0: the running total of earlier launches (store segments).
+constexpr u64 TS_A = 1ull << 32, TS_P = 2ull << 32;
+__device__ __forceinline__ void tile_prefix_warp(u64* __restrict__ state, u32 tile, u32 K, u64 epoch, const u32* counts, u32* excl,
+                                                 const u32* base, int lane) {
+    const u64 tag = epoch << 34;
+    if (tile == 0) {
+        if (lane < (int)K) {
+            u32 b = base ? base[lane] : 0u;
+            excl[lane] = b;
+            st_relaxed(&state[lane], tag | TS_P | (u64)(b + counts[lane]));
+        }
+        __syncwarp();
+        return;
+    }
+    if (lane < (int)K) st_relaxed(&state[(u64)tile * MAXP + lane], tag | TS_A | (u64)counts[lane]);
+    for (u32 k = 0; k < K; k++) {
+        u32 sum = 0;
+        long long pred = (long long)tile - 1 - lane;
+        for (;;) {
+            u64 w;
+            if (pred >= 0) {
+                const u64* p = &state[(u64)pred * MAXP + k];
+                w = ld_relaxed(p);
+                while ((w >> 34) != epoch) { __nanosleep(32); w = ld_relaxed(p); }
+            } else {
+                w = tag | TS_P;  // virtual predecessor of tile 0
+            }
+            const bool is_p = ((w >> 32) & 3ull) == 2ull;
+            const unsigned pm = __ballot_sync(0xffffffffu, is_p);
+            const u32 v = (u32)w;
+            if (pm) {
+                const int first = __ffs(pm) - 1;  // nearest predecessor that already knows its full prefix
+                sum += warp_sum(lane <= first ? v : 0u);
+                break;
+            }
+            sum += warp_sum(v);
+            pred -= 32;
+        }
+        if (lane == 0) {
+            excl[k] = sum;
+            st_relaxed(&state[(u64)tile * MAXP + k], tag | TS_P | (u64)(sum + counts[k]));
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FILTER evaluation on the device. vals[slot] = id bound to the (remapped) slot.
+struct FilterOp {  // same layout as kb_filter_op
+    u32 op, slot, cmp, id;
+    double value;
+};
+static_assert(sizeof(FilterOp) == sizeof(kb_filter_op), "layout");
+
+struct NumTab {
+    const double* num_or0;
+    const u8* is_num;
+    u32 n_ids;
+};
+__device__ __forceinline__ double num_of(const NumTab& nt, u32 id) { return id < nt.n_ids ? __ldg(nt.num_or0 + id) : 0.0; }
+__device__ __forceinline__ bool isnum_of(const NumTab& nt, u32 id) { return id < nt.n_ids ? __ldg(nt.is_num + id) != 0 : false; }
+
+__device__ __forceinline__ bool cmp_num(u32 cmp, double a, double b) {
+    switch (cmp) {  // types.rs:133-148 — only the four ordering operators reach the numeric path
+        case KB_CMP_GT: return a > b;
+        case KB_CMP_GE: return a >= b;
+        case KB_CMP_LT: return a < b;
+        case KB_CMP_LE: return a <= b;
+        default: return false;
+    }
+}
+
+static __device__ __noinline__ bool eval_filter_general(const FilterOp* ops, u32 n_ops, const u32* vals, const NumTab& nt) {
+    double st[12];
+    u32 okm = 0;  // bit i: st[i] valid
+    int sp = 0;
+    for (u32 i = 0; i < n_ops; i++) {
+        const FilterOp op = ops[i];
+        switch (op.op) {
+            case KB_F_CMP_NUM: st[sp] = cmp_num(op.cmp, num_of(nt, vals[op.slot]), op.value) ? 1.0 : 0.0; okm |= 1u << sp; sp++; break;
+            case KB_F_EQ_ID: st[sp] = (op.id != EMPTY32 && vals[op.slot] == op.id) ? 1.0 : 0.0; okm |= 1u << sp; sp++; break;
+            case KB_F_NE_ID: st[sp] = (op.id == EMPTY32 || vals[op.slot] != op.id) ? 1.0 : 0.0; okm |= 1u << sp; sp++; break;
+            case KB_F_AND: sp--; st[sp - 1] = (st[sp - 1] != 0.0 && st[sp] != 0.0) ? 1.0 : 0.0; break;
+            case KB_F_OR: sp--; st[sp - 1] = (st[sp - 1] != 0.0 || st[sp] != 0.0) ? 1.0 : 0.0; break;
+            case KB_F_NOT: st[sp - 1] = (st[sp - 1] == 0.0) ? 1.0 : 0.0; break;
+            case KB_F_PUSH_VAR: {
+                u32 id = vals[op.slot];
+                st[sp] = num_of(nt, id);
+                if (isnum_of(nt, id)) okm |= 1u << sp; else okm &= ~(1u << sp);
+                sp++;
+            } break;
+            case KB_F_PUSH_CONST: st[sp] = op.value; okm |= 1u << sp; sp++; break;
+            case KB_F_ADD: case KB_F_SUB: case KB_F_MUL: case KB_F_DIV: {
+                sp--;
+                bool v = ((okm >> (sp - 1)) & 1u) && ((okm >> sp) & 1u);
+                double a = st[sp - 1], b = st[sp], r;
+                if (op.op == KB_F_ADD) r = a + b;
+                else if (op.op == KB_F_SUB) r = a - b;
+                else if (op.op == KB_F_MUL) r = a * b;
+                else { v = v && b != 0.0; r = v ? a / b : 0.0; }
+                st[sp - 1] = r;
+                if (v) okm |= 1u << (sp - 1); else okm &= ~(1u << (sp - 1));
+            } break;
+            case KB_F_TRUTHY: st[sp - 1] = (((okm >> (sp - 1)) & 1u) && st[sp - 1] != 0.0) ? 1.0 : 0.0; okm |= 1u << (sp - 1); break;
+            case KB_F_IS_TRIPLE: st[sp] = (vals[op.slot] & 0x80000000u) ? 1.0 : 0.0; okm |= 1u << sp; sp++; break;
+            default: return false;
+        }
+        if (sp > 11) return false;
+    }
+    return sp == 1 && st[0] != 0.0;
+}
+
+__device__ __forceinline__ bool eval_filter(const FilterOp* ops, u32 n_ops, const u32* vals, const NumTab& nt) {
+    if (n_ops == 0) return true;
+    if (n_ops == 1 && ops[0].op == KB_F_CMP_NUM)  // FILTER(?x > c): the common case, no stack machine
+        return cmp_num(ops[0].cmp, num_of(nt, vals[ops[0].slot]), ops[0].value);
+    return eval_filter_general(ops, n_ops, vals, nt);
+}
+
+}  // namespace kb

@@ -1,0 +1,139 @@
+// kb_internal.hpp — host-side state behind the C ABI (context, device buffers, relations, store segments).
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "kb_kernels.cuh"
+
+namespace kb {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaStream_t st = nullptr;
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+using Buf = std::shared_ptr<DevBuf>;
+
+struct Col {
+    Buf buf;            // owner (may be shared by views / projections)
+    u32* ptr = nullptr;  // 16-byte aligned, readable up to the next multiple of 256 B past the last row
+};
+
+enum Family { F_SCAN = 0, F_BUILD, F_PROBE, F_FILTER, F_GROUP, F_OTHER, F_COUNT };
+
+struct PendingTimer {
+    cudaEvent_t a, b;
+    int fam;
+};
+
+}  // namespace kb
+
+struct kb_rel {
+    std::vector<kb::u32> slots;
+    std::vector<kb::Col> cols;
+    kb::u64 n = 0;
+    int col_of(kb::u32 slot) const {
+        for (size_t i = 0; i < slots.size(); i++) if (slots[i] == slot) return (int)i;
+        return -1;
+    }
+};
+
+struct kb_groups {
+    std::vector<std::vector<kb::u32>> keys;
+    std::vector<std::vector<double>> vals;
+    std::vector<uint64_t> counts;
+};
+
+namespace kb {
+struct Segment {
+    u64 tag = 0;
+    Col s, p, o;
+    u64 n = 0;
+    cudaEvent_t ready = nullptr;  // set while a chunked upload is in flight: the scan waits on it
+};
+}  // namespace kb
+
+struct kb_ctx {
+    int device = 0;
+    int n_sms = 148;
+    cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr;
+    std::string err;
+    std::vector<kb::Segment> segs;
+    kb::u64 n_triples = 0;
+    kb::Buf num, isnum;
+    kb::u32 n_ids = 0;
+    // tile-state buffer of the look-back prefix (never cleared: words carry the launch epoch)
+    kb::Buf tile_state;
+    size_t tile_state_tiles = 0;
+    kb::u64 epoch = 1;
+    // control arena: small device words (tickets, totals, flags) zeroed at the start of every API call, mirrored in pinned memory
+    kb::u32* ctrl = nullptr;
+    kb::u32* h_ctrl = nullptr;
+    kb::u32 ctrl_used = 0;
+    static constexpr kb::u32 CTRL_WORDS = 8192;
+    // pinned staging for uploads / downloads
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    // timing
+    bool timing = false;
+    std::vector<kb::PendingTimer> timers;
+    std::vector<cudaEvent_t> ev_pool;
+    kb_stats stats{};
+    // knowledge cached across calls: (predicate, key position) pairs whose direct build met duplicate keys
+    std::set<std::pair<kb::u32, kb::u32>> multi_valued;
+    kb::u64 store_version = 0;
+};
+
+namespace kb {
+
+kb_status fail(kb_ctx* ctx, kb_status code, const char* fmt, ...);
+#define KB_CUDA(ctx, call)                                                                                             \
+    do {                                                                                                               \
+        cudaError_t _e = (call);                                                                                       \
+        if (_e != cudaSuccess) return kb::fail((ctx), KB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+#define KB_TRY(expr)                     \
+    do {                                 \
+        kb_status _s = (expr);           \
+        if (_s != KB_OK) return _s;      \
+    } while (0)
+
+kb_status alloc_buf(kb_ctx* ctx, size_t bytes, Buf* out);
+kb_status alloc_col(kb_ctx* ctx, u64 rows, Col* out);
+kb_status begin_call(kb_ctx* ctx);                      // zero the control arena
+u32 ctrl_alloc(kb_ctx* ctx, u32 words);                 // returns word offset into ctx->ctrl
+kb_status ctrl_read(kb_ctx* ctx);                       // D2H of the used part of the arena + stream sync
+kb_status ensure_tile_state(kb_ctx* ctx, u64 tiles);
+NumTab numtab(const kb_ctx* ctx);
+void timer_begin(kb_ctx* ctx, int fam);
+void timer_end(kb_ctx* ctx);
+void timers_flush(kb_ctx* ctx);  // after a stream sync
+
+// internal operators (device-resident, return relations whose row counts are known on the host)
+struct FilterProg {
+    std::vector<kb_filter_op> ops;
+};
+kb_status validate_filter(kb_ctx* ctx, const kb_filter_op* ops, u32 n);
+// split a postfix program into its top-level AND conjuncts
+bool split_conjuncts(const kb_filter_op* ops, u32 n, std::vector<FilterProg>* out);
+std::set<u32> filter_slots(const FilterProg& f);
+
+kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 n_pats, const std::vector<FilterProg>& pushdown, const int* stat_slot /*per pattern or -1*/,
+                    bool want_index, std::vector<std::unique_ptr<kb_rel>>* out, std::vector<u32>* kmin, std::vector<u32>* kmax);
+kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);
+kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const FilterProg* post, std::unique_ptr<kb_rel>* out);
+kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 n_pats, const kb_filter_op* filter, u32 n_ops,
+                         std::unique_ptr<kb_rel>* out);
+void pattern_vars(const kb_pattern& pt, std::vector<u32>* slots, std::vector<u32>* src);
+
+}  // namespace kb

@@ -1,0 +1,845 @@
+// kb_kernels.cu — hand-written sm_100a kernels of the Kolibrie hot path (see kb_kernels.cuh for what each replaces).
+// All of them are HBM-bound integer kernels: column tiles are staged global->shared with TMA bulk copies (cp.async.bulk +
+// mbarrier), matches are compacted with warp ballots, and output positions come from a single-pass decoupled look-back
+// prefix over tiles, so every kernel reads its input exactly once and writes a deterministic, input-ordered output.
+#include "kb_kernels.cuh"
+
+#include <math_constants.h>
+
+namespace kb {
+
+static inline u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
+
+static inline int grid_for(const void* kernel, int threads, size_t smem, int n_sms, u32 n_tiles) {
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long g = (long long)per_sm * n_sms;  // persistent: a whole number of resident CTAs per SM, all 148 SMs
+    if (g > (long long)n_tiles) g = n_tiles;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// =================================================================================================================
+// K_scan
+__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constant__ ScanParams P) {
+    extern __shared__ __align__(128) u32 smem[];
+    u32* sS = smem;
+    u32* sP = smem + SCAN_TILE;
+    u32* sO = smem + 2 * SCAN_TILE;
+    __shared__ __align__(8) u64 bar;
+    __shared__ u32 s_tile;
+    __shared__ u32 s_wcnt[SCAN_THREADS / 32][MAXP];
+    __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
+    __shared__ u32 s_min[MAXP], s_max[MAXP];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 K = P.K;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    if (tid < MAXP) { s_min[tid] = EMPTY32; s_max[tid] = 0u; }
+    u32 parity = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+        __syncthreads();  // publishes s_tile; also: every thread is done reading the previous tile's shared memory
+        const u32 tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const u32 base = tile * (u32)SCAN_TILE;
+        const u32 cnt = min((u32)SCAN_TILE, P.n - base);
+        if (tid == 0) {
+            const u32 bytes = (cnt * 4u + 15u) & ~15u;  // columns are padded to 256 B, so the rounded-up read stays in bounds
+            mbar_arrive_expect_tx(&bar, bytes * 3u);
+            tma_load_1d(sS, P.s + base, bytes, &bar);
+            tma_load_1d(sP, P.p + base, bytes, &bar);
+            tma_load_1d(sO, P.o + base, bytes, &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+
+        // ---- phase 1: evaluate every pattern on this thread's 8 triples; bit (k*8+j) = triple j matches pattern k
+        u64 bits = 0;
+#pragma unroll
+        for (int j = 0; j < SCAN_ITEMS; j++) {
+            const u32 idx = (u32)warp * (32u * SCAN_ITEMS) + (u32)j * 32u + (u32)lane;
+            const bool valid = idx < cnt;
+            const u32 s = sS[idx], p = sP[idx], o = sO[idx];
+            for (u32 k = 0; k < K; k++) {
+                const ScanPat& pt = P.pat[k];
+                const u32 f = pt.flags;
+                bool m = valid;
+                if (f & SP_HAS_P) m = m && (p == pt.cp);
+                if (f & SP_HAS_S) m = m && (s == pt.cs);
+                if (f & SP_HAS_O) m = m && (o == pt.co);
+                if (f & (SP_EQ_SP | SP_EQ_SO | SP_EQ_PO)) {
+                    if (f & SP_EQ_SP) m = m && (s == p);
+                    if (f & SP_EQ_SO) m = m && (s == o);
+                    if (f & SP_EQ_PO) m = m && (p == o);
+                }
+                if (pt.f_len != 0u && m) {
+                    u32 vals[3] = {s, p, o};
+                    m = eval_filter(P.ops + pt.f_begin, pt.f_len, vals, P.nt);
+                }
+                bits |= (u64)(m ? 1u : 0u) << (k * 8u + (u32)j);
+            }
+        }
+        for (u32 k = 0; k < K; k++) {
+            const u32 c = warp_sum((u32)__popc((u32)(bits >> (k * 8u)) & 0xFFu));
+            if (lane == 0) s_wcnt[warp][k] = c;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane < (int)K) {
+                u32 run = 0;
+#pragma unroll
+                for (int w = 0; w < SCAN_THREADS / 32; w++) {
+                    const u32 c = s_wcnt[w][lane];
+                    s_wcnt[w][lane] = run;
+                    run += c;
+                }
+                s_cnt[lane] = run;
+            }
+            __syncwarp();
+            tile_prefix_warp(P.tile_state, tile, K, P.epoch, s_cnt, s_excl, P.totals, lane);
+            if (tile == P.n_tiles - 1 && lane < (int)K) P.totals[lane] = s_excl[lane] + s_cnt[lane];
+        }
+        __syncthreads();
+
+        // ---- phase 2: ordered write of the matches (rank = tile prefix + warp prefix + ballot rank)
+        for (u32 k = 0; k < K; k++) {
+            const u32 mybits = (u32)(bits >> (k * 8u)) & 0xFFu;
+            if (__ballot_sync(0xffffffffu, mybits != 0u) == 0u) continue;
+            const ScanPat& pt = P.pat[k];
+            u32 pos = s_excl[k] + s_wcnt[warp][k];
+            u32 mn = EMPTY32, mx = 0u;
+#pragma unroll
+            for (int j = 0; j < SCAN_ITEMS; j++) {
+                const bool m = (mybits >> j) & 1u;
+                const unsigned b = __ballot_sync(0xffffffffu, m);
+                if (b == 0u) continue;
+                if (m) {
+                    const u32 idx = (u32)warp * (32u * SCAN_ITEMS) + (u32)j * 32u + (u32)lane;
+                    const u32 r = pos + (u32)__popc(b & lt_mask);
+                    const u32 vs = sS[idx], vp = sP[idx], vo = sO[idx];
+                    for (u32 c = 0; c < pt.n_out; c++) {
+                        const u32 src = pt.out_src[c];
+                        pt.out[c][r] = src == 0u ? vs : (src == 1u ? vp : (src == 2u ? vo : P.index_base + base + idx));
+                    }
+                    if (pt.stat_src < 3u) {
+                        const u32 kv = pt.stat_src == 0u ? vs : (pt.stat_src == 1u ? vp : vo);
+                        mn = min(mn, kv);
+                        mx = max(mx, kv);
+                    }
+                }
+                pos += (u32)__popc(b);
+            }
+            if (pt.stat_src < 3u) {
+                mn = __reduce_min_sync(0xffffffffu, mn);
+                mx = __reduce_max_sync(0xffffffffu, mx);
+                if (lane == 0) { atomicMin(&s_min[k], mn); atomicMax(&s_max[k], mx); }
+            }
+        }
+    }
+    __syncthreads();
+    if (tid < (int)K && P.pat[tid].stat_src < 3u && s_min[tid] != EMPTY32) {
+        atomicMin(&P.kmin[tid], s_min[tid]);
+        atomicMax(&P.kmax[tid], s_max[tid]);
+    }
+}
+
+void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    const size_t smem = 3 * SCAN_TILE * sizeof(u32);
+    const int grid = grid_for((const void*)scan_kernel, SCAN_THREADS, smem, n_sms, p.n_tiles);
+    scan_kernel<<<grid, SCAN_THREADS, smem, st>>>(p);
+}
+
+// =================================================================================================================
+// K_build
+__global__ void __launch_bounds__(256) build_direct_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals, u32 n,
+                                                           u32* __restrict__ table, u32 kmin, u32 range, u32* dup_flag) {
+    const u32 stride = gridDim.x * blockDim.x;
+    bool dup = false;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u32 off = keys[i] - kmin;
+        const u32 v = vals ? vals[i] : i;
+        if (off < range) {
+            const u32 old = atomicExch(&table[off], v);
+            dup = dup || (old != EMPTY32);
+        } else {
+            dup = true;  // cannot happen when kmin/range come from the scan statistics; treated like a duplicate -> rebuild chained
+        }
+    }
+    if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) *dup_flag = 1u;
+}
+void launch_build_direct(const u32* keys, const u32* vals, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, int n_sms,
+                         cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    build_direct_kernel<<<grid, 256, 0, st>>>(keys, vals, n, table, kmin, range, dup_flag);
+}
+
+__device__ __forceinline__ u32 key_tag(u32 n_keys, u32 k0, u32 k1, u32 k2, u32 k3) {
+    if (n_keys == 1u) return k0;  // ids are never EMPTY32
+    u32 h = mix32(k0) * 0x9E3779B1u ^ mix32(k1 + 0x7F4A7C15u);
+    if (n_keys > 2u) h = mix32(h ^ k2) * 0x85EBCA77u;
+    if (n_keys > 3u) h = mix32(h ^ k3) * 0xC2B2AE3Du;
+    return h == EMPTY32 ? 0x7FFFFFFEu : h;
+}
+
+__global__ void __launch_bounds__(256) build_chained_kernel(const ChainTab T, u32 n) {
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 mask = T.n_slots - 1u;
+    u32* words = reinterpret_cast<u32*>(T.slots);  // little-endian: word 2*slot = key tag, 2*slot+1 = head row
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u32 k0 = T.bkey[0][i];
+        const u32 k1 = T.n_keys > 1u ? T.bkey[1][i] : 0u;
+        const u32 k2 = T.n_keys > 2u ? T.bkey[2][i] : 0u;
+        const u32 k3 = T.n_keys > 3u ? T.bkey[3][i] : 0u;
+        const u32 tag = key_tag(T.n_keys, k0, k1, k2, k3);
+        u32 slot = mix32(tag) & mask;
+        for (;;) {
+            u32 cur = *reinterpret_cast<volatile u32*>(&words[2u * slot]);
+            if (cur == tag) break;
+            if (cur == EMPTY32) {
+                const u32 old = atomicCAS(&words[2u * slot], EMPTY32, tag);
+                if (old == EMPTY32 || old == tag) break;
+            }
+            slot = (slot + 1u) & mask;
+        }
+        T.next[i] = atomicExch(&words[2u * slot + 1u], i);
+    }
+}
+void launch_build_chained(const ChainTab& t, u32 n, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    build_chained_kernel<<<grid, 256, 0, st>>>(t, n);
+}
+
+// =================================================================================================================
+// K_probe (direct, fused multiway)
+template <int T>
+__global__ void __launch_bounds__(PROBE_THREADS) probe_direct_kernel(const __grid_constant__ ProbeDParams P) {
+    extern __shared__ __align__(128) u32 smem[];  // n_pcols tiles of PROBE_TILE
+    __shared__ __align__(8) u64 bar;
+    __shared__ u32 s_tile;
+    __shared__ u32 s_wcnt[PROBE_THREADS / 32];
+    __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
+    if (P.abort_flag != nullptr) {  // a direct build met duplicate keys: the host will redo this join with the chained operator
+        for (int t = 0; t < T; t++) if (reinterpret_cast<const volatile u32*>(P.abort_flag)[t] != 0u) return;
+    }
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    u32 parity = 0;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const u32* sKey = smem + P.key_col * PROBE_TILE;
+
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const u32 base = tile * (u32)PROBE_TILE;
+        const u32 cnt = min((u32)PROBE_TILE, P.n - base);
+        if (tid == 0) {
+            const u32 bytes = (cnt * 4u + 15u) & ~15u;
+            mbar_arrive_expect_tx(&bar, bytes * P.n_pcols);
+            for (u32 c = 0; c < P.n_pcols; c++) tma_load_1d(smem + c * PROBE_TILE, P.pcol[c] + base, bytes, &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+
+        // all table loads of this thread's rows are issued before any is consumed (ITEMS*T independent loads in flight)
+        u32 v[PROBE_ITEMS][T > 0 ? T : 1];
+#pragma unroll
+        for (int j = 0; j < PROBE_ITEMS; j++) {
+            const u32 idx = (u32)warp * (32u * PROBE_ITEMS) + (u32)j * 32u + (u32)lane;
+            const bool valid = idx < cnt;
+            const u32 key = sKey[idx];
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const u32 off = key - P.tab[t].kmin;
+                v[j][t] = (valid && off < P.tab[t].range) ? __ldg(P.tab[t].tab + off) : EMPTY32;
+            }
+            if (T == 0) v[j][0] = valid ? 0u : EMPTY32;
+        }
+        u32 mbits = 0;
+#pragma unroll
+        for (int j = 0; j < PROBE_ITEMS; j++) {
+            const u32 idx = (u32)warp * (32u * PROBE_ITEMS) + (u32)j * 32u + (u32)lane;
+            bool hit = true;
+#pragma unroll
+            for (int t = 0; t < (T > 0 ? T : 1); t++) hit = hit && (v[j][t] != EMPTY32);
+            if (hit && P.n_ops != 0u) {
+                u32 vals[KB_MAX_COLS];
+                for (u32 c = 0; c < P.n_out; c++) {
+                    const OutCol oc = P.oc[c];
+                    u32 x;
+                    if (oc.kind == OUT_PROBE) x = smem[oc.a * PROBE_TILE + idx];
+                    else {
+                        u32 tv = 0;
+#pragma unroll
+                        for (int t = 0; t < T; t++) if ((u32)t == oc.a) tv = v[j][t];
+                        x = oc.kind == OUT_TABVAL ? tv : __ldg(P.tab[oc.a].pay[oc.b] + tv);
+                    }
+                    vals[c] = x;
+                }
+                hit = eval_filter(P.ops, P.n_ops, vals, P.nt);
+            }
+            mbits |= (hit ? 1u : 0u) << j;
+        }
+        {
+            const u32 c = warp_sum((u32)__popc(mbits));
+            if (lane == 0) s_wcnt[warp] = c;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) {
+                u32 run = 0;
+#pragma unroll
+                for (int w = 0; w < PROBE_THREADS / 32; w++) {
+                    const u32 c = s_wcnt[w];
+                    s_wcnt[w] = run;
+                    run += c;
+                }
+                s_cnt[0] = run;
+            }
+            __syncwarp();
+            tile_prefix_warp(P.tile_state, tile, 1u, P.epoch, s_cnt, s_excl, nullptr, lane);
+            if (tile == P.n_tiles - 1 && lane == 0) *P.total = s_excl[0] + s_cnt[0];
+        }
+        __syncthreads();
+        if (__ballot_sync(0xffffffffu, mbits != 0u) != 0u) {
+            u32 pos = s_excl[0] + s_wcnt[warp];
+#pragma unroll
+            for (int j = 0; j < PROBE_ITEMS; j++) {
+                const bool m = (mbits >> j) & 1u;
+                const unsigned b = __ballot_sync(0xffffffffu, m);
+                if (b == 0u) continue;
+                const u32 r = pos + (u32)__popc(b & lt_mask);
+                if (m && r < P.cap) {
+                    const u32 idx = (u32)warp * (32u * PROBE_ITEMS) + (u32)j * 32u + (u32)lane;
+                    for (u32 c = 0; c < P.n_out; c++) {
+                        const OutCol oc = P.oc[c];
+                        u32 x;
+                        if (oc.kind == OUT_PROBE) x = smem[oc.a * PROBE_TILE + idx];
+                        else {
+                            u32 tv = 0;
+#pragma unroll
+                            for (int t = 0; t < T; t++) if ((u32)t == oc.a) tv = v[j][t];
+                            x = oc.kind == OUT_TABVAL ? tv : __ldg(P.tab[oc.a].pay[oc.b] + tv);
+                        }
+                        P.out[c][r] = x;
+                    }
+                }
+                pos += (u32)__popc(b);
+            }
+        }
+    }
+}
+
+void launch_probe_direct(const ProbeDParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    const size_t smem = (size_t)p.n_pcols * PROBE_TILE * sizeof(u32);
+    const void* fn = nullptr;
+    switch (p.T) {
+        case 0: fn = (const void*)probe_direct_kernel<0>; break;
+        case 1: fn = (const void*)probe_direct_kernel<1>; break;
+        case 2: fn = (const void*)probe_direct_kernel<2>; break;
+        case 3: fn = (const void*)probe_direct_kernel<3>; break;
+        default: fn = (const void*)probe_direct_kernel<4>; break;
+    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = grid_for(fn, PROBE_THREADS, smem, n_sms, p.n_tiles);
+    switch (p.T) {
+        case 0: probe_direct_kernel<0><<<grid, PROBE_THREADS, smem, st>>>(p); break;
+        case 1: probe_direct_kernel<1><<<grid, PROBE_THREADS, smem, st>>>(p); break;
+        case 2: probe_direct_kernel<2><<<grid, PROBE_THREADS, smem, st>>>(p); break;
+        case 3: probe_direct_kernel<3><<<grid, PROBE_THREADS, smem, st>>>(p); break;
+        default: probe_direct_kernel<4><<<grid, PROBE_THREADS, smem, st>>>(p); break;
+    }
+}
+
+// =================================================================================================================
+// K_probe (chained, binary, 1:N)
+__device__ __forceinline__ u32 warp_excl_scan(u32 v, int lane, u32* total) {
+    u32 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+// Walks the chain of probe row `idx` (tile-local) and calls emit(build_row) for every build row whose key columns equal the
+// probe row's and whose joined row passes the FILTER.
+template <class Emit>
+__device__ __forceinline__ void chain_walk(const ProbeCParams& P, const u32* smem, u32 idx, Emit&& emit) {
+    const ChainTab& T = P.tab;
+    u32 pk[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) pk[q] = (u32)q < T.n_keys ? smem[P.pkey[q] * PROBEC_TILE + idx] : 0u;
+    const u32 tag = key_tag(T.n_keys, pk[0], pk[1], pk[2], pk[3]);
+    const u32 mask = T.n_slots - 1u;
+    u32 slot = mix32(tag) & mask;
+    u32 head = EMPTY32;
+    for (;;) {
+        const u64 w = __ldg(reinterpret_cast<const unsigned long long*>(T.slots) + slot);
+        const u32 key = (u32)w;
+        if (key == tag) { head = (u32)(w >> 32); break; }
+        if (key == EMPTY32) break;
+        slot = (slot + 1u) & mask;
+    }
+    for (u32 r = head; r != EMPTY32; r = __ldg(T.next + r)) {
+        bool ok = true;
+        if (T.n_keys > 1u) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) if ((u32)q < T.n_keys) ok = ok && (__ldg(T.bkey[q] + r) == pk[q]);
+        }
+        if (ok && P.n_ops != 0u) {
+            u32 vals[KB_MAX_COLS];
+            for (u32 c = 0; c < P.n_pcols; c++) vals[c] = smem[c * PROBEC_TILE + idx];
+            for (u32 c = 0; c < P.n_bpay; c++) vals[P.n_pcols + c] = __ldg(P.bpay[c] + r);
+            ok = eval_filter(P.ops, P.n_ops, vals, P.nt);
+        }
+        if (ok) emit(r);
+    }
+}
+
+__global__ void __launch_bounds__(PROBEC_THREADS) probe_chained_kernel(const __grid_constant__ ProbeCParams P) {
+    extern __shared__ __align__(128) u32 smem[];
+    __shared__ __align__(8) u64 bar;
+    __shared__ u32 s_tile;
+    __shared__ u32 s_wcnt[PROBEC_THREADS / 32];
+    __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    u32 parity = 0;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const u32 base = tile * (u32)PROBEC_TILE;
+        const u32 cnt = min((u32)PROBEC_TILE, P.n - base);
+        if (tid == 0) {
+            const u32 bytes = (cnt * 4u + 15u) & ~15u;
+            mbar_arrive_expect_tx(&bar, bytes * P.n_pcols);
+            for (u32 c = 0; c < P.n_pcols; c++) tma_load_1d(smem + c * PROBEC_TILE, P.pcol[c] + base, bytes, &bar);
+        }
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+
+        u32 mc[PROBEC_ITEMS];
+        u32 tsum = 0;
+#pragma unroll
+        for (int j = 0; j < PROBEC_ITEMS; j++) {
+            const u32 idx = (u32)warp * (32u * PROBEC_ITEMS) + (u32)j * 32u + (u32)lane;
+            u32 c = 0;
+            if (idx < cnt) chain_walk(P, smem, idx, [&](u32) { c++; });
+            mc[j] = c;
+            tsum += c;
+        }
+        {
+            const u32 c = warp_sum(tsum);
+            if (lane == 0) s_wcnt[warp] = c;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            if (lane == 0) {
+                u32 run = 0;
+#pragma unroll
+                for (int w = 0; w < PROBEC_THREADS / 32; w++) {
+                    const u32 c = s_wcnt[w];
+                    s_wcnt[w] = run;
+                    run += c;
+                }
+                s_cnt[0] = run;
+            }
+            __syncwarp();
+            tile_prefix_warp(P.tile_state, tile, 1u, P.epoch, s_cnt, s_excl, nullptr, lane);
+            if (tile == P.n_tiles - 1 && lane == 0) *P.total = s_excl[0] + s_cnt[0];
+        }
+        __syncthreads();
+        u32 pos = s_excl[0] + s_wcnt[warp];
+#pragma unroll
+        for (int j = 0; j < PROBEC_ITEMS; j++) {
+            u32 tot;
+            const u32 ex = warp_excl_scan(mc[j], lane, &tot);
+            if (mc[j] != 0u) {
+                const u32 idx = (u32)warp * (32u * PROBEC_ITEMS) + (u32)j * 32u + (u32)lane;
+                u32 r = pos + ex;
+                chain_walk(P, smem, idx, [&](u32 br) {
+                    if (r < P.cap) {
+                        for (u32 c = 0; c < P.n_pcols; c++) P.out[c][r] = smem[c * PROBEC_TILE + idx];
+                        for (u32 c = 0; c < P.n_bpay; c++) P.out[P.n_pcols + c][r] = __ldg(P.bpay[c] + br);
+                    }
+                    r++;
+                });
+            }
+            pos += tot;
+        }
+    }
+}
+
+void launch_probe_chained(const ProbeCParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    const size_t smem = (size_t)p.n_pcols * PROBEC_TILE * sizeof(u32);
+    const int grid = grid_for((const void*)probe_chained_kernel, PROBEC_THREADS, smem, n_sms, p.n_tiles);
+    probe_chained_kernel<<<grid, PROBEC_THREADS, smem, st>>>(p);
+}
+
+// cartesian product: output row (i*nr + j) = left row i ++ right row j (engine.rs:1054-1071)
+struct CartParams {
+    const u32* l[KB_MAX_COLS];
+    const u32* r[KB_MAX_COLS];
+    u32* out[KB_MAX_COLS];
+    u32 nl, nr, n_l, n_r;
+};
+__global__ void cartesian_kernel(const CartParams P) {
+    const u64 total = (u64)P.nl * P.nr;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (u64)gridDim.x * blockDim.x) {
+        const u32 li = (u32)(i / P.nr), ri = (u32)(i % P.nr);
+        for (u32 c = 0; c < P.n_l; c++) P.out[c][i] = P.l[c][li];
+        for (u32 c = 0; c < P.n_r; c++) P.out[P.n_l + c][i] = P.r[c][ri];
+    }
+}
+void launch_cartesian(const u32* const* lcols, u32 nl, u32 n_lcols, const u32* const* rcols, u32 nr, u32 n_rcols, u32* const* out,
+                      cudaStream_t st) {
+    CartParams P;
+    P.nl = nl; P.nr = nr; P.n_l = n_lcols; P.n_r = n_rcols;
+    for (u32 c = 0; c < n_lcols; c++) P.l[c] = lcols[c];
+    for (u32 c = 0; c < n_rcols; c++) P.r[c] = rcols[c];
+    for (u32 c = 0; c < n_lcols + n_rcols; c++) P.out[c] = out[c];
+    const u64 total = (u64)nl * nr;
+    if (total == 0) return;
+    int grid = (int)umin64((u64)148 * 8, (total + 255) / 256);
+    cartesian_kernel<<<grid, 256, 0, st>>>(P);
+}
+
+// =================================================================================================================
+// K_group
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (v < __longlong_as_double((long long)old) || __longlong_as_double((long long)old) != __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (v > __longlong_as_double((long long)old) || __longlong_as_double((long long)old) != __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+
+__global__ void group_init_kernel(const GroupParams P) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_slots; i += stride) {
+        P.gstate[i] = 0u;
+        P.gcnt[i] = 0ull;
+        for (u32 a = 0; a < P.n_aggs; a++)
+            P.gval[(u64)i * 8 + a] = P.akind[a] == KB_AGG_MIN ? CUDART_INF : (P.akind[a] == KB_AGG_MAX ? -CUDART_INF : 0.0);
+    }
+}
+void launch_group_init(const GroupParams& p, cudaStream_t st) {
+    int grid = (int)umin64((u64)148 * 4, ((u64)p.n_slots + 255) / 256);
+    group_init_kernel<<<grid, 256, 0, st>>>(p);
+}
+
+// find-or-insert the group of key k[] in the global table; returns slot or EMPTY32 on overflow
+__device__ __forceinline__ u32 group_slot(const GroupParams& P, const u32* k) {
+    u32 h = 0x9E3779B9u;
+    for (u32 c = 0; c < P.n_gcols; c++) h = mix32(h ^ k[c]) * 0x85EBCA77u + c;
+    const u32 mask = P.n_slots - 1u;
+    u32 slot = mix32(h) & mask;
+    for (u32 probes = 0; probes < P.n_slots; probes++) {
+        u32 st = atomicCAS(&P.gstate[slot], 0u, 1u);
+        if (st == 0u) {
+            for (u32 c = 0; c < P.n_gcols; c++) P.gkeys[(u64)slot * 4 + c] = k[c];
+            __threadfence();
+            atomicExch(&P.gstate[slot], 2u);
+            return slot;
+        }
+        while (st == 1u) st = *reinterpret_cast<volatile u32*>(&P.gstate[slot]);
+        __threadfence();
+        bool eq = true;
+        for (u32 c = 0; c < P.n_gcols; c++) eq = eq && (*reinterpret_cast<volatile u32*>(&P.gkeys[(u64)slot * 4 + c]) == k[c]);
+        if (eq) return slot;
+        slot = (slot + 1u) & mask;
+    }
+    return EMPTY32;
+}
+
+// One warp pre-aggregates its 32 rows per distinct group (__match_any_sync) so a GROUP BY with a handful of groups does
+// not serialise on a handful of addresses; leaders then update the global table.
+__global__ void __launch_bounds__(256) group_kernel(const __grid_constant__ GroupParams P) {
+    const int lane = threadIdx.x & 31;
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 n_round = (P.n + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool valid = i < P.n;
+        u32 k[4] = {0, 0, 0, 0};
+        u32 h = 0;
+        if (valid) for (u32 c = 0; c < P.n_gcols; c++) { k[c] = P.gcol[c][i]; h = mix32(h ^ k[c]) + c; }
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        // lanes with the same full key form a group: match on the hash, then confirm equality with the leader
+        unsigned peers = __match_any_sync(act, h);
+        int leader = __ffs(peers) - 1;
+        bool same = true;
+        for (u32 c = 0; c < P.n_gcols; c++) same = same && (__shfl_sync(peers, k[c], leader) == k[c]);
+        // rare hash collision inside a warp: lanes that differ from their leader go alone
+        const unsigned agree = __ballot_sync(act, same);
+        peers = same ? (peers & agree) : (1u << lane);
+        leader = __ffs(peers) - 1;
+        double val[8];
+        for (u32 a = 0; a < P.n_aggs; a++) val[a] = P.acol[a] ? num_of(P.nt, P.acol[a][i]) : 0.0;
+        // leader folds its peers
+        unsigned long long cnt = (unsigned long long)__popc(peers);
+        for (u32 a = 0; a < P.n_aggs; a++) {
+            double acc = val[a];
+            unsigned rest = peers & ~(1u << leader);
+            // every peer lane must take part in the shuffles: iterate over the same mask in all lanes of the group
+            while (rest) {
+                const int src = __ffs(rest) - 1;
+                rest &= rest - 1u;
+                const double o = __shfl_sync(peers, val[a], src);
+                if (P.akind[a] == KB_AGG_MIN) acc = fmin(acc, o);
+                else if (P.akind[a] == KB_AGG_MAX) acc = fmax(acc, o);
+                else acc += o;
+            }
+            val[a] = acc;
+        }
+        if (lane == leader) {
+            const u32 slot = group_slot(P, k);
+            if (slot == EMPTY32) { *P.overflow = 1u; continue; }
+            atomicAdd(&P.gcnt[slot], cnt);
+            for (u32 a = 0; a < P.n_aggs; a++) {
+                double* dst = &P.gval[(u64)slot * 8 + a];
+                if (P.akind[a] == KB_AGG_MIN) atomic_min_f64(dst, val[a]);
+                else if (P.akind[a] == KB_AGG_MAX) atomic_max_f64(dst, val[a]);
+                else if (P.akind[a] != KB_AGG_COUNT) atomicAdd(dst, val[a]);
+            }
+        }
+    }
+}
+void launch_group(const GroupParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)p.n + 255ull) / 256ull);
+    group_kernel<<<grid, 256, 0, st>>>(p);
+}
+
+// =================================================================================================================
+// Datalog: known-fact set with 96-bit keys in 16-byte slots {s,p,o,state}
+__device__ __forceinline__ u32 set_hash(u32 s, u32 p, u32 o) { return mix32(mix32(s) * 0x9E3779B1u ^ mix32(o + 0x632BE5ABu) ^ (p * 0x85EBCA77u)); }
+
+// returns 1 if (s,p,o) was inserted now, 0 if it was already there, 2 on overflow
+__device__ __forceinline__ u32 set_insert(uint4* set, u32 n_slots, u32 s, u32 p, u32 o) {
+    const u32 mask = n_slots - 1u;
+    u32 slot = set_hash(s, p, o) & mask;
+    for (u32 probes = 0; probes < n_slots; probes++) {
+        u32* st_ptr = &reinterpret_cast<u32*>(&set[slot])[3];
+        u32 st = atomicCAS(st_ptr, 0u, 1u);
+        if (st == 0u) {
+            u32* w = reinterpret_cast<u32*>(&set[slot]);
+            w[0] = s; w[1] = p; w[2] = o;
+            __threadfence();
+            atomicExch(st_ptr, 2u);
+            return 1u;
+        }
+        while (st == 1u) st = *reinterpret_cast<volatile u32*>(st_ptr);
+        __threadfence();
+        const volatile u32* w = reinterpret_cast<const volatile u32*>(&set[slot]);
+        if (w[0] == s && w[1] == p && w[2] == o) return 0u;
+        slot = (slot + 1u) & mask;
+    }
+    return 2u;
+}
+
+__global__ void __launch_bounds__(256) set_insert_kernel(uint4* set, u32 set_slots, const u32* s, const u32* p, u32 p_const, const u32* o,
+                                                         u32 n, u32* overflow) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (set_insert(set, set_slots, s[i], p ? p[i] : p_const, o[i]) == 2u) *overflow = 1u;
+}
+void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p, u32 p_const, const u32* o, u32 n, u32* overflow, int n_sms,
+                       cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    set_insert_kernel<<<grid, 256, 0, st>>>(set, set_slots, s, p, p_const, o, n, overflow);
+}
+
+__device__ __forceinline__ bool rule_filters_pass(const DeriveParams& P, u32 i) {
+    for (u32 f = 0; f < P.n_filt; f++) {
+        const RuleFilterDev fl = P.filt[f];
+        const u32 lhs = P.bcol[fl.lhs_col][i];
+        if (fl.rhs_is_var) {  // rules.rs:141-146 — ids of two bound variables; only = / != act
+            const u32 rhs = P.bcol[fl.rhs_col][i];
+            if (fl.cmp == KB_CMP_NE && lhs == rhs) return false;
+            if (fl.cmp == KB_CMP_EQ && lhs != rhs) return false;
+        } else {  // rules.rs:148-160
+            const double a = num_of(P.nt, lhs), c = fl.rhs_value;
+            const double eps = 2.220446049250313e-16;
+            switch (fl.cmp) {
+                case KB_CMP_GT: if (a <= c) return false; break;
+                case KB_CMP_LT: if (a >= c) return false; break;
+                case KB_CMP_GE: if (a < c) return false; break;
+                case KB_CMP_LE: if (a > c) return false; break;
+                case KB_CMP_EQ: if (fabs(a - c) > eps) return false; break;
+                case KB_CMP_NE: if (fabs(a - c) <= eps) return false; break;
+                default: break;
+            }
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) derive_kernel(const __grid_constant__ DeriveParams P) {
+    const int lane = threadIdx.x & 31;
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 n_round = (P.n + 31u) & ~31u;
+    unsigned long long nd = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        const bool pass = i < P.n && rule_filters_pass(P, i);
+        for (u32 h = 0; h < P.n_heads; h++) {
+            bool fresh = false;
+            u32 s = 0, p = 0, o = 0;
+            if (pass) {
+                nd++;
+                s = P.head[h][0].is_var ? P.bcol[P.head[h][0].value][i] : P.head[h][0].value;
+                p = P.head[h][1].is_var ? P.bcol[P.head[h][1].value][i] : P.head[h][1].value;
+                o = P.head[h][2].is_var ? P.bcol[P.head[h][2].value][i] : P.head[h][2].value;
+                const u32 r = set_insert(P.set, P.set_slots, s, p, o);
+                if (r == 2u) *P.overflow = 1u;
+                fresh = r == 1u;
+            }
+            // warp-aggregated append of the facts that were new
+            const unsigned b = __ballot_sync(0xffffffffu, fresh);
+            if (b) {
+                u32 basepos = 0;
+                if (lane == __ffs(b) - 1) basepos = atomicAdd(P.out_count, (u32)__popc(b));
+                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(b) - 1);
+                if (fresh) {
+                    const u32 r = basepos + (u32)__popc(b & ((1u << lane) - 1u));
+                    if (r < P.out_cap) { P.out_s[r] = s; P.out_p[r] = p; P.out_o[r] = o; }
+                    else *P.overflow = 1u;
+                }
+            }
+        }
+    }
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 16);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 8);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 4);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 2);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 1);
+    if (lane == 0 && nd) atomicAdd(P.n_deriv, nd);
+}
+void launch_derive(const DeriveParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)p.n + 255ull) / 256ull);
+    derive_kernel<<<grid, 256, 0, st>>>(p);
+}
+
+// =================================================================================================================
+// utilities
+__global__ void fill_kernel(u32* p, u32 v, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_u32(u32* p, u32 v, u64 n, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)148 * 8, (n + 255) / 256);
+    fill_kernel<<<grid, 256, 0, st>>>(p, v, n);
+}
+void launch_fill_const_col(u32* p, u32 v, u64 n, cudaStream_t st) { launch_fill_u32(p, v, n, st); }
+
+__global__ void __launch_bounds__(256) part_count_kernel(const u32* key, u32 n, u32 n_parts, u32* counts) {
+    __shared__ u32 sc[64];
+    if (threadIdx.x < 64) sc[threadIdx.x] = 0;
+    __syncthreads();
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sc[mix32(key[i]) % n_parts], 1u);
+    __syncthreads();
+    if (threadIdx.x < n_parts && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
+}
+void launch_part_count(const u32* key, u32 n, u32 n_parts, u32* counts, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + 255ull) / 256ull);
+    part_count_kernel<<<grid, 256, 0, st>>>(key, n, n_parts, counts);
+}
+struct PartScatterParams {
+    const u32* in[KB_MAX_COLS];
+    u32* out[KB_MAX_COLS];
+    u32 n_cols;
+};
+__global__ void __launch_bounds__(256) part_scatter_kernel(const u32* key, u32 n, u32 n_parts, u32* cursors, const PartScatterParams P) {
+    const int lane = threadIdx.x & 31;
+    const u32 n_round = (n + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        const u32 part = valid ? mix32(key[i]) % n_parts : 0xFFFFu;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        const unsigned peers = __match_any_sync(act, part);
+        const int leader = __ffs(peers) - 1;
+        u32 basepos = 0;
+        if (lane == leader) basepos = atomicAdd(&cursors[part], (u32)__popc(peers));
+        basepos = __shfl_sync(peers, basepos, leader);
+        const u32 r = basepos + (u32)__popc(peers & ((1u << lane) - 1u));
+        for (u32 c = 0; c < P.n_cols; c++) P.out[c][r] = P.in[c][i];
+    }
+}
+void launch_part_scatter(const u32* key, u32 n, u32 n_parts, u32* cursors, const u32* const* in_cols, u32* const* out_cols, u32 n_cols,
+                         int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    PartScatterParams P;
+    P.n_cols = n_cols;
+    for (u32 c = 0; c < n_cols; c++) { P.in[c] = in_cols[c]; P.out[c] = out_cols[c]; }
+    int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + 255ull) / 256ull);
+    part_scatter_kernel<<<grid, 256, 0, st>>>(key, n, n_parts, cursors, P);
+}
+
+// kb_store_delete: p_out[i] = p[i], or EMPTY32 when (s,p,o)[i] is in the delete set; a scan with a variable predicate and
+// NE_ID(EMPTY32)... is not needed: the store compaction simply rescans with pattern (?s ?p ?o) over (s, p_out, o) and drops
+// rows whose predicate became EMPTY32 (KB_ID_NONE is never a real predicate).
+__global__ void __launch_bounds__(256) delete_mark_kernel(const u32* s, const u32* p, const u32* o, u32 n, const uint4* set, u32 set_slots,
+                                                          u32* p_out) {
+    const u32 mask = set_slots - 1u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 vs = s[i], vp = p[i], vo = o[i];
+        u32 slot = set_hash(vs, vp, vo) & mask;
+        bool found = false;
+        for (u32 probes = 0; probes < set_slots; probes++) {
+            const uint4 e = set[slot];
+            if (e.w == 0u) break;
+            if (e.x == vs && e.y == vp && e.z == vo) { found = true; break; }
+            slot = (slot + 1u) & mask;
+        }
+        p_out[i] = found ? EMPTY32 : vp;
+    }
+}
+void launch_delete_mark(const u32* s, const u32* p, const u32* o, u32 n, const uint4* set, u32 set_slots, u32* p_out, int n_sms,
+                        cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    delete_mark_kernel<<<grid, 256, 0, st>>>(s, p, o, n, set, set_slots, p_out);
+}
+
+}  // namespace kb

@@ -1,0 +1,188 @@
+// kb_kernels.cuh — parameter blocks and launch wrappers of the sm_100a kernels (definitions in kb_kernels.cu).
+#pragma once
+#include "kb_device.cuh"
+
+namespace kb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_scan: fused multi-pattern triple scan + constant filter + pushed-down FILTER + ordered compaction.
+// Replaces execute_table_scan_with_ids (engine.rs:510-584), the index scans (engine.rs:1192-1407), QueryBuilder's
+// Exact filter scan (query_builder.rs:486-531) and the reference's hash_join_kernel (cuda_join.cu:26-45).
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 triples = 24 KB of shared memory per CTA
+
+enum : u32 {
+    SP_HAS_S = 1, SP_HAS_P = 2, SP_HAS_O = 4,   // constant in that position
+    SP_EQ_SP = 8, SP_EQ_SO = 16, SP_EQ_PO = 32  // same variable twice in one pattern (quirk Q4: enforced)
+};
+struct ScanPat {
+    u32 cs, cp, co;
+    u32 flags;
+    u32 n_out;
+    u32 out_src[3];  // 0=s 1=p 2=o 3=global triple index (legacy FFI)
+    u32* out[3];
+    u32 f_begin, f_len;  // pushed-down FILTER program (slots = positions 0/1/2)
+    u32 stat_src;        // position whose min/max is tracked (the join key), 3 = none
+};
+struct ScanParams {
+    const u32 *s, *p, *o;
+    u32 n, n_tiles, K;
+    u32 index_base;  // global index of this segment's first triple
+    ScanPat pat[MAXP];
+    FilterOp ops[KB_MAX_FILTER_OPS];
+    NumTab nt;
+    u64* tile_state;
+    u32* ticket;
+    u64 epoch;
+    u32* totals;  // [MAXP] in: rows written by earlier segments; out: rows written so far
+    u32* kmin;    // [MAXP]
+    u32* kmax;    // [MAXP]
+};
+void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_build
+// DIRECT: dense dictionary ids make the identity a perfect hash: table[key - kmin] = payload (u32, EMPTY32 = none).
+void launch_build_direct(const u32* keys, const u32* vals /*null: row index*/, u32 n, u32* table, u32 kmin, u32 range,
+                         u32* dup_flag, int n_sms, cudaStream_t st);
+// CHAINED multimap: open-addressing slots {key tag, head row} + next[] chains. Insert cost is O(1) whatever the key
+// multiplicity (1:N joins and heavy hitters of the Datalog joins).
+struct ChainTab {
+    u64* slots;   // lo 32: key tag (EMPTY32 free), hi 32: head row index (EMPTY32 = end)
+    u32 n_slots;  // power of two
+    u32* next;    // [n_build]
+    u32 n_keys;   // 1..4 key columns; tag = key itself when n_keys==1 else a 32-bit mix of all
+    const u32* bkey[4];
+};
+void launch_build_chained(const ChainTab& t, u32 n, int n_sms, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_probe (direct, fused multiway): one probe stream against T<=4 direct tables + FILTER + ordered compaction.
+// Replaces execute_star_join_with_ids (engine.rs:587-691) / bind-join chains (engine.rs:840-885) on unique keys.
+constexpr int PROBE_THREADS = 256;
+constexpr int PROBE_ITEMS = 4;
+constexpr int PROBE_TILE = PROBE_THREADS * PROBE_ITEMS;  // 1024 rows
+constexpr int MAXT = 4;
+
+struct DirectTab {
+    const u32* tab;
+    u32 kmin, range;
+    u32 mode;  // 0: payload is a value column  1: payload is a build-row index (gather pay[])  2: existence only
+    u32 n_pay;
+    const u32* pay[2];
+};
+enum : u32 { OUT_PROBE = 0, OUT_TABVAL = 1, OUT_TABPAY = 2 };
+struct OutCol {
+    u32 kind, a, b;  // OUT_PROBE: a = probe column; OUT_TABVAL: a = table; OUT_TABPAY: a = table, b = payload column
+};
+struct ProbeDParams {
+    const u32* pcol[KB_MAX_COLS];
+    u32 n_pcols, key_col, n, n_tiles, T;
+    DirectTab tab[MAXT];
+    u32 n_out;
+    OutCol oc[KB_MAX_COLS];
+    u32* out[KB_MAX_COLS];
+    u32 cap;
+    FilterOp ops[KB_MAX_FILTER_OPS];  // slots = output column indices
+    u32 n_ops;
+    NumTab nt;
+    u64* tile_state;
+    u32* ticket;
+    u64 epoch;
+    u32* total;
+    const u32* abort_flag;  // non-null: exit immediately if *abort_flag != 0 (a direct build met duplicate keys)
+};
+void launch_probe_direct(const ProbeDParams& p, int n_sms, cudaStream_t st);
+
+// K_probe (chained, binary): general natural join with 1:N matches, multi-column keys, FILTER, ordered compaction.
+// Replaces execute_optimized_hash_join_with_ids / execute_hash_join_with_ids / merge join (engine.rs:710-811, 970-1039) and
+// perform_hash_join_for_rules (shared/src/join_algorithm.rs:499-677).
+constexpr int PROBEC_THREADS = 256;
+constexpr int PROBEC_ITEMS = 2;
+constexpr int PROBEC_TILE = PROBEC_THREADS * PROBEC_ITEMS;
+struct ProbeCParams {
+    const u32* pcol[KB_MAX_COLS];
+    u32 n_pcols, n, n_tiles;
+    u32 pkey[4];  // probe columns matching tab.bkey[]
+    ChainTab tab;
+    u32 n_bpay;
+    const u32* bpay[KB_MAX_COLS];  // build columns appended to the output
+    u32 n_out;                      // = n_pcols + n_bpay
+    u32* out[KB_MAX_COLS];
+    u32 cap;
+    FilterOp ops[KB_MAX_FILTER_OPS];
+    u32 n_ops;
+    NumTab nt;
+    u64* tile_state;
+    u32* ticket;
+    u64 epoch;
+    u32* total;
+};
+void launch_probe_chained(const ProbeCParams& p, int n_sms, cudaStream_t st);
+
+// cartesian product (engine.rs:1054-1071) — small inputs only
+void launch_cartesian(const u32* const* lcols, u32 nl, u32 n_lcols, const u32* const* rcols, u32 nr, u32 n_rcols, u32* const* out,
+                      cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// K_group: hash aggregate (execute_query.rs:1150-1227)
+struct GroupParams {
+    const u32* gcol[4];
+    u32 n_gcols;
+    const u32* acol[8];  // null for COUNT
+    u32 akind[8];
+    u32 n_aggs;
+    u32 n;
+    NumTab nt;
+    // global group table
+    u32 n_slots;   // power of two
+    u32* gkeys;    // [n_slots][4] (EMPTY32 in [.,0] lane = free is tracked by gstate)
+    u32* gstate;   // [n_slots] 0 free, 1 being written, 2 ready
+    double* gval;  // [n_slots][8]
+    unsigned long long* gcnt;  // [n_slots]
+    u32* overflow;
+};
+void launch_group(const GroupParams& p, int n_sms, cudaStream_t st);
+void launch_group_init(const GroupParams& p, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// Datalog: instantiate rule heads from binding columns, apply rule filters (rules.rs:133-165), insert into the
+// known-facts set (96-bit keys) and append the facts that were new (infer_generic.rs:42-48).
+struct HeadTerm { u32 is_var, value; };  // value = binding column index or constant id
+struct RuleFilterDev { u32 lhs_col, cmp, rhs_is_var, rhs_col; double rhs_value; };
+struct DeriveParams {
+    const u32* bcol[KB_MAX_COLS];
+    u32 n;
+    HeadTerm head[KB_MAX_CONCLUSIONS][3];
+    u32 n_heads;
+    RuleFilterDev filt[KB_MAX_RULE_FILTERS];
+    u32 n_filt;
+    NumTab nt;
+    // known-fact set: 16-byte slots {s,p,o,state}; state 0 free / 1 claimed-being-written / 2 ready
+    uint4* set;
+    u32 set_slots;  // power of two
+    // append targets
+    u32 *out_s, *out_p, *out_o;
+    u32 out_cap;
+    u32* out_count;               // appended so far (atomic cursor)
+    unsigned long long* n_deriv;  // candidates that passed the filters
+    u32* overflow;                // set or output overflow
+};
+void launch_derive(const DeriveParams& p, int n_sms, cudaStream_t st);
+void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p /*null: p_const*/, u32 p_const, const u32* o, u32 n, u32* overflow,
+                       int n_sms, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// small utilities
+void launch_fill_u32(u32* p, u32 v, u64 n, cudaStream_t st);
+void launch_fill_const_col(u32* p, u32 v, u64 n, cudaStream_t st);
+// partition rows by mix32(key) % n_parts (multi-GPU shuffle): count then scatter
+void launch_part_count(const u32* key, u32 n, u32 n_parts, u32* counts, int n_sms, cudaStream_t st);
+void launch_part_scatter(const u32* key, u32 n, u32 n_parts, u32* cursors, const u32* const* in_cols, u32* const* out_cols, u32 n_cols,
+                         int n_sms, cudaStream_t st);
+// mark rows of a segment that equal any triple of a (small) delete set held in a 96-bit set; then compaction is a scan with flags
+void launch_delete_mark(const u32* s, const u32* p, const u32* o, u32 n, const uint4* set, u32 set_slots, u32* p_out /*p with EMPTY32 where deleted*/,
+                        int n_sms, cudaStream_t st);
+
+}  // namespace kb

@@ -1,0 +1,451 @@
+"""Python mirror of the reference's host-side interfaces for the hot path, on top of the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (paths relative to /root/reference):
+
+* `Dictionary`            — shared/src/dictionary.rs:17-51 (ids dense from 0 in first-seen order)
+* `Term`/`TriplePattern`  — shared/src/terms.rs:13-23
+* `PhysicalOperator`      — kolibrie/src/streamertail_optimizer/operators/physical.rs:16-76 (the operators on the hot path)
+* `ExecutionEngine`       — kolibrie/src/streamertail_optimizer/execution/engine.rs:27,54 (`execute`, `execute_with_ids`)
+* `Condition`             — kolibrie/src/streamertail_optimizer/types.rs:110-186 (FILTER expressions)
+* `SparqlDatabase`        — kolibrie/src/sparql_database.rs:49-60,215-258,3364-3394 (triples + dictionary + build_all_indexes)
+* `Rule`/`FilterCondition`/`Reasoner` — shared/src/rule.rs:14-25, datalog/src/reasoning.rs:31-38,60-100,
+                            datalog/src/reasoning/materialisation/semi_naive.rs:89, my_naive.rs:74
+
+The canonical C++ mirror (the reference is compiled code) is kolibrie_b200/host/kolibrie_host.hpp; this module exists because
+pytest, bench.py and torch.distributed live in Python. All work is done by libkolibrie_b200.so — there is no CPU path here.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import capi as c
+
+# ---------------------------------------------------------------------------------------------------------------------
+_RUST_F64 = re.compile(r"^[+-]?(?:(?:inf|infinity|nan)|(?:(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?))$", re.IGNORECASE)
+_RUST_F64_SPECIAL = re.compile(r"^[+-]?(?:inf|infinity|nan)$", re.IGNORECASE)
+
+
+def rust_parse_f64(s: str) -> Optional[float]:
+    """`str::parse::<f64>()` acceptance of Rust (no whitespace, no '_', no hex; inf/infinity/nan in any case; '5.', '.5', '1e5')."""
+    if not isinstance(s, str) or not s.isascii() or not _RUST_F64.match(s):
+        return None
+    if _RUST_F64_SPECIAL.match(s):
+        return float(s)  # Python accepts the same special spellings
+    return float(s)
+
+
+class Dictionary:
+    def __init__(self):
+        self.string_to_id: Dict[str, int] = {}
+        self.id_to_string: List[str] = []
+
+    def encode(self, value: str) -> int:
+        i = self.string_to_id.get(value)
+        if i is None:
+            i = len(self.id_to_string)
+            assert i < 0x8000_0000, "Dictionary ID space exhausted"  # dictionary.rs:36-40
+            self.string_to_id[value] = i
+            self.id_to_string.append(value)
+        return i
+
+    def lookup(self, value: str) -> Optional[int]:
+        return self.string_to_id.get(value)
+
+    def decode(self, i: int) -> Optional[str]:
+        return self.id_to_string[i] if 0 <= i < len(self.id_to_string) else None
+
+    def numeric_table(self) -> Tuple[np.ndarray, np.ndarray]:
+        n = len(self.id_to_string)
+        num = np.zeros(n, dtype=np.float64)
+        isn = np.zeros(n, dtype=np.uint8)
+        for i, s in enumerate(self.id_to_string):
+            v = rust_parse_f64(s)
+            if v is not None:
+                num[i] = v
+                isn[i] = 1
+        return num, isn
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class Variable:
+    name: str
+
+
+@dataclass(frozen=True)
+class Constant:
+    id: int
+
+
+Term = Union[Variable, Constant]
+TriplePattern = Tuple[Term, Term, Term]
+
+
+def _strip(v: str) -> str:
+    return v[1:] if v.startswith("?") else v  # engine.rs strips '?' from variable names everywhere
+
+
+class SlotMap:
+    """variable name <-> integer slot (variables never reach the device as strings)"""
+
+    def __init__(self):
+        self.slot: Dict[str, int] = {}
+        self.names: List[str] = []
+
+    def of(self, name: str) -> int:
+        name = _strip(name)
+        if name not in self.slot:
+            self.slot[name] = len(self.names)
+            self.names.append(name)
+        return self.slot[name]
+
+    def term(self, t: Term) -> c.KbTerm:
+        return c.V(self.of(t.name)) if isinstance(t, Variable) else c.K(t.id)
+
+    def pattern(self, p: TriplePattern) -> c.KbPattern:
+        return c.pattern(self.term(p[0]), self.term(p[1]), self.term(p[2]))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FILTER expressions (shared/src/query.rs:15-57) and their evaluation contract (types.rs:110-186)
+@dataclass
+class Comparison:
+    var: str
+    op: str
+    value: str
+
+
+@dataclass
+class And:
+    left: object
+    right: object
+
+
+@dataclass
+class Or:
+    left: object
+    right: object
+
+
+@dataclass
+class Not:
+    inner: object
+
+
+@dataclass
+class Arith:
+    """ArithmeticExpression: ('op', l, r) trees with str operands; truthy when != 0"""
+    expr: object
+
+
+@dataclass
+class FunctionCall:
+    name: str
+    args: List[str]
+
+
+_CMP = {">": c.CMP_GT, ">=": c.CMP_GE, "<": c.CMP_LT, "<=": c.CMP_LE}
+
+
+class Condition:
+    def __init__(self, expression):
+        self.expression = expression
+
+    def compile(self, slots: SlotMap, dictionary: Dictionary) -> List[c.KbFilterOp]:
+        ops: List[c.KbFilterOp] = []
+
+        def arith(e):
+            if isinstance(e, str):
+                if e.startswith("?"):
+                    ops.append(c.fop(c.F_PUSH_VAR, slot=slots.of(e)))
+                else:
+                    v = rust_parse_f64(e)
+                    if v is None:
+                        raise c.KolibrieError(c.KB_E_UNSUPPORTED, f"arithmetic operand {e!r} is not a number (the reference evaluates the filter to false)")
+                    ops.append(c.fop(c.F_PUSH_CONST, value=v))
+                return
+            kind, l, r = e
+            arith(l)
+            arith(r)
+            ops.append(c.fop({"+": c.F_ADD, "-": c.F_SUB, "*": c.F_MUL, "/": c.F_DIV}[kind]))
+
+        def rec(e):
+            if isinstance(e, Comparison):
+                slot = slots.of(e.var)
+                if e.op in ("=", "!="):
+                    # decoded == literal  <=>  id == encode(literal) when the literal is in the dictionary (types.rs:131-132)
+                    lit = dictionary.lookup(e.value)
+                    ops.append(c.fop(c.F_EQ_ID if e.op == "=" else c.F_NE_ID, slot=slot, id=c.KB_ID_NONE if lit is None else lit))
+                elif e.op in _CMP:
+                    v = rust_parse_f64(e.value)  # types.rs:133-148: value.parse::<f64>().unwrap_or(0.0) — also for "?other" (quirk Q10)
+                    ops.append(c.fop(c.F_CMP_NUM, slot=slot, cmp=_CMP[e.op], value=0.0 if v is None else v))
+                else:
+                    raise c.KolibrieError(c.KB_E_UNSUPPORTED, f"operator {e.op!r}: the reference evaluates it to false")
+            elif isinstance(e, And):
+                rec(e.left); rec(e.right); ops.append(c.fop(c.F_AND))
+            elif isinstance(e, Or):
+                rec(e.left); rec(e.right); ops.append(c.fop(c.F_OR))
+            elif isinstance(e, Not):
+                rec(e.inner); ops.append(c.fop(c.F_NOT))
+            elif isinstance(e, Arith):
+                arith(e.expr); ops.append(c.fop(c.F_TRUTHY))
+            elif isinstance(e, FunctionCall):
+                if e.name == "isTRIPLE" and e.args:
+                    ops.append(c.fop(c.F_IS_TRIPLE, slot=slots.of(e.args[0])))
+                else:
+                    raise c.KolibrieError(c.KB_E_UNSUPPORTED, f"function {e.name!r}: the reference evaluates it to false")
+            else:
+                raise TypeError(e)
+
+        rec(self.expression)
+        return ops
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PhysicalOperator (operators/physical.rs:16-76) — the variants on the hot path
+@dataclass
+class TableScan:
+    pattern: TriplePattern
+
+
+@dataclass
+class IndexScan:
+    pattern: TriplePattern
+
+
+@dataclass
+class Filter:
+    input: object
+    condition: Condition
+
+
+@dataclass
+class Projection:
+    input: object
+    variables: List[str]
+
+
+@dataclass
+class HashJoin:
+    left: object
+    right: object
+
+
+@dataclass
+class OptimizedHashJoin:
+    left: object
+    right: object
+
+
+@dataclass
+class NestedLoopJoin:
+    left: object
+    right: object
+
+
+@dataclass
+class ParallelJoin:
+    left: object
+    right: object
+
+
+@dataclass
+class StarJoin:
+    join_var: str
+    patterns: List[TriplePattern]
+
+
+@dataclass
+class InMemoryBuffer:
+    content: List[Dict[str, int]]
+
+
+class SparqlDatabase:
+    """triples (set semantics, iteration in (s,p,o) order like the reference's BTreeSet) + dictionary + the device store."""
+
+    def __init__(self, ctx: Optional[c.Context] = None, device: int = 0):
+        self.dictionary = Dictionary()
+        self.triples: set = set()
+        self.ctx = ctx or c.Context(device)
+        self._uploaded_version = -1
+        self._version = 0
+
+    def add_triple_parts(self, s: str, p: str, o: str):
+        t = (self.dictionary.encode(s), self.dictionary.encode(p), self.dictionary.encode(o))
+        self.add_triple(t)
+
+    def add_triple(self, t: Tuple[int, int, int]):  # sparql_database.rs:215-226
+        if t not in self.triples:
+            self.triples.add(t)
+            self._version += 1
+
+    def delete_triple(self, t: Tuple[int, int, int]) -> bool:  # sparql_database.rs:229-242
+        if t in self.triples:
+            self.triples.remove(t)
+            self._version += 1
+            return True
+        return False
+
+    def build_all_indexes(self):
+        """The reference builds its six hash indexes here (sparql_database.rs:3364-3394); the device store is (re)uploaded instead."""
+        self._sync()
+
+    def _sync(self):
+        if self._uploaded_version == self._version:
+            return
+        arr = np.array(sorted(self.triples), dtype=np.uint32).reshape(-1, 3)
+        self.ctx.store_load(arr[:, 0], arr[:, 1], arr[:, 2])
+        num, isn = self.dictionary.numeric_table()
+        self.ctx.dict_numeric_load(num, isn)
+        self._uploaded_version = self._version
+
+
+class ExecutionEngine:
+    """engine.rs:24-143 — static functions on a unit struct."""
+
+    @staticmethod
+    def _run(op, db: SparqlDatabase, slots: SlotMap) -> c.Relation:
+        ctx = db.ctx
+        if isinstance(op, (TableScan, IndexScan)):
+            return ctx.scan([slots.pattern(op.pattern)])[0]
+        if isinstance(op, Filter):
+            # Selection directly over a star / scan: let the fused operator push conjuncts into its scans
+            if isinstance(op.input, StarJoin):
+                return ctx.star_join(slots.of(op.input.join_var), [slots.pattern(p) for p in op.input.patterns],
+                                     op.condition.compile(slots, db.dictionary))
+            rel = ExecutionEngine._run(op.input, db, slots)
+            return ctx.filter(rel, op.condition.compile(slots, db.dictionary))
+        if isinstance(op, Projection):
+            rel = ExecutionEngine._run(op.input, db, slots)
+            return ctx.project(rel, [slots.of(v) for v in op.variables])
+        if isinstance(op, (HashJoin, OptimizedHashJoin, NestedLoopJoin)):
+            return ctx.hash_join(ExecutionEngine._run(op.left, db, slots), ExecutionEngine._run(op.right, db, slots))
+        if isinstance(op, ParallelJoin):
+            # right side a scan -> bind join (engine.rs:935-937) == natural join of left with the pattern's matches
+            return ctx.hash_join(ExecutionEngine._run(op.left, db, slots), ExecutionEngine._run(op.right, db, slots))
+        if isinstance(op, StarJoin):
+            return ctx.star_join(slots.of(op.join_var), [slots.pattern(p) for p in op.patterns])
+        if isinstance(op, InMemoryBuffer):
+            names = sorted({k for row in op.content for k in row})
+            cols = [np.array([row[k] for row in op.content], dtype=np.uint32) for k in names]
+            return ctx.rel_from_host([slots.of(k) for k in names], cols)
+        raise c.KolibrieError(c.KB_E_UNSUPPORTED, f"operator {type(op).__name__} stays on the reference's CPU path")
+
+    @staticmethod
+    def execute_with_ids(op, db: SparqlDatabase) -> List[Dict[str, int]]:
+        db._sync()
+        slots = SlotMap()
+        rel = ExecutionEngine._run(op, db, slots)
+        n, rslots = rel.info()
+        cols = [rel.column(i) for i in range(len(rslots))]
+        names = [slots.names[s] for s in rslots]
+        return [{names[j]: int(cols[j][i]) for j in range(len(names))} for i in range(n)]
+
+    @staticmethod
+    def execute(op, db: SparqlDatabase) -> List[Dict[str, str]]:
+        rows = ExecutionEngine.execute_with_ids(op, db)
+        return [{k: (db.dictionary.decode(v) or "unknown") for k, v in r.items()} for r in rows]  # engine.rs:41-43
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class FilterCondition:  # shared/src/rule.rs:14-18
+    variable: str
+    operator: str
+    value: str
+
+
+@dataclass
+class Rule:  # shared/src/rule.rs:21-25
+    premise: List[TriplePattern]
+    conclusion: List[TriplePattern]
+    filters: List[FilterCondition] = field(default_factory=list)
+
+
+_RULE_CMP = {">": c.CMP_GT, ">=": c.CMP_GE, "<": c.CMP_LT, "<=": c.CMP_LE, "=": c.CMP_EQ, "!=": c.CMP_NE}
+
+
+def compile_rule(rule: Rule) -> dict:
+    slots = SlotMap()
+    prem = [slots.pattern(p) for p in rule.premise]
+    conc = [slots.pattern(p) for p in rule.conclusion]
+    fl = []
+    for f in rule.filters:
+        cmp = _RULE_CMP.get(f.operator, 0)  # e.g. "OR:>" is a no-op in the reference (rules.rs:133-165)
+        name = _strip(f.variable)
+        if name not in slots.slot:
+            continue  # unbound lhs: the reference skips the filter (rules.rs:139)
+        rhs_name = _strip(f.value)
+        if rhs_name in slots.slot:
+            fl.append(c.KbRuleFilter(slots.slot[name], cmp, 1, slots.slot[rhs_name], 0.0))
+        else:
+            v = rust_parse_f64(f.value)
+            fl.append(c.KbRuleFilter(slots.slot[name], cmp, 0, 0, 0.0 if v is None else v))
+    return {"premise": prem, "conclusion": conc, "filters": fl}
+
+
+class Reasoner:
+    """datalog/src/reasoning.rs:31-100. Facts live in the device store; rules are compiled to slot form per call."""
+
+    def __init__(self, ctx: Optional[c.Context] = None, device: int = 0):
+        self.dictionary = Dictionary()
+        self.rules: List[Rule] = []
+        self.ctx = ctx or c.Context(device)
+        self._facts: List[Tuple[int, int, int]] = []
+        self._fact_set: set = set()
+        self._dirty = True
+        self.last_stats = None
+
+    def add_abox_triple(self, subject: str, predicate: str, obj: str):
+        t = (self.dictionary.encode(subject), self.dictionary.encode(predicate), self.dictionary.encode(obj))
+        if t not in self._fact_set:  # index_manager.insert dedups (index_manager.rs:41-57)
+            self._fact_set.add(t)
+            self._facts.append(t)
+            self._dirty = True
+
+    def add_rule(self, rule: Rule):
+        self.rules.append(rule)
+
+    def _sync(self):
+        if self._dirty:
+            arr = np.array(self._facts, dtype=np.uint32).reshape(-1, 3)
+            self.ctx.store_load(arr[:, 0], arr[:, 1], arr[:, 2])
+            self._dirty = False
+        num, isn = self.dictionary.numeric_table()
+        self.ctx.dict_numeric_load(num, isn)
+
+    def _infer(self, strategy: int) -> List[Tuple[int, int, int]]:
+        self._sync()
+        rel, st = self.ctx.datalog_fixpoint([compile_rule(r) for r in self.rules], strategy)
+        self.last_stats = st
+        rows = rel.to_numpy([0, 1, 2])
+        out = [tuple(int(x) for x in r) for r in rows]
+        for t in out:  # the device already appended them to its store (infer_generic.rs:46)
+            self._fact_set.add(t)
+            self._facts.append(t)
+        return out
+
+    def infer_new_facts_semi_naive(self):
+        return self._infer(c.SEMI_NAIVE)
+
+    def infer_new_facts_naive(self):
+        return self._infer(c.NAIVE)
+
+    def infer_new_facts(self):
+        return self.infer_new_facts_naive()  # my_naive.rs:78-80 "for backward compatibility"
+
+    def query_abox(self, subject: Optional[str], predicate: Optional[str], obj: Optional[str]):
+        """reasoning.rs:79-93 — note: like the reference, querying ENCODES unknown strings (they simply match nothing)."""
+        self._sync()
+        ts = []
+        for k, v in enumerate((subject, predicate, obj)):
+            ts.append(c.V(k) if v is None else c.K(self.dictionary.encode(v)))
+        rel = self.ctx.scan([c.pattern(*ts)])[0]
+        n, slots = rel.info()
+        cols = {s: rel.column(i) for i, s in enumerate(slots)}
+        fixed = [None if v is None else self.dictionary.encode(v) for v in (subject, predicate, obj)]
+        return [tuple(int(cols[k][i]) if fixed[k] is None else fixed[k] for k in range(3)) for i in range(n)]
