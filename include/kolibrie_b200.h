@@ -141,6 +141,7 @@ typedef struct kb_stats {
     uint64_t rows_probed;    /* probe-side rows */
     uint64_t rows_out;       /* rows of the last result */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t kernel_launches; /* launches of this library's own kernels (memsets and copies not counted) */
 } kb_stats;
 
 /* ------------------------------------------------------------------ context */

@@ -6,8 +6,10 @@ fallback: if the library (or a GPU) is missing, every entry point raises.
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 import os
+import weakref
 from typing import Iterable, Optional, Sequence
 
 import numpy as np
@@ -65,7 +67,7 @@ class KbStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("scan_ms", "build_ms", "probe_ms", "filter_ms", "group_ms", "other_ms", "total_ms")] + [
         (n, C.c_uint64)
         for n in ("scan_launches", "build_launches", "probe_launches", "filter_launches", "group_launches", "other_launches",
-                  "rows_scanned", "rows_built", "rows_probed", "rows_out", "h2d_bytes", "d2h_bytes")
+                  "rows_scanned", "rows_built", "rows_probed", "rows_out", "h2d_bytes", "d2h_bytes", "kernel_launches")
     ]
 
     def as_dict(self):
@@ -113,6 +115,16 @@ class KolibrieError(RuntimeError):
 
 
 _lib = None
+_LIVE_CONTEXTS = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all():
+    for ctx in list(_LIVE_CONTEXTS):
+        try:
+            ctx.close()
+        except Exception:
+            pass
 
 
 def lib() -> C.CDLL:
@@ -199,6 +211,7 @@ class Relation:
     def __init__(self, ctx: "Context", handle):
         self.ctx = ctx
         self.h = C.c_void_p(handle) if not isinstance(handle, C.c_void_p) else handle
+        ctx._rels.add(self)
 
     def info(self):
         n, nc = C.c_uint64(), C.c_uint32()
@@ -256,9 +269,13 @@ class Context:
             raise KolibrieError(rc, (lib().kb_last_error(None) or b"").decode())
         self.h = h
         self.device = device
+        self._rels = weakref.WeakSet()
+        _LIVE_CONTEXTS.add(self)
 
     def close(self):
         if self.h:
+            for r in list(self._rels):  # relations first, while their stream still exists
+                r.free()
             lib().kb_ctx_destroy(self.h)
             self.h = None
 

@@ -41,6 +41,7 @@ kb_status alloc_buf(kb_ctx* ctx, size_t bytes, Buf* out) {
     auto b = std::make_shared<DevBuf>();
     b->bytes = round256(bytes) + 256;  // every column can be over-read to the next 16-byte boundary by the TMA tile loads
     b->st = ctx->st;
+    b->life = ctx->life;
     cudaError_t e = cudaMallocAsync(&b->p, b->bytes, ctx->st);
     if (e != cudaSuccess) {
         b->p = nullptr;
@@ -88,10 +89,13 @@ kb_status ctrl_read(kb_ctx* ctx) {
 kb_status ensure_tile_state(kb_ctx* ctx, u64 tiles) {
     if (tiles <= ctx->tile_state_tiles) return KB_OK;
     u64 want = std::max<u64>(tiles, 1024) * 2;
-    Buf b;
+    Buf b, b2;
     KB_TRY(alloc_buf(ctx, want * MAXP * sizeof(u64), &b));
+    KB_TRY(alloc_buf(ctx, (want / 32 + 2) * MAXP * sizeof(u64), &b2));
     KB_CUDA(ctx, cudaMemsetAsync(b->p, 0, want * MAXP * sizeof(u64), ctx->st));  // epoch 0 is never used by a launch
+    KB_CUDA(ctx, cudaMemsetAsync(b2->p, 0, (want / 32 + 2) * MAXP * sizeof(u64), ctx->st));
     ctx->tile_state = b;
+    ctx->block_state = b2;
     ctx->tile_state_tiles = want;
     return KB_OK;
 }
@@ -114,7 +118,8 @@ static cudaEvent_t get_event(kb_ctx* ctx) {
     cudaEventCreate(&e);
     return e;
 }
-void timer_begin(kb_ctx* ctx, int fam) {
+void timer_begin(kb_ctx* ctx, int fam, int n_kernels) {
+    ctx->stats.kernel_launches += (u64)n_kernels;
     switch (fam) {
         case F_SCAN: ctx->stats.scan_launches++; break;
         case F_BUILD: ctx->stats.build_launches++; break;
@@ -295,13 +300,13 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
             src.assign(1, 3u);
         }
         rel->slots = slots;
-        sp.n_out = (u32)slots.size();
-        for (u32 c = 0; c < sp.n_out; c++) {
+        for (int q = 0; q < 4; q++) sp.outp[q] = nullptr;
+        for (size_t c = 0; c < slots.size(); c++) {  // columns come out in s,p,o order = order of first appearance
             Col col;
             KB_TRY(alloc_col(ctx, N, &col));
             rel->cols.push_back(col);
-            sp.out[c] = col.ptr;
-            sp.out_src[c] = src[c];
+            sp.outp[src[c]] = col.ptr;
+            sp.flags |= src[c] == 0 ? SP_EMIT_S : src[c] == 1 ? SP_EMIT_P : src[c] == 2 ? SP_EMIT_O : SP_EMIT_IDX;
         }
         sp.f_begin = (u32)ops.size();
         sp.f_len = 0;
@@ -327,21 +332,23 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
     for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
 
     const u32 n_seg = (u32)ctx->segs.size();
-    const u32 off_tot = ctrl_alloc(ctx, MAXP), off_min = ctrl_alloc(ctx, MAXP), off_max = ctrl_alloc(ctx, MAXP);
+    const u32 off_tot = ctrl_alloc(ctx, 2 * MAXP), off_min = ctrl_alloc(ctx, MAXP), off_max = ctrl_alloc(ctx, MAXP);
     const u32 off_ticket = ctrl_alloc(ctx, std::max(n_seg, 1u));
     if (ctx->ctrl_used > kb_ctx::CTRL_WORDS - 64) return fail(ctx, KB_E_LIMIT, "too many store segments (%u)", n_seg);
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_min, 0xFF, MAXP * sizeof(u32), ctx->st));
-    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_tot, 0, MAXP * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_tot, 0, 2 * MAXP * sizeof(u32), ctx->st));
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_max, 0, MAXP * sizeof(u32), ctx->st));
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_ticket, 0, std::max(n_seg, 1u) * sizeof(u32), ctx->st));
-    P.totals = ctx->ctrl + off_tot;
     P.kmin = ctx->ctrl + off_min;
     P.kmax = ctx->ctrl + off_max;
     u64 max_tiles = 0;
     for (auto& sg : ctx->segs) max_tiles = std::max<u64>(max_tiles, (sg.n + SCAN_TILE - 1) / SCAN_TILE);
     KB_TRY(ensure_tile_state(ctx, max_tiles));
     P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+    P.block_state = static_cast<u64*>(ctx->block_state->p);
+    P.ordered = ctx->ordered;
     u64 index_base = 0;
+    u32 n_launched = 0;
     for (u32 g = 0; g < n_seg; g++) {
         const Segment& sg = ctx->segs[g];
         if (sg.n == 0) continue;
@@ -350,6 +357,13 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
         P.n_tiles = (u32)((sg.n + SCAN_TILE - 1) / SCAN_TILE);
         P.index_base = (u32)index_base;
         P.ticket = ctx->ctrl + off_ticket + g;
+        if (ctx->ordered) {  // ping-pong: a launch never writes the word its tiles read their base from
+            P.totals_in = ctx->ctrl + off_tot + (n_launched & 1u) * MAXP;
+            P.totals_out = ctx->ctrl + off_tot + ((n_launched + 1u) & 1u) * MAXP;
+        } else {
+            P.totals_in = P.totals_out = ctx->ctrl + off_tot;
+        }
+        n_launched++;
         P.epoch = ctx->epoch++;
         if (ctx->epoch >= (1ull << 30)) ctx->epoch = 1;
         if (sg.ready) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st, sg.ready, 0));  // chunked upload: start as soon as this chunk landed
@@ -364,7 +378,7 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
     if (kmin) kmin->assign(K, 0);
     if (kmax) kmax->assign(K, 0);
     for (u32 k = 0; k < K; k++) {
-        (*out)[k]->n = ctx->h_ctrl[off_tot + k];
+        (*out)[k]->n = ctx->h_ctrl[off_tot + (ctx->ordered ? (n_launched & 1u) * MAXP : 0u) + k];
         if (kmin) (*kmin)[k] = ctx->h_ctrl[off_min + k];
         if (kmax) (*kmax)[k] = ctx->h_ctrl[off_max + k];
     }
@@ -409,10 +423,13 @@ kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::u
     P.nt = numtab(ctx);
     KB_TRY(ensure_tile_state(ctx, P.n_tiles));
     P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+    P.block_state = static_cast<u64*>(ctx->block_state->p);
+    P.ordered = ctx->ordered;
     const u32 off = ctrl_alloc(ctx, 4);
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
     P.ticket = ctx->ctrl + off;
     P.total = ctx->ctrl + off + 1;
+    P.zero_word = ctx->ctrl + off + 2;
     P.epoch = ctx->epoch++;
     P.abort_flag = nullptr;
     timer_begin(ctx, F_FILTER);
@@ -516,8 +533,11 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
     P.nt = numtab(ctx);
     KB_TRY(ensure_tile_state(ctx, P.n_tiles));
     P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+    P.block_state = static_cast<u64*>(ctx->block_state->p);
+    P.ordered = ctx->ordered;
     const u32 off = ctrl_alloc(ctx, 4);
     P.total = ctx->ctrl + off + 1;
+    P.zero_word = ctx->ctrl + off + 2;
     u64 cap = std::max(Pr.n, B.n);
     ctx->stats.rows_probed += Pr.n;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -656,7 +676,7 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
             std::vector<u32> out_slots = cur->slots;
             std::vector<OutCol> ocs;
             for (u32 c = 0; c < P.n_pcols; c++) ocs.push_back(OutCol{OUT_PROBE, c, 0});
-            timer_begin(ctx, F_BUILD);
+            timer_begin(ctx, F_BUILD, (int)nb);
             for (size_t t = 0; t < nb; t++) {
                 const u32 k = builds[done + t];
                 const kb_rel& B = *rels[k];
@@ -711,8 +731,11 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
             P.nt = numtab(ctx);
             KB_TRY(ensure_tile_state(ctx, P.n_tiles));
             P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+            P.block_state = static_cast<u64*>(ctx->block_state->p);
+    P.ordered = ctx->ordered;
             P.ticket = ctx->ctrl + off;
             P.total = ctx->ctrl + off + 1;
+            P.zero_word = ctx->ctrl + off + 2;
             P.abort_flag = ctx->ctrl + off + 8;  // MAXT consecutive duplicate flags
             P.epoch = ctx->epoch++;
             timer_begin(ctx, F_PROBE);
@@ -807,6 +830,7 @@ kb_status kb_ctx_create(int device, kb_ctx** out) {
         uint64_t thr = UINT64_MAX;  // keep freed blocks cached: steady-state queries never hit cudaMalloc
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
+    if (const char* ord = getenv("KOLIBRIE_ORDERED")) ctx->ordered = (ord[0] == '0') ? 0u : 1u;
     if ((e = cudaMalloc(&ctx->ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMalloc(ctrl)", e);
     if ((e = cudaMallocHost(&ctx->h_ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMallocHost(ctrl)", e);
     *out = ctx;
@@ -823,7 +847,9 @@ void kb_ctx_destroy(kb_ctx* ctx) {
     ctx->num.reset();
     ctx->isnum.reset();
     ctx->tile_state.reset();
+    ctx->block_state.reset();
     cudaStreamSynchronize(ctx->st);
+    ctx->life->alive = false;  // buffers still referenced by live relations fall back to cudaFree
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ctrl) cudaFree(ctx->ctrl);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
@@ -1247,7 +1273,7 @@ kb_status kb_group_aggregate(kb_ctx* ctx, const kb_rel* in, const uint32_t* grou
         const u32 off = kb::ctrl_alloc(ctx, 4);
         KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
         P.overflow = ctx->ctrl + off;
-        kb::timer_begin(ctx, kb::F_GROUP);
+        kb::timer_begin(ctx, kb::F_GROUP, 2);
         kb::launch_group_init(P, ctx->st);
         kb::launch_group(P, ctx->n_sms, ctx->st);
         kb::timer_end(ctx);

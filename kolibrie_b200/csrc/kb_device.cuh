@@ -119,6 +119,159 @@ __device__ __forceinline__ void tile_prefix_warp(u64* __restrict__ state, u32 ti
     __syncwarp();
 }
 
+// TWO-LEVEL ordered prefix (the one the kernels use). Tiles are grouped in blocks of 32 consecutive tickets.
+//   level 1: state1[tile]  = this tile's count (epoch-tagged). A tile sums the counts of the earlier tiles of ITS block: it waits
+//            only until those tiles have COUNTED (they run concurrently with it), never for anybody's look-back.
+//   level 2: state2[block] = A(ggregate of the block) then P(refix through the block), published by the block's last tile.
+//            A tile looks back over whole blocks; ~600 tiles in flight are < 20 blocks, i.e. always inside one 32-wide window.
+// Cost per tile and counter: one publish, 32 + 32 word loads issued together, two memory round trips on the critical path,
+// independent of how many tiles are in flight (the flat decoupled look-back above needs ~tiles_in_flight/32 dependent steps).
+// mode 0 replaces all of this by one atomicAdd on a global cursor: same bytes, output order = tile completion order.
+__device__ __forceinline__ u32 tile_prefix_2level(u64* __restrict__ state1, u64* __restrict__ state2, u32 tile, u32 n_tiles, u32 k, u64 epoch,
+                                                  u32 count, const u32* totals_in, u32* totals_out, u32 ordered, int lane) {
+    // ordered: totals_in[k] = rows written by earlier launches, totals_out[k] (a DIFFERENT word) receives the new total;
+    // unordered: totals_out[k] is the atomic cursor and already holds the earlier launches' rows.
+    if (!ordered) {
+        u32 ex = 0;
+        if (lane == 0) ex = atomicAdd(&totals_out[k], count);
+        return __shfl_sync(0xffffffffu, ex, 0);
+    }
+    const u64 tag = epoch << 34;
+    const u32 b = tile >> 5, i = tile & 31u;
+    const u32 last_i = min(31u, n_tiles - 1u - (b << 5));
+    if (lane == 0) st_relaxed(&state1[(u64)tile * MAXP + k], tag | (u64)count);
+    const u64* p1 = &state1[(u64)((b << 5) + (u32)lane) * MAXP + k];
+    long long pb = (long long)b - 1 - lane;
+    const u32 base_in = totals_in[k];
+    u64 w1 = ((u32)lane < i) ? ld_relaxed(p1) : tag;
+    u64 w2 = (pb >= 0) ? ld_relaxed(&state2[(u64)pb * MAXP + k]) : (tag | TS_P | (u64)(pb == -1 ? base_in : 0u));
+    while ((w1 >> 34) != epoch) w1 = ld_relaxed(p1);
+    const u32 local = warp_sum(((u32)lane < i) ? (u32)w1 : 0u);
+    if (i == last_i && lane == 0) st_relaxed(&state2[(u64)b * MAXP + k], tag | TS_A | (u64)(local + count));
+    u32 sum = 0;
+    for (;;) {
+        if (pb >= 0) {
+            const u64* p2 = &state2[(u64)pb * MAXP + k];
+            while ((w2 >> 34) != epoch) w2 = ld_relaxed(p2);
+        }
+        const bool is_p = ((w2 >> 32) & 3ull) == 2ull;
+        const unsigned pm = __ballot_sync(0xffffffffu, is_p);
+        const u32 v = (u32)w2;
+        if (pm) {
+            const int first = __ffs(pm) - 1;
+            sum += warp_sum(lane <= first ? v : 0u);
+            break;
+        }
+        sum += warp_sum(v);
+        pb -= 32;
+        w2 = (pb >= 0) ? ld_relaxed(&state2[(u64)pb * MAXP + k]) : (tag | TS_P | (u64)(pb == -1 ? base_in : 0u));
+    }
+    const u32 ex = sum + local;
+    if (lane == 0) {
+        if (i == last_i) st_relaxed(&state2[(u64)b * MAXP + k], tag | TS_P | (u64)(ex + count));
+        if (tile == n_tiles - 1u) totals_out[k] = ex + count;
+    }
+    return ex;
+}
+
+// One counter, WIDE window: every lane inspects LBQ consecutive predecessors per step, so a step covers 32*LBQ tiles and "prefix
+// known" (P) status propagates through the in-flight tiles LBQ times faster than with a 32-tile window. With ~450-600 tiles in
+// flight (3-4 CTAs on each of 148 SMs) a 256-tile window ends every look-back in one or two memory round trips.
+// Called by all 32 lanes of a warp; `count` is this tile's total for counter k; returns the exclusive prefix (valid in all lanes).
+constexpr int LBQ = 8;
+__device__ __forceinline__ u32 tile_prefix_wide(u64* __restrict__ state, u32 tile, u32 k, u64 epoch, u32 count, const u32* base, int lane) {
+    const u64 tag = epoch << 34;
+    if (tile == 0) {
+        const u32 b = base ? base[k] : 0u;
+        if (lane == 0) st_relaxed(&state[k], tag | TS_P | (u64)(b + count));
+        return b;
+    }
+    if (lane == 0) st_relaxed(&state[(u64)tile * MAXP + k], tag | TS_A | (u64)count);
+    u32 sum = 0;
+    long long pred0 = (long long)tile - 1 - (long long)lane * LBQ;  // this lane covers pred0, pred0-1, ..., pred0-LBQ+1 (nearest first)
+    for (;;) {
+        u64 w[LBQ];
+#pragma unroll
+        for (int q = 0; q < LBQ; q++) w[q] = (pred0 - q >= 0) ? ld_relaxed(&state[(u64)(pred0 - q) * MAXP + k]) : (tag | TS_P);
+        u32 lane_sum = 0;
+        bool lane_p = false;
+#pragma unroll
+        for (int q = 0; q < LBQ; q++) {
+            if (!lane_p) {
+                while ((w[q] >> 34) != epoch) w[q] = ld_relaxed(&state[(u64)(pred0 - q) * MAXP + k]);
+                lane_sum += (u32)w[q];
+                lane_p = ((w[q] >> 32) & 3ull) == 2ull;
+            }
+        }
+        const unsigned pm = __ballot_sync(0xffffffffu, lane_p);
+        if (pm) {
+            const int first = __ffs(pm) - 1;
+            sum += warp_sum(lane <= first ? lane_sum : 0u);
+            break;
+        }
+        sum += warp_sum(lane_sum);
+        pred0 -= 32 * LBQ;
+    }
+    if (lane == 0) st_relaxed(&state[(u64)tile * MAXP + k], tag | TS_P | (u64)(sum + count));
+    return sum;
+}
+
+// Same protocol for K counters at once (compile-time K): the K state words of a predecessor tile are read with K independent
+// loads, so the look-back costs one memory round trip per window instead of K.
+template <int K>
+__device__ __forceinline__ void tile_prefix_warp_k(u64* __restrict__ state, u32 tile, u64 epoch, const u32* counts, u32* excl, const u32* base,
+                                                   int lane) {
+    const u64 tag = epoch << 34;
+    if (tile == 0) {
+        if (lane < K) {
+            u32 b = base ? base[lane] : 0u;
+            excl[lane] = b;
+            st_relaxed(&state[lane], tag | TS_P | (u64)(b + counts[lane]));
+        }
+        __syncwarp();
+        return;
+    }
+    if (lane < K) st_relaxed(&state[(u64)tile * MAXP + lane], tag | TS_A | (u64)counts[lane]);
+    u32 sum[K];
+    bool done[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { sum[k] = 0; done[k] = false; }
+    long long pred = (long long)tile - 1 - lane;
+    for (;;) {
+        u64 w[K];
+        const u64* p = &state[(u64)(pred >= 0 ? pred : 0) * MAXP];
+#pragma unroll
+        for (int k = 0; k < K; k++) w[k] = (pred >= 0) ? ld_relaxed(p + k) : (tag | TS_P);
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (done[k]) continue;
+            while ((w[k] >> 34) != epoch) { __nanosleep(20); w[k] = ld_relaxed(p + k); }
+            const bool is_p = ((w[k] >> 32) & 3ull) == 2ull;
+            const unsigned pm = __ballot_sync(0xffffffffu, is_p);
+            const u32 v = (u32)w[k];
+            if (pm) {
+                const int first = __ffs(pm) - 1;
+                sum[k] += warp_sum(lane <= first ? v : 0u);
+                done[k] = true;
+            } else {
+                sum[k] += warp_sum(v);
+                all = false;
+            }
+        }
+        if (all) break;
+        pred -= 32;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            excl[k] = sum[k];
+            st_relaxed(&state[(u64)tile * MAXP + k], tag | TS_P | (u64)(sum[k] + counts[k]));
+        }
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // FILTER evaluation on the device. vals[slot] = id bound to the (remapped) slot.
 struct FilterOp {  // same layout as kb_filter_op

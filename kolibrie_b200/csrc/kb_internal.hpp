@@ -12,12 +12,18 @@
 
 namespace kb {
 
+struct Life {  // shared by a context and every buffer it handed out: relations may outlive their context (bindings' GC order)
+    bool alive = true;
+};
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
     cudaStream_t st = nullptr;
+    std::shared_ptr<Life> life;
     ~DevBuf() {
-        if (p) cudaFreeAsync(p, st);
+        if (!p) return;
+        if (life && life->alive) cudaFreeAsync(p, st);  // stream-ordered: kernels still queued on st may be using it
+        else cudaFree(p);                               // the context (and its stream) is gone
     }
 };
 using Buf = std::shared_ptr<DevBuf>;
@@ -68,13 +74,15 @@ struct kb_ctx {
     cudaStream_t st_copy = nullptr;
     cudaEvent_t ev_copy = nullptr;
     std::string err;
+    std::shared_ptr<kb::Life> life = std::make_shared<kb::Life>();
     std::vector<kb::Segment> segs;
     kb::u64 n_triples = 0;
     kb::Buf num, isnum;
     kb::u32 n_ids = 0;
     // tile-state buffer of the look-back prefix (never cleared: words carry the launch epoch)
-    kb::Buf tile_state;
+    kb::Buf tile_state, block_state;
     size_t tile_state_tiles = 0;
+    kb::u32 ordered = 1;  // KOLIBRIE_ORDERED=0 selects completion-order compaction
     kb::u64 epoch = 1;
     // control arena: small device words (tickets, totals, flags) zeroed at the start of every API call, mirrored in pinned memory
     kb::u32* ctrl = nullptr;
@@ -115,7 +123,7 @@ u32 ctrl_alloc(kb_ctx* ctx, u32 words);                 // returns word offset i
 kb_status ctrl_read(kb_ctx* ctx);                       // D2H of the used part of the arena + stream sync
 kb_status ensure_tile_state(kb_ctx* ctx, u64 tiles);
 NumTab numtab(const kb_ctx* ctx);
-void timer_begin(kb_ctx* ctx, int fam);
+void timer_begin(kb_ctx* ctx, int fam, int n_kernels = 1);
 void timer_end(kb_ctx* ctx);
 void timers_flush(kb_ctx* ctx);  // after a stream sync
 

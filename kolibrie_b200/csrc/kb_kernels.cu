@@ -22,139 +22,218 @@ static inline int grid_for(const void* kernel, int threads, size_t smem, int n_s
 
 // =================================================================================================================
 // K_scan
-__global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(const __grid_constant__ ScanParams P) {
+// Thread t owns the 8 consecutive triples [8t, 8t+8) of a 2048-triple tile. The tile is TMA-staged into shared memory, pulled
+// into registers with six LDS.128, and the shared buffer is immediately handed back to TMA for the NEXT tile (single buffer,
+// register-staged double buffering). K is a template parameter so every pattern field is a constant-bank operand.
+__device__ __forceinline__ u32 eq8(const uint4& a, const uint4& b, u32 c) {
+    return (a.x == c ? 1u : 0u) | (a.y == c ? 2u : 0u) | (a.z == c ? 4u : 0u) | (a.w == c ? 8u : 0u) | (b.x == c ? 16u : 0u) | (b.y == c ? 32u : 0u) |
+           (b.z == c ? 64u : 0u) | (b.w == c ? 128u : 0u);
+}
+__device__ __forceinline__ u32 eqv8(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    return (a0.x == b0.x ? 1u : 0u) | (a0.y == b0.y ? 2u : 0u) | (a0.z == b0.z ? 4u : 0u) | (a0.w == b0.w ? 8u : 0u) | (a1.x == b1.x ? 16u : 0u) |
+           (a1.y == b1.y ? 32u : 0u) | (a1.z == b1.z ? 64u : 0u) | (a1.w == b1.w ? 128u : 0u);
+}
+#define KB_ELEM(v0, v1, j) ((j) == 0 ? v0.x : (j) == 1 ? v0.y : (j) == 2 ? v0.z : (j) == 3 ? v0.w : (j) == 4 ? v1.x : (j) == 5 ? v1.y : (j) == 6 ? v1.z : v1.w)
+
+template <int K>
+__global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 4 : 2)) scan_kernel(const __grid_constant__ ScanParams P) {
     extern __shared__ __align__(128) u32 smem[];
-    u32* sS = smem;
-    u32* sP = smem + SCAN_TILE;
-    u32* sO = smem + 2 * SCAN_TILE;
+    const uint4* sS4 = reinterpret_cast<const uint4*>(smem);
+    const uint4* sP4 = reinterpret_cast<const uint4*>(smem + SCAN_TILE);
+    const uint4* sO4 = reinterpret_cast<const uint4*>(smem + 2 * SCAN_TILE);
     __shared__ __align__(8) u64 bar;
-    __shared__ u32 s_tile;
+    __shared__ u32 s_next;
     __shared__ u32 s_wcnt[SCAN_THREADS / 32][MAXP];
     __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
     __shared__ u32 s_min[MAXP], s_max[MAXP];
+    constexpr int NW = (K + 2) / 3;  // packed count words: three 10-bit fields each (a warp holds at most 256 matches per pattern)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 K = P.K;
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
     if (tid < MAXP) { s_min[tid] = EMPTY32; s_max[tid] = 0u; }
-    u32 parity = 0;
-    const unsigned lt_mask = (1u << lane) - 1u;
-
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
-        __syncthreads();  // publishes s_tile; also: every thread is done reading the previous tile's shared memory
-        const u32 tile = s_tile;
-        if (tile >= P.n_tiles) break;
-        const u32 base = tile * (u32)SCAN_TILE;
-        const u32 cnt = min((u32)SCAN_TILE, P.n - base);
-        if (tid == 0) {
-            const u32 bytes = (cnt * 4u + 15u) & ~15u;  // columns are padded to 256 B, so the rounded-up read stays in bounds
+    u32 mn[K], mx[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { mn[k] = EMPTY32; mx[k] = 0u; }
+    __syncthreads();
+    u32 tile = 0;
+    if (tid == 0) {
+        tile = atomicAdd(P.ticket, 1u);
+        s_next = tile;
+        if (tile < P.n_tiles) {
+            const u32 base = tile * (u32)SCAN_TILE;
+            const u32 cnt = min((u32)SCAN_TILE, P.n - base);
+            const u32 bytes = (cnt * 4u + 15u) & ~15u;  // columns are padded to 256 B: the rounded-up read stays in bounds
             mbar_arrive_expect_tx(&bar, bytes * 3u);
-            tma_load_1d(sS, P.s + base, bytes, &bar);
-            tma_load_1d(sP, P.p + base, bytes, &bar);
-            tma_load_1d(sO, P.o + base, bytes, &bar);
-        }
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-
-        // ---- phase 1: evaluate every pattern on this thread's 8 triples; bit (k*8+j) = triple j matches pattern k
-        u64 bits = 0;
-#pragma unroll
-        for (int j = 0; j < SCAN_ITEMS; j++) {
-            const u32 idx = (u32)warp * (32u * SCAN_ITEMS) + (u32)j * 32u + (u32)lane;
-            const bool valid = idx < cnt;
-            const u32 s = sS[idx], p = sP[idx], o = sO[idx];
-            for (u32 k = 0; k < K; k++) {
-                const ScanPat& pt = P.pat[k];
-                const u32 f = pt.flags;
-                bool m = valid;
-                if (f & SP_HAS_P) m = m && (p == pt.cp);
-                if (f & SP_HAS_S) m = m && (s == pt.cs);
-                if (f & SP_HAS_O) m = m && (o == pt.co);
-                if (f & (SP_EQ_SP | SP_EQ_SO | SP_EQ_PO)) {
-                    if (f & SP_EQ_SP) m = m && (s == p);
-                    if (f & SP_EQ_SO) m = m && (s == o);
-                    if (f & SP_EQ_PO) m = m && (p == o);
-                }
-                if (pt.f_len != 0u && m) {
-                    u32 vals[3] = {s, p, o};
-                    m = eval_filter(P.ops + pt.f_begin, pt.f_len, vals, P.nt);
-                }
-                bits |= (u64)(m ? 1u : 0u) << (k * 8u + (u32)j);
-            }
-        }
-        for (u32 k = 0; k < K; k++) {
-            const u32 c = warp_sum((u32)__popc((u32)(bits >> (k * 8u)) & 0xFFu));
-            if (lane == 0) s_wcnt[warp][k] = c;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            if (lane < (int)K) {
-                u32 run = 0;
-#pragma unroll
-                for (int w = 0; w < SCAN_THREADS / 32; w++) {
-                    const u32 c = s_wcnt[w][lane];
-                    s_wcnt[w][lane] = run;
-                    run += c;
-                }
-                s_cnt[lane] = run;
-            }
-            __syncwarp();
-            tile_prefix_warp(P.tile_state, tile, K, P.epoch, s_cnt, s_excl, P.totals, lane);
-            if (tile == P.n_tiles - 1 && lane < (int)K) P.totals[lane] = s_excl[lane] + s_cnt[lane];
-        }
-        __syncthreads();
-
-        // ---- phase 2: ordered write of the matches (rank = tile prefix + warp prefix + ballot rank)
-        for (u32 k = 0; k < K; k++) {
-            const u32 mybits = (u32)(bits >> (k * 8u)) & 0xFFu;
-            if (__ballot_sync(0xffffffffu, mybits != 0u) == 0u) continue;
-            const ScanPat& pt = P.pat[k];
-            u32 pos = s_excl[k] + s_wcnt[warp][k];
-            u32 mn = EMPTY32, mx = 0u;
-#pragma unroll
-            for (int j = 0; j < SCAN_ITEMS; j++) {
-                const bool m = (mybits >> j) & 1u;
-                const unsigned b = __ballot_sync(0xffffffffu, m);
-                if (b == 0u) continue;
-                if (m) {
-                    const u32 idx = (u32)warp * (32u * SCAN_ITEMS) + (u32)j * 32u + (u32)lane;
-                    const u32 r = pos + (u32)__popc(b & lt_mask);
-                    const u32 vs = sS[idx], vp = sP[idx], vo = sO[idx];
-                    for (u32 c = 0; c < pt.n_out; c++) {
-                        const u32 src = pt.out_src[c];
-                        pt.out[c][r] = src == 0u ? vs : (src == 1u ? vp : (src == 2u ? vo : P.index_base + base + idx));
-                    }
-                    if (pt.stat_src < 3u) {
-                        const u32 kv = pt.stat_src == 0u ? vs : (pt.stat_src == 1u ? vp : vo);
-                        mn = min(mn, kv);
-                        mx = max(mx, kv);
-                    }
-                }
-                pos += (u32)__popc(b);
-            }
-            if (pt.stat_src < 3u) {
-                mn = __reduce_min_sync(0xffffffffu, mn);
-                mx = __reduce_max_sync(0xffffffffu, mx);
-                if (lane == 0) { atomicMin(&s_min[k], mn); atomicMax(&s_max[k], mx); }
-            }
+            tma_load_1d(smem, P.s + base, bytes, &bar);
+            tma_load_1d(smem + SCAN_TILE, P.p + base, bytes, &bar);
+            tma_load_1d(smem + 2 * SCAN_TILE, P.o + base, bytes, &bar);
         }
     }
     __syncthreads();
-    if (tid < (int)K && P.pat[tid].stat_src < 3u && s_min[tid] != EMPTY32) {
+    tile = s_next;
+    u32 parity = 0;
+
+    while (tile < P.n_tiles) {
+        const u32 base = tile * (u32)SCAN_TILE;
+        const u32 cnt = min((u32)SCAN_TILE, P.n - base);
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        const uint4 s0 = sS4[2 * tid], s1 = sS4[2 * tid + 1];
+        const uint4 p0 = sP4[2 * tid], p1 = sP4[2 * tid + 1];
+        const uint4 o0 = sO4[2 * tid], o1 = sO4[2 * tid + 1];
+        __syncthreads();  // every thread holds its triples in registers: the buffer can take the next tile
+        if (tid == 0) {
+            const u32 nt = atomicAdd(P.ticket, 1u);
+            s_next = nt;
+            if (nt < P.n_tiles) {
+                const u32 nb = nt * (u32)SCAN_TILE;
+                const u32 nc = min((u32)SCAN_TILE, P.n - nb);
+                const u32 bytes = (nc * 4u + 15u) & ~15u;
+                mbar_arrive_expect_tx(&bar, bytes * 3u);
+                tma_load_1d(smem, P.s + nb, bytes, &bar);
+                tma_load_1d(smem + SCAN_TILE, P.p + nb, bytes, &bar);
+                tma_load_1d(smem + 2 * SCAN_TILE, P.o + nb, bytes, &bar);
+            }
+        }
+        // ---- match: bit j of mk[k] = triple 8*tid+j matches pattern k
+        const u32 first = (u32)tid * 8u;
+        const u32 vmask = first >= cnt ? 0u : (cnt - first >= 8u ? 0xFFu : ((1u << (cnt - first)) - 1u));
+        u32 mk[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 f = P.pat[k].flags;
+            u32 m = vmask;
+            if (f & SP_HAS_P) m &= eq8(p0, p1, P.pat[k].cp);
+            if (f & SP_HAS_S) m &= eq8(s0, s1, P.pat[k].cs);
+            if (f & SP_HAS_O) m &= eq8(o0, o1, P.pat[k].co);
+            if (f & (SP_EQ_SP | SP_EQ_SO | SP_EQ_PO)) {
+                if (f & SP_EQ_SP) m &= eqv8(s0, s1, p0, p1);
+                if (f & SP_EQ_SO) m &= eqv8(s0, s1, o0, o1);
+                if (f & SP_EQ_PO) m &= eqv8(p0, p1, o0, o1);
+            }
+            if (P.pat[k].f_len != 0u) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if ((m >> j) & 1u) {
+                        u32 vals[3] = {KB_ELEM(s0, s1, j), KB_ELEM(p0, p1, j), KB_ELEM(o0, o1, j)};
+                        if (!eval_filter(P.ops + P.pat[k].f_begin, P.pat[k].f_len, vals, P.nt)) m &= ~(1u << j);
+                    }
+                }
+            }
+            mk[k] = m;
+        }
+        // ---- ranks: one packed warp scan per three patterns
+        u32 wex[K];
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            u32 packed = 0;
+#pragma unroll
+            for (int q = 0; q < 3; q++) if (w * 3 + q < K) packed |= (u32)__popc(mk[w * 3 + q]) << (10 * q);
+            u32 incl = packed;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const u32 excl = incl - packed;
+            const u32 tot = __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int q = 0; q < 3; q++) if (w * 3 + q < K) {
+                wex[w * 3 + q] = (excl >> (10 * q)) & 1023u;
+                if (lane == 0) s_wcnt[warp][w * 3 + q] = (tot >> (10 * q)) & 1023u;
+            }
+        }
+        __syncthreads();
+        if (warp < K) {  // warp k owns counter k: cross-warp prefix of its per-warp totals, then the look-back across tiles
+            const u32 c = lane < SCAN_THREADS / 32 ? s_wcnt[lane][warp] : 0u;
+            u32 incl = c;
+#pragma unroll
+            for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            const u32 total = __shfl_sync(0xffffffffu, incl, SCAN_THREADS / 32 - 1);
+            if (lane < SCAN_THREADS / 32) s_wcnt[lane][warp] = incl - c;
+            const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, (u32)warp, P.epoch, total, P.totals_in, P.totals_out, P.ordered, lane);
+            if (lane == 0) s_excl[warp] = ex;
+        }
+        __syncthreads();
+        // ---- ordered write
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const u32 m = mk[k];
+            if (m == 0u) continue;
+            const u32 f = P.pat[k].flags;
+            const u32 pos = s_excl[k] + s_wcnt[warp][k] + wex[k];
+            if (f & SP_EMIT_S) {
+                u32* out = P.pat[k].outp[0];
+#pragma unroll
+                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = KB_ELEM(s0, s1, j);
+            }
+            if (f & SP_EMIT_P) {
+                u32* out = P.pat[k].outp[1];
+#pragma unroll
+                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = KB_ELEM(p0, p1, j);
+            }
+            if (f & SP_EMIT_O) {
+                u32* out = P.pat[k].outp[2];
+#pragma unroll
+                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = KB_ELEM(o0, o1, j);
+            }
+            if (f & SP_EMIT_IDX) {
+                u32* out = P.pat[k].outp[3];
+#pragma unroll
+                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = P.index_base + base + first + (u32)j;
+            }
+            const u32 ss = P.pat[k].stat_src;
+            if (ss < 3u) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) {
+                    const u32 kv = ss == 0u ? KB_ELEM(s0, s1, j) : (ss == 1u ? KB_ELEM(p0, p1, j) : KB_ELEM(o0, o1, j));
+                    mn[k] = min(mn[k], kv);
+                    mx[k] = max(mx[k], kv);
+                }
+            }
+        }
+        tile = s_next;  // written before the first __syncthreads of this iteration's compute phase, stable since
+    }
+    // key statistics: one reduction per CTA at the end
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        if (P.pat[k].stat_src < 3u) {
+            const u32 a = __reduce_min_sync(0xffffffffu, mn[k]);
+            const u32 b = __reduce_max_sync(0xffffffffu, mx[k]);
+            if (lane == 0 && a != EMPTY32) { atomicMin(&s_min[k], a); atomicMax(&s_max[k], b); }
+        }
+    }
+    __syncthreads();
+    if (tid < K && P.pat[tid].stat_src < 3u && s_min[tid] != EMPTY32) {
         atomicMin(&P.kmin[tid], s_min[tid]);
         atomicMax(&P.kmax[tid], s_max[tid]);
     }
 }
 
+template <int K>
+static void launch_scan_k(const ScanParams& p, int n_sms, cudaStream_t st) {
+    const size_t smem = 3 * SCAN_TILE * sizeof(u32);
+    const int grid = grid_for((const void*)scan_kernel<K>, SCAN_THREADS, smem, n_sms, p.n_tiles);
+    scan_kernel<K><<<grid, SCAN_THREADS, smem, st>>>(p);
+}
 void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st) {
     if (p.n == 0) return;
-    const size_t smem = 3 * SCAN_TILE * sizeof(u32);
-    const int grid = grid_for((const void*)scan_kernel, SCAN_THREADS, smem, n_sms, p.n_tiles);
-    scan_kernel<<<grid, SCAN_THREADS, smem, st>>>(p);
+    switch (p.K) {
+        case 1: launch_scan_k<1>(p, n_sms, st); break;
+        case 2: launch_scan_k<2>(p, n_sms, st); break;
+        case 3: launch_scan_k<3>(p, n_sms, st); break;
+        case 4: launch_scan_k<4>(p, n_sms, st); break;
+        case 5: launch_scan_k<5>(p, n_sms, st); break;
+        case 6: launch_scan_k<6>(p, n_sms, st); break;
+        case 7: launch_scan_k<7>(p, n_sms, st); break;
+        default: launch_scan_k<8>(p, n_sms, st); break;
+    }
 }
 
 // =================================================================================================================
@@ -312,8 +391,9 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_direct_kernel(const __gri
                 s_cnt[0] = run;
             }
             __syncwarp();
-            tile_prefix_warp(P.tile_state, tile, 1u, P.epoch, s_cnt, s_excl, nullptr, lane);
-            if (tile == P.n_tiles - 1 && lane == 0) *P.total = s_excl[0] + s_cnt[0];
+            const u32 total = __shfl_sync(0xffffffffu, s_cnt[0], 0);
+            const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
+            if (lane == 0) s_excl[0] = ex;
         }
         __syncthreads();
         if (__ballot_sync(0xffffffffu, mbits != 0u) != 0u) {
@@ -469,8 +549,9 @@ __global__ void __launch_bounds__(PROBEC_THREADS) probe_chained_kernel(const __g
                 s_cnt[0] = run;
             }
             __syncwarp();
-            tile_prefix_warp(P.tile_state, tile, 1u, P.epoch, s_cnt, s_excl, nullptr, lane);
-            if (tile == P.n_tiles - 1 && lane == 0) *P.total = s_excl[0] + s_cnt[0];
+            const u32 total = __shfl_sync(0xffffffffu, s_cnt[0], 0);
+            const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
+            if (lane == 0) s_excl[0] = ex;
         }
         __syncthreads();
         u32 pos = s_excl[0] + s_wcnt[warp];

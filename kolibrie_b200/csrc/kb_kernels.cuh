@@ -13,15 +13,15 @@ constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 triples = 24 KB of shared memory per CTA
 
 enum : u32 {
-    SP_HAS_S = 1, SP_HAS_P = 2, SP_HAS_O = 4,   // constant in that position
-    SP_EQ_SP = 8, SP_EQ_SO = 16, SP_EQ_PO = 32  // same variable twice in one pattern (quirk Q4: enforced)
+    SP_HAS_S = 1, SP_HAS_P = 2, SP_HAS_O = 4,      // constant in that position
+    SP_EQ_SP = 8, SP_EQ_SO = 16, SP_EQ_PO = 32,    // same variable twice in one pattern (quirk Q4: enforced)
+    SP_EMIT_S = 64, SP_EMIT_P = 128, SP_EMIT_O = 256,  // positions written to the output (columns come out in s,p,o order)
+    SP_EMIT_IDX = 512                               // global triple index (legacy FFI)
 };
 struct ScanPat {
     u32 cs, cp, co;
     u32 flags;
-    u32 n_out;
-    u32 out_src[3];  // 0=s 1=p 2=o 3=global triple index (legacy FFI)
-    u32* out[3];
+    u32* outp[4];        // output column of position s / p / o / index (null when not emitted)
     u32 f_begin, f_len;  // pushed-down FILTER program (slots = positions 0/1/2)
     u32 stat_src;        // position whose min/max is tracked (the join key), 3 = none
 };
@@ -32,10 +32,13 @@ struct ScanParams {
     ScanPat pat[MAXP];
     FilterOp ops[KB_MAX_FILTER_OPS];
     NumTab nt;
-    u64* tile_state;
+    u64* tile_state;   // level 1: [n_tiles][MAXP]
+    u64* block_state;  // level 2: [ceil(n_tiles/32)][MAXP]
+    u32 ordered;       // 1: output in store order (two-level prefix)  0: tile completion order (atomic cursor)
     u32* ticket;
     u64 epoch;
-    u32* totals;  // [MAXP] in: rows written by earlier segments; out: rows written so far
+    const u32* totals_in;  // [MAXP] rows written by earlier segments
+    u32* totals_out;       // [MAXP] rows written so far (ordered: a different array than totals_in; unordered: the same, used as atomic cursor)
     u32* kmin;    // [MAXP]
     u32* kmax;    // [MAXP]
 };
@@ -88,9 +91,12 @@ struct ProbeDParams {
     u32 n_ops;
     NumTab nt;
     u64* tile_state;
+    u64* block_state;
+    u32 ordered;
     u32* ticket;
     u64 epoch;
-    u32* total;
+    u32* total;            // result row count; must be zero at launch
+    const u32* zero_word;  // a word that stays zero (ordered mode reads its base from here)
     const u32* abort_flag;  // non-null: exit immediately if *abort_flag != 0 (a direct build met duplicate keys)
 };
 void launch_probe_direct(const ProbeDParams& p, int n_sms, cudaStream_t st);
@@ -115,9 +121,12 @@ struct ProbeCParams {
     u32 n_ops;
     NumTab nt;
     u64* tile_state;
+    u64* block_state;
+    u32 ordered;
     u32* ticket;
     u64 epoch;
     u32* total;
+    const u32* zero_word;
 };
 void launch_probe_chained(const ProbeCParams& p, int n_sms, cudaStream_t st);
 

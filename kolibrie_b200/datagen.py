@@ -47,6 +47,8 @@ class EmployeeData:
     n_employees: int
     salary_of_employee: np.ndarray = field(repr=False, default=None)
     title_of_employee: np.ndarray = field(repr=False, default=None)
+    sal_id_by_value: np.ndarray = field(repr=False, default=None)    # id of the literal str(30000+k), -1 if never drawn
+    title_id_by_value: np.ndarray = field(repr=False, default=None)  # id of POSITIONS[k], -1 if never drawn
 
     @property
     def n_triples(self) -> int:
@@ -118,7 +120,61 @@ def employee_dataset(n_employees: int, seed: int = 42, first: int = 1, global_id
     isn = np.zeros(n_ids, dtype=np.uint8)
     num[sal_new_id[first_s]] = uniq_sal.astype(np.float64)
     isn[sal_new_id[first_s]] = 1
-    return EmployeeData(s, p, o, n_ids, ids, num, isn, E, salary_of_employee=salary, title_of_employee=title_idx)
+    return EmployeeData(s, p, o, n_ids, ids, num, isn, E, salary_of_employee=salary, title_of_employee=title_idx,
+                        sal_id_by_value=sal_id_by_value, title_id_by_value=title_id_by_value)
+
+
+def mix32_np(x: np.ndarray) -> np.ndarray:
+    """kb_shard_of's hash (murmur3 finaliser) on a uint32 array"""
+    with np.errstate(over="ignore"):
+        x = x.astype(np.uint32).copy()
+        x ^= x >> np.uint32(16)
+        x *= np.uint32(0x85EBCA6B)
+        x ^= x >> np.uint32(13)
+        x *= np.uint32(0xC2B2AE35)
+        x ^= x >> np.uint32(16)
+    return x
+
+
+def employee_shard(n_total: int, rank: int, world: int, seed: int = 42, prefix: int = 4_000_000) -> EmployeeData:
+    """The triples of the GLOBAL n_total-employee dataset whose subject id hashes to `rank` (mix32(subject) % world), in global
+    document order — i.e. one GPU's shard under hash(subject) sharding. Ids are those of the global dictionary:
+    once every title and salary literal has been seen (a few million employees) each further employee consumes exactly one id,
+    so the tail is closed-form and a rank never materialises the other ranks' rows."""
+    if world == 1:
+        return employee_dataset(n_total, seed)
+    P = min(prefix, n_total)
+    while True:
+        head = employee_dataset(P, seed)
+        complete = (head.sal_id_by_value >= 0).all() and (head.title_id_by_value >= 0).all()
+        if complete or P == n_total:
+            break
+        P = min(P * 2, n_total)
+    subj_head = head.s[0::6]
+    keep = mix32_np(subj_head) % np.uint32(world) == np.uint32(rank)
+    rows = np.repeat(keep, 6)
+    S, Pp, Oo = [head.s[rows]], [head.p[rows]], [head.o[rows]]
+    n_emp = int(keep.sum())
+    chunk = 8_000_000
+    preds = np.array([1, 2, 4, 6, 8, 10], dtype=np.uint32)
+    for a in range(P, n_total, chunk):
+        b = min(a + chunk, n_total)
+        i = np.arange(a, b, dtype=np.uint64)
+        subj = (np.uint64(head.n_ids) + (i - np.uint64(P))).astype(np.uint32)
+        k = mix32_np(subj) % np.uint32(world) == np.uint32(rank)
+        i, subj = i[k], subj[k]
+        r_title = splitmix64_at(seed, 2 * i)
+        r_sal = splitmix64_at(seed, 2 * i + 1)
+        t_obj = head.title_id_by_value[(r_title % np.uint64(3)).astype(np.int64)]
+        s_obj = head.sal_id_by_value[(r_sal % np.uint64(120000)).astype(np.int64)]
+        m = len(subj)
+        o = np.empty(6 * m, dtype=np.uint32)
+        o[0::6] = subj; o[1::6] = t_obj; o[2::6] = 5; o[3::6] = 7; o[4::6] = 9; o[5::6] = s_obj
+        S.append(np.repeat(subj, 6)); Pp.append(np.tile(preds, m)); Oo.append(o)
+        n_emp += m
+    n_ids = head.n_ids + (n_total - P)
+    return EmployeeData(np.concatenate(S), np.concatenate(Pp), np.concatenate(Oo), n_ids, head.ids, head.num_or0, head.is_num, n_emp,
+                        sal_id_by_value=head.sal_id_by_value, title_id_by_value=head.title_id_by_value)
 
 
 def employee_queries(d: EmployeeData):

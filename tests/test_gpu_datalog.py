@@ -1,0 +1,91 @@
+"""GPU (-m gpu): Datalog fixpoint on the device vs the reference's fc_* known answers and vs the oracle, through the
+reference-shaped Reasoner mirror (kolibrie_b200/engine.py)."""
+import numpy as np
+import pytest
+
+from kolibrie_b200 import capi as c
+from kolibrie_b200 import datagen
+from kolibrie_b200.engine import Reasoner, compile_rule
+from tests import helpers as H
+from tests import oracle_api as O
+
+pytestmark = pytest.mark.gpu
+
+FC = H.load("datalog_fc.json")["cases"]
+
+
+def inferred(r, s, p, o):
+    return len(r.query_abox(s, p, o)) > 0
+
+
+@pytest.mark.parametrize("case", FC, ids=[x["name"] for x in FC])
+def test_fc_like_the_reference_test(ctx, case):
+    """reads like datalog/tests/reasoning_tests.rs: add_abox_triple / add_rule / infer_new_facts_semi_naive / query_abox"""
+    d, facts, rules = H.build_fc_case(case)
+    r = Reasoner(ctx)
+    for s, p, o in case["facts"]:
+        r.add_abox_triple(s, p, o)
+    for name in case["encode_after"]:
+        r.dictionary.encode(name)
+    assert r.dictionary.id_to_string == d.id_to_string
+    for rule in rules:
+        r.add_rule(rule)
+    new_facts = r.infer_new_facts_semi_naive()
+    for t in case["present"]:
+        assert inferred(r, *t), f"{t} should be derivable"
+    for t in case["absent"]:
+        assert not inferred(r, *t), f"{t} must not be derivable"
+    if case.get("expect_empty"):
+        assert new_facts == []
+    if case.get("idempotent"):
+        assert r.infer_new_facts_semi_naive() == [], "second inference pass derives nothing new"
+        for t in case["exactly_once"]:
+            assert len(r.query_abox(*t)) == 1
+    # and bit-exact against the oracle, including the per-round delta sizes
+    db = O.Db(facts[:, 0], facts[:, 1], facts[:, 2], *d.numeric_table())
+    want = db.fixpoint([compile_rule(x) for x in rules], c.SEMI_NAIVE)
+    H.assert_same_bag(np.array(new_facts, dtype=np.uint32).reshape(-1, 3), want["facts"], case["name"])
+
+
+@pytest.mark.parametrize("strategy", [c.SEMI_NAIVE, c.NAIVE])
+def test_taxonomy_closure_vs_oracle(ctx, strategy):
+    """config 4 shape at 1/1000 scale: R1 transitive subClassOf, R2 type propagation; rounds and per-round counts must match"""
+    t = datagen.taxonomy_dataset(fanout=4, depth=5, n_instances=20000)
+    rules = datagen.taxonomy_rules(t)
+    ctx.store_load(t.s, t.p, t.o)
+    rel, st = ctx.datalog_fixpoint(rules, strategy)
+    want = O.Db(t.s, t.p, t.o).fixpoint(rules, strategy)
+    assert want["status"] == 0
+    H.assert_same_bag(rel.to_numpy([0, 1, 2]), want["facts"], "closure")
+    assert st.rounds == len(want["round_new"])
+    assert [st.round_new[i] for i in range(st.rounds)] == want["round_new"]
+    assert st.derivations == want["derivations"]
+    # closed form: every class at depth k has k proper ancestors
+    n_sc = sum((4 ** k) * k for k in range(6))
+    sc = t.ids["rdfs:subClassOf"]
+    got_sc = int((rel.to_numpy([0, 1, 2])[:, 1] == sc).sum()) + int((t.p == sc).sum())
+    assert got_sc == n_sc
+    # the store now holds base + inferred; a second run derives nothing
+    rel2, st2 = ctx.datalog_fixpoint(rules, strategy)
+    assert rel2.n_rows == 0 and st2.rounds == 0
+
+
+def test_rule_filters_and_constants_quirks(ctx):
+    """numeric rule filter (rules.rs:148-160) and quirk Q6: constants in subject/object premise positions are NOT enforced"""
+    from kolibrie_b200.engine import Constant, FilterCondition, Rule, Variable
+
+    r = Reasoner(ctx)
+    for s, p, o in [("a", "age", "30"), ("b", "age", "17"), ("c", "age", "x"), ("a", "type", "Person"), ("b", "type", "Robot")]:
+        r.add_abox_triple(s, p, o)
+    age, adult, typ, human = (r.dictionary.encode(x) for x in ("age", "adult", "type", "human"))
+    yes, person = r.dictionary.encode("yes"), r.dictionary.encode("Person")
+    r.add_rule(Rule([(Variable("X"), Constant(age), Variable("A"))], [(Variable("X"), Constant(adult), Constant(yes))], [FilterCondition("A", ">=", "18")]))
+    r.add_rule(Rule([(Variable("X"), Constant(typ), Constant(person))], [(Variable("X"), Constant(human), Constant(yes))]))
+    got = set(r.infer_new_facts_semi_naive())
+    d = r.dictionary
+    facts = np.array(r._facts[:5], dtype=np.uint32)
+    want = O.Db(facts[:, 0], facts[:, 1], facts[:, 2], *d.numeric_table()).fixpoint([compile_rule(x) for x in r.rules])
+    assert got == {tuple(int(v) for v in row) for row in want["facts"]}
+    a, b = d.lookup("a"), d.lookup("b")
+    assert (a, adult, yes) in got and (b, adult, yes) not in got
+    assert (b, human, yes) in got, "quirk Q6: (?x type Person) matches every type triple in the reference"

@@ -1,0 +1,280 @@
+"""GPU (-m gpu): the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs — bit-exact on u32 ids, compared as
+bags (canonical sort), because the reference's own row order is hash-iteration order."""
+import numpy as np
+import pytest
+
+from kolibrie_b200 import capi as c
+from kolibrie_b200 import datagen
+from kolibrie_b200.engine import Dictionary
+from tests import helpers as H
+from tests import oracle_api as O
+
+pytestmark = pytest.mark.gpu
+
+S, P, Ob = 0, 1, 2
+
+
+def load(ctx, d):
+    ctx.store_load(d.s, d.p, d.o)
+    ctx.dict_numeric_load(d.num_or0, d.is_num)
+    return O.Db(d.s, d.p, d.o, d.num_or0, d.is_num)
+
+
+_EMP = {}
+
+
+@pytest.fixture
+def emp(ctx):
+    """20 000-employee store: generated once, (re)loaded for every test that asks for it (other tests replace the store)"""
+    if "d" not in _EMP:
+        _EMP["d"] = datagen.employee_dataset(20000)
+    d = _EMP["d"]
+    return d, load(ctx, d)
+
+
+def random_store(seed, n, n_terms=50, n_preds=5):
+    rng = np.random.default_rng(seed)
+    tr = np.stack([rng.integers(0, n_terms, n), rng.integers(100, 100 + n_preds, n), rng.integers(0, n_terms, n)], axis=1).astype(np.uint32)
+    return np.unique(tr, axis=0)
+
+
+def test_integration_fixture_on_device(ctx):
+    fx = H.load("integration_fixture.json")
+    tr = np.array(fx["triples"], dtype=np.uint32)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    ex = fx["expect"]
+    r = ctx.scan([c.pattern(c.K(0), c.V(P), c.V(Ob)), c.pattern(c.V(S), c.K(3), c.V(Ob)), c.pattern(c.V(S), c.V(P), c.K(10)),
+                  c.pattern(c.V(S), c.K(6), c.K(2))])
+    assert [x.n_rows for x in r[:3]] == [ex["subject==person1"], ex["predicate==ex:name"], ex["object==Jane Doe"]]
+    assert sorted(r[3].column(0).tolist()) == ex["worksFor_company1_subjects"]
+    # store order == ascending output (deterministic compaction)
+    assert r[0].to_numpy([P, Ob]).tolist() == [[3, 9], [4, 12], [5, 14], [6, 2]]
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 2047, 2048, 2049, 70001])
+def test_scan_edges_vs_oracle(ctx, n):
+    """empty, sub-tile, exact-tile and ragged stores; constants in every position; repeated variable; all patterns in ONE pass"""
+    tr = random_store(n, n) if n else np.empty((0, 3), np.uint32)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2])
+    pats = [c.pattern(c.V(S), c.K(101), c.V(Ob)), c.pattern(c.K(7), c.V(P), c.V(Ob)), c.pattern(c.V(S), c.V(P), c.K(3)),
+            c.pattern(c.K(7), c.K(101), c.V(Ob)), c.pattern(c.V(S), c.K(102), c.K(3)), c.pattern(c.V(S), c.V(P), c.V(Ob)),
+            c.pattern(c.V(S), c.K(103), c.V(S)), c.pattern(c.K(7), c.K(101), c.K(3))]
+    rels = ctx.scan(pats)
+    for pt, r in zip(pats, rels):
+        want = db.scan(pt)
+        assert r.slots == want.slots
+        got = r.to_numpy()
+        assert np.array_equal(got, want.to_numpy()), "ordered compaction must reproduce store order exactly"
+
+
+def test_scan_multi_segment_and_evict(ctx):
+    tr = random_store(5, 30000)
+    parts = np.array_split(tr, 5)
+    ctx.store_clear()
+    for i, pt in enumerate(parts):
+        ctx.store_append(pt[:, 0], pt[:, 1], pt[:, 2], tag=100 + i)
+    assert ctx.store_size() == (len(tr), 5)
+    pat = c.pattern(c.V(S), c.K(102), c.V(Ob))
+    assert np.array_equal(ctx.scan([pat])[0].to_numpy(), O.Db(tr[:, 0], tr[:, 1], tr[:, 2]).scan(pat).to_numpy())
+    ctx.store_evict(102)  # RSP slide: drop the third segment
+    rest = np.concatenate([parts[0], parts[1], parts[3], parts[4]])
+    assert np.array_equal(ctx.scan([pat])[0].to_numpy(), O.Db(rest[:, 0], rest[:, 1], rest[:, 2]).scan(pat).to_numpy())
+    with pytest.raises(c.KolibrieError):
+        ctx.store_evict(999)
+    # kb_store_delete = set difference by value (SparqlDatabase::delete_triple)
+    dele = rest[::7]
+    ctx.store_delete(dele[:, 0], dele[:, 1], dele[:, 2])
+    keep = np.array(sorted(set(map(tuple, rest.tolist())) - set(map(tuple, dele.tolist()))), dtype=np.uint32)
+    s, p, o = ctx.store_download()
+    H.assert_same_bag(np.stack([s, p, o], axis=1), keep, "store after delete")
+
+
+def test_filter_programs_vs_oracle(ctx, emp):
+    d, db = emp
+    sal = d.ids["ds:annual_salary"]
+    rel = ctx.scan([c.pattern(c.V(0), c.K(sal), c.V(2))])[0]
+    orel = db.scan(c.pattern(c.V(0), c.K(sal), c.V(2)))
+    some_salary = int(d.o[5])
+    progs = [
+        [c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_GT, value=100000.0)],
+        [c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_GE, value=60000.0), c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_LT, value=61000.0), c.fop(c.F_AND)],
+        [c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_LE, value=31000.0), c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_GT, value=149000.0), c.fop(c.F_OR), c.fop(c.F_NOT)],
+        [c.fop(c.F_EQ_ID, slot=2, id=some_salary)],
+        [c.fop(c.F_NE_ID, slot=2, id=some_salary)],
+        [c.fop(c.F_EQ_ID, slot=2, id=c.KB_ID_NONE)],          # literal not in the dictionary: = is false ...
+        [c.fop(c.F_NE_ID, slot=2, id=c.KB_ID_NONE)],          # ... != is true (types.rs:131-132)
+        [c.fop(c.F_CMP_NUM, slot=0, cmp=c.CMP_GE, value=0.0)],  # non-numeric term compares as 0.0 (unwrap_or)
+        [c.fop(c.F_CMP_NUM, slot=0, cmp=c.CMP_GT, value=0.0)],
+        # arithmetic: (?s * 2 - 100000) / 1000 truthy; division by zero and non-numeric operands make the expression false
+        [c.fop(c.F_PUSH_VAR, slot=2), c.fop(c.F_PUSH_CONST, value=2.0), c.fop(c.F_MUL), c.fop(c.F_PUSH_CONST, value=100000.0), c.fop(c.F_SUB),
+         c.fop(c.F_PUSH_CONST, value=1000.0), c.fop(c.F_DIV), c.fop(c.F_TRUTHY)],
+        [c.fop(c.F_PUSH_VAR, slot=2), c.fop(c.F_PUSH_CONST, value=0.0), c.fop(c.F_DIV), c.fop(c.F_TRUTHY)],
+        [c.fop(c.F_PUSH_VAR, slot=0), c.fop(c.F_PUSH_CONST, value=1.0), c.fop(c.F_ADD), c.fop(c.F_TRUTHY)],
+        [c.fop(c.F_IS_TRIPLE, slot=0), c.fop(c.F_NOT)],
+    ]
+    for prog in progs:
+        got = ctx.filter(rel, prog).to_numpy()
+        want = db.filter(orel, prog).to_numpy()
+        assert np.array_equal(got, want), prog[0].op
+    # pushed down into the scan: same rows
+    got = ctx.scan([c.pattern(c.V(0), c.K(sal), c.V(2))], [progs[1]])[0].to_numpy()
+    assert np.array_equal(got, db.filter(orel, progs[1]).to_numpy())
+
+
+@pytest.mark.parametrize("q", ["cfg1", "cfg2", "cfg3", "star3"])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_employee_queries_vs_oracle(ctx, emp, q, mode):
+    """BASELINE.md §4 queries: fused star join (scan + direct build + multiway probe) vs oracle columnar AND faithful modes"""
+    d, db = emp
+    js, pats, filt = datagen.employee_queries(d)[q]
+    got = ctx.star_join(js, pats, filt)
+    want = db.bgp(pats, filt, mode=mode)
+    assert sorted(got.slots) == sorted(want.slots)
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), q)
+    got2 = ctx.bgp_execute(pats, filt)
+    H.assert_same_bag(got2.to_numpy(sorted(got2.slots)), want.to_numpy(sorted(want.slots)), q + " via kb_bgp_execute")
+
+
+def test_star_join_is_deterministic_and_ordered(ctx, emp):
+    d, db = emp
+    js, pats, filt = datagen.employee_queries(d)["cfg2"]
+    a = ctx.star_join(js, pats, filt).to_numpy([0, 1, 2, 3])
+    b = ctx.star_join(js, pats, filt).to_numpy([0, 1, 2, 3])
+    assert np.array_equal(a, b), "same query twice -> identical row order"
+    assert (np.diff(a[:, 0].astype(np.int64)) > 0).all(), "probe order = store order = ascending subject"
+
+
+def test_star_join_multivalued_falls_back_to_chained(ctx):
+    """1:N predicates (duplicate keys on the build side) cannot use the direct table: same bag through the chained path"""
+    rng = np.random.default_rng(3)
+    n = 4000
+    subj = rng.integers(0, 600, n)
+    tr = np.unique(np.stack([subj, rng.integers(100, 103, n), rng.integers(1000, 1040, n)], axis=1).astype(np.uint32), axis=0)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2])
+    pats = [c.pattern(c.V(0), c.K(100), c.V(1)), c.pattern(c.V(0), c.K(101), c.V(2)), c.pattern(c.V(0), c.K(102), c.V(3))]
+    want = db.bgp(pats).to_numpy([0, 1, 2, 3])
+    assert len(want) > n  # real 1:N blow-up
+    for _ in range(2):  # second run takes the cached "multi-valued" route directly
+        H.assert_same_bag(ctx.star_join(0, pats).to_numpy([0, 1, 2, 3]), want, "1:N star")
+    # a pattern that shares a NON-join variable with another (quirk Q3) must still be a natural join
+    pats2 = [c.pattern(c.V(0), c.K(100), c.V(1)), c.pattern(c.V(0), c.K(101), c.V(1))]
+    H.assert_same_bag(ctx.star_join(0, pats2).to_numpy([0, 1]), db.bgp(pats2).to_numpy([0, 1]), "shared non-join variable")
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_hash_join_shapes_vs_oracle(ctx, seed):
+    """binary natural joins: 1 and 2 common variables, 1:N both ways, empty sides, cartesian product"""
+    rng = np.random.default_rng(seed)
+
+    def rel(slots, n, hi):
+        cols = [rng.integers(0, hi, n).astype(np.uint32) for _ in slots]
+        return ctx.rel_from_host(slots, cols), O.rel_from_host(slots, cols)
+
+    for (ls, ln, rs, rn, hi) in [((0, 1), 3000, (1, 2), 5000, 200), ((0, 1, 2), 2500, (1, 2, 3), 1800, 12), ((0, 1), 700, (0, 1), 900, 30),
+                                 ((0, 1), 0, (1, 2), 50, 10), ((0, 1), 40, (2, 3), 30, 10), ((0,), 3000, (0, 5), 10, 4)]:
+        (gl, ol), (gr, orr) = rel(ls, ln, hi), rel(rs, rn, hi)
+        got = ctx.hash_join(gl, gr)
+        want = O.hash_join(ol, orr)
+        assert sorted(got.slots) == sorted(want.slots)
+        H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"{ls}x{rs}")
+
+
+def test_bgp_path_join_vs_oracle(ctx):
+    """object->subject path (no star variable): scan all patterns in one pass, then chained joins"""
+    tr = random_store(11, 20000, n_terms=400, n_preds=4)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2])
+    pats = [c.pattern(c.V(0), c.K(100), c.V(1)), c.pattern(c.V(1), c.K(101), c.V(2)), c.pattern(c.V(2), c.K(102), c.V(3))]
+    got = ctx.bgp_execute(pats, project=[0, 3])
+    want = db.bgp(pats, project=[0, 3])
+    H.assert_same_bag(got.to_numpy([0, 3]), want.to_numpy([0, 3]), "3-hop path")
+
+
+def test_group_aggregate_vs_oracle(ctx, emp):
+    d, db = emp
+    js, pats, _ = datagen.employee_queries(d)["cfg3"]
+    rel = ctx.star_join(js, pats)
+    orel = db.bgp(pats)
+    aggs = [(c.AGG_COUNT, 0), (c.AGG_SUM, 2), (c.AGG_MIN, 2), (c.AGG_MAX, 2), (c.AGG_AVG, 2)]
+    for gslots in ([1], [2], [1, 4]):
+        g = ctx.group_aggregate(rel, gslots, aggs)
+        w = db.group(orel, gslots, aggs)
+
+        def table(x):
+            keys = np.stack(x["keys"], axis=1)
+            order = np.lexsort(tuple(keys[:, k] for k in range(keys.shape[1] - 1, -1, -1)))
+            return keys[order], x["counts"][order], [v[order] for v in x["values"]]
+
+        gk, gc, gv = table(g)
+        wk, wc, wv = table(w)
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc)
+        for a, b in zip(gv, wv):
+            # salaries are integers: sums stay exact in f64 (< 2^53), so equality is exact; AVG within 1 ulp-ish
+            assert np.allclose(a, b, rtol=1e-12, atol=0)
+
+
+def test_legacy_ffi_symbol(ctx):
+    """perform_hash_join_cuda as Kolibrie's hash_join_cuda calls it (cuda_join.rs:28-60): ascending indices, literal honoured"""
+    d = datagen.employee_dataset(60000)  # 360 000 triples: beyond the reference stub's ~303 K clamp (cuda_join.cu:81-88)
+    pred = d.ids["foaf:title"]
+    want = O.legacy_select(d.p, d.o, pred)
+    got = c.legacy_hash_join_cuda(d.s, d.p, d.o, pred)
+    assert np.array_equal(got, want) and len(got) == 60000
+    lit = d.ids["Developer"]
+    assert np.array_equal(c.legacy_hash_join_cuda(d.s, d.p, d.o, pred, lit), O.legacy_select(d.p, d.o, pred, lit))
+    assert len(c.legacy_hash_join_cuda(d.s[:0], d.p[:0], d.o[:0], pred)) == 0
+    # the same symbol from the library name Kolibrie links (libcudajoin.so)
+    assert np.array_equal(c.legacy_hash_join_cuda(d.s, d.p, d.o, pred, libpath=c.LEGACY_LIB_PATH), want)
+
+
+def test_legacy_vs_reference_cuda_stub():
+    """oracle/_ref/libcudajoin_ref.so is the reference's OWN cuda_join.cu compiled for sm_100a. Inside the range its clamped grid
+    covers, our symbol must return the same index SET (the reference's order is atomicAdd arrival order)."""
+    import os
+
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libcudajoin_ref.so")
+    if not os.path.exists(ref):
+        pytest.skip("reference CUDA stub not built")
+    d = datagen.employee_dataset(30000)  # 180 000 triples < 148 SMs * 2048 threads
+    pred = d.ids["ds:annual_salary"]
+    theirs = c.legacy_hash_join_cuda(d.s, d.p, d.o, pred, libpath=ref)
+    ours = c.legacy_hash_join_cuda(d.s, d.p, d.o, pred)
+    assert np.array_equal(np.sort(theirs), ours)
+
+
+def test_star_join_host_one_shot(ctx, emp):
+    d, db = emp
+    js, pats, filt = datagen.employee_queries(d)["cfg2"]
+    rows, slots = ctx.star_join_host(d.s, d.p, d.o, js, pats, filt)
+    ctx.dict_numeric_load(d.num_or0, d.is_num)
+    want = db.bgp(pats, filt)
+    H.assert_same_bag(rows[:, [slots.index(s) for s in sorted(slots)]], want.to_numpy(sorted(want.slots)), "host one-shot")
+    ctx.store_load(d.s, d.p, d.o)
+
+
+def test_partition_for_shuffle(ctx, emp):
+    d, db = emp
+    rel = ctx.scan([c.pattern(c.V(0), c.K(d.ids["foaf:title"]), c.V(1))])[0]
+    base = rel.to_numpy([0, 1])
+    for g in (2, 8):
+        part, offs = ctx.partition(rel, 1, g)
+        rows = part.to_numpy([0, 1])
+        assert offs[0] == 0 and offs[-1] == len(base)
+        for r in range(g):
+            chunk = rows[offs[r]:offs[r + 1]]
+            assert all(c.lib().kb_shard_of(int(k), g) == r for k in np.unique(chunk[:, 1]))
+        H.assert_same_bag(rows, base, "partition is a permutation")
+
+
+def test_errors_are_reported_not_swallowed(ctx):
+    with pytest.raises(c.KolibrieError) as e:
+        ctx.scan([c.pattern(c.V(0), c.K(c.KB_ID_NONE), c.V(1))])
+    assert e.value.status == c.KB_E_INVALID
+    with pytest.raises(c.KolibrieError) as e:
+        ctx.star_join(9, [c.pattern(c.V(0), c.K(1), c.V(1)), c.pattern(c.V(0), c.K(2), c.V(2))])
+    assert e.value.status == c.KB_E_INVALID
+    with pytest.raises(c.KolibrieError) as e:
+        ctx.filter(ctx.rel_from_host([0], [np.arange(4, dtype=np.uint32)]), [c.fop(c.F_AND)])
+    assert e.value.status == c.KB_E_INVALID
