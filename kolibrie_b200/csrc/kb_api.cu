@@ -271,8 +271,41 @@ static kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // scan
-kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vector<FilterProg>& pushdown, const int* stat_slot, bool want_index,
-                    std::vector<std::unique_ptr<kb_rel>>* out, std::vector<u32>* kmin, std::vector<u32>* kmax) {
+kb_status segment_stats(kb_ctx* ctx, Segment* sg) {
+    if (sg->has_stats || sg->n == 0) { sg->has_stats = true; return KB_OK; }
+    const u32 off = ctrl_alloc(ctx, 8);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0xFF, 4 * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off + 4, 0, 4 * sizeof(u32), ctx->st));
+    const u32* cols[3] = {sg->s.ptr, sg->p.ptr, sg->o.ptr};
+    timer_begin(ctx, F_OTHER, 3);
+    for (int c = 0; c < 3; c++) launch_col_minmax(cols[c], (u32)sg->n, ctx->ctrl + off + c, ctx->ctrl + off + 4 + c, ctx->n_sms, ctx->st);
+    timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    KB_TRY(ctrl_read(ctx));
+    for (int c = 0; c < 3; c++) { sg->cmin[c] = ctx->h_ctrl[off + c]; sg->cmax[c] = ctx->h_ctrl[off + 4 + c]; }
+    sg->has_stats = true;
+    return KB_OK;
+}
+
+kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r) {
+    if (!(*r)->pair) return KB_OK;
+    auto c = std::make_unique<kb_rel>();
+    c->slots = (*r)->slots;
+    c->n = (*r)->n;
+    Col x, y;
+    KB_TRY(alloc_col(ctx, c->n, &x));
+    KB_TRY(alloc_col(ctx, c->n, &y));
+    timer_begin(ctx, F_OTHER);
+    launch_unpair(reinterpret_cast<const uint2*>((*r)->cols[0].ptr), (u32)c->n, x.ptr, y.ptr, ctx->st);
+    timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    c->cols = {x, y};
+    *r = std::move(c);
+    return KB_OK;
+}
+
+kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vector<FilterProg>& pushdown, bool want_index, bool pairs,
+                    std::vector<std::unique_ptr<kb_rel>>* out) {
     if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a fused scan takes 1..%d patterns (got %u)", MAXP, K);
     const u64 N = ctx->n_triples;
     if (N >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "store holds %llu triples; row positions are 32-bit", (unsigned long long)N);
@@ -301,12 +334,21 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
         }
         rel->slots = slots;
         for (int q = 0; q < 4; q++) sp.outp[q] = nullptr;
-        for (size_t c = 0; c < slots.size(); c++) {  // columns come out in s,p,o order = order of first appearance
-            Col col;
-            KB_TRY(alloc_col(ctx, N, &col));
+        if (pairs && !want_index && slots.size() == 2 && src[0] == 0 && src[1] == 2) {
+            Col col;  // interleaved (subject, object) rows: one 8-byte store per match
+            KB_TRY(alloc_col(ctx, 2 * N, &col));
             rel->cols.push_back(col);
-            sp.outp[src[c]] = col.ptr;
-            sp.flags |= src[c] == 0 ? SP_EMIT_S : src[c] == 1 ? SP_EMIT_P : src[c] == 2 ? SP_EMIT_O : SP_EMIT_IDX;
+            rel->pair = true;
+            sp.outp[0] = col.ptr;
+            sp.flags |= SP_PAIR;
+        } else {
+            for (size_t c = 0; c < slots.size(); c++) {  // columns come out in s,p,o order = order of first appearance
+                Col col;
+                KB_TRY(alloc_col(ctx, N, &col));
+                rel->cols.push_back(col);
+                sp.outp[src[c]] = col.ptr;
+                sp.flags |= src[c] == 0 ? SP_EMIT_S : src[c] == 1 ? SP_EMIT_P : src[c] == 2 ? SP_EMIT_O : SP_EMIT_IDX;
+            }
         }
         sp.f_begin = (u32)ops.size();
         sp.f_len = 0;
@@ -321,26 +363,16 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
             ops.insert(ops.end(), local.begin(), local.end());
             sp.f_len = (u32)local.size();
         }
-        sp.stat_src = 3;
-        if (stat_slot && stat_slot[k] >= 0) {
-            std::vector<u32> vs, vsrc;
-            pattern_vars(pt, &vs, &vsrc);
-            for (size_t i = 0; i < vs.size(); i++) if ((int)vs[i] == stat_slot[k]) sp.stat_src = vsrc[i];
-        }
         out->push_back(std::move(rel));
     }
     for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
 
     const u32 n_seg = (u32)ctx->segs.size();
-    const u32 off_tot = ctrl_alloc(ctx, 2 * MAXP), off_min = ctrl_alloc(ctx, MAXP), off_max = ctrl_alloc(ctx, MAXP);
+    const u32 off_tot = ctrl_alloc(ctx, 2 * MAXP);
     const u32 off_ticket = ctrl_alloc(ctx, std::max(n_seg, 1u));
     if (ctx->ctrl_used > kb_ctx::CTRL_WORDS - 64) return fail(ctx, KB_E_LIMIT, "too many store segments (%u)", n_seg);
-    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_min, 0xFF, MAXP * sizeof(u32), ctx->st));
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_tot, 0, 2 * MAXP * sizeof(u32), ctx->st));
-    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_max, 0, MAXP * sizeof(u32), ctx->st));
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_ticket, 0, std::max(n_seg, 1u) * sizeof(u32), ctx->st));
-    P.kmin = ctx->ctrl + off_min;
-    P.kmax = ctx->ctrl + off_max;
     u64 max_tiles = 0;
     for (auto& sg : ctx->segs) max_tiles = std::max<u64>(max_tiles, (sg.n + SCAN_TILE - 1) / SCAN_TILE);
     KB_TRY(ensure_tile_state(ctx, max_tiles));
@@ -375,13 +407,7 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
     KB_CUDA(ctx, cudaGetLastError());
     ctx->stats.rows_scanned += N;
     KB_TRY(ctrl_read(ctx));
-    if (kmin) kmin->assign(K, 0);
-    if (kmax) kmax->assign(K, 0);
-    for (u32 k = 0; k < K; k++) {
-        (*out)[k]->n = ctx->h_ctrl[off_tot + (ctx->ordered ? (n_launched & 1u) * MAXP : 0u) + k];
-        if (kmin) (*kmin)[k] = ctx->h_ctrl[off_min + k];
-        if (kmax) (*kmax)[k] = ctx->h_ctrl[off_max + k];
-    }
+    for (u32 k = 0; k < K; k++) (*out)[k]->n = ctx->h_ctrl[off_tot + (ctx->ordered ? (n_launched & 1u) * MAXP : 0u) + k];
     return KB_OK;
 }
 
@@ -616,10 +642,29 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
         dst->ops.insert(dst->ops.end(), c.ops.begin(), c.ops.end());
         if (had) { kb_filter_op a{}; a.op = KB_F_AND; dst->ops.push_back(a); }
     }
-    std::vector<int> stat(K, (int)join_slot);
+    // key range of the join variable from the load-time column statistics of the store (its position is the same in every
+    // pattern that can take the fused path)
+    auto key_pos = [&](u32 k) { for (size_t i = 0; i < pv[k].size(); i++) if (pv[k][i] == join_slot) return psrc[k][i]; return 0u; };
+    // fast path shape: every pattern binds exactly two variables in subject and object position (the join variable + one more)
+    bool all_pairs = K >= 2;
+    for (u32 k = 0; k < K; k++) if (!(pv[k].size() == 2 && psrc[k][0] == 0 && psrc[k][1] == 2)) all_pairs = false;
+
     std::vector<std::unique_ptr<kb_rel>> rels;
-    std::vector<u32> kmin, kmax;
-    KB_TRY(scan_impl(ctx, pats, K, pushdown, stat.data(), false, &rels, &kmin, &kmax));
+    KB_TRY(scan_impl(ctx, pats, K, pushdown, false, all_pairs, &rels));
+    if (ctx->upload_stats_off >= 0) {  // one-shot host call: the copy stream computed the column ranges chunk by chunk
+        const u32 o = (u32)ctx->upload_stats_off;
+        for (auto& sg : ctx->segs) {
+            for (int c = 0; c < 3; c++) { sg.cmin[c] = ctx->h_ctrl[o + c]; sg.cmax[c] = ctx->h_ctrl[o + 4 + c]; }
+            sg.has_stats = true;
+        }
+        ctx->upload_stats_off = -1;
+    }
+    u32 kmin = 0xFFFFFFFFu, kmax = 0;
+    for (auto& sg : ctx->segs) {
+        if (sg.n == 0) continue;
+        if (!sg.has_stats) KB_TRY(segment_stats(ctx, &sg));
+        for (u32 k = 0; k < K; k++) { const u32 c = key_pos(k); kmin = std::min(kmin, sg.cmin[c]); kmax = std::max(kmax, sg.cmax[c]); }
+    }
 
     auto empty_result = [&]() -> kb_status {
         auto r = std::make_unique<kb_rel>();
@@ -632,6 +677,7 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
 
     if (K == 1) {
         std::unique_ptr<kb_rel> r = std::move(rels[0]);
+        KB_TRY(unpair_rel(ctx, &r));
         if (!post.ops.empty()) { std::unique_ptr<kb_rel> f; KB_TRY(filter_impl(ctx, *r, post, &f)); r = std::move(f); }
         *out = std::move(r);
         return KB_OK;
@@ -643,117 +689,166 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
     for (u32 k = 0; k < K; k++) if (k != probe) builds.push_back(k);
 
     // the fused path needs: patterns share only the join variable (quirk Q3: the reference never checks the others — we must,
-    // so such shapes take the natural-join chain), dense key ranges, and single-valued keys
-    bool fused_ok = true;
+    // so such shapes take the natural-join chain), a dense key range, and single-valued keys
+    bool fused_ok = kmax >= kmin;
     for (u32 a = 0; a < K && fused_ok; a++)
         for (u32 b = a + 1; b < K && fused_ok; b++)
-            for (u32 s : pv[a]) if (s != join_slot && std::find(pv[b].begin(), pv[b].end(), s) != pv[b].end()) fused_ok = false;
-    auto key_pos = [&](u32 k) { for (size_t i = 0; i < pv[k].size(); i++) if (pv[k][i] == join_slot) return psrc[k][i]; return 0u; };
+            for (u32 s2 : pv[a]) if (s2 != join_slot && std::find(pv[b].begin(), pv[b].end(), s2) != pv[b].end()) fused_ok = false;
+    const u64 range64 = fused_ok ? (u64)kmax - kmin + 1 : 0;
     for (u32 k : builds) {
-        const u64 range = (u64)kmax[k] - kmin[k] + 1;
-        if (range > std::max<u64>(8 * rels[k]->n, 1ull << 16) || range > (1ull << 31)) fused_ok = false;
+        if (range64 > std::max<u64>(8 * rels[k]->n, 1ull << 16) || range64 > (1ull << 31)) fused_ok = false;
         if (!pats[k].p.is_var && ctx->multi_valued.count({pats[k].p.value, key_pos(k)})) fused_ok = false;
         if (pv[k].size() > 3) fused_ok = false;
     }
+    const u32 range = (u32)range64;
+
+    auto to_columnar = [&]() -> kb_status {
+        for (u32 k = 0; k < K; k++) KB_TRY(unpair_rel(ctx, &rels[k]));
+        return KB_OK;
+    };
 
     if (fused_ok) {
-        std::unique_ptr<kb_rel> cur = std::move(rels[probe]);
+        std::unique_ptr<kb_rel> cur;  // result of the batches done so far (columnar); null = still the scan output of `probe`
         bool dup_seen = false;
         size_t done = 0;
         while (done < builds.size() && !dup_seen) {
             const size_t nb = std::min<size_t>(MAXT, builds.size() - done);
             const bool last = done + nb == builds.size();
-            ProbeDParams P{};
-            P.n_pcols = (u32)cur->cols.size();
-            for (u32 c = 0; c < P.n_pcols; c++) P.pcol[c] = cur->cols[c].ptr;
-            P.key_col = (u32)cur->col_of(join_slot);
-            P.n = (u32)cur->n;
-            P.n_tiles = (u32)((cur->n + PROBE_TILE - 1) / PROBE_TILE);
-            P.T = (u32)nb;
+            const bool fast = all_pairs && !cur;  // first batch over pair relations -> register-staged fast probe
+            const kb_rel& PR = cur ? *cur : *rels[probe];
             const u32 off = ctrl_alloc(ctx, 8 + MAXT);
             KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, (8 + MAXT) * sizeof(u32), ctx->st));
             std::vector<Buf> tables(nb);
-            std::vector<u32> out_slots = cur->slots;
+            DirectTab dt[MAXT];
+            std::vector<u32> out_slots = PR.slots;
             std::vector<OutCol> ocs;
-            for (u32 c = 0; c < P.n_pcols; c++) ocs.push_back(OutCol{OUT_PROBE, c, 0});
+            for (u32 c = 0; c < (u32)PR.slots.size(); c++) ocs.push_back(OutCol{OUT_PROBE, c, 0});
             timer_begin(ctx, F_BUILD, (int)nb);
             for (size_t t = 0; t < nb; t++) {
                 const u32 k = builds[done + t];
                 const kb_rel& B = *rels[k];
-                const u32 range = kmax[k] - kmin[k] + 1;
                 KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &tables[t]));
                 u32* tab = static_cast<u32*>(tables[t]->p);
                 KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), ctx->st));
+                DirectTab& D = dt[t];
+                D.tab = tab; D.kmin = kmin; D.range = range; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
                 const int kc = B.col_of(join_slot);
-                DirectTab& D = P.tab[t];
-                D.tab = tab; D.kmin = kmin[k]; D.range = range;
-                const u32* vals = nullptr;
-                if (B.cols.size() == 1) { D.mode = 2; D.n_pay = 0; }
-                else if (B.cols.size() == 2) {
-                    D.mode = 0; D.n_pay = 0;
-                    const int vc = kc == 0 ? 1 : 0;
-                    vals = B.cols[vc].ptr;
-                    out_slots.push_back(B.slots[vc]);
+                if (B.pair) {
+                    D.mode = 0;
+                    out_slots.push_back(B.slots[kc == 0 ? 1 : 0]);
                     ocs.push_back(OutCol{OUT_TABVAL, (u32)t, 0});
+                    launch_build_direct_pairs(reinterpret_cast<const uint2*>(B.cols[0].ptr), kc == 1 ? 1u : 0u, (u32)B.n, tab, kmin, range,
+                                              ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, ctx->st);
                 } else {
-                    D.mode = 1; D.n_pay = 0;
-                    for (size_t c = 0; c < B.cols.size(); c++) if ((int)c != kc) {
-                        D.pay[D.n_pay] = B.cols[c].ptr;
-                        out_slots.push_back(B.slots[c]);
-                        ocs.push_back(OutCol{OUT_TABPAY, (u32)t, D.n_pay});
-                        D.n_pay++;
+                    const u32* vals = nullptr;
+                    if (B.cols.size() == 1) { D.mode = 2; }
+                    else if (B.cols.size() == 2) {
+                        D.mode = 0;
+                        const int vc = kc == 0 ? 1 : 0;
+                        vals = B.cols[vc].ptr;
+                        out_slots.push_back(B.slots[vc]);
+                        ocs.push_back(OutCol{OUT_TABVAL, (u32)t, 0});
+                    } else {
+                        D.mode = 1;
+                        for (size_t c = 0; c < B.cols.size(); c++) if ((int)c != kc) {
+                            D.pay[D.n_pay] = B.cols[c].ptr;
+                            out_slots.push_back(B.slots[c]);
+                            ocs.push_back(OutCol{OUT_TABPAY, (u32)t, D.n_pay});
+                            D.n_pay++;
+                        }
                     }
+                    launch_build_direct(B.cols[kc].ptr, vals, (u32)B.n, tab, kmin, range, ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, ctx->st);
                 }
-                launch_build_direct(B.cols[kc].ptr, vals, (u32)B.n, tab, D.kmin, D.range, ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, ctx->st);
                 ctx->stats.rows_built += B.n;
             }
             timer_end(ctx);
             auto res = std::make_unique<kb_rel>();
             res->slots = out_slots;
-            P.n_out = (u32)out_slots.size();
-            for (u32 c = 0; c < P.n_out; c++) {
-                P.oc[c] = ocs[c];
-                Col col;
-                KB_TRY(alloc_col(ctx, cur->n, &col));
-                res->cols.push_back(col);
-                P.out[c] = col.ptr;
-            }
-            P.cap = (u32)cur->n;
-            P.n_ops = 0;
+            const u32 n_out = (u32)out_slots.size();
+            std::vector<FilterOp> fops;
             if (last && !post.ops.empty()) {
                 std::map<u32, u32> remap;
-                for (u32 c = 0; c < P.n_out; c++) remap[out_slots[c]] = c;
-                std::vector<FilterOp> ops;
-                if (!append_prog(&ops, post, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
-                P.n_ops = (u32)ops.size();
-                for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
+                for (u32 c = 0; c < n_out; c++) remap[out_slots[c]] = c;
+                if (!append_prog(&fops, post, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
             }
-            P.nt = numtab(ctx);
-            KB_TRY(ensure_tile_state(ctx, P.n_tiles));
-            P.tile_state = static_cast<u64*>(ctx->tile_state->p);
-            P.block_state = static_cast<u64*>(ctx->block_state->p);
-    P.ordered = ctx->ordered;
-            P.ticket = ctx->ctrl + off;
-            P.total = ctx->ctrl + off + 1;
-            P.zero_word = ctx->ctrl + off + 2;
-            P.abort_flag = ctx->ctrl + off + 8;  // MAXT consecutive duplicate flags
-            P.epoch = ctx->epoch++;
-            timer_begin(ctx, F_PROBE);
-            launch_probe_direct(P, ctx->n_sms, ctx->st);
-            timer_end(ctx);
+            std::vector<u32*> outp(n_out);
+            for (u32 c = 0; c < n_out; c++) {
+                Col col;
+                KB_TRY(alloc_col(ctx, PR.n, &col));
+                res->cols.push_back(col);
+                outp[c] = col.ptr;
+            }
+            if (fast) {
+                ProbeFParams P{};
+                P.pairs = reinterpret_cast<const uint2*>(PR.cols[0].ptr);
+                P.key_is_y = PR.col_of(join_slot) == 1 ? 1u : 0u;
+                P.n = (u32)PR.n;
+                P.n_tiles = (u32)((PR.n + PROBEF_TILE - 1) / PROBEF_TILE);
+                P.T = (u32)nb;
+                for (size_t t = 0; t < nb; t++) P.tab[t] = dt[t];
+                P.n_out = n_out;
+                for (u32 c = 0; c < n_out; c++) { P.oc[c] = ocs[c]; P.out[c] = outp[c]; }
+                P.cap = (u32)PR.n;
+                P.n_ops = (u32)fops.size();
+                for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
+                P.nt = numtab(ctx);
+                KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+                P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+                P.block_state = static_cast<u64*>(ctx->block_state->p);
+                P.ordered = ctx->ordered;
+                P.ticket = ctx->ctrl + off;
+                P.total = ctx->ctrl + off + 1;
+                P.zero_word = ctx->ctrl + off + 2;
+                P.abort_flag = ctx->ctrl + off + 8;
+                P.epoch = ctx->epoch++;
+                timer_begin(ctx, F_PROBE);
+                launch_probe_fast(P, ctx->n_sms, ctx->st);
+                timer_end(ctx);
+            } else {
+                std::unique_ptr<kb_rel> tmp;
+                const kb_rel* src = &PR;
+                if (PR.pair) {  // generic probe reads columnar input
+                    tmp = std::make_unique<kb_rel>();
+                    tmp->slots = PR.slots; tmp->cols = PR.cols; tmp->n = PR.n; tmp->pair = true;
+                    KB_TRY(unpair_rel(ctx, &tmp));
+                    src = tmp.get();
+                }
+                ProbeDParams P{};
+                P.n_pcols = (u32)src->cols.size();
+                for (u32 c = 0; c < P.n_pcols; c++) P.pcol[c] = src->cols[c].ptr;
+                P.key_col = (u32)src->col_of(join_slot);
+                P.n = (u32)src->n;
+                P.n_tiles = (u32)((src->n + PROBE_TILE - 1) / PROBE_TILE);
+                P.T = (u32)nb;
+                for (size_t t = 0; t < nb; t++) P.tab[t] = dt[t];
+                P.n_out = n_out;
+                for (u32 c = 0; c < n_out; c++) { P.oc[c] = ocs[c]; P.out[c] = outp[c]; }
+                P.cap = (u32)src->n;
+                P.n_ops = (u32)fops.size();
+                for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
+                P.nt = numtab(ctx);
+                KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+                P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+                P.block_state = static_cast<u64*>(ctx->block_state->p);
+                P.ordered = ctx->ordered;
+                P.ticket = ctx->ctrl + off;
+                P.total = ctx->ctrl + off + 1;
+                P.zero_word = ctx->ctrl + off + 2;
+                P.abort_flag = ctx->ctrl + off + 8;
+                P.epoch = ctx->epoch++;
+                timer_begin(ctx, F_PROBE);
+                launch_probe_direct(P, ctx->n_sms, ctx->st);
+                timer_end(ctx);
+            }
             KB_CUDA(ctx, cudaGetLastError());
-            ctx->stats.rows_probed += cur->n;
+            ctx->stats.rows_probed += PR.n;
             KB_TRY(ctrl_read(ctx));
             for (size_t t = 0; t < nb; t++) if (ctx->h_ctrl[off + 8 + t]) {
                 dup_seen = true;
                 const u32 k = builds[done + t];
                 if (!pats[k].p.is_var) ctx->multi_valued.insert({pats[k].p.value, key_pos(k)});
             }
-            if (dup_seen) {
-                // `cur` may already hold the result of an earlier batch; restart the chain from the scan outputs that remain
-                // joinable: earlier batches consumed builds[0..done) — keep cur and join the rest with the general operator
-                break;
-            }
+            if (dup_seen) break;
             res->n = ctx->h_ctrl[off + 1];
             cur = std::move(res);
             done += nb;
@@ -763,7 +858,9 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
             *out = select_cols(*cur, all_slots);
             return KB_OK;
         }
-        // fall through: join the remaining build relations with the chained operator
+        // a build side has duplicate keys: join what is left with the chained (multimap) operator
+        KB_TRY(to_columnar());
+        if (!cur) cur = std::move(rels[probe]);
         std::vector<u32> rest(builds.begin() + done, builds.end());
         std::sort(rest.begin(), rest.end(), [&](u32 a, u32 b) { return rels[a]->n < rels[b]->n; });
         for (size_t i = 0; i < rest.size(); i++) {
@@ -775,6 +872,7 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
         return KB_OK;
     }
     // general chain: natural joins, smallest build sides first
+    KB_TRY(to_columnar());
     std::unique_ptr<kb_rel> cur = std::move(rels[probe]);
     std::sort(builds.begin(), builds.end(), [&](u32 a, u32 b) { return rels[a]->n < rels[b]->n; });
     for (size_t i = 0; i < builds.size(); i++) {
@@ -901,6 +999,7 @@ static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, cons
         KB_CUDA(ctx, cudaMemcpyAsync(sg.o.ptr, o, n * sizeof(u32), kind, ctx->st));
         KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));  // the caller's buffers are borrowed for this call only
         if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += 3 * n * sizeof(u32);
+        KB_TRY(kb::segment_stats(ctx, &sg));
     }
     ctx->segs.push_back(sg);
     ctx->n_triples += n;
@@ -1001,7 +1100,7 @@ kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, con
         keep.ops.push_back(nt);
         std::vector<kb::FilterProg> pd{keep};
         std::vector<std::unique_ptr<kb_rel>> rels;
-        rc = kb::scan_impl(ctx, &pt, 1, pd, nullptr, false, &rels, nullptr, nullptr);
+        rc = kb::scan_impl(ctx, &pt, 1, pd, false, false, &rels);
         ctx->segs.swap(one);
         ctx->n_triples = saved;
         if (rc != KB_OK) break;
@@ -1120,7 +1219,7 @@ kb_status kb_scan(kb_ctx* ctx, const kb_pattern* pats, uint32_t n_pats, const kb
             pd[k].ops.assign(pushdown[k], pushdown[k] + pushdown_len[k]);
         }
     std::vector<std::unique_ptr<kb_rel>> rels;
-    KB_TRY(kb::scan_impl(ctx, pats, n_pats, pd, nullptr, false, &rels, nullptr, nullptr));
+    KB_TRY(kb::scan_impl(ctx, pats, n_pats, pd, false, false, &rels));
     for (u32 k = 0; k < n_pats; k++) out[k] = rels[k].release();
     if (n_pats) ctx->stats.rows_out = out[n_pats - 1]->n;
     return KB_OK;
@@ -1211,7 +1310,7 @@ kb_status kb_bgp_execute(kb_ctx* ctx, const kb_pattern* pats, uint32_t n_pats, c
             if (had) { kb_filter_op a{}; a.op = KB_F_AND; dst->ops.push_back(a); }
         }
         std::vector<std::unique_ptr<kb_rel>> rels;
-        KB_TRY(kb::scan_impl(ctx, pats, n_pats, pushdown, nullptr, false, &rels, nullptr, nullptr));
+        KB_TRY(kb::scan_impl(ctx, pats, n_pats, pushdown, false, false, &rels));
         cur = std::move(rels[0]);
         for (u32 k = 1; k < n_pats; k++) {
             std::unique_ptr<kb_rel> j;
@@ -1392,6 +1491,9 @@ kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, c
     KB_TRY(kb::alloc_col(ctx, n, &cs));
     KB_TRY(kb::alloc_col(ctx, n, &cp));
     KB_TRY(kb::alloc_col(ctx, n, &co));
+    const u32 soff = kb::ctrl_alloc(ctx, 8);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff, 0xFF, 4 * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff + 4, 0, 4 * sizeof(u32), ctx->st));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));  // allocations are stream-ordered on st; the copy stream must see them
     const u64 chunk = (u64)kb::SCAN_TILE * 4096;   // 8 Mi triples = 32 MiB per column
     std::vector<cudaEvent_t> evs;
@@ -1400,6 +1502,11 @@ kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, c
         KB_CUDA(ctx, cudaMemcpyAsync(cs.ptr + b, s + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
         KB_CUDA(ctx, cudaMemcpyAsync(cp.ptr + b, p + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
         KB_CUDA(ctx, cudaMemcpyAsync(co.ptr + b, o + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
+        {  // column ranges of this chunk, on the copy stream right behind its copies (the direct tables need the key range)
+            const u32* cc[3] = {cs.ptr + b, cp.ptr + b, co.ptr + b};
+            for (int c = 0; c < 3; c++) kb::launch_col_minmax(cc[c], (u32)m, ctx->ctrl + soff + c, ctx->ctrl + soff + 4 + c, ctx->n_sms, ctx->st_copy);
+            ctx->stats.kernel_launches += 3;
+        }
         cudaEvent_t ev;
         KB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         KB_CUDA(ctx, cudaEventRecord(ev, ctx->st_copy));
@@ -1416,10 +1523,12 @@ kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, c
     ctx->stats.h2d_bytes += 3 * n * sizeof(u32);
     ctx->store_version++;
     ctx->multi_valued.clear();
+    ctx->upload_stats_off = (int)soff;
     // scan_impl makes st wait on each segment's `ready` event right before that segment's scan kernel: copy i+1 overlaps scan i
     std::unique_ptr<kb_rel> r;
     kb_status rc = kb::star_join_impl(ctx, join_slot, pats, n_pats, filter, n_ops, &r);
     for (auto& sg : ctx->segs) sg.ready = nullptr;
+    ctx->upload_stats_off = -1;
     for (auto ev : evs) cudaEventDestroy(ev);
     if (rc != KB_OK) return rc;
     *n_cols = (u32)r->slots.size();

@@ -46,6 +46,7 @@ struct kb_rel {
     std::vector<kb::u32> slots;
     std::vector<kb::Col> cols;
     kb::u64 n = 0;
+    bool pair = false;  // internal only: slots = {subject var, object var}, cols[0] = interleaved uint2 (s,o) rows
     int col_of(kb::u32 slot) const {
         for (size_t i = 0; i < slots.size(); i++) if (slots[i] == slot) return (int)i;
         return -1;
@@ -64,6 +65,9 @@ struct Segment {
     Col s, p, o;
     u64 n = 0;
     cudaEvent_t ready = nullptr;  // set while a chunked upload is in flight: the scan waits on it
+    u32 cmin[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // per-column id range (s,p,o), computed when the segment is loaded
+    u32 cmax[3] = {0, 0, 0};
+    bool has_stats = false;
 };
 }  // namespace kb
 
@@ -82,7 +86,9 @@ struct kb_ctx {
     // tile-state buffer of the look-back prefix (never cleared: words carry the launch epoch)
     kb::Buf tile_state, block_state;
     size_t tile_state_tiles = 0;
-    kb::u32 ordered = 1;  // KOLIBRIE_ORDERED=0 selects completion-order compaction
+    // 0 (default): compaction in tile-completion order (one atomic per tile; row order of results is unspecified, as in the
+    // reference whose row order is hash-iteration order). 1 (KOLIBRIE_ORDERED=1, and always for the legacy FFI symbol): store order.
+    kb::u32 ordered = 0;
     kb::u64 epoch = 1;
     // control arena: small device words (tickets, totals, flags) zeroed at the start of every API call, mirrored in pinned memory
     kb::u32* ctrl = nullptr;
@@ -100,6 +106,7 @@ struct kb_ctx {
     // knowledge cached across calls: (predicate, key position) pairs whose direct build met duplicate keys
     std::set<std::pair<kb::u32, kb::u32>> multi_valued;
     kb::u64 store_version = 0;
+    int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges
 };
 
 namespace kb {
@@ -136,8 +143,11 @@ kb_status validate_filter(kb_ctx* ctx, const kb_filter_op* ops, u32 n);
 bool split_conjuncts(const kb_filter_op* ops, u32 n, std::vector<FilterProg>* out);
 std::set<u32> filter_slots(const FilterProg& f);
 
-kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 n_pats, const std::vector<FilterProg>& pushdown, const int* stat_slot /*per pattern or -1*/,
-                    bool want_index, std::vector<std::unique_ptr<kb_rel>>* out, std::vector<u32>* kmin, std::vector<u32>* kmax);
+// pairs=true: 2-variable (?s P ?o)-shaped patterns are emitted as interleaved (s,o) pair relations (internal fast path)
+kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 n_pats, const std::vector<FilterProg>& pushdown, bool want_index, bool pairs,
+                    std::vector<std::unique_ptr<kb_rel>>* out);
+kb_status segment_stats(kb_ctx* ctx, Segment* sg);
+kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r);
 kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);
 kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const FilterProg* post, std::unique_ptr<kb_rel>* out);
 kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 n_pats, const kb_filter_op* filter, u32 n_ops,

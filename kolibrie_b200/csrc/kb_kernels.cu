@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 4 : 2)) scan_kernel(co
     __shared__ u32 s_next;
     __shared__ u32 s_wcnt[SCAN_THREADS / 32][MAXP];
     __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
-    __shared__ u32 s_min[MAXP], s_max[MAXP];
     constexpr int NW = (K + 2) / 3;  // packed count words: three 10-bit fields each (a warp holds at most 256 matches per pattern)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -53,10 +52,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 4 : 2)) scan_kernel(co
         mbar_init(&bar, 1);
         fence_mbar_init();
     }
-    if (tid < MAXP) { s_min[tid] = EMPTY32; s_max[tid] = 0u; }
-    u32 mn[K], mx[K];
-#pragma unroll
-    for (int k = 0; k < K; k++) { mn[k] = EMPTY32; mx[k] = 0u; }
     __syncthreads();
     u32 tile = 0;
     if (tid == 0) {
@@ -114,12 +109,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 4 : 2)) scan_kernel(co
                 if (f & SP_EQ_SO) m &= eqv8(s0, s1, o0, o1);
                 if (f & SP_EQ_PO) m &= eqv8(p0, p1, o0, o1);
             }
-            if (P.pat[k].f_len != 0u) {
+            if (P.pat[k].f_len != 0u && m != 0u) {
+                const FilterOp* fo = P.ops + P.pat[k].f_begin;
+                if (P.pat[k].f_len == 1u && fo[0].op == KB_F_CMP_NUM) {  // FILTER(?x <cmp> c): gather the 8 numeric values, then compare
+                    const u32 slot = fo[0].slot, cmp = fo[0].cmp;
+                    const double cv = fo[0].value;
+                    double a[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if ((m >> j) & 1u) {
-                        u32 vals[3] = {KB_ELEM(s0, s1, j), KB_ELEM(p0, p1, j), KB_ELEM(o0, o1, j)};
-                        if (!eval_filter(P.ops + P.pat[k].f_begin, P.pat[k].f_len, vals, P.nt)) m &= ~(1u << j);
+                    for (int j = 0; j < 8; j++) {
+                        const u32 id = slot == 0u ? KB_ELEM(s0, s1, j) : (slot == 1u ? KB_ELEM(p0, p1, j) : KB_ELEM(o0, o1, j));
+                        a[j] = ((m >> j) & 1u) ? num_of(P.nt, id) : 0.0;
+                    }
+                    u32 pass = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) pass |= (cmp_num(cmp, a[j], cv) ? 1u : 0u) << j;
+                    m &= pass;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if ((m >> j) & 1u) {
+                            u32 vals[3] = {KB_ELEM(s0, s1, j), KB_ELEM(p0, p1, j), KB_ELEM(o0, o1, j)};
+                            if (!eval_filter(fo, P.pat[k].f_len, vals, P.nt)) m &= ~(1u << j);
+                        }
                     }
                 }
             }
@@ -161,58 +172,44 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 4 : 2)) scan_kernel(co
             if (lane == 0) s_excl[warp] = ex;
         }
         __syncthreads();
-        // ---- ordered write
+        // ---- write: rank = tile prefix + warp prefix + thread prefix, then a running rank over this thread's 8 triples
 #pragma unroll
         for (int k = 0; k < K; k++) {
             const u32 m = mk[k];
             if (m == 0u) continue;
             const u32 f = P.pat[k].flags;
             const u32 pos = s_excl[k] + s_wcnt[warp][k] + wex[k];
-            if (f & SP_EMIT_S) {
-                u32* out = P.pat[k].outp[0];
+            if (f & SP_PAIR) {
+                uint2* out = reinterpret_cast<uint2*>(P.pat[k].outp[0]) + pos;
 #pragma unroll
-                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = KB_ELEM(s0, s1, j);
+                for (int j = 0; j < 8; j++) {
+                    if ((m >> j) & 1u) *out = make_uint2(KB_ELEM(s0, s1, j), KB_ELEM(o0, o1, j));
+                    out += (m >> j) & 1u;
+                }
+                continue;
+            }
+            if (f & SP_EMIT_S) {
+                u32* out = P.pat[k].outp[0] + pos;
+#pragma unroll
+                for (int j = 0; j < 8; j++) { if ((m >> j) & 1u) *out = KB_ELEM(s0, s1, j); out += (m >> j) & 1u; }
             }
             if (f & SP_EMIT_P) {
-                u32* out = P.pat[k].outp[1];
+                u32* out = P.pat[k].outp[1] + pos;
 #pragma unroll
-                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = KB_ELEM(p0, p1, j);
+                for (int j = 0; j < 8; j++) { if ((m >> j) & 1u) *out = KB_ELEM(p0, p1, j); out += (m >> j) & 1u; }
             }
             if (f & SP_EMIT_O) {
-                u32* out = P.pat[k].outp[2];
+                u32* out = P.pat[k].outp[2] + pos;
 #pragma unroll
-                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = KB_ELEM(o0, o1, j);
+                for (int j = 0; j < 8; j++) { if ((m >> j) & 1u) *out = KB_ELEM(o0, o1, j); out += (m >> j) & 1u; }
             }
             if (f & SP_EMIT_IDX) {
-                u32* out = P.pat[k].outp[3];
+                u32* out = P.pat[k].outp[3] + pos;
 #pragma unroll
-                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) out[pos + __popc(m & ((1u << j) - 1u))] = P.index_base + base + first + (u32)j;
-            }
-            const u32 ss = P.pat[k].stat_src;
-            if (ss < 3u) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) if ((m >> j) & 1u) {
-                    const u32 kv = ss == 0u ? KB_ELEM(s0, s1, j) : (ss == 1u ? KB_ELEM(p0, p1, j) : KB_ELEM(o0, o1, j));
-                    mn[k] = min(mn[k], kv);
-                    mx[k] = max(mx[k], kv);
-                }
+                for (int j = 0; j < 8; j++) { if ((m >> j) & 1u) *out = P.index_base + base + first + (u32)j; out += (m >> j) & 1u; }
             }
         }
-        tile = s_next;  // written before the first __syncthreads of this iteration's compute phase, stable since
-    }
-    // key statistics: one reduction per CTA at the end
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-        if (P.pat[k].stat_src < 3u) {
-            const u32 a = __reduce_min_sync(0xffffffffu, mn[k]);
-            const u32 b = __reduce_max_sync(0xffffffffu, mx[k]);
-            if (lane == 0 && a != EMPTY32) { atomicMin(&s_min[k], a); atomicMax(&s_max[k], b); }
-        }
-    }
-    __syncthreads();
-    if (tid < K && P.pat[tid].stat_src < 3u && s_min[tid] != EMPTY32) {
-        atomicMin(&P.kmin[tid], s_min[tid]);
-        atomicMax(&P.kmax[tid], s_max[tid]);
+        tile = s_next;  // written before this iteration's barriers, stable since
     }
 }
 
@@ -296,6 +293,227 @@ void launch_build_chained(const ChainTab& t, u32 n, int n_sms, cudaStream_t st) 
     if (n == 0) return;
     int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
     build_chained_kernel<<<grid, 256, 0, st>>>(t, n);
+}
+
+__global__ void __launch_bounds__(256) build_direct_pairs_kernel(const uint2* __restrict__ kv, u32 key_is_y, u32 n, u32* __restrict__ table,
+                                                                 u32 kmin, u32 range, u32* dup_flag) {
+    const u32 stride = gridDim.x * blockDim.x;
+    bool dup = false;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 e = kv[i];
+        const u32 off = (key_is_y ? e.y : e.x) - kmin;
+        const u32 v = key_is_y ? e.x : e.y;
+        if (off < range) dup = dup || (atomicExch(&table[off], v) != EMPTY32);
+        else dup = true;
+    }
+    if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) *dup_flag = 1u;
+}
+void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    build_direct_pairs_kernel<<<grid, 256, 0, st>>>(kv, key_is_y, n, table, kmin, range, dup_flag);
+}
+
+__global__ void unpair_kernel(const uint2* __restrict__ kv, u32 n, u32* __restrict__ x, u32* __restrict__ y) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint2 e = kv[i];
+        x[i] = e.x;
+        y[i] = e.y;
+    }
+}
+void launch_unpair(const uint2* kv, u32 n, u32* x, u32* y, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)148 * 8, ((u64)n + 255) / 256);
+    unpair_kernel<<<grid, 256, 0, st>>>(kv, n, x, y);
+}
+
+__global__ void __launch_bounds__(256) col_minmax_kernel(const u32* __restrict__ col, u32 n, u32* out_min, u32* out_max) {
+    u32 mn = EMPTY32, mx = 0u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 v = col[i];
+        mn = min(mn, v);
+        mx = max(mx, v);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(out_min, mn); atomicMax(out_max, mx); }
+}
+void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + 255ull) / 256ull);
+    col_minmax_kernel<<<grid, 256, 0, st>>>(col, n, out_min, out_max);
+}
+
+// =================================================================================================================
+// K_probe (direct, FAST)
+template <int T>
+__global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __grid_constant__ ProbeFParams P) {
+    extern __shared__ __align__(128) u32 smem[];  // PROBEF_TILE pairs
+    const uint4* sm4 = reinterpret_cast<const uint4*>(smem);
+    __shared__ __align__(8) u64 bar;
+    __shared__ u32 s_next;
+    __shared__ u32 s_wcnt[PROBEF_THREADS / 32];
+    __shared__ u32 s_excl1;
+    if (P.abort_flag != nullptr) {
+        for (int t = 0; t < T; t++) if (reinterpret_cast<const volatile u32*>(P.abort_flag)[t] != 0u) return;
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    u32 tile = 0;
+    if (tid == 0) {
+        tile = atomicAdd(P.ticket, 1u);
+        s_next = tile;
+        if (tile < P.n_tiles) {
+            const u32 base = tile * (u32)PROBEF_TILE;
+            const u32 cnt = min((u32)PROBEF_TILE, P.n - base);
+            const u32 bytes = (cnt * 8u + 15u) & ~15u;
+            mbar_arrive_expect_tx(&bar, bytes);
+            tma_load_1d(smem, P.pairs + base, bytes, &bar);
+        }
+    }
+    __syncthreads();
+    tile = s_next;
+    u32 parity = 0;
+    while (tile < P.n_tiles) {
+        const u32 base = tile * (u32)PROBEF_TILE;
+        const u32 cnt = min((u32)PROBEF_TILE, P.n - base);
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        const uint4 r01 = sm4[2 * tid], r23 = sm4[2 * tid + 1];  // rows 4*tid .. 4*tid+3 as (x,y) pairs
+        __syncthreads();
+        if (tid == 0) {
+            const u32 nt = atomicAdd(P.ticket, 1u);
+            s_next = nt;
+            if (nt < P.n_tiles) {
+                const u32 nb = nt * (u32)PROBEF_TILE;
+                const u32 nc = min((u32)PROBEF_TILE, P.n - nb);
+                const u32 bytes = (nc * 8u + 15u) & ~15u;
+                mbar_arrive_expect_tx(&bar, bytes);
+                tma_load_1d(smem, P.pairs + nb, bytes, &bar);
+            }
+        }
+        u32 rx[4] = {r01.x, r01.z, r23.x, r23.z};
+        u32 ry[4] = {r01.y, r01.w, r23.y, r23.w};
+        const u32 first = (u32)tid * 4u;
+        const u32 vmask = first >= cnt ? 0u : (cnt - first >= 4u ? 0xFu : ((1u << (cnt - first)) - 1u));
+        u32 tv[4][T > 0 ? T : 1];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const u32 key = P.key_is_y ? ry[j] : rx[j];
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const u32 off = key - P.tab[t].kmin;
+                tv[j][t] = (((vmask >> j) & 1u) && off < P.tab[t].range) ? __ldg(P.tab[t].tab + off) : EMPTY32;
+            }
+        }
+        u32 m = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            bool hit = (vmask >> j) & 1u;
+#pragma unroll
+            for (int t = 0; t < T; t++) hit = hit && (tv[j][t] != EMPTY32);
+            m |= (hit ? 1u : 0u) << j;
+        }
+        if (P.n_ops != 0u && m != 0u) {
+            if (P.n_ops == 1u && P.ops[0].op == KB_F_CMP_NUM) {
+                const OutCol oc = P.oc[P.ops[0].slot];
+                const u32 cmp = P.ops[0].cmp;
+                const double cv = P.ops[0].value;
+                double a[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    u32 id = oc.kind == OUT_PROBE ? (oc.a == 0u ? rx[j] : ry[j]) : 0u;
+#pragma unroll
+                    for (int t = 0; t < T; t++) if (oc.kind == OUT_TABVAL && oc.a == (u32)t) id = tv[j][t];
+                    a[j] = ((m >> j) & 1u) ? num_of(P.nt, id) : 0.0;
+                }
+                u32 pass = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) pass |= (cmp_num(cmp, a[j], cv) ? 1u : 0u) << j;
+                m &= pass;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if ((m >> j) & 1u) {
+                        u32 vals[KB_MAX_COLS];
+                        for (u32 c = 0; c < P.n_out; c++) {
+                            const OutCol oc = P.oc[c];
+                            u32 x = oc.kind == OUT_PROBE ? (oc.a == 0u ? rx[j] : ry[j]) : 0u;
+#pragma unroll
+                            for (int t = 0; t < T; t++) if (oc.kind == OUT_TABVAL && oc.a == (u32)t) x = tv[j][t];
+                            vals[c] = x;
+                        }
+                        if (!eval_filter(P.ops, P.n_ops, vals, P.nt)) m &= ~(1u << j);
+                    }
+                }
+            }
+        }
+        const u32 c = (u32)__popc(m);
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const u32 wex = incl - c;
+        if (lane == 31) s_wcnt[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const u32 wc = lane < PROBEF_THREADS / 32 ? s_wcnt[lane] : 0u;
+            u32 wi = wc;
+#pragma unroll
+            for (int o = 1; o < PROBEF_THREADS / 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += y;
+            }
+            const u32 total = __shfl_sync(0xffffffffu, wi, PROBEF_THREADS / 32 - 1);
+            if (lane < PROBEF_THREADS / 32) s_wcnt[lane] = wi - wc;
+            const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
+            if (lane == 0) s_excl1 = ex;
+        }
+        __syncthreads();
+        if (m != 0u) {
+            const u32 pos = s_excl1 + s_wcnt[warp] + wex;
+            for (u32 cidx = 0; cidx < P.n_out; cidx++) {
+                const OutCol oc = P.oc[cidx];
+                u32* out = P.out[cidx] + pos;
+                u32 r = pos;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    u32 x = oc.kind == OUT_PROBE ? (oc.a == 0u ? rx[j] : ry[j]) : 0u;
+#pragma unroll
+                    for (int t = 0; t < T; t++) if (oc.kind == OUT_TABVAL && oc.a == (u32)t) x = tv[j][t];
+                    if (((m >> j) & 1u) && r < P.cap) *out = x;
+                    out += (m >> j) & 1u;
+                    r += (m >> j) & 1u;
+                }
+            }
+        }
+        tile = s_next;
+    }
+}
+
+void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    const size_t smem = (size_t)PROBEF_TILE * sizeof(uint2);
+    const void* fn = nullptr;
+    switch (p.T) {
+        case 1: fn = (const void*)probe_fast_kernel<1>; break;
+        case 2: fn = (const void*)probe_fast_kernel<2>; break;
+        case 3: fn = (const void*)probe_fast_kernel<3>; break;
+        default: fn = (const void*)probe_fast_kernel<4>; break;
+    }
+    const int grid = grid_for(fn, PROBEF_THREADS, smem, n_sms, p.n_tiles);
+    switch (p.T) {
+        case 1: probe_fast_kernel<1><<<grid, PROBEF_THREADS, smem, st>>>(p); break;
+        case 2: probe_fast_kernel<2><<<grid, PROBEF_THREADS, smem, st>>>(p); break;
+        case 3: probe_fast_kernel<3><<<grid, PROBEF_THREADS, smem, st>>>(p); break;
+        default: probe_fast_kernel<4><<<grid, PROBEF_THREADS, smem, st>>>(p); break;
+    }
 }
 
 // =================================================================================================================

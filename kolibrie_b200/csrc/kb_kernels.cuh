@@ -16,14 +16,14 @@ enum : u32 {
     SP_HAS_S = 1, SP_HAS_P = 2, SP_HAS_O = 4,      // constant in that position
     SP_EQ_SP = 8, SP_EQ_SO = 16, SP_EQ_PO = 32,    // same variable twice in one pattern (quirk Q4: enforced)
     SP_EMIT_S = 64, SP_EMIT_P = 128, SP_EMIT_O = 256,  // positions written to the output (columns come out in s,p,o order)
-    SP_EMIT_IDX = 512                               // global triple index (legacy FFI)
+    SP_EMIT_IDX = 512,                              // global triple index (legacy FFI)
+    SP_PAIR = 1024  // emit (subject, object) interleaved as uint2 into outp[0]: one 8-byte store per match (2-variable patterns)
 };
 struct ScanPat {
     u32 cs, cp, co;
     u32 flags;
     u32* outp[4];        // output column of position s / p / o / index (null when not emitted)
     u32 f_begin, f_len;  // pushed-down FILTER program (slots = positions 0/1/2)
-    u32 stat_src;        // position whose min/max is tracked (the join key), 3 = none
 };
 struct ScanParams {
     const u32 *s, *p, *o;
@@ -39,8 +39,6 @@ struct ScanParams {
     u64 epoch;
     const u32* totals_in;  // [MAXP] rows written by earlier segments
     u32* totals_out;       // [MAXP] rows written so far (ordered: a different array than totals_in; unordered: the same, used as atomic cursor)
-    u32* kmin;    // [MAXP]
-    u32* kmax;    // [MAXP]
 };
 void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st);
 
@@ -49,6 +47,8 @@ void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st);
 // DIRECT: dense dictionary ids make the identity a perfect hash: table[key - kmin] = payload (u32, EMPTY32 = none).
 void launch_build_direct(const u32* keys, const u32* vals /*null: row index*/, u32 n, u32* table, u32 kmin, u32 range,
                          u32* dup_flag, int n_sms, cudaStream_t st);
+// same from an interleaved (subject, object) pair relation; key_is_y selects which half is the key, the other is the payload
+void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, int n_sms, cudaStream_t st);
 // CHAINED multimap: open-addressing slots {key tag, head row} + next[] chains. Insert cost is O(1) whatever the key
 // multiplicity (1:N joins and heavy hitters of the Datalog joins).
 struct ChainTab {
@@ -100,6 +100,36 @@ struct ProbeDParams {
     const u32* abort_flag;  // non-null: exit immediately if *abort_flag != 0 (a direct build met duplicate keys)
 };
 void launch_probe_direct(const ProbeDParams& p, int n_sms, cudaStream_t st);
+
+// K_probe (direct, FAST): the probe side is a pair relation; each thread owns 4 consecutive rows held in registers, so the shared
+// tile is refilled by TMA while the rows are probed (same register-staged double buffering as K_scan).
+constexpr int PROBEF_THREADS = 256;
+constexpr int PROBEF_ITEMS = 4;
+constexpr int PROBEF_TILE = PROBEF_THREADS * PROBEF_ITEMS;  // 1024 rows = 8 KB of pairs
+struct ProbeFParams {
+    const uint2* pairs;
+    u32 key_is_y;  // which half of the pair is the join key
+    u32 n, n_tiles, T;
+    DirectTab tab[MAXT];  // mode 0 (value payload) or 2 (existence) only
+    u32 n_out;
+    OutCol oc[KB_MAX_COLS];  // OUT_PROBE: a = 0 (pair.x) / 1 (pair.y); OUT_TABVAL: a = table
+    u32* out[KB_MAX_COLS];
+    u32 cap;
+    FilterOp ops[KB_MAX_FILTER_OPS];
+    u32 n_ops;
+    NumTab nt;
+    u64* tile_state;
+    u64* block_state;
+    u32 ordered;
+    u32* ticket;
+    u64 epoch;
+    u32* total;
+    const u32* zero_word;
+    const u32* abort_flag;
+};
+void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st);
+void launch_unpair(const uint2* kv, u32 n, u32* x, u32* y, cudaStream_t st);
+void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_sms, cudaStream_t st);
 
 // K_probe (chained, binary): general natural join with 1:N matches, multi-column keys, FILTER, ordered compaction.
 // Replaces execute_optimized_hash_join_with_ids / execute_hash_join_with_ids / merge join (engine.rs:710-811, 970-1039) and

@@ -15,6 +15,7 @@ static kb_ctx* g_legacy_ctx = nullptr;
 
 static kb_status legacy_select(kb_ctx* ctx, const u32* h_p, const u32* h_o, u32 n, u32 pred, const u32* literal, u32** out_idx, u32* out_n) {
     KB_TRY(begin_call(ctx));
+    ctx->ordered = 1;  // the legacy contract returns ascending indices
     ctx->segs.clear();
     ctx->n_triples = 0;
     Segment sg;
@@ -37,7 +38,7 @@ static kb_status legacy_select(kb_ctx* ctx, const u32* h_p, const u32* h_o, u32 
     pt.o = literal ? kb_term{0, *literal} : kb_term{1, 1};
     std::vector<std::unique_ptr<kb_rel>> rels;
     std::vector<FilterProg> none;
-    KB_TRY(scan_impl(ctx, &pt, 1, none, nullptr, /*want_index=*/true, &rels, nullptr, nullptr));
+    KB_TRY(scan_impl(ctx, &pt, 1, none, /*want_index=*/true, false, &rels));
     const u64 m = rels[0]->n;
     u32* idx = static_cast<u32*>(malloc(std::max<size_t>(m * sizeof(u32), 4)));
     if (!idx) return fail(ctx, KB_E_OOM, "malloc failed");

@@ -240,7 +240,7 @@ def canonical_rows(a: np.ndarray) -> np.ndarray:
     a = np.ascontiguousarray(a, dtype=np.uint32)
     if a.ndim == 1:
         a = a.reshape(-1, 1)
-    if a.shape[0] == 0:
+    if a.shape[0] == 0 or a.shape[1] == 0:
         return a
     order = np.lexsort(tuple(a[:, k] for k in range(a.shape[1] - 1, -1, -1)))
     return a[order]

@@ -1,5 +1,7 @@
 """GPU (-m gpu): the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs — bit-exact on u32 ids, compared as
 bags (canonical sort), because the reference's own row order is hash-iteration order."""
+import os
+
 import numpy as np
 import pytest
 
@@ -12,6 +14,7 @@ from tests import oracle_api as O
 pytestmark = pytest.mark.gpu
 
 S, P, Ob = 0, 1, 2
+ORDERED = os.environ.get("KOLIBRIE_ORDERED", "0") != "0"
 
 
 def load(ctx, d):
@@ -47,8 +50,7 @@ def test_integration_fixture_on_device(ctx):
                   c.pattern(c.V(S), c.K(6), c.K(2))])
     assert [x.n_rows for x in r[:3]] == [ex["subject==person1"], ex["predicate==ex:name"], ex["object==Jane Doe"]]
     assert sorted(r[3].column(0).tolist()) == ex["worksFor_company1_subjects"]
-    # store order == ascending output (deterministic compaction)
-    assert r[0].to_numpy([P, Ob]).tolist() == [[3, 9], [4, 12], [5, 14], [6, 2]]
+    assert sorted(r[0].to_numpy([P, Ob]).tolist()) == [[3, 9], [4, 12], [5, 14], [6, 2]]
 
 
 @pytest.mark.parametrize("n", [0, 1, 31, 2047, 2048, 2049, 70001])
@@ -65,7 +67,10 @@ def test_scan_edges_vs_oracle(ctx, n):
         want = db.scan(pt)
         assert r.slots == want.slots
         got = r.to_numpy()
-        assert np.array_equal(got, want.to_numpy()), "ordered compaction must reproduce store order exactly"
+        if ORDERED:
+            assert np.array_equal(got, want.to_numpy()), "ordered compaction must reproduce store order exactly"
+        else:
+            H.assert_same_bag(got, want.to_numpy(), "scan")
 
 
 def test_scan_multi_segment_and_evict(ctx):
@@ -76,10 +81,11 @@ def test_scan_multi_segment_and_evict(ctx):
         ctx.store_append(pt[:, 0], pt[:, 1], pt[:, 2], tag=100 + i)
     assert ctx.store_size() == (len(tr), 5)
     pat = c.pattern(c.V(S), c.K(102), c.V(Ob))
-    assert np.array_equal(ctx.scan([pat])[0].to_numpy(), O.Db(tr[:, 0], tr[:, 1], tr[:, 2]).scan(pat).to_numpy())
+    same = (lambda a, b: np.array_equal(a, b)) if ORDERED else (lambda a, b: np.array_equal(H.canon(a), H.canon(b)))
+    assert same(ctx.scan([pat])[0].to_numpy(), O.Db(tr[:, 0], tr[:, 1], tr[:, 2]).scan(pat).to_numpy())
     ctx.store_evict(102)  # RSP slide: drop the third segment
     rest = np.concatenate([parts[0], parts[1], parts[3], parts[4]])
-    assert np.array_equal(ctx.scan([pat])[0].to_numpy(), O.Db(rest[:, 0], rest[:, 1], rest[:, 2]).scan(pat).to_numpy())
+    assert same(ctx.scan([pat])[0].to_numpy(), O.Db(rest[:, 0], rest[:, 1], rest[:, 2]).scan(pat).to_numpy())
     with pytest.raises(c.KolibrieError):
         ctx.store_evict(999)
     # kb_store_delete = set difference by value (SparqlDatabase::delete_triple)
@@ -116,10 +122,10 @@ def test_filter_programs_vs_oracle(ctx, emp):
     for prog in progs:
         got = ctx.filter(rel, prog).to_numpy()
         want = db.filter(orel, prog).to_numpy()
-        assert np.array_equal(got, want), prog[0].op
+        H.assert_same_bag(got, want, str(prog[0].op))
     # pushed down into the scan: same rows
     got = ctx.scan([c.pattern(c.V(0), c.K(sal), c.V(2))], [progs[1]])[0].to_numpy()
-    assert np.array_equal(got, db.filter(orel, progs[1]).to_numpy())
+    H.assert_same_bag(got, db.filter(orel, progs[1]).to_numpy(), "pushdown")
 
 
 @pytest.mark.parametrize("q", ["cfg1", "cfg2", "cfg3", "star3"])
@@ -137,12 +143,17 @@ def test_employee_queries_vs_oracle(ctx, emp, q, mode):
 
 
 def test_star_join_is_deterministic_and_ordered(ctx, emp):
+    """KOLIBRIE_ORDERED=1: output in store order, identical from run to run. Default mode: same bag, row order unspecified
+    (like the reference, whose row order is hash-iteration order)."""
     d, db = emp
     js, pats, filt = datagen.employee_queries(d)["cfg2"]
     a = ctx.star_join(js, pats, filt).to_numpy([0, 1, 2, 3])
     b = ctx.star_join(js, pats, filt).to_numpy([0, 1, 2, 3])
-    assert np.array_equal(a, b), "same query twice -> identical row order"
-    assert (np.diff(a[:, 0].astype(np.int64)) > 0).all(), "probe order = store order = ascending subject"
+    if ORDERED:
+        assert np.array_equal(a, b), "same query twice -> identical row order"
+        assert (np.diff(a[:, 0].astype(np.int64)) > 0).all(), "probe order = store order = ascending subject"
+    else:
+        H.assert_same_bag(a, b, "same query twice")
 
 
 def test_star_join_multivalued_falls_back_to_chained(ctx):
