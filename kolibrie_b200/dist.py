@@ -1,0 +1,84 @@
+"""One process per GPU: sharding + the join-key shuffle.
+
+* triples are sharded by mix32(subject) % world (`kb_shard_of` on the host, the same function the device's `kb_partition` uses);
+* a star join on the subject needs no communication: every rank joins its shard, counts are summed, times are max-reduced;
+* a join on a non-subject key shuffles the rows once: `kb_partition` (device) splits a relation into `world` contiguous ranges
+  by mix32(key) % world, `all_to_all_relation` exchanges the range sizes and then the columns with
+  `torch.distributed.all_to_all_single` — NCCL over NVLink on the GPU box, gloo in the CPU tests.
+
+Only plumbing lives here; all data-touching work is in libkolibrie_b200.so.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import datagen
+
+
+def shard_of(keys: np.ndarray, world: int) -> np.ndarray:
+    """rank owning each key: mix32(key) % world (== kb_shard_of)"""
+    return (datagen.mix32_np(np.asarray(keys, dtype=np.uint32)) % np.uint32(world)).astype(np.int64)
+
+
+def shard_triples(s: np.ndarray, p: np.ndarray, o: np.ndarray, rank: int, world: int):
+    """this rank's triples under hash(subject) sharding, store order preserved"""
+    if world == 1:
+        return s, p, o
+    keep = shard_of(s, world) == rank
+    return s[keep], p[keep], o[keep]
+
+
+def all_to_all_relation(cols: Sequence[torch.Tensor], part_offsets: Sequence[int], group=None) -> List[torch.Tensor]:
+    """`cols` are equally long 1-D tensors already partitioned into `world` contiguous ranges [part_offsets[r], part_offsets[r+1]).
+    Range r goes to rank r. Returns the received columns (ranges concatenated in source-rank order)."""
+    world = dist.get_world_size(group)
+    assert len(part_offsets) == world + 1
+    dev = cols[0].device if cols else torch.device("cpu")
+    send_counts = torch.tensor([part_offsets[r + 1] - part_offsets[r] for r in range(world)], dtype=torch.int64, device=dev)
+    recv_counts = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    sc = [int(x) for x in send_counts.tolist()]
+    rc = [int(x) for x in recv_counts.tolist()]
+    out = []
+    for c in cols:
+        recv = torch.empty(sum(rc), dtype=c.dtype, device=dev)
+        dist.all_to_all_single(recv, c.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=group)
+        out.append(recv)
+    return out
+
+
+class _DevPtr:
+    """wraps a raw device pointer of the library as a CUDA array (no copy)"""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
+def shuffle_relation(ctx, rel, key_slot: int, group=None):
+    """GPU only: re-shard `rel` so that every row lives on rank mix32(row[key_slot]) % world. Returns a new Relation."""
+    world = dist.get_world_size(group)
+    n, slots = rel.info()
+    part, offs = ctx.partition(rel, key_slot, world)
+    dev = torch.device("cuda", ctx.device)
+    cols = [torch.as_tensor(_DevPtr(part.device_ptr(i), max(n, 1)), device=dev)[:n] for i in range(len(slots))]
+    recv = all_to_all_relation(cols, offs, group)
+    torch.cuda.synchronize(dev)
+    m = int(recv[0].numel()) if recv else 0
+    out = ctx.rel_from_device(slots, [int(t.data_ptr()) for t in recv], m)
+    return out
+
+
+def sum_over_ranks(value: int, device=None, group=None) -> int:
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t[0])
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t[0])

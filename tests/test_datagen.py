@@ -45,3 +45,18 @@ def test_taxonomy_shape():
     sc = t.p == t.ids["rdfs:subClassOf"]
     assert sc.sum() == 39
     assert (t.o[sc] < t.s[sc]).all()  # parent ids precede children (breadth-first)
+
+
+def test_employee_shard_closed_form_tail():
+    """beyond the point where every salary literal has been seen, shard rows come from the closed form; they must equal the
+    rows of the full sequential dataset"""
+    E = 2_400_000
+    full = datagen.employee_dataset(E)
+    assert (full.sal_id_by_value >= 0).all()
+    parts = [datagen.employee_shard(E, r, 2, prefix=2_000_000) for r in range(2)]
+    from kolibrie_b200.dist import shard_of
+
+    for r, part in enumerate(parts):
+        keep = shard_of(full.s, 2) == r
+        assert np.array_equal(part.s, full.s[keep]) and np.array_equal(part.p, full.p[keep]) and np.array_equal(part.o, full.o[keep])
+    assert sum(p.n_employees for p in parts) == E
