@@ -25,6 +25,9 @@ struct PredRel {
     u64 delta_start = 0;  // facts [delta_start, snapshot) were added by the previous round
     u64 snapshot = 0;
     bool is_head = false;
+    Buf set;              // head predicates only: known (s,o) pairs of this predicate, 64-bit keys
+    u32 set_slots = 0;
+    u64 set_count = 0;
 };
 
 struct Premise {
@@ -47,9 +50,6 @@ struct Fix {
     kb_ctx* ctx;
     std::map<u32, PredRel> rels;
     std::vector<Pending> pend;
-    Buf set;
-    u32 set_slots = 0;
-    u64 set_count = 0;  // keys in the set (exact: every derive reports how many inserts won)
 };
 
 kb_status grow_rel(kb_ctx* ctx, PredRel& r, u64 need) {
@@ -67,36 +67,33 @@ kb_status grow_rel(kb_ctx* ctx, PredRel& r, u64 need) {
     return KB_OK;
 }
 
-// (re)build the known-fact set so that it can take `extra` more keys at load <= 0.5
-kb_status ensure_set(Fix& fx, u64 extra) {
+// (re)build the known-fact set of predicate `r` so that it can take `extra` more keys at load <= 0.5
+kb_status ensure_set(Fix& fx, PredRel& r, u64 extra) {
     kb_ctx* ctx = fx.ctx;
-    const u64 need = (fx.set_count + extra) * 2;
-    if (fx.set && need <= fx.set_slots) return KB_OK;
+    const u64 need = (r.set_count + extra) * 2;
+    if (r.set && need <= r.set_slots) return KB_OK;
     u64 slots = 1024;
-    while (slots < need * 2) slots <<= 1;
-    if (slots > (1ull << 31)) return fail(ctx, KB_E_LIMIT, "known-fact set would need %llu slots", (unsigned long long)slots);
+    while (slots < need) slots <<= 1;
+    if (slots > (1ull << 31)) return fail(ctx, KB_E_LIMIT, "known-fact set of predicate %u would need %llu slots", r.pred, (unsigned long long)slots);
     Buf nb;
-    KB_TRY(alloc_buf(ctx, slots * sizeof(uint4), &nb));
-    KB_CUDA(ctx, cudaMemsetAsync(nb->p, 0, slots * sizeof(uint4), ctx->st));
+    KB_TRY(alloc_buf(ctx, slots * sizeof(u64), &nb));
+    KB_CUDA(ctx, cudaMemsetAsync(nb->p, 0xFF, slots * sizeof(u64), ctx->st));
     const u32 off = ctrl_alloc(ctx, 4);
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
     u64 count = 0;
     timer_begin(ctx, F_BUILD);
-    for (auto& kv : fx.rels) {
-        PredRel& r = kv.second;
-        if (!r.is_head || r.n == 0) continue;
-        launch_set_insert(static_cast<uint4*>(nb->p), (u32)slots, r.s.ptr, nullptr, r.pred, r.o.ptr, (u32)r.n, ctx->ctrl + off, ctx->n_sms, ctx->st);
-        count += r.n;
-    }
+    launch_set64_insert(static_cast<u64*>(nb->p), (u32)slots, r.s.ptr, r.o.ptr, (u32)r.n, ctx->ctrl + off, ctx->n_sms, ctx->st);
+    count += r.n;
     for (auto& pd : fx.pend) {  // a rebuild in the middle of a round must keep this round's facts
-        launch_set_insert(static_cast<uint4*>(nb->p), (u32)slots, pd.s.ptr, nullptr, pd.pred, pd.o.ptr, (u32)pd.count, ctx->ctrl + off, ctx->n_sms, ctx->st);
+        if (pd.pred != r.pred) continue;
+        launch_set64_insert(static_cast<u64*>(nb->p), (u32)slots, pd.s.ptr, pd.o.ptr, (u32)pd.count, ctx->ctrl + off, ctx->n_sms, ctx->st);
         count += pd.count;
     }
     timer_end(ctx);
     KB_CUDA(ctx, cudaGetLastError());
-    fx.set = nb;
-    fx.set_slots = (u32)slots;
-    fx.set_count = count;
+    r.set = nb;
+    r.set_slots = (u32)slots;
+    r.set_count = count;
     return KB_OK;
 }
 
@@ -221,9 +218,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
             }
         }
     }
-    u64 head_base = 0;
-    for (auto& kv : fx.rels) if (kv.second.is_head) head_base += kv.second.n;
-    KB_TRY(ensure_set(fx, head_base + 1024));
+    for (auto& kv : fx.rels) if (kv.second.is_head) KB_TRY(ensure_set(fx, kv.second, kv.second.n + 1024));
 
     // ---- rounds
     for (u32 round = 0;; round++) {
@@ -264,16 +259,14 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     DeriveParams D{};
                     for (size_t k = 0; k < cur->cols.size(); k++) D.bcol[k] = cur->cols[k].ptr;
                     D.n = (u32)cur->n;
-                    D.n_heads = 1;
                     auto term = [&](const kb_term& t) {
                         HeadTerm ht;
                         ht.is_var = t.is_var;
                         ht.value = t.is_var ? (u32)cur->col_of(t.value) : t.value;
                         return ht;
                     };
-                    D.head[0][0] = term(h.s);
-                    D.head[0][1] = HeadTerm{0, h.p.value};
-                    D.head[0][2] = term(h.o);
+                    D.head_s = term(h.s);
+                    D.head_o = term(h.o);
                     D.n_filt = 0;
                     for (u32 f = 0; f < rule.n_filters; f++) {
                         const kb_rule_filter& rf = rule.filters[f];
@@ -292,19 +285,18 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                         D.filt[D.n_filt++] = d;
                     }
                     D.nt = numtab(ctx);
-                    KB_TRY(ensure_set(fx, cur->n));
-                    D.set = static_cast<uint4*>(fx.set->p);
-                    D.set_slots = fx.set_slots;
+                    PredRel& hr = fx.rels[h.p.value];
+                    KB_TRY(ensure_set(fx, hr, cur->n));
+                    D.set = static_cast<u64*>(hr.set->p);
+                    D.set_slots = hr.set_slots;
                     Pending pd;
                     pd.pred = h.p.value;
                     pd.count = 0;
                     KB_TRY(alloc_col(ctx, cur->n, &pd.s));
                     KB_TRY(alloc_col(ctx, cur->n, &pd.o));
-                    Col scratch_p;
-                    KB_TRY(alloc_col(ctx, cur->n, &scratch_p));
                     const u32 coff = ctrl_alloc(ctx, 8);
                     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff, 0, 8 * sizeof(u32), ctx->st));
-                    D.out_s = pd.s.ptr; D.out_p = scratch_p.ptr; D.out_o = pd.o.ptr;
+                    D.out_s = pd.s.ptr; D.out_o = pd.o.ptr;
                     D.out_cap = (u32)cur->n;
                     D.out_count = ctx->ctrl + coff;
                     D.overflow = ctx->ctrl + coff + 1;
@@ -320,7 +312,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     unsigned long long nd;
                     memcpy(&nd, ctx->h_ctrl + coff + 4, sizeof nd);
                     st.derivations += nd;
-                    fx.set_count += pd.count;
+                    hr.set_count += pd.count;
                     if (pd.count) fx.pend.push_back(pd);
                 }
             }

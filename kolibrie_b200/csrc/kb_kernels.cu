@@ -987,6 +987,34 @@ void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p, u3
     set_insert_kernel<<<grid, 256, 0, st>>>(set, set_slots, s, p, p_const, o, n, overflow);
 }
 
+// 64-bit (s,o) set of one predicate: returns 1 inserted now, 0 already present, 2 table full
+__device__ __forceinline__ u32 set64_insert(u64* set, u32 n_slots, u32 s, u32 o) {
+    const u64 key = ((u64)s << 32) | (u64)o;
+    const u32 mask = n_slots - 1u;
+    u32 slot = mix32(mix32(s) * 0x9E3779B1u ^ mix32(o + 0x632BE5ABu)) & mask;
+    for (u32 probes = 0; probes < n_slots; probes++) {
+        const u64 cur = *reinterpret_cast<volatile u64*>(&set[slot]);
+        if (cur == key) return 0u;
+        if (cur == EMPTY64) {
+            const u64 old = atomicCAS(reinterpret_cast<unsigned long long*>(&set[slot]), (unsigned long long)EMPTY64, (unsigned long long)key);
+            if (old == EMPTY64) return 1u;
+            if (old == key) return 0u;
+        }
+        slot = (slot + 1u) & mask;
+    }
+    return 2u;
+}
+__global__ void __launch_bounds__(256) set64_insert_kernel(u64* set, u32 set_slots, const u32* s, const u32* o, u32 n, u32* overflow) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if (set64_insert(set, set_slots, s[i], o[i]) == 2u) *overflow = 1u;
+}
+void launch_set64_insert(u64* set, u32 set_slots, const u32* s, const u32* o, u32 n, u32* overflow, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    set64_insert_kernel<<<grid, 256, 0, st>>>(set, set_slots, s, o, n, overflow);
+}
+
 __device__ __forceinline__ bool rule_filters_pass(const DeriveParams& P, u32 i) {
     for (u32 f = 0; f < P.n_filt; f++) {
         const RuleFilterDev fl = P.filt[f];
@@ -1019,29 +1047,25 @@ __global__ void __launch_bounds__(256) derive_kernel(const __grid_constant__ Der
     unsigned long long nd = 0;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         const bool pass = i < P.n && rule_filters_pass(P, i);
-        for (u32 h = 0; h < P.n_heads; h++) {
-            bool fresh = false;
-            u32 s = 0, p = 0, o = 0;
-            if (pass) {
-                nd++;
-                s = P.head[h][0].is_var ? P.bcol[P.head[h][0].value][i] : P.head[h][0].value;
-                p = P.head[h][1].is_var ? P.bcol[P.head[h][1].value][i] : P.head[h][1].value;
-                o = P.head[h][2].is_var ? P.bcol[P.head[h][2].value][i] : P.head[h][2].value;
-                const u32 r = set_insert(P.set, P.set_slots, s, p, o);
-                if (r == 2u) *P.overflow = 1u;
-                fresh = r == 1u;
-            }
-            // warp-aggregated append of the facts that were new
-            const unsigned b = __ballot_sync(0xffffffffu, fresh);
-            if (b) {
-                u32 basepos = 0;
-                if (lane == __ffs(b) - 1) basepos = atomicAdd(P.out_count, (u32)__popc(b));
-                basepos = __shfl_sync(0xffffffffu, basepos, __ffs(b) - 1);
-                if (fresh) {
-                    const u32 r = basepos + (u32)__popc(b & ((1u << lane) - 1u));
-                    if (r < P.out_cap) { P.out_s[r] = s; P.out_p[r] = p; P.out_o[r] = o; }
-                    else *P.overflow = 1u;
-                }
+        bool fresh = false;
+        u32 s = 0, o = 0;
+        if (pass) {
+            nd++;
+            s = P.head_s.is_var ? P.bcol[P.head_s.value][i] : P.head_s.value;
+            o = P.head_o.is_var ? P.bcol[P.head_o.value][i] : P.head_o.value;
+            const u32 r = set64_insert(P.set, P.set_slots, s, o);
+            if (r == 2u) *P.overflow = 1u;
+            fresh = r == 1u;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, fresh);  // warp-aggregated append of the facts that were new
+        if (b) {
+            u32 basepos = 0;
+            if (lane == __ffs(b) - 1) basepos = atomicAdd(P.out_count, (u32)__popc(b));
+            basepos = __shfl_sync(0xffffffffu, basepos, __ffs(b) - 1);
+            if (fresh) {
+                const u32 r = basepos + (u32)__popc(b & ((1u << lane) - 1u));
+                if (r < P.out_cap) { P.out_s[r] = s; P.out_o[r] = o; }
+                else *P.overflow = 1u;
             }
         }
     }

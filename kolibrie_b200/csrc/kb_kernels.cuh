@@ -193,22 +193,20 @@ struct RuleFilterDev { u32 lhs_col, cmp, rhs_is_var, rhs_col; double rhs_value; 
 struct DeriveParams {
     const u32* bcol[KB_MAX_COLS];
     u32 n;
-    HeadTerm head[KB_MAX_CONCLUSIONS][3];
-    u32 n_heads;
+    HeadTerm head_s, head_o;  // the head predicate is a constant: one known-fact set per predicate, keyed by (s << 32) | o
     RuleFilterDev filt[KB_MAX_RULE_FILTERS];
     u32 n_filt;
     NumTab nt;
-    // known-fact set: 16-byte slots {s,p,o,state}; state 0 free / 1 claimed-being-written / 2 ready
-    uint4* set;
+    u64* set;       // open addressing, EMPTY64 = free; a fact is new iff its atomicCAS wins
     u32 set_slots;  // power of two
-    // append targets
-    u32 *out_s, *out_p, *out_o;
+    u32 *out_s, *out_o;
     u32 out_cap;
     u32* out_count;               // appended so far (atomic cursor)
     unsigned long long* n_deriv;  // candidates that passed the filters
     u32* overflow;                // set or output overflow
 };
 void launch_derive(const DeriveParams& p, int n_sms, cudaStream_t st);
+void launch_set64_insert(u64* set, u32 set_slots, const u32* s, const u32* o, u32 n, u32* overflow, int n_sms, cudaStream_t st);
 void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p /*null: p_const*/, u32 p_const, const u32* o, u32 n, u32* overflow,
                        int n_sms, cudaStream_t st);
 
