@@ -142,6 +142,7 @@ typedef struct kb_stats {
     uint64_t rows_out;       /* rows of the last result */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t kernel_launches; /* launches of this library's own kernels (memsets and copies not counted) */
+    uint64_t fused_scan_builds; /* star joins whose build sides were inserted into their tables by the scan kernel itself */
 } kb_stats;
 
 /* ------------------------------------------------------------------ context */

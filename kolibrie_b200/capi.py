@@ -15,7 +15,7 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkolibrie_b200.so")
+LIB_PATH = os.environ.get("KOLIBRIE_B200_LIB") or os.path.join(_HERE, "libkolibrie_b200.so")  # override: A/B of build variants
 LEGACY_LIB_PATH = os.path.join(_HERE, "libcudajoin.so")
 
 KB_OK = 0
@@ -67,7 +67,7 @@ class KbStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("scan_ms", "build_ms", "probe_ms", "filter_ms", "group_ms", "other_ms", "total_ms")] + [
         (n, C.c_uint64)
         for n in ("scan_launches", "build_launches", "probe_launches", "filter_launches", "group_launches", "other_launches",
-                  "rows_scanned", "rows_built", "rows_probed", "rows_out", "h2d_bytes", "d2h_bytes", "kernel_launches")
+                  "rows_scanned", "rows_built", "rows_probed", "rows_out", "h2d_bytes", "d2h_bytes", "kernel_launches", "fused_scan_builds")
     ]
 
     def as_dict(self):

@@ -305,7 +305,7 @@ kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r) {
 }
 
 kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vector<FilterProg>& pushdown, bool want_index, bool pairs,
-                    std::vector<std::unique_ptr<kb_rel>>* out) {
+                    std::vector<std::unique_ptr<kb_rel>>* out, const std::vector<ScanTable>* tables) {
     if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a fused scan takes 1..%d patterns (got %u)", MAXP, K);
     const u64 N = ctx->n_triples;
     if (N >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "store holds %llu triples; row positions are 32-bit", (unsigned long long)N);
@@ -334,7 +334,15 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
         }
         rel->slots = slots;
         for (int q = 0; q < 4; q++) sp.outp[q] = nullptr;
-        if (pairs && !want_index && slots.size() == 2 && src[0] == 0 && src[1] == 2) {
+        if (tables && k < tables->size() && (*tables)[k].tab) {  // fused build: no output relation, the table is the output
+            const ScanTable& tb = (*tables)[k];
+            rel->pair = true;
+            sp.outp[0] = tb.tab;
+            sp.outp[1] = tb.dup_flag;
+            sp.cs = tb.kmin;
+            sp.co = tb.range;
+            sp.flags |= SP_TABLE | (tb.key_is_o ? SP_TKEY_O : 0u) | (tb.trusted ? SP_TTRUSTED : 0u);
+        } else if (pairs && !want_index && slots.size() == 2 && src[0] == 0 && src[1] == 2) {
             Col col;  // interleaved (subject, object) rows: one 8-byte store per match
             KB_TRY(alloc_col(ctx, 2 * N, &col));
             rel->cols.push_back(col);
@@ -611,6 +619,11 @@ static std::unique_ptr<kb_rel> select_cols(const kb_rel& in, const std::vector<u
 // star join: fused scan -> direct builds -> fused multiway probe; falls back to chained binary joins on 1:N keys
 kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 K, const kb_filter_op* filter, u32 n_ops,
                          std::unique_ptr<kb_rel>* out) {
+    return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, true, out);
+}
+
+kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 K, const kb_filter_op* filter, u32 n_ops, bool allow_fused_scan,
+                          std::unique_ptr<kb_rel>* out) {
     if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a star join takes 1..%d patterns (got %u)", MAXP, K);
     KB_TRY(validate_filter(ctx, filter, n_ops));
     std::vector<std::vector<u32>> pv(K), psrc(K);
@@ -648,6 +661,157 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
     // fast path shape: every pattern binds exactly two variables in subject and object position (the join variable + one more)
     bool all_pairs = K >= 2;
     for (u32 k = 0; k < K; k++) if (!(pv[k].size() == 2 && psrc[k][0] == 0 && psrc[k][1] == 2)) all_pairs = false;
+
+    // ---- scan + build FUSED: the build-side patterns insert straight into their direct tables while the store is scanned; only the
+    // probe-side pattern is materialised. Needs the key range before the scan (load-time statistics) and a probe side chosen without
+    // knowing the counts: the last pattern that carries no pushed-down filter (a filtered side is the smaller build side).
+    if (allow_fused_scan && all_pairs && K - 1 <= (u32)MAXT && ctx->upload_stats_off < 0 && ctx->n_triples > 0) {
+        bool ok = true;
+        u32 kmn = 0xFFFFFFFFu, kmx = 0;
+        for (auto& sg : ctx->segs) {
+            if (sg.n == 0) continue;
+            if (!sg.has_stats) KB_TRY(segment_stats(ctx, &sg));
+            for (u32 k = 0; k < K; k++) { const u32 c = key_pos(k); kmn = std::min(kmn, sg.cmin[c]); kmx = std::max(kmx, sg.cmax[c]); }
+        }
+        const u64 rng = kmx >= kmn ? (u64)kmx - kmn + 1 : 0;
+        if (rng == 0 || rng > std::max<u64>(4 * ctx->n_triples, 1ull << 16) || rng > (1ull << 31)) ok = false;
+        for (u32 a = 0; a < K && ok; a++)
+            for (u32 b = a + 1; b < K && ok; b++)
+                for (u32 s2 : pv[a]) if (s2 != join_slot && std::find(pv[b].begin(), pv[b].end(), s2) != pv[b].end()) ok = false;
+        int probe_k = -1;
+        for (u32 k = 0; k < K; k++) if (pushdown[k].ops.empty()) probe_k = (int)k;
+        if (probe_k < 0) probe_k = (int)K - 1;
+        for (u32 k = 0; k < K && ok; k++)
+            if ((int)k != probe_k && !pats[k].p.is_var && ctx->multi_valued.count({pats[k].p.value, key_pos(k)})) ok = false;
+        if (ok) {
+            const u32 range = (u32)rng;
+            const u32 off = ctrl_alloc(ctx, 8 + MAXT);
+            KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, (8 + MAXT) * sizeof(u32), ctx->st));
+            std::vector<ScanTable> st(K);
+            std::vector<Buf> tabs;
+            std::vector<u32> tab_of(K, 0);
+            DirectTab dt[MAXT];
+            std::vector<u32> out_slots = pv[probe_k];
+            std::vector<OutCol> ocs{OutCol{OUT_PROBE, 0, 0}, OutCol{OUT_PROBE, 1, 0}};
+            timer_begin(ctx, F_BUILD, 0);
+            u32 t = 0;
+            for (u32 k = 0; k < K; k++) {
+                if ((int)k == probe_k) continue;
+                Buf b;
+                KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &b));
+                KB_CUDA(ctx, cudaMemsetAsync(b->p, 0xFF, (size_t)range * sizeof(u32), ctx->st));
+                tabs.push_back(b);
+                st[k].tab = static_cast<u32*>(b->p);
+                st[k].kmin = kmn; st[k].range = range;
+                st[k].key_is_o = key_pos(k) == 2 ? 1u : 0u;
+                st[k].trusted = (!pats[k].p.is_var && ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;
+                st[k].dup_flag = ctx->ctrl + off + 8 + t;
+                DirectTab& D = dt[t];
+                D.tab = st[k].tab; D.kmin = kmn; D.range = range; D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                out_slots.push_back(pv[k][key_pos(k) == 0 ? 1 : 0]);
+                ocs.push_back(OutCol{OUT_TABVAL, t, 0});
+                tab_of[k] = t;
+                t++;
+            }
+            timer_end(ctx);
+            const u32 T = t;
+            std::vector<std::unique_ptr<kb_rel>> rels;
+            KB_TRY(scan_impl(ctx, pats, K, pushdown, false, true, &rels, &st));
+            ctx->stats.fused_scan_builds++;
+            // duplicate keys: the scan stores without reading back, so a multi-valued key shows up as fewer occupied slots than
+            // inserted rows. Tables of (predicate, position) pairs already verified for this store version are not re-counted.
+            bool counted = false;
+            const u32 offc = ctrl_alloc(ctx, MAXT);
+            KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + offc, 0, MAXT * sizeof(u32), ctx->st));
+            for (u32 k = 0; k < K; k++) {
+                if ((int)k == probe_k || st[k].trusted) continue;
+                if (!counted) timer_begin(ctx, F_BUILD, 0);
+                counted = true;
+                ctx->stats.kernel_launches++;
+                launch_count_nonempty(st[k].tab, range, ctx->ctrl + offc + tab_of[k], ctx->n_sms, ctx->st);
+            }
+            if (counted) timer_end(ctx);  // the counts are read together with the probe's result: no extra synchronisation
+            auto check_dups = [&]() -> bool {
+                bool dup = false;
+                for (u32 k = 0; k < K; k++) {
+                    if ((int)k == probe_k) continue;
+                    const bool fewer = !st[k].trusted && ctx->h_ctrl[offc + tab_of[k]] != rels[k]->n;
+                    if (ctx->h_ctrl[off + 8 + tab_of[k]] || fewer) {
+                        dup = true;
+                        if (!pats[k].p.is_var) ctx->multi_valued.insert({pats[k].p.value, key_pos(k)});
+                    }
+                }
+                return dup;
+            };
+            for (u32 k = 0; k < K; k++) if ((int)k != probe_k) ctx->stats.rows_built += rels[k]->n;
+            auto empty_result2 = [&]() -> kb_status {
+                auto r = std::make_unique<kb_rel>();
+                r->slots = all_slots;
+                for (size_t c = 0; c < all_slots.size(); c++) { Col col; KB_TRY(alloc_col(ctx, 0, &col)); r->cols.push_back(col); }
+                *out = std::move(r);
+                return KB_OK;
+            };
+            for (u32 k = 0; k < K; k++) if (rels[k]->n == 0) return empty_result2();
+            for (u32 k = 0; k < K; k++) if ((int)k != probe_k && ctx->h_ctrl[off + 8 + tab_of[k]]) {  // key outside the table range (cannot happen with store statistics)
+                KB_TRY(ctrl_read(ctx));
+                check_dups();
+                return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, false, out);
+            }
+            const kb_rel& PR = *rels[probe_k];
+            auto res = std::make_unique<kb_rel>();
+            res->slots = out_slots;
+            const u32 n_out = (u32)out_slots.size();
+            std::vector<FilterOp> fops;
+            if (!post.ops.empty()) {
+                std::map<u32, u32> remap;
+                for (u32 c = 0; c < n_out; c++) remap[out_slots[c]] = c;
+                if (!append_prog(&fops, post, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
+            }
+            ProbeFParams P{};
+            P.pairs = reinterpret_cast<const uint2*>(PR.cols[0].ptr);
+            P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
+            P.n = (u32)PR.n;
+            P.n_tiles = (u32)((PR.n + PROBEF_TILE - 1) / PROBEF_TILE);
+            P.T = T;
+            for (u32 q = 0; q < T; q++) P.tab[q] = dt[q];
+            P.n_out = n_out;
+            for (u32 c = 0; c < n_out; c++) {
+                Col col;
+                KB_TRY(alloc_col(ctx, PR.n, &col));
+                res->cols.push_back(col);
+                P.oc[c] = ocs[c];
+                P.out[c] = col.ptr;
+            }
+            P.cap = (u32)PR.n;
+            P.n_ops = (u32)fops.size();
+            for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
+            P.nt = numtab(ctx);
+            KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+            P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+            P.block_state = static_cast<u64*>(ctx->block_state->p);
+            P.ordered = ctx->ordered;
+            const u32 off2 = ctrl_alloc(ctx, 8);
+            KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off2, 0, 8 * sizeof(u32), ctx->st));
+            P.ticket = ctx->ctrl + off2;
+            P.total = ctx->ctrl + off2 + 1;
+            P.zero_word = ctx->ctrl + off2 + 2;
+            P.abort_flag = nullptr;
+            P.epoch = ctx->epoch++;
+            timer_begin(ctx, F_PROBE);
+            launch_probe_fast(P, ctx->n_sms, ctx->st);
+            timer_end(ctx);
+            KB_CUDA(ctx, cudaGetLastError());
+            ctx->stats.rows_probed += PR.n;
+            KB_TRY(ctrl_read(ctx));
+            if (check_dups())  // a build side is multi-valued: redo without the fusion (the chained operator needs the build rows)
+                return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, false, out);
+            for (u32 k = 0; k < K; k++)
+                if ((int)k != probe_k && !pats[k].p.is_var && pushdown[k].ops.empty()) ctx->single_valued.insert({pats[k].p.value, key_pos(k)});
+            res->n = ctx->h_ctrl[off2 + 1];
+            *out = select_cols(*res, all_slots);
+            return KB_OK;
+        }
+    }
 
     std::vector<std::unique_ptr<kb_rel>> rels;
     KB_TRY(scan_impl(ctx, pats, K, pushdown, false, all_pairs, &rels));
@@ -724,12 +888,17 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
             std::vector<OutCol> ocs;
             for (u32 c = 0; c < (u32)PR.slots.size(); c++) ocs.push_back(OutCol{OUT_PROBE, c, 0});
             timer_begin(ctx, F_BUILD, (int)nb);
+            for (size_t t = 0; t < nb; t++) KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &tables[t]));  // stream-ordered on st
+            if (nb > 1) {  // independent tables: odd ones are memset + built on the second stream, concurrently with the even ones
+                KB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->st));
+                KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
+            }
             for (size_t t = 0; t < nb; t++) {
                 const u32 k = builds[done + t];
                 const kb_rel& B = *rels[k];
-                KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &tables[t]));
+                cudaStream_t bs = (nb > 1 && (t & 1)) ? ctx->st2 : ctx->st;
                 u32* tab = static_cast<u32*>(tables[t]->p);
-                KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), ctx->st));
+                KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), bs));
                 DirectTab& D = dt[t];
                 D.tab = tab; D.kmin = kmin; D.range = range; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
                 const int kc = B.col_of(join_slot);
@@ -737,8 +906,9 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
                     D.mode = 0;
                     out_slots.push_back(B.slots[kc == 0 ? 1 : 0]);
                     ocs.push_back(OutCol{OUT_TABVAL, (u32)t, 0});
+                    const u32 trusted = (!pats[k].p.is_var && ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;
                     launch_build_direct_pairs(reinterpret_cast<const uint2*>(B.cols[0].ptr), kc == 1 ? 1u : 0u, (u32)B.n, tab, kmin, range,
-                                              ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, ctx->st);
+                                              ctx->ctrl + off + 8 + (u32)t, trusted, ctx->n_sms, bs);
                 } else {
                     const u32* vals = nullptr;
                     if (B.cols.size() == 1) { D.mode = 2; }
@@ -757,9 +927,13 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
                             D.n_pay++;
                         }
                     }
-                    launch_build_direct(B.cols[kc].ptr, vals, (u32)B.n, tab, kmin, range, ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, ctx->st);
+                    launch_build_direct(B.cols[kc].ptr, vals, (u32)B.n, tab, kmin, range, ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, bs);
                 }
                 ctx->stats.rows_built += B.n;
+            }
+            if (nb > 1) {
+                KB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->st2));
+                KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
             }
             timer_end(ctx);
             auto res = std::make_unique<kb_rel>();
@@ -849,6 +1023,11 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
                 if (!pats[k].p.is_var) ctx->multi_valued.insert({pats[k].p.value, key_pos(k)});
             }
             if (dup_seen) break;
+            for (size_t t = 0; t < nb; t++) {  // verified duplicate-free: later builds of the same (predicate, key position) use plain stores
+                const u32 k = builds[done + t];
+                // only when the build side was the WHOLE (?s P ?o) relation: a filtered subset proves nothing about the rest
+                if (!pats[k].p.is_var && rels[k]->pair && pushdown[k].ops.empty()) ctx->single_valued.insert({pats[k].p.value, key_pos(k)});
+            }
             res->n = ctx->h_ctrl[off + 1];
             cur = std::move(res);
             done += nb;
@@ -923,6 +1102,9 @@ kb_status kb_ctx_create(int device, kb_ctx** out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) return bail("cudaEventCreate", e);
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t thr = UINT64_MAX;  // keep freed blocks cached: steady-state queries never hit cudaMalloc
@@ -953,6 +1135,10 @@ void kb_ctx_destroy(kb_ctx* ctx) {
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev_copy);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    cudaStreamSynchronize(ctx->st2);
+    cudaStreamDestroy(ctx->st2);
     cudaStreamDestroy(ctx->st);
     cudaStreamDestroy(ctx->st_copy);
     delete ctx;
@@ -1005,6 +1191,7 @@ static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, cons
     ctx->n_triples += n;
     ctx->store_version++;
     ctx->multi_valued.clear();
+    ctx->single_valued.clear();
     return KB_OK;
 }
 
@@ -1014,6 +1201,7 @@ kb_status kb_store_clear(kb_ctx* ctx) {
     ctx->n_triples = 0;
     ctx->store_version++;
     ctx->multi_valued.clear();
+    ctx->single_valued.clear();
     return KB_OK;
 }
 kb_status kb_store_load(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n) {
@@ -1044,6 +1232,7 @@ kb_status kb_store_evict(kb_ctx* ctx, uint64_t tag) {
     }
     ctx->store_version++;
     ctx->multi_valued.clear();
+    ctx->single_valued.clear();
     return found ? KB_OK : kb::fail(ctx, KB_E_NOT_FOUND, "no segment with tag %llu", (unsigned long long)tag);
 }
 kb_status kb_store_size(kb_ctx* ctx, uint64_t* n, uint32_t* n_seg) {
@@ -1114,6 +1303,7 @@ kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, con
     if (rc != KB_OK) { ctx->segs.swap(old); ctx->n_triples = 0; for (auto& g : ctx->segs) ctx->n_triples += g.n; return rc; }
     ctx->store_version++;
     ctx->multi_valued.clear();
+    ctx->single_valued.clear();
     return KB_OK;
 }
 
@@ -1523,6 +1713,7 @@ kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, c
     ctx->stats.h2d_bytes += 3 * n * sizeof(u32);
     ctx->store_version++;
     ctx->multi_valued.clear();
+    ctx->single_valued.clear();
     ctx->upload_stats_off = (int)soff;
     // scan_impl makes st wait on each segment's `ready` event right before that segment's scan kernel: copy i+1 overlaps scan i
     std::unique_ptr<kb_rel> r;

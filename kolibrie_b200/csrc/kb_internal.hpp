@@ -105,6 +105,9 @@ struct kb_ctx {
     kb_stats stats{};
     // knowledge cached across calls: (predicate, key position) pairs whose direct build met duplicate keys
     std::set<std::pair<kb::u32, kb::u32>> multi_valued;
+    std::set<std::pair<kb::u32, kb::u32>> single_valued;  // verified duplicate-free by an earlier direct build on this store version
+    cudaStream_t st2 = nullptr;                            // second compute stream: independent direct builds run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     kb::u64 store_version = 0;
     int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges
 };
@@ -144,8 +147,16 @@ bool split_conjuncts(const kb_filter_op* ops, u32 n, std::vector<FilterProg>* ou
 std::set<u32> filter_slots(const FilterProg& f);
 
 // pairs=true: 2-variable (?s P ?o)-shaped patterns are emitted as interleaved (s,o) pair relations (internal fast path)
+struct ScanTable {  // scan+build fusion: pattern k inserts its matches into this direct table instead of emitting rows
+    u32* tab = nullptr;
+    u32 kmin = 0, range = 0;
+    u32 key_is_o = 0, trusted = 0;
+    u32* dup_flag = nullptr;
+};
 kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 n_pats, const std::vector<FilterProg>& pushdown, bool want_index, bool pairs,
-                    std::vector<std::unique_ptr<kb_rel>>* out);
+                    std::vector<std::unique_ptr<kb_rel>>* out, const std::vector<ScanTable>* tables = nullptr);
+kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 n_pats, const kb_filter_op* filter, u32 n_ops, bool allow_fused_scan,
+                          std::unique_ptr<kb_rel>* out);
 kb_status segment_stats(kb_ctx* ctx, Segment* sg);
 kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r);
 kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);

@@ -8,7 +8,10 @@ namespace kb {
 // K_scan: fused multi-pattern triple scan + constant filter + pushed-down FILTER + ordered compaction.
 // Replaces execute_table_scan_with_ids (engine.rs:510-584), the index scans (engine.rs:1192-1407), QueryBuilder's
 // Exact filter scan (query_builder.rs:486-531) and the reference's hash_join_kernel (cuda_join.cu:26-45).
-constexpr int SCAN_THREADS = 256;
+#ifndef KB_SCAN_THREADS
+#define KB_SCAN_THREADS 256
+#endif
+constexpr int SCAN_THREADS = KB_SCAN_THREADS;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2048 triples = 24 KB of shared memory per CTA
 
@@ -17,7 +20,12 @@ enum : u32 {
     SP_EQ_SP = 8, SP_EQ_SO = 16, SP_EQ_PO = 32,    // same variable twice in one pattern (quirk Q4: enforced)
     SP_EMIT_S = 64, SP_EMIT_P = 128, SP_EMIT_O = 256,  // positions written to the output (columns come out in s,p,o order)
     SP_EMIT_IDX = 512,                              // global triple index (legacy FFI)
-    SP_PAIR = 1024  // emit (subject, object) interleaved as uint2 into outp[0]: one 8-byte store per match (2-variable patterns)
+    SP_PAIR = 1024,  // emit (subject, object) interleaved as uint2 into outp[0]: one 8-byte store per match (2-variable patterns)
+    // scan + build fused: the match goes straight into a direct join table, table[key - cs] = other half (cs = key base, co = key
+    // range, outp[0] = table, outp[1] = duplicate flag); no intermediate relation is written or re-read
+    SP_TABLE = 2048,
+    SP_TKEY_O = 4096,    // the join key is the object (default: the subject)
+    SP_TTRUSTED = 8192   // (kept for the A/B switch) atomicExch-with-return duplicate detection inside the scan when NOT set and KB_FUSED_ATOMIC
 };
 struct ScanPat {
     u32 cs, cp, co;
@@ -48,7 +56,9 @@ void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st);
 void launch_build_direct(const u32* keys, const u32* vals /*null: row index*/, u32 n, u32* table, u32 kmin, u32 range,
                          u32* dup_flag, int n_sms, cudaStream_t st);
 // same from an interleaved (subject, object) pair relation; key_is_y selects which half is the key, the other is the payload
-void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, int n_sms, cudaStream_t st);
+// trusted=1: the (predicate, key position) is known single-valued for this store version -> plain stores, no read-modify-write
+void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, u32 trusted, int n_sms,
+                               cudaStream_t st);
 // CHAINED multimap: open-addressing slots {key tag, head row} + next[] chains. Insert cost is O(1) whatever the key
 // multiplicity (1:N joins and heavy hitters of the Datalog joins).
 struct ChainTab {
@@ -129,6 +139,8 @@ struct ProbeFParams {
 };
 void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st);
 void launch_unpair(const uint2* kv, u32 n, u32* x, u32* y, cudaStream_t st);
+// number of occupied (non-EMPTY32) slots of a direct table: equals the number of inserted rows iff the keys were single-valued
+void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, cudaStream_t st);
 void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_sms, cudaStream_t st);
 
 // K_probe (chained, binary): general natural join with 1:N matches, multi-column keys, FILTER, ordered compaction.

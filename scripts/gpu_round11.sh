@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+echo "== pytest gpu"; timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -4
+for V in libkolibrie_b200.so libkolibrie_b200_scan128.so; do
+echo "== bench $V"; KOLIBRIE_B200_LIB=$PWD/kolibrie_b200/$V timeout 900 python bench.py --steps 20 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], {k:(round(v['ms'],4), round(v['frac'],3)) for k,v in d['roofline']['families'].items()}, d['roofline']['device_ms_per_step'], d['e2e']['ms_per_step'], d['clocks'])"
+done
