@@ -1550,7 +1550,7 @@ kb_status kb_group_aggregate(kb_ctx* ctx, const kb_rel* in, const uint32_t* grou
     g->keys.resize(n_group);
     g->vals.resize(n_aggs);
     if (in->n == 0) { *out = g.release(); return KB_OK; }
-    u64 slots = 1u << 16;
+    u64 slots = 1u << 12;  // small first try: the table is downloaded whole; overflow -> 16x larger and rerun
     for (;;) {
         P.n_slots = (u32)slots;
         kb::Buf keys, state, val, cnt;

@@ -911,7 +911,9 @@ __device__ __forceinline__ u32 group_slot(const GroupParams& P, const u32* k) {
     const u32 mask = P.n_slots - 1u;
     u32 slot = mix32(h) & mask;
     for (u32 probes = 0; probes < P.n_slots; probes++) {
-        u32 st = atomicCAS(&P.gstate[slot], 0u, 1u);
+        u32 st = *reinterpret_cast<volatile u32*>(&P.gstate[slot]);  // read first: a ready slot must not cost an atomic
+        if (st == 0u) st = atomicCAS(&P.gstate[slot], 0u, 1u);
+        else if (st == 2u) st = 3u;  // ready, skip the claim path
         if (st == 0u) {
             for (u32 c = 0; c < P.n_gcols; c++) P.gkeys[(u64)slot * 4 + c] = k[c];
             __threadfence();
@@ -928,9 +930,33 @@ __device__ __forceinline__ u32 group_slot(const GroupParams& P, const u32* k) {
     return EMPTY32;
 }
 
-// One warp pre-aggregates its 32 rows per distinct group (__match_any_sync) so a GROUP BY with a handful of groups does
-// not serialise on a handful of addresses; leaders then update the global table.
+// Two levels of pre-aggregation keep a GROUP BY with a handful of groups from serialising on a handful of addresses:
+// (1) a warp folds its 32 rows per distinct group (__match_any_sync), (2) leaders accumulate into a 64-entry shared-memory
+// table of the CTA, flushed to the global table once per CTA. Rows whose group does not fit the CTA table go straight to global.
+constexpr int GROUP_SMEM = 64;
+__device__ __forceinline__ void group_update_global(const GroupParams& P, const u32* k, unsigned long long cnt, const double* val) {
+    const u32 slot = group_slot(P, k);
+    if (slot == EMPTY32) { *P.overflow = 1u; return; }
+    atomicAdd(&P.gcnt[slot], cnt);
+    for (u32 a = 0; a < P.n_aggs; a++) {
+        double* dst = &P.gval[(u64)slot * 8 + a];
+        if (P.akind[a] == KB_AGG_MIN) atomic_min_f64(dst, val[a]);
+        else if (P.akind[a] == KB_AGG_MAX) atomic_max_f64(dst, val[a]);
+        else if (P.akind[a] != KB_AGG_COUNT) atomicAdd(dst, val[a]);
+    }
+}
+
 __global__ void __launch_bounds__(256) group_kernel(const __grid_constant__ GroupParams P) {
+    __shared__ u32 sk[GROUP_SMEM][4];
+    __shared__ u32 sstate[GROUP_SMEM];  // 0 free, 1 being written, 2 ready
+    __shared__ unsigned long long scnt[GROUP_SMEM];
+    __shared__ double sval[GROUP_SMEM][8];
+    for (int i = threadIdx.x; i < GROUP_SMEM; i += blockDim.x) {
+        sstate[i] = 0u;
+        scnt[i] = 0ull;
+        for (u32 a = 0; a < 8; a++) sval[i][a] = (a < P.n_aggs && P.akind[a] == KB_AGG_MIN) ? CUDART_INF : ((a < P.n_aggs && P.akind[a] == KB_AGG_MAX) ? -CUDART_INF : 0.0);
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const u32 stride = gridDim.x * blockDim.x;
     const u32 n_round = (P.n + 31u) & ~31u;
@@ -946,19 +972,17 @@ __global__ void __launch_bounds__(256) group_kernel(const __grid_constant__ Grou
         int leader = __ffs(peers) - 1;
         bool same = true;
         for (u32 c = 0; c < P.n_gcols; c++) same = same && (__shfl_sync(peers, k[c], leader) == k[c]);
-        // rare hash collision inside a warp: lanes that differ from their leader go alone
         const unsigned agree = __ballot_sync(act, same);
-        peers = same ? (peers & agree) : (1u << lane);
+        peers = same ? (peers & agree) : (1u << lane);  // rare hash collision inside a warp: the odd lanes go alone
         leader = __ffs(peers) - 1;
         double val[8];
         for (u32 a = 0; a < P.n_aggs; a++) val[a] = P.acol[a] ? num_of(P.nt, P.acol[a][i]) : 0.0;
-        // leader folds its peers
-        unsigned long long cnt = (unsigned long long)__popc(peers);
+        const unsigned long long cnt = (unsigned long long)__popc(peers);
         for (u32 a = 0; a < P.n_aggs; a++) {
+            if (P.akind[a] == KB_AGG_COUNT) continue;  // COUNT needs no values: popc(peers) is the fold
             double acc = val[a];
             unsigned rest = peers & ~(1u << leader);
-            // every peer lane must take part in the shuffles: iterate over the same mask in all lanes of the group
-            while (rest) {
+            while (rest) {  // every lane of the group runs the same shuffles
                 const int src = __ffs(rest) - 1;
                 rest &= rest - 1u;
                 const double o = __shfl_sync(peers, val[a], src);
@@ -968,17 +992,43 @@ __global__ void __launch_bounds__(256) group_kernel(const __grid_constant__ Grou
             }
             val[a] = acc;
         }
-        if (lane == leader) {
-            const u32 slot = group_slot(P, k);
-            if (slot == EMPTY32) { *P.overflow = 1u; continue; }
-            atomicAdd(&P.gcnt[slot], cnt);
-            for (u32 a = 0; a < P.n_aggs; a++) {
-                double* dst = &P.gval[(u64)slot * 8 + a];
-                if (P.akind[a] == KB_AGG_MIN) atomic_min_f64(dst, val[a]);
-                else if (P.akind[a] == KB_AGG_MAX) atomic_max_f64(dst, val[a]);
-                else if (P.akind[a] != KB_AGG_COUNT) atomicAdd(dst, val[a]);
+        if (lane != leader) continue;
+        // CTA table: find or claim
+        u32 slot = mix32(h) & (GROUP_SMEM - 1);
+        bool done = false;
+        for (int probes = 0; probes < GROUP_SMEM && !done; probes++) {
+            u32 st = *reinterpret_cast<volatile u32*>(&sstate[slot]);
+            if (st == 0u) st = atomicCAS(&sstate[slot], 0u, 1u);
+            else if (st == 2u) st = 3u;
+            if (st == 0u) {
+                for (u32 c = 0; c < 4; c++) sk[slot][c] = k[c];
+                __threadfence_block();
+                atomicExch(&sstate[slot], 2u);
+                st = 3u;
             }
+            while (st == 1u) st = *reinterpret_cast<volatile u32*>(&sstate[slot]);
+            __threadfence_block();
+            bool eq = true;
+            for (u32 c = 0; c < P.n_gcols; c++) eq = eq && (*reinterpret_cast<volatile u32*>(&sk[slot][c]) == k[c]);
+            if (eq) {
+                atomicAdd(&scnt[slot], cnt);
+                for (u32 a = 0; a < P.n_aggs; a++) {
+                    if (P.akind[a] == KB_AGG_MIN) atomic_min_f64(&sval[slot][a], val[a]);
+                    else if (P.akind[a] == KB_AGG_MAX) atomic_max_f64(&sval[slot][a], val[a]);
+                    else if (P.akind[a] != KB_AGG_COUNT) atomicAdd(&sval[slot][a], val[a]);
+                }
+                done = true;
+            } else slot = (slot + 1u) & (GROUP_SMEM - 1);
         }
+        if (!done) group_update_global(P, k, cnt, val);  // more than 64 distinct groups in this CTA
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GROUP_SMEM; i += blockDim.x) {
+        if (sstate[i] != 2u) continue;
+        u32 k[4] = {sk[i][0], sk[i][1], sk[i][2], sk[i][3]};
+        double v[8];
+        for (u32 a = 0; a < 8; a++) v[a] = sval[i][a];
+        group_update_global(P, k, scnt[i], v);
     }
 }
 void launch_group(const GroupParams& p, int n_sms, cudaStream_t st) {

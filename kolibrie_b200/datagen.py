@@ -208,7 +208,7 @@ class TaxonomyData:
     n_instances: int
 
 
-def taxonomy_dataset(fanout: int = 10, depth: int = 6, n_instances: int = 48_888_890, seed: int = 43) -> TaxonomyData:
+def taxonomy_dataset(fanout: int = 10, depth: int = 6, n_instances: int = 48_888_890, seed: int = 43, first_instance: int = 0) -> TaxonomyData:
     """Complete `fanout`-ary class tree of `depth` levels below the root (subClassOf child->parent) + `x rdf:type C` facts.
     ids: rdfs:subClassOf = 0, rdf:type = 1, classes 2..2+n_classes-1 (breadth-first, root first), instances after."""
     n_classes = sum(fanout ** k for k in range(depth + 1))
@@ -216,12 +216,12 @@ def taxonomy_dataset(fanout: int = 10, depth: int = 6, n_instances: int = 48_888
     child = np.arange(1, n_classes, dtype=np.int64)
     parent = (child - 1) // fanout
     X0 = C0 + n_classes
-    j = np.arange(n_instances, dtype=np.uint64)
+    j = np.arange(first_instance, first_instance + n_instances, dtype=np.uint64)  # a rank's slice of the global instance range
     cls = (splitmix64_at(seed, j) % np.uint64(n_classes)).astype(np.int64)
     s = np.concatenate([child + C0, j.astype(np.int64) + X0]).astype(np.uint32)
     p = np.concatenate([np.full(len(child), SC), np.full(n_instances, TYPE)]).astype(np.uint32)
     o = np.concatenate([parent + C0, cls + C0]).astype(np.uint32)
-    return TaxonomyData(s, p, o, int(X0 + n_instances), {"rdfs:subClassOf": SC, "rdf:type": TYPE}, n_classes, n_instances)
+    return TaxonomyData(s, p, o, int(X0 + first_instance + n_instances), {"rdfs:subClassOf": SC, "rdf:type": TYPE}, n_classes, n_instances)
 
 
 def taxonomy_rules(d: TaxonomyData):

@@ -82,3 +82,61 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Datalog across ranks (config 4 shape): broadcast the small relations, keep the big ones sharded by subject.
+def _allgather_rows(rows: np.ndarray, device=None, group=None) -> np.ndarray:
+    """concatenation over ranks of an [n, k] uint32 array (n differs per rank)"""
+    world = dist.get_world_size(group)
+    dev = device or torch.device("cpu")
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x[0]) for x in sizes]
+    mx = max(sizes + [1])
+    pad = torch.zeros((mx, rows.shape[1]), dtype=torch.int32, device=dev)
+    if rows.shape[0]:
+        pad[: rows.shape[0]] = torch.from_numpy(rows.astype(np.int32)).to(dev)
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    return np.concatenate([o[:m].cpu().numpy().astype(np.uint32) for o, m in zip(out, sizes)], axis=0)
+
+
+def check_broadcast_plan(rules: Sequence[dict], replicated_preds: Sequence[int]):
+    """A rule set can run shard-locally after broadcasting `replicated_preds` when every rule has at most one premise over a
+    sharded predicate and, if it has one, its heads keep that premise's subject variable and a sharded head predicate (derived facts
+    stay on the rank that owns the subject); rules over replicated predicates only must derive replicated predicates (they are
+    evaluated redundantly and identically on every rank). Raises ValueError otherwise."""
+    rep = set(int(x) for x in replicated_preds)
+    for ri, r in enumerate(rules):
+        sharded = [p for p in r["premise"] if p.p.is_var or int(p.p.value) not in rep]
+        if len(sharded) > 1:
+            raise ValueError(f"rule {ri}: two premises over sharded predicates need a join-key shuffle")
+        for h in r["conclusion"]:
+            if h.p.is_var:
+                raise ValueError(f"rule {ri}: variable head predicate")
+            head_rep = int(h.p.value) in rep
+            if sharded:
+                sp = sharded[0]
+                if head_rep or not (h.s.is_var and sp.s.is_var and h.s.value == sp.s.value):
+                    raise ValueError(f"rule {ri}: head must keep the sharded premise's subject and a sharded predicate")
+            elif not head_rep:
+                raise ValueError(f"rule {ri}: a rule over replicated predicates must derive a replicated predicate")
+
+
+def datalog_fixpoint_sharded(local_fixpoint, s, p, o, rules, replicated_preds, device=None, group=None):
+    """`s,p,o`: this rank's shard (hash(subject) sharding). `local_fixpoint(s,p,o) -> [n,3] inferred` runs the fixpoint on one rank
+    (the device library on the GPU box, the oracle in the CPU tests). Returns this rank's inferred facts: sharded predicates as
+    derived locally, replicated predicates on rank 0 only (every rank derives the same ones)."""
+    check_broadcast_plan(rules, replicated_preds)
+    rank = dist.get_rank(group)
+    rep = np.isin(p, np.asarray(list(replicated_preds), dtype=np.uint32))
+    rep_rows = _allgather_rows(np.stack([s[rep], p[rep], o[rep]], axis=1), device, group)
+    rep_rows = np.unique(rep_rows, axis=0) if len(rep_rows) else rep_rows
+    S = np.concatenate([rep_rows[:, 0], s[~rep]])
+    P = np.concatenate([rep_rows[:, 1], p[~rep]])
+    O = np.concatenate([rep_rows[:, 2], o[~rep]])
+    inferred = np.asarray(local_fixpoint(S, P, O), dtype=np.uint32).reshape(-1, 3)
+    is_rep = np.isin(inferred[:, 1], np.asarray(list(replicated_preds), dtype=np.uint32))
+    return inferred[~is_rep] if rank != 0 else inferred

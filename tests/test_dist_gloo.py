@@ -53,6 +53,20 @@ def _worker(rank, world, port, q):
         mine = mine[kd.shard_of(mine[:, 1], world) == rank]
         assert np.array_equal(datagen.canonical_rows(got), datagen.canonical_rows(mine))
         assert kd.max_over_ranks(float(rank)) == world - 1
+        # 4. Datalog (config 4 shape): broadcast subClassOf, keep rdf:type sharded by subject; union over ranks == global closure
+        t = datagen.taxonomy_dataset(fanout=3, depth=4, n_instances=4000)
+        rules = datagen.taxonomy_rules(t)
+        ts, tp, to = kd.shard_triples(t.s, t.p, t.o, rank, world)
+        local = lambda S, P, Ob: O.Db(S, P, Ob).fixpoint(rules)["facts"]
+        mine = kd.datalog_fixpoint_sharded(local, ts, tp, to, rules, [t.ids["rdfs:subClassOf"]])
+        allf = kd._allgather_rows(mine)
+        want = O.Db(t.s, t.p, t.o).fixpoint(rules)["facts"]
+        assert np.array_equal(datagen.canonical_rows(allf), datagen.canonical_rows(want)), "sharded closure == global closure"
+        try:
+            kd.check_broadcast_plan(rules, [])  # nothing replicated: R2 joins two sharded predicates on a non-subject key
+            raise AssertionError("plan check should have refused")
+        except ValueError:
+            pass
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
