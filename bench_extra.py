@@ -77,6 +77,7 @@ def main():
     if "cfg3" in only:
         E = int(16_666_667 * args.scale)
         d = datagen.employee_shard(E * world, rank, world)
+        ctx.set_sharding(rank, world)
         ctx.store_load(d.s, d.p, d.o)
         ctx.dict_numeric_load(d.num_or0, d.is_num)
         js, pats, _ = datagen.employee_queries(d)["cfg3"]

@@ -121,7 +121,11 @@ typedef struct kb_rule {
 
 enum kb_strategy {
     KB_SEMI_NAIVE = 0, /* datalog/src/reasoning/materialisation/semi_naive.rs:53-91 */
-    KB_NAIVE = 1       /* datalog/src/reasoning/materialisation/my_naive.rs:10-71 */
+    KB_NAIVE = 1,      /* datalog/src/reasoning/materialisation/my_naive.rs:10-71 */
+    /* datalog/src/reasoning/materialisation/semi_naive_parallel.rs:11-176: semi-naive rounds over rules with 1 or 2 premises only
+     * (others are skipped, :149), rule filters are NOT evaluated, premises are matched with matches_rule_pattern (rules.rs:9-72):
+     * constants in subject/object positions ARE enforced (unlike the hash-join strategies, quirk Q6). */
+    KB_SEMI_NAIVE_PARALLEL = 2
 };
 
 typedef struct kb_fixpoint_stats {
@@ -220,8 +224,14 @@ KB_API kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint32_t
 
 /* ------------------------------------------------------------------ multi-GPU helpers (one process per GPU; the host layer
  * runs the NCCL all-to-all between kb_partition and kb_rel_from_device) */
-KB_API uint32_t kb_shard_of(uint32_t key, uint32_t n_shards); /* mix32(key) % n_shards — same function the device uses */
-/* split `in` by kb_shard_of(row[key_slot]) into n_parts contiguous ranges of ONE output relation;
+/* Shard function (host and device agree): block-cyclic on the dictionary id, (key >> KB_SHARD_BLOCK_BITS) % n_shards. Dictionary ids
+ * are dense (shared/src/dictionary.rs:32-48), so this balances like a hash AND keeps every shard's key domain dense: a shard's keys
+ * compact to ((key >> B) / n) << B | (key & (2^B - 1)), which keeps the direct join tables as small on N GPUs as on one. */
+#define KB_SHARD_BLOCK_BITS 10
+KB_API uint32_t kb_shard_of(uint32_t key, uint32_t n_shards);
+/* tell the context that its store holds shard `rank` of `world` (sharded by subject): enables the key compaction above */
+KB_API kb_status kb_set_sharding(kb_ctx* ctx, uint32_t rank, uint32_t world);
+/* split `in` by kb_shard_of(row[key_slot], n_parts) into n_parts contiguous ranges of ONE output relation;
  * part_offsets[n_parts+1] (host) receives the row offsets. */
 KB_API kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, kb_rel** out, uint64_t* part_offsets);
 KB_API kb_status kb_rel_from_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out);

@@ -28,7 +28,7 @@ KB_TAG_INFERRED = 0xFFFFFFFFFFFFFFF0
 F_CMP_NUM, F_EQ_ID, F_NE_ID, F_AND, F_OR, F_NOT, F_PUSH_VAR, F_PUSH_CONST, F_ADD, F_SUB, F_MUL, F_DIV, F_TRUTHY, F_IS_TRIPLE = range(1, 15)
 CMP_GT, CMP_GE, CMP_LT, CMP_LE, CMP_EQ, CMP_NE = range(1, 7)
 AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_AVG = range(5)
-SEMI_NAIVE, NAIVE = 0, 1
+SEMI_NAIVE, NAIVE, SEMI_NAIVE_PARALLEL = 0, 1, 2
 
 
 class KbTerm(C.Structure):
@@ -175,6 +175,7 @@ def lib() -> C.CDLL:
         "kb_groups_free": (None, [vp]),
         "kb_datalog_fixpoint": (i32, [vp, P(KbRule), u32, u32, P(vp), P(KbFixpointStats)]),
         "kb_shard_of": (u32, [u32, u32]),
+        "kb_set_sharding": (i32, [vp, u32, u32]),
         "kb_partition": (i32, [vp, vp, u32, u32, P(vp), P(u64)]),
         "kb_star_join_host": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), P(u64)]),
         "perform_hash_join_cuda": (None, [vp, vp, vp, u32, u32, P(u32), P(P(u32)), P(u32)]),
@@ -193,7 +194,7 @@ EXPORTED_SYMBOLS = [
     "kb_store_download", "kb_dict_numeric_load", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free",
-    "kb_datalog_fixpoint", "kb_shard_of", "kb_partition", "kb_star_join_host", "perform_hash_join_cuda",
+    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_star_join_host", "perform_hash_join_cuda",
 ]
 
 
@@ -467,6 +468,10 @@ class Context:
 
     def synchronize(self):
         self._check(lib().kb_synchronize(self.h))
+
+    def set_sharding(self, rank: int, world: int):
+        """the store holds shard `rank` of `world` (sharded by subject with kb_shard_of): enables the dense key compaction"""
+        self._check(lib().kb_set_sharding(self.h, rank, world))
 
 
 def star_join_host_raw(ctx: Context, s_ptr: int, p_ptr: int, o_ptr: int, n: int, join_slot: int, pats, filt, out_ptrs: Sequence[int], out_cap: int):

@@ -272,17 +272,20 @@ static kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt) {
 // ---------------------------------------------------------------------------------------------------------------
 // scan
 kb_status segment_stats(kb_ctx* ctx, Segment* sg) {
-    if (sg->has_stats || sg->n == 0) { sg->has_stats = true; return KB_OK; }
+    if ((sg->has_stats && sg->stats_world == ctx->shard_world) || sg->n == 0) { sg->has_stats = true; sg->stats_world = ctx->shard_world; return KB_OK; }
     const u32 off = ctrl_alloc(ctx, 8);
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0xFF, 4 * sizeof(u32), ctx->st));
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off + 4, 0, 4 * sizeof(u32), ctx->st));
     const u32* cols[3] = {sg->s.ptr, sg->p.ptr, sg->o.ptr};
     timer_begin(ctx, F_OTHER, 3);
     for (int c = 0; c < 3; c++) launch_col_minmax(cols[c], (u32)sg->n, ctx->ctrl + off + c, ctx->ctrl + off + 4 + c, ctx->n_sms, ctx->st);
+    if (ctx->shard_world > 1) launch_count_foreign(sg->s.ptr, (u32)sg->n, ctx->shard_rank, ctx->shard_world, ctx->ctrl + off + 7, ctx->n_sms, ctx->st);
     timer_end(ctx);
     KB_CUDA(ctx, cudaGetLastError());
     KB_TRY(ctrl_read(ctx));
     for (int c = 0; c < 3; c++) { sg->cmin[c] = ctx->h_ctrl[off + c]; sg->cmax[c] = ctx->h_ctrl[off + 4 + c]; }
+    sg->sharded_ok = ctx->h_ctrl[off + 7] == 0;  // key compaction is only sound when every subject is ours
+    sg->stats_world = ctx->shard_world;
     sg->has_stats = true;
     return KB_OK;
 }
@@ -342,6 +345,7 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
             sp.cs = tb.kmin;
             sp.co = tb.range;
             sp.flags |= SP_TABLE | (tb.key_is_o ? SP_TKEY_O : 0u) | (tb.trusted ? SP_TTRUSTED : 0u);
+            P.cshift = tb.cshift;
         } else if (pairs && !want_index && slots.size() == 2 && src[0] == 0 && src[1] == 2) {
             Col col;  // interleaved (subject, object) rows: one 8-byte store per match
             KB_TRY(alloc_col(ctx, 2 * N, &col));
@@ -673,6 +677,16 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             if (!sg.has_stats) KB_TRY(segment_stats(ctx, &sg));
             for (u32 k = 0; k < K; k++) { const u32 c = key_pos(k); kmn = std::min(kmn, sg.cmin[c]); kmx = std::max(kmx, sg.cmax[c]); }
         }
+        // a subject-sharded store (kb_set_sharding) owns every world-th block of ids: compact the key domain so the tables stay dense
+        u32 cshift = 0;
+        {
+            bool subj = true;
+            for (u32 k = 0; k < K; k++) if (key_pos(k) != 0) subj = false;
+            for (auto& sg : ctx->segs) if (sg.n && !sg.sharded_ok) subj = false;
+            const u32 w = ctx->shard_world;
+            if (subj && w > 1 && (w & (w - 1)) == 0) while ((1u << cshift) < w) cshift++;
+        }
+        if (kmx >= kmn) { kmn = compact_key(kmn, cshift); kmx = compact_key(kmx, cshift); }
         const u64 rng = kmx >= kmn ? (u64)kmx - kmn + 1 : 0;
         if (rng == 0 || rng > std::max<u64>(4 * ctx->n_triples, 1ull << 16) || rng > (1ull << 31)) ok = false;
         for (u32 a = 0; a < K && ok; a++)
@@ -702,12 +716,12 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 KB_CUDA(ctx, cudaMemsetAsync(b->p, 0xFF, (size_t)range * sizeof(u32), ctx->st));
                 tabs.push_back(b);
                 st[k].tab = static_cast<u32*>(b->p);
-                st[k].kmin = kmn; st[k].range = range;
+                st[k].kmin = kmn; st[k].range = range; st[k].cshift = cshift;
                 st[k].key_is_o = key_pos(k) == 2 ? 1u : 0u;
                 st[k].trusted = (!pats[k].p.is_var && ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;
                 st[k].dup_flag = ctx->ctrl + off + 8 + t;
                 DirectTab& D = dt[t];
-                D.tab = st[k].tab; D.kmin = kmn; D.range = range; D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                D.tab = st[k].tab; D.kmin = kmn; D.range = range; D.cshift = cshift; D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
                 out_slots.push_back(pv[k][key_pos(k) == 0 ? 1 : 0]);
                 ocs.push_back(OutCol{OUT_TABVAL, t, 0});
                 tab_of[k] = t;
@@ -900,14 +914,14 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 u32* tab = static_cast<u32*>(tables[t]->p);
                 KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), bs));
                 DirectTab& D = dt[t];
-                D.tab = tab; D.kmin = kmin; D.range = range; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                D.tab = tab; D.kmin = kmin; D.range = range; D.cshift = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
                 const int kc = B.col_of(join_slot);
                 if (B.pair) {
                     D.mode = 0;
                     out_slots.push_back(B.slots[kc == 0 ? 1 : 0]);
                     ocs.push_back(OutCol{OUT_TABVAL, (u32)t, 0});
                     const u32 trusted = (!pats[k].p.is_var && ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;
-                    launch_build_direct_pairs(reinterpret_cast<const uint2*>(B.cols[0].ptr), kc == 1 ? 1u : 0u, (u32)B.n, tab, kmin, range,
+                    launch_build_direct_pairs(reinterpret_cast<const uint2*>(B.cols[0].ptr), kc == 1 ? 1u : 0u, (u32)B.n, tab, kmin, range, 0u,
                                               ctx->ctrl + off + 8 + (u32)t, trusted, ctx->n_sms, bs);
                 } else {
                     const u32* vals = nullptr;
@@ -927,7 +941,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                             D.n_pay++;
                         }
                     }
-                    launch_build_direct(B.cols[kc].ptr, vals, (u32)B.n, tab, kmin, range, ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, bs);
+                    launch_build_direct(B.cols[kc].ptr, vals, (u32)B.n, tab, kmin, range, 0u, ctx->ctrl + off + 8 + (u32)t, ctx->n_sms, bs);
                 }
                 ctx->stats.rows_built += B.n;
             }
@@ -1622,7 +1636,15 @@ kb_status kb_groups_counts(const kb_groups* g, const uint64_t** counts) {
 void kb_groups_free(kb_groups* g) { delete g; }
 
 // ------------------------------------------------------------------ multi-GPU helpers
-uint32_t kb_shard_of(uint32_t key, uint32_t n_shards) { return n_shards ? kb::mix32(key) % n_shards : 0; }
+uint32_t kb_shard_of(uint32_t key, uint32_t n_shards) { return n_shards ? kb::shard_of(key, n_shards) : 0; }
+
+kb_status kb_set_sharding(kb_ctx* ctx, uint32_t rank, uint32_t world) {
+    if (!ctx) return KB_E_INVALID;
+    if (world == 0 || rank >= world) return kb::fail(ctx, KB_E_INVALID, "rank %u / world %u", rank, world);
+    ctx->shard_rank = rank;
+    ctx->shard_world = world;
+    return KB_OK;
+}
 
 kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, kb_rel** out, uint64_t* part_offsets) {
     KB_ENTER(ctx);

@@ -34,6 +34,8 @@ struct Premise {
     int s_var, o_var;  // variable slots (real or synthetic, quirk Q6)
     bool pred_const;
     u32 pred;
+    bool s_is_const = false, o_is_const = false;  // enforced only by KB_SEMI_NAIVE_PARALLEL (matches_rule_pattern, rules.rs:9-72)
+    u32 s_const = 0, o_const = 0;
 };
 struct RulePlan {
     std::vector<Premise> prem;
@@ -119,6 +121,21 @@ kb_status make_view(kb_ctx* ctx, const PredRel& r, u64 start, u64 n, u32 s_slot,
     return KB_OK;
 }
 
+// KB_SEMI_NAIVE_PARALLEL: keep only the rows whose subject / object equal the premise's constants (the synthetic columns then
+// carry a single value and simply ride along)
+kb_status enforce_constants(kb_ctx* ctx, const Premise& pr, std::unique_ptr<kb_rel>* v) {
+    if (!pr.s_is_const && !pr.o_is_const) return KB_OK;
+    FilterProg f;
+    auto eq = [&](u32 slot, u32 id) { kb_filter_op op{}; op.op = KB_F_EQ_ID; op.slot = slot; op.id = id; f.ops.push_back(op); };
+    if (pr.s_is_const) eq((u32)pr.s_var, pr.s_const);
+    if (pr.o_is_const) eq((u32)pr.o_var, pr.o_const);
+    if (pr.s_is_const && pr.o_is_const) { kb_filter_op a{}; a.op = KB_F_AND; f.ops.push_back(a); }
+    std::unique_ptr<kb_rel> out;
+    KB_TRY(filter_impl(ctx, **v, f, &out));
+    *v = std::move(out);
+    return KB_OK;
+}
+
 }  // namespace
 
 extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy, kb_rel** inferred,
@@ -130,7 +147,8 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     KB_TRY(begin_call(ctx));
     if ((n_rules && !rules) || !inferred) return fail(ctx, KB_E_INVALID, "NULL argument");
-    if (strategy != KB_SEMI_NAIVE && strategy != KB_NAIVE) return fail(ctx, KB_E_INVALID, "unknown strategy %u", strategy);
+    if (strategy != KB_SEMI_NAIVE && strategy != KB_NAIVE && strategy != KB_SEMI_NAIVE_PARALLEL) return fail(ctx, KB_E_INVALID, "unknown strategy %u", strategy);
+    const bool strict = strategy == KB_SEMI_NAIVE_PARALLEL;
     kb_fixpoint_stats st{};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEventCreate(&ev0);
@@ -165,6 +183,8 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
             pr.o_var = (int)(p.o.is_var ? p.o.value : syn(2, p.o.value));
             pr.pred_const = !p.p.is_var;
             pr.pred = p.p.value;
+            pr.s_is_const = !p.s.is_var; pr.s_const = p.s.value;
+            pr.o_is_const = !p.o.is_var; pr.o_const = p.o.value;
             if (pr.s_var == pr.o_var)
                 return fail(ctx, KB_E_UNSUPPORTED, "rule %u premise %u repeats one variable in subject and object", r, i);
             if (pr.pred_const) { fx.rels[pr.pred].pred = pr.pred; bound.insert((u32)pr.s_var); bound.insert((u32)pr.o_var); }
@@ -232,6 +252,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
             bool dead = false;
             for (auto& pr : pl.prem) if (!pr.pred_const) dead = true;  // a variable predicate never matches (join_algorithm.rs:515-521)
             if (dead) continue;
+            if (strict && np != 1 && np != 2) continue;  // semi_naive_parallel.rs:149: other arities are skipped
             const u32 n_start = strategy == KB_NAIVE ? 1 : np;
             for (u32 i = 0; i < n_start; i++) {
                 // premise i over the delta (semi-naive) or over all facts (naive), then the others over all facts
@@ -242,6 +263,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     const u64 n = pr.snapshot - a;
                     if (n == 0) continue;
                     KB_TRY(make_view(ctx, pr, a, n, (u32)pl.prem[i].s_var, (u32)pl.prem[i].o_var, &cur));
+                    if (strict) KB_TRY(enforce_constants(ctx, pl.prem[i], &cur));
                 }
                 for (u32 j = 0; j < np && cur->n; j++) {
                     if (j == i) continue;
@@ -249,6 +271,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     if (pr.snapshot == 0) { cur->n = 0; break; }
                     std::unique_ptr<kb_rel> all, joined;
                     KB_TRY(make_view(ctx, pr, 0, pr.snapshot, (u32)pl.prem[j].s_var, (u32)pl.prem[j].o_var, &all));
+                    if (strict) KB_TRY(enforce_constants(ctx, pl.prem[j], &all));
                     KB_TRY(hash_join_impl(ctx, *cur, *all, nullptr, &joined));
                     cur = std::move(joined);
                 }
@@ -268,7 +291,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     D.head_s = term(h.s);
                     D.head_o = term(h.o);
                     D.n_filt = 0;
-                    for (u32 f = 0; f < rule.n_filters; f++) {
+                    for (u32 f = 0; f < (strict ? 0u : rule.n_filters); f++) {  // the parallel variant never evaluates rule.filters
                         const kb_rule_filter& rf = rule.filters[f];
                         const int lc = cur->col_of(rf.lhs_slot);
                         if (lc < 0 || rf.cmp == 0) continue;  // unbound lhs: the reference skips the filter (rules.rs:139)

@@ -22,6 +22,14 @@ __host__ __device__ __forceinline__ u32 mix32(u32 x) {  // murmur3 finaliser; al
     return x;
 }
 
+// shard function and the per-shard key compaction (include/kolibrie_b200.h: kb_shard_of)
+constexpr u32 SHARD_B = KB_SHARD_BLOCK_BITS;
+__host__ __device__ __forceinline__ u32 shard_of(u32 key, u32 n) { return (key >> SHARD_B) % n; }
+// cshift = log2(world) for a power-of-two world, 0 = no compaction. Monotone on the keys one shard owns.
+__host__ __device__ __forceinline__ u32 compact_key(u32 key, u32 cshift) {
+    return cshift ? ((((key >> SHARD_B) >> cshift) << SHARD_B) | (key & ((1u << SHARD_B) - 1u))) : key;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // mbarrier + TMA (cp.async.bulk, 1-D: no tensor map needed for flat u32 columns). SASS: UBLKCP / SYNCS.
 __device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }

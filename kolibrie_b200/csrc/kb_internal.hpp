@@ -68,6 +68,8 @@ struct Segment {
     u32 cmin[3] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};  // per-column id range (s,p,o), computed when the segment is loaded
     u32 cmax[3] = {0, 0, 0};
     bool has_stats = false;
+    u32 stats_world = 0;   // sharding the statistics were checked against
+    bool sharded_ok = true;  // every subject belongs to this context's shard (checked when kb_set_sharding is in effect)
 };
 }  // namespace kb
 
@@ -109,6 +111,7 @@ struct kb_ctx {
     cudaStream_t st2 = nullptr;                            // second compute stream: independent direct builds run concurrently
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     kb::u64 store_version = 0;
+    kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject
     int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges
 };
 
@@ -149,7 +152,8 @@ std::set<u32> filter_slots(const FilterProg& f);
 // pairs=true: 2-variable (?s P ?o)-shaped patterns are emitted as interleaved (s,o) pair relations (internal fast path)
 struct ScanTable {  // scan+build fusion: pattern k inserts its matches into this direct table instead of emitting rows
     u32* tab = nullptr;
-    u32 kmin = 0, range = 0;
+    u32 kmin = 0, range = 0;  // compacted key space when cshift != 0
+    u32 cshift = 0;
     u32 key_is_o = 0, trusted = 0;
     u32* dup_flag = nullptr;
 };

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
                     if ((m >> j) & 1u) {
                         const u32 key = (f & SP_TKEY_O) ? KB_ELEM(o0, o1, j) : KB_ELEM(s0, s1, j);
                         const u32 val = (f & SP_TKEY_O) ? KB_ELEM(s0, s1, j) : KB_ELEM(o0, o1, j);
-                        const u32 off = key - kbase;
+                        const u32 off = compact_key(key, P.cshift) - kbase;
                         // plain fire-and-forget store: a returning atomic here stalls the tile loop (measured 0.61 ms vs 0.49 ms for
                         // separate scan + build); duplicate keys are detected afterwards by counting the occupied slots
                         if (off < krange) tab[off] = val;
@@ -255,11 +255,11 @@ void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st) {
 // =================================================================================================================
 // K_build
 __global__ void __launch_bounds__(256) build_direct_kernel(const u32* __restrict__ keys, const u32* __restrict__ vals, u32 n,
-                                                           u32* __restrict__ table, u32 kmin, u32 range, u32* dup_flag) {
+                                                           u32* __restrict__ table, u32 kmin, u32 range, u32 cshift, u32* dup_flag) {
     const u32 stride = gridDim.x * blockDim.x;
     bool dup = false;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const u32 off = keys[i] - kmin;
+        const u32 off = compact_key(keys[i], cshift) - kmin;
         const u32 v = vals ? vals[i] : i;
         if (off < range) {
             const u32 old = atomicExch(&table[off], v);
@@ -270,11 +270,11 @@ __global__ void __launch_bounds__(256) build_direct_kernel(const u32* __restrict
     }
     if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) *dup_flag = 1u;
 }
-void launch_build_direct(const u32* keys, const u32* vals, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, int n_sms,
+void launch_build_direct(const u32* keys, const u32* vals, u32 n, u32* table, u32 kmin, u32 range, u32 cshift, u32* dup_flag, int n_sms,
                          cudaStream_t st) {
     if (n == 0) return;
     int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
-    build_direct_kernel<<<grid, 256, 0, st>>>(keys, vals, n, table, kmin, range, dup_flag);
+    build_direct_kernel<<<grid, 256, 0, st>>>(keys, vals, n, table, kmin, range, cshift, dup_flag);
 }
 
 __device__ __forceinline__ u32 key_tag(u32 n_keys, u32 k0, u32 k1, u32 k2, u32 k3) {
@@ -316,12 +316,12 @@ void launch_build_chained(const ChainTab& t, u32 n, int n_sms, cudaStream_t st) 
 
 template <bool TRUSTED>
 __global__ void __launch_bounds__(256) build_direct_pairs_kernel(const uint2* __restrict__ kv, u32 key_is_y, u32 n, u32* __restrict__ table,
-                                                                 u32 kmin, u32 range, u32* dup_flag) {
+                                                                 u32 kmin, u32 range, u32 cshift, u32* dup_flag) {
     const u32 stride = gridDim.x * blockDim.x;
     bool dup = false;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint2 e = kv[i];
-        const u32 off = (key_is_y ? e.y : e.x) - kmin;
+        const u32 off = compact_key(key_is_y ? e.y : e.x, cshift) - kmin;
         const u32 v = key_is_y ? e.x : e.y;
         if (off < range) {
             if (TRUSTED) table[off] = v;
@@ -330,12 +330,12 @@ __global__ void __launch_bounds__(256) build_direct_pairs_kernel(const uint2* __
     }
     if (__any_sync(0xffffffffu, dup) && (threadIdx.x & 31) == 0) *dup_flag = 1u;
 }
-void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, u32 trusted, int n_sms,
-                               cudaStream_t st) {
+void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32 cshift, u32* dup_flag, u32 trusted,
+                               int n_sms, cudaStream_t st) {
     if (n == 0) return;
     int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
-    if (trusted) build_direct_pairs_kernel<true><<<grid, 256, 0, st>>>(kv, key_is_y, n, table, kmin, range, dup_flag);
-    else build_direct_pairs_kernel<false><<<grid, 256, 0, st>>>(kv, key_is_y, n, table, kmin, range, dup_flag);
+    if (trusted) build_direct_pairs_kernel<true><<<grid, 256, 0, st>>>(kv, key_is_y, n, table, kmin, range, cshift, dup_flag);
+    else build_direct_pairs_kernel<false><<<grid, 256, 0, st>>>(kv, key_is_y, n, table, kmin, range, cshift, dup_flag);
 }
 
 __global__ void unpair_kernel(const uint2* __restrict__ kv, u32 n, u32* __restrict__ x, u32* __restrict__ y) {
@@ -377,6 +377,17 @@ void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, c
     const u32 n4 = n / 4;
     int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n4 + 255ull) / 256ull + 1ull);
     count_nonempty_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(table), n4, table + (u64)n4 * 4, n - n4 * 4, out_count);
+}
+__global__ void __launch_bounds__(256) count_foreign_kernel(const u32* __restrict__ col, u32 n, u32 rank, u32 world, u32* out) {
+    u32 c = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += shard_of(col[i], world) != rank;
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+void launch_count_foreign(const u32* col, u32 n, u32 rank, u32 world, u32* out, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + 255ull) / 256ull);
+    count_foreign_kernel<<<grid, 256, 0, st>>>(col, n, rank, world, out);
 }
 void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_sms, cudaStream_t st) {
     if (n == 0) return;
@@ -446,7 +457,7 @@ __global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __g
             const u32 key = P.key_is_y ? ry[j] : rx[j];
 #pragma unroll
             for (int t = 0; t < T; t++) {
-                const u32 off = key - P.tab[t].kmin;
+                const u32 off = compact_key(key, P.tab[t].cshift) - P.tab[t].kmin;
                 tv[j][t] = (((vmask >> j) & 1u) && off < P.tab[t].range) ? __ldg(P.tab[t].tab + off) : EMPTY32;
             }
         }
@@ -602,7 +613,7 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_direct_kernel(const __gri
             const u32 key = sKey[idx];
 #pragma unroll
             for (int t = 0; t < T; t++) {
-                const u32 off = key - P.tab[t].kmin;
+                const u32 off = compact_key(key, P.tab[t].cshift) - P.tab[t].kmin;
                 v[j][t] = (valid && off < P.tab[t].range) ? __ldg(P.tab[t].tab + off) : EMPTY32;
             }
             if (T == 0) v[j][0] = valid ? 0u : EMPTY32;
@@ -1188,7 +1199,7 @@ __global__ void __launch_bounds__(256) part_count_kernel(const u32* key, u32 n, 
     __shared__ u32 sc[64];
     if (threadIdx.x < 64) sc[threadIdx.x] = 0;
     __syncthreads();
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sc[mix32(key[i]) % n_parts], 1u);
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sc[shard_of(key[i], n_parts)], 1u);
     __syncthreads();
     if (threadIdx.x < n_parts && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
 }
@@ -1207,7 +1218,7 @@ __global__ void __launch_bounds__(256) part_scatter_kernel(const u32* key, u32 n
     const u32 n_round = (n + 31u) & ~31u;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         const bool valid = i < n;
-        const u32 part = valid ? mix32(key[i]) % n_parts : 0xFFFFu;
+        const u32 part = valid ? shard_of(key[i], n_parts) : 0xFFFFu;
         const unsigned act = __ballot_sync(0xffffffffu, valid);
         if (!valid) continue;
         const unsigned peers = __match_any_sync(act, part);

@@ -37,6 +37,7 @@ struct ScanParams {
     const u32 *s, *p, *o;
     u32 n, n_tiles, K;
     u32 index_base;  // global index of this segment's first triple
+    u32 cshift;      // SP_TABLE patterns: log2(world) key compaction of a subject-sharded store (0 = none)
     ScanPat pat[MAXP];
     FilterOp ops[KB_MAX_FILTER_OPS];
     NumTab nt;
@@ -53,12 +54,12 @@ void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st);
 // ---------------------------------------------------------------------------------------------------------------
 // K_build
 // DIRECT: dense dictionary ids make the identity a perfect hash: table[key - kmin] = payload (u32, EMPTY32 = none).
-void launch_build_direct(const u32* keys, const u32* vals /*null: row index*/, u32 n, u32* table, u32 kmin, u32 range,
+void launch_build_direct(const u32* keys, const u32* vals /*null: row index*/, u32 n, u32* table, u32 kmin, u32 range, u32 cshift,
                          u32* dup_flag, int n_sms, cudaStream_t st);
 // same from an interleaved (subject, object) pair relation; key_is_y selects which half is the key, the other is the payload
 // trusted=1: the (predicate, key position) is known single-valued for this store version -> plain stores, no read-modify-write
-void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32* dup_flag, u32 trusted, int n_sms,
-                               cudaStream_t st);
+void launch_build_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32 cshift, u32* dup_flag, u32 trusted,
+                               int n_sms, cudaStream_t st);
 // CHAINED multimap: open-addressing slots {key tag, head row} + next[] chains. Insert cost is O(1) whatever the key
 // multiplicity (1:N joins and heavy hitters of the Datalog joins).
 struct ChainTab {
@@ -80,7 +81,8 @@ constexpr int MAXT = 4;
 
 struct DirectTab {
     const u32* tab;
-    u32 kmin, range;
+    u32 kmin, range;  // in compacted key space when cshift != 0
+    u32 cshift;
     u32 mode;  // 0: payload is a value column  1: payload is a build-row index (gather pay[])  2: existence only
     u32 n_pay;
     const u32* pay[2];
@@ -141,6 +143,8 @@ void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st);
 void launch_unpair(const uint2* kv, u32 n, u32* x, u32* y, cudaStream_t st);
 // number of occupied (non-EMPTY32) slots of a direct table: equals the number of inserted rows iff the keys were single-valued
 void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, cudaStream_t st);
+// number of keys that do NOT belong to shard `rank` of `world` (kb_shard_of): 0 for a correctly sharded column
+void launch_count_foreign(const u32* col, u32 n, u32 rank, u32 world, u32* out, int n_sms, cudaStream_t st);
 void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_sms, cudaStream_t st);
 
 // K_probe (chained, binary): general natural join with 1:N matches, multi-column keys, FILTER, ordered compaction.

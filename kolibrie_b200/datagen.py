@@ -124,6 +124,14 @@ def employee_dataset(n_employees: int, seed: int = 42, first: int = 1, global_id
                         sal_id_by_value=sal_id_by_value, title_id_by_value=title_id_by_value)
 
 
+SHARD_BLOCK_BITS = 10  # == KB_SHARD_BLOCK_BITS
+
+
+def shard_of_np(keys: np.ndarray, world: int) -> np.ndarray:
+    """kb_shard_of on an array: block-cyclic on the dense dictionary id, (key >> 10) % world"""
+    return ((np.asarray(keys, dtype=np.uint32) >> np.uint32(SHARD_BLOCK_BITS)) % np.uint32(world)).astype(np.int64)
+
+
 def mix32_np(x: np.ndarray) -> np.ndarray:
     """kb_shard_of's hash (murmur3 finaliser) on a uint32 array"""
     with np.errstate(over="ignore"):
@@ -137,7 +145,7 @@ def mix32_np(x: np.ndarray) -> np.ndarray:
 
 
 def employee_shard(n_total: int, rank: int, world: int, seed: int = 42, prefix: int = 4_000_000) -> EmployeeData:
-    """The triples of the GLOBAL n_total-employee dataset whose subject id hashes to `rank` (mix32(subject) % world), in global
+    """The triples of the GLOBAL n_total-employee dataset whose subject id belongs to `rank` (kb_shard_of(subject, world)), in global
     document order — i.e. one GPU's shard under hash(subject) sharding. Ids are those of the global dictionary:
     once every title and salary literal has been seen (a few million employees) each further employee consumes exactly one id,
     so the tail is closed-form and a rank never materialises the other ranks' rows."""
@@ -151,7 +159,7 @@ def employee_shard(n_total: int, rank: int, world: int, seed: int = 42, prefix: 
             break
         P = min(P * 2, n_total)
     subj_head = head.s[0::6]
-    keep = mix32_np(subj_head) % np.uint32(world) == np.uint32(rank)
+    keep = shard_of_np(subj_head, world) == rank
     rows = np.repeat(keep, 6)
     S, Pp, Oo = [head.s[rows]], [head.p[rows]], [head.o[rows]]
     n_emp = int(keep.sum())
@@ -161,7 +169,7 @@ def employee_shard(n_total: int, rank: int, world: int, seed: int = 42, prefix: 
         b = min(a + chunk, n_total)
         i = np.arange(a, b, dtype=np.uint64)
         subj = (np.uint64(head.n_ids) + (i - np.uint64(P))).astype(np.uint32)
-        k = mix32_np(subj) % np.uint32(world) == np.uint32(rank)
+        k = shard_of_np(subj, world) == rank
         i, subj = i[k], subj[k]
         r_title = splitmix64_at(seed, 2 * i)
         r_sal = splitmix64_at(seed, 2 * i + 1)

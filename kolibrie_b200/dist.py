@@ -1,9 +1,11 @@
 """One process per GPU: sharding + the join-key shuffle.
 
-* triples are sharded by mix32(subject) % world (`kb_shard_of` on the host, the same function the device's `kb_partition` uses);
+* triples are sharded by `kb_shard_of(subject, world)` = (subject >> 10) % world — block-cyclic on the dense dictionary id, the same
+  function the device's `kb_partition` uses; it balances like a hash and keeps each shard's key domain dense (direct join tables
+  stay as small on N GPUs as on one: `Context.set_sharding`);
 * a star join on the subject needs no communication: every rank joins its shard, counts are summed, times are max-reduced;
 * a join on a non-subject key shuffles the rows once: `kb_partition` (device) splits a relation into `world` contiguous ranges
-  by mix32(key) % world, `all_to_all_relation` exchanges the range sizes and then the columns with
+  by kb_shard_of(key, world), `all_to_all_relation` exchanges the range sizes and then the columns with
   `torch.distributed.all_to_all_single` — NCCL over NVLink on the GPU box, gloo in the CPU tests.
 
 Only plumbing lives here; all data-touching work is in libkolibrie_b200.so.
@@ -20,8 +22,8 @@ from . import datagen
 
 
 def shard_of(keys: np.ndarray, world: int) -> np.ndarray:
-    """rank owning each key: mix32(key) % world (== kb_shard_of)"""
-    return (datagen.mix32_np(np.asarray(keys, dtype=np.uint32)) % np.uint32(world)).astype(np.int64)
+    """rank owning each key (== kb_shard_of): block-cyclic on the dense dictionary id"""
+    return datagen.shard_of_np(keys, world)
 
 
 def shard_triples(s: np.ndarray, p: np.ndarray, o: np.ndarray, rank: int, world: int):
@@ -59,7 +61,7 @@ class _DevPtr:
 
 
 def shuffle_relation(ctx, rel, key_slot: int, group=None):
-    """GPU only: re-shard `rel` so that every row lives on rank mix32(row[key_slot]) % world. Returns a new Relation."""
+    """GPU only: re-shard `rel` so that every row lives on rank kb_shard_of(row[key_slot], world). Returns a new Relation."""
     world = dist.get_world_size(group)
     n, slots = rel.info()
     part, offs = ctx.partition(rel, key_slot, world)

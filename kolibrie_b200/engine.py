@@ -435,6 +435,9 @@ class Reasoner:
     def infer_new_facts_naive(self):
         return self._infer(c.NAIVE)
 
+    def infer_new_facts_semi_naive_parallel(self):
+        return self._infer(c.SEMI_NAIVE_PARALLEL)  # semi_naive_parallel.rs:11: 1-2 premise rules, no filters, constants enforced
+
     def infer_new_facts(self):
         return self.infer_new_facts_naive()  # my_naive.rs:78-80 "for backward compatibility"
 

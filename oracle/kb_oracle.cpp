@@ -635,7 +635,7 @@ struct Bind { u32 v[MAXV]; };
 
 struct RulePlan {
     u32 n_vars = 0;  // real + synthetic (quirk Q6) variable slots
-    struct Prem { int s_var, o_var; bool pred_const; u32 pred; } prem[KB_MAX_PREMISES];
+    struct Prem { int s_var, o_var; bool pred_const; u32 pred; bool s_is_const, o_is_const; u32 s_const, o_const; } prem[KB_MAX_PREMISES];
     u32 n_prem = 0;
 };
 
@@ -662,6 +662,8 @@ RulePlan plan_rule(const kb_rule& r, u32 max_real_slot_plus1) {
         pl.prem[i].o_var = (int)(p.o.is_var ? p.o.value : syn(2, p.o.value));
         pl.prem[i].pred_const = !p.p.is_var;
         pl.prem[i].pred = p.p.value;
+        pl.prem[i].s_is_const = !p.s.is_var; pl.prem[i].s_const = p.s.value;
+        pl.prem[i].o_is_const = !p.o.is_var; pl.prem[i].o_const = p.o.value;
     }
     pl.n_vars = next;
     return pl;
@@ -670,12 +672,17 @@ RulePlan plan_rule(const kb_rule& r, u32 max_real_slot_plus1) {
 struct PairHash { size_t operator()(const std::pair<u32, u32>& p) const { return (size_t)mix64(((u64)p.first << 32) | p.second); } };
 
 // perform_hash_join_for_rules (join_algorithm.rs:499-570) + build_simple_hash_table (:582-622) + process_triple_fast (:625-677)
-std::vector<Bind> join_premise(const RulePlan::Prem& pr, const Triple* facts, u64 n_facts, const std::vector<Bind>& cur) {
+std::vector<Bind> join_premise(const RulePlan::Prem& pr, const Triple* facts, u64 n_facts, const std::vector<Bind>& cur, bool strict = false) {
     std::vector<Bind> out;
     if (cur.empty()) return out;        // :510-512
     if (!pr.pred_const) return out;     // :515-521 variable predicate never matches
     std::vector<const Triple*> filt;    // :528-534 predicate pre-filter
-    for (u64 i = 0; i < n_facts; i++) if (facts[i].p == pr.pred) filt.push_back(&facts[i]);
+    for (u64 i = 0; i < n_facts; i++) {
+        if (facts[i].p != pr.pred) continue;
+        // strict = matches_rule_pattern (rules.rs:9-72): constants in subject / object position must equal the fact's
+        if (strict && ((pr.s_is_const && facts[i].s != pr.s_const) || (pr.o_is_const && facts[i].o != pr.o_const))) continue;
+        filt.push_back(&facts[i]);
+    }
     if (filt.empty()) return out;
     std::unordered_map<std::pair<u32, u32>, std::vector<u32>, PairHash> both;
     std::unordered_map<u32, std::vector<u32>> sb, ob;
@@ -762,6 +769,8 @@ FixpointOut fixpoint(const std::vector<Triple>& base, const kb_rule* rules, u32 
             std::vector<Bind> sols;
             Bind empty;
             for (u32 k = 0; k < MAXV; k++) empty.v[k] = UNB;
+            const bool strict = strategy == KB_SEMI_NAIVE_PARALLEL;
+            if (strict && rule.n_premise != 1 && rule.n_premise != 2) continue;  // semi_naive_parallel.rs:149 `_ => {}`
             if (strategy == KB_NAIVE) {
                 if (rule.n_premise > 0) {
                     std::vector<Bind> cur{empty};
@@ -771,17 +780,17 @@ FixpointOut fixpoint(const std::vector<Triple>& base, const kb_rule* rules, u32 
             } else {
                 for (u32 i = 0; i < rule.n_premise; i++) {  // semi_naive.rs:22-44
                     std::vector<Bind> cur{empty};
-                    cur = join_premise(pl.prem[i], delta, n_delta, cur);
+                    cur = join_premise(pl.prem[i], delta, n_delta, cur, strict);
                     for (u32 j = 0; j < rule.n_premise; j++) {
                         if (j == i) continue;
-                        cur = join_premise(pl.prem[j], all.data(), end, cur);
+                        cur = join_premise(pl.prem[j], all.data(), end, cur, strict);
                         if (cur.empty()) break;
                     }
                     sols.insert(sols.end(), cur.begin(), cur.end());
                 }
             }
             for (const Bind& b : sols) {
-                if (!rule_filters_pass(rule, b, nt)) continue;
+                if (!strict && !rule_filters_pass(rule, b, nt)) continue;  // the parallel variant never evaluates rule.filters
                 for (u32 c = 0; c < rule.n_conclusion; c++) {
                     const kb_pattern& h = rule.conclusion[c];
                     auto term = [&](const kb_term& t, bool* ok) -> u32 {

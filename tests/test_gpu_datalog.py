@@ -47,7 +47,7 @@ def test_fc_like_the_reference_test(ctx, case):
     H.assert_same_bag(np.array(new_facts, dtype=np.uint32).reshape(-1, 3), want["facts"], case["name"])
 
 
-@pytest.mark.parametrize("strategy", [c.SEMI_NAIVE, c.NAIVE])
+@pytest.mark.parametrize("strategy", [c.SEMI_NAIVE, c.NAIVE, c.SEMI_NAIVE_PARALLEL])
 def test_taxonomy_closure_vs_oracle(ctx, strategy):
     """config 4 shape at 1/1000 scale: R1 transitive subClassOf, R2 type propagation; rounds and per-round counts must match"""
     t = datagen.taxonomy_dataset(fanout=4, depth=5, n_instances=20000)
@@ -89,3 +89,15 @@ def test_rule_filters_and_constants_quirks(ctx):
     a, b = d.lookup("a"), d.lookup("b")
     assert (a, adult, yes) in got and (b, adult, yes) not in got
     assert (b, human, yes) in got, "quirk Q6: (?x type Person) matches every type triple in the reference"
+    # the parallel strategy (semi_naive_parallel.rs) enforces the constant and skips the filter — same answer as the oracle's
+    r2 = Reasoner(ctx)
+    for t in [("a", "age", "30"), ("b", "age", "17"), ("c", "age", "x"), ("a", "type", "Person"), ("b", "type", "Robot")]:
+        r2.add_abox_triple(*t)
+    for x in ("age", "adult", "type", "human", "yes", "Person"):
+        r2.dictionary.encode(x)
+    assert r2.dictionary.id_to_string == d.id_to_string[: len(r2.dictionary.id_to_string)]
+    r2.rules = list(r.rules)
+    got2 = set(r2.infer_new_facts_semi_naive_parallel())
+    want2 = O.Db(facts[:, 0], facts[:, 1], facts[:, 2], *d.numeric_table()).fixpoint([compile_rule(x) for x in r.rules], c.SEMI_NAIVE_PARALLEL)
+    assert got2 == {tuple(int(v) for v in row) for row in want2["facts"]}
+    assert (b, human, yes) not in got2 and (b, adult, yes) in got2

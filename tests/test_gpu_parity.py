@@ -289,3 +289,26 @@ def test_errors_are_reported_not_swallowed(ctx):
     with pytest.raises(c.KolibrieError) as e:
         ctx.filter(ctx.rel_from_host([0], [np.arange(4, dtype=np.uint32)]), [c.fop(c.F_AND)])
     assert e.value.status == c.KB_E_INVALID
+
+
+@pytest.mark.parametrize("claimed_rank", [1, 2])
+def test_sharded_store_key_compaction(claimed_rank):
+    """one rank's shard of a 4-way subject-sharded store: kb_set_sharding compacts the key domain of the direct tables
+    (block-cyclic shard function). A context that CLAIMS the wrong rank must notice (foreign subjects) and stay correct."""
+    world, rank = 4, 1
+    d = datagen.employee_shard(60000, rank, world, prefix=20000)
+    assert (np.array([c.lib().kb_shard_of(int(x), world) for x in d.s[::997]]) == rank).all()
+    ctx2 = c.Context(0)
+    try:
+        ctx2.set_sharding(claimed_rank, world)
+        ctx2.store_load(d.s, d.p, d.o)
+        ctx2.dict_numeric_load(d.num_or0, d.is_num)
+        db = O.Db(d.s, d.p, d.o, d.num_or0, d.is_num)
+        for q in ("cfg2", "cfg3"):
+            js, pats, filt = datagen.employee_queries(d)[q]
+            got = ctx2.star_join(js, pats, filt)
+            want = db.bgp(pats, filt)
+            H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"{q} claimed rank {claimed_rank}")
+        assert ctx2.get_stats()["fused_scan_builds"] >= 2
+    finally:
+        ctx2.close()

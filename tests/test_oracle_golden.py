@@ -40,6 +40,41 @@ def test_fc_fixture(case, strategy):
         assert len(again["facts"]) == 0, "second inference pass derives nothing new"
 
 
+PAR_OK = [x for x in FC if all(not r["filters"] and len(r["premise"]) <= 2 for r in x["rules"])]
+
+
+@pytest.mark.parametrize("case", PAR_OK, ids=[x["name"] for x in PAR_OK])
+def test_fc_fixture_parallel_strategy(case):
+    """infer_new_facts_semi_naive_parallel (semi_naive_parallel.rs:11-176) has no test in the reference; on rule sets without
+    filters and with at most two premises it must agree with the semi-naive strategy the fixtures pin."""
+    d, facts, rules = H.build_fc_case(case)
+    db = O.Db(facts[:, 0], facts[:, 1], facts[:, 2], *d.numeric_table())
+    a = db.fixpoint([compile_rule(r) for r in rules], c.SEMI_NAIVE)
+    b = db.fixpoint([compile_rule(r) for r in rules], c.SEMI_NAIVE_PARALLEL)
+    H.assert_same_bag(a["facts"], b["facts"], case["name"])
+
+
+def test_parallel_strategy_enforces_constants_and_ignores_filters():
+    """matches_rule_pattern (rules.rs:9-72) checks constants in subject/object positions — the hash-join strategies do not
+    (quirk Q6) — and the parallel variant never evaluates rule.filters."""
+    from kolibrie_b200.engine import Constant, FilterCondition, Rule, Variable
+
+    d = Dictionary()
+    facts = np.array([[d.encode(s), d.encode(p), d.encode(o)] for s, p, o in
+                      [("a", "type", "Person"), ("b", "type", "Robot"), ("a", "parent", "P"), ("b", "parent", "P")]], dtype=np.uint32)
+    typ, human, yes, person, parent, sib = (d.encode(x) for x in ("type", "human", "yes", "Person", "parent", "sibling"))
+    rules = [Rule([(Variable("X"), Constant(typ), Constant(person))], [(Variable("X"), Constant(human), Constant(yes))]),
+             Rule([(Variable("X"), Constant(parent), Variable("Z")), (Variable("Y"), Constant(parent), Variable("Z"))],
+                  [(Variable("X"), Constant(sib), Variable("Y"))], [FilterCondition("X", "!=", "Y")])]
+    db = O.Db(facts[:, 0], facts[:, 1], facts[:, 2], *d.numeric_table())
+    par = {tuple(int(v) for v in r) for r in db.fixpoint([compile_rule(r) for r in rules], c.SEMI_NAIVE_PARALLEL)["facts"]}
+    sn = {tuple(int(v) for v in r) for r in db.fixpoint([compile_rule(r) for r in rules], c.SEMI_NAIVE)["facts"]}
+    a, b = d.lookup("a"), d.lookup("b")
+    assert (a, human, yes) in par and (b, human, yes) not in par, "parallel: constant object enforced"
+    assert (b, human, yes) in sn, "hash-join strategies: quirk Q6"
+    assert (a, sib, a) in par and (a, sib, a) not in sn, "parallel: filters are not evaluated"
+
+
 def test_integration_fixture_scan_counts():
     """kolibrie/tests/integration_test.rs:131-299 — Exact-filter scans are id-equality scans."""
     fx = H.load("integration_fixture.json")
