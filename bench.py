@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=300_000, help="employees in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-index", action="store_true", help="headline on the store-scanning path (no predicate-partitioned index)")
     return ap.parse_args()
 
 
@@ -204,6 +205,8 @@ def main():
     ctx.set_sharding(rank, world)
     ctx.dict_numeric_load(d.num_or0, d.is_num)
     ctx.store_load(d.s, d.p, d.o)
+    # SparqlDatabase::build_all_indexes, once, outside the timed region (the reference's harnesses do the same, n_triple_10M.rs:91-95)
+    n_pred, index_ms = (0, 0.0) if args.no_index else ctx.build_index()
     js, pats, filt = datagen.employee_queries(d)[args.query]
 
     def step_resident():
@@ -226,6 +229,24 @@ def main():
     barrier()
     dt = time.perf_counter() - t0
     st = ctx.get_stats(reset=True)
+    # the same K steps on the store-SCANNING path (index switched off): the K_scan / K_build / K_probe numbers of SURVEY.md §8(d)
+    scan_leg = None
+    if not args.no_index:
+        ctx.set_use_index(False)
+        for _ in range(3):
+            step_resident()
+        ctx.get_stats(reset=True)
+        barrier()
+        t0s = time.perf_counter()
+        for _ in range(args.steps):
+            rows_scan = step_resident()
+        ctx.synchronize()
+        barrier()
+        dts = time.perf_counter() - t0s
+        st_scan = ctx.get_stats(reset=True)
+        assert rows_scan == rows_step
+        scan_leg = (dts, st_scan)
+        ctx.set_use_index(True)
     ctx.set_timing(False)
 
     # ---- e2e: host (pinned) buffers in, host (pinned) buffers out, through kb_star_join_host
@@ -258,11 +279,13 @@ def main():
 
     # ---- reduce over ranks: max time, sum of rows
     if world > 1:
-        t = torch.tensor([dt, e2e["dt"] if e2e else 0.0], dtype=torch.float64, device=dev)
+        t = torch.tensor([dt, e2e["dt"] if e2e else 0.0, scan_leg[0] if scan_leg else 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         r = torch.tensor([rows_step, n], dtype=torch.int64, device=dev)
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
         dt, dte = float(t[0]), float(t[1])
+        if scan_leg:
+            scan_leg = (float(t[2]), scan_leg[1])
         rows_all, n_all = int(r[0]), int(r[1])
     else:
         dte = e2e["dt"] if e2e else 0.0
@@ -278,53 +301,72 @@ def main():
 
     # ---- roofline of each kernel family (rank 0's launches): algorithmic bytes per SURVEY.md §8(d)
     K = args.steps
-    # rows per pattern after push-down: the FILTER pattern keeps rows_step rows, the others keep every employee
     E_loc = d.n_employees
     n_pat = len(pats)
     m_rows = []
     for k in range(n_pat):
         filtered = bool(filt) and k == 1  # cfg2: the salary pattern carries the FILTER
         m_rows.append(rows_step if filtered else E_loc)
-    b_scan = 12 * n + sum(4 * 2 * m for m in m_rows)
-    probe_k = int(np.argmax(m_rows))
-    builds = [m for k, m in enumerate(m_rows) if k != probe_k]
-    b_build = sum(16 * m for m in builds)
+    probe_k = max((k for k in range(n_pat) if not (bool(filt) and k == 1)), key=lambda k: m_rows[k])
+    builds = [k for k in range(n_pat) if k != probe_k]
     T = len(builds)
     b_probe = 4 * 2 * m_rows[probe_k] + 8 * T * m_rows[probe_k] + 4 * (n_pat + 1) * rows_step
-    fused = st.get("fused_scan_builds", 0) > 0
-    if fused:
-        # the scan kernel inserts the build-side patterns straight into their direct tables: one kernel does K_scan and K_build of
-        # SURVEY.md §8(d) (the table memsets are timed in the same family); its algorithmic bytes are the sum of the two formulas
-        fam = {
-            "scan+build": {"alg_bytes": b_scan + b_build, "ms": (st["scan_ms"] + st["build_ms"]) / K, "launches_per_step": st["scan_launches"] / K,
-                           "note": "fused scan_kernel<K> (SP_TABLE patterns) + cudaMemsetAsync of the direct tables"},
-            "probe": {"alg_bytes": b_probe, "ms": st["probe_ms"] / K, "launches_per_step": st["probe_launches"] / K},
-        }
-    else:
-        fam = {
-            "scan": {"alg_bytes": b_scan, "ms": st["scan_ms"] / K, "launches_per_step": st["scan_launches"] / K},
-            "build": {"alg_bytes": b_build, "ms": st["build_ms"] / K, "launches_per_step": st["build_launches"] / K},
-            "probe": {"alg_bytes": b_probe, "ms": st["probe_ms"] / K, "launches_per_step": st["probe_launches"] / K},
-        }
-    for k, v in fam.items():
-        v["achieved_gbs"] = v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None
-        v["frac"] = v["achieved_gbs"] / peak if v["achieved_gbs"] else None
-    dom = max(fam, key=lambda k: fam[k]["ms"])
-    roofline = {"bound": "hbm", "kernel": {"scan": "kb::scan_kernel<K>", "scan+build": "kb::scan_kernel<K> (fused scan + direct-table build)", "build": "kb::build_direct_pairs_kernel (+ table memset)", "probe": "kb::probe_fast_kernel<T>"}[dom],
-                "achieved": fam[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": fam[dom]["frac"], "traffic": traffic_from_profiles(dom.split("+")[0]),
-                "peak_source": peak_src, "alg_bytes_per_launch": fam[dom]["alg_bytes"], "ms_per_launch": fam[dom]["ms"], "families": fam,
-                "device_ms_per_step": st["total_ms"] / K}
+    kernel_names = {"scan": "kb::scan_kernel<K>", "scan+build": "kb::scan_kernel<K> (fused scan + direct-table build) + table memsets",
+                    "build": "kb::build_pairs_filtered_kernel / build_direct_pairs_kernel + table memsets", "probe": "kb::probe_fast_kernel<T>"}
+
+    def families(stx, indexed):
+        if indexed:
+            # build sides are read from their predicate slices: 8 B per slice row in, (filtered) rows into the table: 8*M_slice + 8*M_b
+            b_build = sum(8 * E_loc + 8 * m_rows[k] for k in builds)
+            fam = {"build": {"alg_bytes": b_build, "ms": stx["build_ms"] / K, "launches_per_step": T,
+                             "note": "index path: K_build reads the predicate slice (8 B/row) and evaluates the pushed-down FILTER itself"},
+                   "probe": {"alg_bytes": b_probe, "ms": stx["probe_ms"] / K, "launches_per_step": stx["probe_launches"] / K}}
+        else:
+            b_scan = 12 * n + sum(4 * 2 * m for m in m_rows)
+            b_build = sum(16 * m_rows[k] for k in builds)
+            if stx.get("fused_scan_builds", 0) > 0:
+                fam = {"scan+build": {"alg_bytes": b_scan + b_build, "ms": (stx["scan_ms"] + stx["build_ms"]) / K, "launches_per_step": stx["scan_launches"] / K,
+                                      "note": "one kernel does K_scan and K_build of SURVEY.md 8(d): build-side patterns insert into their direct tables"},
+                       "probe": {"alg_bytes": b_probe, "ms": stx["probe_ms"] / K, "launches_per_step": stx["probe_launches"] / K}}
+            else:
+                fam = {"scan": {"alg_bytes": b_scan, "ms": stx["scan_ms"] / K, "launches_per_step": stx["scan_launches"] / K},
+                       "build": {"alg_bytes": b_build, "ms": stx["build_ms"] / K, "launches_per_step": stx["build_launches"] / K},
+                       "probe": {"alg_bytes": b_probe, "ms": stx["probe_ms"] / K, "launches_per_step": stx["probe_launches"] / K}}
+        for v in fam.values():
+            v["achieved_gbs"] = v["alg_bytes"] / (v["ms"] * 1e-3) / 1e9 if v["ms"] > 0 else None
+            v["frac"] = v["achieved_gbs"] / peak if v["achieved_gbs"] else None
+        return fam
+
+    def roof(fam, stx):
+        dom = max(fam, key=lambda k: fam[k]["ms"])
+        return {"bound": "hbm", "kernel": kernel_names[dom], "achieved": fam[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": fam[dom]["frac"],
+                "traffic": traffic_from_profiles(dom.split("+")[0] + ("_index" if stx.get("index_joins", 0) else "")), "peak_source": peak_src,
+                "alg_bytes_per_launch": fam[dom]["alg_bytes"], "ms_per_launch": fam[dom]["ms"], "families": fam, "device_ms_per_step": stx["total_ms"] / K}
+
+    indexed = st.get("index_joins", 0) > 0
+    roofline = roof(families(st, indexed), st)
+    scan_path = None
+    if scan_leg is not None:
+        dts, st_scan = scan_leg
+        scan_path = {"value": rows_all / (dts / K), "unit": UNIT, "ms_per_step": dts / K * 1e3, "gpu_launches": int(st_scan["kernel_launches"]),
+                     "roofline": roof(families(st_scan, False), st_scan),
+                     "note": "same K steps with the index switched off: every step scans the 12-byte/triple store (the e2e leg always does)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(args), "triples_total": n_all, "bindings_per_step": rows_all, "sharding": "kb_shard_of(subject) = (id >> 10) % n_gpus (block-cyclic on dense ids), no data-path collective",
-                   "l2": "inputs (1.2 GB of triple columns per GPU) are far larger than the 126 MB L2; no explicit flush", "datagen_s": round(t_gen, 1),
+                   "l2": "inputs per step (index path: 0.4 GB of predicate slices + 0.13 GB of tables; scan path: 1.2 GB of triple columns) exceed the 126 MB L2; no explicit flush",
+                   "store": ("predicate-partitioned index built ONCE at load by kb_store_build_index (= SparqlDatabase::build_all_indexes), %d predicates, %.1f ms, outside the timed region"
+                             % (n_pred, index_ms)) if not args.no_index else "unindexed: every step scans the store",
+                   "datagen_s": round(t_gen, 1),
                    "timing": "wall clock around K steps between barrier+synchronize, max over ranks; every step ends with a stream sync inside the library"},
         "roofline": roofline,
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": sampler.summary(),
     }
+    if scan_path:
+        line["scan_path"] = scan_path
     if e2e:
         line["e2e"] = {"value": rows_all / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "ms_per_step": dte / args.steps * 1e3, "api": "kb_star_join_host (pinned host columns in, pinned host binding columns out; chunked upload overlapped with the scan)"}

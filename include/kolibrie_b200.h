@@ -147,6 +147,7 @@ typedef struct kb_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t kernel_launches; /* launches of this library's own kernels (memsets and copies not counted) */
     uint64_t fused_scan_builds; /* star joins whose build sides were inserted into their tables by the scan kernel itself */
+    uint64_t index_joins;       /* star joins answered from the predicate-partitioned index (no store scan) */
 } kb_stats;
 
 /* ------------------------------------------------------------------ context */
@@ -168,6 +169,12 @@ KB_API kb_status kb_store_evict(kb_ctx* ctx, uint64_t segment_tag);
 /* set-difference by value (SparqlDatabase::delete_triple, sparql_database.rs:229-242) */
 KB_API kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n);
 KB_API kb_status kb_store_clear(kb_ctx* ctx);
+/* SparqlDatabase::build_all_indexes (kolibrie/src/sparql_database.rs:3364-3394) on the device: partitions the store by predicate into
+ * interleaved (subject, object) slices — what the reference's pos/pso indexes give an index scan of `?s P ?o` (engine.rs:1364-1378).
+ * Joins over such patterns then read 8 bytes per MATCHING triple instead of scanning 12 bytes per triple of the store. Dropped by
+ * any store mutation (load/append/evict/delete/inferred facts); skipped (KB_OK, n_predicates = 0) above 4096 distinct predicates. */
+KB_API kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* build_ms);
+KB_API kb_status kb_set_use_index(kb_ctx* ctx, int enabled);
 KB_API kb_status kb_store_size(kb_ctx* ctx, uint64_t* n_triples, uint32_t* n_segments);
 /* id -> f64 side table computed by the host with Rust `str::parse::<f64>` acceptance:
  * num_or0[id] = parse().unwrap_or(0.0); is_num[id] = parse().is_ok(). ids >= n_ids read as (0.0, not numeric). */

@@ -67,7 +67,7 @@ class KbStats(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("scan_ms", "build_ms", "probe_ms", "filter_ms", "group_ms", "other_ms", "total_ms")] + [
         (n, C.c_uint64)
         for n in ("scan_launches", "build_launches", "probe_launches", "filter_launches", "group_launches", "other_launches",
-                  "rows_scanned", "rows_built", "rows_probed", "rows_out", "h2d_bytes", "d2h_bytes", "kernel_launches", "fused_scan_builds")
+                  "rows_scanned", "rows_built", "rows_probed", "rows_out", "h2d_bytes", "d2h_bytes", "kernel_launches", "fused_scan_builds", "index_joins")
     ]
 
     def as_dict(self):
@@ -152,6 +152,8 @@ def lib() -> C.CDLL:
         "kb_store_evict": (i32, [vp, u64]),
         "kb_store_delete": (i32, [vp, vp, vp, vp, u64]),
         "kb_store_clear": (i32, [vp]),
+        "kb_store_build_index": (i32, [vp, P(u32), P(C.c_double)]),
+        "kb_set_use_index": (i32, [vp, C.c_int]),
         "kb_store_size": (i32, [vp, P(u64), P(u32)]),
         "kb_store_download": (i32, [vp, vp, vp, vp, u64, P(u64)]),
         "kb_dict_numeric_load": (i32, [vp, vp, vp, u32]),
@@ -190,7 +192,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "kb_version", "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_set_timing", "kb_get_stats", "kb_synchronize",
-    "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_size",
+    "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
     "kb_store_download", "kb_dict_numeric_load", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free",
@@ -311,6 +313,15 @@ class Context:
 
     def store_clear(self):
         self._check(lib().kb_store_clear(self.h))
+
+    def build_index(self):
+        """SparqlDatabase::build_all_indexes on the device: partition the store by predicate. Returns (n_predicates, build_ms)."""
+        n, ms = C.c_uint32(), C.c_double()
+        self._check(lib().kb_store_build_index(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def set_use_index(self, on: bool):
+        self._check(lib().kb_set_use_index(self.h, 1 if on else 0))
 
     def store_size(self):
         n, ns = C.c_uint64(), C.c_uint32()

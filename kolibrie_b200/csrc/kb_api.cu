@@ -666,6 +666,173 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
     bool all_pairs = K >= 2;
     for (u32 k = 0; k < K; k++) if (!(pv[k].size() == 2 && psrc[k][0] == 0 && psrc[k][1] == 2)) all_pairs = false;
 
+    // ---- INDEX path: every pattern is (?s P ?o) over a predicate the store index has a slice for: no store scan at all. Build sides
+    // are inserted from their slices (pushed-down FILTER evaluated in the build kernel), the probe side IS its slice (zero copy).
+    if (allow_fused_scan && ctx->use_index && ctx->index_version == ctx->store_version && all_pairs && K - 1 <= (u32)MAXT) {
+        bool ok = true, empty = false;
+        std::vector<const PredSlice*> sl(K, nullptr);
+        for (u32 k = 0; k < K; k++) {
+            if (pats[k].p.is_var) { ok = false; break; }
+            auto it = ctx->index.find(pats[k].p.value);
+            if (it == ctx->index.end() || it->second.n == 0) { empty = true; continue; }  // predicate absent from the store
+            sl[k] = &it->second;
+        }
+        for (u32 a = 0; a < K && ok; a++)
+            for (u32 b = a + 1; b < K && ok; b++)
+                for (u32 s2 : pv[a]) if (s2 != join_slot && std::find(pv[b].begin(), pv[b].end(), s2) != pv[b].end()) ok = false;
+        if (ok && empty) {
+            auto r = std::make_unique<kb_rel>();
+            r->slots = all_slots;
+            for (size_t c = 0; c < all_slots.size(); c++) { Col col; KB_TRY(alloc_col(ctx, 0, &col)); r->cols.push_back(col); }
+            *out = std::move(r);
+            return KB_OK;
+        }
+        u32 kmn = 0xFFFFFFFFu, kmx = 0;
+        u32 cshift = 0;
+        if (ok) {
+            bool subj = true;
+            for (u32 k = 0; k < K; k++) {
+                const bool y = key_pos(k) == 2;
+                kmn = std::min(kmn, y ? sl[k]->ymin : sl[k]->xmin);
+                kmx = std::max(kmx, y ? sl[k]->ymax : sl[k]->xmax);
+                if (y) subj = false;
+            }
+            for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world || !sg.sharded_ok)) subj = false;
+            const u32 w = ctx->shard_world;
+            if (subj && w > 1 && (w & (w - 1)) == 0) while ((1u << cshift) < w) cshift++;
+            kmn = compact_key(kmn, cshift);
+            kmx = compact_key(kmx, cshift);
+        }
+        // probe side: the largest slice among the patterns without a pushed-down filter (a filtered side is the smaller build side)
+        int probe_k = -1;
+        for (u32 k = 0; k < K && ok; k++) if (pushdown[k].ops.empty() && (probe_k < 0 || sl[k]->n > sl[probe_k]->n)) probe_k = (int)k;
+        if (ok && probe_k < 0) { probe_k = 0; for (u32 k = 1; k < K; k++) if (sl[k]->n > sl[probe_k]->n) probe_k = (int)k; }
+        const u64 rng = (ok && kmx >= kmn) ? (u64)kmx - kmn + 1 : 0;
+        for (u32 k = 0; k < K && ok; k++) {
+            if ((int)k == probe_k) continue;
+            if (rng == 0 || rng > std::max<u64>(8 * sl[k]->n, 1ull << 16) || rng > (1ull << 31)) ok = false;
+            if (ctx->multi_valued.count({pats[k].p.value, key_pos(k)})) ok = false;
+        }
+        if (ok) {
+            const u32 range = (u32)rng;
+            const u32 off = ctrl_alloc(ctx, 16 + 2 * MAXT);
+            KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, (16 + 2 * MAXT) * sizeof(u32), ctx->st));
+            std::vector<Buf> tabs;
+            DirectTab dt[MAXT];
+            std::vector<u32> tab_k;
+            std::vector<u32> out_slots = pv[probe_k];
+            std::vector<OutCol> ocs{OutCol{OUT_PROBE, 0, 0}, OutCol{OUT_PROBE, 1, 0}};
+            const u32 T = K - 1;
+            timer_begin(ctx, F_BUILD, (int)T);
+            for (u32 t = 0; t < T; t++) { Buf b; KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &b)); tabs.push_back(b); }
+            if (T > 1) {
+                KB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->st));
+                KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
+            }
+            u32 t = 0;
+            for (u32 k = 0; k < K; k++) {
+                if ((int)k == probe_k) continue;
+                cudaStream_t bs = (T > 1 && (t & 1)) ? ctx->st2 : ctx->st;
+                u32* tab = static_cast<u32*>(tabs[t]->p);
+                KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), bs));
+                BuildPairsParams B{};
+                B.kv = reinterpret_cast<const uint2*>(sl[k]->pairs.ptr);
+                B.n = (u32)sl[k]->n;
+                B.key_is_y = key_pos(k) == 2 ? 1u : 0u;
+                B.pred = pats[k].p.value;
+                B.table = tab; B.kmin = kmn; B.range = range; B.cshift = cshift;
+                B.dup_flag = ctx->ctrl + off + 16 + t;
+                B.count = ctx->ctrl + off + 16 + MAXT + t;
+                B.trusted = ((key_pos(k) == 2 ? sl[k]->y_unique : sl[k]->x_unique) || ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;
+                B.nt = numtab(ctx);
+                if (!pushdown[k].ops.empty()) {
+                    std::map<u32, u32> remap;
+                    for (size_t i = 0; i < pv[k].size(); i++) remap[pv[k][i]] = psrc[k][i];
+                    std::vector<FilterOp> fo;
+                    if (!append_prog(&fo, pushdown[k], remap)) return fail(ctx, KB_E_INVALID, "pushed-down filter uses a variable the pattern does not bind");
+                    B.n_ops = (u32)fo.size();
+                    for (size_t i = 0; i < fo.size(); i++) B.ops[i] = fo[i];
+                }
+                launch_build_direct_pairs_filtered(B, ctx->n_sms, bs);
+                DirectTab& D = dt[t];
+                D.tab = tab; D.kmin = kmn; D.range = range; D.cshift = cshift; D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                out_slots.push_back(pv[k][key_pos(k) == 0 ? 1 : 0]);
+                ocs.push_back(OutCol{OUT_TABVAL, t, 0});
+                tab_k.push_back(k);
+                ctx->stats.rows_built += sl[k]->n;
+                t++;
+            }
+            if (T > 1) {
+                KB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->st2));
+                KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
+            }
+            timer_end(ctx);
+            const PredSlice& PS = *sl[probe_k];
+            auto res = std::make_unique<kb_rel>();
+            res->slots = out_slots;
+            const u32 n_out = (u32)out_slots.size();
+            FilterProg postp = post;  // a filter pushed to the probe pattern is evaluated on the joined row instead
+            if (!pushdown[probe_k].ops.empty()) {
+                const bool had = !postp.ops.empty();
+                postp.ops.insert(postp.ops.end(), pushdown[probe_k].ops.begin(), pushdown[probe_k].ops.end());
+                if (had) { kb_filter_op a{}; a.op = KB_F_AND; postp.ops.push_back(a); }
+            }
+            std::vector<FilterOp> fops;
+            if (!postp.ops.empty()) {
+                std::map<u32, u32> remap;
+                for (u32 c = 0; c < n_out; c++) remap[out_slots[c]] = c;
+                if (!append_prog(&fops, postp, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
+                if (fops.size() > KB_MAX_FILTER_OPS) return fail(ctx, KB_E_LIMIT, "filter too long");
+            }
+            ProbeFParams P{};
+            P.pairs = reinterpret_cast<const uint2*>(PS.pairs.ptr);
+            P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
+            P.n = (u32)PS.n;
+            P.n_tiles = (u32)((PS.n + PROBEF_TILE - 1) / PROBEF_TILE);
+            P.T = T;
+            for (u32 q = 0; q < T; q++) P.tab[q] = dt[q];
+            P.n_out = n_out;
+            for (u32 c = 0; c < n_out; c++) {
+                Col col;
+                KB_TRY(alloc_col(ctx, PS.n, &col));
+                res->cols.push_back(col);
+                P.oc[c] = ocs[c];
+                P.out[c] = col.ptr;
+            }
+            P.cap = (u32)PS.n;
+            P.n_ops = (u32)fops.size();
+            for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
+            P.nt = numtab(ctx);
+            KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+            P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+            P.block_state = static_cast<u64*>(ctx->block_state->p);
+            P.ordered = ctx->ordered;
+            P.ticket = ctx->ctrl + off;
+            P.total = ctx->ctrl + off + 1;
+            P.zero_word = ctx->ctrl + off + 2;
+            P.abort_flag = nullptr;
+            P.epoch = ctx->epoch++;
+            timer_begin(ctx, F_PROBE);
+            launch_probe_fast(P, ctx->n_sms, ctx->st);
+            timer_end(ctx);
+            KB_CUDA(ctx, cudaGetLastError());
+            ctx->stats.rows_probed += PS.n;
+            ctx->stats.index_joins++;
+            KB_TRY(ctrl_read(ctx));
+            bool dup = false;
+            for (u32 q = 0; q < T; q++) if (ctx->h_ctrl[off + 16 + q]) {
+                dup = true;
+                ctx->multi_valued.insert({pats[tab_k[q]].p.value, key_pos(tab_k[q])});
+            }
+            if (dup) return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, true, out);  // multi-valued is now cached: takes the chained route
+            for (u32 q = 0; q < T; q++)
+                if (pushdown[tab_k[q]].ops.empty()) ctx->single_valued.insert({pats[tab_k[q]].p.value, key_pos(tab_k[q])});
+            res->n = ctx->h_ctrl[off + 1];
+            *out = select_cols(*res, all_slots);
+            return KB_OK;
+        }
+    }
+
     // ---- scan + build FUSED: the build-side patterns insert straight into their direct tables while the store is scanned; only the
     // probe-side pattern is materialised. Needs the key range before the scan (load-time statistics) and a probe side chosen without
     // knowing the counts: the last pattern that carries no pushed-down filter (a filtered side is the smaller build side).
@@ -1125,6 +1292,7 @@ kb_status kb_ctx_create(int device, kb_ctx** out) {
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     if (const char* ord = getenv("KOLIBRIE_ORDERED")) ctx->ordered = (ord[0] == '0') ? 0u : 1u;
+    if (const char* ui = getenv("KOLIBRIE_USE_INDEX")) ctx->use_index = ui[0] != '0';
     if ((e = cudaMalloc(&ctx->ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMalloc(ctrl)", e);
     if ((e = cudaMallocHost(&ctx->h_ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMallocHost(ctrl)", e);
     *out = ctx;
@@ -1138,6 +1306,7 @@ void kb_ctx_destroy(kb_ctx* ctx) {
     cudaStreamSynchronize(ctx->st_copy);
     kb::timers_flush(ctx);
     ctx->segs.clear();
+    ctx->index.clear();
     ctx->num.reset();
     ctx->isnum.reset();
     ctx->tile_state.reset();
@@ -1206,6 +1375,7 @@ static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, cons
     ctx->store_version++;
     ctx->multi_valued.clear();
     ctx->single_valued.clear();
+    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
     return KB_OK;
 }
 
@@ -1216,6 +1386,7 @@ kb_status kb_store_clear(kb_ctx* ctx) {
     ctx->store_version++;
     ctx->multi_valued.clear();
     ctx->single_valued.clear();
+    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
     return KB_OK;
 }
 kb_status kb_store_load(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n) {
@@ -1247,8 +1418,110 @@ kb_status kb_store_evict(kb_ctx* ctx, uint64_t tag) {
     ctx->store_version++;
     ctx->multi_valued.clear();
     ctx->single_valued.clear();
+    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
     return found ? KB_OK : kb::fail(ctx, KB_E_NOT_FOUND, "no segment with tag %llu", (unsigned long long)tag);
 }
+kb_status kb_set_use_index(kb_ctx* ctx, int enabled) {
+    if (!ctx) return KB_E_INVALID;
+    ctx->use_index = enabled != 0;
+    return KB_OK;
+}
+
+kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* build_ms) {
+    KB_ENTER(ctx);
+    if (n_predicates) *n_predicates = 0;
+    if (build_ms) *build_ms = 0.0;
+    ctx->index.clear();
+    ctx->index_version = ~0ull;
+    if (ctx->n_triples == 0) return KB_OK;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->st);
+    // 1. distinct predicates
+    const u32 set_slots = 8192;
+    kb::Buf set;
+    KB_TRY(kb::alloc_buf(ctx, set_slots * sizeof(u32), &set));
+    KB_CUDA(ctx, cudaMemsetAsync(set->p, 0xFF, set_slots * sizeof(u32), ctx->st));
+    const u32 off = kb::ctrl_alloc(ctx, 4);
+    kb::timer_begin(ctx, kb::F_OTHER, (int)ctx->segs.size());
+    for (auto& sg : ctx->segs) kb::launch_distinct(sg.p.ptr, (u32)sg.n, static_cast<u32*>(set->p), set_slots, ctx->ctrl + off, ctx->n_sms, ctx->st);
+    kb::timer_end(ctx);
+    std::vector<u32> hset(set_slots);
+    KB_CUDA(ctx, cudaMemcpyAsync(hset.data(), set->p, set_slots * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+    KB_TRY(kb::ctrl_read(ctx));
+    std::vector<u32> preds;
+    for (u32 v : hset) if (v != kb::EMPTY32) preds.push_back(v);
+    std::sort(preds.begin(), preds.end());
+    if (ctx->h_ctrl[off] || preds.size() > 4096) { cudaEventDestroy(e0); cudaEventDestroy(e1); return KB_OK; }  // too many predicates: keep scanning
+    // 2. one fused scan per 8 predicates, pair output, then shrink each slice to its size and take its id ranges
+    for (size_t b = 0; b < preds.size(); b += kb::MAXP) {
+        const u32 k = (u32)std::min<size_t>(kb::MAXP, preds.size() - b);
+        kb_pattern pats[kb::MAXP];
+        for (u32 i = 0; i < k; i++) { pats[i].s = kb_term{1, 0}; pats[i].p = kb_term{0, preds[b + i]}; pats[i].o = kb_term{1, 1}; }
+        std::vector<std::unique_ptr<kb_rel>> rels;
+        std::vector<kb::FilterProg> none;
+        KB_TRY(kb::scan_impl(ctx, pats, k, none, false, true, &rels));
+        const u32 soff = kb::ctrl_alloc(ctx, 4 * kb::MAXP);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff, 0, 4 * kb::MAXP * sizeof(u32), ctx->st));
+        for (u32 i = 0; i < k; i++) KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff + 4 * i, 0xFF, 2 * sizeof(u32), ctx->st));
+        for (u32 i = 0; i < k; i++) {
+            kb::PredSlice ps;
+            ps.n = rels[i]->n;
+            KB_TRY(kb::alloc_col(ctx, 2 * ps.n, &ps.pairs));
+            if (ps.n) KB_CUDA(ctx, cudaMemcpyAsync(ps.pairs.ptr, rels[i]->cols[0].ptr, ps.n * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->st));
+            kb::launch_pair_minmax(reinterpret_cast<const uint2*>(ps.pairs.ptr), (u32)ps.n, ctx->ctrl + soff + 4 * i, ctx->n_sms, ctx->st);
+            ctx->stats.kernel_launches++;
+            ctx->index[preds[b + i]] = ps;
+        }
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(kb::ctrl_read(ctx));
+        for (u32 i = 0; i < k; i++) {
+            kb::PredSlice& ps = ctx->index[preds[b + i]];
+            ps.xmin = ctx->h_ctrl[soff + 4 * i]; ps.ymin = ctx->h_ctrl[soff + 4 * i + 1];
+            ps.xmax = ctx->h_ctrl[soff + 4 * i + 2]; ps.ymax = ctx->h_ctrl[soff + 4 * i + 3];
+        }
+        // 3. key uniqueness per slice and position (one trial direct build each): joins keyed on a unique column skip duplicate detection
+        const u32 uoff = kb::ctrl_alloc(ctx, 2 * kb::MAXP);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + uoff, 0, 2 * kb::MAXP * sizeof(u32), ctx->st));
+        std::vector<int> tried(2 * k, 0);
+        for (u32 i = 0; i < k; i++) {
+            kb::PredSlice& ps = ctx->index[preds[b + i]];
+            if (ps.n == 0) continue;
+            for (u32 y = 0; y < 2; y++) {
+                const u32 lo = y ? ps.ymin : ps.xmin, hi = y ? ps.ymax : ps.xmax;
+                const u64 range = (u64)hi - lo + 1;
+                if (range > std::max<u64>(8 * ps.n, 1ull << 16) || range > (1ull << 28)) continue;
+                kb::Buf tab;
+                KB_TRY(kb::alloc_buf(ctx, range * sizeof(u32), &tab));
+                KB_CUDA(ctx, cudaMemsetAsync(tab->p, 0xFF, range * sizeof(u32), ctx->st));
+                kb::launch_build_direct_pairs(reinterpret_cast<const uint2*>(ps.pairs.ptr), y, (u32)ps.n, static_cast<u32*>(tab->p), lo, (u32)range, 0u,
+                                              ctx->ctrl + uoff + 2 * i + y, 0u, ctx->n_sms, ctx->st);
+                ctx->stats.kernel_launches++;
+                tried[2 * i + y] = 1;
+            }
+        }
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(kb::ctrl_read(ctx));
+        for (u32 i = 0; i < k; i++) {
+            kb::PredSlice& ps = ctx->index[preds[b + i]];
+            ps.x_unique = tried[2 * i] && ctx->h_ctrl[uoff + 2 * i] == 0;
+            ps.y_unique = tried[2 * i + 1] && ctx->h_ctrl[uoff + 2 * i + 1] == 0;
+        }
+    }
+    for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world)) KB_TRY(kb::segment_stats(ctx, &sg));
+    cudaEventRecord(e1, ctx->st);
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->index_version = ctx->store_version;
+    if (n_predicates) *n_predicates = (uint32_t)preds.size();
+    if (build_ms) *build_ms = ms;
+    return KB_OK;
+}
+
 kb_status kb_store_size(kb_ctx* ctx, uint64_t* n, uint32_t* n_seg) {
     if (!ctx) return KB_E_INVALID;
     if (n) *n = ctx->n_triples;
@@ -1318,6 +1591,7 @@ kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, con
     ctx->store_version++;
     ctx->multi_valued.clear();
     ctx->single_valued.clear();
+    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
     return KB_OK;
 }
 
@@ -1736,6 +2010,7 @@ kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, c
     ctx->store_version++;
     ctx->multi_valued.clear();
     ctx->single_valued.clear();
+    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
     ctx->upload_stats_off = (int)soff;
     // scan_impl makes st wait on each segment's `ready` event right before that segment's scan kernel: copy i+1 overlaps scan i
     std::unique_ptr<kb_rel> r;

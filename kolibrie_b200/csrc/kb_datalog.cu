@@ -388,6 +388,8 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
         ctx->n_triples += st.inferred;
         ctx->store_version++;
         ctx->multi_valued.clear();
+        ctx->single_valued.clear();
+        ctx->index.clear();
     }
     cudaEventRecord(ev1, ctx->st);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));

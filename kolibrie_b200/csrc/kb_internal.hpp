@@ -73,6 +73,16 @@ struct Segment {
 };
 }  // namespace kb
 
+namespace kb {
+struct PredSlice {  // one predicate's (subject, object) rows of the store, interleaved — the device analogue of pos[P] (index_manager.rs:18-26)
+    Col pairs;
+    u64 n = 0;
+    u32 xmin = 0xFFFFFFFFu, xmax = 0, ymin = 0xFFFFFFFFu, ymax = 0;  // id range of subjects (x) and objects (y)
+    bool x_unique = false, y_unique = false;  // verified at index build: no subject (object) occurs twice -> builds keyed on it need no
+                                              // duplicate detection (functional / inverse-functional predicate in this store)
+};
+}  // namespace kb
+
 struct kb_ctx {
     int device = 0;
     int n_sms = 148;
@@ -111,6 +121,9 @@ struct kb_ctx {
     cudaStream_t st2 = nullptr;                            // second compute stream: independent direct builds run concurrently
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     kb::u64 store_version = 0;
+    std::map<kb::u32, kb::PredSlice> index;  // kb_store_build_index: predicate -> slice; valid while index_version == store_version
+    kb::u64 index_version = ~0ull;
+    bool use_index = true;               // KOLIBRIE_USE_INDEX=0 / kb_set_use_index: force the scanning path
     kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject
     int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges
 };

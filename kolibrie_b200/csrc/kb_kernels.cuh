@@ -141,6 +141,24 @@ struct ProbeFParams {
 };
 void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st);
 void launch_unpair(const uint2* kv, u32 n, u32* x, u32* y, cudaStream_t st);
+// direct build from a predicate slice of the store index, with the pattern's pushed-down FILTER evaluated on (s, P, o)
+struct BuildPairsParams {
+    const uint2* kv;
+    u32 n, key_is_y, pred;
+    u32* table;
+    u32 kmin, range, cshift;
+    u32* dup_flag;
+    u32 trusted;
+    FilterOp ops[KB_MAX_FILTER_OPS];  // slots = positions 0/1/2
+    u32 n_ops;
+    NumTab nt;
+    u32* count;  // rows inserted (after the filter)
+};
+void launch_build_direct_pairs_filtered(const BuildPairsParams& p, int n_sms, cudaStream_t st);
+// distinct values of a column into a small open-addressing set (EMPTY32 = free); *overflow set when it fills up
+void launch_distinct(const u32* col, u32 n, u32* set, u32 set_slots, u32* overflow, int n_sms, cudaStream_t st);
+// min/max of both halves of a pair relation: out[0..3] = min x, min y, max x, max y
+void launch_pair_minmax(const uint2* kv, u32 n, u32* out4, int n_sms, cudaStream_t st);
 // number of occupied (non-EMPTY32) slots of a direct table: equals the number of inserted rows iff the keys were single-valued
 void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, cudaStream_t st);
 // number of keys that do NOT belong to shard `rank` of `world` (kb_shard_of): 0 for a correctly sharded column

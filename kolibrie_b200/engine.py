@@ -291,8 +291,10 @@ class SparqlDatabase:
         return False
 
     def build_all_indexes(self):
-        """The reference builds its six hash indexes here (sparql_database.rs:3364-3394); the device store is (re)uploaded instead."""
+        """The reference builds its six hash indexes here (sparql_database.rs:3364-3394); the device store is (re)uploaded and
+        partitioned by predicate (kb_store_build_index)."""
         self._sync()
+        self.ctx.build_index()
 
     def _sync(self):
         if self._uploaded_version == self._version:

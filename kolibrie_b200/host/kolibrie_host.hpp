@@ -325,7 +325,8 @@ class SparqlDatabase {
     void add_triple_parts(const std::string& s, const std::string& p, const std::string& o) { add_triple(Triple{dictionary.encode(s), dictionary.encode(p), dictionary.encode(o)}); }
     void add_triple(const Triple& t) { if (triples.insert(t).second) version_++; }        // sparql_database.rs:215-226
     bool delete_triple(const Triple& t) { if (triples.erase(t)) { version_++; return true; } return false; }  // :229-242
-    void build_all_indexes() { sync(); }  // the reference builds six hash indexes here (:3364-3394); we (re)upload the store
+    // the reference builds six hash indexes here (:3364-3394); we (re)upload the store and partition it by predicate on the device
+    void build_all_indexes() { sync(); dev_->check(kb_store_build_index(dev_->get(), nullptr, nullptr)); }
     void sync() {
         if (uploaded_ == version_) return;
         std::vector<uint32_t> s, p, o;

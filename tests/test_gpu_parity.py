@@ -312,3 +312,48 @@ def test_sharded_store_key_compaction(claimed_rank):
         assert ctx2.get_stats()["fused_scan_builds"] >= 2
     finally:
         ctx2.close()
+
+
+@pytest.mark.parametrize("q", ["cfg1", "cfg2", "cfg3", "star3"])
+def test_index_path_vs_oracle(ctx, emp, q):
+    """kb_store_build_index (= build_all_indexes): star joins read predicate slices instead of scanning the store; same bag"""
+    d, db = emp
+    n_pred, ms = ctx.build_index()
+    assert n_pred == 6
+    before = ctx.get_stats()["index_joins"]
+    js, pats, filt = datagen.employee_queries(d)[q]
+    got = ctx.star_join(js, pats, filt)
+    assert ctx.get_stats()["index_joins"] == before + 1, "the index path must have been taken"
+    want = db.bgp(pats, filt)
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), q)
+    # a filter on the PROBE-side pattern and one spanning two patterns
+    js, pats, _ = datagen.employee_queries(d)["cfg2"]
+    f2 = [c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_GT, value=60000.0), c.fop(c.F_EQ_ID, slot=1, id=d.ids["Manager"]), c.fop(c.F_AND),
+          c.fop(c.F_NE_ID, slot=3, id=int(d.s[0])), c.fop(c.F_AND)]
+    got = ctx.star_join(js, pats, f2)
+    want = db.bgp(pats, f2)
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), "compound filter")
+    # any mutation drops the index: the next query scans again and still agrees
+    ctx.store_append(d.s[:6], d.p[:6], d.o[:6], tag=77)
+    assert ctx.get_stats()["index_joins"] == ctx.get_stats()["index_joins"]
+    n0 = ctx.get_stats()["index_joins"]
+    ctx.star_join(js, pats, filt if q != "cfg1" else None)
+    assert ctx.get_stats()["index_joins"] == n0, "stale index must not be used"
+
+
+def test_index_path_multivalued_and_missing_predicate(ctx):
+    rng = np.random.default_rng(5)
+    n = 5000
+    tr = np.unique(np.stack([rng.integers(0, 700, n), rng.integers(100, 103, n), rng.integers(1000, 1040, n)], axis=1).astype(np.uint32), axis=0)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    assert ctx.build_index()[0] == 3
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2])
+    pats = [c.pattern(c.V(0), c.K(100), c.V(1)), c.pattern(c.V(0), c.K(101), c.V(2)), c.pattern(c.V(0), c.K(102), c.V(3))]
+    want = db.bgp(pats).to_numpy([0, 1, 2, 3])
+    for _ in range(2):
+        H.assert_same_bag(ctx.star_join(0, pats).to_numpy([0, 1, 2, 3]), want, "1:N star with index")
+    none = ctx.star_join(0, [c.pattern(c.V(0), c.K(100), c.V(1)), c.pattern(c.V(0), c.K(999), c.V(2))])
+    assert none.n_rows == 0 and sorted(none.slots) == [0, 1, 2]
+    # object-keyed star: ?a P1 ?x . ?b P2 ?x joined on the object
+    pats_o = [c.pattern(c.V(1), c.K(100), c.V(0)), c.pattern(c.V(2), c.K(101), c.V(0))]
+    H.assert_same_bag(ctx.star_join(0, pats_o).to_numpy([0, 1, 2]), db.bgp(pats_o).to_numpy([0, 1, 2]), "object star")
