@@ -703,13 +703,27 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             kmn = compact_key(kmn, cshift);
             kmx = compact_key(kmx, cshift);
         }
-        // probe side: the largest slice among the patterns without a pushed-down filter (a filtered side is the smaller build side)
+        // a pattern whose key column has a persistent table in the index needs no build at all: it is looked up like spo[s][P]
+        auto persistent = [&](u32 k) -> bool {
+            if (!ok) return false;
+            const bool y = key_pos(k) == 2;
+            return y ? (bool)sl[k]->ytab : ((bool)sl[k]->xtab && sl[k]->tab_cshift == cshift);
+        };
+        // probe side: prefer a pattern WITHOUT a persistent table (it would need a build), then the smallest slice (fewest lookups);
+        // when builds remain, the classic choice: the largest unfiltered slice probes, filtered sides build
         int probe_k = -1;
-        for (u32 k = 0; k < K && ok; k++) if (pushdown[k].ops.empty() && (probe_k < 0 || sl[k]->n > sl[probe_k]->n)) probe_k = (int)k;
-        if (ok && probe_k < 0) { probe_k = 0; for (u32 k = 1; k < K; k++) if (sl[k]->n > sl[probe_k]->n) probe_k = (int)k; }
+        bool all_persistent = ok;
+        for (u32 k = 0; k < K && ok; k++) if (!persistent(k)) all_persistent = false;
+        if (ok && all_persistent) {
+            probe_k = 0;
+            for (u32 k = 1; k < K; k++) if (sl[k]->n < sl[probe_k]->n) probe_k = (int)k;
+        } else {
+            for (u32 k = 0; k < K && ok; k++) if (pushdown[k].ops.empty() && (probe_k < 0 || sl[k]->n > sl[probe_k]->n)) probe_k = (int)k;
+            if (ok && probe_k < 0) { probe_k = 0; for (u32 k = 1; k < K; k++) if (sl[k]->n > sl[probe_k]->n) probe_k = (int)k; }
+        }
         const u64 rng = (ok && kmx >= kmn) ? (u64)kmx - kmn + 1 : 0;
         for (u32 k = 0; k < K && ok; k++) {
-            if ((int)k == probe_k) continue;
+            if ((int)k == probe_k || persistent(k)) continue;
             if (rng == 0 || rng > std::max<u64>(8 * sl[k]->n, 1ull << 16) || rng > (1ull << 31)) ok = false;
             if (ctx->multi_valued.count({pats[k].p.value, key_pos(k)})) ok = false;
         }
@@ -723,60 +737,75 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             std::vector<u32> out_slots = pv[probe_k];
             std::vector<OutCol> ocs{OutCol{OUT_PROBE, 0, 0}, OutCol{OUT_PROBE, 1, 0}};
             const u32 T = K - 1;
-            timer_begin(ctx, F_BUILD, (int)T);
-            for (u32 t = 0; t < T; t++) { Buf b; KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &b)); tabs.push_back(b); }
-            if (T > 1) {
+            FilterProg postp = post;  // filters of patterns that are not built (probe side, persistent tables) run on the joined row
+            auto to_post = [&](u32 k) {
+                if (pushdown[k].ops.empty()) return;
+                const bool had = !postp.ops.empty();
+                postp.ops.insert(postp.ops.end(), pushdown[k].ops.begin(), pushdown[k].ops.end());
+                if (had) { kb_filter_op a{}; a.op = KB_F_AND; postp.ops.push_back(a); }
+            };
+            to_post((u32)probe_k);
+            u32 n_build = 0;
+            for (u32 k = 0; k < K; k++) if ((int)k != probe_k && !persistent(k)) n_build++;
+            if (n_build) timer_begin(ctx, F_BUILD, (int)n_build);
+            for (u32 k = 0; k < K; k++) if ((int)k != probe_k && !persistent(k)) { Buf b; KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &b)); tabs.push_back(b); }
+            if (n_build > 1) {
                 KB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->st));
                 KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
             }
-            u32 t = 0;
+            u32 t = 0, bi = 0;
             for (u32 k = 0; k < K; k++) {
                 if ((int)k == probe_k) continue;
-                cudaStream_t bs = (T > 1 && (t & 1)) ? ctx->st2 : ctx->st;
-                u32* tab = static_cast<u32*>(tabs[t]->p);
-                KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), bs));
-                BuildPairsParams B{};
-                B.kv = reinterpret_cast<const uint2*>(sl[k]->pairs.ptr);
-                B.n = (u32)sl[k]->n;
-                B.key_is_y = key_pos(k) == 2 ? 1u : 0u;
-                B.pred = pats[k].p.value;
-                B.table = tab; B.kmin = kmn; B.range = range; B.cshift = cshift;
-                B.dup_flag = ctx->ctrl + off + 16 + t;
-                B.count = ctx->ctrl + off + 16 + MAXT + t;
-                B.trusted = ((key_pos(k) == 2 ? sl[k]->y_unique : sl[k]->x_unique) || ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;
-                B.nt = numtab(ctx);
-                if (!pushdown[k].ops.empty()) {
-                    std::map<u32, u32> remap;
-                    for (size_t i = 0; i < pv[k].size(); i++) remap[pv[k][i]] = psrc[k][i];
-                    std::vector<FilterOp> fo;
-                    if (!append_prog(&fo, pushdown[k], remap)) return fail(ctx, KB_E_INVALID, "pushed-down filter uses a variable the pattern does not bind");
-                    B.n_ops = (u32)fo.size();
-                    for (size_t i = 0; i < fo.size(); i++) B.ops[i] = fo[i];
-                }
-                launch_build_direct_pairs_filtered(B, ctx->n_sms, bs);
                 DirectTab& D = dt[t];
-                D.tab = tab; D.kmin = kmn; D.range = range; D.cshift = cshift; D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                if (persistent(k)) {
+                    const bool y = key_pos(k) == 2;
+                    D.tab = static_cast<const u32*>(y ? sl[k]->ytab->p : sl[k]->xtab->p);
+                    D.kmin = y ? sl[k]->ytab_min : sl[k]->xtab_min;
+                    D.range = y ? sl[k]->ytab_range : sl[k]->xtab_range;
+                    D.cshift = y ? 0u : sl[k]->tab_cshift;
+                    to_post(k);
+                } else {
+                    cudaStream_t bs = (n_build > 1 && (bi & 1)) ? ctx->st2 : ctx->st;
+                    u32* tab = static_cast<u32*>(tabs[bi]->p);
+                    KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), bs));
+                    BuildPairsParams B{};
+                    B.kv = reinterpret_cast<const uint2*>(sl[k]->pairs.ptr);
+                    B.n = (u32)sl[k]->n;
+                    B.key_is_y = key_pos(k) == 2 ? 1u : 0u;
+                    B.pred = pats[k].p.value;
+                    B.table = tab; B.kmin = kmn; B.range = range; B.cshift = cshift;
+                    B.dup_flag = ctx->ctrl + off + 16 + t;
+                    B.count = ctx->ctrl + off + 16 + MAXT + t;
+                    B.trusted = ((key_pos(k) == 2 ? sl[k]->y_unique : sl[k]->x_unique) || ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;
+                    B.nt = numtab(ctx);
+                    if (!pushdown[k].ops.empty()) {
+                        std::map<u32, u32> remap;
+                        for (size_t i = 0; i < pv[k].size(); i++) remap[pv[k][i]] = psrc[k][i];
+                        std::vector<FilterOp> fo;
+                        if (!append_prog(&fo, pushdown[k], remap)) return fail(ctx, KB_E_INVALID, "pushed-down filter uses a variable the pattern does not bind");
+                        B.n_ops = (u32)fo.size();
+                        for (size_t i = 0; i < fo.size(); i++) B.ops[i] = fo[i];
+                    }
+                    launch_build_direct_pairs_filtered(B, ctx->n_sms, bs);
+                    D.tab = tab; D.kmin = kmn; D.range = range; D.cshift = cshift;
+                    ctx->stats.rows_built += sl[k]->n;
+                    bi++;
+                }
                 out_slots.push_back(pv[k][key_pos(k) == 0 ? 1 : 0]);
                 ocs.push_back(OutCol{OUT_TABVAL, t, 0});
                 tab_k.push_back(k);
-                ctx->stats.rows_built += sl[k]->n;
                 t++;
             }
-            if (T > 1) {
+            if (n_build > 1) {
                 KB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->st2));
                 KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
             }
-            timer_end(ctx);
+            if (n_build) timer_end(ctx);
             const PredSlice& PS = *sl[probe_k];
             auto res = std::make_unique<kb_rel>();
             res->slots = out_slots;
             const u32 n_out = (u32)out_slots.size();
-            FilterProg postp = post;  // a filter pushed to the probe pattern is evaluated on the joined row instead
-            if (!pushdown[probe_k].ops.empty()) {
-                const bool had = !postp.ops.empty();
-                postp.ops.insert(postp.ops.end(), pushdown[probe_k].ops.begin(), pushdown[probe_k].ops.end());
-                if (had) { kb_filter_op a{}; a.op = KB_F_AND; postp.ops.push_back(a); }
-            }
             std::vector<FilterOp> fops;
             if (!postp.ops.empty()) {
                 std::map<u32, u32> remap;
@@ -826,7 +855,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             }
             if (dup) return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, true, out);  // multi-valued is now cached: takes the chained route
             for (u32 q = 0; q < T; q++)
-                if (pushdown[tab_k[q]].ops.empty()) ctx->single_valued.insert({pats[tab_k[q]].p.value, key_pos(tab_k[q])});
+                if (!persistent(tab_k[q]) && pushdown[tab_k[q]].ops.empty()) ctx->single_valued.insert({pats[tab_k[q]].p.value, key_pos(tab_k[q])});
             res->n = ctx->h_ctrl[off + 1];
             *out = select_cols(*res, all_slots);
             return KB_OK;
@@ -1485,20 +1514,31 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
         const u32 uoff = kb::ctrl_alloc(ctx, 2 * kb::MAXP);
         KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + uoff, 0, 2 * kb::MAXP * sizeof(u32), ctx->st));
         std::vector<int> tried(2 * k, 0);
+        u32 cshift = 0;  // subject-sharded store: compact the subject keys (see compact_key)
+        {
+            bool sharded = ctx->shard_world > 1 && (ctx->shard_world & (ctx->shard_world - 1)) == 0;
+            for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world)) KB_TRY(kb::segment_stats(ctx, &sg));
+            for (auto& sg : ctx->segs) if (sg.n && !sg.sharded_ok) sharded = false;
+            if (sharded) while ((1u << cshift) < ctx->shard_world) cshift++;
+        }
         for (u32 i = 0; i < k; i++) {
             kb::PredSlice& ps = ctx->index[preds[b + i]];
             if (ps.n == 0) continue;
+            ps.tab_cshift = cshift;
             for (u32 y = 0; y < 2; y++) {
-                const u32 lo = y ? ps.ymin : ps.xmin, hi = y ? ps.ymax : ps.xmax;
+                const u32 cs = y ? 0u : cshift;  // only subjects are sharded
+                const u32 lo = kb::compact_key(y ? ps.ymin : ps.xmin, cs), hi = kb::compact_key(y ? ps.ymax : ps.xmax, cs);
                 const u64 range = (u64)hi - lo + 1;
                 if (range > std::max<u64>(8 * ps.n, 1ull << 16) || range > (1ull << 28)) continue;
                 kb::Buf tab;
                 KB_TRY(kb::alloc_buf(ctx, range * sizeof(u32), &tab));
                 KB_CUDA(ctx, cudaMemsetAsync(tab->p, 0xFF, range * sizeof(u32), ctx->st));
-                kb::launch_build_direct_pairs(reinterpret_cast<const uint2*>(ps.pairs.ptr), y, (u32)ps.n, static_cast<u32*>(tab->p), lo, (u32)range, 0u,
+                kb::launch_build_direct_pairs(reinterpret_cast<const uint2*>(ps.pairs.ptr), y, (u32)ps.n, static_cast<u32*>(tab->p), lo, (u32)range, cs,
                                               ctx->ctrl + uoff + 2 * i + y, 0u, ctx->n_sms, ctx->st);
                 ctx->stats.kernel_launches++;
                 tried[2 * i + y] = 1;
+                if (y) { ps.ytab = tab; ps.ytab_min = lo; ps.ytab_range = (u32)range; }
+                else { ps.xtab = tab; ps.xtab_min = lo; ps.xtab_range = (u32)range; }
             }
         }
         KB_CUDA(ctx, cudaGetLastError());
@@ -1507,6 +1547,8 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
             kb::PredSlice& ps = ctx->index[preds[b + i]];
             ps.x_unique = tried[2 * i] && ctx->h_ctrl[uoff + 2 * i] == 0;
             ps.y_unique = tried[2 * i + 1] && ctx->h_ctrl[uoff + 2 * i + 1] == 0;
+            if (!ps.x_unique || ps.xtab_range > 4 * ps.n + 65536) ps.xtab.reset();  // keep only tables of unique, dense columns
+            if (!ps.y_unique || ps.ytab_range > 4 * ps.n + 65536) ps.ytab.reset();
         }
     }
     for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world)) KB_TRY(kb::segment_stats(ctx, &sg));

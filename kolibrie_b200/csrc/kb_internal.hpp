@@ -78,6 +78,10 @@ struct PredSlice {  // one predicate's (subject, object) rows of the store, inte
     Col pairs;
     u64 n = 0;
     u32 xmin = 0xFFFFFFFFu, xmax = 0, ymin = 0xFFFFFFFFu, ymax = 0;  // id range of subjects (x) and objects (y)
+    // persistent direct tables built with the index when the column is unique and dense: xtab[subject - xtab_min] = object (what
+    // the reference's spo[s][P] lookup answers, index_manager.rs:18-26) and ytab[object - ytab_min] = subject (pos[P][o])
+    Buf xtab, ytab;
+    u32 xtab_min = 0, xtab_range = 0, ytab_min = 0, ytab_range = 0, tab_cshift = 0;
     bool x_unique = false, y_unique = false;  // verified at index build: no subject (object) occurs twice -> builds keyed on it need no
                                               // duplicate detection (functional / inverse-functional predicate in this store)
 };
