@@ -715,8 +715,11 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
         bool all_persistent = ok;
         for (u32 k = 0; k < K && ok; k++) if (!persistent(k)) all_persistent = false;
         if (ok && all_persistent) {
-            probe_k = 0;
-            for (u32 k = 1; k < K; k++) if (sl[k]->n < sl[probe_k]->n) probe_k = (int)k;
+            // no builds at all: the probe side should be the most selective stream — a pattern that carries its own FILTER (evaluated
+            // on the probe row before any lookup), else the smallest slice
+            probe_k = -1;
+            for (u32 k = 0; k < K; k++) if (!pushdown[k].ops.empty() && pushdown[k].ops.size() <= 8 && (probe_k < 0 || sl[k]->n < sl[probe_k]->n)) probe_k = (int)k;
+            if (probe_k < 0) { probe_k = 0; for (u32 k = 1; k < K; k++) if (sl[k]->n < sl[probe_k]->n) probe_k = (int)k; }
         } else {
             for (u32 k = 0; k < K && ok; k++) if (pushdown[k].ops.empty() && (probe_k < 0 || sl[k]->n > sl[probe_k]->n)) probe_k = (int)k;
             if (ok && probe_k < 0) { probe_k = 0; for (u32 k = 1; k < K; k++) if (sl[k]->n > sl[probe_k]->n) probe_k = (int)k; }
@@ -744,7 +747,8 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 postp.ops.insert(postp.ops.end(), pushdown[k].ops.begin(), pushdown[k].ops.end());
                 if (had) { kb_filter_op a{}; a.op = KB_F_AND; postp.ops.push_back(a); }
             };
-            to_post((u32)probe_k);
+            const bool pre_filter = !pushdown[probe_k].ops.empty() && pushdown[probe_k].ops.size() <= 8;
+            if (!pre_filter) to_post((u32)probe_k);
             u32 n_build = 0;
             for (u32 k = 0; k < K; k++) if ((int)k != probe_k && !persistent(k)) n_build++;
             if (n_build) timer_begin(ctx, F_BUILD, (int)n_build);
@@ -814,6 +818,15 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 if (fops.size() > KB_MAX_FILTER_OPS) return fail(ctx, KB_E_LIMIT, "filter too long");
             }
             ProbeFParams P{};
+            if (pre_filter) {  // slots of the probe pattern's own filter -> pair halves (x = subject, y = object)
+                std::map<u32, u32> remap;
+                for (size_t i = 0; i < pv[probe_k].size(); i++) remap[pv[probe_k][i]] = psrc[probe_k][i] == 0 ? 0u : 1u;
+                std::vector<FilterOp> fo;
+                if (!append_prog(&fo, pushdown[probe_k], remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
+                P.n_pre = (u32)fo.size();
+                for (size_t i = 0; i < fo.size(); i++) P.pre_ops[i] = fo[i];
+                if (sl[probe_k]->ynum && sl[probe_k]->ynum_version == ctx->num_version) P.pre_num = static_cast<const double*>(sl[probe_k]->ynum->p);
+            }
             P.pairs = reinterpret_cast<const uint2*>(PS.pairs.ptr);
             P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
             P.n = (u32)PS.n;
@@ -1543,8 +1556,24 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
         }
         KB_CUDA(ctx, cudaGetLastError());
         KB_TRY(kb::ctrl_read(ctx));
+        // 4. typed literal column: the f64 value of every object, for slices that have numeric objects at all (FILTER(?o <cmp> c) then
+        //    reads it sequentially instead of gathering num_or0[object] at random)
+        std::vector<kb::Buf> ynum(k);
+        const u32 noff = kb::ctrl_alloc(ctx, kb::MAXP);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + noff, 0, kb::MAXP * sizeof(u32), ctx->st));
+        if (ctx->n_ids) for (u32 i = 0; i < k; i++) {
+            kb::PredSlice& ps = ctx->index[preds[b + i]];
+            if (ps.n == 0) continue;
+            KB_TRY(kb::alloc_buf(ctx, ps.n * sizeof(double), &ynum[i]));
+            kb::launch_pair_numcol(reinterpret_cast<const uint2*>(ps.pairs.ptr), (u32)ps.n, kb::numtab(ctx), static_cast<double*>(ynum[i]->p), ctx->ctrl + noff + i,
+                                   ctx->n_sms, ctx->st);
+            ctx->stats.kernel_launches++;
+        }
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(kb::ctrl_read(ctx));
         for (u32 i = 0; i < k; i++) {
             kb::PredSlice& ps = ctx->index[preds[b + i]];
+            if (ynum[i] && ctx->h_ctrl[noff + i] > 0) { ps.ynum = ynum[i]; ps.ynum_version = ctx->num_version; }
             ps.x_unique = tried[2 * i] && ctx->h_ctrl[uoff + 2 * i] == 0;
             ps.y_unique = tried[2 * i + 1] && ctx->h_ctrl[uoff + 2 * i + 1] == 0;
             if (!ps.x_unique || ps.xtab_range > 4 * ps.n + 65536) ps.xtab.reset();  // keep only tables of unique, dense columns
@@ -1658,6 +1687,7 @@ kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t
     ctx->num.reset();
     ctx->isnum.reset();
     ctx->n_ids = 0;
+    ctx->num_version++;
     if (n_ids == 0) return KB_OK;
     if (!num_or0 || !is_num) return kb::fail(ctx, KB_E_INVALID, "NULL numeric table");
     KB_TRY(kb::alloc_buf(ctx, (size_t)n_ids * sizeof(double), &ctx->num));
@@ -1666,6 +1696,7 @@ kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t
     KB_CUDA(ctx, cudaMemcpyAsync(ctx->isnum->p, is_num, (size_t)n_ids, cudaMemcpyHostToDevice, ctx->st));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     ctx->n_ids = n_ids;
+    ctx->num_version++;
     return KB_OK;
 }
 

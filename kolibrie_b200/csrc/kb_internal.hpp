@@ -82,6 +82,9 @@ struct PredSlice {  // one predicate's (subject, object) rows of the store, inte
     // the reference's spo[s][P] lookup answers, index_manager.rs:18-26) and ytab[object - ytab_min] = subject (pos[P][o])
     Buf xtab, ytab;
     u32 xtab_min = 0, xtab_range = 0, ytab_min = 0, ytab_range = 0, tab_cshift = 0;
+    Buf ynum;  // typed literal column: f64 value of every object (num_or0), kept when the slice has numeric objects; valid for the
+               // numeric side table version it was built from (ynum_version)
+    u64 ynum_version = 0;
     bool x_unique = false, y_unique = false;  // verified at index build: no subject (object) occurs twice -> builds keyed on it need no
                                               // duplicate detection (functional / inverse-functional predicate in this store)
 };
@@ -99,6 +102,7 @@ struct kb_ctx {
     kb::u64 n_triples = 0;
     kb::Buf num, isnum;
     kb::u32 n_ids = 0;
+    kb::u64 num_version = 1;  // bumped by kb_dict_numeric_load: typed literal columns of the index are tied to it
     // tile-state buffer of the look-back prefix (never cleared: words carry the launch epoch)
     kb::Buf tile_state, block_state;
     size_t tile_state_tiles = 0;

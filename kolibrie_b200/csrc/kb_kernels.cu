@@ -446,6 +446,21 @@ __global__ void __launch_bounds__(256) pair_minmax_kernel(const uint2* __restric
     mxx = __reduce_max_sync(0xffffffffu, mxx); mxy = __reduce_max_sync(0xffffffffu, mxy);
     if ((threadIdx.x & 31) == 0) { atomicMin(&out4[0], mnx); atomicMin(&out4[1], mny); atomicMax(&out4[2], mxx); atomicMax(&out4[3], mxy); }
 }
+__global__ void __launch_bounds__(256) pair_numcol_kernel(const uint2* __restrict__ kv, u32 n, NumTab nt, double* __restrict__ out, u32* n_numeric) {
+    u32 c = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const u32 id = kv[i].y;
+        out[i] = num_of(nt, id);
+        c += isnum_of(nt, id) ? 1u : 0u;
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_numeric, c);
+}
+void launch_pair_numcol(const uint2* kv, u32 n, NumTab nt, double* out, u32* n_numeric, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    pair_numcol_kernel<<<grid, 256, 0, st>>>(kv, n, nt, out, n_numeric);
+}
 void launch_pair_minmax(const uint2* kv, u32 n, u32* out4, int n_sms, cudaStream_t st) {
     if (n == 0) return;
     int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + 255ull) / 256ull);
@@ -512,7 +527,8 @@ void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_
 // =================================================================================================================
 // K_probe (direct, FAST)
 template <int T>
-__global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __grid_constant__ ProbeFParams P) {
+__global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) probe_fast_kernel(const __grid_constant__ ProbeFParams P) {
+    constexpr int R = PROBEF_ITEMS;  // rows per thread, consecutive
     extern __shared__ __align__(128) u32 smem[];  // PROBEF_TILE pairs
     const uint4* sm4 = reinterpret_cast<const uint4*>(smem);
     __shared__ __align__(8) u64 bar;
@@ -543,12 +559,18 @@ __global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __g
     __syncthreads();
     tile = s_next;
     u32 parity = 0;
+    const u32 full = (1u << R) - 1u;
     while (tile < P.n_tiles) {
         const u32 base = tile * (u32)PROBEF_TILE;
         const u32 cnt = min((u32)PROBEF_TILE, P.n - base);
         mbar_wait(&bar, parity);
         parity ^= 1u;
-        const uint4 r01 = sm4[2 * tid], r23 = sm4[2 * tid + 1];  // rows 4*tid .. 4*tid+3 as (x,y) pairs
+        u32 rx[R], ry[R];  // rows R*tid .. R*tid+R-1 as (x,y) pairs
+#pragma unroll
+        for (int q = 0; q < R / 2; q++) {
+            const uint4 v = sm4[(R / 2) * tid + q];
+            rx[2 * q] = v.x; ry[2 * q] = v.y; rx[2 * q + 1] = v.z; ry[2 * q + 1] = v.w;
+        }
         __syncthreads();
         if (tid == 0) {
             const u32 nt = atomicAdd(P.ticket, 1u);
@@ -561,13 +583,32 @@ __global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __g
                 tma_load_1d(smem, P.pairs + nb, bytes, &bar);
             }
         }
-        u32 rx[4] = {r01.x, r01.z, r23.x, r23.z};
-        u32 ry[4] = {r01.y, r01.w, r23.y, r23.w};
-        const u32 first = (u32)tid * 4u;
-        const u32 vmask = first >= cnt ? 0u : (cnt - first >= 4u ? 0xFu : ((1u << (cnt - first)) - 1u));
-        u32 tv[4][T > 0 ? T : 1];
+        const u32 first = (u32)tid * (u32)R;
+        u32 vmask = first >= cnt ? 0u : (cnt - first >= (u32)R ? full : ((1u << (cnt - first)) - 1u));
+        // FILTER conjuncts over the probe row alone. The common shape FILTER(?x <cmp> c) needs one numeric gather per row: it is issued
+        // together with the table lookups (independent loads, one memory round trip) and resolved afterwards — gating the lookups on
+        // it would put two dependent round trips on the critical path of a latency-bound kernel.
+        const bool pre_fast = P.n_pre == 1u && P.pre_ops[0].op == KB_F_CMP_NUM;
+        double pa[R];
+        if (pre_fast) {
+            const u32 slot = P.pre_ops[0].slot;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < R; j++) {
+                if (P.pre_num != nullptr && slot == 1u) pa[j] = ((vmask >> j) & 1u) ? __ldg(P.pre_num + base + first + (u32)j) : 0.0;
+                else pa[j] = ((vmask >> j) & 1u) ? num_of(P.nt, slot == 0u ? rx[j] : ry[j]) : 0.0;
+            }
+        } else if (P.n_pre != 0u && vmask != 0u) {
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                if ((vmask >> j) & 1u) {
+                    u32 vals[2] = {rx[j], ry[j]};
+                    if (!eval_filter(P.pre_ops, P.n_pre, vals, P.nt)) vmask &= ~(1u << j);
+                }
+            }
+        }
+        u32 tv[R][T > 0 ? T : 1];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
             const u32 key = P.key_is_y ? ry[j] : rx[j];
 #pragma unroll
             for (int t = 0; t < T; t++) {
@@ -575,9 +616,17 @@ __global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __g
                 tv[j][t] = (((vmask >> j) & 1u) && off < P.tab[t].range) ? __ldg(P.tab[t].tab + off) : EMPTY32;
             }
         }
+        if (pre_fast) {
+            const u32 cmp = P.pre_ops[0].cmp;
+            const double cv = P.pre_ops[0].value;
+            u32 pass = 0;
+#pragma unroll
+            for (int j = 0; j < R; j++) pass |= (cmp_num(cmp, pa[j], cv) ? 1u : 0u) << j;
+            vmask &= pass;
+        }
         u32 m = 0;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < R; j++) {
             bool hit = (vmask >> j) & 1u;
 #pragma unroll
             for (int t = 0; t < T; t++) hit = hit && (tv[j][t] != EMPTY32);
@@ -588,9 +637,9 @@ __global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __g
                 const OutCol oc = P.oc[P.ops[0].slot];
                 const u32 cmp = P.ops[0].cmp;
                 const double cv = P.ops[0].value;
-                double a[4];
+                double a[R];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < R; j++) {
                     u32 id = oc.kind == OUT_PROBE ? (oc.a == 0u ? rx[j] : ry[j]) : 0u;
 #pragma unroll
                     for (int t = 0; t < T; t++) if (oc.kind == OUT_TABVAL && oc.a == (u32)t) id = tv[j][t];
@@ -598,11 +647,11 @@ __global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __g
                 }
                 u32 pass = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) pass |= (cmp_num(cmp, a[j], cv) ? 1u : 0u) << j;
+                for (int j = 0; j < R; j++) pass |= (cmp_num(cmp, a[j], cv) ? 1u : 0u) << j;
                 m &= pass;
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < R; j++) {
                     if ((m >> j) & 1u) {
                         u32 vals[KB_MAX_COLS];
                         for (u32 c = 0; c < P.n_out; c++) {
@@ -648,7 +697,7 @@ __global__ void __launch_bounds__(PROBEF_THREADS, 4) probe_fast_kernel(const __g
                 u32* out = P.out[cidx] + pos;
                 u32 r = pos;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < R; j++) {
                     u32 x = oc.kind == OUT_PROBE ? (oc.a == 0u ? rx[j] : ry[j]) : 0u;
 #pragma unroll
                     for (int t = 0; t < T; t++) if (oc.kind == OUT_TABVAL && oc.a == (u32)t) x = tv[j][t];

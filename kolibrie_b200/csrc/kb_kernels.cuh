@@ -116,8 +116,11 @@ void launch_probe_direct(const ProbeDParams& p, int n_sms, cudaStream_t st);
 // K_probe (direct, FAST): the probe side is a pair relation; each thread owns 4 consecutive rows held in registers, so the shared
 // tile is refilled by TMA while the rows are probed (same register-staged double buffering as K_scan).
 constexpr int PROBEF_THREADS = 256;
-constexpr int PROBEF_ITEMS = 4;
-constexpr int PROBEF_TILE = PROBEF_THREADS * PROBEF_ITEMS;  // 1024 rows = 8 KB of pairs
+#ifndef KB_PROBEF_ITEMS
+#define KB_PROBEF_ITEMS 4
+#endif
+constexpr int PROBEF_ITEMS = KB_PROBEF_ITEMS;  // rows per thread: 8 keeps twice the lookups in flight per thread (the kernel is latency-bound)
+constexpr int PROBEF_TILE = PROBEF_THREADS * PROBEF_ITEMS;
 struct ProbeFParams {
     const uint2* pairs;
     u32 key_is_y;  // which half of the pair is the join key
@@ -129,6 +132,10 @@ struct ProbeFParams {
     u32 cap;
     FilterOp ops[KB_MAX_FILTER_OPS];
     u32 n_ops;
+    FilterOp pre_ops[8];  // conjuncts over the probe row alone (slot 0 = pair.x, 1 = pair.y): evaluated BEFORE any table lookup
+    u32 n_pre;
+    const double* pre_num;  // non-null: numeric value of pair.y per probe row (typed literal column of the index): a coalesced read
+                            // replaces the random gather num_or0[pair.y] when the pre-filter is FILTER(?y <cmp> c)
     NumTab nt;
     u64* tile_state;
     u64* block_state;
@@ -158,6 +165,8 @@ void launch_build_direct_pairs_filtered(const BuildPairsParams& p, int n_sms, cu
 // distinct values of a column into a small open-addressing set (EMPTY32 = free); *overflow set when it fills up
 void launch_distinct(const u32* col, u32 n, u32* set, u32 set_slots, u32* overflow, int n_sms, cudaStream_t st);
 // min/max of both halves of a pair relation: out[0..3] = min x, min y, max x, max y
+// typed literal column of a predicate slice: out[i] = num_or0[kv[i].y]; *n_numeric += rows whose object is numeric
+void launch_pair_numcol(const uint2* kv, u32 n, NumTab nt, double* out, u32* n_numeric, int n_sms, cudaStream_t st);
 void launch_pair_minmax(const uint2* kv, u32 n, u32* out4, int n_sms, cudaStream_t st);
 // number of occupied (non-EMPTY32) slots of a direct table: equals the number of inserted rows iff the keys were single-valued
 void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, cudaStream_t st);
