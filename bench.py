@@ -343,7 +343,8 @@ def main():
 
     def roof(fam, stx):
         dom = max(fam, key=lambda k: fam[k]["ms"])
-        return {"bound": "hbm", "kernel": kernel_names[dom], "achieved": fam[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": fam[dom]["frac"],
+        name = "kb::probe_index_kernel<T,PRE>" if (dom == "probe" and stx.get("index_joins", 0) and stx["build_launches"] == 0) else kernel_names[dom]
+        return {"bound": "hbm", "kernel": name, "achieved": fam[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": fam[dom]["frac"],
                 "traffic": traffic_from_profiles(dom.split("+")[0] + ("_index" if stx.get("index_joins", 0) else "")), "peak_source": peak_src,
                 "alg_bytes_per_launch": fam[dom]["alg_bytes"], "ms_per_launch": fam[dom]["ms"], "families": fam, "device_ms_per_step": stx["total_ms"] / K}
 

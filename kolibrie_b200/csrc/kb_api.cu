@@ -63,11 +63,15 @@ kb_status alloc_col(kb_ctx* ctx, u64 rows, Col* out) {
 kb_status begin_call(kb_ctx* ctx) {
     ctx->err.clear();
     ctx->ctrl_used = 0;
-    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl, 0, kb_ctx::CTRL_WORDS * sizeof(u32), ctx->st));
+    if (ctx->ctrl_dirty) {
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl, 0, kb_ctx::CTRL_WORDS * sizeof(u32), ctx->st));
+        ctx->ctrl_dirty = false;
+    }
     return KB_OK;
 }
 
 u32 ctrl_alloc(kb_ctx* ctx, u32 words) {
+    ctx->ctrl_dirty = true;
     u32 off = ctx->ctrl_used;
     ctx->ctrl_used += (words + 3u) & ~3u;
     if (ctx->ctrl_used > kb_ctx::CTRL_WORDS) {  // wrap: callers never keep more than a few hundred words live per call
@@ -730,6 +734,103 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             if (rng == 0 || rng > std::max<u64>(8 * sl[k]->n, 1ull << 16) || rng > (1ull << 31)) ok = false;
             if (ctx->multi_valued.count({pats[k].p.value, key_pos(k)})) ok = false;
         }
+        if (ok && all_persistent && ctx->fast_index_kernel) {
+            // every build side is a persistent table: the whole join is one launch of probe_index_kernel
+            const PredSlice& PS = *sl[probe_k];
+            const u32 T = K - 1;
+            ProbeIParams P{};
+            std::vector<u32> out_slots = pv[probe_k];
+            FilterProg postp = post;
+            auto to_post = [&](u32 k) {
+                if (pushdown[k].ops.empty()) return;
+                const bool had = !postp.ops.empty();
+                postp.ops.insert(postp.ops.end(), pushdown[k].ops.begin(), pushdown[k].ops.end());
+                if (had) { kb_filter_op a{}; a.op = KB_F_AND; postp.ops.push_back(a); }
+            };
+            u32 t = 0;
+            for (u32 k = 0; k < K; k++) {
+                if ((int)k == probe_k) continue;
+                const bool y = key_pos(k) == 2;
+                DirectTab& D = P.tab[t++];
+                D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                D.tab = static_cast<const u32*>(y ? sl[k]->ytab->p : sl[k]->xtab->p);
+                D.kmin = y ? sl[k]->ytab_min : sl[k]->xtab_min;
+                D.range = y ? sl[k]->ytab_range : sl[k]->xtab_range;
+                D.cshift = y ? 0u : sl[k]->tab_cshift;
+                to_post(k);
+                out_slots.push_back(pv[k][y ? 0 : 1]);
+            }
+            const FilterProg& pf = pushdown[probe_k];
+            if (!pf.ops.empty()) {
+                if (pf.ops.size() > 8) to_post((u32)probe_k);
+                else {
+                    std::map<u32, u32> remap;  // slots of the probe pattern's own filter -> pair halves (x = subject, y = object)
+                    for (size_t i = 0; i < pv[probe_k].size(); i++) remap[pv[probe_k][i]] = psrc[probe_k][i] == 0 ? 0u : 1u;
+                    std::vector<FilterOp> fo;
+                    if (!append_prog(&fo, pf, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
+                    const bool typed = PS.ynum && PS.ynum_version == ctx->num_version && fo.size() == 1 && fo[0].op == KB_F_CMP_NUM && fo[0].slot == 1u;
+                    if (typed) {
+                        P.pre_mode = 1; P.pre_cmp = fo[0].cmp; P.pre_val = fo[0].value;
+                        P.ynum = static_cast<const double*>(PS.ynum->p);
+                    } else {
+                        P.pre_mode = 2; P.n_pre = (u32)fo.size();
+                        for (size_t i = 0; i < fo.size(); i++) P.pre_ops[i] = fo[i];
+                    }
+                }
+            }
+            const u32 n_out = 2 + T;
+            if (!postp.ops.empty()) {
+                std::map<u32, u32> remap;
+                for (u32 c = 0; c < n_out; c++) remap[out_slots[c]] = c;
+                std::vector<FilterOp> fops;
+                if (!append_prog(&fops, postp, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
+                if (fops.size() > KB_MAX_FILTER_OPS) return fail(ctx, KB_E_LIMIT, "filter too long");
+                P.n_ops = (u32)fops.size();
+                for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
+            }
+            auto res = std::make_unique<kb_rel>();
+            res->slots = out_slots;
+            {   // one allocation holds all output columns
+                const size_t stride = round256((size_t)PS.n * sizeof(u32)) + 256;
+                Buf b;
+                KB_TRY(alloc_buf(ctx, stride * n_out, &b));
+                for (u32 c = 0; c < n_out; c++) {
+                    Col col;
+                    col.buf = b;
+                    col.ptr = reinterpret_cast<u32*>(static_cast<char*>(b->p) + stride * c);
+                    res->cols.push_back(col);
+                    P.out[c] = col.ptr;
+                }
+            }
+            P.pairs = reinterpret_cast<const uint2*>(PS.pairs.ptr);
+            P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
+            P.n = (u32)PS.n;
+            P.n_tiles = (u32)((PS.n + PROBEF_TILE - 1) / PROBEF_TILE);
+            P.T = T;
+            P.cap = (u32)PS.n;
+            P.nt = numtab(ctx);
+            P.ordered = ctx->ordered;
+            if (P.ordered) {
+                KB_TRY(ensure_tile_state(ctx, P.n_tiles));
+                P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+                P.block_state = static_cast<u64*>(ctx->block_state->p);
+            }
+            P.epoch = ctx->epoch++;
+            P.cb = ctx->fast_cb;
+            P.host_total = ctx->d_fast;
+            timer_begin(ctx, F_PROBE);
+            launch_probe_index(P, ctx->n_sms, ctx->st);
+            timer_end(ctx);
+            KB_CUDA(ctx, cudaGetLastError());
+            ctx->stats.rows_probed += PS.n;
+            ctx->stats.index_joins++;
+            KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+            timers_flush(ctx);
+            ctx->stats.d2h_bytes += sizeof(u32);
+            res->n = *reinterpret_cast<volatile u32*>(ctx->h_fast);
+            *out = select_cols(*res, all_slots);
+            return KB_OK;
+        }
         if (ok) {
             const u32 range = (u32)rng;
             const u32 off = ctrl_alloc(ctx, 16 + 2 * MAXT);
@@ -1335,8 +1436,13 @@ kb_status kb_ctx_create(int device, kb_ctx** out) {
     }
     if (const char* ord = getenv("KOLIBRIE_ORDERED")) ctx->ordered = (ord[0] == '0') ? 0u : 1u;
     if (const char* ui = getenv("KOLIBRIE_USE_INDEX")) ctx->use_index = ui[0] != '0';
+    if (const char* fk = getenv("KOLIBRIE_INDEX_KERNEL")) ctx->fast_index_kernel = fk[0] != '0';
     if ((e = cudaMalloc(&ctx->ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMalloc(ctrl)", e);
     if ((e = cudaMallocHost(&ctx->h_ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMallocHost(ctrl)", e);
+    if ((e = cudaMalloc(&ctx->fast_cb, 64)) != cudaSuccess) return bail("cudaMalloc(fast_cb)", e);
+    if ((e = cudaMemset(ctx->fast_cb, 0, 64)) != cudaSuccess) return bail("cudaMemset(fast_cb)", e);
+    if ((e = cudaHostAlloc(&ctx->h_fast, 64, cudaHostAllocMapped)) != cudaSuccess) return bail("cudaHostAlloc(h_fast)", e);
+    if ((e = cudaHostGetDevicePointer(&ctx->d_fast, ctx->h_fast, 0)) != cudaSuccess) return bail("cudaHostGetDevicePointer", e);
     *out = ctx;
     return KB_OK;
 }
@@ -1358,6 +1464,8 @@ void kb_ctx_destroy(kb_ctx* ctx) {
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->ctrl) cudaFree(ctx->ctrl);
     if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
+    if (ctx->fast_cb) cudaFree(ctx->fast_cb);
+    if (ctx->h_fast) cudaFreeHost(ctx->h_fast);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev_copy);
     cudaEventDestroy(ctx->ev_fork);

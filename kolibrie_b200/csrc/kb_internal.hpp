@@ -114,6 +114,12 @@ struct kb_ctx {
     kb::u32* ctrl = nullptr;
     kb::u32* h_ctrl = nullptr;
     kb::u32 ctrl_used = 0;
+    bool ctrl_dirty = true;  // words handed out since the arena was last zeroed (a call that hands out none skips the memset)
+    // control block of the one-kernel index join: device words {ticket, total, 0, done} that the kernel itself leaves zeroed, and the
+    // pinned host word the kernel publishes the row count to
+    kb::u32* fast_cb = nullptr;
+    kb::u32* h_fast = nullptr;
+    kb::u32* d_fast = nullptr;  // device address of h_fast
     static constexpr kb::u32 CTRL_WORDS = 8192;
     // pinned staging for uploads / downloads
     void* pinned = nullptr;
@@ -131,6 +137,7 @@ struct kb_ctx {
     kb::u64 store_version = 0;
     std::map<kb::u32, kb::PredSlice> index;  // kb_store_build_index: predicate -> slice; valid while index_version == store_version
     kb::u64 index_version = ~0ull;
+    bool fast_index_kernel = true;       // KOLIBRIE_INDEX_KERNEL=0: index joins go through the generic probe kernel (A/B switch)
     bool use_index = true;               // KOLIBRIE_USE_INDEX=0 / kb_set_use_index: force the scanning path
     kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject
     int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges

@@ -731,6 +731,192 @@ void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st) {
 }
 
 // =================================================================================================================
+// K_probe (INDEX)
+#ifndef KB_PI_MINB
+#define KB_PI_MINB 4
+#endif
+template <int T, int PRE>
+__global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel(const __grid_constant__ ProbeIParams P) {
+    constexpr int R = 4;  // rows per thread (striped over the warp's 128-row chunk, see below)
+    constexpr u32 TILE = PROBEF_THREADS * R;
+    extern __shared__ __align__(128) u32 smem[];  // TILE pairs [+ TILE doubles]
+    __shared__ __align__(8) u64 bar;
+    __shared__ u32 s_next;
+    __shared__ u32 s_wcnt[PROBEF_THREADS / 32];
+    __shared__ u32 s_excl1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    auto issue = [&](u32 t) {
+        const u32 b = t * TILE;
+        const u32 c = min(TILE, P.n - b);
+        const u32 bytes = (c * 8u + 15u) & ~15u;
+        mbar_arrive_expect_tx(&bar, PRE == 1 ? 2u * bytes : bytes);
+        tma_load_1d(smem, P.pairs + b, bytes, &bar);
+        if (PRE == 1) tma_load_1d(smem + 2 * TILE, P.ynum + b, bytes, &bar);
+    };
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+        const u32 t0 = atomicAdd(&P.cb[0], 1u);
+        s_next = t0;
+        if (t0 < P.n_tiles) issue(t0);
+    }
+    __syncthreads();
+    u32 tile = s_next;
+    u32 parity = 0;
+    while (tile < P.n_tiles) {
+        const u32 base = tile * TILE;
+        const u32 cnt = min(TILE, P.n - base);
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        u32 rx[R], ry[R];
+        double pa[R];
+        // striped: row j of this thread is row (warp*128 + j*32 + lane) of the tile, so one warp instruction touches 32 CONSECUTIVE
+        // rows: lookups into a table indexed by a sorted key hit 4 sectors instead of 16, and the compacted stores of one j are
+        // one contiguous run
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const u32 idx = (u32)warp * (32u * R) + (u32)j * 32u + (u32)lane;
+            const uint2 v = reinterpret_cast<const uint2*>(smem)[idx];
+            rx[j] = v.x; ry[j] = v.y;
+            if (PRE == 1) pa[j] = reinterpret_cast<const double*>(smem + 2 * TILE)[idx];
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const u32 nt = atomicAdd(&P.cb[0], 1u);
+            s_next = nt;
+            if (nt < P.n_tiles) issue(nt);
+        }
+        u32 vmask = 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) vmask |= (((u32)warp * (32u * R) + (u32)j * 32u + (u32)lane) < cnt ? 1u : 0u) << j;
+        if (PRE == 1) {
+            u32 pass = 0;
+#pragma unroll
+            for (int j = 0; j < R; j++) pass |= (cmp_num(P.pre_cmp, pa[j], P.pre_val) ? 1u : 0u) << j;
+            vmask &= pass;
+        } else if (P.pre_mode == 2u && vmask != 0u) {
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                if ((vmask >> j) & 1u) {
+                    u32 vals[2] = {rx[j], ry[j]};
+                    if (!eval_filter(P.pre_ops, P.n_pre, vals, P.nt)) vmask &= ~(1u << j);
+                }
+            }
+        }
+        u32 tv[R][T];
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const u32 key = P.key_is_y ? ry[j] : rx[j];
+#pragma unroll
+            for (int t = 0; t < T; t++) {
+                const u32 off = compact_key(key, P.tab[t].cshift) - P.tab[t].kmin;
+                tv[j][t] = (((vmask >> j) & 1u) && off < P.tab[t].range) ? __ldg(P.tab[t].tab + off) : EMPTY32;
+            }
+        }
+        u32 m = 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            bool hit = (vmask >> j) & 1u;
+#pragma unroll
+            for (int t = 0; t < T; t++) hit = hit && (tv[j][t] != EMPTY32);
+            m |= (hit ? 1u : 0u) << j;
+        }
+        if (P.n_ops != 0u && m != 0u) {
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                if ((m >> j) & 1u) {
+                    u32 vals[KB_MAX_COLS];
+                    vals[0] = rx[j]; vals[1] = ry[j];
+#pragma unroll
+                    for (int t = 0; t < T; t++) vals[2 + t] = tv[j][t];
+                    if (!eval_filter(P.ops, P.n_ops, vals, P.nt)) m &= ~(1u << j);
+                }
+            }
+        }
+        u32 bal[R];
+        u32 wtot = 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            bal[j] = __ballot_sync(0xffffffffu, (m >> j) & 1u);
+            wtot += (u32)__popc(bal[j]);
+        }
+        if (lane == 0) s_wcnt[warp] = wtot;
+        __syncthreads();
+        if (warp == 0) {
+            const u32 wc = lane < PROBEF_THREADS / 32 ? s_wcnt[lane] : 0u;
+            u32 wi = wc;
+#pragma unroll
+            for (int o = 1; o < PROBEF_THREADS / 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += y;
+            }
+            const u32 total = __shfl_sync(0xffffffffu, wi, PROBEF_THREADS / 32 - 1);
+            if (lane < PROBEF_THREADS / 32) s_wcnt[lane] = wi - wc;
+            const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.cb + 2, P.cb + 1, P.ordered, lane);
+            if (lane == 0) s_excl1 = ex;
+        }
+        __syncthreads();
+        {
+            u32 run = s_excl1 + s_wcnt[warp];
+            const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const u32 pos = run + (u32)__popc(bal[j] & lt);
+                if (((m >> j) & 1u) && pos < P.cap) {
+                    P.out[0][pos] = rx[j];
+                    P.out[1][pos] = ry[j];
+#pragma unroll
+                    for (int t = 0; t < T; t++) P.out[2 + t][pos] = tv[j][t];
+                }
+                run += (u32)__popc(bal[j]);
+            }
+        }
+        tile = s_next;
+    }
+    // the last CTA to get here publishes the row count and leaves the control block zeroed for the next launch
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        const u32 prev = atomicAdd(&P.cb[3], 1u);
+        if (prev == gridDim.x - 1u) {
+            __threadfence();
+            const u32 total = atomicExch(&P.cb[1], 0u);
+            *reinterpret_cast<volatile u32*>(P.host_total) = total;
+            P.cb[0] = 0u;
+            P.cb[3] = 0u;
+            __threadfence_system();
+        }
+    }
+}
+
+template <int T, int PRE>
+static void launch_probe_index_tp(const ProbeIParams& p, int n_sms, cudaStream_t st) {
+    static int per_sm = 0;  // occupancy is a property of the kernel image: asked once per instantiation
+    const size_t smem = (size_t)PROBEF_THREADS * 4 * (PRE == 1 ? 16 : 8);
+    if (per_sm == 0) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_index_kernel<T, PRE>, PROBEF_THREADS, smem);
+        if (per_sm < 1) per_sm = 1;
+    }
+    long long g = (long long)per_sm * n_sms;
+    if (g > (long long)p.n_tiles) g = p.n_tiles;
+    probe_index_kernel<T, PRE><<<(int)g, PROBEF_THREADS, smem, st>>>(p);
+}
+template <int T>
+static void launch_probe_index_t(const ProbeIParams& p, int n_sms, cudaStream_t st) {
+    if (p.pre_mode == 1u) launch_probe_index_tp<T, 1>(p, n_sms, st);
+    else launch_probe_index_tp<T, 0>(p, n_sms, st);
+}
+void launch_probe_index(const ProbeIParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    switch (p.T) {
+        case 1: launch_probe_index_t<1>(p, n_sms, st); break;
+        case 2: launch_probe_index_t<2>(p, n_sms, st); break;
+        case 3: launch_probe_index_t<3>(p, n_sms, st); break;
+        default: launch_probe_index_t<4>(p, n_sms, st); break;
+    }
+}
+
+// =================================================================================================================
 // K_probe (direct, fused multiway)
 template <int T>
 __global__ void __launch_bounds__(PROBE_THREADS) probe_direct_kernel(const __grid_constant__ ProbeDParams P) {

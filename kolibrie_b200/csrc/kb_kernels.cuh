@@ -147,6 +147,36 @@ struct ProbeFParams {
     const u32* abort_flag;
 };
 void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st);
+
+// K_probe (INDEX): the star join over the store index when every non-probe pattern has a persistent per-predicate table. The probe
+// rows are one predicate slice (x = subject, y = object) and, when the pattern carries FILTER(?y <cmp> c), the slice's typed literal
+// column; both are TMA-staged into shared memory by the same mbarrier, so the FILTER is resolved BEFORE any table lookup is issued.
+// Output layout is fixed: column 0 = x, 1 = y, 2+t = value found in table t. The launch owns a 4-word control block
+// {ticket, total, zero, done} that the last CTA to finish resets to zero after publishing the row count to pinned host memory: a
+// query is ONE device operation (no memset before, no copy after).
+struct ProbeIParams {
+    const uint2* pairs;
+    const double* ynum;  // typed literal column of the slice (non-null iff pre_mode == 1)
+    u32 key_is_y, n, n_tiles, T;
+    DirectTab tab[MAXT];
+    u32* out[2 + MAXT];
+    u32 cap;
+    u32 pre_mode;  // 0: none, 1: cmp_num(pre_cmp, ynum[row], pre_val), 2: pre_ops over (x, y)
+    u32 pre_cmp;
+    double pre_val;
+    FilterOp pre_ops[8];
+    u32 n_pre;
+    FilterOp ops[KB_MAX_FILTER_OPS];  // conjuncts that need a looked-up value: evaluated over the output row
+    u32 n_ops;
+    NumTab nt;
+    u64* tile_state;
+    u64* block_state;
+    u32 ordered;
+    u64 epoch;
+    u32* cb;          // device control block: [0] ticket, [1] total, [2] always 0, [3] CTAs done
+    u32* host_total;  // mapped pinned host word
+};
+void launch_probe_index(const ProbeIParams& p, int n_sms, cudaStream_t st);
 void launch_unpair(const uint2* kv, u32 n, u32* x, u32* y, cudaStream_t st);
 // direct build from a predicate slice of the store index, with the pattern's pushed-down FILTER evaluated on (s, P, o)
 struct BuildPairsParams {

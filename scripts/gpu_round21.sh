@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+for v in kolibrie_b200 kb_minb5 kb_minb6 kb_oneshot kb_oneshot5 kb_noatomic; do
+echo "== variant $v"; KOLIBRIE_B200_LIB=$PWD/kolibrie_b200/lib$v.so timeout 600 python bench.py --steps 50 --warmup 5 --no-cpu --no-e2e 2>&1 | tail -1 > gpurun_out/var_$v.json; python -c "
+import json; d=json.load(open('gpurun_out/var_$v.json')); print(d['value'], d['ms_per_step'], d['roofline']['ms_per_launch'], d['roofline']['frac'])"
+done
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:probe_index -s 1 -c 1 -o gpurun_out/prof_probe_index_r1l -f python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e > /dev/null 2>&1
+ls -la gpurun_out/prof_probe_index_r1l.ncu-rep

@@ -357,3 +357,62 @@ def test_index_path_multivalued_and_missing_predicate(ctx):
     # object-keyed star: ?a P1 ?x . ?b P2 ?x joined on the object
     pats_o = [c.pattern(c.V(1), c.K(100), c.V(0)), c.pattern(c.V(2), c.K(101), c.V(0))]
     H.assert_same_bag(ctx.star_join(0, pats_o).to_numpy([0, 1, 2]), db.bgp(pats_o).to_numpy([0, 1, 2]), "object star")
+
+
+@pytest.mark.parametrize("n_subj", [1, 1023, 1024, 3017, 40000])
+def test_index_kernel_shapes(ctx, n_subj):
+    """the one-launch index join (probe_index_kernel): every build side is a persistent table. T = 1..4 tables, typed / general /
+    no pre-filter on the probe slice, filters on looked-up values, object-keyed joins, ragged last tiles, and the self-cleaning
+    control block across many launches in a row"""
+    rng = np.random.default_rng(n_subj)
+    subj = np.arange(50, 50 + n_subj, dtype=np.uint32)
+    base = 50 + n_subj
+    vals = np.arange(base, base + 64, dtype=np.uint32)            # 64 numeric literals
+    uniq = base + 64 + rng.permutation(n_subj).astype(np.uint32)  # a unique, dense object per subject (inverse functional)
+    few = np.arange(base + 64 + n_subj, base + 64 + n_subj + 3, dtype=np.uint32)
+    n_ids = int(few[-1]) + 1
+    num = np.zeros(n_ids)
+    isn = np.zeros(n_ids, np.uint8)
+    num[vals] = np.linspace(-5.0, 250.5, 64)
+    isn[vals] = 1
+    cols = []
+    for pid, ob in ((100, vals[rng.integers(0, 64, n_subj)]), (101, uniq), (102, few[rng.integers(0, 3, n_subj)]), (103, vals[rng.integers(0, 64, n_subj)]),
+                    (104, few[rng.integers(0, 3, n_subj)])):
+        keep = np.ones(n_subj, bool) if pid != 103 else rng.random(n_subj) < 0.7  # P103 is missing for ~30 % of the subjects
+        cols.append(np.stack([subj[keep], np.full(keep.sum(), pid, np.uint32), ob[keep]], axis=1))
+    tr = np.concatenate(cols).astype(np.uint32)
+    tr = tr[rng.permutation(len(tr))]
+    ctx.dict_numeric_load(num, isn)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    assert ctx.build_index()[0] == 5
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2], num, isn)
+    P = lambda pid, v: c.pattern(c.V(0), c.K(pid), c.V(v))
+    gt = lambda slot, v: [c.fop(c.F_CMP_NUM, slot=slot, cmp=c.CMP_GT, value=v)]
+    cases = [
+        ("T1 no filter", [P(100, 1), P(101, 2)], None),
+        ("T2 typed pre-filter", [P(101, 1), P(100, 2), P(102, 3)], gt(2, 100.0)),
+        ("T2 typed <=", [P(101, 1), P(100, 2), P(102, 3)], [c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_LE, value=17.25)]),
+        ("T3 partial predicate", [P(100, 1), P(101, 2), P(102, 3), P(103, 4)], gt(1, 0.0)),
+        ("T4 everything", [P(100, 1), P(101, 2), P(102, 3), P(103, 4), P(104, 5)], None),
+        ("general pre-filter (id equality AND numeric)", [P(102, 1), P(100, 2)], [c.fop(c.F_EQ_ID, slot=1, id=int(few[1])), c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_LT, value=200.0), c.fop(c.F_AND)]),
+        ("filter spanning two patterns", [P(100, 1), P(103, 2), P(101, 3)], [c.fop(c.F_PUSH_VAR, slot=1), c.fop(c.F_PUSH_VAR, slot=2), c.fop(c.F_SUB), c.fop(c.F_TRUTHY)]),
+        ("two numeric filters on different patterns", [P(100, 1), P(103, 2), P(102, 3)], gt(1, 50.0) + gt(2, 20.0) + [c.fop(c.F_AND)]),
+        ("filter on the subject", [P(100, 1), P(102, 2)], [c.fop(c.F_NE_ID, slot=0, id=int(subj[0]))]),
+    ]
+    before = ctx.get_stats()["index_joins"]
+    for name, pats, filt in cases:
+        for rep in range(2):  # the second launch starts from the control block the first one left behind
+            got = ctx.star_join(0, pats, filt)
+            want = db.bgp(pats, filt)
+            H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"{name} (n={n_subj}, rep {rep})")
+    assert ctx.get_stats()["index_joins"] == before + 2 * len(cases)
+    # object-keyed: ?a P101 ?x . ?b P101 ?x (the persistent table is ytab)
+    pats_o = [c.pattern(c.V(1), c.K(101), c.V(0)), c.pattern(c.V(2), c.K(101), c.V(0))]
+    got = ctx.star_join(0, pats_o)
+    H.assert_same_bag(got.to_numpy([0, 1, 2]), db.bgp(pats_o).to_numpy([0, 1, 2]), "object-keyed")
+    # a scan-path query in between must not disturb the control block
+    ctx.set_use_index(False)
+    r = ctx.star_join(0, cases[1][1], cases[1][2])
+    ctx.set_use_index(True)
+    got = ctx.star_join(0, cases[1][1], cases[1][2])
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), r.to_numpy(sorted(r.slots)), "index vs scan path")
