@@ -73,7 +73,7 @@ def main():
         sync_all()
         dt = (time.perf_counter() - t0) / (args.steps * 10)
         emit({"workload": "cfg1: employee 10K (60 000 triples), 2-pattern BGP", "value": rows / dt, "unit": "bindings/s", "ms_per_query": dt * 1e3, "rows": rows,
-              "note": "latency-bound: one query = 2 kernel launches + 2 synchronisations"})
+              "note": "latency-bound: one query = one kernel launch + one stream synchronisation"})
 
     if "cfg3" in only:
         E = int(16_666_667 * args.scale)
@@ -94,15 +94,20 @@ def main():
         for _ in range(3):
             rows, g = step()
         sync_all()
+        ctx.set_timing(True)
+        ctx.get_stats(reset=True)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             rows, g = step()
         sync_all()
         dt = (time.perf_counter() - t0) / args.steps
+        st3 = ctx.get_stats(reset=True)
+        ctx.set_timing(False)
         rows_all, dt = reduce(rows, dt)
         assert int(g["counts"].sum()) == rows and len(g["counts"]) == 3
         emit({"workload": f"cfg3: {6 * E} triples per GPU x {world} GPU, 4-pattern star + GROUP BY ?t COUNT", "value": rows_all / dt, "unit": "bindings/s",
-              "ms_per_query": dt * 1e3, "groups": 3, "n_gpus": world, "scaling": "weak"})
+              "ms_per_query": dt * 1e3, "groups": 3, "n_gpus": world, "scaling": "weak",
+              "device_ms_per_query": {"join": st3["probe_ms"] / args.steps, "group": st3["group_ms"] / args.steps}})
 
     if "cfg4" in only:
         n_inst = int(48_888_890 * args.scale)

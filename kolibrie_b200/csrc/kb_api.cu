@@ -2022,12 +2022,13 @@ kb_status kb_group_aggregate(kb_ctx* ctx, const kb_rel* in, const uint32_t* grou
     u64 slots = 1u << 12;  // small first try: the table is downloaded whole; overflow -> 16x larger and rerun
     for (;;) {
         P.n_slots = (u32)slots;
-        kb::Buf keys, state, val, cnt;
-        KB_TRY(kb::alloc_buf(ctx, slots * 4 * sizeof(u32), &keys));
-        KB_TRY(kb::alloc_buf(ctx, slots * sizeof(u32), &state));
-        KB_TRY(kb::alloc_buf(ctx, slots * 8 * sizeof(double), &val));
-        KB_TRY(kb::alloc_buf(ctx, slots * sizeof(unsigned long long), &cnt));
-        P.gkeys = (u32*)keys->p; P.gstate = (u32*)state->p; P.gval = (double*)val->p; P.gcnt = (unsigned long long*)cnt->p;
+        // one device buffer [val | cnt | keys | state] so that the table comes back in one copy into pinned memory
+        const size_t o_val = 0, o_cnt = o_val + slots * 8 * sizeof(double), o_keys = o_cnt + slots * sizeof(unsigned long long),
+                     o_state = o_keys + slots * 4 * sizeof(u32), tab_bytes = o_state + slots * sizeof(u32);
+        kb::Buf tab;
+        KB_TRY(kb::alloc_buf(ctx, tab_bytes, &tab));
+        char* tb = static_cast<char*>(tab->p);
+        P.gval = (double*)(tb + o_val); P.gcnt = (unsigned long long*)(tb + o_cnt); P.gkeys = (u32*)(tb + o_keys); P.gstate = (u32*)(tb + o_state);
         const u32 off = kb::ctrl_alloc(ctx, 4);
         KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
         P.overflow = ctx->ctrl + off;
@@ -2038,14 +2039,28 @@ kb_status kb_group_aggregate(kb_ctx* ctx, const kb_rel* in, const uint32_t* grou
         KB_CUDA(ctx, cudaGetLastError());
         KB_TRY(kb::ctrl_read(ctx));
         if (ctx->h_ctrl[off] == 0) {
-            std::vector<u32> hstate(slots), hkeys(slots * 4);
-            std::vector<double> hval(slots * 8);
-            std::vector<unsigned long long> hcnt(slots);
-            KB_CUDA(ctx, cudaMemcpyAsync(hstate.data(), P.gstate, slots * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
-            KB_CUDA(ctx, cudaMemcpyAsync(hkeys.data(), P.gkeys, slots * 4 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
-            KB_CUDA(ctx, cudaMemcpyAsync(hval.data(), P.gval, slots * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->st));
-            KB_CUDA(ctx, cudaMemcpyAsync(hcnt.data(), P.gcnt, slots * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->st));
+            std::vector<char> big;  // tables past 32 MB (hundreds of thousands of groups) are not worth pinning
+            void* dst = nullptr;
+            if (tab_bytes <= (32u << 20)) {
+                if (ctx->pinned_bytes < tab_bytes) {
+                    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+                    ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+                    KB_CUDA(ctx, cudaMallocHost(&ctx->pinned, tab_bytes));
+                    ctx->pinned_bytes = tab_bytes;
+                }
+                dst = ctx->pinned;
+            } else {
+                big.resize(tab_bytes);
+                dst = big.data();
+            }
+            KB_CUDA(ctx, cudaMemcpyAsync(dst, tb, tab_bytes, cudaMemcpyDeviceToHost, ctx->st));
             KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+            ctx->stats.d2h_bytes += tab_bytes;
+            const char* hb = static_cast<const char*>(dst);
+            const double* hval = (const double*)(hb + o_val);
+            const unsigned long long* hcnt = (const unsigned long long*)(hb + o_cnt);
+            const u32* hkeys = (const u32*)(hb + o_keys);
+            const u32* hstate = (const u32*)(hb + o_state);
             for (u64 i = 0; i < slots; i++) {
                 if (hstate[i] != 2u) continue;
                 for (u32 c = 0; c < n_group; c++) g->keys[c].push_back(hkeys[i * 4 + c]);

@@ -530,7 +530,6 @@ template <int T>
 __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) probe_fast_kernel(const __grid_constant__ ProbeFParams P) {
     constexpr int R = PROBEF_ITEMS;  // rows per thread, consecutive
     extern __shared__ __align__(128) u32 smem[];  // PROBEF_TILE pairs
-    const uint4* sm4 = reinterpret_cast<const uint4*>(smem);
     __shared__ __align__(8) u64 bar;
     __shared__ u32 s_next;
     __shared__ u32 s_wcnt[PROBEF_THREADS / 32];
@@ -559,17 +558,18 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
     __syncthreads();
     tile = s_next;
     u32 parity = 0;
-    const u32 full = (1u << R) - 1u;
     while (tile < P.n_tiles) {
         const u32 base = tile * (u32)PROBEF_TILE;
         const u32 cnt = min((u32)PROBEF_TILE, P.n - base);
         mbar_wait(&bar, parity);
         parity ^= 1u;
-        u32 rx[R], ry[R];  // rows R*tid .. R*tid+R-1 as (x,y) pairs
+        // striped: row j of this thread is row (warp*32*R + j*32 + lane) of the tile — one warp instruction touches 32 consecutive rows, so
+        // lookups by a sorted key hit 4 sectors instead of 16 and the compacted stores of one j form one contiguous run
+        u32 rx[R], ry[R];
 #pragma unroll
-        for (int q = 0; q < R / 2; q++) {
-            const uint4 v = sm4[(R / 2) * tid + q];
-            rx[2 * q] = v.x; ry[2 * q] = v.y; rx[2 * q + 1] = v.z; ry[2 * q + 1] = v.w;
+        for (int j = 0; j < R; j++) {
+            const uint2 v = reinterpret_cast<const uint2*>(smem)[(u32)warp * (32u * R) + (u32)j * 32u + (u32)lane];
+            rx[j] = v.x; ry[j] = v.y;
         }
         __syncthreads();
         if (tid == 0) {
@@ -583,8 +583,10 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
                 tma_load_1d(smem, P.pairs + nb, bytes, &bar);
             }
         }
-        const u32 first = (u32)tid * (u32)R;
-        u32 vmask = first >= cnt ? 0u : (cnt - first >= (u32)R ? full : ((1u << (cnt - first)) - 1u));
+        const u32 row0 = (u32)warp * (32u * R) + (u32)lane;  // row j = row0 + 32*j
+        u32 vmask = 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) vmask |= (row0 + 32u * (u32)j < cnt ? 1u : 0u) << j;
         // FILTER conjuncts over the probe row alone. The common shape FILTER(?x <cmp> c) needs one numeric gather per row: it is issued
         // together with the table lookups (independent loads, one memory round trip) and resolved afterwards — gating the lookups on
         // it would put two dependent round trips on the critical path of a latency-bound kernel.
@@ -594,7 +596,7 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
             const u32 slot = P.pre_ops[0].slot;
 #pragma unroll
             for (int j = 0; j < R; j++) {
-                if (P.pre_num != nullptr && slot == 1u) pa[j] = ((vmask >> j) & 1u) ? __ldg(P.pre_num + base + first + (u32)j) : 0.0;
+                if (P.pre_num != nullptr && slot == 1u) pa[j] = ((vmask >> j) & 1u) ? __ldg(P.pre_num + base + row0 + 32u * (u32)j) : 0.0;
                 else pa[j] = ((vmask >> j) & 1u) ? num_of(P.nt, slot == 0u ? rx[j] : ry[j]) : 0.0;
             }
         } else if (P.n_pre != 0u && vmask != 0u) {
@@ -666,15 +668,14 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
                 }
             }
         }
-        const u32 c = (u32)__popc(m);
-        u32 incl = c;
+        u32 bal[R];
+        u32 wtot = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+        for (int j = 0; j < R; j++) {
+            bal[j] = __ballot_sync(0xffffffffu, (m >> j) & 1u);
+            wtot += (u32)__popc(bal[j]);
         }
-        const u32 wex = incl - c;
-        if (lane == 31) s_wcnt[warp] = incl;
+        if (lane == 0) s_wcnt[warp] = wtot;
         __syncthreads();
         if (warp == 0) {
             const u32 wc = lane < PROBEF_THREADS / 32 ? s_wcnt[lane] : 0u;
@@ -690,20 +691,21 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
             if (lane == 0) s_excl1 = ex;
         }
         __syncthreads();
-        if (m != 0u) {
-            const u32 pos = s_excl1 + s_wcnt[warp] + wex;
+        {
+            const u32 lt = (1u << lane) - 1u;
+            const u32 wbase = s_excl1 + s_wcnt[warp];
             for (u32 cidx = 0; cidx < P.n_out; cidx++) {
                 const OutCol oc = P.oc[cidx];
-                u32* out = P.out[cidx] + pos;
-                u32 r = pos;
+                u32* out = P.out[cidx];
+                u32 run = wbase;
 #pragma unroll
                 for (int j = 0; j < R; j++) {
                     u32 x = oc.kind == OUT_PROBE ? (oc.a == 0u ? rx[j] : ry[j]) : 0u;
 #pragma unroll
                     for (int t = 0; t < T; t++) if (oc.kind == OUT_TABVAL && oc.a == (u32)t) x = tv[j][t];
-                    if (((m >> j) & 1u) && r < P.cap) *out = x;
-                    out += (m >> j) & 1u;
-                    r += (m >> j) & 1u;
+                    const u32 pos = run + (u32)__popc(bal[j] & lt);
+                    if (((m >> j) & 1u) && pos < P.cap) out[pos] = x;
+                    run += (u32)__popc(bal[j]);
                 }
             }
         }
@@ -1391,8 +1393,102 @@ __global__ void __launch_bounds__(256) group_kernel(const __grid_constant__ Grou
         group_update_global(P, k, scnt[i], v);
     }
 }
+// GROUP BY one variable with at most one aggregate (GROUP BY ?t COUNT, SUM/AVG/MIN/MAX(?x) GROUP BY ?t — execute_query.rs:1150-1227):
+// the key itself is the match value, four rows per thread are loaded before any is folded (the loop is load-latency bound), the CTA
+// table is keyed by a CAS on the key word and counts are 32-bit shared atomics.
+template <int AGG>  // 0: COUNT only, else the kb_agg kind of the single value aggregate
+__global__ void __launch_bounds__(256) group1_kernel(const __grid_constant__ GroupParams P) {
+    constexpr int IT = 4;
+    __shared__ u32 sk[GROUP_SMEM];
+    __shared__ u32 scnt[GROUP_SMEM];
+    __shared__ double sval[GROUP_SMEM];
+    for (int i = threadIdx.x; i < GROUP_SMEM; i += blockDim.x) {
+        sk[i] = EMPTY32;
+        scnt[i] = 0u;
+        sval[i] = AGG == KB_AGG_MIN ? CUDART_INF : (AGG == KB_AGG_MAX ? -CUDART_INF : 0.0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const u32 stride = gridDim.x * blockDim.x;
+    const u32 n_round = (P.n + 31u) & ~31u;
+    const u32* __restrict__ kc = P.gcol[0];
+    const u32* __restrict__ ac = P.acol[0];
+    for (u32 i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n_round; i0 += IT * stride) {
+        u32 key[IT];
+        double val[IT];
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            const u32 i = i0 + (u32)j * stride;
+            key[j] = i < P.n ? __ldg(kc + i) : EMPTY32;
+            if (AGG != 0) val[j] = i < P.n ? num_of(P.nt, __ldg(ac + i)) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < IT; j++) {
+            const u32 i = i0 + (u32)j * stride;
+            if (i - (u32)lane >= P.n) continue;  // the whole warp is past the end (warp-uniform)
+            const bool valid = i < P.n;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (!valid) continue;
+            const unsigned peers = __match_any_sync(act, key[j]);
+            const int leader = __ffs(peers) - 1;
+            double acc = 0.0;
+            if (AGG != 0) {
+                acc = val[j];
+                unsigned rest = peers & ~(1u << leader);
+                while (rest) {
+                    const int src = __ffs(rest) - 1;
+                    rest &= rest - 1u;
+                    const double o = __shfl_sync(peers, val[j], src);
+                    if (AGG == KB_AGG_MIN) acc = fmin(acc, o);
+                    else if (AGG == KB_AGG_MAX) acc = fmax(acc, o);
+                    else acc += o;
+                }
+            }
+            if (lane != leader) continue;
+            const u32 cnt = (u32)__popc(peers);
+            u32 slot = mix32(key[j]) & (GROUP_SMEM - 1);
+            bool done = false;
+            for (int probes = 0; probes < GROUP_SMEM && !done && key[j] != EMPTY32; probes++) {  // EMPTY32 marks a free entry
+                u32 cur = *reinterpret_cast<volatile u32*>(&sk[slot]);
+                if (cur == EMPTY32) cur = atomicCAS(&sk[slot], EMPTY32, key[j]);
+                if (cur == EMPTY32 || cur == key[j]) {
+                    atomicAdd(&scnt[slot], cnt);
+                    if (AGG == KB_AGG_MIN) atomic_min_f64(&sval[slot], acc);
+                    else if (AGG == KB_AGG_MAX) atomic_max_f64(&sval[slot], acc);
+                    else if (AGG != 0) atomicAdd(&sval[slot], acc);
+                    done = true;
+                } else slot = (slot + 1u) & (GROUP_SMEM - 1);
+            }
+            if (!done) {  // more than 64 distinct groups in this CTA
+                u32 k[4] = {key[j], 0u, 0u, 0u};
+                double v[8] = {acc, 0, 0, 0, 0, 0, 0, 0};
+                group_update_global(P, k, (unsigned long long)cnt, v);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < GROUP_SMEM; i += blockDim.x) {
+        if (sk[i] == EMPTY32) continue;
+        u32 k[4] = {sk[i], 0u, 0u, 0u};
+        double v[8] = {sval[i], 0, 0, 0, 0, 0, 0, 0};
+        group_update_global(P, k, (unsigned long long)scnt[i], v);
+    }
+}
 void launch_group(const GroupParams& p, int n_sms, cudaStream_t st) {
     if (p.n == 0) return;
+    if (p.n_gcols == 1 && p.n_aggs <= 1) {
+        // a CTA's 32-bit shared counters see at most n / grid * ... rows: far below 2^32
+        int grid = (int)umin64((u64)n_sms * 8ull, ((u64)p.n + 1023ull) / 1024ull);
+        const u32 kind = (p.n_aggs == 0 || p.akind[0] == KB_AGG_COUNT) ? 0u : p.akind[0];
+        switch (kind) {
+            case 0: group1_kernel<0><<<grid, 256, 0, st>>>(p); break;
+            case KB_AGG_SUM: group1_kernel<KB_AGG_SUM><<<grid, 256, 0, st>>>(p); break;
+            case KB_AGG_AVG: group1_kernel<KB_AGG_AVG><<<grid, 256, 0, st>>>(p); break;
+            case KB_AGG_MIN: group1_kernel<KB_AGG_MIN><<<grid, 256, 0, st>>>(p); break;
+            default: group1_kernel<KB_AGG_MAX><<<grid, 256, 0, st>>>(p); break;
+        }
+        return;
+    }
     int grid = (int)umin64((u64)n_sms * 8ull, ((u64)p.n + 255ull) / 256ull);
     group_kernel<<<grid, 256, 0, st>>>(p);
 }

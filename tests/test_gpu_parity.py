@@ -208,8 +208,11 @@ def test_group_aggregate_vs_oracle(ctx, emp):
     js, pats, _ = datagen.employee_queries(d)["cfg3"]
     rel = ctx.star_join(js, pats)
     orel = db.bgp(pats)
-    aggs = [(c.AGG_COUNT, 0), (c.AGG_SUM, 2), (c.AGG_MIN, 2), (c.AGG_MAX, 2), (c.AGG_AVG, 2)]
-    for gslots in ([1], [2], [1, 4]):
+    all_aggs = [(c.AGG_COUNT, 0), (c.AGG_SUM, 2), (c.AGG_MIN, 2), (c.AGG_MAX, 2), (c.AGG_AVG, 2)]
+    # all five at once (general kernel), then one variable + one aggregate (the single-key kernel): 3 groups, and thousands of
+    # groups (more than a CTA's shared table holds)
+    cases = [(gs, all_aggs) for gs in ([1], [2], [1, 4])] + [(gs, [a]) for gs in ([1], [2]) for a in all_aggs] + [([1], [])]
+    for gslots, aggs in cases:
         g = ctx.group_aggregate(rel, gslots, aggs)
         w = db.group(orel, gslots, aggs)
 
