@@ -534,6 +534,96 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
     const kb_rel& B = build_left ? L : R;
     const kb_rel& Pr = build_left ? R : L;
 
+    // ---- grouped (CSR) join: one key column with a dense id range and no join filter
+    if (ctx->csr_join && common.size() == 1 && (!post || post->ops.empty())) {
+        const u32* bk = B.cols[B.col_of(common[0])].ptr;
+        const u32 off = ctrl_alloc(ctx, 8);  // [0] min, [1] max, [2..3] u64 output rows, [4] ticket, [5] total, [6] zero
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0xFF, sizeof(u32), ctx->st));
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off + 1, 0, 7 * sizeof(u32), ctx->st));
+        timer_begin(ctx, F_BUILD);
+        launch_col_minmax(bk, (u32)B.n, ctx->ctrl + off, ctx->ctrl + off + 1, ctx->n_sms, ctx->st);
+        timer_end(ctx);
+        KB_TRY(ctrl_read(ctx));
+        const u32 kmin = ctx->h_ctrl[off], kmax = ctx->h_ctrl[off + 1];
+        const u64 range = (u64)kmax - kmin + 1;
+        if (kmax >= kmin && range <= std::max<u64>(16 * B.n, 1ull << 20) && range < (1ull << 31)) {
+            Buf dir, cursor, scratch;
+            KB_TRY(alloc_buf(ctx, (range + 1) * sizeof(u32), &dir));
+            KB_TRY(alloc_buf(ctx, range * sizeof(u32), &cursor));
+            KB_TRY(alloc_buf(ctx, ((range + 1) / 2048 + 4) * sizeof(u32), &scratch));
+            CsrTab tab{};
+            tab.off = static_cast<const u32*>(dir->p);
+            tab.kmin = kmin;
+            tab.range = (u32)range;
+            std::vector<u32> kernel_slots = Pr.slots;  // kernel output order: probe columns, then build payload columns
+            std::vector<const u32*> pay_in;
+            std::vector<u32*> pay_out;
+            std::vector<Col> pay_cols;
+            for (size_t c = 0; c < B.slots.size(); c++) {
+                if (B.slots[c] == common[0]) continue;
+                Col pc;
+                KB_TRY(alloc_col(ctx, B.n, &pc));
+                pay_cols.push_back(pc);
+                pay_in.push_back(B.cols[c].ptr);
+                pay_out.push_back(pc.ptr);
+                tab.pay[tab.n_pay++] = pc.ptr;
+                kernel_slots.push_back(B.slots[c]);
+            }
+            timer_begin(ctx, F_BUILD, 5);
+            KB_CUDA(ctx, cudaMemsetAsync(dir->p, 0, (range + 1) * sizeof(u32), ctx->st));
+            launch_csr_count(bk, (u32)B.n, kmin, static_cast<u32*>(dir->p), ctx->n_sms, ctx->st);
+            launch_exclusive_scan_u32(static_cast<u32*>(dir->p), (u32)range + 1, static_cast<u32*>(scratch->p), ctx->st);
+            KB_CUDA(ctx, cudaMemcpyAsync(cursor->p, dir->p, range * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            launch_csr_fill(bk, (u32)B.n, kmin, static_cast<u32*>(cursor->p), pay_in.data(), pay_out.data(), tab.n_pay, ctx->n_sms, ctx->st);
+            timer_end(ctx);
+            ctx->stats.rows_built += B.n;
+            const u32* pk = Pr.cols[Pr.col_of(common[0])].ptr;
+            timer_begin(ctx, F_PROBE);
+            launch_csr_total(pk, (u32)Pr.n, tab, reinterpret_cast<unsigned long long*>(ctx->ctrl + off + 2), ctx->n_sms, ctx->st);
+            timer_end(ctx);
+            KB_CUDA(ctx, cudaGetLastError());
+            KB_TRY(ctrl_read(ctx));
+            unsigned long long total = 0;
+            memcpy(&total, ctx->h_ctrl + off + 2, sizeof total);
+            if (total >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "join result of %llu rows exceeds 2^32", total);
+            ProbeGParams G{};
+            G.n_pcols = (u32)Pr.cols.size();
+            G.n = (u32)Pr.n;
+            G.n_tiles = (u32)((Pr.n + PROBEG_TILE - 1) / PROBEG_TILE);
+            for (u32 c = 0; c < G.n_pcols; c++) G.pcol[c] = Pr.cols[c].ptr;
+            G.pkey = (u32)Pr.col_of(common[0]);
+            G.tab = tab;
+            rel->cols.clear();
+            rel->cols.resize(rel->slots.size());
+            for (size_t c = 0; c < kernel_slots.size(); c++) {
+                Col col;
+                KB_TRY(alloc_col(ctx, total, &col));
+                rel->cols[rel->col_of(kernel_slots[c])] = col;
+                G.out[c] = col.ptr;
+            }
+            G.cap = (u32)total;
+            KB_TRY(ensure_tile_state(ctx, G.n_tiles));
+            G.tile_state = static_cast<u64*>(ctx->tile_state->p);
+            G.block_state = static_cast<u64*>(ctx->block_state->p);
+            G.ordered = ctx->ordered;
+            G.ticket = ctx->ctrl + off + 4;
+            G.total = ctx->ctrl + off + 5;
+            G.zero_word = ctx->ctrl + off + 6;
+            G.epoch = ctx->epoch++;
+            ctx->stats.rows_probed += Pr.n;
+            if (total) {
+                timer_begin(ctx, F_PROBE);
+                launch_probe_grouped(G, ctx->n_sms, ctx->st);
+                timer_end(ctx);
+                KB_CUDA(ctx, cudaGetLastError());
+            }
+            rel->n = total;
+            // dir / cursor / payload copies are released stream-ordered (cudaFreeAsync on ctx->st), i.e. after the launch above
+            *out = std::move(rel);
+            return KB_OK;
+        }
+    }
+
     ChainTab T{};
     T.n_slots = pow2_at_least(B.n * 2);
     T.n_keys = (u32)common.size();
@@ -1437,6 +1527,7 @@ kb_status kb_ctx_create(int device, kb_ctx** out) {
     if (const char* ord = getenv("KOLIBRIE_ORDERED")) ctx->ordered = (ord[0] == '0') ? 0u : 1u;
     if (const char* ui = getenv("KOLIBRIE_USE_INDEX")) ctx->use_index = ui[0] != '0';
     if (const char* fk = getenv("KOLIBRIE_INDEX_KERNEL")) ctx->fast_index_kernel = fk[0] != '0';
+    if (const char* cj = getenv("KOLIBRIE_CSR_JOIN")) ctx->csr_join = cj[0] != '0';
     if ((e = cudaMalloc(&ctx->ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMalloc(ctrl)", e);
     if ((e = cudaMallocHost(&ctx->h_ctrl, kb_ctx::CTRL_WORDS * sizeof(u32))) != cudaSuccess) return bail("cudaMallocHost(ctrl)", e);
     if ((e = cudaMalloc(&ctx->fast_cb, 64)) != cudaSuccess) return bail("cudaMalloc(fast_cb)", e);

@@ -10,6 +10,9 @@
 // Round structure is the reference's: every rule of a round sees the same snapshot; new facts become visible (and become the
 // next delta) only after the round (infer_generic.rs:42-48) — so round counts and per-round fact counts match the oracle.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "kb_internal.hpp"
 
@@ -48,6 +51,19 @@ struct Pending {  // facts derived in the current round, not yet visible to the 
     u64 count;
 };
 
+// KOLIBRIE_TRACE=1: synchronise after every phase of the fixpoint and print where the wall-clock time went (stderr)
+struct Trace {
+    bool on = getenv("KOLIBRIE_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(kb_ctx* ctx, const char* what, unsigned long long rows = 0) {
+        if (!on) return;
+        cudaStreamSynchronize(ctx->st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[kb trace] %-28s %9.3f ms  rows=%llu\n", what, std::chrono::duration<double, std::milli>(now - t).count(), rows);
+        t = std::chrono::steady_clock::now();
+    }
+};
+
 struct Fix {
     kb_ctx* ctx;
     std::map<u32, PredRel> rels;
@@ -69,14 +85,21 @@ kb_status grow_rel(kb_ctx* ctx, PredRel& r, u64 need) {
     return KB_OK;
 }
 
-// (re)build the known-fact set of predicate `r` so that it can take `extra` more keys at load <= 0.5
-kb_status ensure_set(Fix& fx, PredRel& r, u64 extra) {
+// (re)build the known-fact set of predicate `r` so that it can take the facts the next launch is EXPECTED to add at load <= 0.5.
+// `extra` counts candidates, most of which are usually known already (cfg4: 1.25e9 candidates for 2.9e8 new facts), so the
+// expectation is capped at half the set's size (and at least 2^20 facts); derive_kernel enforces the real bound (budget) and the launch is repeated on a
+// larger table when the cap was too optimistic. A rebuild re-inserts every known fact, so every (re)build allocates twice the need.
+kb_status ensure_set(Fix& fx, PredRel& r, u64 extra, bool must_grow = false) {
     kb_ctx* ctx = fx.ctx;
-    const u64 need = (r.set_count + extra) * 2;
-    if (r.set && need <= r.set_slots) return KB_OK;
+    const u64 expect = std::min<u64>(extra, std::max<u64>(r.set_count / 2, 1u << 20));
+    const u64 need = (r.set_count + expect) * 2;
+    if (r.set && need <= r.set_slots && !must_grow) return KB_OK;
     u64 slots = 1024;
-    while (slots < need) slots <<= 1;
-    if (slots > (1ull << 31)) return fail(ctx, KB_E_LIMIT, "known-fact set of predicate %u would need %llu slots", r.pred, (unsigned long long)slots);
+    while (slots < need * 2) slots <<= 1;
+    if (must_grow) slots = std::max<u64>(slots, (u64)r.set_slots * 2);
+    if (slots > (1ull << 31)) slots = 1ull << 31;
+    if (slots < need || (must_grow && r.set && slots <= r.set_slots))
+        return fail(ctx, KB_E_LIMIT, "known-fact set of predicate %u would need more than 2^31 slots", r.pred);
     Buf nb;
     KB_TRY(alloc_buf(ctx, slots * sizeof(u64), &nb));
     KB_CUDA(ctx, cudaMemsetAsync(nb->p, 0xFF, slots * sizeof(u64), ctx->st));
@@ -158,6 +181,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     // ---- compile the rules (host): variable slots, synthetic variables for constants in s/o (quirk Q6), safety checks
     std::vector<RulePlan> plans(n_rules);
     Fix fx;
+    Trace tr;
     fx.ctx = ctx;
     for (u32 r = 0; r < n_rules; r++) {
         const kb_rule& rule = rules[r];
@@ -238,7 +262,12 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
             }
         }
     }
-    for (auto& kv : fx.rels) if (kv.second.is_head) KB_TRY(ensure_set(fx, kv.second, kv.second.n + 1024));
+    tr.mark(ctx, "split store by predicate");
+    for (auto& kv : fx.rels) if (kv.second.is_head) {
+        kv.second.set_count = kv.second.n;
+        KB_TRY(ensure_set(fx, kv.second, 1024));
+    }
+    tr.mark(ctx, "initial known-fact sets");
 
     // ---- rounds
     for (u32 round = 0;; round++) {
@@ -272,8 +301,10 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     std::unique_ptr<kb_rel> all, joined;
                     KB_TRY(make_view(ctx, pr, 0, pr.snapshot, (u32)pl.prem[j].s_var, (u32)pl.prem[j].o_var, &all));
                     if (strict) KB_TRY(enforce_constants(ctx, pl.prem[j], &all));
+                    tr.mark(ctx, "  views");
                     KB_TRY(hash_join_impl(ctx, *cur, *all, nullptr, &joined));
                     cur = std::move(joined);
+                    tr.mark(ctx, "  join", cur->n);
                 }
                 if (cur->n == 0) continue;
                 // heads: filters + instantiate + dedup against known facts + append
@@ -310,8 +341,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     D.nt = numtab(ctx);
                     PredRel& hr = fx.rels[h.p.value];
                     KB_TRY(ensure_set(fx, hr, cur->n));
-                    D.set = static_cast<u64*>(hr.set->p);
-                    D.set_slots = hr.set_slots;
+                    tr.mark(ctx, "  ensure_set", hr.set_slots);
                     Pending pd;
                     pd.pred = h.p.value;
                     pd.count = 0;
@@ -324,19 +354,37 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                     D.out_count = ctx->ctrl + coff;
                     D.overflow = ctx->ctrl + coff + 1;
                     D.n_deriv = reinterpret_cast<unsigned long long*>(ctx->ctrl + coff + 4);
-                    timer_begin(ctx, F_OTHER);
-                    launch_derive(D, ctx->n_sms, ctx->st);
-                    timer_end(ctx);
-                    KB_CUDA(ctx, cudaGetLastError());
-                    // counts are read immediately: the control arena may be recycled by later joins of this round
-                    KB_TRY(ctrl_read(ctx));
-                    if (ctx->h_ctrl[coff + 1]) return fail(ctx, KB_E_LIMIT, "known-fact set overflow");
-                    pd.count = ctx->h_ctrl[coff];
+                    const u64 count_before = hr.set_count;
+                    for (;;) {
+                        D.set = static_cast<u64*>(hr.set->p);
+                        D.set_slots = hr.set_slots;
+                        // the set may fill up to 3/4 before it has to grow (expected: 1/2)
+                        D.budget = (u32)std::min<u64>((u64)hr.set_slots / 4 * 3 - count_before, 0xFFFFFFFFull);
+                        timer_begin(ctx, F_OTHER);
+                        launch_derive(D, ctx->n_sms, ctx->st);
+                        timer_end(ctx);
+                        KB_CUDA(ctx, cudaGetLastError());
+                        // counts are read immediately: the control arena may be recycled by later joins of this round
+                        KB_TRY(ctrl_read(ctx));
+                        pd.count = ctx->h_ctrl[coff];
+                        if (ctx->h_ctrl[coff + 1] == 1u) return fail(ctx, KB_E_LIMIT, "known-fact set overflow");
+                        if (ctx->h_ctrl[coff + 1] == 0u) break;
+                        // budget reached: rebuild the set larger WITH the facts appended so far, then repeat the launch (facts already
+                        // inserted are found present and are not appended twice; the derivation count is the last, complete pass's)
+                        fx.pend.push_back(pd);
+                        const kb_status gs = ensure_set(fx, hr, cur->n, true);
+                        fx.pend.pop_back();
+                        if (gs != KB_OK) return gs;
+                        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff + 1, 0, sizeof(u32), ctx->st));
+                        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff + 4, 0, 2 * sizeof(u32), ctx->st));
+                    }
                     unsigned long long nd;
                     memcpy(&nd, ctx->h_ctrl + coff + 4, sizeof nd);
                     st.derivations += nd;
+                    hr.set_count = count_before;
                     hr.set_count += pd.count;
                     if (pd.count) fx.pend.push_back(pd);
+                    tr.mark(ctx, "  derive", pd.count);
                 }
             }
         }
@@ -353,6 +401,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
             round_new += cnt;
         }
         fx.pend.clear();
+        tr.mark(ctx, "round end: append", round_new);
         if (round_new == 0) break;
         if (st.rounds < 64) st.round_new[st.rounds] = round_new;
         st.rounds++;
@@ -391,6 +440,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
         ctx->single_valued.clear();
         ctx->index.clear();
     }
+    tr.mark(ctx, "result assembly", st.inferred);
     cudaEventRecord(ev1, ctx->st);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     timers_flush(ctx);

@@ -137,6 +137,7 @@ struct kb_ctx {
     kb::u64 store_version = 0;
     std::map<kb::u32, kb::PredSlice> index;  // kb_store_build_index: predicate -> slice; valid while index_version == store_version
     kb::u64 index_version = ~0ull;
+    bool csr_join = true;                // KOLIBRIE_CSR_JOIN=0: 1:N joins always use the chained table (A/B switch)
     bool fast_index_kernel = true;       // KOLIBRIE_INDEX_KERNEL=0: index joins go through the generic probe kernel (A/B switch)
     bool use_index = true;               // KOLIBRIE_USE_INDEX=0 / kb_set_use_index: force the scanning path
     kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject

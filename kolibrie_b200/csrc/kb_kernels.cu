@@ -1202,6 +1202,250 @@ void launch_probe_chained(const ProbeCParams& p, int n_sms, cudaStream_t st) {
     probe_chained_kernel<<<grid, PROBEC_THREADS, smem, st>>>(p);
 }
 
+// =================================================================================================================
+// K_build / K_probe (grouped by key, CSR directory)
+__global__ void __launch_bounds__(256) csr_count_kernel(const u32* __restrict__ keys, u32 n, u32 kmin, u32* __restrict__ counts) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&counts[keys[i] - kmin], 1u);
+}
+void launch_csr_count(const u32* keys, u32 n, u32 kmin, u32* counts, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    csr_count_kernel<<<grid, 256, 0, st>>>(keys, n, kmin, counts);
+}
+
+// exclusive scan in three passes over 2048-element tiles: tile sums, scan of the tile sums by one CTA, local scan + tile base
+constexpr u32 SCAN_TILE_ELEMS = 2048;
+__device__ __forceinline__ u32 cta_excl_scan_256(u32 v, u32* s_w, u32* total) {  // 256 threads; returns the exclusive prefix of v
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const u32 w = lane < 8 ? s_w[lane] : 0u;
+        u32 wi = w;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        if (lane < 8) s_w[lane] = wi - w;
+        if (lane == 7) s_w[8] = wi;
+    }
+    __syncthreads();
+    const u32 ex = s_w[warp] + incl - v;
+    *total = s_w[8];
+    __syncthreads();
+    return ex;
+}
+__global__ void __launch_bounds__(256) scan_tile_sums_kernel(const u32* __restrict__ a, u32 n, u32* __restrict__ sums) {
+    __shared__ u32 s_w[9];
+    const u32 base = blockIdx.x * SCAN_TILE_ELEMS;
+    u32 v = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const u32 i = base + (u32)j * 256u + threadIdx.x;
+        v += i < n ? a[i] : 0u;
+    }
+    u32 tot;
+    cta_excl_scan_256(v, s_w, &tot);
+    if (threadIdx.x == 0) sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) scan_sums_kernel(u32* sums, u32 n_tiles) {  // one CTA: exclusive scan of the tile sums, total at [n_tiles]
+    __shared__ u32 s_w[9];
+    u32 run = 0;
+    for (u32 b = 0; b < n_tiles; b += 256u) {
+        const u32 i = b + threadIdx.x;
+        const u32 v = i < n_tiles ? sums[i] : 0u;
+        u32 tot;
+        const u32 ex = cta_excl_scan_256(v, s_w, &tot);
+        if (i < n_tiles) sums[i] = run + ex;
+        run += tot;
+    }
+    if (threadIdx.x == 0) sums[n_tiles] = run;
+}
+__global__ void __launch_bounds__(256) scan_apply_kernel(u32* __restrict__ a, u32 n, const u32* __restrict__ sums) {
+    __shared__ u32 s_w[9];
+    const u32 base = blockIdx.x * SCAN_TILE_ELEMS + threadIdx.x * 8u;  // 8 consecutive elements per thread
+    u32 v[8];
+    u32 t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { v[j] = base + (u32)j < n ? a[base + (u32)j] : 0u; t += v[j]; }
+    u32 tot;
+    u32 ex = cta_excl_scan_256(t, s_w, &tot) + sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (base + (u32)j < n) a[base + (u32)j] = ex;
+        ex += v[j];
+    }
+}
+void launch_exclusive_scan_u32(u32* a, u32 n, u32* scratch, cudaStream_t st) {
+    if (n == 0) return;
+    const u32 n_tiles = (n + SCAN_TILE_ELEMS - 1) / SCAN_TILE_ELEMS;
+    scan_tile_sums_kernel<<<n_tiles, 256, 0, st>>>(a, n, scratch);
+    scan_sums_kernel<<<1, 256, 0, st>>>(scratch, n_tiles);
+    scan_apply_kernel<<<n_tiles, 256, 0, st>>>(a, n, scratch);
+}
+
+struct CsrFillParams {
+    const u32* keys;
+    u32 n, kmin, n_pay;
+    u32* cursor;
+    const u32* pay_in[KB_MAX_COLS];
+    u32* pay_out[KB_MAX_COLS];
+};
+__global__ void __launch_bounds__(256) csr_fill_kernel(const CsrFillParams P) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
+        const u32 pos = atomicAdd(&P.cursor[P.keys[i] - P.kmin], 1u);
+        for (u32 c = 0; c < P.n_pay; c++) P.pay_out[c][pos] = P.pay_in[c][i];
+    }
+}
+void launch_csr_fill(const u32* keys, u32 n, u32 kmin, u32* cursor, const u32* const* pay_in, u32* const* pay_out, u32 n_pay, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    CsrFillParams P{};
+    P.keys = keys; P.n = n; P.kmin = kmin; P.n_pay = n_pay; P.cursor = cursor;
+    for (u32 c = 0; c < n_pay; c++) { P.pay_in[c] = pay_in[c]; P.pay_out[c] = pay_out[c]; }
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    csr_fill_kernel<<<grid, 256, 0, st>>>(P);
+}
+
+__global__ void __launch_bounds__(256) csr_total_kernel(const u32* __restrict__ pk, u32 n, const u32* __restrict__ off, u32 kmin, u32 range,
+                                                        unsigned long long* total) {
+    const u32 stride = gridDim.x * blockDim.x;
+    unsigned long long t = 0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u32 o = pk[i] - kmin;
+        if (o < range) t += (unsigned long long)(__ldg(off + o + 1) - __ldg(off + o));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(total, t);
+}
+void launch_csr_total(const u32* pkeys, u32 n, const CsrTab& tab, unsigned long long* total, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    csr_total_kernel<<<grid, 256, 0, st>>>(pkeys, n, tab.off, tab.kmin, tab.range, total);
+}
+
+// One tile = 1024 probe rows staged by TMA. Pass 1: every row reads its directory entry (begin, count); the counts are scanned over the
+// tile. Pass 2: output row r of the tile belongs to the probe row whose prefix range holds r (binary search in shared memory), so
+// consecutive threads write consecutive output rows and read consecutive payload rows.
+__global__ void __launch_bounds__(PROBEG_THREADS) probe_grouped_kernel(const __grid_constant__ ProbeGParams P) {
+    extern __shared__ __align__(128) u32 smem[];  // n_pcols tiles, then begin[TILE], pref[TILE]
+    u32* s_begin = smem + P.n_pcols * PROBEG_TILE;
+    u32* s_pref = s_begin + PROBEG_TILE;
+    __shared__ __align__(8) u64 bar;
+    __shared__ u32 s_tile;
+    __shared__ u32 s_w[PROBEG_THREADS / 32 + 1];
+    __shared__ u32 s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    u32 parity = 0;
+    const u32* sKey = smem + P.pkey * PROBEG_TILE;
+    for (;;) {
+        __syncthreads();  // the previous tile's expansion has finished reading shared memory
+        if (tid == 0) {
+            const u32 t = atomicAdd(P.ticket, 1u);
+            s_tile = t;
+            if (t < P.n_tiles) {
+                const u32 b = t * (u32)PROBEG_TILE;
+                const u32 c = min((u32)PROBEG_TILE, P.n - b);
+                const u32 bytes = (c * 4u + 15u) & ~15u;
+                mbar_arrive_expect_tx(&bar, bytes * P.n_pcols);
+                for (u32 q = 0; q < P.n_pcols; q++) tma_load_1d(smem + q * PROBEG_TILE, P.pcol[q] + b, bytes, &bar);
+            }
+        }
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const u32 cnt = min((u32)PROBEG_TILE, P.n - tile * (u32)PROBEG_TILE);
+        mbar_wait(&bar, parity);
+        parity ^= 1u;
+        // pass 1: directory reads (all of a thread's rows in flight together), warp-local exclusive scan in row order
+        u32 b[PROBEG_ITEMS], c[PROBEG_ITEMS];
+#pragma unroll
+        for (int j = 0; j < PROBEG_ITEMS; j++) {
+            const u32 idx = (u32)warp * (32u * PROBEG_ITEMS) + (u32)j * 32u + (u32)lane;
+            const u32 o = sKey[idx] - P.tab.kmin;
+            const bool ok = idx < cnt && o < P.tab.range;
+            b[j] = ok ? __ldg(P.tab.off + o) : 0u;
+            c[j] = ok ? __ldg(P.tab.off + o + 1) : 0u;
+        }
+        u32 run = 0;
+#pragma unroll
+        for (int j = 0; j < PROBEG_ITEMS; j++) {
+            const u32 idx = (u32)warp * (32u * PROBEG_ITEMS) + (u32)j * 32u + (u32)lane;
+            const u32 n_match = c[j] - b[j];
+            u32 incl = n_match;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            s_begin[idx] = b[j];
+            s_pref[idx] = run + incl - n_match;  // exclusive within the warp's 128 rows; the warp base is added below
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) s_w[warp] = run;
+        __syncthreads();
+        if (warp == 0) {
+            const u32 w = lane < PROBEG_THREADS / 32 ? s_w[lane] : 0u;
+            u32 wi = w;
+#pragma unroll
+            for (int o = 1; o < PROBEG_THREADS / 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += y;
+            }
+            const u32 total = __shfl_sync(0xffffffffu, wi, PROBEG_THREADS / 32 - 1);
+            if (lane < PROBEG_THREADS / 32) s_w[lane] = wi - w;
+            if (lane == 0) s_w[PROBEG_THREADS / 32] = total;
+            const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
+            if (lane == 0) s_base = ex;
+        }
+        __syncthreads();
+        {
+            const u32 wb = s_w[warp];
+#pragma unroll
+            for (int j = 0; j < PROBEG_ITEMS; j++) s_pref[(u32)warp * (32u * PROBEG_ITEMS) + (u32)j * 32u + (u32)lane] += wb;
+        }
+        __syncthreads();
+        // pass 2: load-balanced expansion
+        const u32 total = s_w[PROBEG_THREADS / 32];
+        const u32 gbase = s_base;
+        for (u32 r = (u32)tid; r < total; r += PROBEG_THREADS) {
+            u32 lo = 0, hi = PROBEG_TILE - 1;  // largest idx with pref[idx] <= r
+#pragma unroll
+            for (int step = 0; step < 10; step++) {
+                const u32 mid = (lo + hi + 1u) >> 1;
+                if (s_pref[mid] <= r) lo = mid; else hi = mid - 1u;
+            }
+            const u32 src = lo;
+            const u32 brow = s_begin[src] + (r - s_pref[src]);
+            const u32 pos = gbase + r;
+            if (pos < P.cap) {
+                for (u32 q = 0; q < P.n_pcols; q++) P.out[q][pos] = smem[q * PROBEG_TILE + src];
+                for (u32 q = 0; q < P.tab.n_pay; q++) P.out[P.n_pcols + q][pos] = __ldg(P.tab.pay[q] + brow);
+            }
+        }
+    }
+}
+void launch_probe_grouped(const ProbeGParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    const size_t smem = (size_t)(p.n_pcols + 2) * PROBEG_TILE * sizeof(u32);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(probe_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = grid_for((const void*)probe_grouped_kernel, PROBEG_THREADS, smem, n_sms, p.n_tiles);
+    probe_grouped_kernel<<<grid, PROBEG_THREADS, smem, st>>>(p);
+}
+
 // cartesian product: output row (i*nr + j) = left row i ++ right row j (engine.rs:1054-1071)
 struct CartParams {
     const u32* l[KB_MAX_COLS];
@@ -1592,15 +1836,19 @@ __global__ void __launch_bounds__(256) derive_kernel(const __grid_constant__ Der
     const u32 n_round = (P.n + 31u) & ~31u;
     unsigned long long nd = 0;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        const bool pass = i < P.n && rule_filters_pass(P, i);
+        bool pass = i < P.n && rule_filters_pass(P, i);
         bool fresh = false;
         u32 s = 0, o = 0;
+        if (pass) nd++;
+        if (pass && *reinterpret_cast<volatile u32*>(P.out_count) >= P.budget) {  // the set must grow first; this launch is run again
+            *P.overflow = 2u;
+            pass = false;
+        }
         if (pass) {
-            nd++;
             s = P.head_s.is_var ? P.bcol[P.head_s.value][i] : P.head_s.value;
             o = P.head_o.is_var ? P.bcol[P.head_o.value][i] : P.head_o.value;
             const u32 r = set64_insert(P.set, P.set_slots, s, o);
-            if (r == 2u) *P.overflow = 1u;
+            if (r == 2u) atomicMax(P.overflow, 1u);
             fresh = r == 1u;
         }
         const unsigned b = __ballot_sync(0xffffffffu, fresh);  // warp-aggregated append of the facts that were new

@@ -233,6 +233,43 @@ struct ProbeCParams {
 };
 void launch_probe_chained(const ProbeCParams& p, int n_sms, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------------------------
+// K_build / K_probe (grouped): 1:N equi-join on ONE key column whose ids are dense. The build side is grouped by key into a CSR
+// directory — off[key - kmin] .. off[key - kmin + 1] delimit the key's rows in payload columns permuted into key order — so a probe
+// is two directory reads and a contiguous run of payload, and the expansion can hand consecutive OUTPUT rows to consecutive threads
+// (coalesced stores). Replaces the (tag, head) + next[] chains wherever the key range allows; same bag of rows as
+// perform_hash_join_for_rules (join_algorithm.rs:499-677) / execute_hash_join_with_ids (engine.rs:710-811).
+struct CsrTab {
+    const u32* off;  // [range + 1]
+    u32 kmin, range;
+    u32 n_pay;
+    const u32* pay[KB_MAX_COLS];  // payload columns in key order
+};
+void launch_csr_count(const u32* keys, u32 n, u32 kmin, u32* counts, int n_sms, cudaStream_t st);
+// in-place exclusive prefix sum of a[0..n) (n >= 1); scratch holds ceil(n / 2048) + 1 words
+void launch_exclusive_scan_u32(u32* a, u32 n, u32* scratch, cudaStream_t st);
+void launch_csr_fill(const u32* keys, u32 n, u32 kmin, u32* cursor, const u32* const* pay_in, u32* const* pay_out, u32 n_pay, int n_sms, cudaStream_t st);
+void launch_csr_total(const u32* pkeys, u32 n, const CsrTab& tab, unsigned long long* total, int n_sms, cudaStream_t st);
+constexpr int PROBEG_THREADS = 256;
+constexpr int PROBEG_ITEMS = 4;
+constexpr int PROBEG_TILE = PROBEG_THREADS * PROBEG_ITEMS;
+struct ProbeGParams {
+    const u32* pcol[KB_MAX_COLS];
+    u32 n_pcols, n, n_tiles;
+    u32 pkey;  // probe column holding the key
+    CsrTab tab;
+    u32* out[KB_MAX_COLS];  // n_pcols probe columns, then tab.n_pay payload columns
+    u32 cap;
+    u64* tile_state;
+    u64* block_state;
+    u32 ordered;
+    u32* ticket;
+    u64 epoch;
+    u32* total;
+    const u32* zero_word;
+};
+void launch_probe_grouped(const ProbeGParams& p, int n_sms, cudaStream_t st);
+
 // cartesian product (engine.rs:1054-1071) — small inputs only
 void launch_cartesian(const u32* const* lcols, u32 nl, u32 n_lcols, const u32* const* rcols, u32 nr, u32 n_rcols, u32* const* out,
                       cudaStream_t st);
@@ -274,9 +311,10 @@ struct DeriveParams {
     u32 set_slots;  // power of two
     u32 *out_s, *out_o;
     u32 out_cap;
+    u32 budget;                   // stop inserting once this many facts were appended (keeps the set's load bounded): overflow = 2
     u32* out_count;               // appended so far (atomic cursor)
     unsigned long long* n_deriv;  // candidates that passed the filters
-    u32* overflow;                // set or output overflow
+    u32* overflow;                // 1: set or output full (error); 2: budget reached, the host grows the set and runs the launch again
 };
 void launch_derive(const DeriveParams& p, int n_sms, cudaStream_t st);
 void launch_set64_insert(u64* set, u32 set_slots, const u32* s, const u32* o, u32 n, u32* overflow, int n_sms, cudaStream_t st);

@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+echo "== pytest gpu datalog/rsp/cpp"; timeout 1200 python -m pytest tests -m gpu -x -q -k "datalog or fc or taxonomy or rsp or cpp or known" 2>&1 | tail -5
+KOLIBRIE_TRACE=1 timeout 600 python scripts/datalog_trace.py 2>&1 | tail -150 > gpurun_out/dl_trace2.txt; grep "wall" gpurun_out/dl_trace2.txt
+timeout 600 python scripts/datalog_trace.py 2>&1 | tail -6
+echo "== extra cfg4"; timeout 900 python bench_extra.py --only cfg4 2>&1 | grep "^{" | cut -c1-400

@@ -101,3 +101,24 @@ def test_rule_filters_and_constants_quirks(ctx):
     want2 = O.Db(facts[:, 0], facts[:, 1], facts[:, 2], *d.numeric_table()).fixpoint([compile_rule(x) for x in r.rules], c.SEMI_NAIVE_PARALLEL)
     assert got2 == {tuple(int(v) for v in row) for row in want2["facts"]}
     assert (b, human, yes) not in got2 and (b, adult, yes) in got2
+
+
+def test_known_fact_set_grows_mid_launch(ctx):
+    """a head predicate that starts empty and receives 4 M new facts from ONE launch: the known-fact set is sized for an expected
+    doubling (at least 2^20 facts), the derive launch stops at its budget, the set is rebuilt larger with the facts appended so far
+    and the launch is repeated — every fact must still come out exactly once"""
+    n = 4_000_000
+    s = np.arange(10, 10 + n, dtype=np.uint32)
+    o = (s * np.uint32(7) + np.uint32(3)) % np.uint32(1 << 22) + np.uint32(10)
+    p = np.full(n, 5, np.uint32)
+    ctx.store_load(s, p, o)
+    rule = {"premise": [c.pattern(c.V(0), c.K(5), c.V(1))], "conclusion": [c.pattern(c.V(1), c.K(6), c.V(0))], "filters": []}
+    rel, st = ctx.datalog_fixpoint([rule], c.SEMI_NAIVE)
+    assert st.inferred == n and st.rounds == 1 and st.derivations == n
+    got = rel.to_numpy([0, 1, 2])
+    assert (got[:, 1] == 6).all()
+    order = np.argsort(got[:, 2], kind="stable")
+    assert np.array_equal(got[order, 2], s) and np.array_equal(got[order, 0], o)
+    # a second run over the store (which now holds the inferred facts) derives nothing
+    rel2, st2 = ctx.datalog_fixpoint([rule], c.SEMI_NAIVE)
+    assert st2.inferred == 0

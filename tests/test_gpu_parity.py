@@ -192,6 +192,41 @@ def test_hash_join_shapes_vs_oracle(ctx, seed):
         H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"{ls}x{rs}")
 
 
+@pytest.mark.parametrize("csr", ["1", "0"])
+def test_join_fanout_grouped_and_chained(csr, monkeypatch):
+    """1:N / N:M joins with skewed fan-out through BOTH multimap layouts: the key-grouped (CSR) directory (default for one dense key
+    column) and the chained table (KOLIBRIE_CSR_JOIN=0, and always for sparse key ranges / several key columns)"""
+    monkeypatch.setenv("KOLIBRIE_CSR_JOIN", csr)
+    cx = c.Context(0)
+    try:
+        rng = np.random.default_rng(17)
+
+        def both(slots, cols):
+            cols = [np.ascontiguousarray(x, dtype=np.uint32) for x in cols]
+            return cx.rel_from_host(slots, cols), O.rel_from_host(slots, cols)
+
+        hot = np.full(700, 77, np.uint32)  # one key with 700 build rows ...
+        bkeys = np.concatenate([hot, rng.integers(0, 5000, 20000).astype(np.uint32)])
+        pkeys = np.concatenate([np.full(2000, 77, np.uint32), rng.integers(0, 9000, 40000).astype(np.uint32)])  # ... probed 2000 times; keys 5000..8999 miss
+        cases = {
+            "skewed 1:N": (((0, 1), [bkeys, rng.integers(0, 1 << 20, len(bkeys))]), ((0, 2, 3), [pkeys, rng.integers(0, 50, len(pkeys)), rng.integers(0, 50, len(pkeys))])),
+            "key-only build side": (((0,), [bkeys[:3000]]), ((0, 2), [pkeys[:5000], rng.integers(0, 50, 5000)])),
+            "sparse key range": (((0, 1), [bkeys * 100003, bkeys]), ((0, 2), [pkeys * 100003, pkeys])),
+            "single row each": (((0, 1), [[5], [6]]), ((0, 2), [[5], [7]])),
+            "no key in common": (((0, 1), [[1, 2, 3], [4, 5, 6]]), ((0, 2), [[7, 8], [9, 9]])),
+            "exact tile multiples": (((0, 1), [np.arange(2048) % 64, np.arange(2048)]), ((0, 2), [np.arange(1024) % 128, np.arange(1024)])),
+        }
+        for name, ((ls, lc), (rs, rc)) in cases.items():
+            (gl, ol), (gr, orr) = both(ls, lc), both(rs, rc)
+            for a, b, oa, ob in ((gl, gr, ol, orr), (gr, gl, orr, ol)):
+                got = cx.hash_join(a, b)
+                want = O.hash_join(oa, ob)
+                assert sorted(got.slots) == sorted(want.slots)
+                H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"{name} (csr={csr})")
+    finally:
+        cx.close()
+
+
 def test_bgp_path_join_vs_oracle(ctx):
     """object->subject path (no star variable): scan all patterns in one pass, then chained joins"""
     tr = random_store(11, 20000, n_terms=400, n_preds=4)
