@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--query", default="cfg2", choices=["cfg2", "star3", "cfg3", "cfg1"])
     ap.add_argument("--cpu-sample", type=int, default=300_000, help="employees in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-index", action="store_true", help="headline on the store-scanning path (no predicate-partitioned index)")
     return ap.parse_args()
@@ -161,6 +162,44 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_near_gpu(local):
+    """Run this rank (and first-touch the pinned buffers it allocates) on the NUMA node its GPU hangs off: host<->device copies of the
+    e2e leg then stay on one socket. Returns (previous affinity, node or None); placement only, no effect on results."""
+    try:
+        prev = os.sched_getaffinity(0)
+    except (AttributeError, OSError):
+        return None, None
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+            bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()[-12:]
+        except Exception:
+            return prev, None
+    try:
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return prev, None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= prev
+        if not cpus:
+            return prev, None
+        os.sched_setaffinity(0, cpus)
+        return prev, node
+    except (OSError, ValueError):
+        return prev, None
+
+
 def workload_name(args):
     q = {"cfg2": "3-pattern star BGP (?e title ?t . ?e annual_salary ?s . ?e name ?n) + FILTER(?s > 100000)",
          "star3": "3-pattern star BGP (?e title ?t . ?e annual_salary ?s . ?e name ?n), no FILTER",
@@ -187,6 +226,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: kolibrie_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    prev_affinity, numa_node = (None, None) if args.no_numa else bind_near_gpu(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -364,7 +404,7 @@ def main():
                    "l2": "inputs per step (index path: 0.4 GB of predicate slices + 0.13 GB of tables; scan path: 1.2 GB of triple columns) exceed the 126 MB L2; no explicit flush",
                    "store": ("predicate-partitioned index built ONCE at load by kb_store_build_index (= SparqlDatabase::build_all_indexes), %d predicates, %.1f ms, outside the timed region"
                              % (n_pred, index_ms)) if not args.no_index else "unindexed: every step scans the store",
-                   "datagen_s": round(t_gen, 1),
+                   "datagen_s": round(t_gen, 1), "host_numa_node": numa_node,
                    "timing": "wall clock around K steps between barrier+synchronize, max over ranks; every step ends with a stream sync inside the library"},
         "roofline": roofline,
         "gpu_launches": int(st["kernel_launches"]),
@@ -376,6 +416,8 @@ def main():
         line["e2e"] = {"value": rows_all / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                        "ms_per_step": dte / args.steps * 1e3, "api": "kb_star_join_host (pinned host columns in, pinned host binding columns out; chunked upload overlapped with the scan)"}
     if world == 1 and not args.no_cpu:
+        if prev_affinity:
+            os.sched_setaffinity(0, prev_affinity)  # the CPU arm gets every host thread back
         base, _ = cpu_reference_run(args, steps=5, warmup=1)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_columnar_openmp"] = base["columnar_openmp"]

@@ -47,52 +47,45 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
     __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
     constexpr int NW = (K + 2) / 3;  // packed count words: three 10-bit fields each (a warp holds at most 256 matches per pattern)
 
+    __shared__ u32 s_tcnt, s_tindex;  // triples in the staged tile, global index of its first triple
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // thread 0: take the next tile, find its segment, start the three column copies
+    auto issue_next = [&]() {
+        const u32 t = atomicAdd(P.ticket, 1u);
+        s_next = t;
+        if (t < P.n_tiles) {
+            u32 g = 0;
+            while (g + 1u < P.n_seg && t >= P.seg[g + 1u].tile0) g++;
+            const ScanSeg& sg = P.seg[g];
+            const u32 b = (t - sg.tile0) * (u32)SCAN_TILE;
+            const u32 c = min((u32)SCAN_TILE, sg.n - b);
+            const u32 bytes = (c * 4u + 15u) & ~15u;  // columns are padded to 256 B: the rounded-up read stays in bounds
+            s_tcnt = c;
+            s_tindex = sg.index_base + b;
+            mbar_arrive_expect_tx(&bar, bytes * 3u);
+            tma_load_1d(smem, sg.s + b, bytes, &bar);
+            tma_load_1d(smem + SCAN_TILE, sg.p + b, bytes, &bar);
+            tma_load_1d(smem + 2 * SCAN_TILE, sg.o + b, bytes, &bar);
+        }
+    };
     if (tid == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
+        issue_next();
     }
     __syncthreads();
-    u32 tile = 0;
-    if (tid == 0) {
-        tile = atomicAdd(P.ticket, 1u);
-        s_next = tile;
-        if (tile < P.n_tiles) {
-            const u32 base = tile * (u32)SCAN_TILE;
-            const u32 cnt = min((u32)SCAN_TILE, P.n - base);
-            const u32 bytes = (cnt * 4u + 15u) & ~15u;  // columns are padded to 256 B: the rounded-up read stays in bounds
-            mbar_arrive_expect_tx(&bar, bytes * 3u);
-            tma_load_1d(smem, P.s + base, bytes, &bar);
-            tma_load_1d(smem + SCAN_TILE, P.p + base, bytes, &bar);
-            tma_load_1d(smem + 2 * SCAN_TILE, P.o + base, bytes, &bar);
-        }
-    }
-    __syncthreads();
-    tile = s_next;
+    u32 tile = s_next;
     u32 parity = 0;
 
     while (tile < P.n_tiles) {
-        const u32 base = tile * (u32)SCAN_TILE;
-        const u32 cnt = min((u32)SCAN_TILE, P.n - base);
         mbar_wait(&bar, parity);
         parity ^= 1u;
         const uint4 s0 = sS4[2 * tid], s1 = sS4[2 * tid + 1];
         const uint4 p0 = sP4[2 * tid], p1 = sP4[2 * tid + 1];
         const uint4 o0 = sO4[2 * tid], o1 = sO4[2 * tid + 1];
+        const u32 cnt = s_tcnt, tindex = s_tindex;
         __syncthreads();  // every thread holds its triples in registers: the buffer can take the next tile
-        if (tid == 0) {
-            const u32 nt = atomicAdd(P.ticket, 1u);
-            s_next = nt;
-            if (nt < P.n_tiles) {
-                const u32 nb = nt * (u32)SCAN_TILE;
-                const u32 nc = min((u32)SCAN_TILE, P.n - nb);
-                const u32 bytes = (nc * 4u + 15u) & ~15u;
-                mbar_arrive_expect_tx(&bar, bytes * 3u);
-                tma_load_1d(smem, P.s + nb, bytes, &bar);
-                tma_load_1d(smem + SCAN_TILE, P.p + nb, bytes, &bar);
-                tma_load_1d(smem + 2 * SCAN_TILE, P.o + nb, bytes, &bar);
-            }
-        }
+        if (tid == 0) issue_next();
         // ---- match: bit j of mk[k] = triple 8*tid+j matches pattern k
         const u32 first = (u32)tid * 8u;
         const u32 vmask = first >= cnt ? 0u : (cnt - first >= 8u ? 0xFFu : ((1u << (cnt - first)) - 1u));
@@ -225,7 +218,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
             if (f & SP_EMIT_IDX) {
                 u32* out = P.pat[k].outp[3] + pos;
 #pragma unroll
-                for (int j = 0; j < 8; j++) { if ((m >> j) & 1u) *out = P.index_base + base + first + (u32)j; out += (m >> j) & 1u; }
+                for (int j = 0; j < 8; j++) { if ((m >> j) & 1u) *out = tindex + first + (u32)j; out += (m >> j) & 1u; }
             }
         }
         tile = s_next;  // written before this iteration's barriers, stable since
@@ -239,7 +232,7 @@ static void launch_scan_k(const ScanParams& p, int n_sms, cudaStream_t st) {
     scan_kernel<K><<<grid, SCAN_THREADS, smem, st>>>(p);
 }
 void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st) {
-    if (p.n == 0) return;
+    if (p.n_tiles == 0) return;
     switch (p.K) {
         case 1: launch_scan_k<1>(p, n_sms, st); break;
         case 2: launch_scan_k<2>(p, n_sms, st); break;

@@ -33,10 +33,17 @@ struct ScanPat {
     u32* outp[4];        // output column of position s / p / o / index (null when not emitted)
     u32 f_begin, f_len;  // pushed-down FILTER program (slots = positions 0/1/2)
 };
-struct ScanParams {
+constexpr int SCAN_MAXSEG = 16;  // store segments one launch can walk (an RSP window of slides is scanned in ONE launch)
+struct ScanSeg {
     const u32 *s, *p, *o;
-    u32 n, n_tiles, K;
-    u32 index_base;  // global index of this segment's first triple
+    u32 n;           // triples
+    u32 tile0;       // first tile of this segment in the launch's tile numbering
+    u32 index_base;  // global index of the segment's first triple
+};
+struct ScanParams {
+    ScanSeg seg[SCAN_MAXSEG];
+    u32 n_seg;
+    u32 n_tiles, K;  // n_tiles: over all segments of the launch
     u32 cshift;      // SP_TABLE patterns: log2(world) key compaction of a subject-sharded store (0 = none)
     ScanPat pat[MAXP];
     FilterOp ops[KB_MAX_FILTER_OPS];

@@ -94,6 +94,17 @@ def test_scan_multi_segment_and_evict(ctx):
     keep = np.array(sorted(set(map(tuple, rest.tolist())) - set(map(tuple, dele.tolist()))), dtype=np.uint32)
     s, p, o = ctx.store_download()
     H.assert_same_bag(np.stack([s, p, o], axis=1), keep, "store after delete")
+    # more segments than one scan launch walks (16), of ragged sizes, one of them empty: a star join over the window
+    tr2 = random_store(6, 60000, n_terms=3000)
+    cuts = sorted(np.random.default_rng(1).choice(np.arange(1, len(tr2)), 22, replace=False).tolist())
+    ctx.store_clear()
+    for i, pt in enumerate(np.split(tr2, cuts[:10] + [cuts[10], cuts[10]] + cuts[11:])):
+        ctx.store_append(pt[:, 0], pt[:, 1], pt[:, 2], tag=500 + i)
+    assert ctx.store_size() == (len(tr2), 24)
+    db2 = O.Db(tr2[:, 0], tr2[:, 1], tr2[:, 2])
+    assert same(ctx.scan([pat])[0].to_numpy(), db2.scan(pat).to_numpy())
+    pats = [c.pattern(c.V(0), c.K(100), c.V(1)), c.pattern(c.V(0), c.K(101), c.V(2))]
+    H.assert_same_bag(ctx.star_join(0, pats).to_numpy([0, 1, 2]), db2.bgp(pats).to_numpy([0, 1, 2]), "24-segment window")
 
 
 def test_filter_programs_vs_oracle(ctx, emp):
