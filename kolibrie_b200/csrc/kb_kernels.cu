@@ -37,22 +37,22 @@ __device__ __forceinline__ u32 eqv8(const uint4& a0, const uint4& a1, const uint
 
 template <int K>
 __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 512 / SCAN_THREADS)) scan_kernel(const __grid_constant__ ScanParams P) {
-    extern __shared__ __align__(128) u32 smem[];
-    const uint4* sS4 = reinterpret_cast<const uint4*>(smem);
-    const uint4* sP4 = reinterpret_cast<const uint4*>(smem + SCAN_TILE);
-    const uint4* sO4 = reinterpret_cast<const uint4*>(smem + 2 * SCAN_TILE);
-    __shared__ __align__(8) u64 bar;
-    __shared__ u32 s_next;
+    // two shared stages of three column tiles each: tile i+1 is in flight while tile i is processed; the stage of tile i is handed
+    // back to TMA (for tile i+2) right after the first compaction barrier — every thread has its triples in registers by then, so
+    // the hand-over costs no barrier of its own
+    extern __shared__ __align__(128) u32 smem_all[];
+    constexpr u32 STAGE_WORDS = 3u * SCAN_TILE;
+    __shared__ __align__(8) u64 bars[2];
+    __shared__ u32 s_nexts[2];
     __shared__ u32 s_wcnt[SCAN_THREADS / 32][MAXP];
     __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
     constexpr int NW = (K + 2) / 3;  // packed count words: three 10-bit fields each (a warp holds at most 256 matches per pattern)
-
-    __shared__ u32 s_tcnt, s_tindex;  // triples in the staged tile, global index of its first triple
+    __shared__ u32 s_tcnt[2], s_tindex[2];  // triples in the staged tile, global index of its first triple
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // thread 0: take the next tile, find its segment, start the three column copies
-    auto issue_next = [&]() {
+    // one thread: take the next tile, find its segment, start the three column copies into `stage`
+    auto issue_next = [&](u32 stage) {
         const u32 t = atomicAdd(P.ticket, 1u);
-        s_next = t;
+        s_nexts[stage] = t;
         if (t < P.n_tiles) {
             u32 g = 0;
             while (g + 1u < P.n_seg && t >= P.seg[g + 1u].tile0) g++;
@@ -60,32 +60,36 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
             const u32 b = (t - sg.tile0) * (u32)SCAN_TILE;
             const u32 c = min((u32)SCAN_TILE, sg.n - b);
             const u32 bytes = (c * 4u + 15u) & ~15u;  // columns are padded to 256 B: the rounded-up read stays in bounds
-            s_tcnt = c;
-            s_tindex = sg.index_base + b;
-            mbar_arrive_expect_tx(&bar, bytes * 3u);
-            tma_load_1d(smem, sg.s + b, bytes, &bar);
-            tma_load_1d(smem + SCAN_TILE, sg.p + b, bytes, &bar);
-            tma_load_1d(smem + 2 * SCAN_TILE, sg.o + b, bytes, &bar);
+            s_tcnt[stage] = c;
+            s_tindex[stage] = sg.index_base + b;
+            u32* dst = smem_all + stage * STAGE_WORDS;
+            mbar_arrive_expect_tx(&bars[stage], bytes * 3u);
+            tma_load_1d(dst, sg.s + b, bytes, &bars[stage]);
+            tma_load_1d(dst + SCAN_TILE, sg.p + b, bytes, &bars[stage]);
+            tma_load_1d(dst + 2 * SCAN_TILE, sg.o + b, bytes, &bars[stage]);
         }
     };
     if (tid == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
         fence_mbar_init();
-        issue_next();
+        issue_next(0);
+        issue_next(1);
     }
     __syncthreads();
-    u32 tile = s_next;
-    u32 parity = 0;
+    u32 tile = s_nexts[0];
+    u32 it = 0;
 
     while (tile < P.n_tiles) {
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
+        const u32 stage = it & 1u;
+        mbar_wait(&bars[stage], (it >> 1) & 1u);
+        const uint4* sS4 = reinterpret_cast<const uint4*>(smem_all + stage * STAGE_WORDS);
+        const uint4* sP4 = sS4 + SCAN_TILE / 4;
+        const uint4* sO4 = sS4 + 2 * (SCAN_TILE / 4);
         const uint4 s0 = sS4[2 * tid], s1 = sS4[2 * tid + 1];
         const uint4 p0 = sP4[2 * tid], p1 = sP4[2 * tid + 1];
         const uint4 o0 = sO4[2 * tid], o1 = sO4[2 * tid + 1];
-        const u32 cnt = s_tcnt, tindex = s_tindex;
-        __syncthreads();  // every thread holds its triples in registers: the buffer can take the next tile
-        if (tid == 0) issue_next();
+        const u32 cnt = s_tcnt[stage], tindex = s_tindex[stage];
         // ---- match: bit j of mk[k] = triple 8*tid+j matches pattern k
         const u32 first = (u32)tid * 8u;
         const u32 vmask = first >= cnt ? 0u : (cnt - first >= 8u ? 0xFFu : ((1u << (cnt - first)) - 1u));
@@ -151,6 +155,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
             }
         }
         __syncthreads();
+        const u32 following = s_nexts[stage ^ 1u];  // the next iteration's tile (its copies are already in flight)
+        if (tid == SCAN_THREADS - 1) issue_next(stage);
         if (warp < K) {  // warp k owns counter k: cross-warp prefix of its per-warp totals, then the look-back across tiles
             const u32 c = lane < SCAN_THREADS / 32 ? s_wcnt[lane][warp] : 0u;
             u32 incl = c;
@@ -221,13 +227,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
                 for (int j = 0; j < 8; j++) { if ((m >> j) & 1u) *out = tindex + first + (u32)j; out += (m >> j) & 1u; }
             }
         }
-        tile = s_next;  // written before this iteration's barriers, stable since
+        tile = following;
+        it++;
     }
 }
 
 template <int K>
 static void launch_scan_k(const ScanParams& p, int n_sms, cudaStream_t st) {
-    const size_t smem = 3 * SCAN_TILE * sizeof(u32);
+    const size_t smem = 2 * 3 * SCAN_TILE * sizeof(u32);  // two stages: 48 KB, above the default dynamic limit
+    cudaFuncSetAttribute(scan_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = grid_for((const void*)scan_kernel<K>, SCAN_THREADS, smem, n_sms, p.n_tiles);
     scan_kernel<K><<<grid, SCAN_THREADS, smem, st>>>(p);
 }
@@ -522,40 +530,43 @@ void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_
 template <int T>
 __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) probe_fast_kernel(const __grid_constant__ ProbeFParams P) {
     constexpr int R = PROBEF_ITEMS;  // rows per thread, consecutive
-    extern __shared__ __align__(128) u32 smem[];  // PROBEF_TILE pairs
-    __shared__ __align__(8) u64 bar;
-    __shared__ u32 s_next;
+    extern __shared__ __align__(128) u32 smem_all[];  // two stages of PROBEF_TILE pairs (see probe_index_kernel)
+    constexpr u32 STAGE_WORDS = 2u * PROBEF_TILE;
+    __shared__ __align__(8) u64 bars[2];
+    __shared__ u32 s_nexts[2];
     __shared__ u32 s_wcnt[PROBEF_THREADS / 32];
     __shared__ u32 s_excl1;
     if (P.abort_flag != nullptr) {
         for (int t = 0; t < T; t++) if (reinterpret_cast<const volatile u32*>(P.abort_flag)[t] != 0u) return;
     }
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    u32 tile = 0;
-    if (tid == 0) {
-        tile = atomicAdd(P.ticket, 1u);
-        s_next = tile;
-        if (tile < P.n_tiles) {
-            const u32 base = tile * (u32)PROBEF_TILE;
-            const u32 cnt = min((u32)PROBEF_TILE, P.n - base);
-            const u32 bytes = (cnt * 8u + 15u) & ~15u;
-            mbar_arrive_expect_tx(&bar, bytes);
-            tma_load_1d(smem, P.pairs + base, bytes, &bar);
+    auto issue_next = [&](u32 stage) {
+        const u32 t = atomicAdd(P.ticket, 1u);
+        s_nexts[stage] = t;
+        if (t < P.n_tiles) {
+            const u32 b = t * (u32)PROBEF_TILE;
+            const u32 c = min((u32)PROBEF_TILE, P.n - b);
+            const u32 bytes = (c * 8u + 15u) & ~15u;
+            mbar_arrive_expect_tx(&bars[stage], bytes);
+            tma_load_1d(smem_all + stage * STAGE_WORDS, P.pairs + b, bytes, &bars[stage]);
         }
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+        issue_next(0);
+        issue_next(1);
     }
     __syncthreads();
-    tile = s_next;
-    u32 parity = 0;
+    u32 tile = s_nexts[0];
+    u32 it = 0;
     while (tile < P.n_tiles) {
+        const u32 stage = it & 1u;
+        const u32* smem = smem_all + stage * STAGE_WORDS;
         const u32 base = tile * (u32)PROBEF_TILE;
         const u32 cnt = min((u32)PROBEF_TILE, P.n - base);
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
+        mbar_wait(&bars[stage], (it >> 1) & 1u);
         // striped: row j of this thread is row (warp*32*R + j*32 + lane) of the tile — one warp instruction touches 32 consecutive rows, so
         // lookups by a sorted key hit 4 sectors instead of 16 and the compacted stores of one j form one contiguous run
         u32 rx[R], ry[R];
@@ -563,18 +574,6 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
         for (int j = 0; j < R; j++) {
             const uint2 v = reinterpret_cast<const uint2*>(smem)[(u32)warp * (32u * R) + (u32)j * 32u + (u32)lane];
             rx[j] = v.x; ry[j] = v.y;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const u32 nt = atomicAdd(P.ticket, 1u);
-            s_next = nt;
-            if (nt < P.n_tiles) {
-                const u32 nb = nt * (u32)PROBEF_TILE;
-                const u32 nc = min((u32)PROBEF_TILE, P.n - nb);
-                const u32 bytes = (nc * 8u + 15u) & ~15u;
-                mbar_arrive_expect_tx(&bar, bytes);
-                tma_load_1d(smem, P.pairs + nb, bytes, &bar);
-            }
         }
         const u32 row0 = (u32)warp * (32u * R) + (u32)lane;  // row j = row0 + 32*j
         u32 vmask = 0;
@@ -670,6 +669,8 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
         }
         if (lane == 0) s_wcnt[warp] = wtot;
         __syncthreads();
+        const u32 following = s_nexts[stage ^ 1u];
+        if (tid == 32) issue_next(stage);  // every thread holds its rows in registers: refill this stage with the tile after next
         if (warp == 0) {
             const u32 wc = lane < PROBEF_THREADS / 32 ? s_wcnt[lane] : 0u;
             u32 wi = wc;
@@ -702,13 +703,14 @@ __global__ void __launch_bounds__(PROBEF_THREADS, (PROBEF_ITEMS <= 4 ? 4 : 3)) p
                 }
             }
         }
-        tile = s_next;
+        tile = following;
+        it++;
     }
 }
 
 void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st) {
     if (p.n == 0) return;
-    const size_t smem = (size_t)PROBEF_TILE * sizeof(uint2);
+    const size_t smem = 2 * (size_t)PROBEF_TILE * sizeof(uint2);
     const void* fn = nullptr;
     switch (p.T) {
         case 1: fn = (const void*)probe_fast_kernel<1>; break;
@@ -734,13 +736,16 @@ template <int T, int PRE>
 __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel(const __grid_constant__ ProbeIParams P) {
     constexpr int R = 4;  // rows per thread (striped over the warp's 128-row chunk, see below)
     constexpr u32 TILE = PROBEF_THREADS * R;
-    extern __shared__ __align__(128) u32 smem[];  // TILE pairs [+ TILE doubles]
-    __shared__ __align__(8) u64 bar;
-    __shared__ u32 s_next;
+    extern __shared__ __align__(128) u32 smem_all[];  // per stage: TILE pairs [+ TILE doubles]
+    constexpr u32 STAGE_WORDS = (PRE == 1 ? 4u : 2u) * TILE;
+    __shared__ __align__(8) u64 bars[2];
+    __shared__ u32 s_nexts[2];
     __shared__ u32 s_wcnt[PROBEF_THREADS / 32];
     __shared__ u32 s_excl1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    auto issue = [&](u32 t) {
+    auto issue = [&](u32 t, u32 stage) {
+        u32* smem = smem_all + stage * STAGE_WORDS;
+        u64& bar = bars[stage];
         const u32 b = t * TILE;
         const u32 c = min(TILE, P.n - b);
         const u32 bytes = (c * 8u + 15u) & ~15u;
@@ -748,21 +753,27 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
         tma_load_1d(smem, P.pairs + b, bytes, &bar);
         if (PRE == 1) tma_load_1d(smem + 2 * TILE, P.ynum + b, bytes, &bar);
     };
+    // two shared stages: tile i+1 is in flight while tile i is processed, and the stage of tile i is refilled (tile i+2) right after
+    // the first compaction barrier — by then every thread has its rows in registers, so no barrier is spent on the hand-over
     if (tid == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
         fence_mbar_init();
-        const u32 t0 = atomicAdd(&P.cb[0], 1u);
-        s_next = t0;
-        if (t0 < P.n_tiles) issue(t0);
+        for (u32 st = 0; st < 2; st++) {
+            const u32 t0 = atomicAdd(&P.cb[0], 1u);
+            s_nexts[st] = t0;
+            if (t0 < P.n_tiles) issue(t0, st);
+        }
     }
     __syncthreads();
-    u32 tile = s_next;
-    u32 parity = 0;
+    u32 tile = s_nexts[0];
+    u32 it = 0;
     while (tile < P.n_tiles) {
+        const u32 stage = it & 1u;
+        const u32* smem = smem_all + stage * STAGE_WORDS;
         const u32 base = tile * TILE;
         const u32 cnt = min(TILE, P.n - base);
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
+        mbar_wait(&bars[stage], (it >> 1) & 1u);
         u32 rx[R], ry[R];
         double pa[R];
         // striped: row j of this thread is row (warp*128 + j*32 + lane) of the tile, so one warp instruction touches 32 CONSECUTIVE
@@ -774,12 +785,6 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
             const uint2 v = reinterpret_cast<const uint2*>(smem)[idx];
             rx[j] = v.x; ry[j] = v.y;
             if (PRE == 1) pa[j] = reinterpret_cast<const double*>(smem + 2 * TILE)[idx];
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const u32 nt = atomicAdd(&P.cb[0], 1u);
-            s_next = nt;
-            if (nt < P.n_tiles) issue(nt);
         }
         u32 vmask = 0;
 #pragma unroll
@@ -837,6 +842,12 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
         }
         if (lane == 0) s_wcnt[warp] = wtot;
         __syncthreads();
+        const u32 following = s_nexts[stage ^ 1u];  // tile of the next iteration (its copy is in flight)
+        if (tid == 32) {  // a lane outside the prefix warp refills this stage with the tile after that one
+            const u32 nt = atomicAdd(&P.cb[0], 1u);
+            s_nexts[stage] = nt;
+            if (nt < P.n_tiles) issue(nt, stage);
+        }
         if (warp == 0) {
             const u32 wc = lane < PROBEF_THREADS / 32 ? s_wcnt[lane] : 0u;
             u32 wi = wc;
@@ -866,7 +877,8 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
                 run += (u32)__popc(bal[j]);
             }
         }
-        tile = s_next;
+        tile = following;
+        it++;
     }
     // the last CTA to get here publishes the row count and leaves the control block zeroed for the next launch
     __syncthreads();
@@ -887,7 +899,7 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
 template <int T, int PRE>
 static void launch_probe_index_tp(const ProbeIParams& p, int n_sms, cudaStream_t st) {
     static int per_sm = 0;  // occupancy is a property of the kernel image: asked once per instantiation
-    const size_t smem = (size_t)PROBEF_THREADS * 4 * (PRE == 1 ? 16 : 8);
+    const size_t smem = (size_t)PROBEF_THREADS * 4 * (PRE == 1 ? 16 : 8) * 2;
     if (per_sm == 0) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_index_kernel<T, PRE>, PROBEF_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
