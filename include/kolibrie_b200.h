@@ -180,6 +180,18 @@ KB_API kb_status kb_store_size(kb_ctx* ctx, uint64_t* n_triples, uint32_t* n_seg
  * num_or0[id] = parse().unwrap_or(0.0); is_num[id] = parse().is_ok(). ids >= n_ids read as (0.0, not numeric). */
 KB_API kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t* is_num, uint32_t n_ids);
 
+/* Dictionary strings on the device + result decode: the id -> string step that ends ExecutionEngine::execute
+ * (kolibrie/src/streamertail_optimizer/execution/engine.rs:27-51) and Dictionary::decode (shared/src/dictionary.rs:50-52).
+ * String i is bytes[offsets[i] .. offsets[i+1]) (UTF-8, no terminator). */
+KB_API kb_status kb_dict_strings_load(kb_ctx* ctx, const uint64_t* offsets /* [n_ids + 1] */, const uint8_t* bytes, uint32_t n_ids);
+typedef struct kb_strings kb_strings; /* device-resident decoded column: offsets [n+1] + bytes */
+/* Decodes column `col` of `r`: row i becomes the string of its id; an id the dictionary does not hold becomes "unknown" (engine.rs:44).
+ * Quoted-triple ids (bit 31, shared/src/quoted_triple_store.rs:28-55) -> KB_E_UNSUPPORTED. At most 2^32-1 bytes per call. */
+KB_API kb_status kb_rel_decode(kb_ctx* ctx, const kb_rel* r, uint32_t col, kb_strings** out);
+KB_API kb_status kb_strings_info(const kb_strings* s, uint64_t* n_strings, uint64_t* total_bytes);
+KB_API kb_status kb_strings_download(kb_ctx* ctx, const kb_strings* s, uint64_t* offsets /* [n + 1] */, uint8_t* bytes /* total_bytes */);
+KB_API void kb_strings_free(kb_ctx* ctx, kb_strings* s);
+
 /* ------------------------------------------------------------------ relations */
 KB_API kb_status kb_rel_info(const kb_rel* r, uint64_t* n_rows, uint32_t* n_cols, uint32_t* slots /* [KB_MAX_COLS] or NULL */);
 KB_API kb_status kb_rel_download(kb_ctx* ctx, const kb_rel* r, uint32_t col, uint32_t* host_dst /* n_rows */);

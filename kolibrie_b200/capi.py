@@ -10,7 +10,7 @@ import atexit
 import ctypes as C
 import os
 import weakref
-from typing import Iterable, Optional, Sequence
+from typing import List, Iterable, Optional, Sequence
 
 import numpy as np
 
@@ -157,6 +157,11 @@ def lib() -> C.CDLL:
         "kb_store_size": (i32, [vp, P(u64), P(u32)]),
         "kb_store_download": (i32, [vp, vp, vp, vp, u64, P(u64)]),
         "kb_dict_numeric_load": (i32, [vp, vp, vp, u32]),
+        "kb_dict_strings_load": (i32, [vp, vp, vp, u32]),
+        "kb_rel_decode": (i32, [vp, vp, u32, P(vp)]),
+        "kb_strings_info": (i32, [vp, P(u64), P(u64)]),
+        "kb_strings_download": (i32, [vp, vp, vp, vp]),
+        "kb_strings_free": (None, [vp, vp]),
         "kb_rel_info": (i32, [vp, P(u64), P(u32), P(u32)]),
         "kb_rel_download": (i32, [vp, vp, u32, vp]),
         "kb_rel_device_col": (i32, [vp, u32, P(vp)]),
@@ -193,7 +198,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "kb_version", "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_set_timing", "kb_get_stats", "kb_synchronize",
     "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
-    "kb_store_download", "kb_dict_numeric_load", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
+    "kb_store_download", "kb_dict_numeric_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free",
     "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_star_join_host", "perform_hash_join_cuda",
@@ -235,6 +240,26 @@ class Relation:
         out = np.empty(n, dtype=np.uint32)
         self.ctx._check(lib().kb_rel_download(self.ctx.h, self.h, col, _ptr(out)))
         return out
+
+    def decode(self, col: int):
+        """kb_rel_decode: the column's ids as strings, decoded on the device. Returns (offsets uint64 [n+1], bytes uint8): string i
+        is bytes[offsets[i]:offsets[i+1]] (UTF-8); ids the dictionary does not hold read "unknown" (engine.rs:44)."""
+        h = C.c_void_p()
+        self.ctx._check(lib().kb_rel_decode(self.ctx.h, self.h, col, C.byref(h)))
+        try:
+            n, total = C.c_uint64(), C.c_uint64()
+            self.ctx._check(lib().kb_strings_info(h, C.byref(n), C.byref(total)))
+            off = np.empty(n.value + 1, dtype=np.uint64)
+            data = np.empty(total.value, dtype=np.uint8)
+            self.ctx._check(lib().kb_strings_download(self.ctx.h, h, _ptr(off), _ptr(data)))
+        finally:
+            lib().kb_strings_free(self.ctx.h, h)
+        return off, data
+
+    def decode_strings(self, col: int) -> List[str]:
+        off, data = self.decode(col)
+        raw = data.tobytes()
+        return [raw[int(off[i]):int(off[i + 1])].decode("utf-8") for i in range(len(off) - 1)]
 
     def device_ptr(self, col: int) -> int:
         p = C.c_void_p()
@@ -340,6 +365,16 @@ class Context:
         isn = np.ascontiguousarray(is_num, dtype=np.uint8)
         assert len(num) == len(isn)
         self._check(lib().kb_dict_numeric_load(self.h, _ptr(num), _ptr(isn), len(num)))
+
+    def dict_strings_load(self, strings: Sequence[str]):
+        """kb_dict_strings_load: string i = the term with dictionary id i (Dictionary::id_to_string, dictionary.rs:17-21)"""
+        enc = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in strings]
+        off = np.zeros(len(enc) + 1, dtype=np.uint64)
+        if enc:
+            off[1:] = np.cumsum([len(b) for b in enc], dtype=np.uint64)
+        data = np.frombuffer(b"".join(enc), dtype=np.uint8) if enc else np.empty(0, np.uint8)
+        data = np.ascontiguousarray(data)
+        self._check(lib().kb_dict_strings_load(self.h, _ptr(off), _ptr(data) if len(data) else None, len(enc)))
 
     # ---- operators
     def scan(self, pats: Sequence[KbPattern], pushdown: Optional[Sequence[Optional[Sequence[KbFilterOp]]]] = None):

@@ -1563,6 +1563,8 @@ void kb_ctx_destroy(kb_ctx* ctx) {
     ctx->index.clear();
     ctx->num.reset();
     ctx->isnum.reset();
+    ctx->dict_off.reset();
+    ctx->dict_bytes.reset();
     ctx->tile_state.reset();
     ctx->block_state.reset();
     cudaStreamSynchronize(ctx->st);
@@ -1921,6 +1923,91 @@ kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t
     ctx->n_ids = n_ids;
     ctx->num_version++;
     return KB_OK;
+}
+
+kb_status kb_dict_strings_load(kb_ctx* ctx, const uint64_t* offsets, const uint8_t* bytes, uint32_t n_ids) {
+    KB_ENTER(ctx);
+    ctx->dict_off.reset();
+    ctx->dict_bytes.reset();
+    ctx->dict_ids = 0;
+    if (n_ids == 0) return KB_OK;
+    if (!offsets) return kb::fail(ctx, KB_E_INVALID, "NULL offsets");
+    const uint64_t total = offsets[n_ids];
+    if (offsets[0] != 0 || (total && !bytes)) return kb::fail(ctx, KB_E_INVALID, "offsets must start at 0 and bytes must not be NULL");
+    for (uint32_t i = 0; i < n_ids; i++) if (offsets[i + 1] < offsets[i]) return kb::fail(ctx, KB_E_INVALID, "offsets decrease at id %u", i);
+    KB_TRY(kb::alloc_buf(ctx, ((size_t)n_ids + 1) * sizeof(uint64_t), &ctx->dict_off));
+    KB_TRY(kb::alloc_buf(ctx, (size_t)total + 16, &ctx->dict_bytes));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->dict_off->p, offsets, ((size_t)n_ids + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->st));
+    if (total) KB_CUDA(ctx, cudaMemcpyAsync(ctx->dict_bytes->p, bytes, (size_t)total, cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->stats.h2d_bytes += ((size_t)n_ids + 1) * sizeof(uint64_t) + total;
+    ctx->dict_ids = n_ids;
+    return KB_OK;
+}
+
+kb_status kb_rel_decode(kb_ctx* ctx, const kb_rel* r, uint32_t col, kb_strings** out) {
+    KB_ENTER(ctx);
+    if (!r || !out) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (col >= r->cols.size()) return kb::fail(ctx, KB_E_INVALID, "column %u out of range", col);
+    if (r->n >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
+    auto res = std::make_unique<kb_strings>();
+    res->n = r->n;
+    const u32 n = (u32)r->n;
+    KB_TRY(kb::alloc_buf(ctx, ((size_t)n + 1) * sizeof(u32), &res->off));
+    u32* off = static_cast<u32*>(res->off->p);
+    const u32 c = kb::ctrl_alloc(ctx, 4);  // [0..1] u64 total bytes, [2] quoted-triple id seen
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + c, 0, 4 * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(off + n, 0, sizeof(u32), ctx->st));  // the scan runs over n + 1 entries: off[n] becomes the total
+    const auto* doff = ctx->dict_ids ? static_cast<const unsigned long long*>(ctx->dict_off->p) : nullptr;
+    const auto* dbytes = ctx->dict_ids ? static_cast<const unsigned char*>(ctx->dict_bytes->p) : nullptr;
+    kb::Buf scratch;
+    KB_TRY(kb::alloc_buf(ctx, (((size_t)n + 1) / 2048 + 4) * sizeof(u32), &scratch));
+    kb::timer_begin(ctx, kb::F_OTHER, 4);
+    kb::launch_decode_lengths(r->cols[col].ptr, n, doff, ctx->dict_ids, off, reinterpret_cast<unsigned long long*>(ctx->ctrl + c), ctx->ctrl + c + 2,
+                              ctx->n_sms, ctx->st);
+    kb::launch_exclusive_scan_u32(off, n + 1, static_cast<u32*>(scratch->p), ctx->st);
+    kb::timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    KB_TRY(kb::ctrl_read(ctx));
+    unsigned long long total = 0;
+    memcpy(&total, ctx->h_ctrl + c, sizeof total);
+    if (ctx->h_ctrl[c + 2]) return kb::fail(ctx, KB_E_UNSUPPORTED, "the column holds quoted-triple ids (bit 31): decode them on the host (dictionary.rs:58-68)");
+    if (total > 0xFFFFFFFFull) return kb::fail(ctx, KB_E_LIMIT, "decoded column would take %llu bytes (limit 2^32-1 per call)", total);
+    res->total = total;
+    KB_TRY(kb::alloc_buf(ctx, (size_t)total + 16, &res->bytes));
+    kb::timer_begin(ctx, kb::F_OTHER);
+    kb::launch_decode_gather(r->cols[col].ptr, n, doff, dbytes, ctx->dict_ids, off, static_cast<unsigned char*>(res->bytes->p), ctx->n_sms, ctx->st);
+    kb::timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    *out = res.release();
+    return KB_OK;
+}
+kb_status kb_strings_info(const kb_strings* s, uint64_t* n_strings, uint64_t* total_bytes) {
+    if (!s) return KB_E_INVALID;
+    if (n_strings) *n_strings = s->n;
+    if (total_bytes) *total_bytes = s->total;
+    return KB_OK;
+}
+kb_status kb_strings_download(kb_ctx* ctx, const kb_strings* s, uint64_t* offsets, uint8_t* bytes) {
+    if (!ctx || !s) return KB_E_INVALID;
+    kb::DeviceGuard guard(ctx->device);
+    if (offsets) {
+        std::vector<u32> h((size_t)s->n + 1);
+        KB_CUDA(ctx, cudaMemcpyAsync(h.data(), s->off->p, h.size() * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+        for (size_t i = 0; i < h.size(); i++) offsets[i] = h[i];
+    }
+    if (bytes && s->total) {
+        KB_CUDA(ctx, cudaMemcpyAsync(bytes, s->bytes->p, (size_t)s->total, cudaMemcpyDeviceToHost, ctx->st));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    }
+    ctx->stats.d2h_bytes += ((size_t)s->n + 1) * sizeof(u32) + s->total;
+    return KB_OK;
+}
+void kb_strings_free(kb_ctx* ctx, kb_strings* s) {
+    if (!s) return;
+    if (ctx) { kb::DeviceGuard guard(ctx->device); delete s; }
+    else delete s;
 }
 
 // ------------------------------------------------------------------ relations

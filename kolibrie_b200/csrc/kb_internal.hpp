@@ -53,6 +53,12 @@ struct kb_rel {
     }
 };
 
+struct kb_strings {
+    kb::Buf off;    // u32 [n + 1] (exclusive prefix of the lengths)
+    kb::Buf bytes;
+    kb::u64 n = 0, total = 0;
+};
+
 struct kb_groups {
     std::vector<std::vector<kb::u32>> keys;
     std::vector<std::vector<double>> vals;
@@ -101,6 +107,8 @@ struct kb_ctx {
     std::vector<kb::Segment> segs;
     kb::u64 n_triples = 0;
     kb::Buf num, isnum;
+    kb::Buf dict_off, dict_bytes;  // kb_dict_strings_load: u64 offsets [dict_ids + 1] + UTF-8 bytes
+    kb::u32 dict_ids = 0;
     kb::u32 n_ids = 0;
     kb::u64 num_version = 1;  // bumped by kb_dict_numeric_load: typed literal columns of the index are tied to it
     // tile-state buffer of the look-back prefix (never cleared: words carry the launch epoch)

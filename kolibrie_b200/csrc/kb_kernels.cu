@@ -1882,6 +1882,66 @@ void launch_derive(const DeriveParams& p, int n_sms, cudaStream_t st) {
 }
 
 // =================================================================================================================
+// dictionary decode
+__global__ void __launch_bounds__(256) decode_lengths_kernel(const u32* __restrict__ ids, u32 n, const unsigned long long* __restrict__ dict_off, u32 dict_ids,
+                                                             u32* __restrict__ len, unsigned long long* total, u32* quoted) {
+    const u32 stride = gridDim.x * blockDim.x;
+    unsigned long long t = 0;
+    bool q = false;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u32 id = ids[i];
+        q = q || (id & 0x80000000u) != 0u;
+        const u32 l = id < dict_ids ? (u32)(__ldg(dict_off + id + 1) - __ldg(dict_off + id)) : 7u;  // "unknown"
+        len[i] = l;
+        t += l;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(total, t);
+    if (q) *quoted = 1u;
+}
+void launch_decode_lengths(const u32* ids, u32 n, const unsigned long long* dict_off, u32 dict_ids, u32* len, unsigned long long* total, u32* quoted,
+                           int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    decode_lengths_kernel<<<grid, 256, 0, st>>>(ids, n, dict_off, dict_ids, len, total, quoted);
+}
+__global__ void __launch_bounds__(256) decode_gather_kernel(const u32* __restrict__ ids, u32 n, const unsigned long long* __restrict__ dict_off,
+                                                            const unsigned char* __restrict__ dict_bytes, u32 dict_ids, const u32* __restrict__ off,
+                                                            unsigned char* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const u32 warps = (gridDim.x * blockDim.x) >> 5;
+    const u32 n_chunks = (n + 31u) >> 5;
+    for (u32 chunk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; chunk < n_chunks; chunk += warps) {
+        const u32 i = chunk * 32u + (u32)lane;
+        u32 id = 0, dst = 0, l = 0;
+        unsigned long long src = 0;
+        bool known = false;
+        if (i < n) {
+            id = ids[i];
+            dst = off[i];
+            l = off[i + 1] - dst;
+            known = id < dict_ids;
+            if (known) src = __ldg(dict_off + id);
+        }
+        for (int r = 0; r < 32; r++) {  // the warp copies row r of its chunk: consecutive lanes, consecutive bytes
+            const u32 rl = __shfl_sync(0xffffffffu, l, r);
+            if (rl == 0u) continue;
+            const u32 rdst = __shfl_sync(0xffffffffu, dst, r);
+            const unsigned long long rsrc = __shfl_sync(0xffffffffu, src, r);
+            const bool rknown = __shfl_sync(0xffffffffu, known ? 1 : 0, r) != 0;
+            for (u32 b = (u32)lane; b < rl; b += 32u) out[rdst + b] = rknown ? __ldg(dict_bytes + rsrc + b) : (unsigned char)"unknown"[b];
+        }
+    }
+}
+void launch_decode_gather(const u32* ids, u32 n, const unsigned long long* dict_off, const unsigned char* dict_bytes, u32 dict_ids, const u32* off,
+                          unsigned char* out, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    decode_gather_kernel<<<grid, 256, 0, st>>>(ids, n, dict_off, dict_bytes, dict_ids, off, out);
+}
+
+// =================================================================================================================
 // utilities
 __global__ void fill_kernel(u32* p, u32 v, u64 n) {
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;

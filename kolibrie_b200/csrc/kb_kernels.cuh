@@ -329,6 +329,16 @@ void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p /*n
                        int n_sms, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------------
+// id -> string decode of a result column (engine.rs:27-51): lengths, exclusive scan (launch_exclusive_scan_u32), byte gather
+// len[i] = length of the string of ids[i] ("unknown" = 7 bytes when the dictionary does not hold the id); *total += sum; *quoted = 1
+// when an id carries the quoted-triple bit
+void launch_decode_lengths(const u32* ids, u32 n, const unsigned long long* dict_off, u32 dict_ids, u32* len, unsigned long long* total, u32* quoted,
+                           int n_sms, cudaStream_t st);
+// out[off[i] .. off[i+1]) = bytes of the string of ids[i]; one warp per 32 rows, the lanes copy each string together
+void launch_decode_gather(const u32* ids, u32 n, const unsigned long long* dict_off, const unsigned char* dict_bytes, u32 dict_ids, const u32* off,
+                          unsigned char* out, int n_sms, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
 // small utilities
 void launch_fill_u32(u32* p, u32 v, u64 n, cudaStream_t st);
 void launch_fill_const_col(u32* p, u32 v, u64 n, cudaStream_t st);

@@ -303,6 +303,7 @@ class SparqlDatabase:
         self.ctx.store_load(arr[:, 0], arr[:, 1], arr[:, 2])
         num, isn = self.dictionary.numeric_table()
         self.ctx.dict_numeric_load(num, isn)
+        self.ctx.dict_strings_load(self.dictionary.id_to_string)  # the final id -> string step runs on the device too
         self._uploaded_version = self._version
 
 
@@ -349,8 +350,14 @@ class ExecutionEngine:
 
     @staticmethod
     def execute(op, db: SparqlDatabase) -> List[Dict[str, str]]:
-        rows = ExecutionEngine.execute_with_ids(op, db)
-        return [{k: (db.dictionary.decode(v) or "unknown") for k, v in r.items()} for r in rows]  # engine.rs:41-43
+        # engine.rs:33-49: ids are turned into strings only at the very end — here by kb_rel_decode, column by column, on the device
+        db._sync()
+        slots = SlotMap()
+        rel = ExecutionEngine._run(op, db, slots)
+        n, rslots = rel.info()
+        cols = [rel.decode_strings(i) for i in range(len(rslots))]
+        names = [slots.names[s] for s in rslots]
+        return [{names[j]: cols[j][i] for j in range(len(names))} for i in range(n)]
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -335,6 +335,11 @@ class SparqlDatabase {
         std::vector<double> num; std::vector<uint8_t> isn;
         dictionary.numeric_table(&num, &isn);
         dev_->check(kb_dict_numeric_load(dev_->get(), num.data(), isn.data(), (uint32_t)num.size()));
+        // the strings themselves: the final id -> string step of execute() runs on the device (kb_rel_decode)
+        std::vector<uint64_t> off(dictionary.id_to_string.size() + 1, 0);
+        std::string bytes;
+        for (size_t i = 0; i < dictionary.id_to_string.size(); i++) { bytes += dictionary.id_to_string[i]; off[i + 1] = bytes.size(); }
+        dev_->check(kb_dict_strings_load(dev_->get(), off.data(), reinterpret_cast<const uint8_t*>(bytes.data()), (uint32_t)dictionary.id_to_string.size()));
         uploaded_ = version_;
     }
     const Device& device() const { return *dev_; }
@@ -398,11 +403,27 @@ struct ExecutionEngine {
         for (uint64_t i = 0; i < n; i++) for (size_t c = 0; c < slots.size(); c++) rows[i][sm.names[slots[c]]] = cols[c][i];
         return rows;
     }
-    // engine.rs:27 — ids decoded only at the final step
+    // engine.rs:27-51 — ids all the way, decoded only at the final step: kb_rel_decode gathers each column's strings on the device
     static std::vector<std::unordered_map<std::string, std::string>> execute(const PhysicalOperator& op, SparqlDatabase& db) {
-        auto ids = execute_with_ids(op, db);
-        std::vector<std::unordered_map<std::string, std::string>> out(ids.size());
-        for (size_t i = 0; i < ids.size(); i++) for (auto& kv : ids[i]) { const std::string* s = db.dictionary.decode(kv.second); out[i][kv.first] = s ? *s : "unknown"; }
+        db.sync();
+        SlotMap sm;
+        Rel rel = run(op, db, sm);
+        uint64_t n = 0;
+        uint32_t n_cols = 0, slots[KB_MAX_COLS];
+        db.device().check(kb_rel_info(rel->r, &n, &n_cols, slots));
+        std::vector<std::unordered_map<std::string, std::string>> out(n);
+        for (uint32_t c = 0; c < n_cols; c++) {
+            kb_strings* h = nullptr;
+            db.device().check(kb_rel_decode(db.device().get(), rel->r, c, &h));
+            uint64_t cnt = 0, total = 0;
+            kb_strings_info(h, &cnt, &total);
+            std::vector<uint64_t> off(cnt + 1);
+            std::string bytes(total, '\0');
+            const kb_status st = kb_strings_download(db.device().get(), h, off.data(), reinterpret_cast<uint8_t*>(&bytes[0]));
+            kb_strings_free(db.device().get(), h);
+            db.device().check(st);
+            for (uint64_t i = 0; i < cnt; i++) out[i][sm.names[slots[c]]] = bytes.substr(off[i], off[i + 1] - off[i]);
+        }
         return out;
     }
 };
