@@ -122,3 +122,27 @@ def test_known_fact_set_grows_mid_launch(ctx):
     # a second run over the store (which now holds the inferred facts) derives nothing
     rel2, st2 = ctx.datalog_fixpoint([rule], c.SEMI_NAIVE)
     assert st2.inferred == 0
+
+
+def test_known_fact_set_skewed_subject(ctx):
+    """every derived fact of one rule has the SAME subject (constant in the head) and many candidates are duplicates of each other:
+    heavy skew on one half of the 64-bit set key; every fact must still be derived exactly once"""
+    rng = np.random.default_rng(9)
+    n = 300_000
+    s = rng.integers(100, 5000, n).astype(np.uint32)
+    o = rng.integers(10_000, 10_000 + 120_000, n).astype(np.uint32)  # ~36 % of the objects occur more than once
+    tr = np.unique(np.stack([s, np.full(n, 5, np.uint32), o], axis=1), axis=0)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    rules = [{"premise": [c.pattern(c.V(0), c.K(5), c.V(1))], "conclusion": [c.pattern(c.K(7), c.K(6), c.V(1))], "filters": []},
+             {"premise": [c.pattern(c.V(0), c.K(5), c.V(1))], "conclusion": [c.pattern(c.V(0), c.K(8), c.K(7))], "filters": []}]
+    rel, st = ctx.datalog_fixpoint(rules, c.SEMI_NAIVE)
+    got = rel.to_numpy([0, 1, 2])
+    objs = np.unique(tr[:, 2])
+    subs = np.unique(tr[:, 0])
+    want = np.concatenate([np.stack([np.full(len(objs), 7, np.uint32), np.full(len(objs), 6, np.uint32), objs], axis=1),
+                           np.stack([subs, np.full(len(subs), 8, np.uint32), np.full(len(subs), 7, np.uint32)], axis=1)])
+    H.assert_same_bag(got, want, "constant-subject heads")
+    assert st.derivations == 2 * len(tr) and st.rounds == 1
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2])
+    w = db.fixpoint(rules, c.SEMI_NAIVE)
+    H.assert_same_bag(got, w["facts"], "vs oracle")
