@@ -42,8 +42,10 @@ def summarize(rep, name, family, traffic):
         ia, ie = h.index("Source"), h.index("Instructions Executed")
         op = collections.Counter()
         for r in src[2:]:
+            if len(r) <= max(ia, ie):  # a second kernel's header / separator rows in a multi-kernel report
+                continue
             m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[ia])
-            op[(m.group(2).split(".")[0] if m else "?")] += int(r[ie] or 0)
+            op[(m.group(2).split(".")[0] if m else "?")] += int(r[ie]) if r[ie].isdigit() else 0
         tot_i = sum(op.values()) or 1
         lines.append("opcode mix (% of executed warp instructions): " + ", ".join(f"{o} {100 * c / tot_i:.1f}" for o, c in op.most_common(14)))
         sass = " ".join(op.keys())
@@ -75,7 +77,7 @@ if __name__ == "__main__":
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    for fam in ("scan", "build", "probe", "probe_index"):
+    for fam in ("scan", "build", "probe", "probe_index", "derive"):
         rep = os.path.join(ROOT, "gpurun_out", f"prof_{fam}_{tag}.ncu-rep")
         if os.path.exists(rep):
             summarize(rep, f"{fam}_{tag}", fam, traffic)
