@@ -253,6 +253,15 @@ KB_API kb_status kb_set_sharding(kb_ctx* ctx, uint32_t rank, uint32_t world);
 /* split `in` by kb_shard_of(row[key_slot], n_parts) into n_parts contiguous ranges of ONE output relation;
  * part_offsets[n_parts+1] (host) receives the row offsets. */
 KB_API kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, kb_rel** out, uint64_t* part_offsets);
+/* The same exchange FUSED with its transfer (SURVEY.md 8e "fused peer stores from the partition kernel"): every row is written straight
+ * into the receive buffer of the rank that owns its key, over NVLink peer memory, instead of partition + all-to-all.
+ * kb_partition_counts: rows of `r` per destination. The caller exchanges the counts (a world x world matrix of integers), derives
+ * base[d] = first row of this rank's range in rank d's receive buffer, and passes peer_cols[d * n_cols + c] = device-visible address
+ * of column c of rank d's receive buffer (peer-mapped memory, e.g. torch symmetric memory or cudaIpc). The call returns when this
+ * rank's stores have been issued and fenced system-wide; a barrier across ranks must follow before the buffers are read. */
+KB_API kb_status kb_partition_counts(kb_ctx* ctx, const kb_rel* r, uint32_t key_slot, uint32_t n_parts, uint64_t* counts /* [n_parts] */);
+KB_API kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* r, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols /* [n_parts * n_cols] */,
+                                    const uint64_t* base /* [n_parts] */, uint64_t capacity_rows);
 KB_API kb_status kb_rel_from_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out);
 KB_API kb_status kb_store_download(kb_ctx* ctx, uint32_t* s, uint32_t* p, uint32_t* o, uint64_t cap, uint64_t* n);
 

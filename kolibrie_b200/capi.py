@@ -184,6 +184,8 @@ def lib() -> C.CDLL:
         "kb_shard_of": (u32, [u32, u32]),
         "kb_set_sharding": (i32, [vp, u32, u32]),
         "kb_partition": (i32, [vp, vp, u32, u32, P(vp), P(u64)]),
+        "kb_partition_counts": (i32, [vp, vp, u32, u32, P(u64)]),
+        "kb_shuffle_scatter": (i32, [vp, vp, u32, u32, P(vp), P(u64), u64]),
         "kb_star_join_host": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), P(u64)]),
         "perform_hash_join_cuda": (None, [vp, vp, vp, u32, u32, P(u32), P(P(u32)), P(u32)]),
     }
@@ -201,7 +203,7 @@ EXPORTED_SYMBOLS = [
     "kb_store_download", "kb_dict_numeric_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free",
-    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_star_join_host", "perform_hash_join_cuda",
+    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_star_join_host", "perform_hash_join_cuda",
 ]
 
 
@@ -483,6 +485,17 @@ class Context:
         offs = (C.c_uint64 * (n_parts + 1))()
         self._check(lib().kb_partition(self.h, rel.h, key_slot, n_parts, C.byref(out), offs))
         return Relation(self, out), [offs[i] for i in range(n_parts + 1)]
+
+    def partition_counts(self, rel: Relation, key_slot: int, n_parts: int) -> List[int]:
+        cnt = (C.c_uint64 * n_parts)()
+        self._check(lib().kb_partition_counts(self.h, rel.h, key_slot, n_parts, cnt))
+        return [int(cnt[i]) for i in range(n_parts)]
+
+    def shuffle_scatter(self, rel: Relation, key_slot: int, n_parts: int, peer_cols: Sequence[int], base: Sequence[int], capacity_rows: int):
+        """kb_shuffle_scatter: peer_cols[d * n_cols + c] = address of column c of rank d's receive buffer (peer-mapped)"""
+        pc = (C.c_void_p * len(peer_cols))(*peer_cols)
+        bs = (C.c_uint64 * n_parts)(*base)
+        self._check(lib().kb_shuffle_scatter(self.h, rel.h, key_slot, n_parts, pc, bs, capacity_rows))
 
     def star_join_host(self, s, p, o, join_slot: int, pats: Sequence[KbPattern], filt=None):
         """One-shot host-buffer call (kb_star_join_host): upload + star join + download; result columns are malloc'd by the

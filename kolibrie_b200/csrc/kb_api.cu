@@ -2318,6 +2318,70 @@ kb_status kb_set_sharding(kb_ctx* ctx, uint32_t rank, uint32_t world) {
     return KB_OK;
 }
 
+kb_status kb_partition_counts(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, uint64_t* counts) {
+    KB_ENTER(ctx);
+    if (!in || !counts) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n_parts == 0 || n_parts > 64) return kb::fail(ctx, KB_E_LIMIT, "1..64 partitions");
+    const int kc = in->col_of(key_slot);
+    if (kc < 0) return kb::fail(ctx, KB_E_INVALID, "partition key slot %u is not a column", key_slot);
+    if (in->n >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
+    const u32 off = kb::ctrl_alloc(ctx, 64);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 64 * sizeof(u32), ctx->st));
+    kb::timer_begin(ctx, kb::F_OTHER);
+    kb::launch_part_count(in->cols[kc].ptr, (u32)in->n, n_parts, ctx->ctrl + off, ctx->n_sms, ctx->st);
+    kb::timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    KB_TRY(kb::ctrl_read(ctx));
+    for (u32 i = 0; i < n_parts; i++) counts[i] = ctx->h_ctrl[off + i];
+    return KB_OK;
+}
+
+kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols, const uint64_t* base,
+                             uint64_t capacity_rows) {
+    KB_ENTER(ctx);
+    if (!in || !peer_cols || !base) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n_parts == 0 || n_parts > 64) return kb::fail(ctx, KB_E_LIMIT, "1..64 partitions");
+    const int kc = in->col_of(key_slot);
+    if (kc < 0) return kb::fail(ctx, KB_E_INVALID, "partition key slot %u is not a column", key_slot);
+    if (in->n >= 0xFFFFFFF0ull || capacity_rows >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
+    const u32 n_cols = (u32)in->cols.size();
+    for (u32 i = 0; i < n_parts * n_cols; i++) if (!peer_cols[i]) return kb::fail(ctx, KB_E_INVALID, "peer column %u is NULL", i);
+    // device-side tables: peer column addresses, bases, cursors, overflow flag
+    kb::Buf tab;
+    const size_t ptr_bytes = (size_t)n_parts * n_cols * sizeof(u32*);
+    KB_TRY(kb::alloc_buf(ctx, ptr_bytes + 3 * 64 * sizeof(u32), &tab));
+    char* tb = static_cast<char*>(tab->p);
+    std::vector<u32> hbase(64, 0);
+    for (u32 i = 0; i < n_parts; i++) {
+        if (base[i] > capacity_rows) return kb::fail(ctx, KB_E_INVALID, "base[%u] beyond the receive capacity", i);
+        hbase[i] = (u32)base[i];
+    }
+    KB_CUDA(ctx, cudaMemcpyAsync(tb, peer_cols, ptr_bytes, cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(tb + ptr_bytes, hbase.data(), 64 * sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(tb + ptr_bytes + 64 * sizeof(u32), 0, 2 * 64 * sizeof(u32), ctx->st));
+    kb::ShuffleParams P{};
+    P.key = in->cols[kc].ptr;
+    P.n = (u32)in->n;
+    P.n_parts = n_parts;
+    P.n_cols = n_cols;
+    for (u32 c = 0; c < n_cols; c++) P.in[c] = in->cols[c].ptr;
+    P.peer_cols = reinterpret_cast<u32* const*>(tb);
+    P.base = reinterpret_cast<const u32*>(tb + ptr_bytes);
+    P.cursors = reinterpret_cast<u32*>(tb + ptr_bytes + 64 * sizeof(u32));
+    P.overflow = P.cursors + 64;
+    P.capacity = (u32)capacity_rows;
+    kb::timer_begin(ctx, kb::F_OTHER);
+    kb::launch_shuffle_scatter(P, ctx->n_sms, ctx->st);
+    kb::timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    u32 ovf = 0;
+    KB_CUDA(ctx, cudaMemcpyAsync(&ovf, P.overflow, sizeof ovf, cudaMemcpyDeviceToHost, ctx->st));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    kb::timers_flush(ctx);
+    if (ovf) return kb::fail(ctx, KB_E_LIMIT, "a receive buffer is smaller than the rows sent to it (capacity %llu rows)", (unsigned long long)capacity_rows);
+    return KB_OK;
+}
+
 kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, kb_rel** out, uint64_t* part_offsets) {
     KB_ENTER(ctx);
     if (!in || !out || !part_offsets) return kb::fail(ctx, KB_E_INVALID, "NULL argument");

@@ -1998,6 +1998,35 @@ void launch_part_scatter(const u32* key, u32 n, u32 n_parts, u32* cursors, const
     part_scatter_kernel<<<grid, 256, 0, st>>>(key, n, n_parts, cursors, P);
 }
 
+__global__ void __launch_bounds__(256) shuffle_scatter_kernel(const __grid_constant__ ShuffleParams P) {
+    const int lane = threadIdx.x & 31;
+    const u32 n_round = (P.n + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < P.n;
+        const u32 part = valid ? shard_of(P.key[i], P.n_parts) : 0xFFFFu;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        // the lanes bound for the same rank take one range of its buffer together: consecutive positions, coalesced peer stores
+        const unsigned peers = __match_any_sync(act, part);
+        const int leader = __ffs(peers) - 1;
+        u32 basepos = 0;
+        if (lane == leader) basepos = atomicAdd(&P.cursors[part], (u32)__popc(peers));
+        basepos = __shfl_sync(peers, basepos, leader);
+        const u32 r = P.base[part] + basepos + (u32)__popc(peers & ((1u << lane) - 1u));
+        if (r < P.capacity) {
+            for (u32 c = 0; c < P.n_cols; c++) P.peer_cols[part * P.n_cols + c][r] = P.in[c][i];
+        } else {
+            *P.overflow = 1u;
+        }
+    }
+    __threadfence_system();  // the stores must be visible to the peers before the host-side barrier that follows the launch
+}
+void launch_shuffle_scatter(const ShuffleParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 4ull, ((u64)p.n + 255ull) / 256ull);
+    shuffle_scatter_kernel<<<grid, 256, 0, st>>>(p);
+}
+
 // kb_store_delete: p_out[i] = p[i], or EMPTY32 when (s,p,o)[i] is in the delete set; a scan with a variable predicate and
 // NE_ID(EMPTY32)... is not needed: the store compaction simply rescans with pattern (?s ?p ?o) over (s, p_out, o) and drops
 // rows whose predicate became EMPTY32 (KB_ID_NONE is never a real predicate).

@@ -328,6 +328,20 @@ void launch_set64_insert(u64* set, u32 set_slots, const u32* s, const u32* o, u3
 void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p /*null: p_const*/, u32 p_const, const u32* o, u32 n, u32* overflow,
                        int n_sms, cudaStream_t st);
 
+// fused partition + transfer of the multi-GPU join-key shuffle: row i goes to rank d = shard_of(key[i], n_parts), at position
+// base[d] + (rows this launch already sent to d), written with plain stores into d's receive buffer (peer memory over NVLink)
+struct ShuffleParams {
+    const u32* key;
+    u32 n, n_parts, n_cols;
+    const u32* in[KB_MAX_COLS];
+    u32* const* peer_cols;  // device array [n_parts * n_cols]
+    const u32* base;        // device array [n_parts]
+    u32* cursors;           // device array [n_parts], zeroed
+    u32 capacity;
+    u32* overflow;
+};
+void launch_shuffle_scatter(const ShuffleParams& p, int n_sms, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------------------------------
 // id -> string decode of a result column (engine.rs:27-51): lengths, exclusive scan (launch_exclusive_scan_u32), byte gather
 // len[i] = length of the string of ids[i] ("unknown" = 7 bytes when the dictionary does not hold the id); *total += sum; *quoted = 1

@@ -4,9 +4,12 @@
   function the device's `kb_partition` uses; it balances like a hash and keeps each shard's key domain dense (direct join tables
   stay as small on N GPUs as on one: `Context.set_sharding`);
 * a star join on the subject needs no communication: every rank joins its shard, counts are summed, times are max-reduced;
-* a join on a non-subject key shuffles the rows once: `kb_partition` (device) splits a relation into `world` contiguous ranges
-  by kb_shard_of(key, world), `all_to_all_relation` exchanges the range sizes and then the columns with
-  `torch.distributed.all_to_all_single` — NCCL over NVLink on the GPU box, gloo in the CPU tests.
+* a join on a non-subject key shuffles the rows once. Two implementations of that exchange:
+  - `PeerShuffle` (GPU box): ONE kernel partitions and transfers — `kb_shuffle_scatter` writes every row straight into the receive
+    buffer of the rank that owns its key, peer memory over NVLink (buffers from torch symmetric memory, which is only plumbing
+    here: allocation, address exchange, barrier). Only the world x world matrix of row counts travels through a collective.
+  - `shuffle_relation`: `kb_partition` (device) splits a relation into `world` contiguous ranges, `all_to_all_relation` exchanges
+    the range sizes and then the columns with `torch.distributed.all_to_all_single` — NCCL on the GPU box, gloo in the CPU tests.
 
 Only plumbing lives here; all data-touching work is in libkolibrie_b200.so.
 """
@@ -72,6 +75,50 @@ def shuffle_relation(ctx, rel, key_slot: int, group=None):
     m = int(recv[0].numel()) if recv else 0
     out = ctx.rel_from_device(slots, [int(t.data_ptr()) for t in recv], m)
     return out
+
+
+def shuffle_plan(counts_matrix: np.ndarray, rank: int):
+    """counts_matrix[src][dst] = rows rank src sends to rank dst. Returns (base, recv_total): base[d] = first row of this rank's range
+    in rank d's receive buffer (ranges in source-rank order), recv_total = rows this rank receives."""
+    m = np.asarray(counts_matrix, dtype=np.int64)
+    base = [int(m[:rank, d].sum()) for d in range(m.shape[1])]
+    return base, int(m[:, rank].sum())
+
+
+class PeerShuffle:
+    """Receive buffers in peer-mapped memory, allocated and rendezvoused once, reused for every shuffle of up to `capacity_rows`
+    rows x `n_cols` columns per rank."""
+
+    def __init__(self, ctx, n_cols: int, capacity_rows: int, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.ctx, self.n_cols, self.cap = ctx, n_cols, int(capacity_rows)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.dev = torch.device("cuda", ctx.device)
+        self.buf = symm_mem.empty(n_cols * self.cap, dtype=torch.int32, device=self.dev)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+
+    def col_ptr(self, peer: int, col: int) -> int:
+        return self.ptrs[peer] + 4 * col * self.cap
+
+    def shuffle(self, rel, key_slot: int):
+        """re-shard `rel` so that every row lives on rank kb_shard_of(row[key_slot], world); returns a new Relation"""
+        n, slots = rel.info()
+        assert len(slots) == self.n_cols
+        mine = torch.tensor(self.ctx.partition_counts(rel, key_slot, self.world), dtype=torch.int64, device=self.dev)
+        allc = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allc, mine, group=self.group)
+        base, recv_total = shuffle_plan(torch.stack(allc).cpu().numpy(), self.rank)
+        if recv_total > self.cap:
+            raise ValueError(f"rank {self.rank} would receive {recv_total} rows, capacity {self.cap}")
+        self.hdl.barrier()  # every rank is done reading what the previous shuffle left in its buffer
+        peer_cols = [self.col_ptr(d, c_) for d in range(self.world) for c_ in range(self.n_cols)]
+        self.ctx.shuffle_scatter(rel, key_slot, self.world, peer_cols, base, self.cap)  # returns after its stores are fenced
+        self.hdl.barrier()  # every rank's stores have landed
+        torch.cuda.synchronize(self.dev)
+        return self.ctx.rel_from_device(slots, [self.col_ptr(self.rank, c_) for c_ in range(self.n_cols)], recv_total)
 
 
 def sum_over_ranks(value: int, device=None, group=None) -> int:

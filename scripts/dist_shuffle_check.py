@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N: a 2-hop PATH join (?x p1 ?y . ?y p2 ?z) over a store sharded by hash(subject): the first pattern's
-rows must be re-sharded by ?y (a non-subject key) before the local join — kb_partition + NCCL all-to-all (kolibrie_b200.dist).
-Every rank checks its slice against the oracle run on the full store."""
+rows must be re-sharded by ?y (a non-subject key) before the local join. Both exchanges are checked: kb_partition + NCCL all-to-all
+and the fused peer-memory kernel (kolibrie_b200.dist.PeerShuffle). Every rank checks its slice against the oracle run on the full
+store; then both exchanges are timed on a large relation."""
 import os, sys
 import numpy as np
 import torch, torch.distributed as dist
@@ -27,6 +28,35 @@ want = O.Db(tr[:, 0], tr[:, 1], tr[:, 2]).bgp([c.pattern(c.V(X), c.K(100), c.V(Y
 mine = want[kd.shard_of(want[:, 1], world) == rank]
 ok = np.array_equal(datagen.canonical_rows(got), datagen.canonical_rows(mine))
 total = kd.sum_over_ranks(len(got), device=torch.device("cuda", local))
-print(f"rank {rank}: local rows {len(got)} ok={ok} global {total} want {len(want)}", flush=True)
+print(f"rank {rank}: NCCL exchange: local rows {len(got)} ok={ok} global {total} want {len(want)}", flush=True)
 assert ok and total == len(want)
+
+# ---- the same exchange fused with its transfer: one kernel writes into the peers' receive buffers over NVLink
+import time
+ps = kd.PeerShuffle(ctx, n_cols=2, capacity_rows=40_000_000)
+left_p2p = ps.shuffle(left, Y)
+H = datagen.canonical_rows
+ok2 = np.array_equal(H(left_p2p.to_numpy(sorted(left_p2p.slots))), H(left_sh.to_numpy(sorted(left_sh.slots))))
+got2 = ctx.hash_join(left_p2p, right).to_numpy([X, Y, Z])
+ok3 = np.array_equal(H(got2), H(mine))
+print(f"rank {rank}: peer-memory exchange: same rows as NCCL {ok2}, join ok {ok3}", flush=True)
+assert ok2 and ok3
+
+# ---- timing on a large 2-column relation (rows per rank)
+nbig = 30_000_000
+big = ctx.rel_from_host([X, Y], [rng.integers(0, 1 << 24, nbig).astype(np.uint32), rng.integers(0, 1 << 24, nbig).astype(np.uint32)])
+dev = torch.device("cuda", local)
+for name, fn in (("partition + NCCL all_to_all", lambda: kd.shuffle_relation(ctx, big, Y)), ("fused peer-memory kernel", lambda: ps.shuffle(big, Y))):
+    ts = []
+    for rep in range(4):
+        dist.barrier(device_ids=[local]); torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize(dev); dist.barrier(device_ids=[local])
+        ts.append(time.perf_counter() - t0)
+        m = r.n_rows
+        r.free()
+    t = kd.max_over_ranks(min(ts[1:]), device=dev)
+    if rank == 0:
+        print(f"{name}: {nbig} rows x 2 columns per rank, {world} ranks: {t * 1e3:.2f} ms ({8 * nbig * (world - 1) / world / t / 1e9:.1f} GB/s sent per rank over NVLink)", flush=True)
 dist.destroy_process_group()

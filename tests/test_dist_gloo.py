@@ -88,3 +88,20 @@ def test_two_rank_sharding_and_shuffle_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_peer_shuffle_plan_ranges_are_disjoint_and_complete():
+    """host side of the fused peer-memory shuffle: from the world x world matrix of row counts every sender derives where its rows
+    start in every receiver's buffer; the ranges must tile each receive buffer exactly (source-rank order, no gaps, no overlap)"""
+    from kolibrie_b200 import dist as kd
+
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 8):
+        m = rng.integers(0, 1000, (world, world))
+        plans = [kd.shuffle_plan(m, r) for r in range(world)]
+        for d in range(world):
+            spans = sorted((plans[src][0][d], plans[src][0][d] + int(m[src, d])) for src in range(world))
+            assert spans[0][0] == 0
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            assert spans[-1][1] == plans[d][1] == int(m[:, d].sum())
