@@ -1957,7 +1957,18 @@ __global__ void __launch_bounds__(256) part_count_kernel(const u32* key, u32 n, 
     __shared__ u32 sc[64];
     if (threadIdx.x < 64) sc[threadIdx.x] = 0;
     __syncthreads();
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&sc[shard_of(key[i], n_parts)], 1u);
+    const int lane = threadIdx.x & 31;
+    const u32 n_round = (n + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        const u32 part = valid ? shard_of(key[i], n_parts) : 0xFFFFu;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        // one shared atomic per (warp, destination) instead of one per row: with a handful of destinations the rows of a warp
+        // pile up on a handful of addresses
+        const unsigned peers = __match_any_sync(act, part);
+        if (lane == __ffs(peers) - 1) atomicAdd(&sc[part], (u32)__popc(peers));
+    }
     __syncthreads();
     if (threadIdx.x < n_parts && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], sc[threadIdx.x]);
 }
