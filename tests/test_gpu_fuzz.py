@@ -1,0 +1,95 @@
+"""GPU (-m gpu): differential fuzzing of whole BGPs — random stores, random patterns (variables shared in any position, constants,
+repeated variables), random FILTER programs and projections — device vs oracle, with and without the store index. Seeds are fixed:
+a failure names the case that reproduces it."""
+import numpy as np
+import pytest
+
+from kolibrie_b200 import capi as c
+from tests import helpers as H
+from tests import oracle_api as O
+
+pytestmark = pytest.mark.gpu
+
+TALLY = {"ran": 0, "declined": 0}
+
+
+def random_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n_terms = int(rng.choice([6, 20, 60, 200]))
+    n_preds = int(rng.integers(2, 6))
+    n = int(rng.choice([0, 1, 40, 700, 5000, 30000], p=[0.04, 0.04, 0.17, 0.25, 0.3, 0.2]))
+    tr = np.stack([rng.integers(0, n_terms, n), rng.integers(100, 100 + n_preds, n), rng.integers(0, n_terms, n)], axis=1).astype(np.uint32)
+    tr = np.unique(tr, axis=0) if n else tr
+    num = np.zeros(n_terms + 200)
+    isn = np.zeros(n_terms + 200, np.uint8)
+    numeric = rng.random(n_terms) < 0.6
+    num[:n_terms][numeric] = np.round(rng.normal(50, 40, int(numeric.sum())), 1)
+    isn[:n_terms][numeric] = 1
+    n_pats = int(rng.integers(1, 5))
+    star = rng.random() < 0.5  # half of the cases: every pattern shares variable 0 in the subject (the star-join planner paths)
+    pats, bound = [], set()
+    for k in range(n_pats):
+        def term(pos):
+            if pos == 1:
+                return c.K(int(rng.integers(100, 100 + n_preds))) if rng.random() < 0.9 else c.V(int(rng.integers(4, 6)))
+            if star and pos == 0:
+                return c.V(0)
+            if rng.random() < 0.08:
+                return c.K(int(rng.integers(0, n_terms)))
+            return c.V(int(rng.integers(0, 4)))
+        s_, p_, o_ = term(0), term(1), term(2)
+        pats.append(c.pattern(s_, p_, o_))
+        for t in (s_, p_, o_):
+            if t.is_var:
+                bound.add(int(t.value))
+    bound = sorted(bound)
+    filt = None
+    if bound and rng.random() < 0.6:
+        ops = []
+        for q in range(int(rng.integers(1, 4))):
+            slot = int(rng.choice(bound))
+            kind = rng.choice([0, 0, 0, 1, 2, 2])
+            if kind == 0:
+                ops.append(c.fop(c.F_CMP_NUM, slot=slot, cmp=int(rng.choice([c.CMP_GT, c.CMP_GE, c.CMP_LT, c.CMP_LE])), value=float(rng.normal(50, 30))))
+            elif kind == 1:
+                ops.append(c.fop(c.F_EQ_ID, slot=slot, id=int(rng.integers(0, n_terms))))
+            else:
+                ops.append(c.fop(c.F_NE_ID, slot=slot, id=int(rng.integers(0, n_terms))))
+            if q:
+                ops.append(c.fop(c.F_AND if rng.random() < 0.7 else c.F_OR))
+        filt = ops
+    project = None
+    if bound and rng.random() < 0.3:
+        project = [int(x) for x in rng.choice(bound, int(rng.integers(1, len(bound) + 1)), replace=False)]
+    return tr, num, isn, pats, filt, project
+
+
+@pytest.mark.parametrize("seed", range(80))
+def test_random_bgp_vs_oracle(ctx, seed):
+    tr, num, isn, pats, filt, project = random_case(seed)
+    ctx.dict_numeric_load(num, isn)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2], num, isn)
+    want = db.bgp(pats, filt, project)
+    wslots = sorted(want.slots)
+    wrows = want.to_numpy(wslots)
+    for indexed in (False, True):
+        if indexed:
+            ctx.build_index()
+        try:
+            got = ctx.bgp_execute(pats, filt, project)
+        except c.KolibrieError as e:
+            # shapes the device declines (documented limits / KB_E_UNSUPPORTED) must be declined on both paths alike
+            assert e.status in (c.KB_E_UNSUPPORTED, c.KB_E_LIMIT), e
+            TALLY["declined"] += 1
+            continue
+        assert sorted(got.slots) == wslots, (seed, indexed)
+        H.assert_same_bag(got.to_numpy(wslots), wrows, f"seed {seed} indexed={indexed}")
+        got.free()
+        TALLY["ran"] += 1
+
+
+def test_fuzz_mostly_executes():
+    """the fuzzer is only worth something if the device actually answers most of its cases (runs after the cases above)"""
+    total = TALLY["ran"] + TALLY["declined"]
+    assert total == 0 or TALLY["declined"] <= total // 5, TALLY
