@@ -93,3 +93,62 @@ def test_fuzz_mostly_executes():
     """the fuzzer is only worth something if the device actually answers most of its cases (runs after the cases above)"""
     total = TALLY["ran"] + TALLY["declined"]
     assert total == 0 or TALLY["declined"] <= total // 5, TALLY
+
+
+def random_rules(seed):
+    rng = np.random.default_rng(5000 + seed)
+    n_terms, n_preds = int(rng.choice([8, 25, 60])), int(rng.integers(2, 5))
+    n = int(rng.choice([0, 30, 200, 800]))
+    tr = np.stack([rng.integers(0, n_terms, n), rng.integers(100, 100 + n_preds, n), rng.integers(0, n_terms, n)], axis=1).astype(np.uint32)
+    tr = np.unique(tr, axis=0) if n else tr
+    num = np.zeros(n_terms + 200)
+    isn = np.zeros(n_terms + 200, np.uint8)
+    numeric = rng.random(n_terms) < 0.7
+    num[:n_terms][numeric] = rng.integers(0, 100, int(numeric.sum()))
+    isn[:n_terms][numeric] = 1
+    rules = []
+    for r in range(int(rng.integers(1, 4))):
+        n_prem = int(rng.integers(1, 4))
+        prem, vars_ = [], []
+        for k in range(n_prem):
+            # a chain / star mix: reuse an earlier variable in one position, a fresh one in the other; constants now and then (quirk Q6)
+            a = int(rng.choice(vars_)) if vars_ and rng.random() < 0.8 else (max(vars_) + 1 if vars_ else 0)
+            b = max(vars_ + [a]) + 1
+            s_, o_ = (c.V(a), c.V(b)) if rng.random() < 0.5 else (c.V(b), c.V(a))
+            if rng.random() < 0.1:
+                o_ = c.K(int(rng.integers(0, n_terms)))
+            prem.append(c.pattern(s_, c.K(int(rng.integers(100, 100 + n_preds))), o_))
+            vars_ += [int(t.value) for t in (s_, o_) if t.is_var and int(t.value) not in vars_]
+        concl = []
+        for h in range(int(rng.integers(1, 3))):
+            hs = c.V(int(rng.choice(vars_))) if rng.random() < 0.9 else c.K(int(rng.integers(0, n_terms)))
+            ho = c.V(int(rng.choice(vars_))) if rng.random() < 0.9 else c.K(int(rng.integers(0, n_terms)))
+            concl.append(c.pattern(hs, c.K(int(rng.integers(100, 100 + n_preds + 1))), ho))  # sometimes a predicate no base fact has
+        filters = []
+        if rng.random() < 0.4:
+            lhs = int(rng.choice(vars_))
+            if rng.random() < 0.5 and len(vars_) > 1:
+                filters.append(c.KbRuleFilter(lhs, int(rng.choice([c.CMP_EQ, c.CMP_NE])), 1, int(rng.choice(vars_)), 0.0))
+            else:
+                filters.append(c.KbRuleFilter(lhs, int(rng.choice([c.CMP_GT, c.CMP_GE, c.CMP_LT, c.CMP_LE, c.CMP_EQ, c.CMP_NE])), 0, 0, float(rng.integers(0, 100))))
+        rules.append({"premise": prem, "conclusion": concl, "filters": filters})
+    return tr, num, isn, rules
+
+
+@pytest.mark.parametrize("seed", range(40))
+@pytest.mark.parametrize("strategy", [c.SEMI_NAIVE, c.NAIVE, c.SEMI_NAIVE_PARALLEL])
+def test_random_rules_vs_oracle(ctx, seed, strategy):
+    tr, num, isn, rules = random_rules(seed)
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2], num, isn)
+    want = db.fixpoint(rules, strategy)
+    ctx.dict_numeric_load(num, isn)
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    try:
+        rel, st = ctx.datalog_fixpoint(rules, strategy)
+    except c.KolibrieError as e:
+        assert e.status == c.KB_E_UNSUPPORTED and want["status"] != 0, (seed, str(e), want["status"])
+        return
+    assert want["status"] == 0, (seed, "the oracle declines this rule set, the device ran it")
+    H.assert_same_bag(rel.to_numpy([0, 1, 2]), want["facts"], f"rules seed {seed} strategy {strategy}")
+    assert [int(st.round_new[i]) for i in range(st.rounds)] == want["round_new"]
+    assert st.derivations == want["derivations"]
