@@ -117,6 +117,7 @@ def cpu_reference_run(args, steps, warmup):
     js, pats, filt = datagen.employee_queries(d)[args.query]
     db = O.Db(d.s, d.p, d.o, d.num_or0, d.is_num)
     db.build_index()
+    O.set_threads(O.usable_cpus())  # the CPU arm gets every host thread this process may use (affinity mask and cgroup quota)
     cores = O.num_threads()
     rows = 0
     for _ in range(max(1, min(warmup, 2))):

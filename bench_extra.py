@@ -84,11 +84,8 @@ def main():
         ctx.build_index()
         js, pats, _ = datagen.employee_queries(d)["cfg3"]
 
-        def step():
-            r = ctx.star_join(js, pats)
-            g = ctx.group_aggregate(r, [1], [(c.AGG_COUNT, 0)])
-            n = r.n_rows
-            r.free()
+        def step():  # kb_star_join_aggregate: with the index the GROUP BY is folded into the probe kernel, no joined row is written
+            g, n = ctx.star_join_aggregate(js, pats, None, [1], [(c.AGG_COUNT, 0)])
             return n, g
 
         for _ in range(3):
@@ -107,7 +104,7 @@ def main():
         assert int(g["counts"].sum()) == rows and len(g["counts"]) == 3
         emit({"workload": f"cfg3: {6 * E} triples per GPU x {world} GPU, 4-pattern star + GROUP BY ?t COUNT", "value": rows_all / dt, "unit": "bindings/s",
               "ms_per_query": dt * 1e3, "groups": 3, "n_gpus": world, "scaling": "weak",
-              "device_ms_per_query": {"join": st3["probe_ms"] / args.steps, "group": st3["group_ms"] / args.steps}})
+              "device_ms_per_query": {"join+group (one kernel)": st3["probe_ms"] / args.steps, "group": st3["group_ms"] / args.steps}})
 
     if "cfg4" in only:
         n_inst = int(48_888_890 * args.scale)

@@ -232,6 +232,12 @@ KB_API kb_status kb_groups_keys(const kb_groups* g, uint32_t col, const uint32_t
 KB_API kb_status kb_groups_values(const kb_groups* g, uint32_t agg, const double** values); /* host pointer, n_groups */
 KB_API kb_status kb_groups_counts(const kb_groups* g, const uint64_t** counts);            /* rows per group */
 KB_API void kb_groups_free(kb_groups* g);
+/* StarJoin + GROUP BY in one call (the aggregate of execute_query.rs:1150-1227 over the rows of engine.rs:587-691). With the store
+ * index valid, one GROUP BY variable and at most one aggregate, the grouping is folded into the probe kernel and no joined row is
+ * ever written; every other shape = kb_star_join followed by kb_group_aggregate. *n_rows (nullable) receives the joined row count. */
+KB_API kb_status kb_star_join_aggregate(kb_ctx* ctx, uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter,
+                                        uint32_t n_filter_ops, const uint32_t* group_slots, uint32_t n_group, const kb_agg* aggs, uint32_t n_aggs,
+                                        kb_groups** out, uint64_t* n_rows);
 
 /* ------------------------------------------------------------------ Datalog (Reasoner::infer_with_strategy, infer_generic.rs:27-53)
  * Facts = the ctx store. Inferred facts are appended to the store (segment tag KB_TAG_INFERRED), exactly as the

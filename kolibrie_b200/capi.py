@@ -180,6 +180,7 @@ def lib() -> C.CDLL:
         "kb_groups_values": (i32, [vp, u32, P(P(C.c_double))]),
         "kb_groups_counts": (i32, [vp, P(P(u64))]),
         "kb_groups_free": (None, [vp]),
+        "kb_star_join_aggregate": (i32, [vp, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), u32, P(KbAgg), u32, P(vp), P(u64)]),
         "kb_datalog_fixpoint": (i32, [vp, P(KbRule), u32, u32, P(vp), P(KbFixpointStats)]),
         "kb_shard_of": (u32, [u32, u32]),
         "kb_set_sharding": (i32, [vp, u32, u32]),
@@ -202,7 +203,7 @@ EXPORTED_SYMBOLS = [
     "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
     "kb_store_download", "kb_dict_numeric_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
-    "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free",
+    "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_star_join_aggregate",
     "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_star_join_host", "perform_hash_join_cuda",
 ]
 
@@ -453,6 +454,22 @@ class Context:
             ag[i] = KbAgg(k, s)
         g = C.c_void_p()
         self._check(lib().kb_group_aggregate(self.h, rel.h, gs, len(group_slots), ag, len(aggs), C.byref(g)))
+        return self._groups_to_dict(g)
+
+    def star_join_aggregate(self, join_slot: int, pats: Sequence[KbPattern], filt, group_slots: Sequence[int], aggs: Sequence[tuple]):
+        """kb_star_join_aggregate: star join + GROUP BY without materialising the join when the fused path applies.
+        Returns (groups dict as group_aggregate, joined row count)."""
+        a, nf = filter_prog(filt)
+        gs = (C.c_uint32 * max(len(group_slots), 1))(*group_slots)
+        ag = (KbAgg * max(len(aggs), 1))()
+        for i, (k, s) in enumerate(aggs):
+            ag[i] = KbAgg(k, s)
+        g = C.c_void_p()
+        n_rows = C.c_uint64()
+        self._check(lib().kb_star_join_aggregate(self.h, join_slot, patterns(pats), len(pats), a, nf, gs, len(group_slots), ag, len(aggs), C.byref(g), C.byref(n_rows)))
+        return self._groups_to_dict(g), n_rows.value
+
+    def _groups_to_dict(self, g):
         try:
             n, ng, na = C.c_uint64(), C.c_uint32(), C.c_uint32()
             self._check(lib().kb_groups_info(g, C.byref(n), C.byref(ng), C.byref(na)))

@@ -736,7 +736,7 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
 }
 
 kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 K, const kb_filter_op* filter, u32 n_ops, bool allow_fused_scan,
-                          std::unique_ptr<kb_rel>* out) {
+                          std::unique_ptr<kb_rel>* out, AggSpec* agg) {
     if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a star join takes 1..%d patterns (got %u)", MAXP, K);
     KB_TRY(validate_filter(ctx, filter, n_ops));
     std::vector<std::vector<u32>> pv(K), psrc(K);
@@ -893,6 +893,60 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 P.n_ops = (u32)fops.size();
                 for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
             }
+            P.pairs = reinterpret_cast<const uint2*>(PS.pairs.ptr);
+            P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
+            P.n = (u32)PS.n;
+            P.n_tiles = (u32)((PS.n + PROBEF_TILE - 1) / PROBEF_TILE);
+            P.T = T;
+            P.cap = (u32)PS.n;
+            P.nt = numtab(ctx);
+            P.cb = ctx->fast_cb;
+            P.host_total = ctx->d_fast;
+            if (agg) {
+                // GROUP BY folded into the probe kernel: no joined row is written. One try with a 4096-slot table; more groups than
+                // that (or a group / aggregate variable the join does not bind) leave agg->applied false: the caller groups separately
+                int gsel = -1, asel = -1;
+                for (u32 c = 0; c < n_out; c++) {
+                    if (out_slots[c] == agg->group_slot) gsel = (int)c;
+                    if (agg->has_agg && out_slots[c] == agg->agg_slot) asel = (int)c;
+                }
+                const bool needs_value = agg->has_agg && agg->kind != KB_AGG_COUNT;
+                if (gsel >= 0 && (!needs_value || asel >= 0)) {
+                    GroupParams G{};
+                    G.n_gcols = 1;
+                    G.n_aggs = agg->has_agg ? 1u : 0u;
+                    G.akind[0] = agg->has_agg ? agg->kind : (u32)KB_AGG_COUNT;
+                    G.nt = numtab(ctx);
+                    GroupTable tab;
+                    KB_TRY(group_table_create(ctx, 1u << 12, &G, &tab));
+                    const u32 goff = ctrl_alloc(ctx, 4);
+                    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + goff, 0, 4 * sizeof(u32), ctx->st));
+                    G.overflow = ctx->ctrl + goff;
+                    P.gsel = (u32)gsel;
+                    P.asel = asel >= 0 ? (u32)asel : 0u;
+                    P.akind = G.akind[0];
+                    P.ordered = 0;
+                    P.epoch = ctx->epoch++;
+                    timer_begin(ctx, F_PROBE);
+                    launch_probe_index(P, &G, ctx->n_sms, ctx->st);
+                    timer_end(ctx);
+                    KB_CUDA(ctx, cudaGetLastError());
+                    ctx->stats.rows_probed += PS.n;
+                    ctx->stats.index_joins++;
+                    KB_TRY(ctrl_read(ctx));
+                    if (ctx->h_ctrl[goff] == 0) {
+                        agg->n_rows = *reinterpret_cast<volatile u32*>(ctx->h_fast);
+                        agg->groups = std::make_unique<kb_groups>();
+                        agg->groups->keys.resize(1);
+                        agg->groups->vals.resize(agg->has_agg ? 1 : 0);
+                        kb_agg a1{agg->kind, agg->agg_slot};
+                        KB_TRY(group_table_collect(ctx, tab, 1, &a1, agg->has_agg ? 1u : 0u, agg->groups.get()));
+                        agg->applied = true;
+                        return KB_OK;
+                    }
+                }
+                // fall through: join without the fused GROUP BY (the control block was left clean by the kernel)
+            }
             auto res = std::make_unique<kb_rel>();
             res->slots = out_slots;
             {   // one allocation holds all output columns
@@ -907,13 +961,6 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                     P.out[c] = col.ptr;
                 }
             }
-            P.pairs = reinterpret_cast<const uint2*>(PS.pairs.ptr);
-            P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
-            P.n = (u32)PS.n;
-            P.n_tiles = (u32)((PS.n + PROBEF_TILE - 1) / PROBEF_TILE);
-            P.T = T;
-            P.cap = (u32)PS.n;
-            P.nt = numtab(ctx);
             P.ordered = ctx->ordered;
             if (P.ordered) {
                 KB_TRY(ensure_tile_state(ctx, P.n_tiles));
@@ -921,10 +968,8 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 P.block_state = static_cast<u64*>(ctx->block_state->p);
             }
             P.epoch = ctx->epoch++;
-            P.cb = ctx->fast_cb;
-            P.host_total = ctx->d_fast;
             timer_begin(ctx, F_PROBE);
-            launch_probe_index(P, ctx->n_sms, ctx->st);
+            launch_probe_index(P, nullptr, ctx->n_sms, ctx->st);
             timer_end(ctx);
             KB_CUDA(ctx, cudaGetLastError());
             ctx->stats.rows_probed += PS.n;
@@ -1072,7 +1117,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 dup = true;
                 ctx->multi_valued.insert({pats[tab_k[q]].p.value, key_pos(tab_k[q])});
             }
-            if (dup) return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, true, out);  // multi-valued is now cached: takes the chained route
+            if (dup) return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, true, out, agg);  // multi-valued is now cached: takes the chained route
             for (u32 q = 0; q < T; q++)
                 if (!persistent(tab_k[q]) && pushdown[tab_k[q]].ops.empty()) ctx->single_valued.insert({pats[tab_k[q]].p.value, key_pos(tab_k[q])});
             res->n = ctx->h_ctrl[off + 1];
@@ -1184,7 +1229,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             for (u32 k = 0; k < K; k++) if ((int)k != probe_k && ctx->h_ctrl[off + 8 + tab_of[k]]) {  // key outside the table range (cannot happen with store statistics)
                 KB_TRY(ctrl_read(ctx));
                 check_dups();
-                return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, false, out);
+                return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, false, out, agg);
             }
             const kb_rel& PR = *rels[probe_k];
             auto res = std::make_unique<kb_rel>();
@@ -1233,7 +1278,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             ctx->stats.rows_probed += PR.n;
             KB_TRY(ctrl_read(ctx));
             if (check_dups())  // a build side is multi-valued: redo without the fusion (the chained operator needs the build rows)
-                return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, false, out);
+                return star_join_impl2(ctx, join_slot, pats, K, filter, n_ops, false, out, agg);
             for (u32 k = 0; k < K; k++)
                 if ((int)k != probe_k && !pats[k].p.is_var && pushdown[k].ops.empty()) ctx->single_valued.insert({pats[k].p.value, key_pos(k)});
             res->n = ctx->h_ctrl[off2 + 1];
@@ -1500,6 +1545,62 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
     if (!(ctx)) return KB_E_INVALID;                          \
     kb::DeviceGuard _guard((ctx)->device);                    \
     KB_TRY(kb::begin_call(ctx))
+
+namespace kb {
+kb_status group_table_create(kb_ctx* ctx, u64 slots, GroupParams* P, GroupTable* t) {
+    t->slots = slots;
+    t->o_val = 0;
+    t->o_cnt = t->o_val + slots * 8 * sizeof(double);
+    t->o_keys = t->o_cnt + slots * sizeof(unsigned long long);
+    t->o_state = t->o_keys + slots * 4 * sizeof(u32);
+    t->bytes = t->o_state + slots * sizeof(u32);
+    KB_TRY(alloc_buf(ctx, t->bytes, &t->buf));
+    char* tb = static_cast<char*>(t->buf->p);
+    P->n_slots = (u32)slots;
+    P->gval = (double*)(tb + t->o_val);
+    P->gcnt = (unsigned long long*)(tb + t->o_cnt);
+    P->gkeys = (u32*)(tb + t->o_keys);
+    P->gstate = (u32*)(tb + t->o_state);
+    launch_group_init(*P, ctx->st);
+    return KB_OK;
+}
+kb_status group_table_collect(kb_ctx* ctx, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g) {
+    std::vector<char> big;  // tables past 32 MB (hundreds of thousands of groups) are not worth pinning
+    void* dst = nullptr;
+    if (t.bytes <= (32u << 20)) {
+        if (ctx->pinned_bytes < t.bytes) {
+            if (ctx->pinned) cudaFreeHost(ctx->pinned);
+            ctx->pinned = nullptr; ctx->pinned_bytes = 0;
+            KB_CUDA(ctx, cudaMallocHost(&ctx->pinned, t.bytes));
+            ctx->pinned_bytes = t.bytes;
+        }
+        dst = ctx->pinned;
+    } else {
+        big.resize(t.bytes);
+        dst = big.data();
+    }
+    KB_CUDA(ctx, cudaMemcpyAsync(dst, t.buf->p, t.bytes, cudaMemcpyDeviceToHost, ctx->st));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->stats.d2h_bytes += t.bytes;
+    const char* hb = static_cast<const char*>(dst);
+    const double* hval = (const double*)(hb + t.o_val);
+    const unsigned long long* hcnt = (const unsigned long long*)(hb + t.o_cnt);
+    const u32* hkeys = (const u32*)(hb + t.o_keys);
+    const u32* hstate = (const u32*)(hb + t.o_state);
+    for (u64 i = 0; i < t.slots; i++) {
+        if (hstate[i] != 2u) continue;
+        for (u32 c = 0; c < n_group; c++) g->keys[c].push_back(hkeys[i * 4 + c]);
+        g->counts.push_back(hcnt[i]);
+        for (u32 a = 0; a < n_aggs; a++) {
+            double v = hval[i * 8 + a];
+            if (aggs[a].kind == KB_AGG_AVG) v = v / (double)hcnt[i];   // execute_query.rs:1216
+            if (aggs[a].kind == KB_AGG_COUNT) v = (double)hcnt[i];
+            g->vals[a].push_back(v);
+        }
+    }
+    return KB_OK;
+}
+}  // namespace kb
 
 extern "C" {
 
@@ -2223,57 +2324,18 @@ kb_status kb_group_aggregate(kb_ctx* ctx, const kb_rel* in, const uint32_t* grou
     if (in->n == 0) { *out = g.release(); return KB_OK; }
     u64 slots = 1u << 12;  // small first try: the table is downloaded whole; overflow -> 16x larger and rerun
     for (;;) {
-        P.n_slots = (u32)slots;
-        // one device buffer [val | cnt | keys | state] so that the table comes back in one copy into pinned memory
-        const size_t o_val = 0, o_cnt = o_val + slots * 8 * sizeof(double), o_keys = o_cnt + slots * sizeof(unsigned long long),
-                     o_state = o_keys + slots * 4 * sizeof(u32), tab_bytes = o_state + slots * sizeof(u32);
-        kb::Buf tab;
-        KB_TRY(kb::alloc_buf(ctx, tab_bytes, &tab));
-        char* tb = static_cast<char*>(tab->p);
-        P.gval = (double*)(tb + o_val); P.gcnt = (unsigned long long*)(tb + o_cnt); P.gkeys = (u32*)(tb + o_keys); P.gstate = (u32*)(tb + o_state);
+        kb::GroupTable tab;
+        KB_TRY(kb::group_table_create(ctx, slots, &P, &tab));
         const u32 off = kb::ctrl_alloc(ctx, 4);
         KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
         P.overflow = ctx->ctrl + off;
         kb::timer_begin(ctx, kb::F_GROUP, 2);
-        kb::launch_group_init(P, ctx->st);
         kb::launch_group(P, ctx->n_sms, ctx->st);
         kb::timer_end(ctx);
         KB_CUDA(ctx, cudaGetLastError());
         KB_TRY(kb::ctrl_read(ctx));
         if (ctx->h_ctrl[off] == 0) {
-            std::vector<char> big;  // tables past 32 MB (hundreds of thousands of groups) are not worth pinning
-            void* dst = nullptr;
-            if (tab_bytes <= (32u << 20)) {
-                if (ctx->pinned_bytes < tab_bytes) {
-                    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-                    ctx->pinned = nullptr; ctx->pinned_bytes = 0;
-                    KB_CUDA(ctx, cudaMallocHost(&ctx->pinned, tab_bytes));
-                    ctx->pinned_bytes = tab_bytes;
-                }
-                dst = ctx->pinned;
-            } else {
-                big.resize(tab_bytes);
-                dst = big.data();
-            }
-            KB_CUDA(ctx, cudaMemcpyAsync(dst, tb, tab_bytes, cudaMemcpyDeviceToHost, ctx->st));
-            KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
-            ctx->stats.d2h_bytes += tab_bytes;
-            const char* hb = static_cast<const char*>(dst);
-            const double* hval = (const double*)(hb + o_val);
-            const unsigned long long* hcnt = (const unsigned long long*)(hb + o_cnt);
-            const u32* hkeys = (const u32*)(hb + o_keys);
-            const u32* hstate = (const u32*)(hb + o_state);
-            for (u64 i = 0; i < slots; i++) {
-                if (hstate[i] != 2u) continue;
-                for (u32 c = 0; c < n_group; c++) g->keys[c].push_back(hkeys[i * 4 + c]);
-                g->counts.push_back(hcnt[i]);
-                for (u32 a = 0; a < n_aggs; a++) {
-                    double v = hval[i * 8 + a];
-                    if (aggs[a].kind == KB_AGG_AVG) v = v / (double)hcnt[i];   // execute_query.rs:1216
-                    if (aggs[a].kind == KB_AGG_COUNT) v = (double)hcnt[i];
-                    g->vals[a].push_back(v);
-                }
-            }
+            KB_TRY(kb::group_table_collect(ctx, tab, n_group, aggs, n_aggs, g.get()));
             break;
         }
         if (slots >= 2 * in->n && slots >= (1u << 20)) return kb::fail(ctx, KB_E_LIMIT, "group table overflow");
@@ -2306,6 +2368,31 @@ kb_status kb_groups_counts(const kb_groups* g, const uint64_t** counts) {
     return KB_OK;
 }
 void kb_groups_free(kb_groups* g) { delete g; }
+
+kb_status kb_star_join_aggregate(kb_ctx* ctx, uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops,
+                                 const uint32_t* group_slots, uint32_t n_group, const kb_agg* aggs, uint32_t n_aggs, kb_groups** out, uint64_t* n_rows) {
+    KB_ENTER(ctx);
+    if (!pats || !out || (n_group && !group_slots) || (n_aggs && !aggs)) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n_group == 0 || n_group > 4) return kb::fail(ctx, KB_E_LIMIT, "GROUP BY takes 1..4 variables");
+    if (n_aggs > 8) return kb::fail(ctx, KB_E_LIMIT, "at most 8 aggregates");
+    for (u32 a = 0; a < n_aggs; a++) if (aggs[a].kind > KB_AGG_AVG) return kb::fail(ctx, KB_E_INVALID, "unknown aggregate kind %u", aggs[a].kind);
+    kb::AggSpec spec;
+    const bool fusable = n_group == 1 && n_aggs <= 1;
+    if (fusable) {
+        spec.group_slot = group_slots[0];
+        spec.has_agg = n_aggs == 1;
+        if (n_aggs) { spec.kind = aggs[0].kind; spec.agg_slot = aggs[0].slot; }
+    }
+    std::unique_ptr<kb_rel> rel;
+    KB_TRY(kb::star_join_impl2(ctx, join_slot, pats, n_pats, filter, n_ops, true, &rel, fusable ? &spec : nullptr));
+    if (spec.applied) {
+        if (n_rows) *n_rows = spec.n_rows;
+        *out = spec.groups.release();
+        return KB_OK;
+    }
+    if (n_rows) *n_rows = rel->n;
+    return kb_group_aggregate(ctx, rel.get(), group_slots, n_group, aggs, n_aggs, out);
+}
 
 // ------------------------------------------------------------------ multi-GPU helpers
 uint32_t kb_shard_of(uint32_t key, uint32_t n_shards) { return n_shards ? kb::shard_of(key, n_shards) : 0; }

@@ -196,8 +196,26 @@ struct ScanTable {  // scan+build fusion: pattern k inserts its matches into thi
 };
 kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 n_pats, const std::vector<FilterProg>& pushdown, bool want_index, bool pairs,
                     std::vector<std::unique_ptr<kb_rel>>* out, const std::vector<ScanTable>* tables = nullptr);
+// fused GROUP BY of a star join (kb_star_join_aggregate): in = group / aggregate spec; out = groups when the one-kernel index path took it
+struct AggSpec {
+    u32 group_slot = 0;
+    bool has_agg = false;
+    u32 kind = 0, agg_slot = 0;
+    bool applied = false;  // false on return: the caller joins and groups in two steps
+    u64 n_rows = 0;        // joined rows (when applied)
+    std::unique_ptr<kb_groups> groups;
+};
 kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 n_pats, const kb_filter_op* filter, u32 n_ops, bool allow_fused_scan,
-                          std::unique_ptr<kb_rel>* out);
+                          std::unique_ptr<kb_rel>* out, AggSpec* agg = nullptr);
+// GROUP BY hash table on the device (kb_group_aggregate and the fused path): one buffer [val | cnt | keys | state]
+struct GroupTable {
+    Buf buf;
+    u64 slots = 0;
+    size_t o_val = 0, o_cnt = 0, o_keys = 0, o_state = 0, bytes = 0;
+};
+kb_status group_table_create(kb_ctx* ctx, u64 slots, GroupParams* P, GroupTable* t);  // allocates, points P at it, runs the init kernel
+// downloads the table and appends its groups to g (AVG divided, COUNT filled in)
+kb_status group_table_collect(kb_ctx* ctx, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g);
 kb_status segment_stats(kb_ctx* ctx, Segment* sg);
 kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r);
 kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);

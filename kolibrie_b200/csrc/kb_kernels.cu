@@ -732,8 +732,15 @@ void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st) {
 #ifndef KB_PI_MINB
 #define KB_PI_MINB 4
 #endif
-template <int T, int PRE>
-__global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel(const __grid_constant__ ProbeIParams P) {
+// AGG = true: the joined rows are not written; GROUP BY one output column with at most one aggregate is folded in the kernel
+// (execute_query.rs:1150-1227 over the rows of engine.rs:587-691): per warp __match_any_sync on the key, a 64-entry CTA table in shared
+// memory, flushed to the global group table when the CTA is done. Only the row count and the groups leave the kernel.
+constexpr int PI_GROUP_SMEM = 64;
+__device__ void group_update_global(const GroupParams& P, const u32* k, unsigned long long cnt, const double* val);
+__device__ void atomic_min_f64(double* addr, double v);
+__device__ void atomic_max_f64(double* addr, double v);
+template <int T, int PRE, bool AGG>
+__global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel(const __grid_constant__ ProbeIParams P, const __grid_constant__ GroupParams G) {
     constexpr int R = 4;  // rows per thread (striped over the warp's 128-row chunk, see below)
     constexpr u32 TILE = PROBEF_THREADS * R;
     extern __shared__ __align__(128) u32 smem_all[];  // per stage: TILE pairs [+ TILE doubles]
@@ -742,7 +749,18 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
     __shared__ u32 s_nexts[2];
     __shared__ u32 s_wcnt[PROBEF_THREADS / 32];
     __shared__ u32 s_excl1;
+    __shared__ u32 a_key[AGG ? PI_GROUP_SMEM : 1];
+    __shared__ u32 a_cnt[AGG ? PI_GROUP_SMEM : 1];
+    __shared__ double a_val[AGG ? PI_GROUP_SMEM : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u32 my_rows = 0;  // AGG: joined rows seen by this thread
+    if (AGG) {
+        for (int i = tid; i < PI_GROUP_SMEM; i += PROBEF_THREADS) {
+            a_key[i] = EMPTY32;
+            a_cnt[i] = 0u;
+            a_val[i] = P.akind == KB_AGG_MIN ? CUDART_INF : (P.akind == KB_AGG_MAX ? -CUDART_INF : 0.0);
+        }
+    }
     auto issue = [&](u32 t, u32 stage) {
         u32* smem = smem_all + stage * STAGE_WORDS;
         u64& bar = bars[stage];
@@ -833,6 +851,68 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
                 }
             }
         }
+        if constexpr (AGG) {
+            __syncthreads();  // every thread holds its rows in registers: the stage can take the tile after next
+            const u32 following_a = s_nexts[stage ^ 1u];
+            if (tid == 32) {
+                const u32 nt = atomicAdd(&P.cb[0], 1u);
+                s_nexts[stage] = nt;
+                if (nt < P.n_tiles) issue(nt, stage);
+            }
+            my_rows += (u32)__popc(m);
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const bool on = (m >> j) & 1u;
+                const unsigned act = __ballot_sync(0xffffffffu, on);
+                if (act == 0u || !on) continue;
+                u32 key = P.gsel == 0u ? rx[j] : ry[j];
+                u32 vid = P.asel == 0u ? rx[j] : ry[j];
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    if (P.gsel == 2u + (u32)t) key = tv[j][t];
+                    if (P.asel == 2u + (u32)t) vid = tv[j][t];
+                }
+                const unsigned peers = __match_any_sync(act, key);
+                const int leader = __ffs(peers) - 1;
+                double acc = 0.0;
+                if (P.akind != KB_AGG_COUNT) {
+                    const double mine = num_of(P.nt, vid);
+                    acc = mine;
+                    unsigned rest = peers & ~(1u << leader);
+                    while (rest) {  // every lane of the group runs the same shuffles
+                        const int src = __ffs(rest) - 1;
+                        rest &= rest - 1u;
+                        const double o = __shfl_sync(peers, mine, src);
+                        if (P.akind == KB_AGG_MIN) acc = fmin(acc, o);
+                        else if (P.akind == KB_AGG_MAX) acc = fmax(acc, o);
+                        else acc += o;
+                    }
+                }
+                if (lane != leader) continue;
+                const u32 cnt_g = (u32)__popc(peers);
+                u32 slot = mix32(key) & (PI_GROUP_SMEM - 1);
+                bool done = false;
+                for (int probes = 0; probes < PI_GROUP_SMEM && !done && key != EMPTY32; probes++) {  // EMPTY32 marks a free entry
+                    u32 cur = *reinterpret_cast<volatile u32*>(&a_key[slot]);
+                    if (cur == EMPTY32) cur = atomicCAS(&a_key[slot], EMPTY32, key);
+                    if (cur == EMPTY32 || cur == key) {
+                        atomicAdd(&a_cnt[slot], cnt_g);
+                        if (P.akind == KB_AGG_MIN) atomic_min_f64(&a_val[slot], acc);
+                        else if (P.akind == KB_AGG_MAX) atomic_max_f64(&a_val[slot], acc);
+                        else if (P.akind != KB_AGG_COUNT) atomicAdd(&a_val[slot], acc);
+                        done = true;
+                    } else slot = (slot + 1u) & (PI_GROUP_SMEM - 1);
+                }
+                if (!done) {  // more than 64 distinct groups in this CTA
+                    u32 kk[4] = {key, 0u, 0u, 0u};
+                    double vv[8] = {acc, 0, 0, 0, 0, 0, 0, 0};
+                    group_update_global(G, kk, (unsigned long long)cnt_g, vv);
+                }
+            }
+            tile = following_a;
+            it++;
+            continue;
+        }
         u32 bal[R];
         u32 wtot = 0;
 #pragma unroll
@@ -880,6 +960,18 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
         tile = following;
         it++;
     }
+    if constexpr (AGG) {
+        __syncthreads();
+        for (int i = tid; i < PI_GROUP_SMEM; i += PROBEF_THREADS) {
+            if (a_key[i] == EMPTY32) continue;
+            u32 kk[4] = {a_key[i], 0u, 0u, 0u};
+            double vv[8] = {a_val[i], 0, 0, 0, 0, 0, 0, 0};
+            group_update_global(G, kk, (unsigned long long)a_cnt[i], vv);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_rows += __shfl_xor_sync(0xffffffffu, my_rows, o);
+        if (lane == 0 && my_rows) atomicAdd(&P.cb[1], my_rows);
+    }
     // the last CTA to get here publishes the row count and leaves the control block zeroed for the next launch
     __syncthreads();
     if (tid == 0) {
@@ -896,30 +988,36 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
     }
 }
 
-template <int T, int PRE>
-static void launch_probe_index_tp(const ProbeIParams& p, int n_sms, cudaStream_t st) {
+template <int T, int PRE, bool AGG>
+static void launch_probe_index_tp(const ProbeIParams& p, const GroupParams& g, int n_sms, cudaStream_t st) {
     static int per_sm = 0;  // occupancy is a property of the kernel image: asked once per instantiation
     const size_t smem = (size_t)PROBEF_THREADS * 4 * (PRE == 1 ? 16 : 8) * 2;
     if (per_sm == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_index_kernel<T, PRE>, PROBEF_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_index_kernel<T, PRE, AGG>, PROBEF_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
     }
-    long long g = (long long)per_sm * n_sms;
-    if (g > (long long)p.n_tiles) g = p.n_tiles;
-    probe_index_kernel<T, PRE><<<(int)g, PROBEF_THREADS, smem, st>>>(p);
+    long long grid = (long long)per_sm * n_sms;
+    if (grid > (long long)p.n_tiles) grid = p.n_tiles;
+    probe_index_kernel<T, PRE, AGG><<<(int)grid, PROBEF_THREADS, smem, st>>>(p, g);
 }
 template <int T>
-static void launch_probe_index_t(const ProbeIParams& p, int n_sms, cudaStream_t st) {
-    if (p.pre_mode == 1u) launch_probe_index_tp<T, 1>(p, n_sms, st);
-    else launch_probe_index_tp<T, 0>(p, n_sms, st);
+static void launch_probe_index_t(const ProbeIParams& p, const GroupParams* g, int n_sms, cudaStream_t st) {
+    static const GroupParams none{};
+    if (g) {
+        if (p.pre_mode == 1u) launch_probe_index_tp<T, 1, true>(p, *g, n_sms, st);
+        else launch_probe_index_tp<T, 0, true>(p, *g, n_sms, st);
+    } else {
+        if (p.pre_mode == 1u) launch_probe_index_tp<T, 1, false>(p, none, n_sms, st);
+        else launch_probe_index_tp<T, 0, false>(p, none, n_sms, st);
+    }
 }
-void launch_probe_index(const ProbeIParams& p, int n_sms, cudaStream_t st) {
+void launch_probe_index(const ProbeIParams& p, const GroupParams* agg, int n_sms, cudaStream_t st) {
     if (p.n == 0) return;
     switch (p.T) {
-        case 1: launch_probe_index_t<1>(p, n_sms, st); break;
-        case 2: launch_probe_index_t<2>(p, n_sms, st); break;
-        case 3: launch_probe_index_t<3>(p, n_sms, st); break;
-        default: launch_probe_index_t<4>(p, n_sms, st); break;
+        case 1: launch_probe_index_t<1>(p, agg, n_sms, st); break;
+        case 2: launch_probe_index_t<2>(p, agg, n_sms, st); break;
+        case 3: launch_probe_index_t<3>(p, agg, n_sms, st); break;
+        default: launch_probe_index_t<4>(p, agg, n_sms, st); break;
     }
 }
 
@@ -1481,7 +1579,7 @@ void launch_cartesian(const u32* const* lcols, u32 nl, u32 n_lcols, const u32* c
 
 // =================================================================================================================
 // K_group
-__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+__device__ void atomic_min_f64(double* addr, double v) {
     unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
     unsigned long long old = *a;
     while (v < __longlong_as_double((long long)old) || __longlong_as_double((long long)old) != __longlong_as_double((long long)old)) {
@@ -1490,7 +1588,7 @@ __device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
         if (old == assumed) break;
     }
 }
-__device__ __forceinline__ void atomic_max_f64(double* addr, double v) {
+__device__ void atomic_max_f64(double* addr, double v) {
     unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
     unsigned long long old = *a;
     while (v > __longlong_as_double((long long)old) || __longlong_as_double((long long)old) != __longlong_as_double((long long)old)) {
@@ -1545,7 +1643,7 @@ __device__ __forceinline__ u32 group_slot(const GroupParams& P, const u32* k) {
 // (1) a warp folds its 32 rows per distinct group (__match_any_sync), (2) leaders accumulate into a 64-entry shared-memory
 // table of the CTA, flushed to the global table once per CTA. Rows whose group does not fit the CTA table go straight to global.
 constexpr int GROUP_SMEM = 64;
-__device__ __forceinline__ void group_update_global(const GroupParams& P, const u32* k, unsigned long long cnt, const double* val) {
+__device__ void group_update_global(const GroupParams& P, const u32* k, unsigned long long cnt, const double* val) {
     const u32 slot = group_slot(P, k);
     if (slot == EMPTY32) { *P.overflow = 1u; return; }
     atomicAdd(&P.gcnt[slot], cnt);

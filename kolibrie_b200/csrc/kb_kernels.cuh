@@ -180,10 +180,13 @@ struct ProbeIParams {
     u64* block_state;
     u32 ordered;
     u64 epoch;
+    u32 gsel, asel, akind;  // fused GROUP BY (launch_probe_index with `agg`): output column of the key / of the aggregated value, kb_agg kind
     u32* cb;          // device control block: [0] ticket, [1] total, [2] always 0, [3] CTAs done
     u32* host_total;  // mapped pinned host word
 };
-void launch_probe_index(const ProbeIParams& p, int n_sms, cudaStream_t st);
+struct GroupParams;
+// agg == nullptr: the joined rows are written to p.out; else they are folded into the group table *agg (GROUP BY column p.gsel)
+void launch_probe_index(const ProbeIParams& p, const GroupParams* agg, int n_sms, cudaStream_t st);
 void launch_unpair(const uint2* kv, u32 n, u32* x, u32* y, cudaStream_t st);
 // direct build from a predicate slice of the store index, with the pattern's pushed-down FILTER evaluated on (s, P, o)
 struct BuildPairsParams {

@@ -14,11 +14,32 @@ LIB = os.path.join(ROOT, "oracle", "liboracle.so")
 _L = None
 
 
+def usable_cpus() -> int:
+    """CPUs this process may really use: affinity mask and cgroup quota, not the machine's thread count. An OpenMP team sized by
+    `nproc` on a box whose container is capped far below it spends its time in oversubscribed barriers (measured: 0.4-1.1 s per tiny
+    oracle query with 128 threads)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(q) // int(per)))
+    except (OSError, ValueError):
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
+
+
 def lib():
     global _L
     if _L is None:
         if not os.path.exists(LIB):
             raise ImportError(f"{LIB} missing: run `make -C oracle`")
+        os.environ.setdefault("OMP_WAIT_POLICY", "passive")  # idle team members sleep instead of spinning next to the CUDA host thread
         L = C.CDLL(LIB)
         vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
         P = C.POINTER
@@ -46,6 +67,7 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _L = L
+        L.ko_set_threads(min(usable_cpus(), int(os.environ.get("KOLIBRIE_ORACLE_THREADS", "16"))))  # checker runs: small inputs
     return _L
 
 

@@ -275,6 +275,51 @@ def test_group_aggregate_vs_oracle(ctx, emp):
             assert np.allclose(a, b, rtol=1e-12, atol=0)
 
 
+def test_star_join_aggregate_fused_vs_oracle(ctx, emp):
+    """kb_star_join_aggregate: GROUP BY folded into the index probe kernel (no joined row is written) for one group variable and at
+    most one aggregate; every other shape, and a store without index, takes join + group — all must equal the oracle's group over
+    the oracle's join"""
+    d, db = emp
+    js, pats, _ = datagen.employee_queries(d)["cfg3"]          # slots: e=0, t=1, s=2, n=3, c=4
+    _, pats2, filt2 = datagen.employee_queries(d)["cfg2"]
+
+    def table(x):
+        keys = np.stack(x["keys"], axis=1)
+        order = np.lexsort(tuple(keys[:, k] for k in range(keys.shape[1] - 1, -1, -1)))
+        return keys[order], x["counts"][order], [v[order] for v in x["values"]]
+
+    def check(pp, ff, gslots, aggs, what):
+        g, n_rows = ctx.star_join_aggregate(js, pp, ff, gslots, aggs)
+        orel = db.bgp(pp, ff)
+        w = db.group(orel, gslots, aggs)
+        gk, gc, gv = table(g)
+        wk, wc, wv = table(w)
+        assert n_rows == len(orel.to_numpy(sorted(orel.slots))), what
+        assert np.array_equal(gk, wk) and np.array_equal(gc, wc), what
+        for a, b in zip(gv, wv):
+            assert np.allclose(a, b, rtol=1e-12, atol=0), what
+
+    one = [[(c.AGG_COUNT, 0)], [(c.AGG_SUM, 2)], [(c.AGG_MIN, 2)], [(c.AGG_MAX, 2)], [(c.AGG_AVG, 2)], []]
+    for indexed in (True, False):
+        if indexed:
+            ctx.build_index()
+        before = ctx.get_stats()["kernel_launches"]
+        for aggs in one:
+            check(pats, None, [1], aggs, f"by title {aggs} indexed={indexed}")            # 3 groups: the CTA table
+            check(pats, None, [2], aggs, f"by salary {aggs} indexed={indexed}")           # thousands of groups: past the CTA table, past 4096 slots
+            check(pats2, filt2, [1], aggs, f"FILTER + by title {aggs} indexed={indexed}")  # typed pre-filter on the probe slice
+        check(pats, None, [1, 4], [(c.AGG_COUNT, 0)], "two group variables: join + group")
+        check(pats, None, [1], [(c.AGG_COUNT, 0), (c.AGG_SUM, 2)], "two aggregates: join + group")
+        f_post = [c.fop(c.F_NE_ID, slot=1, id=d.ids["Manager"]), c.fop(c.F_CMP_NUM, slot=2, cmp=c.CMP_GT, value=70000.0), c.fop(c.F_AND)]
+        check(pats, f_post, [1], [(c.AGG_AVG, 2)], "filters on two patterns")
+        if indexed:  # COUNT by title with the index: one probe launch + the table init, nothing else
+            n0 = ctx.get_stats()["kernel_launches"]
+            ctx.star_join_aggregate(js, pats, None, [1], [(c.AGG_COUNT, 0)])
+            assert ctx.get_stats()["kernel_launches"] - n0 <= 2
+        assert ctx.get_stats()["kernel_launches"] > before
+        ctx.store_load(d.s, d.p, d.o)  # drops the index for the second pass
+
+
 def test_legacy_ffi_symbol(ctx):
     """perform_hash_join_cuda as Kolibrie's hash_join_cuda calls it (cuda_join.rs:28-60): ascending indices, literal honoured"""
     d = datagen.employee_dataset(60000)  # 360 000 triples: beyond the reference stub's ~303 K clamp (cuda_join.cu:81-88)
