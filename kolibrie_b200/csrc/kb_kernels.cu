@@ -111,12 +111,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
                 if (P.pat[k].f_len == 1u && fo[0].op == KB_F_CMP_NUM) {  // FILTER(?x <cmp> c): gather the 8 numeric values, then compare
                     const u32 slot = fo[0].slot, cmp = fo[0].cmp;
                     const double cv = fo[0].value;
+                    // the column is chosen once (two vector selects), not once per element
+                    const uint4 x0 = slot == 0u ? s0 : (slot == 1u ? p0 : o0);
+                    const uint4 x1 = slot == 0u ? s1 : (slot == 1u ? p1 : o1);
                     double a[8];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const u32 id = slot == 0u ? KB_ELEM(s0, s1, j) : (slot == 1u ? KB_ELEM(p0, p1, j) : KB_ELEM(o0, o1, j));
-                        a[j] = ((m >> j) & 1u) ? num_of(P.nt, id) : 0.0;
-                    }
+                    for (int j = 0; j < 8; j++) a[j] = ((m >> j) & 1u) ? num_of(P.nt, KB_ELEM(x0, x1, j)) : 0.0;
                     u32 pass = 0;
 #pragma unroll
                     for (int j = 0; j < 8; j++) pass |= (cmp_num(cmp, a[j], cv) ? 1u : 0u) << j;
@@ -180,19 +180,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
             if (f & SP_TABLE) {  // fused build: insert into the direct table of this pattern
                 u32* tab = P.pat[k].outp[0];
                 const u32 kbase = P.pat[k].cs, krange = P.pat[k].co;
-                bool dup = false;
+                // key / value columns chosen once; offsets computed for all eight triples, stores predicated (no branch per triple).
+                // Plain fire-and-forget stores: a returning atomic here stalls the tile loop (measured 0.61 ms vs 0.49 ms for separate
+                // scan + build); duplicate keys are detected afterwards by counting the occupied slots
+                const bool key_o = (f & SP_TKEY_O) != 0u;
+                const uint4 k0 = key_o ? o0 : s0, k1 = key_o ? o1 : s1;
+                const uint4 v0 = key_o ? s0 : o0, v1 = key_o ? s1 : o1;
+                u32 bad = 0;
+                if (P.cshift == 0u) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if ((m >> j) & 1u) {
-                        const u32 key = (f & SP_TKEY_O) ? KB_ELEM(o0, o1, j) : KB_ELEM(s0, s1, j);
-                        const u32 val = (f & SP_TKEY_O) ? KB_ELEM(s0, s1, j) : KB_ELEM(o0, o1, j);
-                        const u32 off = compact_key(key, P.cshift) - kbase;
-                        // plain fire-and-forget store: a returning atomic here stalls the tile loop (measured 0.61 ms vs 0.49 ms for
-                        // separate scan + build); duplicate keys are detected afterwards by counting the occupied slots
-                        if (off < krange) tab[off] = val;
-                        else dup = true;
+                    for (int j = 0; j < 8; j++) {
+                        const u32 off = KB_ELEM(k0, k1, j) - kbase;
+                        const bool on = (m >> j) & 1u;
+                        if (on && off < krange) tab[off] = KB_ELEM(v0, v1, j);
+                        bad |= (on && off >= krange) ? 1u : 0u;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const u32 off = compact_key(KB_ELEM(k0, k1, j), P.cshift) - kbase;
+                        const bool on = (m >> j) & 1u;
+                        if (on && off < krange) tab[off] = KB_ELEM(v0, v1, j);
+                        bad |= (on && off >= krange) ? 1u : 0u;
                     }
                 }
+                const bool dup = bad != 0u;
                 if (dup) *P.pat[k].outp[1] = 1u;
                 continue;
             }
