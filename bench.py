@@ -43,7 +43,8 @@ def parse_args():
     ap.add_argument("--query", default="cfg2", choices=["cfg2", "star3", "cfg3", "cfg1"])
     ap.add_argument("--cpu-sample", type=int, default=300_000, help="employees in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--numa", action="store_true", help="bind the rank to its GPU's NUMA node (helps the e2e leg at 8 ranks: 28 vs 33 ms per "
+                    "step; off by default: the one 8-rank run with it on also showed a 3x slower host side of the resident step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-index", action="store_true", help="headline on the store-scanning path (no predicate-partitioned index)")
     return ap.parse_args()
@@ -51,39 +52,62 @@ def parse_args():
 
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons of one GPU during the timed region (B200_PROFILING.md recipe)"""
+    """SM clocks / throttle reasons of the job's GPUs during the timed region (B200_PROFILING.md recipe). Rank 0 samples every GPU of
+    the job through NVML in-process; one `nvidia-smi` subprocess per rank every 0.2 s (the first version) initialises NVML for all
+    eight GPUs each time and takes driver locks next to the ranks' launches — at 8 ranks that alone tripled the host side of a
+    0.1 ms step. Falls back to nvidia-smi when pynvml is missing."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
+        self.indices = list(indices)
+        self.samples = []  # (sm_mhz, max_mhz, [reasons])
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            if not self.indices:
+                raise RuntimeError("nothing to sample")
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        for h in self.handles:
+            sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            mask = int(get(h))
+            self.samples.append((float(sm), float(mx), [k for k, b in self.BITS.items() if mask & b]))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", ",".join(str(i) for i in self.indices)],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            self.samples.append((float(f[0]), float(f[1]), [k for k, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7])
+                                                                 if v.lower().startswith("active")]))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
-                for n, v in zip(names, s[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        reasons = sorted({r for s in self.samples for r in s[2]})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm),
+                "gpus_sampled": len(self.indices), "via": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peak():
@@ -227,7 +251,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: kolibrie_b200 has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    prev_affinity, numa_node = (None, None) if args.no_numa else bind_near_gpu(local)
+    prev_affinity, numa_node = bind_near_gpu(local) if args.numa else (None, None)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -256,8 +280,10 @@ def main():
         r.free()
         return rows
 
-    sampler = ClockSampler(local)  # samples through warm-up, the timed region and the e2e leg: all of it is load
-    sampler.start()
+    # rank 0 samples all GPUs of the job through warm-up, the timed region and the e2e leg (all of it is load)
+    sampler = ClockSampler(range(world) if rank == 0 else [])
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         rows_step = step_resident()
     ctx.get_stats(reset=True)
@@ -316,7 +342,8 @@ def main():
         while time.perf_counter() - t_s < 1.2:
             step_resident() if args.no_e2e else step_e2e()
     sampler.stop_flag.set()
-    sampler.join(timeout=2)
+    if rank == 0:
+        sampler.join(timeout=2)
 
     # ---- reduce over ranks: max time, sum of rows
     if world > 1:
