@@ -8,8 +8,10 @@
 // /root/reference/datalog/tests/reasoning_tests.rs:28-404, replayed in tests/test_oracle_golden.py) and for
 // scan/filter (kolibrie/tests/integration_test.rs:19-76,131-299 fixture counts; 4-employee dataset of
 // kolibrie/examples/sparql_syntax/simple_select/simple_select_synth_data.rs:16-52).
-// UNPINNED for multi-pattern BGP join rows: no reference test asserts them (SURVEY.md §4 "Gap that matters"); there the
-// authority is the relational semantics of the cited lines, cross-checked faithful-vs-columnar-vs-brute-force.
+// Multi-pattern BGP joins: pinned only by the two joins whose answers kolibrie/tests/integration_test.rs asserts (:286-299 a
+// 2-pattern join, :302-342 a 3-pattern join + numeric FILTER; tests/test_oracle_golden.py, both oracle modes). No reference test
+// asserts the rows of larger joins through the executor (SURVEY.md §4 "Gap that matters"): beyond those two, parity is UNPINNED and
+// the authority is the relational semantics of the cited lines, cross-checked faithful-vs-columnar-vs-brute-force.
 // The reference is a Rust workspace and cannot be built in this image (no cargo/rustc), so there is no oracle/_ref
 // for the CPU path; oracle/_ref holds only the reference's own CUDA stub (see oracle/Makefile).
 //

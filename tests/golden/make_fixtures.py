@@ -70,10 +70,14 @@ terms = ["http://example.org/person1", "http://example.org/person2", "http://exa
          "ex:founded", "ex:industry", "John Smith", "Jane Doe", "ACME Corp", "30", "25", "john@example.com", "jane@example.com", "2000", "Technology"]
 triples = [(0, 3, 9), (0, 4, 12), (0, 5, 14), (0, 6, 2), (1, 3, 10), (1, 4, 13), (1, 5, 15), (1, 6, 2), (2, 3, 11), (2, 7, 16), (2, 8, 17)]
 dump("integration_fixture.json", {
-    "source": "/root/reference/kolibrie/tests/integration_test.rs:19-76 (fixture), :131-299 (asserted counts)",
+    "source": "/root/reference/kolibrie/tests/integration_test.rs:19-76 (fixture), :131-299 (asserted counts), :286-299 and :302-342 (two joins whose answers the test asserts)",
     "terms": terms, "triples": triples,
     "expect": {"subject==person1": 4, "predicate==ex:name": 3, "object==Jane Doe": 1, "numeric_objects": 3, "count(ex:name)": 3,
-               "worksFor_company1_subjects": [0, 1], "person1_emails_after_add": 2}})
+               "worksFor_company1_subjects": [0, 1], "person1_emails_after_add": 2,
+               # :286-299  ?c ex:industry "Technology" . ?e ex:worksFor ?c      -> 2 employees, person1 among them
+               "tech_employees": [0, 1],
+               # :302-342  ?c ex:name "ACME Corp" . ?e ex:worksFor ?c . ?e ex:age ?a FILTER(?a < 30)  -> person2 only
+               "young_acme_employees": [1]}})
 
 dump("employee4.json", {
     "source": "/root/reference/kolibrie/examples/sparql_syntax/simple_select/simple_select_synth_data.rs:16-52",

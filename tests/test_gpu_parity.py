@@ -51,6 +51,24 @@ def test_integration_fixture_on_device(ctx):
     assert [x.n_rows for x in r[:3]] == [ex["subject==person1"], ex["predicate==ex:name"], ex["object==Jane Doe"]]
     assert sorted(r[3].column(0).tolist()) == ex["worksFor_company1_subjects"]
     assert sorted(r[0].to_numpy([P, Ob]).tolist()) == [[3, 9], [4, 12], [5, 14], [6, 2]]
+    # the two joins whose answers integration_test.rs asserts (:286-299 tech employees, :302-342 ACME employees under 30), on the
+    # device, with and without the store index. ids: terms list of the fixture (ex:name 3, ex:age 4, ex:worksFor 6, ex:industry 8, ...)
+    t = {name: i for i, name in enumerate(fx["terms"])}
+    num = np.zeros(len(t))
+    isn = np.zeros(len(t), np.uint8)
+    for name in ("30", "25", "2000"):
+        num[t[name]], isn[t[name]] = float(name), 1
+    ctx.dict_numeric_load(num, isn)
+    C_, E_, A_ = 0, 1, 2
+    tech = [c.pattern(c.V(C_), c.K(t["ex:industry"]), c.K(t["Technology"])), c.pattern(c.V(E_), c.K(t["ex:worksFor"]), c.V(C_))]
+    young = [c.pattern(c.V(C_), c.K(t["ex:name"]), c.K(t["ACME Corp"])), c.pattern(c.V(E_), c.K(t["ex:worksFor"]), c.V(C_)),
+             c.pattern(c.V(E_), c.K(t["ex:age"]), c.V(A_))]
+    lt30 = [c.fop(c.F_CMP_NUM, slot=A_, cmp=c.CMP_LT, value=30.0)]
+    for indexed in (False, True):
+        if indexed:
+            ctx.build_index()
+        assert sorted(ctx.bgp_execute(tech).to_numpy([E_])[:, 0].tolist()) == ex["tech_employees"]
+        assert sorted(ctx.bgp_execute(young, lt30).to_numpy([E_])[:, 0].tolist()) == ex["young_acme_employees"]
 
 
 @pytest.mark.parametrize("n", [0, 1, 31, 2047, 2048, 2049, 70001])

@@ -98,6 +98,15 @@ def test_integration_fixture_scan_counts():
     tr2 = np.concatenate([tr, np.array([[0, 5, extra]], dtype=np.uint32)])
     db2 = O.Db(tr2[:, 0], tr2[:, 1], tr2[:, 2])
     assert db2.scan(c.pattern(c.K(0), c.K(5), Ob)).n_rows == ex["person1_emails_after_add"]
+    # the two joins the reference's test asserts the answers of (:286-299, :302-342): they pin the oracle's multi-pattern join + FILTER
+    C_, E_, A_ = 0, 1, 2
+    tech = [c.pattern(c.V(C_), c.K(d.lookup("ex:industry")), c.K(d.lookup("Technology"))), c.pattern(c.V(E_), c.K(d.lookup("ex:worksFor")), c.V(C_))]
+    young = [c.pattern(c.V(C_), c.K(d.lookup("ex:name")), c.K(d.lookup("ACME Corp"))), c.pattern(c.V(E_), c.K(d.lookup("ex:worksFor")), c.V(C_)),
+             c.pattern(c.V(E_), c.K(d.lookup("ex:age")), c.V(A_))]
+    lt30 = [c.fop(c.F_CMP_NUM, slot=A_, cmp=c.CMP_LT, value=30.0)]
+    for mode in (0, 1):  # columnar and faithful oracle modes
+        assert sorted(db.bgp(tech, mode=mode).to_numpy([E_])[:, 0].tolist()) == ex["tech_employees"]
+        assert sorted(db.bgp(young, lt30, mode=mode).to_numpy([E_])[:, 0].tolist()) == ex["young_acme_employees"]
 
 
 def employee4():
