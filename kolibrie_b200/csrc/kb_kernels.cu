@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
     __shared__ __align__(8) u64 bars[2];
     __shared__ u32 s_nexts[2];
     __shared__ u32 s_wcnt[SCAN_THREADS / 32][MAXP];
-    __shared__ u32 s_cnt[MAXP], s_excl[MAXP];
+    __shared__ u32 s_excl[MAXP];
     constexpr int NW = (K + 2) / 3;  // packed count words: three 10-bit fields each (a warp holds at most 256 matches per pattern)
     __shared__ u32 s_tcnt[2], s_tindex[2];  // triples in the staged tile, global index of its first triple
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
