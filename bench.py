@@ -72,10 +72,23 @@ class ClockSampler(threading.Thread):
             import pynvml
 
             pynvml.nvmlInit()
-            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.handles = [self._handle(pynvml, i) for i in self.indices]
             self.nvml = pynvml
         except Exception:
             self.nvml = None
+
+    @staticmethod
+    def _handle(n, cuda_index):
+        """NVML handle of CUDA device `cuda_index`: by PCI bus id, so that a CUDA_VISIBLE_DEVICES remapping cannot make the sampler
+        watch somebody else's (idle) GPU; by index when torch does not expose the bus id"""
+        try:
+            import torch
+
+            pr = torch.cuda.get_device_properties(cuda_index)
+            bus = "%08X:%02X:%02X.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            return n.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return n.nvmlDeviceGetHandleByIndex(cuda_index)
 
     def _sample_nvml(self):
         n = self.nvml
