@@ -52,3 +52,21 @@ def test_struct_layouts_match_header():
     assert C.sizeof(capi.KbAgg) == 8 and C.sizeof(capi.KbRuleFilter) == 24 and C.sizeof(capi.KbRule) == 48
     assert C.sizeof(capi.KbFixpointStats) == 8 + 8 + 8 + 64 * 8 + 8
     assert capi.lib().kb_shard_of(12345, 8) < 8
+
+
+def test_every_entry_point_is_documented_for_the_integrator():
+    """INTEGRATION.md is the binding guide: every function the header declares must at least be named there"""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "kolibrie_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    fns = re.findall(r"KB_API\s+[\w\s\*]+?\b(kb_\w+)\s*\(", header)
+    assert len(fns) >= 45
+    names = set(re.findall(r"kb_\w+", doc))
+    # `kb_groups_info/keys/values/counts/free` style lists name a family by its prefix
+    for fam in re.findall(r"(kb_\w+?_)(\w+(?:/\w+)+)", doc):
+        for tail in fam[1].split("/"):
+            names.add(fam[0] + tail)
+    missing = [f for f in fns if f not in names]
+    assert not missing, missing
