@@ -1802,9 +1802,7 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
     ctx->index.clear();
     ctx->index_version = ~0ull;
     if (ctx->n_triples == 0) return KB_OK;
-    cudaEvent_t e0, e1;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
+    kb::ScopedEvent e0, e1;
     cudaEventRecord(e0, ctx->st);
     // 1. distinct predicates
     const u32 set_slots = 8192;
@@ -1821,7 +1819,7 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
     std::vector<u32> preds;
     for (u32 v : hset) if (v != kb::EMPTY32) preds.push_back(v);
     std::sort(preds.begin(), preds.end());
-    if (ctx->h_ctrl[off] || preds.size() > 4096) { cudaEventDestroy(e0); cudaEventDestroy(e1); return KB_OK; }  // too many predicates: keep scanning
+    if (ctx->h_ctrl[off] || preds.size() > 4096) return KB_OK;  // too many predicates: keep scanning
     // 2. one fused scan per 8 predicates, pair output, then shrink each slice to its size and take its id ranges
     for (size_t b = 0; b < preds.size(); b += kb::MAXP) {
         const u32 k = (u32)std::min<size_t>(kb::MAXP, preds.size() - b);
@@ -1911,8 +1909,6 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     ctx->index_version = ctx->store_version;
     if (n_predicates) *n_predicates = (uint32_t)preds.size();
     if (build_ms) *build_ms = ms;

@@ -173,9 +173,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     if (strategy != KB_SEMI_NAIVE && strategy != KB_NAIVE && strategy != KB_SEMI_NAIVE_PARALLEL) return fail(ctx, KB_E_INVALID, "unknown strategy %u", strategy);
     const bool strict = strategy == KB_SEMI_NAIVE_PARALLEL;
     kb_fixpoint_stats st{};
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
+    ScopedEvent ev0, ev1;
     cudaEventRecord(ev0, ctx->st);
 
     // ---- compile the rules (host): variable slots, synthetic variables for constants in s/o (quirk Q6), safety checks
@@ -447,8 +445,6 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     float ms = 0.f;
     cudaEventElapsedTime(&ms, ev0, ev1);
     st.device_ms = ms;
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
     if (stats) *stats = st;
     ctx->stats.rows_out = st.inferred;
     *inferred = res.release();

@@ -33,6 +33,16 @@ struct Col {
     u32* ptr = nullptr;  // 16-byte aligned, readable up to the next multiple of 256 B past the last row
 };
 
+// a timing event that is destroyed on every return path
+struct ScopedEvent {
+    cudaEvent_t e = nullptr;
+    ScopedEvent() { cudaEventCreate(&e); }
+    ~ScopedEvent() { if (e) cudaEventDestroy(e); }
+    ScopedEvent(const ScopedEvent&) = delete;
+    ScopedEvent& operator=(const ScopedEvent&) = delete;
+    operator cudaEvent_t() const { return e; }
+};
+
 enum Family { F_SCAN = 0, F_BUILD, F_PROBE, F_FILTER, F_GROUP, F_OTHER, F_COUNT };
 
 struct PendingTimer {
