@@ -271,13 +271,23 @@ KB_API kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* r, uint32_t key_s
 KB_API kb_status kb_rel_from_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out);
 KB_API kb_status kb_store_download(kb_ctx* ctx, uint32_t* s, uint32_t* p, uint32_t* o, uint64_t cap, uint64_t* n);
 
-/* ------------------------------------------------------------------ one-shot host-buffer entry (end-to-end measurement and the
- * reference's per-call GPU usage, sparql_database.rs:3193-3353): upload (chunked, overlapped with the scan),
- * star-join, download. Result columns are malloc'd by the callee and owned by the caller (free()). */
+/* ------------------------------------------------------------------ one-shot host-buffer entries (end-to-end measurement and the
+ * reference's per-call GPU usage, sparql_database.rs:3193-3353): upload (chunked, overlapped with the scan), star-join, download.
+ * The store of ctx is REPLACED by the uploaded triples (and is left empty when the call fails). Patterns and filter are validated
+ * before the upload starts; on every return path the caller's input buffers are no longer read.
+ * kb_star_join_host: result columns cols[0 .. *n_cols) are malloc'd by the callee and owned by the caller (free()); whatever cols[]
+ * held on entry is ignored and entries past *n_cols are set to NULL. */
 KB_API kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n,
                                    uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats,
                                    const kb_filter_op* filter, uint32_t n_filter_ops,
                                    uint32_t* n_cols, uint32_t* slots /* [KB_MAX_COLS] */, uint32_t** cols /* [KB_MAX_COLS] */, uint64_t* n_rows);
+/* same, into CALLER-provided buffers (e.g. pinned memory): cols[c] must hold capacity_rows rows for every result column (one per
+ * distinct variable of the patterns, at most KB_MAX_COLS); a result larger than capacity_rows -> KB_E_LIMIT with *n_rows = its size. */
+KB_API kb_status kb_star_join_host_into(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n,
+                                        uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats,
+                                        const kb_filter_op* filter, uint32_t n_filter_ops,
+                                        uint32_t* n_cols, uint32_t* slots /* [KB_MAX_COLS] */, uint32_t* const* cols /* [KB_MAX_COLS] */,
+                                        uint64_t capacity_rows, uint64_t* n_rows);
 
 #ifdef __cplusplus
 }

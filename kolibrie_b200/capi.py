@@ -188,6 +188,7 @@ def lib() -> C.CDLL:
         "kb_partition_counts": (i32, [vp, vp, u32, u32, P(u64)]),
         "kb_shuffle_scatter": (i32, [vp, vp, u32, u32, P(vp), P(u64), u64]),
         "kb_star_join_host": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), P(u64)]),
+        "kb_star_join_host_into": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), u64, P(u64)]),
         "perform_hash_join_cuda": (None, [vp, vp, vp, u32, u32, P(u32), P(P(u32)), P(u32)]),
     }
     for name, (res, args) in sig.items():
@@ -204,7 +205,7 @@ EXPORTED_SYMBOLS = [
     "kb_store_download", "kb_dict_numeric_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_star_join_aggregate",
-    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_star_join_host", "perform_hash_join_cuda",
+    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
 ]
 
 
@@ -551,15 +552,15 @@ class Context:
 
 
 def star_join_host_raw(ctx: Context, s_ptr: int, p_ptr: int, o_ptr: int, n: int, join_slot: int, pats, filt, out_ptrs: Sequence[int], out_cap: int):
-    """kb_star_join_host with raw host pointers (pinned torch / numpy memory). Returns (n_rows, slots)."""
+    """kb_star_join_host_into with raw host pointers (pinned torch / numpy memory) for inputs and outputs. Returns (n_rows, slots)."""
     a, nf = filter_prog(filt)
-    n_cols, n_rows = C.c_uint32(), C.c_uint64(out_cap)
+    n_cols, n_rows = C.c_uint32(), C.c_uint64(0)
     slots = (C.c_uint32 * KB_MAX_COLS)()
     cols = (C.c_void_p * KB_MAX_COLS)()
     for i, ptr in enumerate(out_ptrs):
         cols[i] = ptr
-    ctx._check(lib().kb_star_join_host(ctx.h, C.c_void_p(s_ptr), C.c_void_p(p_ptr), C.c_void_p(o_ptr), n, join_slot, patterns(pats), len(pats),
-                                       a, nf, C.byref(n_cols), slots, cols, C.byref(n_rows)))
+    ctx._check(lib().kb_star_join_host_into(ctx.h, C.c_void_p(s_ptr), C.c_void_p(p_ptr), C.c_void_p(o_ptr), n, join_slot, patterns(pats), len(pats),
+                                            a, nf, C.byref(n_cols), slots, cols, out_cap, C.byref(n_rows)))
     return n_rows.value, [slots[i] for i in range(n_cols.value)]
 
 

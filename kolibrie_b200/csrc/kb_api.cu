@@ -264,7 +264,7 @@ void pattern_vars(const kb_pattern& pt, std::vector<u32>* slots, std::vector<u32
     }
 }
 
-static kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt) {
+kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt) {
     const kb_term* ts[3] = {&pt.s, &pt.p, &pt.o};
     for (auto* t : ts) {
         if (t->is_var > 1) return fail(ctx, KB_E_INVALID, "kb_term.is_var must be 0 or 1");
@@ -385,9 +385,11 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
     for (size_t i = 0; i < ops.size(); i++) P.ops[i] = ops[i];
 
     const u32 n_seg = (u32)ctx->segs.size();
+    // the guard depends on the segment count alone: where the arena cursor stands is irrelevant, ctrl_alloc wraps (an index build
+    // over hundreds of predicates hands out ~76 words per 8-predicate batch and every consumer clears its own words)
+    if (std::max(n_seg, 1u) + 2u * MAXP > kb_ctx::CTRL_WORDS - 64u) return fail(ctx, KB_E_LIMIT, "too many store segments (%u)", n_seg);
     const u32 off_tot = ctrl_alloc(ctx, 2 * MAXP);
     const u32 off_ticket = ctrl_alloc(ctx, std::max(n_seg, 1u));
-    if (ctx->ctrl_used > kb_ctx::CTRL_WORDS - 64) return fail(ctx, KB_E_LIMIT, "too many store segments (%u)", n_seg);
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_tot, 0, 2 * MAXP * sizeof(u32), ctx->st));
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_ticket, 0, std::max(n_seg, 1u) * sizeof(u32), ctx->st));
     u64 all_tiles = 0;
@@ -682,9 +684,10 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
     P.tile_state = static_cast<u64*>(ctx->tile_state->p);
     P.block_state = static_cast<u64*>(ctx->block_state->p);
     P.ordered = ctx->ordered;
-    const u32 off = ctrl_alloc(ctx, 4);
+    const u32 off = ctrl_alloc(ctx, 8);  // [0] ticket, [1] total (32-bit positions), [2] zero, [4..5] exact total in 64 bits
     P.total = ctx->ctrl + off + 1;
     P.zero_word = ctx->ctrl + off + 2;
+    P.total64 = reinterpret_cast<unsigned long long*>(ctx->ctrl + off + 4);
     u64 cap = std::max(Pr.n, B.n);
     ctx->stats.rows_probed += Pr.n;
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -697,7 +700,7 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
             P.out[c] = col.ptr;
         }
         P.cap = (u32)std::min<u64>(cap, 0xFFFFFFF0ull);
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 8 * sizeof(u32), ctx->st));
         P.ticket = ctx->ctrl + off;
         P.epoch = ctx->epoch++;
         timer_begin(ctx, F_PROBE);
@@ -705,7 +708,9 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
         timer_end(ctx);
         KB_CUDA(ctx, cudaGetLastError());
         KB_TRY(ctrl_read(ctx));
-        const u64 total = ctx->h_ctrl[off + 1];
+        unsigned long long total = 0;
+        memcpy(&total, ctx->h_ctrl + off + 4, sizeof total);
+        if (total >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "join result of %llu rows exceeds 2^32", total);
         rel->n = total;
         if (total <= cap) break;
         if (attempt == 1) return fail(ctx, KB_E_LIMIT, "join output did not fit after resizing");
@@ -1950,7 +1955,8 @@ kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, con
     for (auto& sg : old) {
         kb::Segment marked = sg;
         if (sg.n) {
-            KB_TRY(kb::alloc_col(ctx, sg.n, &marked.p));
+            rc = kb::alloc_col(ctx, sg.n, &marked.p);
+            if (rc != KB_OK) break;  // the restore path below puts the untouched segments back
             kb::launch_delete_mark(sg.s.ptr, sg.p.ptr, sg.o.ptr, (u32)sg.n, static_cast<const uint4*>(set->p), set_slots, marked.p.ptr,
                                    ctx->n_sms, ctx->st);
         }
@@ -2506,18 +2512,30 @@ kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_
 }
 
 // ------------------------------------------------------------------ one-shot host-buffer star join
-kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint32_t join_slot,
-                            const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops, uint32_t* n_cols,
-                            uint32_t* slots, uint32_t** cols, uint64_t* n_rows) {
-    KB_ENTER(ctx);
+static kb_status star_join_host_common(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint32_t join_slot,
+                                       const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops, uint32_t* n_cols,
+                                       uint32_t* slots, uint32_t** cols, uint64_t* n_rows, bool caller_bufs, uint64_t caller_cap) {
     if (!pats || !n_cols || !slots || !cols || !n_rows) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
     if (n && (!s || !p || !o)) return kb::fail(ctx, KB_E_INVALID, "NULL column pointer");
     if (n >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "too many triples");
-    const bool caller_bufs = cols[0] != nullptr;
-    const u64 caller_cap = caller_bufs ? *n_rows : 0;
+    // everything that can be rejected without looking at the data is rejected BEFORE the upload starts: an early return must not
+    // leave copies in flight that still read the caller's (borrowed) buffers
+    if (n_pats == 0 || n_pats > (u32)kb::MAXP) return kb::fail(ctx, KB_E_LIMIT, "a star join takes 1..%d patterns (got %u)", kb::MAXP, n_pats);
+    KB_TRY(kb::validate_filter(ctx, filter, n_ops));
+    for (u32 k = 0; k < n_pats; k++) {
+        KB_TRY(kb::check_pattern(ctx, pats[k]));
+        std::vector<u32> vs, src;
+        kb::pattern_vars(pats[k], &vs, &src);
+        if (std::find(vs.begin(), vs.end(), join_slot) == vs.end())
+            return kb::fail(ctx, KB_E_INVALID, "star join: pattern %u does not contain the join variable (slot %u)", k, join_slot);
+    }
     // upload in chunks on the copy stream; each chunk is a store segment the scan starts on as soon as its copy has landed
     ctx->segs.clear();
     ctx->n_triples = 0;
+    ctx->store_version++;
+    ctx->multi_valued.clear();
+    ctx->single_valued.clear();
+    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
     kb::Col cs, cp, co;
     KB_TRY(kb::alloc_col(ctx, n, &cs));
     KB_TRY(kb::alloc_col(ctx, n, &cp));
@@ -2528,20 +2546,39 @@ kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, c
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));  // allocations are stream-ordered on st; the copy stream must see them
     const u64 chunk = (u64)kb::SCAN_TILE * 4096;   // 8 Mi triples = 32 MiB per column
     std::vector<cudaEvent_t> evs;
+    // whatever happens from here on, the caller's buffers are not read after this function returns and a failed call leaves an
+    // EMPTY store (never segments whose copies did not complete)
+    auto finish = [&](kb_status rc) -> kb_status {
+        cudaStreamSynchronize(ctx->st_copy);
+        for (auto& sg : ctx->segs) sg.ready = nullptr;
+        ctx->upload_stats_off = -1;
+        for (auto ev : evs) cudaEventDestroy(ev);
+        if (rc != KB_OK) {
+            cudaStreamSynchronize(ctx->st);
+            ctx->segs.clear();
+            ctx->n_triples = 0;
+        }
+        return rc;
+    };
+#define KB_HOST_CUDA(call)                                                                                                    \
+    do {                                                                                                                      \
+        cudaError_t _e = (call);                                                                                              \
+        if (_e != cudaSuccess) return finish(kb::fail(ctx, KB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__)); \
+    } while (0)
     for (u64 b = 0; b < n; b += chunk) {
         const u64 m = std::min(chunk, n - b);
-        KB_CUDA(ctx, cudaMemcpyAsync(cs.ptr + b, s + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
-        KB_CUDA(ctx, cudaMemcpyAsync(cp.ptr + b, p + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
-        KB_CUDA(ctx, cudaMemcpyAsync(co.ptr + b, o + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
+        KB_HOST_CUDA(cudaMemcpyAsync(cs.ptr + b, s + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
+        KB_HOST_CUDA(cudaMemcpyAsync(cp.ptr + b, p + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
+        KB_HOST_CUDA(cudaMemcpyAsync(co.ptr + b, o + b, m * sizeof(u32), cudaMemcpyHostToDevice, ctx->st_copy));
         {  // column ranges of this chunk, on the copy stream right behind its copies (the direct tables need the key range)
             const u32* cc[3] = {cs.ptr + b, cp.ptr + b, co.ptr + b};
             for (int c = 0; c < 3; c++) kb::launch_col_minmax(cc[c], (u32)m, ctx->ctrl + soff + c, ctx->ctrl + soff + 4 + c, ctx->n_sms, ctx->st_copy);
             ctx->stats.kernel_launches += 3;
         }
         cudaEvent_t ev;
-        KB_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        KB_CUDA(ctx, cudaEventRecord(ev, ctx->st_copy));
+        KB_HOST_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         evs.push_back(ev);
+        KB_HOST_CUDA(cudaEventRecord(ev, ctx->st_copy));
         kb::Segment sg;
         sg.tag = 0; sg.n = m;
         sg.ready = ev;
@@ -2552,33 +2589,47 @@ kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, c
         ctx->n_triples += m;
     }
     ctx->stats.h2d_bytes += 3 * n * sizeof(u32);
-    ctx->store_version++;
-    ctx->multi_valued.clear();
-    ctx->single_valued.clear();
-    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
     ctx->upload_stats_off = (int)soff;
     // scan_impl makes st wait on each segment's `ready` event right before that segment's scan kernel: copy i+1 overlaps scan i
     std::unique_ptr<kb_rel> r;
     kb_status rc = kb::star_join_impl(ctx, join_slot, pats, n_pats, filter, n_ops, &r);
-    for (auto& sg : ctx->segs) sg.ready = nullptr;
-    ctx->upload_stats_off = -1;
-    for (auto ev : evs) cudaEventDestroy(ev);
-    if (rc != KB_OK) return rc;
+    if (rc != KB_OK) return finish(rc);
     *n_cols = (u32)r->slots.size();
     *n_rows = r->n;
     for (size_t c = 0; c < r->slots.size(); c++) slots[c] = r->slots[c];
-    if (caller_bufs && caller_cap < r->n) return kb::fail(ctx, KB_E_LIMIT, "caller buffers hold %llu rows, result has %llu", (unsigned long long)caller_cap, (unsigned long long)r->n);
+    if (caller_bufs && caller_cap < r->n)
+        return finish(kb::fail(ctx, KB_E_LIMIT, "caller buffers hold %llu rows, result has %llu", (unsigned long long)caller_cap, (unsigned long long)r->n));
+    if (!caller_bufs) for (size_t c = 0; c < KB_MAX_COLS; c++) cols[c] = nullptr;
     for (size_t c = 0; c < r->slots.size(); c++) {
         if (!caller_bufs) {
             cols[c] = (uint32_t*)malloc(std::max<size_t>(r->n * sizeof(u32), 4));
-            if (!cols[c]) return kb::fail(ctx, KB_E_OOM, "malloc failed");
-        } else if (!cols[c]) return kb::fail(ctx, KB_E_INVALID, "caller-provided column buffer %zu is NULL", c);
-        if (r->n) KB_CUDA(ctx, cudaMemcpyAsync(cols[c], r->cols[c].ptr, r->n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+            if (!cols[c]) {
+                for (size_t d = 0; d < c; d++) { free(cols[d]); cols[d] = nullptr; }
+                return finish(kb::fail(ctx, KB_E_OOM, "malloc failed"));
+            }
+        } else if (!cols[c]) return finish(kb::fail(ctx, KB_E_INVALID, "caller-provided column buffer %zu is NULL", c));
+        if (r->n) KB_HOST_CUDA(cudaMemcpyAsync(cols[c], r->cols[c].ptr, r->n * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
     }
-    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    KB_HOST_CUDA(cudaStreamSynchronize(ctx->st));
+#undef KB_HOST_CUDA
     ctx->stats.d2h_bytes += r->slots.size() * r->n * sizeof(u32);
     ctx->stats.rows_out = r->n;
-    return KB_OK;
+    return finish(KB_OK);
+}
+
+kb_status kb_star_join_host(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint32_t join_slot,
+                            const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops, uint32_t* n_cols,
+                            uint32_t* slots, uint32_t** cols, uint64_t* n_rows) {
+    KB_ENTER(ctx);
+    return star_join_host_common(ctx, s, p, o, n, join_slot, pats, n_pats, filter, n_ops, n_cols, slots, cols, n_rows, false, 0);
+}
+
+kb_status kb_star_join_host_into(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint32_t join_slot,
+                                 const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops, uint32_t* n_cols,
+                                 uint32_t* slots, uint32_t* const* cols, uint64_t capacity_rows, uint64_t* n_rows) {
+    KB_ENTER(ctx);
+    return star_join_host_common(ctx, s, p, o, n, join_slot, pats, n_pats, filter, n_ops, n_cols, slots, const_cast<uint32_t**>(cols), n_rows, true,
+                                 capacity_rows);
 }
 
 }  // extern "C"

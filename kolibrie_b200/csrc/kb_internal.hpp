@@ -233,5 +233,6 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
 kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 n_pats, const kb_filter_op* filter, u32 n_ops,
                          std::unique_ptr<kb_rel>* out);
 void pattern_vars(const kb_pattern& pt, std::vector<u32>* slots, std::vector<u32>* src);
+kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt);
 
 }  // namespace kb

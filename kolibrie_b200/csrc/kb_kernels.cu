@@ -1128,7 +1128,9 @@ __global__ void __launch_bounds__(PROBE_THREADS) probe_direct_kernel(const __gri
             __syncwarp();
             const u32 total = __shfl_sync(0xffffffffu, s_cnt[0], 0);
             const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
-            if (lane == 0) s_excl[0] = ex;
+            if (lane == 0) {
+                s_excl[0] = ex;
+            }
         }
         __syncthreads();
         if (__ballot_sync(0xffffffffu, mbits != 0u) != 0u) {
@@ -1286,7 +1288,10 @@ __global__ void __launch_bounds__(PROBEC_THREADS) probe_chained_kernel(const __g
             __syncwarp();
             const u32 total = __shfl_sync(0xffffffffu, s_cnt[0], 0);
             const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
-            if (lane == 0) s_excl[0] = ex;
+            if (lane == 0) {
+                s_excl[0] = ex;
+                if (total) atomicAdd(P.total64, (unsigned long long)total);
+            }
         }
         __syncthreads();
         u32 pos = s_excl[0] + s_wcnt[warp];

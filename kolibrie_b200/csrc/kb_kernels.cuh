@@ -240,6 +240,7 @@ struct ProbeCParams {
     u64 epoch;
     u32* total;
     const u32* zero_word;
+    unsigned long long* total64;  // exact output size in 64 bits (the 32-bit positions wrap past 2^32 rows: the host checks this one)
 };
 void launch_probe_chained(const ProbeCParams& p, int n_sms, cudaStream_t st);
 

@@ -25,15 +25,15 @@ import numpy as np
 from . import capi as c
 
 # ---------------------------------------------------------------------------------------------------------------------
-_RUST_F64 = re.compile(r"^[+-]?(?:(?:inf|infinity|nan)|(?:(?:\d+\.?\d*|\.\d+)(?:[eE][+-]?\d+)?))$", re.IGNORECASE)
-_RUST_F64_SPECIAL = re.compile(r"^[+-]?(?:inf|infinity|nan)$", re.IGNORECASE)
+_RUST_F64 = re.compile(r"[+-]?(?:(?:inf|infinity|nan)|(?:(?:[0-9]+\.?[0-9]*|\.[0-9]+)(?:[eE][+-]?[0-9]+)?))", re.IGNORECASE)
+_RUST_F64_SPECIAL = re.compile(r"[+-]?(?:inf|infinity|nan)", re.IGNORECASE)
 
 
 def rust_parse_f64(s: str) -> Optional[float]:
     """`str::parse::<f64>()` acceptance of Rust (no whitespace, no '_', no hex; inf/infinity/nan in any case; '5.', '.5', '1e5')."""
-    if not isinstance(s, str) or not s.isascii() or not _RUST_F64.match(s):
+    if not isinstance(s, str) or not s.isascii() or not _RUST_F64.fullmatch(s):
         return None
-    if _RUST_F64_SPECIAL.match(s):
+    if _RUST_F64_SPECIAL.fullmatch(s):
         return float(s)  # Python accepts the same special spellings
     return float(s)
 

@@ -90,4 +90,4 @@ dump("rust_parse_f64.json", {
     "accept": {"1": 1.0, "+1.0": 1.0, "-2.5": -2.5, ".5": 0.5, "5.": 5.0, "1e5": 100000.0, "1E-2": 0.01, "1.5e+3": 1500.0, "inf": "inf", "-inf": "-inf",
                "Infinity": "inf", "INFINITY": "inf", "nan": "nan", "NaN": "nan", "+nan": "nan", "100000": 100000.0, "0": 0.0, "007": 7.0},
     "reject": ["", " 1", "1 ", "1_000", "0x10", "1e", "e5", ".", "+", "-", "1.2.3", "--1", "infinit", "nane", "1f", "Developer",
-               "http://example.org/employee1", "١"]})
+               "http://example.org/employee1", "١", "5\n", " 5", "5 ", "5\t", "\n5", "1e5\n"]})
