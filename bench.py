@@ -1,17 +1,26 @@
 #!/usr/bin/env python
 """bench.py — joined bindings/s of the 3-pattern BGP hot path (BASELINE.json metric) on B200.
 
-A "step" = one pass of the hot path over the resident store: ONE fused TMA scan of all three patterns (FILTER pushed into
-the salary pattern) -> two direct hash builds -> one fused multiway probe that emits the joined bindings.
-Workload (config.workload): the BASELINE configs[1] query (`?e foaf:title ?t . ?e ds:annual_salary ?s . ?e foaf:name ?n
-FILTER(?s > 100000)`) on the employee shape scaled to the size the metric is quoted on: 16 666 667 employees = 100 000 002
-dictionary-encoded triples PER GPU (weak scaling: with N GPUs the global dataset has N x that, sharded by kb_shard_of(subject, N);
-a subject-star join needs no exchange).
+A "step" = one pass of the hot path over the resident store = one evaluation of the BASELINE configs[1] query
+(`?e foaf:title ?t . ?e ds:annual_salary ?s . ?e foaf:name ?n FILTER(?s > 100000)`) on the employee shape scaled to the size the
+metric is quoted on: 16 666 667 employees = 100 000 002 dictionary-encoded triples PER GPU (weak scaling: with N GPUs the global
+dataset has N x that, sharded by kb_shard_of(subject, N); a subject-star join needs no exchange).
 
-  value      bindings/s with the store already resident in HBM (device path only), whole job over all ranks
+  value      protocol "index-resident": the store and its predicate index (kb_store_build_index = build_all_indexes, built once,
+             untimed, as the reference's harnesses do) are resident in HBM; a step is ONE launch of probe_index_kernel through a
+             prepared plan (kb_star_join_prepare / kb_plan_submit / kb_plan_collect): K steps run back to back on the device, the host
+             stays a ring of launches ahead, every step's row count is read back. Bindings/s of the whole job over all ranks.
+  sync_path  the same K steps through the synchronous operator kb_star_join (one host round trip per step): what round 1 quoted
+  scan_path  protocol "SURVEY.md §8(d) scan+build+probe": the same K steps with the index switched off — every step scans the
+             12-byte/triple store, builds the direct tables and probes
   e2e        same metric through the one-shot C-ABI call with HOST (pinned) buffers: upload of the triple columns, the join,
              and the download of the binding columns are all inside the timed region
   roofline   algorithmic bytes (SURVEY.md §8d formulas) / CUDA-event time of the dominant kernel family, vs the measured HBM peak
+  multi_gpu  (N > 1) the legs that exercise the real multi-GPU path, each parity-asserted against closed-form digests of the generator:
+             cfg3 = 4-pattern star + GROUP BY ?t COUNT with the cross-rank merge of the partial groups (all-gather + kb_groups_merge);
+             shuffle_join = a path join on a NON-subject key through the fused peer-memory shuffle (kb_shuffle_push over NVLink);
+             strong = the 100 M-triple store of BASELINE configs[2] split over the N GPUs (strong scaling)
+  cfg2_10M   (N = 1) the same query on BASELINE configs[1]'s own 10 M-triple store: the size the CPU arm runs
   cpu_baseline / --impl reference: the oracle's restatement of the reference's own algorithm, timed on the host cores
 """
 import argparse
@@ -41,7 +50,10 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--employees", type=int, default=DEFAULT_EMPLOYEES, help="employees per GPU (6 triples each)")
     ap.add_argument("--query", default="cfg2", choices=["cfg2", "star3", "cfg3", "cfg1"])
-    ap.add_argument("--cpu-sample", type=int, default=300_000, help="employees in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=300_000, help="employees in the bounded CPU sample of the GPU arm's own cpu_baseline leg")
+    ap.add_argument("--cpu-employees", type=int, default=0, help="--impl reference: employees in the store (default: BASELINE configs[1]'s 10 M triples)")
+    ap.add_argument("--ring", type=int, default=4, help="result buffers of the prepared plan = queries in flight + 1")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the cfg3-merge / shuffle-join / strong-scaling legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--numa", action="store_true", help="bind the rank to its GPU's NUMA node (helps the e2e leg at 8 ranks: 28 vs 33 ms per "
                     "step; off by default: the one 8-rank run with it on also showed a 3x slower host side of the resident step)")
@@ -140,31 +152,36 @@ def traffic_from_profiles(family):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(args, steps, warmup):
+CFG2_10M_EMPLOYEES = 1_666_667  # BASELINE configs[1]: "scaled to 10M triples"
+
+
+def cpu_reference_run(args, steps, warmup, employees, budget_s=120.0):
     """The reference's own algorithm for this query, restated (oracle 'faithful' mode): StarJoin plan (optimizer.rs:84-152) =
     index scan of the first pattern, then per binding one bound index lookup per remaining pattern in the reference's SEQUENTIAL
     mode (engine.rs:621-655: results > 10 000), rows of maps, then the FILTER. Indexes are built before timing, as the reference's
     harnesses do (n_triple_10M.rs:79-95). Result caps (quirk Q1) off. Also times the oracle's columnar OpenMP mode as the strong
-    CPU competitor."""
+    CPU competitor. `employees` = store size of the run; the timed loop stops after `budget_s` seconds."""
     from kolibrie_b200 import datagen
     from tests import oracle_api as O
 
-    E = min(args.cpu_sample, args.employees)
+    E = int(employees)
     d = datagen.employee_dataset(E)
     js, pats, filt = datagen.employee_queries(d)[args.query]
     db = O.Db(d.s, d.p, d.o, d.num_or0, d.is_num)
+    t_i = time.perf_counter()
     db.build_index()
+    t_i = time.perf_counter() - t_i
     O.set_threads(O.usable_cpus())  # the CPU arm gets every host thread this process may use (affinity mask and cgroup quota)
     cores = O.num_threads()
     rows = 0
-    for _ in range(max(1, min(warmup, 2))):
+    for _ in range(max(1, min(warmup, 1))):
         rows = db.bgp(pats, filt, mode=1).n_rows
     t0 = time.perf_counter()
     n_done = 0
     for _ in range(steps):
         rows = db.bgp(pats, filt, mode=1).n_rows
         n_done += 1
-        if time.perf_counter() - t0 > 120:  # bounded: never more than ~2 minutes of CPU work
+        if time.perf_counter() - t0 > budget_s:  # bounded: never more than ~2 minutes of CPU work
             break
     dt = (time.perf_counter() - t0) / n_done
     t1 = time.perf_counter()
@@ -176,22 +193,27 @@ def cpu_reference_run(args, steps, warmup):
     assert rows_c == rows
     return {
         "value": rows / dt, "unit": UNIT, "cores": cores, "kind": "port",
-        "sample": f"{E} employees = {6 * E} triples, query {args.query}, {n_done} steps; oracle faithful mode (reference StarJoin, sequential mode as engine.rs:621 "
-                  f"dictates above 10 000 rows => 1 worker thread; FILTER stage on {cores} threads); indexes prebuilt",
-        "ms_per_step": dt * 1e3, "rows_per_step": int(rows),
-        "columnar_openmp": {"value": rows / dt_c, "unit": UNIT, "cores": cores, "note": "oracle columnar mode (OpenMP scan + hash joins on u32 columns), same sample"},
+        "sample": f"{E} employees = {6 * E} triples, query {args.query}, {n_done} timed steps; oracle faithful mode (reference StarJoin, sequential mode as engine.rs:621 "
+                  f"dictates above 10 000 rows => 1 worker thread; FILTER stage on {cores} threads); indexes prebuilt ({t_i:.1f} s, untimed)",
+        "ms_per_step": dt * 1e3, "rows_per_step": int(rows), "triples": 6 * E,
+        "columnar_openmp": {"value": rows / dt_c, "unit": UNIT, "cores": cores, "ms_per_step": dt_c * 1e3,
+                            "note": "oracle columnar mode (OpenMP scan + hash joins on u32 columns, no index), same store"},
     }, n_done
 
 
 def run_reference(args):
+    """--impl reference: the CPU arm. Store = BASELINE configs[1]'s own size (10 M triples) — the largest the faithful restatement
+    (four nested hash-map indexes, rows of maps: ~0.4 KB of host memory per triple, ~3 s of index build per million triples) runs
+    inside the bound; its throughput per row does not depend on the store size (hash lookups per binding)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, n_done = cpu_reference_run(args, args.steps, args.warmup)
+    E = min(args.cpu_employees or CFG2_10M_EMPLOYEES, args.employees)
+    base, n_done = cpu_reference_run(args, args.steps, args.warmup, E)
     line = {
-        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n_done, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n_done, "warmup": 1,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "sample": base["sample"]},
+        "config": {"workload": workload_name(args)},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "columnar_openmp": base["columnar_openmp"],
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -245,6 +267,20 @@ def workload_name(args):
     return f"employee shape, {args.employees} employees = {6 * args.employees} triples per GPU, {q}"
 
 
+def run_pipelined(plan, steps):
+    """K prepared queries back to back: submit, and collect the query submitted ring-1 steps earlier. Returns the last row count."""
+    depth = max(1, plan.ring - 1)
+    inflight = []
+    rows = 0
+    for _ in range(steps):
+        inflight.append(plan.submit())
+        if len(inflight) > depth:
+            rows = plan.collect(inflight.pop(0))
+    while inflight:
+        rows = plan.collect(inflight.pop(0))
+    return rows
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
@@ -256,6 +292,7 @@ def main():
 
     from kolibrie_b200 import capi as c
     from kolibrie_b200 import datagen
+    from kolibrie_b200 import dist as kd
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,6 +310,22 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    def reduce_max(*xs):
+        if world == 1:
+            return [float(x) for x in xs]
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
+
+    def reduce_sum(*xs):
+        if world == 1:
+            return [int(x) for x in xs]
+        t = torch.tensor([int(x) for x in xs], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [int(v) for v in t]
+
+    K = args.steps
+    W = max(args.warmup, 3)
     # ---- setup (untimed): this rank's shard of the global dataset, pinned on the host and resident on the device
     t_gen = time.perf_counter()
     d = datagen.employee_shard(args.employees * world, rank, world)
@@ -283,11 +336,15 @@ def main():
     ctx.set_sharding(rank, world)
     ctx.dict_numeric_load(d.num_or0, d.is_num)
     ctx.store_load(d.s, d.p, d.o)
-    # SparqlDatabase::build_all_indexes, once, outside the timed region (the reference's harnesses do the same, n_triple_10M.rs:91-95)
+    # SparqlDatabase::build_all_indexes, once, outside the timed region (the reference's harnesses do the same, n_triple_10M.rs:91-95).
+    # Built twice: the first build also grows the stream-ordered memory pool from empty (cudaMalloc of ~3 GB of slices, tables and
+    # scan scratch: hundreds of ms); the second is the steady-state cost of the operation, the one reported.
+    n_pred, index_ms_first = (0, 0.0) if args.no_index else ctx.build_index()
     n_pred, index_ms = (0, 0.0) if args.no_index else ctx.build_index()
     js, pats, filt = datagen.employee_queries(d)[args.query]
+    plan = None if args.no_index else ctx.prepare_star_join(js, pats, filt, ring=args.ring)
 
-    def step_resident():
+    def step_sync():
         r = ctx.star_join(js, pats, filt)
         rows = r.n_rows
         r.free()
@@ -297,39 +354,50 @@ def main():
     sampler = ClockSampler(range(world) if rank == 0 else [])
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        rows_step = step_resident()
-    ctx.get_stats(reset=True)
+
+    # ---- headline: K prepared queries back to back (protocol "index-resident"); without an index: the synchronous scanning step
+    def timed(fn, k):
+        """fn(k) runs k steps and returns the last row count; wall clock between barrier + synchronize on both sides"""
+        ctx.get_stats(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        rows = fn(k)
+        ctx.synchronize()
+        barrier()
+        return rows, time.perf_counter() - t0, ctx.get_stats(reset=True)
+
+    sync_loop = lambda k: [step_sync() for _ in range(k)][-1]
+    head_fn = (lambda k: run_pipelined(plan, k)) if plan else sync_loop
+    head_fn(W)
     ctx.set_timing(True)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        rows_step = step_resident()
-    ctx.synchronize()
-    barrier()
-    dt = time.perf_counter() - t0
-    st = ctx.get_stats(reset=True)
+    rows_step, dt, st = timed(head_fn, K)
+    # the same K steps through the synchronous operator (one host round trip per step)
+    sync_leg = None
+    if plan:
+        sync_loop(3)
+        rows_sync, dt_sync, st_sync = timed(sync_loop, K)
+        assert rows_sync == rows_step
+        sync_leg = (dt_sync, st_sync)
     # the same K steps on the store-SCANNING path (index switched off): the K_scan / K_build / K_probe numbers of SURVEY.md §8(d)
     scan_leg = None
     if not args.no_index:
         ctx.set_use_index(False)
-        for _ in range(3):
-            step_resident()
-        ctx.get_stats(reset=True)
-        barrier()
-        t0s = time.perf_counter()
-        for _ in range(args.steps):
-            rows_scan = step_resident()
-        ctx.synchronize()
-        barrier()
-        dts = time.perf_counter() - t0s
-        st_scan = ctx.get_stats(reset=True)
+        sync_loop(3)
+        rows_scan, dts, st_scan = timed(sync_loop, K)
         assert rows_scan == rows_step
         scan_leg = (dts, st_scan)
         ctx.set_use_index(True)
     ctx.set_timing(False)
 
-    # ---- e2e: host (pinned) buffers in, host (pinned) buffers out, through kb_star_join_host
+    # ---- multi-GPU legs (N > 1): the cross-rank GROUP BY merge, the non-subject-key join through the peer-memory shuffle, strong scaling
+    multi = None
+    if world > 1 and not args.no_multi:
+        multi = multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max, reduce_sum, c, datagen, kd, torch)
+
+    # ---- e2e: host (pinned) buffers in, host (pinned) buffers out, through kb_star_join_host_into. This call REPLACES the device store
+    # (and drops the index and the plan with it), so it runs after every leg that needs them.
+    if plan:
+        plan.free()
     e2e = None
     if not args.no_e2e:
         n_out_cols = len({t.value for pt in pats for t in (pt.s, pt.p, pt.o) if t.is_var})
@@ -342,7 +410,7 @@ def main():
             rows_e, slots_e = step_e2e()
         barrier()
         t1 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(K):
             rows_e, slots_e = step_e2e()
         ctx.synchronize()
         barrier()
@@ -350,38 +418,55 @@ def main():
         assert rows_e == rows_step, (rows_e, rows_step)
         e2e = {"dt": dt_e, "h2d": 3 * 4 * n, "d2h": len(slots_e) * 4 * rows_e}
         ctx.get_stats(reset=True)
-    if args.no_e2e or args.steps * 0.03 < 1.0:  # keep the GPU under the same load until nvidia-smi has a few samples
+    if args.no_e2e or K * 0.03 < 1.0:  # keep the GPU under the same load until the clock sampler has a few samples
         t_s = time.perf_counter()
         while time.perf_counter() - t_s < 1.2:
-            step_resident() if args.no_e2e else step_e2e()
+            step_sync() if args.no_e2e else step_e2e()
     sampler.stop_flag.set()
     if rank == 0:
         sampler.join(timeout=2)
 
     # ---- reduce over ranks: max time, sum of rows
-    if world > 1:
-        t = torch.tensor([dt, e2e["dt"] if e2e else 0.0, scan_leg[0] if scan_leg else 0.0], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        r = torch.tensor([rows_step, n], dtype=torch.int64, device=dev)
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        dt, dte = float(t[0]), float(t[1])
-        if scan_leg:
-            scan_leg = (float(t[2]), scan_leg[1])
-        rows_all, n_all = int(r[0]), int(r[1])
-    else:
-        dte = e2e["dt"] if e2e else 0.0
-        rows_all, n_all = rows_step, n
+    dt, dte, dt_sync_m, dts_m = reduce_max(dt, e2e["dt"] if e2e else 0.0, sync_leg[0] if sync_leg else 0.0, scan_leg[0] if scan_leg else 0.0)
+    rows_all, n_all = reduce_sum(rows_step, n)
+    dev_ms_step_max, = reduce_max(st["total_ms"] / K)
+
+    # ---- N = 1: BASELINE configs[1]'s own size (10 M triples) through the same prepared path — the size the CPU arm runs
+    cfg2_10m = None
+    if world == 1 and not args.no_cpu and args.employees > CFG2_10M_EMPLOYEES and args.query == "cfg2":
+        d10 = datagen.employee_dataset(CFG2_10M_EMPLOYEES)
+        ctx.dict_numeric_load(d10.num_or0, d10.is_num)
+        ctx.store_load(d10.s, d10.p, d10.o)
+        ctx.build_index()
+        js10, pats10, filt10 = datagen.employee_queries(d10)["cfg2"]
+        p10 = ctx.prepare_star_join(js10, pats10, filt10, ring=args.ring)
+        run_pipelined(p10, W)
+        rows10, dt10, st10 = timed(lambda k: run_pipelined(p10, k), K)
+        p10.free()
+        h10 = [torch.from_numpy(x).pin_memory() for x in (d10.s, d10.p, d10.o)]
+        o10 = [torch.empty(rows10 + 16, dtype=torch.int32).pin_memory() for _ in range(4)]
+        e10 = lambda: c.star_join_host_raw(ctx, h10[0].data_ptr(), h10[1].data_ptr(), h10[2].data_ptr(), d10.n_triples, js10, pats10, filt10, [o.data_ptr() for o in o10], o10[0].numel())
+        e10()
+        ctx.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(K):
+            re10, _ = e10()
+        ctx.synchronize()
+        dte10 = (time.perf_counter() - t1) / K
+        assert re10 == rows10
+        cfg2_10m = {"workload": f"BASELINE configs[1]: {CFG2_10M_EMPLOYEES} employees = {d10.n_triples} triples, same query, prepared index path",
+                    "value": rows10 / (dt10 / K), "unit": UNIT, "ms_per_step": dt10 / K * 1e3, "bindings_per_step": int(rows10),
+                    "e2e": {"value": rows10 / dte10, "unit": UNIT, "ms_per_step": dte10 * 1e3, "h2d_bytes_per_step": 12 * d10.n_triples, "d2h_bytes_per_step": 16 * int(rows10)}}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    ms_step = dt / args.steps * 1e3
-    value = rows_all / (dt / args.steps)
+    ms_step = dt / K * 1e3
+    value = rows_all / (dt / K)
     peak, peak_src = measured_peak()
 
     # ---- roofline of each kernel family (rank 0's launches): algorithmic bytes per SURVEY.md §8(d)
-    K = args.steps
     E_loc = d.n_employees
     n_pat = len(pats)
     m_rows = []
@@ -405,7 +490,7 @@ def main():
                 fam["build"] = {"alg_bytes": b_build, "ms": stx["build_ms"] / K, "launches_per_step": stx["build_launches"] / K,
                                 "note": "index path: K_build reads the predicate slice (8 B/row) and evaluates the pushed-down FILTER itself"}
             else:
-                fam["probe"]["note"] += "; all build sides are persistent per-predicate tables of the index (the reference's spo[s][P] lookup): no per-query build" 
+                fam["probe"]["note"] += "; all build sides are persistent per-predicate tables of the index (the reference's spo[s][P] lookup): no per-query build"
         else:
             b_scan = 12 * n + sum(4 * 2 * m for m in m_rows)
             b_build = sum(16 * m_rows[k] for k in builds)
@@ -431,40 +516,176 @@ def main():
 
     indexed = st.get("index_joins", 0) > 0
     roofline = roof(families(st, indexed), st)
-    scan_path = None
-    if scan_leg is not None:
-        dts, st_scan = scan_leg
-        scan_path = {"value": rows_all / (dts / K), "unit": UNIT, "ms_per_step": dts / K * 1e3, "gpu_launches": int(st_scan["kernel_launches"]),
-                     "roofline": roof(families(st_scan, False), st_scan),
-                     "note": "same K steps with the index switched off: every step scans the 12-byte/triple store (the e2e leg always does)"}
-
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "triples_total": n_all, "bindings_per_step": rows_all, "sharding": "kb_shard_of(subject) = (id >> 10) % n_gpus (block-cyclic on dense ids), no data-path collective",
-                   "l2": "inputs per step (index path: 0.4 GB of predicate slices + 0.13 GB of tables; scan path: 1.2 GB of triple columns) exceed the 126 MB L2; no explicit flush",
-                   "store": ("predicate-partitioned index built ONCE at load by kb_store_build_index (= SparqlDatabase::build_all_indexes), %d predicates, %.1f ms, outside the timed region"
-                             % (n_pred, index_ms)) if not args.no_index else "unindexed: every step scans the store",
-                   "datagen_s": round(t_gen, 1), "host_numa_node": numa_node,
-                   "timing": "wall clock around K steps between barrier+synchronize, max over ranks; every step ends with a stream sync inside the library"},
+        "protocol": ("index-resident: store + predicate index resident in HBM, one probe_index_kernel launch per step through a prepared plan (ring of %d), "
+                     "K steps back to back, every step's row count collected" % args.ring) if plan is not None or indexed else "SURVEY.md 8(d): scan + build + probe every step",
+        "config": {"workload": workload_name(args)},
+        "details": {"triples_total": n_all, "bindings_per_step": rows_all, "sharding": "kb_shard_of(subject) = (id >> 10) % n_gpus (block-cyclic on dense ids), no data-path collective",
+                    "l2": "inputs per step (index path: 0.4 GB of predicate slices + 0.13 GB of tables; scan path: 1.2 GB of triple columns) exceed the 126 MB L2; no explicit flush",
+                    "store": ("predicate-partitioned index built ONCE at load by kb_store_build_index (= SparqlDatabase::build_all_indexes), %d predicates, %.1f ms "
+                              "(first build in a fresh process, which also grows the CUDA memory pool from empty: %.1f ms), outside the timed region"
+                              % (n_pred, index_ms, index_ms_first)) if not args.no_index else "unindexed: every step scans the store",
+                    "datagen_s": round(t_gen, 1), "host_numa_node": numa_node,
+                    "timing": "wall clock around K steps between barrier+synchronize, max over ranks",
+                    "host_overhead_us_per_step": (ms_step - dev_ms_step_max) * 1e3, "device_ms_per_step_max_over_ranks": dev_ms_step_max},
         "roofline": roofline,
         "gpu_launches": int(st["kernel_launches"]),
         "clocks": sampler.summary(),
     }
-    if scan_path:
-        line["scan_path"] = scan_path
+    if sync_leg:
+        line["sync_path"] = {"value": rows_all / (dt_sync_m / K), "unit": UNIT, "ms_per_step": dt_sync_m / K * 1e3, "gpu_launches": int(sync_leg[1]["kernel_launches"]),
+                             "device_ms_per_step": sync_leg[1]["total_ms"] / K,
+                             "note": "same K steps through the synchronous kb_star_join (result allocation + stream synchronisation every step)"}
+    if scan_leg:
+        st_scan = scan_leg[1]
+        line["scan_path"] = {"value": rows_all / (dts_m / K), "unit": UNIT, "ms_per_step": dts_m / K * 1e3, "gpu_launches": int(st_scan["kernel_launches"]),
+                             "protocol": "SURVEY.md 8(d): R / (t_scan + t_build + t_probe), every step scans the 12-byte/triple store",
+                             "roofline": roof(families(st_scan, False), st_scan)}
+    if multi:
+        line["multi_gpu"] = multi
+    if cfg2_10m:
+        line["cfg2_10M"] = cfg2_10m
     if e2e:
-        line["e2e"] = {"value": rows_all / (dte / args.steps), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                       "ms_per_step": dte / args.steps * 1e3, "api": "kb_star_join_host (pinned host columns in, pinned host binding columns out; chunked upload overlapped with the scan)"}
+        line["e2e"] = {"value": rows_all / (dte / K), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                       "ms_per_step": dte / K * 1e3, "api": "kb_star_join_host_into (pinned host columns in, pinned host binding columns out; chunked upload overlapped with the scan)"}
     if world == 1 and not args.no_cpu:
         if prev_affinity:
             os.sched_setaffinity(0, prev_affinity)  # the CPU arm gets every host thread back
-        base, _ = cpu_reference_run(args, steps=5, warmup=1)
+        base, _ = cpu_reference_run(args, steps=3, warmup=1, employees=min(args.cpu_sample, args.employees), budget_s=20.0)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         line["cpu_columnar_openmp"] = base["columnar_openmp"]
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max, reduce_sum, c, datagen, kd, torch):
+    """The legs that exercise the multi-GPU path proper. Every result is asserted against closed forms of the generator."""
+    import numpy as np
+
+    out = {}
+    E_glob = args.employees * world
+    # ---- cfg3: 4-pattern star + GROUP BY ?t COUNT, local fused join+group per rank, partial groups all-gathered (NCCL) and folded by
+    # kb_groups_merge on every rank. Pipelined: query i+1 is on the device while the partials of query i are exchanged and merged.
+    js3, pats3, _ = datagen.employee_queries(d)["cfg3"]
+    plan3 = ctx.prepare_star_join(js3, pats3, None, group_slots=[1], aggs=[(c.AGG_COUNT, 0)], ring=args.ring)
+
+    def cfg3_steps(k):
+        prev, merged, rows = None, None, 0
+        for _ in range(k):
+            t = plan3.submit()
+            if prev is not None:
+                packed, rows = plan3.collect_groups(prev, packed=True)
+                merged = ctx.groups_merge(kd.allgather_groups(packed, dev))
+            prev = t
+        packed, rows = plan3.collect_groups(prev, packed=True)
+        merged = ctx.groups_merge(kd.allgather_groups(packed, dev))
+        return rows, merged
+
+    cfg3_steps(3)
+    ctx.get_stats(reset=True)
+    ctx.set_timing(True)
+    barrier()
+    t0 = time.perf_counter()
+    rows3, merged = cfg3_steps(K)
+    ctx.synchronize()
+    barrier()
+    dt3 = time.perf_counter() - t0
+    st3 = ctx.get_stats(reset=True)
+    ctx.set_timing(False)
+    plan3.free()
+    # parity: every employee has all four patterns -> one row each; groups = global title histogram (closed form per shard, summed)
+    idx = datagen.employee_indices_of_shard(d, rank, world)
+    titles = datagen.employee_title_ids(d, idx)
+    tids = [int(x) for x in d.title_id_by_value]
+    want = reduce_sum(*[int((titles == t).sum()) for t in tids])
+    got = {int(k): int(n_) for k, n_ in zip(merged["keys"][0], merged["counts"])}
+    assert got == {t: w for t, w in zip(tids, want) if w}, (got, want)
+    rows3_all, = reduce_sum(rows3)
+    assert rows3_all == E_glob == sum(want)
+    dt3m, dev3 = reduce_max(dt3, st3["probe_ms"] / K)
+    out["cfg3_group_by_merge"] = {
+        "workload": f"BASELINE configs[2]: {6 * args.employees} triples per GPU x {world} GPUs, 4-pattern star + GROUP BY ?t COUNT; per-rank fused join+group kernel, "
+                    "partial groups all-gathered over NCCL, folded on every rank by kb_groups_merge",
+        "value": rows3_all / (dt3m / K), "unit": "bindings/s", "ms_per_step": dt3m / K * 1e3, "device_ms_per_step_join_group": dev3, "groups": len(got),
+        "collective": "all_gather_into_tensor of one %d-byte slot per rank and step" % kd.GROUPS_SLOT_BYTES, "parity": "groups == closed-form global title histogram"}
+
+    # ---- shuffle_join: (?e reports_to ?m) . (?m foaf:title ?t) — the first pattern's rows live with ?e, the join key ?m is not their
+    # subject: they are re-sharded by ?m with ONE kernel per rank (kb_shuffle_push: peer stores over NVLink) and joined locally.
+    E_, M_, T_ = 0, 5, 1
+    e_ids, m_ids, t_of_m = datagen.reports_to_relation(d, rank, world)
+    left = ctx.rel_from_host([E_, M_], [e_ids, m_ids])
+    right = ctx.scan([c.pattern(c.V(M_), c.K(d.ids["foaf:title"]), c.V(T_))])[0]
+    cap = int(len(e_ids) * 1.25) + 65536
+    ps = kd.PeerShuffle(ctx, n_cols=2, capacity_rows=cap)
+    sh_times, join_times, rows_j = [], [], 0
+    for rep in range(1 + max(3, min(K, 6))):
+        barrier()
+        t0 = time.perf_counter()
+        sh = ps.shuffle(left, M_)
+        t1 = time.perf_counter()
+        j = ctx.hash_join(sh, right)
+        rows_j = j.n_rows
+        ctx.synchronize()
+        t2 = time.perf_counter()
+        if rep:
+            sh_times.append(t1 - t0)
+            join_times.append(t2 - t1)
+        if rep == 0:  # parity (untimed): order-independent digest of the joined rows, summed over ranks == closed form summed over ranks
+            got_d = datagen.row_checksums(j.to_numpy([E_, M_, T_]))
+            want_d = datagen.row_checksums(np.stack([e_ids, m_ids, t_of_m], axis=1))
+            owner_ok = bool((datagen.shard_of_np(sh.to_numpy([E_, M_])[:, 1], world) == rank).all())
+        sh.free()
+        j.free()
+    # the 64-bit digests travel as two 32-bit halves (the all-reduce sums int64) and are recombined modulo 2^64
+    n_got, lo_g, hi_g = reduce_sum(got_d[0], got_d[1] & 0xFFFFFFFF, got_d[1] >> 32)
+    n_want, lo_w, hi_w = reduce_sum(want_d[0], want_d[1] & 0xFFFFFFFF, want_d[1] >> 32)
+    ok_all, = reduce_sum(int(owner_ok))
+    assert n_got == n_want == E_glob and ok_all == world, (n_got, n_want, ok_all)
+    assert ((hi_g << 32) + lo_g) % (1 << 64) == ((hi_w << 32) + lo_w) % (1 << 64), "joined rows differ from the closed form"
+    t_sh, t_j = reduce_max(float(np.median(sh_times)), float(np.median(join_times)))
+    rows_j_all, sent = reduce_sum(rows_j, int((datagen.shard_of_np(m_ids, world) != rank).sum()))
+    nv_bytes_rank = 8 * sent / world
+    out["shuffle_join"] = {
+        "workload": f"path join (?e reports_to ?m).(?m foaf:title ?t): {len(e_ids)} rows per rank x {world} ranks re-sharded by the non-subject key ?m, then joined locally",
+        "value": rows_j_all / (t_sh + t_j), "unit": "bindings/s", "ms_shuffle": t_sh * 1e3, "ms_join": t_j * 1e3,
+        "nvlink_bytes_sent_per_rank": nv_bytes_rank, "nvlink_gbs_per_rank": nv_bytes_rank / t_sh / 1e9,
+        "exchange": "kb_shuffle_push: one kernel per rank sorts a tile by destination in shared memory, reserves its range on the receiver's own cursor "
+                    "(peer atomic) and streams 128-byte-aligned runs into the receiver's buffer; two symmetric-memory barriers around it; no count exchange",
+        "parity": "bag digest of the joined rows summed over ranks == closed form; every received row belongs to its rank"}
+    left.free()
+    right.free()
+    del ps
+
+    # ---- strong scaling: the 100 M-triple store of BASELINE configs[2] (args.employees in total) split over the N GPUs
+    ctx2 = c.Context(local)
+    ds = datagen.employee_shard(args.employees, rank, world)
+    ctx2.set_sharding(rank, world)
+    ctx2.dict_numeric_load(ds.num_or0, ds.is_num)
+    ctx2.store_load(ds.s, ds.p, ds.o)
+    ctx2.build_index()
+    jss, patss, filts = datagen.employee_queries(ds)[args.query]
+    plans = ctx2.prepare_star_join(jss, patss, filts, ring=args.ring)
+    run_pipelined(plans, 5)
+    ctx2.set_timing(True)
+    ctx2.get_stats(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    rows_s = run_pipelined(plans, K)
+    ctx2.synchronize()
+    barrier()
+    dt_s = time.perf_counter() - t0
+    sts = ctx2.get_stats(reset=True)
+    plans.free()
+    ctx2.close()
+    rows_s_all, = reduce_sum(rows_s)
+    dt_sm, dev_s = reduce_max(dt_s, sts["total_ms"] / K)
+    out["strong"] = {"workload": f"{6 * args.employees} triples in TOTAL over {world} GPUs (BASELINE configs[2] store), same query and protocol as the headline",
+                     "value": rows_s_all / (dt_sm / K), "unit": "bindings/s", "ms_per_step": dt_sm / K * 1e3, "device_ms_per_step": dev_s,
+                     "bindings_per_step": rows_s_all, "scaling": "strong"}
+    return out
 
 
 if __name__ == "__main__":

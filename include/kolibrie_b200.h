@@ -232,12 +232,42 @@ KB_API kb_status kb_groups_keys(const kb_groups* g, uint32_t col, const uint32_t
 KB_API kb_status kb_groups_values(const kb_groups* g, uint32_t agg, const double** values); /* host pointer, n_groups */
 KB_API kb_status kb_groups_counts(const kb_groups* g, const uint64_t** counts);            /* rows per group */
 KB_API void kb_groups_free(kb_groups* g);
+/* Cross-rank GROUP BY (one process per GPU, store sharded by subject): every rank aggregates its shard, serialises the partial result
+ * with kb_groups_pack (dst == NULL: *bytes = size needed), the host layer gathers the buffers (NCCL / any all-gather), and
+ * kb_groups_merge folds them on the device: counts and SUM/AVG accumulators add, MIN/MAX fold, AVG = total sum / total count —
+ * the aggregate of execute_query.rs:1150-1227 over the union of the shards' rows. */
+KB_API kb_status kb_groups_pack(const kb_groups* g, void* dst, uint64_t capacity_bytes, uint64_t* bytes);
+KB_API kb_status kb_groups_merge(kb_ctx* ctx, const void* const* parts, const uint64_t* part_bytes, uint32_t n_parts, kb_groups** out);
 /* StarJoin + GROUP BY in one call (the aggregate of execute_query.rs:1150-1227 over the rows of engine.rs:587-691). With the store
  * index valid, one GROUP BY variable and at most one aggregate, the grouping is folded into the probe kernel and no joined row is
  * ever written; every other shape = kb_star_join followed by kb_group_aggregate. *n_rows (nullable) receives the joined row count. */
 KB_API kb_status kb_star_join_aggregate(kb_ctx* ctx, uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter,
                                         uint32_t n_filter_ops, const uint32_t* group_slots, uint32_t n_group, const kb_agg* aggs, uint32_t n_aggs,
                                         kb_groups** out, uint64_t* n_rows);
+
+/* ------------------------------------------------------------------ prepared star joins: resolve once, launch many times.
+ * The reference optimises a query into a PhysicalOperator once and executes it per call (engine.rs:54); here the per-call work of the
+ * synchronous operators — pattern/filter marshalling, cudaMallocAsync of the result, the stream synchronisation after the launch — is
+ * what limits a 0.1 ms query, so a plan keeps the resolved launch and a ring of `ring` pre-allocated result buffers:
+ *   kb_plan_submit   ONE kernel launch (asynchronous; no allocation, no host synchronisation), returns a ticket
+ *   kb_plan_collect  waits for exactly that launch; *n_rows = joined rows; *rows (nullable) = a VIEW of the ring slot (kb_rel_free it;
+ *                    its columns stay valid until `ring` further submits reuse the slot); *groups (nullable) = the GROUP BY result of
+ *                    a grouped plan (kb_groups_free it).
+ * Only queries that take the one-kernel index path can be prepared (kb_store_build_index done; every pattern (?s P ?o) whose key
+ * column has a persistent table): anything else -> KB_E_UNSUPPORTED, use the synchronous operators. n_group = 0: rows are produced;
+ * n_group = 1 and n_aggs <= 1: GROUP BY folded into the kernel as in kb_star_join_aggregate (fixed 4096-group table; more groups ->
+ * KB_E_LIMIT from kb_plan_collect). A plan is bound to the store / index / numeric-table version it was prepared on: after any
+ * mutation kb_plan_submit returns KB_E_INVALID ("stale plan"). Submitting while the ring slot's previous ticket is uncollected ->
+ * KB_E_LIMIT. Row order and bag of rows are those of kb_star_join. */
+typedef struct kb_plan kb_plan;
+KB_API kb_status kb_star_join_prepare(kb_ctx* ctx, uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter,
+                                      uint32_t n_filter_ops, const uint32_t* group_slots, uint32_t n_group, const kb_agg* aggs, uint32_t n_aggs,
+                                      uint32_t ring, kb_plan** out);
+KB_API kb_status kb_plan_submit(kb_ctx* ctx, kb_plan* plan, uint64_t* ticket);
+KB_API kb_status kb_plan_collect(kb_ctx* ctx, kb_plan* plan, uint64_t ticket, uint64_t* n_rows, kb_rel** rows, kb_groups** groups);
+KB_API kb_status kb_plan_info(const kb_plan* plan, uint32_t* ring, uint64_t* capacity_rows, uint32_t* n_cols, uint32_t* slots /* [KB_MAX_COLS] or NULL */,
+                              uint32_t* grouped);
+KB_API void kb_plan_free(kb_ctx* ctx, kb_plan* plan);
 
 /* ------------------------------------------------------------------ Datalog (Reasoner::infer_with_strategy, infer_generic.rs:27-53)
  * Facts = the ctx store. Inferred facts are appended to the store (segment tag KB_TAG_INFERRED), exactly as the
@@ -268,6 +298,15 @@ KB_API kb_status kb_partition(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, 
 KB_API kb_status kb_partition_counts(kb_ctx* ctx, const kb_rel* r, uint32_t key_slot, uint32_t n_parts, uint64_t* counts /* [n_parts] */);
 KB_API kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* r, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols /* [n_parts * n_cols] */,
                                     const uint64_t* base /* [n_parts] */, uint64_t capacity_rows);
+/* The same without the count pass and without any count exchange: peer_cursors[d] = device-visible address of a u32 cursor that rank d
+ * owns (peer-mapped, zeroed by d before the exchange, and a barrier across ranks before anybody pushes). A tile's rows for d are
+ * appended where an atomicAdd on d's cursor reserves them, so after the barrier that follows the call every rank reads how many rows
+ * it received from its OWN cursor. Rows of different senders interleave (a relation is a bag). */
+KB_API kb_status kb_shuffle_push(kb_ctx* ctx, const kb_rel* r, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols /* [n_parts * n_cols] */,
+                                 uint32_t* const* peer_cursors /* [n_parts] */, uint64_t capacity_rows);
+/* a relation over columns the CALLER owns (e.g. a shuffle's receive buffer): no copy. Every column must be 16-byte aligned, stay
+ * allocated while the relation is in use and be readable up to the next multiple of 256 bytes past its last row (TMA tile loads). */
+KB_API kb_status kb_rel_wrap_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out);
 KB_API kb_status kb_rel_from_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out);
 KB_API kb_status kb_store_download(kb_ctx* ctx, uint32_t* s, uint32_t* p, uint32_t* o, uint64_t cap, uint64_t* n);
 

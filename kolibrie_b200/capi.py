@@ -180,6 +180,13 @@ def lib() -> C.CDLL:
         "kb_groups_values": (i32, [vp, u32, P(P(C.c_double))]),
         "kb_groups_counts": (i32, [vp, P(P(u64))]),
         "kb_groups_free": (None, [vp]),
+        "kb_groups_pack": (i32, [vp, vp, u64, P(u64)]),
+        "kb_groups_merge": (i32, [vp, P(vp), P(u64), u32, P(vp)]),
+        "kb_star_join_prepare": (i32, [vp, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), u32, P(KbAgg), u32, u32, P(vp)]),
+        "kb_plan_submit": (i32, [vp, vp, P(u64)]),
+        "kb_plan_collect": (i32, [vp, vp, u64, P(u64), P(vp), P(vp)]),
+        "kb_plan_info": (i32, [vp, P(u32), P(u64), P(u32), P(u32), P(u32)]),
+        "kb_plan_free": (None, [vp, vp]),
         "kb_star_join_aggregate": (i32, [vp, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), u32, P(KbAgg), u32, P(vp), P(u64)]),
         "kb_datalog_fixpoint": (i32, [vp, P(KbRule), u32, u32, P(vp), P(KbFixpointStats)]),
         "kb_shard_of": (u32, [u32, u32]),
@@ -187,6 +194,8 @@ def lib() -> C.CDLL:
         "kb_partition": (i32, [vp, vp, u32, u32, P(vp), P(u64)]),
         "kb_partition_counts": (i32, [vp, vp, u32, u32, P(u64)]),
         "kb_shuffle_scatter": (i32, [vp, vp, u32, u32, P(vp), P(u64), u64]),
+        "kb_shuffle_push": (i32, [vp, vp, u32, u32, P(vp), P(vp), u64]),
+        "kb_rel_wrap_device": (i32, [vp, P(u32), u32, P(vp), u64, P(vp)]),
         "kb_star_join_host": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), P(u64)]),
         "kb_star_join_host_into": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), u64, P(u64)]),
         "perform_hash_join_cuda": (None, [vp, vp, vp, u32, u32, P(u32), P(P(u32)), P(u32)]),
@@ -204,8 +213,9 @@ EXPORTED_SYMBOLS = [
     "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
     "kb_store_download", "kb_dict_numeric_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
-    "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_star_join_aggregate",
-    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
+    "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_groups_pack", "kb_groups_merge", "kb_star_join_aggregate",
+    "kb_star_join_prepare", "kb_plan_submit", "kb_plan_collect", "kb_plan_info", "kb_plan_free",
+    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_shuffle_push", "kb_rel_wrap_device", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
 ]
 
 
@@ -302,10 +312,13 @@ class Context:
         self.h = h
         self.device = device
         self._rels = weakref.WeakSet()
+        self._plans = weakref.WeakSet()
         _LIVE_CONTEXTS.add(self)
 
     def close(self):
         if self.h:
+            for pl in list(self._plans):
+                pl.free()
             for r in list(self._rels):  # relations first, while their stream still exists
                 r.free()
             lib().kb_ctx_destroy(self.h)
@@ -470,6 +483,49 @@ class Context:
         self._check(lib().kb_star_join_aggregate(self.h, join_slot, patterns(pats), len(pats), a, nf, gs, len(group_slots), ag, len(aggs), C.byref(g), C.byref(n_rows)))
         return self._groups_to_dict(g), n_rows.value
 
+    def star_join_aggregate_packed(self, join_slot: int, pats: Sequence[KbPattern], filt, group_slots: Sequence[int], aggs: Sequence[tuple]):
+        """kb_star_join_aggregate, result left in its transport form (kb_groups_pack): what one rank contributes to a cross-rank
+        GROUP BY. Returns (uint8 array, joined row count)."""
+        a, nf = filter_prog(filt)
+        gs = (C.c_uint32 * max(len(group_slots), 1))(*group_slots)
+        ag = (KbAgg * max(len(aggs), 1))()
+        for i, (k, s) in enumerate(aggs):
+            ag[i] = KbAgg(k, s)
+        g = C.c_void_p()
+        n_rows = C.c_uint64()
+        self._check(lib().kb_star_join_aggregate(self.h, join_slot, patterns(pats), len(pats), a, nf, gs, len(group_slots), ag, len(aggs), C.byref(g), C.byref(n_rows)))
+        try:
+            return self._groups_pack(g), n_rows.value
+        finally:
+            lib().kb_groups_free(g)
+
+    def _groups_pack(self, g) -> np.ndarray:
+        need = C.c_uint64()
+        self._check(lib().kb_groups_pack(g, None, 0, C.byref(need)))
+        buf = np.empty(need.value, dtype=np.uint8)
+        self._check(lib().kb_groups_pack(g, _ptr(buf), need.value, C.byref(need)))
+        return buf
+
+    def groups_merge(self, parts: Sequence[np.ndarray]):
+        """kb_groups_merge: fold the packed partial GROUP BY results of several ranks (device kernel); returns the groups dict"""
+        parts = [np.ascontiguousarray(p_, dtype=np.uint8) for p_ in parts]
+        ptrs = (C.c_void_p * len(parts))(*[p_.ctypes.data for p_ in parts])
+        sizes = (C.c_uint64 * len(parts))(*[p_.nbytes for p_ in parts])
+        g = C.c_void_p()
+        self._check(lib().kb_groups_merge(self.h, ptrs, sizes, len(parts), C.byref(g)))
+        return self._groups_to_dict(g)
+
+    def prepare_star_join(self, join_slot: int, pats: Sequence[KbPattern], filt=None, group_slots: Sequence[int] = (), aggs: Sequence[tuple] = (), ring: int = 4) -> "Plan":
+        """kb_star_join_prepare: resolve the query once; Plan.submit() is then one asynchronous kernel launch"""
+        a, nf = filter_prog(filt)
+        gs = (C.c_uint32 * max(len(group_slots), 1))(*group_slots)
+        ag = (KbAgg * max(len(aggs), 1))()
+        for i, (k, s) in enumerate(aggs):
+            ag[i] = KbAgg(k, s)
+        h = C.c_void_p()
+        self._check(lib().kb_star_join_prepare(self.h, join_slot, patterns(pats), len(pats), a, nf, gs, len(group_slots), ag, len(aggs), ring, C.byref(h)))
+        return Plan(self, h)
+
     def _groups_to_dict(self, g):
         try:
             n, ng, na = C.c_uint64(), C.c_uint32(), C.c_uint32()
@@ -515,6 +571,21 @@ class Context:
         bs = (C.c_uint64 * n_parts)(*base)
         self._check(lib().kb_shuffle_scatter(self.h, rel.h, key_slot, n_parts, pc, bs, capacity_rows))
 
+    def shuffle_push(self, rel: Relation, key_slot: int, n_parts: int, peer_cols: Sequence[int], peer_cursors: Sequence[int], capacity_rows: int):
+        """kb_shuffle_push: like shuffle_scatter, ranges reserved on the receivers' own cursors (peer_cursors[d] = address of rank d's
+        u32 cursor in peer-mapped memory): no count pass, no count exchange"""
+        pc = (C.c_void_p * len(peer_cols))(*peer_cols)
+        cu = (C.c_void_p * n_parts)(*peer_cursors)
+        self._check(lib().kb_shuffle_push(self.h, rel.h, key_slot, n_parts, pc, cu, capacity_rows))
+
+    def rel_wrap_device(self, slots: Sequence[int], ptrs_: Sequence[int], n: int) -> Relation:
+        """kb_rel_wrap_device: a relation over device columns the caller owns (no copy)"""
+        sl = (C.c_uint32 * max(len(slots), 1))(*slots)
+        ptrs = (C.c_void_p * max(len(ptrs_), 1))(*ptrs_)
+        out = C.c_void_p()
+        self._check(lib().kb_rel_wrap_device(self.h, sl, len(slots), ptrs, n, C.byref(out)))
+        return Relation(self, out)
+
     def star_join_host(self, s, p, o, join_slot: int, pats: Sequence[KbPattern], filt=None):
         """One-shot host-buffer call (kb_star_join_host): upload + star join + download; result columns are malloc'd by the
         library and copied into numpy arrays here. Returns (rows x cols uint32 array, slots)."""
@@ -549,6 +620,63 @@ class Context:
     def set_sharding(self, rank: int, world: int):
         """the store holds shard `rank` of `world` (sharded by subject with kb_shard_of): enables the dense key compaction"""
         self._check(lib().kb_set_sharding(self.h, rank, world))
+
+
+class Plan:
+    """kb_plan: a prepared star join with a ring of result buffers. submit() launches, collect(ticket) waits for that launch."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self.h = handle
+        ring, cap, nc, grouped = C.c_uint32(), C.c_uint64(), C.c_uint32(), C.c_uint32()
+        slots = (C.c_uint32 * KB_MAX_COLS)()
+        ctx._check(lib().kb_plan_info(self.h, C.byref(ring), C.byref(cap), C.byref(nc), slots, C.byref(grouped)))
+        self.ring, self.capacity_rows, self.grouped = ring.value, cap.value, bool(grouped.value)
+        self.slots = [slots[i] for i in range(nc.value)]
+        self._ticket = C.c_uint64()
+        self._rows = C.c_uint64()
+        ctx._plans.add(self)
+
+    def submit(self) -> int:
+        rc = lib().kb_plan_submit(self.ctx.h, self.h, C.byref(self._ticket))
+        if rc != KB_OK:
+            self.ctx._check(rc)
+        return self._ticket.value
+
+    def collect(self, ticket: int) -> int:
+        """joined row count of the query `ticket` (waits for it)"""
+        rc = lib().kb_plan_collect(self.ctx.h, self.h, ticket, C.byref(self._rows), None, None)
+        if rc != KB_OK:
+            self.ctx._check(rc)
+        return self._rows.value
+
+    def collect_rows(self, ticket: int) -> Relation:
+        """the result as a Relation VIEW of the ring slot (valid until `ring` further submits)"""
+        r = C.c_void_p()
+        self.ctx._check(lib().kb_plan_collect(self.ctx.h, self.h, ticket, C.byref(self._rows), C.byref(r), None))
+        return Relation(self.ctx, r)
+
+    def collect_groups(self, ticket: int, packed: bool = False):
+        """(groups dict — or the kb_groups_pack bytes when packed=True —, joined row count) of a grouped plan"""
+        g = C.c_void_p()
+        self.ctx._check(lib().kb_plan_collect(self.ctx.h, self.h, ticket, C.byref(self._rows), None, C.byref(g)))
+        if packed:
+            try:
+                return self.ctx._groups_pack(g), self._rows.value
+            finally:
+                lib().kb_groups_free(g)
+        return self.ctx._groups_to_dict(g), self._rows.value
+
+    def free(self):
+        if self.h:
+            lib().kb_plan_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 def star_join_host_raw(ctx: Context, s_ptr: int, p_ptr: int, o_ptr: int, n: int, join_slot: int, pats, filt, out_ptrs: Sequence[int], out_cap: int):

@@ -146,8 +146,13 @@ void timer_end(kb_ctx* ctx) {
     cudaEventRecord(ctx->timers.back().b, ctx->st);
 }
 void timers_flush(kb_ctx* ctx) {
+    size_t kept = 0;
     for (auto& t : ctx->timers) {
         float ms = 0.f;
+        if (cudaEventQuery(t.b) == cudaErrorNotReady) {  // launched by an asynchronous submit that has not finished: next flush
+            ctx->timers[kept++] = t;
+            continue;
+        }
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
             switch (t.fam) {
                 case F_SCAN: ctx->stats.scan_ms += ms; break;
@@ -164,7 +169,8 @@ void timers_flush(kb_ctx* ctx) {
         ctx->ev_pool.push_back(t.a);
         ctx->ev_pool.push_back(t.b);
     }
-    ctx->timers.clear();
+    cudaGetLastError();  // cudaErrorNotReady is sticky in the per-thread last-error slot
+    ctx->timers.resize(kept);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -501,7 +507,7 @@ kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::u
     return KB_OK;
 }
 
-static u32 pow2_at_least(u64 x) {
+u32 pow2_at_least(u64 x) {
     u64 p = 1024;
     while (p < x) p <<= 1;
     return (u32)std::min<u64>(p, 1ull << 31);
@@ -741,7 +747,7 @@ kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32
 }
 
 kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 K, const kb_filter_op* filter, u32 n_ops, bool allow_fused_scan,
-                          std::unique_ptr<kb_rel>* out, AggSpec* agg) {
+                          std::unique_ptr<kb_rel>* out, AggSpec* agg, IndexPlan* plan_only) {
     if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a star join takes 1..%d patterns (got %u)", MAXP, K);
     KB_TRY(validate_filter(ctx, filter, n_ops));
     std::vector<std::vector<u32>> pv(K), psrc(K);
@@ -794,6 +800,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
         for (u32 a = 0; a < K && ok; a++)
             for (u32 b = a + 1; b < K && ok; b++)
                 for (u32 s2 : pv[a]) if (s2 != join_slot && std::find(pv[b].begin(), pv[b].end(), s2) != pv[b].end()) ok = false;
+        if (ok && empty && plan_only) return fail(ctx, KB_E_UNSUPPORTED, "prepared plan: a pattern's predicate does not occur in the store (the answer is empty)");
         if (ok && empty) {
             auto r = std::make_unique<kb_rel>();
             r->slots = all_slots;
@@ -907,6 +914,33 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             P.nt = numtab(ctx);
             P.cb = ctx->fast_cb;
             P.host_total = ctx->d_fast;
+            if (plan_only) {  // kb_star_join_prepare: keep the resolved launch, run nothing
+                plan_only->P = P;
+                plan_only->out_slots = out_slots;
+                plan_only->all_slots = all_slots;
+                plan_only->n_out = n_out;
+                plan_only->probe_rows = PS.n;
+                if (agg) {
+                    int gsel = -1, asel = -1;
+                    for (u32 c = 0; c < n_out; c++) {
+                        if (out_slots[c] == agg->group_slot) gsel = (int)c;
+                        if (agg->has_agg && out_slots[c] == agg->agg_slot) asel = (int)c;
+                    }
+                    const bool needs_value = agg->has_agg && agg->kind != KB_AGG_COUNT;
+                    if (gsel < 0 || (needs_value && asel < 0))
+                        return fail(ctx, KB_E_UNSUPPORTED, "prepared GROUP BY: the group or aggregate variable is not bound by the join");
+                    plan_only->agg = true;
+                    plan_only->has_agg = agg->has_agg;
+                    plan_only->agg_kind = agg->has_agg ? agg->kind : (u32)KB_AGG_COUNT;
+                    plan_only->agg_slot = agg->agg_slot;
+                    plan_only->group_slot = agg->group_slot;
+                    plan_only->P.gsel = (u32)gsel;
+                    plan_only->P.asel = asel >= 0 ? (u32)asel : 0u;
+                    plan_only->P.akind = plan_only->agg_kind;
+                }
+                plan_only->ok = true;
+                return KB_OK;
+            }
             if (agg) {
                 // GROUP BY folded into the probe kernel: no joined row is written. One try with a 4096-slot table; more groups than
                 // that (or a group / aggregate variable the join does not bind) leave agg->applied false: the caller groups separately
@@ -986,6 +1020,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             *out = select_cols(*res, all_slots);
             return KB_OK;
         }
+        if (plan_only) return fail(ctx, KB_E_UNSUPPORTED, "prepared plans take the one-kernel index path only: every pattern (?s P ?o) over a predicate whose key column has a persistent table in the store index");
         if (ok) {
             const u32 range = (u32)rng;
             const u32 off = ctrl_alloc(ctx, 16 + 2 * MAXT);
@@ -1131,6 +1166,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
         }
     }
 
+    if (plan_only) return fail(ctx, KB_E_UNSUPPORTED, "prepared plans need a valid store index (kb_store_build_index) and (?s P ?o) patterns");
     // ---- scan + build FUSED: the build-side patterns insert straight into their direct tables while the store is scanned; only the
     // probe-side pattern is materialised. Needs the key range before the scan (load-time statistics) and a probe side chosen without
     // knowing the counts: the last pattern that carries no pushed-down filter (a filtered side is the smaller build side).
@@ -1569,6 +1605,26 @@ kb_status group_table_create(kb_ctx* ctx, u64 slots, GroupParams* P, GroupTable*
     launch_group_init(*P, ctx->st);
     return KB_OK;
 }
+void groups_from_host_table(const char* hb, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g) {
+    const double* hval = (const double*)(hb + t.o_val);
+    const unsigned long long* hcnt = (const unsigned long long*)(hb + t.o_cnt);
+    const u32* hkeys = (const u32*)(hb + t.o_keys);
+    const u32* hstate = (const u32*)(hb + t.o_state);
+    if (g->kinds.empty()) for (u32 a = 0; a < n_aggs; a++) g->kinds.push_back(aggs[a].kind);
+    g->raw.resize(n_aggs);
+    for (u64 i = 0; i < t.slots; i++) {
+        if (hstate[i] != 2u) continue;
+        for (u32 c = 0; c < n_group; c++) g->keys[c].push_back(hkeys[i * 4 + c]);
+        g->counts.push_back(hcnt[i]);
+        for (u32 a = 0; a < n_aggs; a++) {
+            double v = hval[i * 8 + a];
+            g->raw[a].push_back(v);
+            if (aggs[a].kind == KB_AGG_AVG) v = v / (double)hcnt[i];   // execute_query.rs:1216
+            if (aggs[a].kind == KB_AGG_COUNT) v = (double)hcnt[i];
+            g->vals[a].push_back(v);
+        }
+    }
+}
 kb_status group_table_collect(kb_ctx* ctx, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g) {
     std::vector<char> big;  // tables past 32 MB (hundreds of thousands of groups) are not worth pinning
     void* dst = nullptr;
@@ -1587,22 +1643,7 @@ kb_status group_table_collect(kb_ctx* ctx, const GroupTable& t, u32 n_group, con
     KB_CUDA(ctx, cudaMemcpyAsync(dst, t.buf->p, t.bytes, cudaMemcpyDeviceToHost, ctx->st));
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     ctx->stats.d2h_bytes += t.bytes;
-    const char* hb = static_cast<const char*>(dst);
-    const double* hval = (const double*)(hb + t.o_val);
-    const unsigned long long* hcnt = (const unsigned long long*)(hb + t.o_cnt);
-    const u32* hkeys = (const u32*)(hb + t.o_keys);
-    const u32* hstate = (const u32*)(hb + t.o_state);
-    for (u64 i = 0; i < t.slots; i++) {
-        if (hstate[i] != 2u) continue;
-        for (u32 c = 0; c < n_group; c++) g->keys[c].push_back(hkeys[i * 4 + c]);
-        g->counts.push_back(hcnt[i]);
-        for (u32 a = 0; a < n_aggs; a++) {
-            double v = hval[i * 8 + a];
-            if (aggs[a].kind == KB_AGG_AVG) v = v / (double)hcnt[i];   // execute_query.rs:1216
-            if (aggs[a].kind == KB_AGG_COUNT) v = (double)hcnt[i];
-            g->vals[a].push_back(v);
-        }
-    }
+    groups_from_host_table(static_cast<const char*>(dst), t, n_group, aggs, n_aggs, g);
     return KB_OK;
 }
 }  // namespace kb
@@ -2371,6 +2412,106 @@ kb_status kb_groups_counts(const kb_groups* g, const uint64_t** counts) {
 }
 void kb_groups_free(kb_groups* g) { delete g; }
 
+// ---- partial GROUP BY results across ranks: pack on every rank, gather, merge on the device
+namespace {
+struct GroupsHeader {
+    uint64_t magic, n_groups;
+    uint32_t n_group_cols, n_aggs;
+    uint32_t kinds[8];
+};
+static_assert(sizeof(GroupsHeader) == 56, "layout");
+constexpr uint64_t GROUPS_MAGIC = 0x4B4247524F555031ull;  // "KBGROUP1"
+}  // namespace
+
+kb_status kb_groups_pack(const kb_groups* g, void* dst, uint64_t capacity_bytes, uint64_t* bytes) {
+    if (!g || !bytes) return KB_E_INVALID;
+    const uint64_t n = g->counts.size();
+    const uint64_t need = sizeof(GroupsHeader) + n * sizeof(kb::GroupRecord);
+    *bytes = need;
+    if (!dst) return KB_OK;  // size query
+    if (capacity_bytes < need) return KB_E_LIMIT;
+    if (g->keys.size() > 4 || g->vals.size() > 8 || g->raw.size() != g->vals.size() || g->kinds.size() != g->vals.size()) return KB_E_INVALID;
+    GroupsHeader h{};
+    h.magic = GROUPS_MAGIC;
+    h.n_groups = n;
+    h.n_group_cols = (uint32_t)g->keys.size();
+    h.n_aggs = (uint32_t)g->vals.size();
+    for (size_t a = 0; a < g->kinds.size(); a++) h.kinds[a] = g->kinds[a];
+    memcpy(dst, &h, sizeof h);
+    auto* rec = reinterpret_cast<kb::GroupRecord*>(static_cast<char*>(dst) + sizeof h);
+    for (uint64_t i = 0; i < n; i++) {
+        kb::GroupRecord r{};
+        for (size_t c = 0; c < g->keys.size(); c++) r.keys[c] = g->keys[c][i];
+        r.count = g->counts[i];
+        for (size_t a = 0; a < g->raw.size(); a++) r.raw[a] = g->raw[a][i];
+        memcpy(rec + i, &r, sizeof r);
+    }
+    return KB_OK;
+}
+
+kb_status kb_groups_merge(kb_ctx* ctx, const void* const* parts, const uint64_t* part_bytes, uint32_t n_parts, kb_groups** out) {
+    KB_ENTER(ctx);
+    if (!parts || !part_bytes || !out || n_parts == 0) return kb::fail(ctx, KB_E_INVALID, "NULL or empty argument");
+    GroupsHeader h0{};
+    uint64_t total = 0;
+    for (u32 i = 0; i < n_parts; i++) {
+        if (!parts[i] || part_bytes[i] < sizeof(GroupsHeader)) return kb::fail(ctx, KB_E_INVALID, "partial %u is truncated", i);
+        GroupsHeader h;
+        memcpy(&h, parts[i], sizeof h);
+        if (h.magic != GROUPS_MAGIC) return kb::fail(ctx, KB_E_INVALID, "partial %u is not a kb_groups_pack buffer", i);
+        if (part_bytes[i] < sizeof h + h.n_groups * sizeof(kb::GroupRecord)) return kb::fail(ctx, KB_E_INVALID, "partial %u is truncated", i);
+        if (i == 0) h0 = h;
+        else if (h.n_group_cols != h0.n_group_cols || h.n_aggs != h0.n_aggs || memcmp(h.kinds, h0.kinds, sizeof h.kinds) != 0)
+            return kb::fail(ctx, KB_E_INVALID, "partial %u was produced by a different GROUP BY (columns / aggregates differ)", i);
+        total += h.n_groups;
+    }
+    if (h0.n_group_cols == 0 || h0.n_group_cols > 4 || h0.n_aggs > 8) return kb::fail(ctx, KB_E_INVALID, "bad header");
+    if (total >= (1ull << 30)) return kb::fail(ctx, KB_E_LIMIT, "too many partial groups");
+    auto g = std::make_unique<kb_groups>();
+    g->keys.resize(h0.n_group_cols);
+    g->vals.resize(h0.n_aggs);
+    std::vector<kb_agg> aggs(h0.n_aggs);
+    for (u32 a = 0; a < h0.n_aggs; a++) { aggs[a].kind = h0.kinds[a]; aggs[a].slot = 0; }
+    if (total == 0) {
+        for (u32 a = 0; a < h0.n_aggs; a++) g->kinds.push_back(h0.kinds[a]);
+        g->raw.resize(h0.n_aggs);
+        *out = g.release();
+        return KB_OK;
+    }
+    // partial records -> device, merged by find-or-insert into a group table sized for the worst case (every partial group distinct)
+    kb::Buf recs;
+    KB_TRY(kb::alloc_buf(ctx, total * sizeof(kb::GroupRecord), &recs));
+    uint64_t at = 0;
+    for (u32 i = 0; i < n_parts; i++) {
+        GroupsHeader h;
+        memcpy(&h, parts[i], sizeof h);
+        if (h.n_groups == 0) continue;
+        KB_CUDA(ctx, cudaMemcpyAsync(static_cast<kb::GroupRecord*>(recs->p) + at, static_cast<const char*>(parts[i]) + sizeof h, h.n_groups * sizeof(kb::GroupRecord),
+                                     cudaMemcpyHostToDevice, ctx->st));
+        at += h.n_groups;
+    }
+    ctx->stats.h2d_bytes += total * sizeof(kb::GroupRecord);
+    kb::GroupParams P{};
+    P.n_gcols = h0.n_group_cols;
+    P.n_aggs = h0.n_aggs;
+    for (u32 a = 0; a < h0.n_aggs; a++) P.akind[a] = h0.kinds[a];
+    P.nt = kb::numtab(ctx);
+    kb::GroupTable tab;
+    KB_TRY(kb::group_table_create(ctx, kb::pow2_at_least(std::max<u64>(2 * total, 1024)), &P, &tab));
+    const u32 off = kb::ctrl_alloc(ctx, 4);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+    P.overflow = ctx->ctrl + off;
+    kb::timer_begin(ctx, kb::F_GROUP);
+    kb::launch_group_merge(P, static_cast<const kb::GroupRecord*>(recs->p), (u32)total, ctx->n_sms, ctx->st);
+    kb::timer_end(ctx);
+    KB_CUDA(ctx, cudaGetLastError());
+    KB_TRY(kb::ctrl_read(ctx));
+    if (ctx->h_ctrl[off]) return kb::fail(ctx, KB_E_LIMIT, "group table overflow while merging partials");
+    KB_TRY(kb::group_table_collect(ctx, tab, h0.n_group_cols, aggs.data(), h0.n_aggs, g.get()));
+    *out = g.release();
+    return KB_OK;
+}
+
 kb_status kb_star_join_aggregate(kb_ctx* ctx, uint32_t join_slot, const kb_pattern* pats, uint32_t n_pats, const kb_filter_op* filter, uint32_t n_ops,
                                  const uint32_t* group_slots, uint32_t n_group, const kb_agg* aggs, uint32_t n_aggs, kb_groups** out, uint64_t* n_rows) {
     KB_ENTER(ctx);
@@ -2425,29 +2566,38 @@ kb_status kb_partition_counts(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, 
     return KB_OK;
 }
 
-kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols, const uint64_t* base,
-                             uint64_t capacity_rows) {
-    KB_ENTER(ctx);
-    if (!in || !peer_cols || !base) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+static kb_status shuffle_common(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols, const uint64_t* base,
+                                uint32_t* const* peer_cursors, uint64_t capacity_rows) {
+    if (!in || !peer_cols || (!base && !peer_cursors)) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
     if (n_parts == 0 || n_parts > 64) return kb::fail(ctx, KB_E_LIMIT, "1..64 partitions");
     const int kc = in->col_of(key_slot);
     if (kc < 0) return kb::fail(ctx, KB_E_INVALID, "partition key slot %u is not a column", key_slot);
     if (in->n >= 0xFFFFFFF0ull || capacity_rows >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
     const u32 n_cols = (u32)in->cols.size();
     for (u32 i = 0; i < n_parts * n_cols; i++) if (!peer_cols[i]) return kb::fail(ctx, KB_E_INVALID, "peer column %u is NULL", i);
-    // device-side tables: peer column addresses, bases, cursors, overflow flag
+    if (peer_cursors) for (u32 i = 0; i < n_parts; i++) if (!peer_cursors[i]) return kb::fail(ctx, KB_E_INVALID, "peer cursor %u is NULL", i);
+    // device-side tables: peer column addresses | cursor addresses | bases | local cursors | overflow flag, ticket
     kb::Buf tab;
-    const size_t ptr_bytes = (size_t)n_parts * n_cols * sizeof(u32*);
-    KB_TRY(kb::alloc_buf(ctx, ptr_bytes + 3 * 64 * sizeof(u32), &tab));
+    const size_t col_bytes = (size_t)n_parts * n_cols * sizeof(u32*);
+    const size_t cur_bytes = 64 * sizeof(u32*);
+    KB_TRY(kb::alloc_buf(ctx, col_bytes + cur_bytes + 3 * 64 * sizeof(u32), &tab));
     char* tb = static_cast<char*>(tab->p);
+    u32* d_base = reinterpret_cast<u32*>(tb + col_bytes + cur_bytes);
+    u32* d_cursors = d_base + 64;
+    u32* d_flags = d_cursors + 64;  // [0] overflow, [1] tile ticket
     std::vector<u32> hbase(64, 0);
+    std::vector<u32*> hcur(64, nullptr);
     for (u32 i = 0; i < n_parts; i++) {
-        if (base[i] > capacity_rows) return kb::fail(ctx, KB_E_INVALID, "base[%u] beyond the receive capacity", i);
-        hbase[i] = (u32)base[i];
+        if (base) {
+            if (base[i] > capacity_rows) return kb::fail(ctx, KB_E_INVALID, "base[%u] beyond the receive capacity", i);
+            hbase[i] = (u32)base[i];
+        }
+        hcur[i] = peer_cursors ? peer_cursors[i] : d_cursors + i;
     }
-    KB_CUDA(ctx, cudaMemcpyAsync(tb, peer_cols, ptr_bytes, cudaMemcpyHostToDevice, ctx->st));
-    KB_CUDA(ctx, cudaMemcpyAsync(tb + ptr_bytes, hbase.data(), 64 * sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
-    KB_CUDA(ctx, cudaMemsetAsync(tb + ptr_bytes + 64 * sizeof(u32), 0, 2 * 64 * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(tb, peer_cols, col_bytes, cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(tb + col_bytes, hcur.data(), cur_bytes, cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(d_base, hbase.data(), 64 * sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(d_cursors, 0, 2 * 64 * sizeof(u32), ctx->st));
     kb::ShuffleParams P{};
     P.key = in->cols[kc].ptr;
     P.n = (u32)in->n;
@@ -2455,9 +2605,10 @@ kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, u
     P.n_cols = n_cols;
     for (u32 c = 0; c < n_cols; c++) P.in[c] = in->cols[c].ptr;
     P.peer_cols = reinterpret_cast<u32* const*>(tb);
-    P.base = reinterpret_cast<const u32*>(tb + ptr_bytes);
-    P.cursors = reinterpret_cast<u32*>(tb + ptr_bytes + 64 * sizeof(u32));
-    P.overflow = P.cursors + 64;
+    P.cursor_ptrs = reinterpret_cast<u32* const*>(tb + col_bytes);
+    P.base = d_base;
+    P.overflow = d_flags;
+    P.ticket = d_flags + 1;
     P.capacity = (u32)capacity_rows;
     kb::timer_begin(ctx, kb::F_OTHER);
     kb::launch_shuffle_scatter(P, ctx->n_sms, ctx->st);
@@ -2468,6 +2619,39 @@ kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, u
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     kb::timers_flush(ctx);
     if (ovf) return kb::fail(ctx, KB_E_LIMIT, "a receive buffer is smaller than the rows sent to it (capacity %llu rows)", (unsigned long long)capacity_rows);
+    return KB_OK;
+}
+
+kb_status kb_shuffle_scatter(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols, const uint64_t* base,
+                             uint64_t capacity_rows) {
+    KB_ENTER(ctx);
+    if (!base) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    return shuffle_common(ctx, in, key_slot, n_parts, peer_cols, base, nullptr, capacity_rows);
+}
+
+kb_status kb_shuffle_push(kb_ctx* ctx, const kb_rel* in, uint32_t key_slot, uint32_t n_parts, uint32_t* const* peer_cols, uint32_t* const* peer_cursors,
+                          uint64_t capacity_rows) {
+    KB_ENTER(ctx);
+    if (!peer_cursors) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    return shuffle_common(ctx, in, key_slot, n_parts, peer_cols, nullptr, peer_cursors, capacity_rows);
+}
+
+kb_status kb_rel_wrap_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out) {
+    if (!ctx) return KB_E_INVALID;
+    if (!out || (n_cols && (!slots || !d_cols))) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    if (n_cols > KB_MAX_COLS) return kb::fail(ctx, KB_E_LIMIT, "more than %d columns", KB_MAX_COLS);
+    if (n_rows >= 0xFFFFFFF0ull) return kb::fail(ctx, KB_E_LIMIT, "relation too large");
+    auto r = std::make_unique<kb_rel>();
+    r->n = n_rows;
+    for (u32 c = 0; c < n_cols; c++) {
+        for (u32 d = 0; d < c; d++) if (slots[d] == slots[c]) return kb::fail(ctx, KB_E_INVALID, "duplicate slot %u", slots[c]);
+        if (!d_cols[c] || (reinterpret_cast<uintptr_t>(d_cols[c]) & 15u)) return kb::fail(ctx, KB_E_INVALID, "column %u must be a 16-byte aligned device pointer", c);
+        kb::Col col;  // no owner: the caller keeps the memory alive (and readable to the next 256-byte boundary) while the relation is used
+        col.ptr = d_cols[c];
+        r->slots.push_back(slots[c]);
+        r->cols.push_back(col);
+    }
+    *out = r.release();
     return KB_OK;
 }
 

@@ -73,6 +73,9 @@ struct kb_groups {
     std::vector<std::vector<kb::u32>> keys;
     std::vector<std::vector<double>> vals;
     std::vector<uint64_t> counts;
+    std::vector<kb::u32> kinds;            // kb_agg_kind of every aggregate
+    std::vector<std::vector<double>> raw;  // the accumulators as the device left them (AVG: the SUM, before the division): what a
+                                           // cross-rank merge combines (kb_groups_pack / kb_groups_merge)
 };
 
 namespace kb {
@@ -215,8 +218,22 @@ struct AggSpec {
     u64 n_rows = 0;        // joined rows (when applied)
     std::unique_ptr<kb_groups> groups;
 };
+// What the one-kernel index path resolves a star join into (kb_star_join_prepare keeps it; kb_plan_submit only launches): the kernel
+// parameters minus everything that belongs to one launch (output buffers, control block, epoch).
+struct IndexPlan {
+    bool ok = false;
+    ProbeIParams P{};
+    std::vector<u32> out_slots;  // variable of kernel output column c
+    std::vector<u32> all_slots;  // column order of the relation handed to the caller
+    u32 n_out = 0;
+    u64 probe_rows = 0;          // rows of the probe slice = capacity a result buffer needs
+    bool agg = false;            // GROUP BY folded into the kernel (P.gsel / P.asel / P.akind are set)
+    bool has_agg = false;
+    u32 agg_kind = 0, agg_slot = 0, group_slot = 0;
+};
+// plan_only != nullptr: resolve the one-kernel index path and return without launching (KB_E_UNSUPPORTED when the query does not take it)
 kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 n_pats, const kb_filter_op* filter, u32 n_ops, bool allow_fused_scan,
-                          std::unique_ptr<kb_rel>* out, AggSpec* agg = nullptr);
+                          std::unique_ptr<kb_rel>* out, AggSpec* agg = nullptr, IndexPlan* plan_only = nullptr);
 // GROUP BY hash table on the device (kb_group_aggregate and the fused path): one buffer [val | cnt | keys | state]
 struct GroupTable {
     Buf buf;
@@ -226,6 +243,8 @@ struct GroupTable {
 kb_status group_table_create(kb_ctx* ctx, u64 slots, GroupParams* P, GroupTable* t);  // allocates, points P at it, runs the init kernel
 // downloads the table and appends its groups to g (AVG divided, COUNT filled in)
 kb_status group_table_collect(kb_ctx* ctx, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g);
+// the host half of it: `hb` = a host copy of the table's buffer
+void groups_from_host_table(const char* hb, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g);
 kb_status segment_stats(kb_ctx* ctx, Segment* sg);
 kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r);
 kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);
@@ -233,6 +252,7 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
 kb_status star_join_impl(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u32 n_pats, const kb_filter_op* filter, u32 n_ops,
                          std::unique_ptr<kb_rel>* out);
 void pattern_vars(const kb_pattern& pt, std::vector<u32>* slots, std::vector<u32>* src);
+u32 pow2_at_least(u64 x);
 kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt);
 
 }  // namespace kb

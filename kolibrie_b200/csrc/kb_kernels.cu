@@ -1618,6 +1618,7 @@ __device__ void atomic_max_f64(double* addr, double v) {
 
 __global__ void group_init_kernel(const GroupParams P) {
     const u32 stride = gridDim.x * blockDim.x;
+    if (P.overflow != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *P.overflow = 0u;  // prepared plans: the flag lives behind the table
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_slots; i += stride) {
         P.gstate[i] = 0u;
         P.gcnt[i] = 0ull;
@@ -1670,6 +1671,20 @@ __device__ void group_update_global(const GroupParams& P, const u32* k, unsigned
         else if (P.akind[a] == KB_AGG_MAX) atomic_max_f64(dst, val[a]);
         else if (P.akind[a] != KB_AGG_COUNT) atomicAdd(dst, val[a]);
     }
+}
+
+__global__ void __launch_bounds__(256) group_merge_kernel(const __grid_constant__ GroupParams P, const GroupRecord* __restrict__ recs, u32 n) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const GroupRecord r = recs[i];
+        if (r.count == 0ull) continue;
+        group_update_global(P, r.keys, r.count, r.raw);
+    }
+}
+void launch_group_merge(const GroupParams& p, const GroupRecord* recs, u32 n, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + 255ull) / 256ull);
+    group_merge_kernel<<<grid, 256, 0, st>>>(p, recs, n);
 }
 
 __global__ void __launch_bounds__(256) group_kernel(const __grid_constant__ GroupParams P) {
@@ -2124,33 +2139,110 @@ void launch_part_scatter(const u32* key, u32 n, u32 n_parts, u32* cursors, const
     part_scatter_kernel<<<grid, 256, 0, st>>>(key, n, n_parts, cursors, P);
 }
 
-__global__ void __launch_bounds__(256) shuffle_scatter_kernel(const __grid_constant__ ShuffleParams P) {
-    const int lane = threadIdx.x & 31;
-    const u32 n_round = (P.n + 31u) & ~31u;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        const bool valid = i < P.n;
-        const u32 part = valid ? shard_of(P.key[i], P.n_parts) : 0xFFFFu;
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
-        if (!valid) continue;
-        // the lanes bound for the same rank take one range of its buffer together: consecutive positions, coalesced peer stores
-        const unsigned peers = __match_any_sync(act, part);
-        const int leader = __ffs(peers) - 1;
-        u32 basepos = 0;
-        if (lane == leader) basepos = atomicAdd(&P.cursors[part], (u32)__popc(peers));
-        basepos = __shfl_sync(peers, basepos, leader);
-        const u32 r = P.base[part] + basepos + (u32)__popc(peers & ((1u << lane) - 1u));
-        if (r < P.capacity) {
-            for (u32 c = 0; c < P.n_cols; c++) P.peer_cols[part * P.n_cols + c][r] = P.in[c][i];
-        } else {
-            *P.overflow = 1u;
+// Join-key shuffle FUSED with its transfer. A CTA takes a tile of rows, sorts it by destination rank in shared memory
+// (histogram -> offsets -> staged columns), reserves ONE range per (tile, destination) in the destination's receive buffer — an
+// atomicAdd on the cursor the destination owns (peer memory: no count pass and no count exchange before the transfer), or on a local
+// cursor when the caller fixed the ranges beforehand — and then streams every (destination, column) run out of shared memory with
+// warp stores whose 32-lane windows are aligned to 128-byte lines of the REMOTE address: NVLink carries full lines, not the 4-byte
+// scatter a row-at-a-time kernel produces.
+constexpr int SHUF_THREADS = 256;
+__global__ void __launch_bounds__(SHUF_THREADS) shuffle_scatter_kernel(const __grid_constant__ ShuffleParams P) {
+    extern __shared__ __align__(16) u32 sh_stage[];  // [n_cols][tile] staged columns, then tile bytes of destinations
+    __shared__ u32 s_cnt[64], s_off[64], s_fill[64], s_gbase[64];
+    __shared__ u32 s_tile;
+    const u32 TILE = P.tile;
+    unsigned char* s_dest = reinterpret_cast<unsigned char*>(sh_stage + (size_t)P.n_cols * TILE);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 items = TILE / SHUF_THREADS;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+        if (tid < 64) { s_cnt[tid] = 0u; s_fill[tid] = 0u; }
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= P.n_tiles) break;
+        const u32 row0 = tile * TILE;
+        const u32 cnt = min(TILE, P.n - row0);
+        // ---- 1. destinations + histogram (one shared atomic per warp and destination)
+        for (u32 j = 0; j < items; j++) {
+            const u32 r = j * SHUF_THREADS + (u32)tid;
+            const bool valid = r < cnt;
+            const u32 part = valid ? shard_of(__ldg(P.key + row0 + r), P.n_parts) : 0xFFu;
+            if (valid) s_dest[r] = (unsigned char)part;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                const unsigned peers = __match_any_sync(act, part);
+                if (lane == __ffs(peers) - 1) atomicAdd(&s_cnt[part], (u32)__popc(peers));
+            }
         }
+        __syncthreads();
+        // ---- 2. offsets inside the tile; one range reservation per destination (remote cursor: the receiver's own word)
+        if (warp == 0) {
+            u32 run = 0;
+            for (u32 d0 = 0; d0 < P.n_parts; d0 += 32u) {
+                const u32 d = d0 + (u32)lane;
+                const u32 c = d < P.n_parts ? s_cnt[d] : 0u;
+                u32 incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (d < P.n_parts) {
+                    s_off[d] = run + incl - c;
+                    u32 g = 0u;
+                    if (c) g = P.base[d] + atomicAdd_system(P.cursor_ptrs[d], c);
+                    if (c && (u64)g + c > (u64)P.capacity) { *P.overflow = 1u; g = EMPTY32; }
+                    s_gbase[d] = g;
+                }
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        __syncthreads();
+        // ---- 3. stage the columns sorted by destination
+        for (u32 j = 0; j < items; j++) {
+            const u32 r = j * SHUF_THREADS + (u32)tid;
+            const bool valid = r < cnt;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (!valid) continue;
+            const u32 part = s_dest[r];
+            const unsigned peers = __match_any_sync(act, part);
+            const int leader = __ffs(peers) - 1;
+            u32 b = 0;
+            if (lane == leader) b = atomicAdd(&s_fill[part], (u32)__popc(peers));
+            b = __shfl_sync(peers, b, leader);
+            const u32 pos = s_off[part] + b + (u32)__popc(peers & ((1u << lane) - 1u));
+            for (u32 c = 0; c < P.n_cols; c++) sh_stage[c * TILE + pos] = __ldg(P.in[c] + row0 + r);
+        }
+        __syncthreads();
+        // ---- 4. flush: every (destination, column) run goes out as 128-byte-aligned warp stores
+        const u32 n_runs = P.n_parts * P.n_cols;
+        for (u32 q = (u32)warp; q < n_runs; q += SHUF_THREADS / 32) {
+            const u32 d = q / P.n_cols, c = q - d * P.n_cols;
+            const u32 m = s_cnt[d];
+            const u32 g = s_gbase[d];
+            if (m == 0u || g == EMPTY32) continue;
+            u32* dst = P.peer_cols[q] + g;
+            const u32* src = sh_stage + c * TILE + s_off[d];
+            const u32 mis = (u32)((reinterpret_cast<uintptr_t>(dst) >> 2) & 31u);  // elements past the previous 128-byte boundary
+            for (int e0 = -(int)mis; e0 < (int)m; e0 += 32) {
+                const int e = e0 + lane;
+                if (e >= 0 && e < (int)m) dst[e] = src[e];
+            }
+        }
+        __syncthreads();
     }
-    __threadfence_system();  // the stores must be visible to the peers before the host-side barrier that follows the launch
+    __threadfence_system();  // the stores must be visible to the peers before the barrier that follows the launch
 }
-void launch_shuffle_scatter(const ShuffleParams& p, int n_sms, cudaStream_t st) {
-    if (p.n == 0) return;
-    const int grid = (int)umin64((u64)n_sms * 4ull, ((u64)p.n + 255ull) / 256ull);
-    shuffle_scatter_kernel<<<grid, 256, 0, st>>>(p);
+void launch_shuffle_scatter(const ShuffleParams& p_in, int n_sms, cudaStream_t st) {
+    if (p_in.n == 0) return;
+    ShuffleParams p = p_in;
+    p.tile = p.n_cols <= 4 ? 4096u : (p.n_cols <= 8 ? 2048u : 1024u);
+    p.n_tiles = (p.n + p.tile - 1u) / p.tile;
+    const size_t smem = (size_t)p.n_cols * p.tile * sizeof(u32) + p.tile;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(shuffle_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024); attr = true; }
+    const int grid = grid_for((const void*)shuffle_scatter_kernel, SHUF_THREADS, smem, n_sms, p.n_tiles);
+    shuffle_scatter_kernel<<<grid, SHUF_THREADS, smem, st>>>(p);
 }
 
 // kb_store_delete: p_out[i] = p[i], or EMPTY32 when (s,p,o)[i] is in the delete set; a scan with a variable predicate and

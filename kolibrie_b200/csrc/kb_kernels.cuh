@@ -305,6 +305,16 @@ struct GroupParams {
 };
 void launch_group(const GroupParams& p, int n_sms, cudaStream_t st);
 void launch_group_init(const GroupParams& p, cudaStream_t st);
+// one partial group of a GROUP BY evaluated elsewhere (another rank): its key, its row count and the raw accumulators (AVG: the sum)
+struct GroupRecord {
+    u32 keys[4];
+    unsigned long long count;
+    double raw[8];
+};
+static_assert(sizeof(GroupRecord) == 88, "layout");
+// folds n partial groups into the global table of p: counts add, SUM/AVG accumulators add, MIN/MAX fold (execute_query.rs:1150-1227
+// applied to the union of the partials' rows)
+void launch_group_merge(const GroupParams& p, const GroupRecord* recs, u32 n, int n_sms, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Datalog: instantiate rule heads from binding columns, apply rule filters (rules.rs:133-165), insert into the
@@ -332,17 +342,21 @@ void launch_set64_insert(u64* set, u32 set_slots, const u32* s, const u32* o, u3
 void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p /*null: p_const*/, u32 p_const, const u32* o, u32 n, u32* overflow,
                        int n_sms, cudaStream_t st);
 
-// fused partition + transfer of the multi-GPU join-key shuffle: row i goes to rank d = shard_of(key[i], n_parts), at position
-// base[d] + (rows this launch already sent to d), written with plain stores into d's receive buffer (peer memory over NVLink)
+// fused partition + transfer of the multi-GPU join-key shuffle: a tile of rows is sorted by destination rank d = shard_of(key, n_parts)
+// in shared memory, one range per (tile, destination) is reserved with an atomicAdd on *cursor_ptrs[d] — the destination's own cursor
+// in peer memory (push mode, base = 0) or a local cursor behind a precomputed base[d] — and the runs are streamed into d's receive
+// buffer (peer memory over NVLink) as 128-byte-aligned warp stores
 struct ShuffleParams {
     const u32* key;
     u32 n, n_parts, n_cols;
     const u32* in[KB_MAX_COLS];
-    u32* const* peer_cols;  // device array [n_parts * n_cols]
-    const u32* base;        // device array [n_parts]
-    u32* cursors;           // device array [n_parts], zeroed
+    u32* const* peer_cols;     // device array [n_parts * n_cols]
+    u32* const* cursor_ptrs;   // device array [n_parts]: word the range of destination d is reserved on
+    const u32* base;           // device array [n_parts]
     u32 capacity;
     u32* overflow;
+    u32* ticket;               // zeroed tile counter
+    u32 tile, n_tiles;         // set by the launcher
 };
 void launch_shuffle_scatter(const ShuffleParams& p, int n_sms, cudaStream_t st);
 

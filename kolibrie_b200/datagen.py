@@ -49,6 +49,12 @@ class EmployeeData:
     title_of_employee: np.ndarray = field(repr=False, default=None)
     sal_id_by_value: np.ndarray = field(repr=False, default=None)    # id of the literal str(30000+k), -1 if never drawn
     title_id_by_value: np.ndarray = field(repr=False, default=None)  # id of POSITIONS[k], -1 if never drawn
+    # closed form of the GLOBAL dataset this shard was cut from (employee_subject_ids): subject ids of its first `len(subj_prefix)`
+    # employees; every later employee i has id prefix_ids + (i - len(subj_prefix))
+    subj_prefix: np.ndarray = field(repr=False, default=None)
+    prefix_ids: int = 0
+    n_total: int = 0
+    seed: int = 42
 
     @property
     def n_triples(self) -> int:
@@ -121,7 +127,8 @@ def employee_dataset(n_employees: int, seed: int = 42, first: int = 1, global_id
     num[sal_new_id[first_s]] = uniq_sal.astype(np.float64)
     isn[sal_new_id[first_s]] = 1
     return EmployeeData(s, p, o, n_ids, ids, num, isn, E, salary_of_employee=salary, title_of_employee=title_idx,
-                        sal_id_by_value=sal_id_by_value, title_id_by_value=title_id_by_value)
+                        sal_id_by_value=sal_id_by_value, title_id_by_value=title_id_by_value,
+                        subj_prefix=subj.astype(np.uint32), prefix_ids=n_ids, n_total=E, seed=seed)
 
 
 SHARD_BLOCK_BITS = 10  # == KB_SHARD_BLOCK_BITS
@@ -182,7 +189,44 @@ def employee_shard(n_total: int, rank: int, world: int, seed: int = 42, prefix: 
         n_emp += m
     n_ids = head.n_ids + (n_total - P)
     return EmployeeData(np.concatenate(S), np.concatenate(Pp), np.concatenate(Oo), n_ids, head.ids, head.num_or0, head.is_num, n_emp,
-                        sal_id_by_value=head.sal_id_by_value, title_id_by_value=head.title_id_by_value)
+                        sal_id_by_value=head.sal_id_by_value, title_id_by_value=head.title_id_by_value,
+                        subj_prefix=subj_head.astype(np.uint32), prefix_ids=head.n_ids, n_total=n_total, seed=seed)
+
+
+def employee_subject_ids(d: EmployeeData, index: np.ndarray) -> np.ndarray:
+    """dictionary id of the subject of global employee number `index` (0-based) of the dataset `d` was cut from"""
+    index = np.asarray(index, dtype=np.int64)
+    P = len(d.subj_prefix)
+    out = (np.int64(d.prefix_ids) + (index - P)).astype(np.uint32)
+    head = index < P
+    out[head] = d.subj_prefix[index[head]]
+    return out
+
+
+def employee_title_ids(d: EmployeeData, index: np.ndarray) -> np.ndarray:
+    """dictionary id of the foaf:title object of global employee number `index` (closed form: first draw of the employee's pair)"""
+    r = splitmix64_at(d.seed, 2 * np.asarray(index, dtype=np.uint64))
+    return d.title_id_by_value[(r % np.uint64(3)).astype(np.int64)].astype(np.uint32)
+
+
+def employee_indices_of_shard(d: EmployeeData, rank: int, world: int) -> np.ndarray:
+    """global employee numbers whose subject belongs to shard `rank` (the employees of employee_shard(n_total, rank, world)), in order"""
+    if world == 1:
+        return np.arange(d.n_total, dtype=np.int64)
+    P = len(d.subj_prefix)
+    head = np.nonzero(shard_of_np(d.subj_prefix, world) == rank)[0].astype(np.int64)
+    tail_i = np.arange(P, d.n_total, dtype=np.int64)
+    tail_ids = (np.int64(d.prefix_ids) + (tail_i - P)).astype(np.uint32)
+    return np.concatenate([head, tail_i[shard_of_np(tail_ids, world) == rank]])
+
+
+def reports_to_relation(d: EmployeeData, rank: int, world: int, seed: int = 77):
+    """A path-join companion of the employee shape (bench.py's shuffle leg): (?e ds:reports_to ?m) for the employees of this shard,
+    ?m = a pseudo-random employee of the GLOBAL dataset — the rows live with ?e but join with (?m foaf:title ?t), which lives on the
+    owner of ?m: a non-subject-key join. Returns (e ids, m ids, closed-form title id of m)."""
+    idx = employee_indices_of_shard(d, rank, world)
+    m_idx = (splitmix64_at(seed, idx.astype(np.uint64)) % np.uint64(d.n_total)).astype(np.int64)
+    return employee_subject_ids(d, idx), employee_subject_ids(d, m_idx), employee_title_ids(d, m_idx)
 
 
 def employee_queries(d: EmployeeData):

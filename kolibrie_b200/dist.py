@@ -86,39 +86,133 @@ def shuffle_plan(counts_matrix: np.ndarray, rank: int):
 
 
 class PeerShuffle:
-    """Receive buffers in peer-mapped memory, allocated and rendezvoused once, reused for every shuffle of up to `capacity_rows`
-    rows x `n_cols` columns per rank."""
+    """Receive buffers + receive cursor in peer-mapped memory, allocated and rendezvoused once, reused for every shuffle of up to
+    `capacity_rows` rows x `n_cols` columns per rank. One exchange = ONE kernel per rank between two barriers: the kernel reserves
+    its ranges on the receivers' cursors itself (kb_shuffle_push), so no row counts are computed or exchanged beforehand."""
 
     def __init__(self, ctx, n_cols: int, capacity_rows: int, group=None):
         import torch.distributed._symmetric_memory as symm_mem
 
-        self.ctx, self.n_cols, self.cap = ctx, n_cols, int(capacity_rows)
+        self.ctx, self.n_cols = ctx, n_cols
+        self.cap = (int(capacity_rows) + 63) // 64 * 64  # columns start 256-byte aligned
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.dev = torch.device("cuda", ctx.device)
-        self.buf = symm_mem.empty(n_cols * self.cap, dtype=torch.int32, device=self.dev)
+        # [n_cols columns of cap rows][64 words: word 0 = receive cursor][64 words of slack for the 256-byte over-read of the last column]
+        self.buf = symm_mem.empty(n_cols * self.cap + 128, dtype=torch.int32, device=self.dev)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        self.cursor = self.buf[n_cols * self.cap: n_cols * self.cap + 64]
+        self.peer_cols = [self.col_ptr(d, c_) for d in range(self.world) for c_ in range(self.n_cols)]
+        self.peer_cursors = [self.ptrs[d] + 4 * self.n_cols * self.cap for d in range(self.world)]
+        self.last_bytes_sent = 0
 
     def col_ptr(self, peer: int, col: int) -> int:
         return self.ptrs[peer] + 4 * col * self.cap
 
-    def shuffle(self, rel, key_slot: int):
-        """re-shard `rel` so that every row lives on rank kb_shard_of(row[key_slot], world); returns a new Relation"""
+    def _barrier(self):
+        self.hdl.barrier()                      # device-side barrier on torch's current stream ...
+        torch.cuda.current_stream(self.dev).synchronize()  # ... the library launches on its own stream: order through the host
+
+    def shuffle(self, rel, key_slot: int, copy: bool = False):
+        """re-shard `rel` so that every row lives on rank kb_shard_of(row[key_slot], world). Returns a Relation over the receive buffer
+        (a VIEW, overwritten by the next shuffle; copy=True for an owned relation)."""
         n, slots = rel.info()
         assert len(slots) == self.n_cols
+        self.cursor.zero_()
+        self._barrier()  # every cursor is zero and every rank is done reading what the previous shuffle left in its buffer
+        self.ctx.shuffle_push(rel, key_slot, self.world, self.peer_cols, self.peer_cursors, self.cap)  # returns after its stores are fenced
+        self._barrier()  # every rank's stores have landed
+        recv_total = int(self.cursor[0].item())
+        ptrs = [self.col_ptr(self.rank, c_) for c_ in range(self.n_cols)]
+        if copy:
+            return self.ctx.rel_from_device(slots, ptrs, recv_total)
+        return self.ctx.rel_wrap_device(slots, ptrs, recv_total)
+
+    def shuffle_planned(self, rel, key_slot: int):
+        """the two-pass variant (kb_partition_counts -> all_gather of the count matrix -> kb_shuffle_scatter with fixed ranges):
+        deterministic placement, rows in source-rank order; kept for A/B and as the reference for the push variant's tests"""
+        n, slots = rel.info()
         mine = torch.tensor(self.ctx.partition_counts(rel, key_slot, self.world), dtype=torch.int64, device=self.dev)
         allc = [torch.empty_like(mine) for _ in range(self.world)]
         dist.all_gather(allc, mine, group=self.group)
         base, recv_total = shuffle_plan(torch.stack(allc).cpu().numpy(), self.rank)
         if recv_total > self.cap:
             raise ValueError(f"rank {self.rank} would receive {recv_total} rows, capacity {self.cap}")
-        self.hdl.barrier()  # every rank is done reading what the previous shuffle left in its buffer
-        peer_cols = [self.col_ptr(d, c_) for d in range(self.world) for c_ in range(self.n_cols)]
-        self.ctx.shuffle_scatter(rel, key_slot, self.world, peer_cols, base, self.cap)  # returns after its stores are fenced
-        self.hdl.barrier()  # every rank's stores have landed
-        torch.cuda.synchronize(self.dev)
+        self._barrier()
+        self.ctx.shuffle_scatter(rel, key_slot, self.world, self.peer_cols, base, self.cap)
+        self._barrier()
         return self.ctx.rel_from_device(slots, [self.col_ptr(self.rank, c_) for c_ in range(self.n_cols)], recv_total)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GROUP BY across ranks: every rank aggregates its shard; the packed partials (kb_groups_pack) are all-gathered and folded by
+# kb_groups_merge. One collective: the buffers travel in fixed-size slots whose first 8 bytes carry the payload length.
+GROUPS_SLOT_BYTES = 56 + 88 * 4096 + 8  # header + 4096 groups (the capacity of a prepared GROUP BY) + the length prefix
+
+
+def allgather_bytes(buf: np.ndarray, device=None, group=None, slot_bytes: int = GROUPS_SLOT_BYTES) -> List[np.ndarray]:
+    """all-gather of one variable-length byte string per rank (NCCL on `device`, gloo on the CPU). Payloads longer than the slot
+    take a second collective sized by the longest one."""
+    world = dist.get_world_size(group)
+    dev = device or torch.device("cpu")
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+
+    def gather(slot):
+        mine = np.zeros(slot, dtype=np.uint8)
+        mine[:8] = np.frombuffer(np.int64(buf.nbytes).tobytes(), dtype=np.uint8)
+        m = min(buf.nbytes, slot - 8)
+        mine[8:8 + m] = buf[:m]
+        t = torch.from_numpy(mine).to(dev)
+        out = torch.empty(world * slot, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(out, t, group=group)
+        return out.cpu().numpy().reshape(world, slot)
+
+    got = gather(slot_bytes)
+    sizes = [int(np.frombuffer(got[r, :8].tobytes(), dtype=np.int64)[0]) for r in range(world)]
+    if max(sizes) + 8 > slot_bytes:
+        got = gather((max(sizes) + 8 + 255) // 256 * 256)
+    return [got[r, 8:8 + sizes[r]].copy() for r in range(world)]
+
+
+GROUPS_MAGIC = 0x4B4247524F555031  # "KBGROUP1": layout of kb_groups_pack (include/kolibrie_b200.h)
+_REC = np.dtype([("keys", "<u4", 4), ("count", "<u8"), ("raw", "<f8", 8)])
+assert _REC.itemsize == 88
+
+
+def pack_groups_np(keys: Sequence[np.ndarray], counts: np.ndarray, raw: Sequence[np.ndarray], kinds: Sequence[int]) -> np.ndarray:
+    """the kb_groups_pack byte layout built on the host (gloo tests, tooling): header {magic u64, n_groups u64, n_group_cols u32,
+    n_aggs u32, kinds u32[8]} then one 88-byte record {keys u32[4], count u64, raw f64[8]} per group; raw = the accumulator (AVG: the sum)"""
+    n = len(counts)
+    head = np.zeros(56, dtype=np.uint8)
+    head[:16] = np.frombuffer(np.array([GROUPS_MAGIC, n], dtype="<u8").tobytes(), dtype=np.uint8)
+    kk = np.zeros(8, dtype="<u4")
+    kk[: len(kinds)] = kinds
+    head[16:24] = np.frombuffer(np.array([len(keys), len(raw)], dtype="<u4").tobytes(), dtype=np.uint8)
+    head[24:56] = np.frombuffer(kk.tobytes(), dtype=np.uint8)
+    rec = np.zeros(n, dtype=_REC)
+    for c, k in enumerate(keys):
+        rec["keys"][:, c] = k
+    rec["count"] = counts
+    for a, v in enumerate(raw):
+        rec["raw"][:, a] = v
+    return np.concatenate([head, np.frombuffer(rec.tobytes(), dtype=np.uint8)])
+
+
+def unpack_groups_np(buf: np.ndarray):
+    """inverse of pack_groups_np / kb_groups_pack: (keys [n, n_group_cols], counts [n], raw [n, n_aggs], kinds)"""
+    buf = np.ascontiguousarray(buf, dtype=np.uint8)
+    magic, n = np.frombuffer(buf[:16].tobytes(), dtype="<u8")
+    assert int(magic) == GROUPS_MAGIC, "not a kb_groups_pack buffer"
+    ng, na = (int(x) for x in np.frombuffer(buf[16:24].tobytes(), dtype="<u4"))
+    kinds = [int(x) for x in np.frombuffer(buf[24:56].tobytes(), dtype="<u4")[:na]]
+    rec = np.frombuffer(buf[56:56 + int(n) * 88].tobytes(), dtype=_REC)
+    return rec["keys"][:, :ng].copy(), rec["count"].copy(), rec["raw"][:, :na].copy(), kinds
+
+
+def allgather_groups(packed: np.ndarray, device=None, group=None) -> List[np.ndarray]:
+    """the packed partial GROUP BY results of all ranks, in rank order (input of Context.groups_merge)"""
+    return allgather_bytes(packed, device, group)
 
 
 def sum_over_ranks(value: int, device=None, group=None) -> int:

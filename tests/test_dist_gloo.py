@@ -67,6 +67,29 @@ def _worker(rank, world, port, q):
             raise AssertionError("plan check should have refused")
         except ValueError:
             pass
+        # 5. GROUP BY across ranks: per-shard partials in the kb_groups_pack layout, gathered in ONE collective (fixed slots with a
+        #    length prefix; an oversized payload takes the second, sized collective), folded = the GROUP BY of the whole store
+        gdb = O.Db(full.s, full.p, full.o, full.num_or0, full.is_num)
+        js3, pats3, _ = datagen.employee_queries(full)["cfg3"]
+        ldb = O.Db(d.s, d.p, d.o, full.num_or0, full.is_num)
+        for gslot, slot_bytes in ((1, kd.GROUPS_SLOT_BYTES), (2, 4096)):  # by title: 3 groups; by salary: thousands (overflows a 4 KB slot)
+            part = ldb.group(ldb.bgp(pats3), [gslot], [(c.AGG_AVG, 2)])
+            sums = part["values"][0] * part["counts"]  # the device ships the SUM; the oracle hands back the average
+            packed = kd.pack_groups_np(part["keys"], part["counts"], [sums], [c.AGG_AVG])
+            parts = kd.allgather_bytes(packed, slot_bytes=slot_bytes)
+            assert len(parts) == world and np.array_equal(parts[rank], packed)
+            acc = {}
+            for pb in parts:
+                kk, cc, rr, kinds = kd.unpack_groups_np(pb)
+                assert kinds == [c.AGG_AVG]
+                for k, n_, v in zip(kk[:, 0], cc, rr[:, 0]):
+                    a = acc.setdefault(int(k), [0, 0.0])
+                    a[0] += int(n_)
+                    a[1] += float(v)
+            want = gdb.group(gdb.bgp(pats3), [gslot], [(c.AGG_AVG, 2)])
+            assert sorted(acc) == sorted(int(k) for k in want["keys"][0])
+            for k, n_, v in zip(want["keys"][0], want["counts"], want["values"][0]):
+                assert acc[int(k)][0] == int(n_) and abs(acc[int(k)][1] / acc[int(k)][0] - v) <= 1e-9 * abs(v)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
