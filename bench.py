@@ -363,8 +363,9 @@ def main():
         t0 = time.perf_counter()
         rows = fn(k)
         ctx.synchronize()
+        t1 = time.perf_counter()  # this rank's K steps are complete on its device; the MAX over ranks of these spans is reported
         barrier()
-        return rows, time.perf_counter() - t0, ctx.get_stats(reset=True)
+        return rows, t1 - t0, ctx.get_stats(reset=True)
 
     sync_loop = lambda k: [step_sync() for _ in range(k)][-1]
     head_fn = (lambda k: run_pipelined(plan, k)) if plan else sync_loop
@@ -413,8 +414,8 @@ def main():
         for _ in range(K):
             rows_e, slots_e = step_e2e()
         ctx.synchronize()
-        barrier()
         dt_e = time.perf_counter() - t1
+        barrier()
         assert rows_e == rows_step, (rows_e, rows_step)
         e2e = {"dt": dt_e, "h2d": 3 * 4 * n, "d2h": len(slots_e) * 4 * rows_e}
         ctx.get_stats(reset=True)
@@ -528,7 +529,7 @@ def main():
                               "(first build in a fresh process, which also grows the CUDA memory pool from empty: %.1f ms), outside the timed region"
                               % (n_pred, index_ms, index_ms_first)) if not args.no_index else "unindexed: every step scans the store",
                     "datagen_s": round(t_gen, 1), "host_numa_node": numa_node,
-                    "timing": "wall clock around K steps between barrier+synchronize, max over ranks",
+                    "timing": "per rank: wall clock from the opening barrier+synchronize to the synchronize that ends its K steps (a closing barrier follows); MAX over ranks",
                     "host_overhead_us_per_step": (ms_step - dev_ms_step_max) * 1e3, "device_ms_per_step_max_over_ranks": dev_ms_step_max},
         "roofline": roofline,
         "gpu_launches": int(st["kernel_launches"]),
@@ -570,6 +571,55 @@ def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max
     # ---- cfg3: 4-pattern star + GROUP BY ?t COUNT, local fused join+group per rank, partial groups all-gathered (NCCL) and folded by
     # kb_groups_merge on every rank. Pipelined: query i+1 is on the device while the partials of query i are exchanged and merged.
     js3, pats3, _ = datagen.employee_queries(d)["cfg3"]
+    idx = datagen.employee_indices_of_shard(d, rank, world)
+    titles = datagen.employee_title_ids(d, idx)
+    tids = [int(x) for x in d.title_id_by_value]
+    want = reduce_sum(*[int((titles == t).sum()) for t in tids])  # closed form: the global title histogram
+
+    def check_groups(groups):
+        got = {int(k): int(n_) for k, n_ in zip(groups["keys"][0], groups["counts"])}
+        assert got == {t: w for t, w in zip(tids, want) if w}, (got, want)
+        return len(got)
+
+    # (a) the merge INSIDE the plan: partial tables in peer-mapped memory, device-side barrier, one merge kernel reading the peers'
+    #     tables over NVLink — a submit is asynchronous end to end, K queries run back to back
+    plan_p = kd.attach_group_plan(ctx.prepare_star_join(js3, pats3, None, group_slots=[1], aggs=[(c.AGG_COUNT, 0)], ring=max(args.ring, 2)))
+
+    def cfg3_peer_steps(k):
+        depth, inflight, out_ = max(1, plan_p.ring - 1), [], (None, 0)
+        for _ in range(k):
+            inflight.append(plan_p.submit())
+            if len(inflight) > depth:
+                out_ = plan_p.collect_groups(inflight.pop(0))
+        while inflight:
+            out_ = plan_p.collect_groups(inflight.pop(0))
+        return out_
+
+    cfg3_peer_steps(5)
+    ctx.get_stats(reset=True)
+    ctx.set_timing(True)
+    barrier()
+    t0 = time.perf_counter()
+    g_p, rows_p = cfg3_peer_steps(K)
+    ctx.synchronize()
+    dt_p = time.perf_counter() - t0
+    barrier()
+    st_p = ctx.get_stats(reset=True)
+    ctx.set_timing(False)
+    plan_p.free()
+    n_groups = check_groups(g_p)
+    rows_p_all, = reduce_sum(rows_p)
+    assert rows_p_all == E_glob == sum(want)
+    dt_pm, dev_p, dev_pg = reduce_max(dt_p, st_p["probe_ms"] / K, st_p["group_ms"] / K)
+    table_bytes = 4096 * 92 + 16
+    out["cfg3_group_by_merge"] = {
+        "workload": f"BASELINE configs[2]: {6 * args.employees} triples per GPU x {world} GPUs, 4-pattern star + GROUP BY ?t COUNT, global groups on every rank",
+        "value": rows_p_all / (dt_pm / K), "unit": "bindings/s", "ms_per_step": dt_pm / K * 1e3, "device_ms_per_step_join_group": dev_p,
+        "device_ms_per_step_barrier_init_merge": dev_pg, "groups": n_groups,
+        "exchange": "fused: per-rank join+group kernel -> device-side barrier over peer-memory flags -> one merge kernel per rank reading the %d partial tables over NVLink "
+                    "(P2P loads, %d bytes each); no NCCL call and no host round trip per query" % (world, table_bytes),
+        "nvlink_bytes_read_per_rank_per_step": (world - 1) * table_bytes, "parity": "groups == closed-form global title histogram on every rank"}
+    # (b) the portable variant: partial groups all-gathered over NCCL, folded by kb_groups_merge
     plan3 = ctx.prepare_star_join(js3, pats3, None, group_slots=[1], aggs=[(c.AGG_COUNT, 0)], ring=args.ring)
 
     def cfg3_steps(k):
@@ -591,25 +641,18 @@ def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max
     t0 = time.perf_counter()
     rows3, merged = cfg3_steps(K)
     ctx.synchronize()
-    barrier()
     dt3 = time.perf_counter() - t0
+    barrier()
     st3 = ctx.get_stats(reset=True)
     ctx.set_timing(False)
     plan3.free()
-    # parity: every employee has all four patterns -> one row each; groups = global title histogram (closed form per shard, summed)
-    idx = datagen.employee_indices_of_shard(d, rank, world)
-    titles = datagen.employee_title_ids(d, idx)
-    tids = [int(x) for x in d.title_id_by_value]
-    want = reduce_sum(*[int((titles == t).sum()) for t in tids])
-    got = {int(k): int(n_) for k, n_ in zip(merged["keys"][0], merged["counts"])}
-    assert got == {t: w for t, w in zip(tids, want) if w}, (got, want)
+    check_groups(merged)
     rows3_all, = reduce_sum(rows3)
-    assert rows3_all == E_glob == sum(want)
+    assert rows3_all == E_glob
     dt3m, dev3 = reduce_max(dt3, st3["probe_ms"] / K)
-    out["cfg3_group_by_merge"] = {
-        "workload": f"BASELINE configs[2]: {6 * args.employees} triples per GPU x {world} GPUs, 4-pattern star + GROUP BY ?t COUNT; per-rank fused join+group kernel, "
-                    "partial groups all-gathered over NCCL, folded on every rank by kb_groups_merge",
-        "value": rows3_all / (dt3m / K), "unit": "bindings/s", "ms_per_step": dt3m / K * 1e3, "device_ms_per_step_join_group": dev3, "groups": len(got),
+    out["cfg3_group_by_merge_nccl"] = {
+        "workload": "same query; partial groups packed (kb_groups_pack), all-gathered over NCCL, folded on every rank by kb_groups_merge",
+        "value": rows3_all / (dt3m / K), "unit": "bindings/s", "ms_per_step": dt3m / K * 1e3, "device_ms_per_step_join_group": dev3,
         "collective": "all_gather_into_tensor of one %d-byte slot per rank and step" % kd.GROUPS_SLOT_BYTES, "parity": "groups == closed-form global title histogram"}
 
     # ---- shuffle_join: (?e reports_to ?m) . (?m foaf:title ?t) — the first pattern's rows live with ?e, the join key ?m is not their
@@ -618,7 +661,7 @@ def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max
     e_ids, m_ids, t_of_m = datagen.reports_to_relation(d, rank, world)
     left = ctx.rel_from_host([E_, M_], [e_ids, m_ids])
     right = ctx.scan([c.pattern(c.V(M_), c.K(d.ids["foaf:title"]), c.V(T_))])[0]
-    cap = int(len(e_ids) * 1.25) + 65536
+    cap = int(reduce_max(len(e_ids))[0] * 1.25) + 65536  # symmetric memory: the same size on every rank
     ps = kd.PeerShuffle(ctx, n_cols=2, capacity_rows=cap)
     sh_times, join_times, rows_j = [], [], 0
     for rep in range(1 + max(3, min(K, 6))):
@@ -675,8 +718,8 @@ def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max
     t0 = time.perf_counter()
     rows_s = run_pipelined(plans, K)
     ctx2.synchronize()
-    barrier()
     dt_s = time.perf_counter() - t0
+    barrier()
     sts = ctx2.get_stats(reset=True)
     plans.free()
     ctx2.close()

@@ -268,6 +268,14 @@ KB_API kb_status kb_plan_collect(kb_ctx* ctx, kb_plan* plan, uint64_t ticket, ui
 KB_API kb_status kb_plan_info(const kb_plan* plan, uint32_t* ring, uint64_t* capacity_rows, uint32_t* n_cols, uint32_t* slots /* [KB_MAX_COLS] or NULL */,
                               uint32_t* grouped);
 KB_API void kb_plan_free(kb_ctx* ctx, kb_plan* plan);
+/* Cross-rank GROUP BY inside the plan (one process per GPU, store sharded by subject): every rank allocates
+ * kb_plan_peer_scratch_bytes(plan) bytes of ZEROED peer-mapped memory (torch symmetric memory, cudaIpc, VMM), exchanges the addresses and
+ * attaches them before the first submit (ring >= 2, same plan on every rank). A submit then runs, on the library's stream and without
+ * any host round trip: the fused join+group kernel (partial table into the own scratch) -> a device-side barrier over peer-memory
+ * flags -> ONE merge kernel that reads all ranks' partial tables over NVLink and folds them; kb_plan_collect returns the GLOBAL groups
+ * on every rank (*n_rows stays the rank's own joined rows). All ranks must submit the same number of queries. */
+KB_API uint64_t kb_plan_peer_scratch_bytes(const kb_plan* plan);
+KB_API kb_status kb_plan_attach_peers(kb_ctx* ctx, kb_plan* plan, uint32_t rank, uint32_t world, void* const* peer_scratch /* [world] */);
 
 /* ------------------------------------------------------------------ Datalog (Reasoner::infer_with_strategy, infer_generic.rs:27-53)
  * Facts = the ctx store. Inferred facts are appended to the store (segment tag KB_TAG_INFERRED), exactly as the

@@ -187,6 +187,8 @@ def lib() -> C.CDLL:
         "kb_plan_collect": (i32, [vp, vp, u64, P(u64), P(vp), P(vp)]),
         "kb_plan_info": (i32, [vp, P(u32), P(u64), P(u32), P(u32), P(u32)]),
         "kb_plan_free": (None, [vp, vp]),
+        "kb_plan_peer_scratch_bytes": (u64, [vp]),
+        "kb_plan_attach_peers": (i32, [vp, vp, u32, u32, P(vp)]),
         "kb_star_join_aggregate": (i32, [vp, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), u32, P(KbAgg), u32, P(vp), P(u64)]),
         "kb_datalog_fixpoint": (i32, [vp, P(KbRule), u32, u32, P(vp), P(KbFixpointStats)]),
         "kb_shard_of": (u32, [u32, u32]),
@@ -214,7 +216,7 @@ EXPORTED_SYMBOLS = [
     "kb_store_download", "kb_dict_numeric_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_groups_pack", "kb_groups_merge", "kb_star_join_aggregate",
-    "kb_star_join_prepare", "kb_plan_submit", "kb_plan_collect", "kb_plan_info", "kb_plan_free",
+    "kb_star_join_prepare", "kb_plan_submit", "kb_plan_collect", "kb_plan_info", "kb_plan_free", "kb_plan_peer_scratch_bytes", "kb_plan_attach_peers",
     "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_shuffle_push", "kb_rel_wrap_device", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
 ]
 
@@ -666,6 +668,16 @@ class Plan:
             finally:
                 lib().kb_groups_free(g)
         return self.ctx._groups_to_dict(g), self._rows.value
+
+    def peer_scratch_bytes(self) -> int:
+        return int(lib().kb_plan_peer_scratch_bytes(self.h))
+
+    def attach_peers(self, rank: int, world: int, peer_scratch: Sequence[int], keep=None):
+        """kb_plan_attach_peers: peer_scratch[r] = device-visible address of rank r's zeroed scratch (peer_scratch_bytes() each);
+        `keep` = whatever owns that memory (kept alive with the plan)"""
+        ptrs = (C.c_void_p * world)(*peer_scratch)
+        self.ctx._check(lib().kb_plan_attach_peers(self.ctx.h, self.h, rank, world, ptrs))
+        self._keep = keep
 
     def free(self):
         if self.h:

@@ -1687,6 +1687,62 @@ void launch_group_merge(const GroupParams& p, const GroupRecord* recs, u32 n, in
     group_merge_kernel<<<grid, 256, 0, st>>>(p, recs, n);
 }
 
+// ---- cross-rank GROUP BY over peer memory
+__device__ __forceinline__ void st_release_sys(u32* p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {
+    u32 v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+template <class T>
+__device__ __forceinline__ T ld_sys(const T* p) { return *reinterpret_cast<const volatile T*>(p); }
+
+__global__ void __launch_bounds__(64) peer_barrier_kernel(const __grid_constant__ PeerTables T, u32 epoch) {
+    const u32 r = threadIdx.x;
+    __threadfence_system();
+    if (r < T.world) {
+        st_release_sys(T.flags[r] + T.rank, epoch);                                  // "I have arrived" in r's array
+        const u32* mine = T.flags[T.rank] + r;
+        unsigned long long t0, now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while ((int)(ld_acquire_sys(mine) - epoch) < 0) {                            // r has arrived (epochs only grow; wrap-safe compare)
+            __nanosleep(100);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (now - t0 > 5000000000ull) {  // 5 s: a rank never submitted this query — give up loudly instead of hanging the GPU
+                atomicExch(T.flags[T.rank] + 63, 1u);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+void launch_peer_barrier(const PeerTables& t, u32 epoch, cudaStream_t st) { peer_barrier_kernel<<<1, 64, 0, st>>>(t, epoch); }
+
+__global__ void __launch_bounds__(256) group_merge_peers_kernel(const __grid_constant__ GroupParams P, const __grid_constant__ PeerTables T) {
+    const u32 total = T.world * T.n_slots;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const u32 r = i / T.n_slots, s = i - r * T.n_slots;
+        const char* tb = T.table[r];
+        if (s == 0u && ld_sys(reinterpret_cast<const u32*>(tb + T.o_overflow)) != 0u) *P.overflow = 1u;  // a partial overflowed: so does the merge
+        if (i == 0u && ld_sys(T.flags[T.rank] + 63) != 0u) *P.overflow = 2u;                               // the barrier before this kernel timed out
+        if (ld_sys(reinterpret_cast<const u32*>(tb + T.o_state) + s) != 2u) continue;
+        u32 k[4];
+        double v[8];
+#pragma unroll
+        for (int c = 0; c < 4; c++) k[c] = ld_sys(reinterpret_cast<const u32*>(tb + T.o_keys) + (u64)s * 4 + c);
+        const unsigned long long cnt = ld_sys(reinterpret_cast<const unsigned long long*>(tb + T.o_cnt) + s);
+#pragma unroll
+        for (int a = 0; a < 8; a++) v[a] = (u32)a < P.n_aggs ? ld_sys(reinterpret_cast<const double*>(tb + T.o_val) + (u64)s * 8 + a) : 0.0;
+        group_update_global(P, k, cnt, v);
+    }
+}
+void launch_group_merge_peers(const GroupParams& p, const PeerTables& t, int n_sms, cudaStream_t st) {
+    const u64 total = (u64)t.world * t.n_slots;
+    const int grid = (int)umin64((u64)n_sms * 2ull, (total + 255ull) / 256ull);
+    group_merge_peers_kernel<<<grid, 256, 0, st>>>(p, t);
+}
+
 __global__ void __launch_bounds__(256) group_kernel(const __grid_constant__ GroupParams P) {
     __shared__ u32 sk[GROUP_SMEM][4];
     __shared__ u32 sstate[GROUP_SMEM];  // 0 free, 1 being written, 2 ready

@@ -315,6 +315,20 @@ static_assert(sizeof(GroupRecord) == 88, "layout");
 // folds n partial groups into the global table of p: counts add, SUM/AVG accumulators add, MIN/MAX fold (execute_query.rs:1150-1227
 // applied to the union of the partials' rows)
 void launch_group_merge(const GroupParams& p, const GroupRecord* recs, u32 n, int n_sms, cudaStream_t st);
+// Cross-rank GROUP BY without a host round trip (one process per GPU, partial tables in peer-mapped memory):
+//   launch_peer_barrier: rank `rank` stores `epoch` into slot [rank] of every peer's flag array (system-scope release) and waits until
+//                        every slot of its OWN flag array has reached `epoch` (acquire): all ranks' earlier kernels are then visible
+//   launch_group_merge_peers: folds the `world` partial group tables (layout of GroupTable: val | cnt | keys | state, then the overflow
+//                        word) — read straight from the peers' memory over NVLink — into the local table of p
+struct PeerTables {
+    const char* table[64];   // device-visible address of rank r's partial table
+    u32* flags[64];          // device-visible address of rank r's flag array [64]
+    u32 world, rank;
+    u32 n_slots;             // slots per partial table
+    u32 o_val, o_cnt, o_keys, o_state, o_overflow;  // byte offsets inside a partial table
+};
+void launch_peer_barrier(const PeerTables& t, u32 epoch, cudaStream_t st);
+void launch_group_merge_peers(const GroupParams& p, const PeerTables& t, int n_sms, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------------------------------
 // Datalog: instantiate rule heads from binding columns, apply rule filters (rules.rs:133-165), insert into the

@@ -32,6 +32,17 @@ struct kb_plan {
     u32* d_totals = nullptr;
     u64 next_ticket = 1;
     kb_agg agg1{};
+    // kb_plan_attach_peers: the partial group tables live in peer-mapped scratch [flags: 64 words][ring x table_stride]; after a
+    // device-side barrier a merge kernel reads every rank's partial table over NVLink into the slot's local merged table
+    bool attached = false;
+    u32 world = 1, rank = 0;
+    size_t table_stride = 0;
+    std::vector<char*> peer_scratch;
+    struct Merged {
+        GroupTable tab;
+        char* h_tab = nullptr;
+    };
+    std::vector<Merged> merged;
 };
 
 namespace {
@@ -53,6 +64,7 @@ void plan_release(kb_plan* pl) {
         if (s.h_tab) cudaFreeHost(s.h_tab);
     }
     if (pl->h_totals) cudaFreeHost(pl->h_totals);
+    for (auto& m : pl->merged) if (m.h_tab) cudaFreeHost(m.h_tab);
     delete pl;
 }
 }  // namespace
@@ -143,7 +155,8 @@ kb_status kb_plan_submit(kb_ctx* ctx, kb_plan* pl, uint64_t* ticket) {
         G.n_aggs = pl->ip.has_agg ? 1u : 0u;
         G.akind[0] = pl->ip.agg_kind;
         G.nt = numtab(ctx);
-        char* tb = static_cast<char*>(s.tab.buf->p);
+        const u32 si = (u32)(t % pl->ring);
+        char* tb = pl->attached ? pl->peer_scratch[pl->rank] + 256 + (size_t)si * pl->table_stride : static_cast<char*>(s.tab.buf->p);
         G.n_slots = (u32)s.tab.slots;
         G.gval = (double*)(tb + s.tab.o_val);
         G.gcnt = (unsigned long long*)(tb + s.tab.o_cnt);
@@ -158,8 +171,39 @@ kb_status kb_plan_submit(kb_ctx* ctx, kb_plan* pl, uint64_t* ticket) {
         launch_probe_index(P, &G, ctx->n_sms, ctx->st);
         timer_end(ctx);
         KB_CUDA(ctx, cudaGetLastError());
-        KB_CUDA(ctx, cudaMemcpyAsync(s.h_tab, tb, s.tab.bytes + 16, cudaMemcpyDeviceToHost, ctx->st));
-        ctx->stats.d2h_bytes += s.tab.bytes + 16;
+        if (pl->attached) {
+            // device-side barrier (every rank's partial table of this ticket is complete and visible), then ONE kernel folds all the
+            // partial tables, read from the peers' memory, into this slot's merged table
+            PeerTables T{};
+            T.world = pl->world; T.rank = pl->rank;
+            T.n_slots = (u32)s.tab.slots;
+            T.o_val = (u32)s.tab.o_val; T.o_cnt = (u32)s.tab.o_cnt; T.o_keys = (u32)s.tab.o_keys; T.o_state = (u32)s.tab.o_state;
+            T.o_overflow = (u32)s.tab.bytes;
+            for (u32 r = 0; r < pl->world; r++) {
+                T.flags[r] = reinterpret_cast<u32*>(pl->peer_scratch[r]);
+                T.table[r] = pl->peer_scratch[r] + 256 + (size_t)si * pl->table_stride;
+            }
+            kb_plan::Merged& M = pl->merged[si];
+            GroupParams Gm = G;
+            char* mb = static_cast<char*>(M.tab.buf->p);
+            Gm.n_slots = (u32)M.tab.slots;
+            Gm.gval = (double*)(mb + M.tab.o_val);
+            Gm.gcnt = (unsigned long long*)(mb + M.tab.o_cnt);
+            Gm.gkeys = (u32*)(mb + M.tab.o_keys);
+            Gm.gstate = (u32*)(mb + M.tab.o_state);
+            Gm.overflow = (u32*)(mb + M.tab.bytes);
+            timer_begin(ctx, F_GROUP, 3);
+            launch_peer_barrier(T, (u32)t, ctx->st);
+            launch_group_init(Gm, ctx->st);
+            launch_group_merge_peers(Gm, T, ctx->n_sms, ctx->st);
+            timer_end(ctx);
+            KB_CUDA(ctx, cudaGetLastError());
+            KB_CUDA(ctx, cudaMemcpyAsync(M.h_tab, mb, M.tab.bytes + 16, cudaMemcpyDeviceToHost, ctx->st));
+            ctx->stats.d2h_bytes += M.tab.bytes + 16;
+        } else {
+            KB_CUDA(ctx, cudaMemcpyAsync(s.h_tab, tb, s.tab.bytes + 16, cudaMemcpyDeviceToHost, ctx->st));
+            ctx->stats.d2h_bytes += s.tab.bytes + 16;
+        }
     } else {
         for (u32 c = 0; c < pl->ip.n_out; c++) P.out[c] = s.cols[c].ptr;
         P.ordered = ctx->ordered;
@@ -195,6 +239,23 @@ kb_status kb_plan_collect(kb_ctx* ctx, kb_plan* pl, uint64_t ticket, uint64_t* n
     ctx->stats.d2h_bytes += sizeof(u32);
     ctx->stats.rows_out = total;
     if (n_rows) *n_rows = total;
+    if (pl->ip.agg && pl->attached) {
+        // the merged (GLOBAL) groups of all ranks; *n_rows stays this rank's own joined rows
+        if (rows) *rows = nullptr;
+        const kb_plan::Merged& M = pl->merged[ticket % pl->ring];
+        if (*reinterpret_cast<const u32*>(M.h_tab + M.tab.bytes) == 2u)
+            return fail(ctx, KB_E_CUDA, "the cross-rank barrier of this query timed out: a rank did not submit it (all ranks must submit the same queries)");
+        if (*reinterpret_cast<const u32*>(M.h_tab + M.tab.bytes))
+            return fail(ctx, KB_E_LIMIT, "more than %llu groups on some rank or in the merge: the prepared GROUP BY holds fixed tables", (unsigned long long)s.tab.slots);
+        if (groups) {
+            auto g = std::make_unique<kb_groups>();
+            g->keys.resize(1);
+            g->vals.resize(pl->ip.has_agg ? 1 : 0);
+            groups_from_host_table(M.h_tab, M.tab, 1, &pl->agg1, pl->ip.has_agg ? 1u : 0u, g.get());
+            *groups = g.release();
+        }
+        return KB_OK;
+    }
     if (pl->ip.agg) {
         if (rows) *rows = nullptr;
         const u32 ovf = *reinterpret_cast<const u32*>(s.h_tab + s.tab.bytes);
@@ -222,6 +283,42 @@ kb_status kb_plan_collect(kb_ctx* ctx, kb_plan* pl, uint64_t ticket, uint64_t* n
         }
         *rows = r.release();
     }
+    return KB_OK;
+}
+
+uint64_t kb_plan_peer_scratch_bytes(const kb_plan* pl) {
+    if (!pl || !pl->ip.agg) return 0;
+    const size_t stride = round256(pl->slots[0].tab.bytes + 16);
+    return 256 + (uint64_t)pl->ring * stride;
+}
+
+kb_status kb_plan_attach_peers(kb_ctx* ctx, kb_plan* pl, uint32_t rank, uint32_t world, void* const* peer_scratch) {
+    if (!ctx || !pl || pl->ctx != ctx) return KB_E_INVALID;
+    DevGuard guard(ctx->device);
+    if (!pl->ip.agg) return fail(ctx, KB_E_UNSUPPORTED, "only grouped plans merge across ranks (row plans need no exchange for subject stars)");
+    if (!peer_scratch || world == 0 || world > 64 || rank >= world) return fail(ctx, KB_E_INVALID, "rank %u / world %u (1..64 ranks)", rank, world);
+    if (pl->ring < 2) return fail(ctx, KB_E_INVALID, "a plan that merges across ranks needs a ring of at least 2 (a slot must not be refilled while a peer still reads it)");
+    if (pl->next_ticket != 1) return fail(ctx, KB_E_INVALID, "attach the peers before the first submit");
+    for (u32 r = 0; r < world; r++) if (!peer_scratch[r]) return fail(ctx, KB_E_INVALID, "peer scratch %u is NULL", r);
+    pl->world = world;
+    pl->rank = rank;
+    pl->table_stride = round256(pl->slots[0].tab.bytes + 16);
+    pl->peer_scratch.assign(world, nullptr);
+    for (u32 r = 0; r < world; r++) pl->peer_scratch[r] = static_cast<char*>(peer_scratch[r]);
+    pl->merged.resize(pl->ring);
+    for (u32 i = 0; i < pl->ring; i++) {
+        GroupParams G{};
+        // every partial group may be distinct: the merged table takes world x the partial capacity at load <= 1/2
+        u64 slots = 1024;
+        while (slots < 2ull * world * pl->slots[0].tab.slots) slots <<= 1;
+        KB_TRY(group_table_create(ctx, slots, &G, &pl->merged[i].tab));
+        Buf b;
+        KB_TRY(alloc_buf(ctx, pl->merged[i].tab.bytes + 16, &b));
+        pl->merged[i].tab.buf = b;
+        KB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&pl->merged[i].h_tab), pl->merged[i].tab.bytes + 16));
+    }
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    pl->attached = true;
     return KB_OK;
 }
 

@@ -210,6 +210,25 @@ def unpack_groups_np(buf: np.ndarray):
     return rec["keys"][:, :ng].copy(), rec["count"].copy(), rec["raw"][:, :na].copy(), kinds
 
 
+def attach_group_plan(plan, group=None):
+    """Give a grouped prepared plan its peers: scratch in torch symmetric memory (plumbing: allocation + address exchange), after which
+    plan.submit() merges the GROUP BY across ranks on the device (barrier over peer-memory flags + one merge kernel reading the peers'
+    partial tables over NVLink) and plan.collect_groups() returns the global groups on every rank."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    grp = group if group is not None else dist.group.WORLD
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    n = (plan.peer_scratch_bytes() + 3) // 4
+    buf = symm_mem.empty(n, dtype=torch.int32, device=torch.device("cuda", plan.ctx.device))
+    buf.zero_()
+    hdl = symm_mem.rendezvous(buf, grp)
+    torch.cuda.synchronize()
+    hdl.barrier()
+    torch.cuda.synchronize()
+    plan.attach_peers(rank, world, [int(x) for x in hdl.buffer_ptrs], keep=(buf, hdl))
+    return plan
+
+
 def allgather_groups(packed: np.ndarray, device=None, group=None) -> List[np.ndarray]:
     """the packed partial GROUP BY results of all ranks, in rank order (input of Context.groups_merge)"""
     return allgather_bytes(packed, device, group)

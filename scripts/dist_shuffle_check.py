@@ -34,29 +34,37 @@ assert ok and total == len(want)
 # ---- the same exchange fused with its transfer: one kernel writes into the peers' receive buffers over NVLink
 import time
 ps = kd.PeerShuffle(ctx, n_cols=2, capacity_rows=40_000_000)
-left_p2p = ps.shuffle(left, Y)
 H = datagen.canonical_rows
-ok2 = np.array_equal(H(left_p2p.to_numpy(sorted(left_p2p.slots))), H(left_sh.to_numpy(sorted(left_sh.slots))))
-got2 = ctx.hash_join(left_p2p, right).to_numpy([X, Y, Z])
-ok3 = np.array_equal(H(got2), H(mine))
-print(f"rank {rank}: peer-memory exchange: same rows as NCCL {ok2}, join ok {ok3}", flush=True)
-assert ok2 and ok3
+for name, fn in (("push (receiver-owned cursors)", lambda r: ps.shuffle(r, Y, copy=True)), ("planned (count matrix)", lambda r: ps.shuffle_planned(r, Y))):
+    left_p2p = fn(left)
+    ok2 = np.array_equal(H(left_p2p.to_numpy(sorted(left_p2p.slots))), H(left_sh.to_numpy(sorted(left_sh.slots))))
+    got2 = ctx.hash_join(left_p2p, right).to_numpy([X, Y, Z])
+    ok3 = np.array_equal(H(got2), H(mine))
+    print(f"rank {rank}: peer-memory exchange [{name}]: same rows as NCCL {ok2}, join ok {ok3}", flush=True)
+    assert ok2 and ok3
 
 # ---- timing on a large 2-column relation (rows per rank)
 nbig = 30_000_000
 big = ctx.rel_from_host([X, Y], [rng.integers(0, 1 << 24, nbig).astype(np.uint32), rng.integers(0, 1 << 24, nbig).astype(np.uint32)])
 dev = torch.device("cuda", local)
-for name, fn in (("partition + NCCL all_to_all", lambda: kd.shuffle_relation(ctx, big, Y)), ("fused peer-memory kernel", lambda: ps.shuffle(big, Y))):
-    ts = []
-    for rep in range(4):
+ctx.set_timing(True)
+for name, fn in (("partition + NCCL all_to_all", lambda: kd.shuffle_relation(ctx, big, Y)), ("fused peer-memory kernel, planned ranges", lambda: ps.shuffle_planned(big, Y)),
+                 ("fused peer-memory kernel, push", lambda: ps.shuffle(big, Y))):
+    ts, ks = [], []
+    for rep in range(5):
         dist.barrier(device_ids=[local]); torch.cuda.synchronize(dev)
+        ctx.get_stats(reset=True)
         t0 = time.perf_counter()
         r = fn()
         torch.cuda.synchronize(dev); dist.barrier(device_ids=[local])
         ts.append(time.perf_counter() - t0)
+        ks.append(ctx.get_stats(reset=True)["other_ms"])
         m = r.n_rows
         r.free()
     t = kd.max_over_ranks(min(ts[1:]), device=dev)
+    k = kd.max_over_ranks(min(ks[1:]), device=dev)
     if rank == 0:
-        print(f"{name}: {nbig} rows x 2 columns per rank, {world} ranks: {t * 1e3:.2f} ms ({8 * nbig * (world - 1) / world / t / 1e9:.1f} GB/s sent per rank over NVLink)", flush=True)
+        sent = 8 * nbig * (world - 1) / world
+        print(f"{name}: {nbig} rows x 2 columns per rank, {world} ranks: whole exchange {t * 1e3:.3f} ms ({sent / t / 1e9:.1f} GB/s sent per rank over NVLink); "
+              f"kernels alone {k:.3f} ms ({sent / (k * 1e-3) / 1e9:.1f} GB/s)", flush=True)
 dist.destroy_process_group()

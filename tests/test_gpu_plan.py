@@ -212,3 +212,60 @@ def test_shuffle_kernel_single_gpu(ctx, n_parts, n_cols, n):
         H.assert_same_bag(w.to_numpy(slots), full, "wrapped relation")
         w.free()
     rel.free()
+
+
+def test_peer_merged_group_plan_two_ranks_on_one_gpu(ctx):
+    """kb_plan_attach_peers with two 'ranks' = two contexts on this GPU whose scratch buffers see each other (the same protocol two
+    processes run over NVLink): each context holds one shard; after a submit on both, each collect returns the GLOBAL groups"""
+    import torch
+
+    d = datagen.employee_dataset(30000)
+    db = O.Db(d.s, d.p, d.o, d.num_or0, d.is_num)
+    js, pats, _ = datagen.employee_queries(d)["cfg3"]
+    orel = db.bgp(pats)
+    owner = datagen.shard_of_np(d.s, 2)
+    ctx2 = c.Context(ctx.device)
+    try:
+        cx = [ctx, ctx2]
+        dev = torch.device("cuda", ctx.device)
+        for aggs in ([(c.AGG_COUNT, 0)], [(c.AGG_AVG, 2)], [(c.AGG_MIN, 2)], [(c.AGG_MAX, 2)], [(c.AGG_SUM, 2)]):
+            plans, local_rows = [], []
+            for r in range(2):
+                keep = owner == r
+                cx[r].store_load(d.s[keep], d.p[keep], d.o[keep])
+                cx[r].dict_numeric_load(d.num_or0, d.is_num)
+                cx[r].build_index()
+                plans.append(cx[r].prepare_star_join(js, pats, None, group_slots=[1], aggs=aggs, ring=2))
+            nbytes = plans[0].peer_scratch_bytes()
+            assert nbytes == plans[1].peer_scratch_bytes() and nbytes > 0
+            scratch = [torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=dev) for _ in range(2)]
+            torch.cuda.synchronize()
+            for r in range(2):
+                plans[r].attach_peers(r, 2, [x.data_ptr() for x in scratch], keep=scratch)
+            w = db.group(orel, [1], aggs)
+            wk, wc, wv = table(w)
+            for rep in range(5):  # more queries than ring slots: the slots and the barrier epochs are reused
+                tk = [plans[0].submit(), plans[1].submit()]  # rank 0's barrier kernel waits on the device until rank 1's arrives
+                rows = 0
+                for r in range(2):
+                    g, n_rows = plans[r].collect_groups(tk[r])
+                    rows += n_rows
+                    gk, gc, gv = table(g)
+                    assert np.array_equal(gk, wk) and np.array_equal(gc, wc), (aggs, r, rep)
+                    for a, b in zip(gv, wv):
+                        assert np.allclose(a, b, rtol=1e-12, atol=0), (aggs, r, rep)
+                assert rows == orel.n_rows
+            for pl in plans:
+                pl.free()
+        # a row plan has nothing to merge; a ring of one cannot be attached
+        ctx.build_index()
+        p1 = ctx.prepare_star_join(js, pats, None, ring=2)
+        with pytest.raises(c.KolibrieError):
+            p1.attach_peers(0, 1, [scratch[0].data_ptr()])
+        p1.free()
+        p2 = ctx.prepare_star_join(js, pats, None, group_slots=[1], aggs=[(c.AGG_COUNT, 0)], ring=1)
+        with pytest.raises(c.KolibrieError):
+            p2.attach_peers(0, 1, [scratch[0].data_ptr()])
+        p2.free()
+    finally:
+        ctx2.close()
