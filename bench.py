@@ -660,7 +660,7 @@ def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max
     E_, M_, T_ = 0, 5, 1
     e_ids, m_ids, t_of_m = datagen.reports_to_relation(d, rank, world)
     left = ctx.rel_from_host([E_, M_], [e_ids, m_ids])
-    right = ctx.scan([c.pattern(c.V(M_), c.K(d.ids["foaf:title"]), c.V(T_))])[0]
+    right_pat = c.pattern(c.V(M_), c.K(d.ids["foaf:title"]), c.V(T_))
     cap = int(reduce_max(len(e_ids))[0] * 1.25) + 65536  # symmetric memory: the same size on every rank
     ps = kd.PeerShuffle(ctx, n_cols=2, capacity_rows=cap)
     sh_times, join_times, rows_j = [], [], 0
@@ -669,7 +669,7 @@ def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max
         t0 = time.perf_counter()
         sh = ps.shuffle(left, M_)
         t1 = time.perf_counter()
-        j = ctx.hash_join(sh, right)
+        j = ctx.bind_join(sh, right_pat)  # (?m foaf:title ?t): one lookup kernel against the index's persistent table
         rows_j = j.n_rows
         ctx.synchronize()
         t2 = time.perf_counter()
@@ -699,7 +699,6 @@ def multi_gpu_legs(args, ctx, d, rank, world, local, dev, K, barrier, reduce_max
                     "(peer atomic) and streams 128-byte-aligned runs into the receiver's buffer; two symmetric-memory barriers around it; no count exchange",
         "parity": "bag digest of the joined rows summed over ranks == closed form; every received row belongs to its rank"}
     left.free()
-    right.free()
     del ps
 
     # ---- strong scaling: the 100 M-triple store of BASELINE configs[2] (args.employees in total) split over the N GPUs

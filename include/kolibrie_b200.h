@@ -214,6 +214,10 @@ KB_API kb_status kb_project(kb_ctx* ctx, const kb_rel* in, const uint32_t* slots
 /* OptimizedHashJoin / HashJoin / merge join / NestedLoopJoin (engine.rs:710-837, 970-1039): natural join on the
  * common slots; no common slot -> cartesian product (engine.rs:1054-1071, limited to 2^28 output rows). */
 KB_API kb_status kb_hash_join(kb_ctx* ctx, const kb_rel* left, const kb_rel* right, kb_rel** out);
+/* BindJoin of a relation with ONE store pattern (engine.rs:840-885): natural join of `left` with the pattern's matches. With a valid store
+ * index, the pattern (?x P ?y) and exactly one of its variables bound by `left` through a unique dense column of the predicate, it is
+ * one probe kernel against the index's persistent table (the reference's spo[x][P] / pos[P][y] lookups); otherwise scan + hash join. */
+KB_API kb_status kb_bind_join(kb_ctx* ctx, const kb_rel* left, const kb_pattern* pattern, kb_rel** out);
 /* StarJoin (engine.rs:587-691) and bind-join chains on one variable (engine.rs:840-885): fused scan + build + probe.
  * Every pattern must contain join_slot. `filter` (nullable) is applied to the joined rows (engine.rs:73-85);
  * conjuncts that touch one pattern only are pushed into the scan. Result caps of the reference (quirk Q1) are NOT applied. */

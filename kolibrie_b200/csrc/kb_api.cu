@@ -1625,6 +1625,22 @@ void groups_from_host_table(const char* hb, const GroupTable& t, u32 n_group, co
         }
     }
 }
+void groups_from_records(const GroupRecord* recs, u64 n, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g) {
+    if (g->kinds.empty()) for (u32 a = 0; a < n_aggs; a++) g->kinds.push_back(aggs[a].kind);
+    g->raw.resize(n_aggs);
+    for (u64 i = 0; i < n; i++) {
+        const GroupRecord& r = recs[i];
+        for (u32 c = 0; c < n_group; c++) g->keys[c].push_back(r.keys[c]);
+        g->counts.push_back(r.count);
+        for (u32 a = 0; a < n_aggs; a++) {
+            double v = r.raw[a];
+            g->raw[a].push_back(v);
+            if (aggs[a].kind == KB_AGG_AVG) v = v / (double)r.count;   // execute_query.rs:1216
+            if (aggs[a].kind == KB_AGG_COUNT) v = (double)r.count;
+            g->vals[a].push_back(v);
+        }
+    }
+}
 kb_status group_table_collect(kb_ctx* ctx, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g) {
     std::vector<char> big;  // tables past 32 MB (hundreds of thousands of groups) are not worth pinning
     void* dst = nullptr;
@@ -2257,6 +2273,104 @@ kb_status kb_hash_join(kb_ctx* ctx, const kb_rel* left, const kb_rel* right, kb_
     if (!left || !right || !out) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
     std::unique_ptr<kb_rel> r;
     KB_TRY(kb::hash_join_impl(ctx, *left, *right, nullptr, &r));
+    ctx->stats.rows_out = r->n;
+    *out = r.release();
+    return KB_OK;
+}
+
+// BindJoin (engine.rs:840-885): every row of `left` is extended by the matches of ONE store pattern. With the store index valid, the
+// pattern (?x P ?y) and `left` binding exactly one of its variables through a unique, dense column, this is one probe kernel against the
+// persistent table of the index (spo[x][P] / pos[P][y] lookups, no scan, no build); every other shape = scan of the pattern + natural join.
+kb_status kb_bind_join(kb_ctx* ctx, const kb_rel* left, const kb_pattern* pat, kb_rel** out) {
+    KB_ENTER(ctx);
+    if (!left || !pat || !out) return kb::fail(ctx, KB_E_INVALID, "NULL argument");
+    KB_TRY(kb::check_pattern(ctx, *pat));
+    std::vector<u32> pv, psrc;
+    kb::pattern_vars(*pat, &pv, &psrc);
+    const bool pair_shape = pv.size() == 2 && psrc[0] == 0 && psrc[1] == 2 && !pat->p.is_var;
+    if (pair_shape && ctx->use_index && ctx->index_version == ctx->store_version && left->n > 0 && left->n < 0xFFFFFFF0ull && !left->pair &&
+        left->cols.size() < KB_MAX_COLS) {
+        const int cx = left->col_of(pv[0]), cy = left->col_of(pv[1]);
+        auto it = ctx->index.find(pat->p.value);
+        if ((cx >= 0) != (cy >= 0) && it != ctx->index.end() && it->second.n > 0) {
+            const kb::PredSlice& ps = it->second;
+            const bool by_y = cy >= 0;  // the bound variable is the pattern's object: look up pos[P][y]
+            const kb::Buf& tab = by_y ? ps.ytab : ps.xtab;
+            // the persistent tables of a subject-sharded store are keyed by the COMPACTED subject: a relation that went through a
+            // shuffle holds exactly the keys this shard owns, so the compaction applies to its rows too
+            bool usable = (bool)tab;
+            if (usable && !by_y && ps.tab_cshift != 0u) {
+                // compacted keys alias across shards: the lookup is only sound when every key of `left` belongs to this shard
+                const u32 foff = kb::ctrl_alloc(ctx, 4);
+                KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + foff, 0, 4 * sizeof(u32), ctx->st));
+                kb::timer_begin(ctx, kb::F_OTHER);
+                kb::launch_count_foreign(left->cols[cx].ptr, (u32)left->n, ctx->shard_rank, ctx->shard_world, ctx->ctrl + foff, ctx->n_sms, ctx->st);
+                kb::timer_end(ctx);
+                KB_CUDA(ctx, cudaGetLastError());
+                KB_TRY(kb::ctrl_read(ctx));
+                usable = ctx->h_ctrl[foff] == 0;
+            }
+            if (usable) {
+                kb::ProbeDParams P{};
+                P.n_pcols = (u32)left->cols.size();
+                P.key_col = (u32)(by_y ? cy : cx);
+                P.n = (u32)left->n;
+                P.n_tiles = (u32)((left->n + kb::PROBE_TILE - 1) / kb::PROBE_TILE);
+                P.T = 1;
+                kb::DirectTab& D = P.tab[0];
+                D.tab = static_cast<const u32*>(tab->p);
+                D.kmin = by_y ? ps.ytab_min : ps.xtab_min;
+                D.range = by_y ? ps.ytab_range : ps.xtab_range;
+                D.cshift = by_y ? 0u : ps.tab_cshift;
+                D.mode = 0; D.n_pay = 0; D.pay[0] = D.pay[1] = nullptr;
+                auto rel = std::make_unique<kb_rel>();
+                rel->slots = left->slots;
+                rel->slots.push_back(by_y ? pv[0] : pv[1]);
+                P.n_out = (u32)rel->slots.size();
+                const size_t stride = round256((size_t)left->n * sizeof(u32)) + 256;
+                kb::Buf b;
+                KB_TRY(kb::alloc_buf(ctx, stride * P.n_out, &b));
+                for (u32 c2 = 0; c2 < P.n_out; c2++) {
+                    kb::Col col;
+                    col.buf = b;
+                    col.ptr = reinterpret_cast<u32*>(static_cast<char*>(b->p) + stride * c2);
+                    rel->cols.push_back(col);
+                    P.out[c2] = col.ptr;
+                    P.oc[c2] = c2 + 1 < P.n_out ? kb::OutCol{kb::OUT_PROBE, c2, 0} : kb::OutCol{kb::OUT_TABVAL, 0, 0};
+                    if (c2 + 1 < P.n_out) P.pcol[c2] = left->cols[c2].ptr;
+                }
+                P.cap = (u32)left->n;
+                P.nt = kb::numtab(ctx);
+                KB_TRY(kb::ensure_tile_state(ctx, P.n_tiles));
+                P.tile_state = static_cast<u64*>(ctx->tile_state->p);
+                P.block_state = static_cast<u64*>(ctx->block_state->p);
+                P.ordered = ctx->ordered;
+                const u32 off = kb::ctrl_alloc(ctx, 4);
+                KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+                P.ticket = ctx->ctrl + off;
+                P.total = ctx->ctrl + off + 1;
+                P.zero_word = ctx->ctrl + off + 2;
+                P.epoch = ctx->epoch++;
+                P.abort_flag = nullptr;
+                kb::timer_begin(ctx, kb::F_PROBE);
+                kb::launch_probe_direct(P, ctx->n_sms, ctx->st);
+                kb::timer_end(ctx);
+                KB_CUDA(ctx, cudaGetLastError());
+                ctx->stats.rows_probed += left->n;
+                ctx->stats.index_joins++;
+                KB_TRY(kb::ctrl_read(ctx));
+                rel->n = ctx->h_ctrl[off + 1];
+                ctx->stats.rows_out = rel->n;
+                *out = rel.release();
+                return KB_OK;
+            }
+        }
+    }
+    std::vector<std::unique_ptr<kb_rel>> rels;
+    std::vector<kb::FilterProg> none;
+    KB_TRY(kb::scan_impl(ctx, pat, 1, none, false, false, &rels));
+    std::unique_ptr<kb_rel> r;
+    KB_TRY(kb::hash_join_impl(ctx, *left, *rels[0], nullptr, &r));
     ctx->stats.rows_out = r->n;
     *out = r.release();
     return KB_OK;

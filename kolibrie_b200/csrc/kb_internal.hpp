@@ -245,6 +245,8 @@ kb_status group_table_create(kb_ctx* ctx, u64 slots, GroupParams* P, GroupTable*
 kb_status group_table_collect(kb_ctx* ctx, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g);
 // the host half of it: `hb` = a host copy of the table's buffer
 void groups_from_host_table(const char* hb, const GroupTable& t, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g);
+// the same from a dense record list (launch_group_compact)
+void groups_from_records(const GroupRecord* recs, u64 n, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g);
 kb_status segment_stats(kb_ctx* ctx, Segment* sg);
 kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r);
 kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);

@@ -1687,6 +1687,33 @@ void launch_group_merge(const GroupParams& p, const GroupRecord* recs, u32 n, in
     group_merge_kernel<<<grid, 256, 0, st>>>(p, recs, n);
 }
 
+__global__ void __launch_bounds__(1024) group_compact_kernel(const __grid_constant__ GroupParams P, GroupRecord* __restrict__ out, u32* header, u32 cap) {
+    __shared__ u32 s_n;
+    if (threadIdx.x == 0) s_n = 0u;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < P.n_slots; i += blockDim.x) {
+        if (P.gstate[i] != 2u) continue;
+        const u32 at = atomicAdd(&s_n, 1u);
+        if (at >= cap) continue;
+        GroupRecord r;
+#pragma unroll
+        for (int c = 0; c < 4; c++) r.keys[c] = (u32)c < P.n_gcols ? P.gkeys[(u64)i * 4 + c] : 0u;
+        r.count = P.gcnt[i];
+#pragma unroll
+        for (int a = 0; a < 8; a++) r.raw[a] = (u32)a < P.n_aggs ? P.gval[(u64)i * 8 + a] : 0.0;
+        out[at] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        header[1] = (P.overflow ? *P.overflow : 0u) | (s_n > cap ? 1u : 0u);
+        header[0] = min(s_n, cap);
+        __threadfence_system();
+    }
+}
+void launch_group_compact(const GroupParams& p, GroupRecord* out, u32* header, u32 cap, cudaStream_t st) {
+    group_compact_kernel<<<1, 1024, 0, st>>>(p, out, header, cap);
+}
+
 // ---- cross-rank GROUP BY over peer memory
 __device__ __forceinline__ void st_release_sys(u32* p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ u32 ld_acquire_sys(const u32* p) {

@@ -327,6 +327,9 @@ struct PeerTables {
     u32 n_slots;             // slots per partial table
     u32 o_val, o_cnt, o_keys, o_state, o_overflow;  // byte offsets inside a partial table
 };
+// the occupied slots of p's table as a dense GroupRecord list: out[0 .. *count), header[0] = count, header[1] = the table's overflow
+// word. `out` / `header` may be mapped pinned host memory: a prepared query then needs no device-to-host copy of the sparse table
+void launch_group_compact(const GroupParams& p, GroupRecord* out, u32* header, u32 cap, cudaStream_t st);
 void launch_peer_barrier(const PeerTables& t, u32 epoch, cudaStream_t st);
 void launch_group_merge_peers(const GroupParams& p, const PeerTables& t, int n_sms, cudaStream_t st);
 

@@ -21,8 +21,10 @@ struct kb_plan {
     struct Slot {
         Buf out;                  // one allocation: n_out columns of probe_rows rows (row plans)
         std::vector<Col> cols;
-        GroupTable tab;           // aggregate plans: the device group table of this slot ...
-        char* h_tab = nullptr;    // ... and its pinned host copy (+ the overflow word behind it)
+        GroupTable tab;           // aggregate plans: the device group table of this slot (the overflow word rides behind it) ...
+        char* h_rec = nullptr;    // ... and the mapped pinned list its groups are compacted into: {u32 count, u32 overflow, pad} + GroupRecord[cap]
+        char* d_rec = nullptr;
+        u32 rec_cap = 0;
         cudaEvent_t done = nullptr;
         u64 ticket = 0;
         bool busy = false;        // submitted, not yet collected
@@ -40,7 +42,6 @@ struct kb_plan {
     std::vector<char*> peer_scratch;
     struct Merged {
         GroupTable tab;
-        char* h_tab = nullptr;
     };
     std::vector<Merged> merged;
 };
@@ -61,10 +62,10 @@ struct DevGuard {
 void plan_release(kb_plan* pl) {
     for (auto& s : pl->slots) {
         if (s.done) cudaEventDestroy(s.done);
-        if (s.h_tab) cudaFreeHost(s.h_tab);
+        if (s.h_rec) cudaFreeHost(s.h_rec);
     }
     if (pl->h_totals) cudaFreeHost(pl->h_totals);
-    for (auto& m : pl->merged) if (m.h_tab) cudaFreeHost(m.h_tab);
+
     delete pl;
 }
 }  // namespace
@@ -117,7 +118,10 @@ kb_status kb_star_join_prepare(kb_ctx* ctx, uint32_t join_slot, const kb_pattern
             Buf b;
             KB_TRY(alloc_buf(ctx, s.tab.bytes + 16, &b));
             s.tab.buf = b;
-            KB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&s.h_tab), s.tab.bytes + 16));
+            s.rec_cap = (u32)s.tab.slots;
+            KB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&s.h_rec), 16 + (size_t)s.rec_cap * sizeof(GroupRecord), cudaHostAllocMapped));
+            memset(s.h_rec, 0, 16);
+            KB_CUDA(ctx, cudaHostGetDevicePointer(reinterpret_cast<void**>(&s.d_rec), s.h_rec, 0));
         } else {
             const size_t stride = round256((size_t)ip.probe_rows * sizeof(u32)) + 256;
             KB_TRY(alloc_buf(ctx, stride * ip.n_out, &s.out));
@@ -197,12 +201,14 @@ kb_status kb_plan_submit(kb_ctx* ctx, kb_plan* pl, uint64_t* ticket) {
             launch_group_init(Gm, ctx->st);
             launch_group_merge_peers(Gm, T, ctx->n_sms, ctx->st);
             timer_end(ctx);
+            launch_group_compact(Gm, reinterpret_cast<GroupRecord*>(s.d_rec + 16), reinterpret_cast<u32*>(s.d_rec), s.rec_cap, ctx->st);
+            ctx->stats.kernel_launches++;
             KB_CUDA(ctx, cudaGetLastError());
-            KB_CUDA(ctx, cudaMemcpyAsync(M.h_tab, mb, M.tab.bytes + 16, cudaMemcpyDeviceToHost, ctx->st));
-            ctx->stats.d2h_bytes += M.tab.bytes + 16;
         } else {
-            KB_CUDA(ctx, cudaMemcpyAsync(s.h_tab, tb, s.tab.bytes + 16, cudaMemcpyDeviceToHost, ctx->st));
-            ctx->stats.d2h_bytes += s.tab.bytes + 16;
+            timer_begin(ctx, F_GROUP);
+            launch_group_compact(G, reinterpret_cast<GroupRecord*>(s.d_rec + 16), reinterpret_cast<u32*>(s.d_rec), s.rec_cap, ctx->st);
+            timer_end(ctx);
+            KB_CUDA(ctx, cudaGetLastError());
         }
     } else {
         for (u32 c = 0; c < pl->ip.n_out; c++) P.out[c] = s.cols[c].ptr;
@@ -239,32 +245,22 @@ kb_status kb_plan_collect(kb_ctx* ctx, kb_plan* pl, uint64_t ticket, uint64_t* n
     ctx->stats.d2h_bytes += sizeof(u32);
     ctx->stats.rows_out = total;
     if (n_rows) *n_rows = total;
-    if (pl->ip.agg && pl->attached) {
-        // the merged (GLOBAL) groups of all ranks; *n_rows stays this rank's own joined rows
-        if (rows) *rows = nullptr;
-        const kb_plan::Merged& M = pl->merged[ticket % pl->ring];
-        if (*reinterpret_cast<const u32*>(M.h_tab + M.tab.bytes) == 2u)
-            return fail(ctx, KB_E_CUDA, "the cross-rank barrier of this query timed out: a rank did not submit it (all ranks must submit the same queries)");
-        if (*reinterpret_cast<const u32*>(M.h_tab + M.tab.bytes))
-            return fail(ctx, KB_E_LIMIT, "more than %llu groups on some rank or in the merge: the prepared GROUP BY holds fixed tables", (unsigned long long)s.tab.slots);
-        if (groups) {
-            auto g = std::make_unique<kb_groups>();
-            g->keys.resize(1);
-            g->vals.resize(pl->ip.has_agg ? 1 : 0);
-            groups_from_host_table(M.h_tab, M.tab, 1, &pl->agg1, pl->ip.has_agg ? 1u : 0u, g.get());
-            *groups = g.release();
-        }
-        return KB_OK;
-    }
     if (pl->ip.agg) {
+        // attached plans: the merged (GLOBAL) groups of all ranks; *n_rows stays this rank's own joined rows
         if (rows) *rows = nullptr;
-        const u32 ovf = *reinterpret_cast<const u32*>(s.h_tab + s.tab.bytes);
-        if (ovf) return fail(ctx, KB_E_LIMIT, "more than %llu groups: the prepared GROUP BY holds a fixed table (use kb_star_join + kb_group_aggregate)", (unsigned long long)s.tab.slots);
+        const u32* hdr = reinterpret_cast<const u32*>(s.h_rec);
+        const u32 n_groups = reinterpret_cast<const volatile u32*>(hdr)[0], ovf = reinterpret_cast<const volatile u32*>(hdr)[1];
+        ctx->stats.d2h_bytes += 16 + (u64)n_groups * sizeof(GroupRecord);
+        if (ovf & 2u)
+            return fail(ctx, KB_E_CUDA, "the cross-rank barrier of this query timed out: a rank did not submit it (all ranks must submit the same queries)");
+        if (ovf)
+            return fail(ctx, KB_E_LIMIT, "more than %llu groups%s: the prepared GROUP BY holds fixed tables (use kb_star_join + kb_group_aggregate)",
+                        (unsigned long long)s.tab.slots, pl->attached ? " on some rank or in the merge" : "");
         if (groups) {
             auto g = std::make_unique<kb_groups>();
             g->keys.resize(1);
             g->vals.resize(pl->ip.has_agg ? 1 : 0);
-            groups_from_host_table(s.h_tab, s.tab, 1, &pl->agg1, pl->ip.has_agg ? 1u : 0u, g.get());
+            groups_from_records(reinterpret_cast<const GroupRecord*>(s.h_rec + 16), n_groups, 1, &pl->agg1, pl->ip.has_agg ? 1u : 0u, g.get());
             *groups = g.release();
         }
         return KB_OK;
@@ -308,14 +304,12 @@ kb_status kb_plan_attach_peers(kb_ctx* ctx, kb_plan* pl, uint32_t rank, uint32_t
     pl->merged.resize(pl->ring);
     for (u32 i = 0; i < pl->ring; i++) {
         GroupParams G{};
-        // every partial group may be distinct: the merged table takes world x the partial capacity at load <= 1/2
-        u64 slots = 1024;
-        while (slots < 2ull * world * pl->slots[0].tab.slots) slots <<= 1;
-        KB_TRY(group_table_create(ctx, slots, &G, &pl->merged[i].tab));
+        // the GLOBAL result is bounded like a rank's: at most `slots` groups (the record list's capacity); the merged table holds
+        // them at load <= 1/2, more distinct groups than that are reported as overflow by the compaction
+        KB_TRY(group_table_create(ctx, 2 * pl->slots[0].tab.slots, &G, &pl->merged[i].tab));
         Buf b;
         KB_TRY(alloc_buf(ctx, pl->merged[i].tab.bytes + 16, &b));
         pl->merged[i].tab.buf = b;
-        KB_CUDA(ctx, cudaMallocHost(reinterpret_cast<void**>(&pl->merged[i].h_tab), pl->merged[i].tab.bytes + 16));
     }
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     pl->attached = true;

@@ -3,7 +3,7 @@
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-[ -n "${SKIP_SHUF:-}" ] || timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/dist_shuffle_check.py 2>&1 | grep -v "^W\|^\[W\|warn" | tail -12 | tee gpurun_out/dist_shuffle_${N}gpu_r2b.txt
+[ -n "${SKIP_SHUF:-}" ] || timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 scripts/dist_shuffle_check.py 2>&1 | grep -v "^W\|^\[W\|warn" | tail -12 | tee gpurun_out/dist_shuffle_${N}gpu_r2b.txt
 echo "== bench N=$N"; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_${N}gpu_r2b.json 2> gpurun_out/bench_${N}gpu_r2b.err; tail -c 1500 gpurun_out/bench_${N}gpu_r2b.err
 python - <<PY
 import json

@@ -214,58 +214,82 @@ def test_shuffle_kernel_single_gpu(ctx, n_parts, n_cols, n):
     rel.free()
 
 
-def test_peer_merged_group_plan_two_ranks_on_one_gpu(ctx):
-    """kb_plan_attach_peers with two 'ranks' = two contexts on this GPU whose scratch buffers see each other (the same protocol two
-    processes run over NVLink): each context holds one shard; after a submit on both, each collect returns the GLOBAL groups"""
+def test_peer_merged_group_plan_world_of_one(ctx):
+    """kb_plan_attach_peers with a world of one rank (its own scratch is its only peer): submit runs join+group -> barrier -> merge
+    kernel -> compaction, and collect returns the same groups as the oracle. The two-and-more-rank protocol needs one process per GPU
+    (two spinning kernels of one process may share a hardware queue): scripts/dist_group_check.py under torchrun, and bench.py's cfg3
+    leg, assert it against the oracle / the closed form at N >= 2."""
     import torch
 
     d = datagen.employee_dataset(30000)
     db = O.Db(d.s, d.p, d.o, d.num_or0, d.is_num)
     js, pats, _ = datagen.employee_queries(d)["cfg3"]
     orel = db.bgp(pats)
-    owner = datagen.shard_of_np(d.s, 2)
-    ctx2 = c.Context(ctx.device)
-    try:
-        cx = [ctx, ctx2]
-        dev = torch.device("cuda", ctx.device)
-        for aggs in ([(c.AGG_COUNT, 0)], [(c.AGG_AVG, 2)], [(c.AGG_MIN, 2)], [(c.AGG_MAX, 2)], [(c.AGG_SUM, 2)]):
-            plans, local_rows = [], []
-            for r in range(2):
-                keep = owner == r
-                cx[r].store_load(d.s[keep], d.p[keep], d.o[keep])
-                cx[r].dict_numeric_load(d.num_or0, d.is_num)
-                cx[r].build_index()
-                plans.append(cx[r].prepare_star_join(js, pats, None, group_slots=[1], aggs=aggs, ring=2))
-            nbytes = plans[0].peer_scratch_bytes()
-            assert nbytes == plans[1].peer_scratch_bytes() and nbytes > 0
-            scratch = [torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=dev) for _ in range(2)]
-            torch.cuda.synchronize()
-            for r in range(2):
-                plans[r].attach_peers(r, 2, [x.data_ptr() for x in scratch], keep=scratch)
-            w = db.group(orel, [1], aggs)
-            wk, wc, wv = table(w)
-            for rep in range(5):  # more queries than ring slots: the slots and the barrier epochs are reused
-                tk = [plans[0].submit(), plans[1].submit()]  # rank 0's barrier kernel waits on the device until rank 1's arrives
-                rows = 0
-                for r in range(2):
-                    g, n_rows = plans[r].collect_groups(tk[r])
-                    rows += n_rows
-                    gk, gc, gv = table(g)
-                    assert np.array_equal(gk, wk) and np.array_equal(gc, wc), (aggs, r, rep)
-                    for a, b in zip(gv, wv):
-                        assert np.allclose(a, b, rtol=1e-12, atol=0), (aggs, r, rep)
-                assert rows == orel.n_rows
-            for pl in plans:
-                pl.free()
-        # a row plan has nothing to merge; a ring of one cannot be attached
-        ctx.build_index()
-        p1 = ctx.prepare_star_join(js, pats, None, ring=2)
-        with pytest.raises(c.KolibrieError):
-            p1.attach_peers(0, 1, [scratch[0].data_ptr()])
-        p1.free()
-        p2 = ctx.prepare_star_join(js, pats, None, group_slots=[1], aggs=[(c.AGG_COUNT, 0)], ring=1)
-        with pytest.raises(c.KolibrieError):
-            p2.attach_peers(0, 1, [scratch[0].data_ptr()])
-        p2.free()
-    finally:
-        ctx2.close()
+    ctx.store_load(d.s, d.p, d.o)
+    ctx.dict_numeric_load(d.num_or0, d.is_num)
+    ctx.build_index()
+    dev = torch.device("cuda", ctx.device)
+    for aggs in ([(c.AGG_COUNT, 0)], [(c.AGG_AVG, 2)], [(c.AGG_MIN, 2)], [(c.AGG_MAX, 2)], [(c.AGG_SUM, 2)], []):
+        plan = ctx.prepare_star_join(js, pats, None, group_slots=[1], aggs=aggs, ring=2)
+        nbytes = plan.peer_scratch_bytes()
+        assert nbytes > 0
+        scratch = torch.zeros((nbytes + 3) // 4, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        plan.attach_peers(0, 1, [scratch.data_ptr()], keep=scratch)
+        w = db.group(orel, [1], aggs)
+        wk, wc, wv = table(w)
+        tickets = []
+        for rep in range(5):  # more queries than ring slots: the slots and the barrier epochs are reused
+            tickets.append(plan.submit())
+            if len(tickets) == 2:
+                g, n_rows = plan.collect_groups(tickets.pop(0))
+                assert n_rows == orel.n_rows
+                gk, gc, gv = table(g)
+                assert np.array_equal(gk, wk) and np.array_equal(gc, wc), (aggs, rep)
+                for a, b in zip(gv, wv):
+                    assert np.allclose(a, b, rtol=1e-12, atol=0), (aggs, rep)
+        plan.collect_groups(tickets.pop(0))
+        plan.free()
+    # a row plan has nothing to merge; a ring of one cannot be attached
+    p1 = ctx.prepare_star_join(js, pats, None, ring=2)
+    with pytest.raises(c.KolibrieError):
+        p1.attach_peers(0, 1, [scratch.data_ptr()])
+    p1.free()
+    p2 = ctx.prepare_star_join(js, pats, None, group_slots=[1], aggs=[(c.AGG_COUNT, 0)], ring=1)
+    with pytest.raises(c.KolibrieError):
+        p2.attach_peers(0, 1, [scratch.data_ptr()])
+    p2.free()
+
+
+def test_bind_join_vs_oracle(ctx):
+    """kb_bind_join (engine.rs:840-885): a relation joined with one store pattern — through the index's persistent tables when they
+    exist (subject-bound and object-bound lookups), through scan + hash join otherwise; always the oracle's natural join"""
+    d = datagen.employee_dataset(20000)
+    db = O.Db(d.s, d.p, d.o, d.num_or0, d.is_num)
+    ctx.store_load(d.s, d.p, d.o)
+    ctx.dict_numeric_load(d.num_or0, d.is_num)
+    rng = np.random.default_rng(5)
+    subj = d.s[0::6]
+    e_col = np.concatenate([rng.choice(subj, 30000), np.array([0xFFFFFF0, 3], dtype=np.uint32)]).astype(np.uint32)  # duplicates + keys that match nothing
+    tag = rng.integers(0, 1000, len(e_col)).astype(np.uint32)
+    E, T, X, N = 0, 1, 7, 3
+    title_p, name_p, sal_p = (c.pattern(c.V(E), c.K(d.ids[k]), c.V(v)) for k, v in (("foaf:title", T), ("foaf:name", N), ("ds:annual_salary", 2)))
+    cases = [("subject-bound, unique dense column", title_p, E), ("object-bound (name object = employee id, unique)", c.pattern(c.V(9), c.K(d.ids["foaf:name"]), c.V(E)), E),
+             ("bound through the object of a multi-valued column", c.pattern(c.V(9), c.K(d.ids["foaf:title"]), c.V(E)), E)]
+    for indexed in (False, True):
+        if indexed:
+            ctx.build_index()
+        for what, pat, key in cases:
+            col = e_col if "multi" not in what else np.array([d.ids["Manager"], d.ids["Developer"], 5], dtype=np.uint32)
+            tg = tag[: len(col)]
+            left = ctx.rel_from_host([key, X], [col, tg])
+            n0 = ctx.get_stats()["index_joins"]
+            got = ctx.bind_join(left, pat)
+            want = O.hash_join(O.rel_from_host([key, X], [col, tg]), db.bgp([pat]))
+            H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"{what} indexed={indexed}")
+            took_index = ctx.get_stats()["index_joins"] > n0
+            assert took_index == (indexed and "multi" not in what), (what, indexed)
+    # both variables bound, or none: natural join / cartesian semantics through the general path
+    left = ctx.rel_from_host([E, T], [subj[:50], d.o[1::6][:50]])
+    got = ctx.bind_join(left, title_p)
+    assert got.n_rows == 50
