@@ -400,7 +400,7 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
     KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_ticket, 0, std::max(n_seg, 1u) * sizeof(u32), ctx->st));
     u64 all_tiles = 0;
     for (auto& sg : ctx->segs) all_tiles += (sg.n + SCAN_TILE - 1) / SCAN_TILE;
-    KB_TRY(ensure_tile_state(ctx, all_tiles));
+    KB_TRY(ensure_tile_state(ctx, all_tiles * 4));  // the star-shape kernel may walk the store in smaller tiles than SCAN_TILE
     P.tile_state = static_cast<u64*>(ctx->tile_state->p);
     P.block_state = static_cast<u64*>(ctx->block_state->p);
     P.ordered = ctx->ordered;

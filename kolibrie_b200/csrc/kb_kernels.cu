@@ -5,6 +5,7 @@
 #include "kb_kernels.cuh"
 
 #include <math_constants.h>
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 
@@ -252,13 +253,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, (K <= 4 ? 1024 / SCAN_THREADS : 
 // compile time removes what made the general kernel issue-bound (2.8 warp instructions per triple): no per-tile flag tests, no
 // comparison switch per element (a < c is evaluated as -a > -c, so every operator is one DSETP), no divergent branches — every store is
 // predicated — and no rank computation for patterns whose matches go to a table.
+#ifndef KB_STAR_THREADS
+#define KB_STAR_THREADS 256
+#endif
+constexpr int STAR_THREADS = KB_STAR_THREADS;  // K <= 4 patterns need 4 prefix warps: 128 threads suffice (smaller CTAs, cheaper barriers)
+constexpr int STAR_TILE = STAR_THREADS * SCAN_ITEMS;
 template <int K>
-__global__ void __launch_bounds__(SCAN_THREADS, 4) scan_star_kernel(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(STAR_THREADS, 1024 / STAR_THREADS) scan_star_kernel(const __grid_constant__ ScanParams P) {
     extern __shared__ __align__(128) u32 smem_all[];
-    constexpr u32 STAGE_WORDS = 3u * SCAN_TILE;
+    constexpr u32 STAGE_WORDS = 3u * STAR_TILE;
     __shared__ __align__(8) u64 bars[2];
     __shared__ u32 s_nexts[2];
-    __shared__ u32 s_wcnt[SCAN_THREADS / 32][MAXP];
+    __shared__ u32 s_wcnt[STAR_THREADS / 32][MAXP];
     __shared__ u32 s_excl[MAXP];
     __shared__ u32 s_tcnt[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -269,15 +275,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_star_kernel(const __grid
             u32 g = 0;
             while (g + 1u < P.n_seg && t >= P.seg[g + 1u].tile0) g++;
             const ScanSeg& sg = P.seg[g];
-            const u32 b = (t - sg.tile0) * (u32)SCAN_TILE;
-            const u32 c = min((u32)SCAN_TILE, sg.n - b);
+            const u32 b = (t - sg.tile0) * (u32)STAR_TILE;
+            const u32 c = min((u32)STAR_TILE, sg.n - b);
             const u32 bytes = (c * 4u + 15u) & ~15u;
             s_tcnt[stage] = c;
             u32* dst = smem_all + stage * STAGE_WORDS;
             mbar_arrive_expect_tx(&bars[stage], bytes * 3u);
             tma_load_1d(dst, sg.s + b, bytes, &bars[stage]);
-            tma_load_1d(dst + SCAN_TILE, sg.p + b, bytes, &bars[stage]);
-            tma_load_1d(dst + 2 * SCAN_TILE, sg.o + b, bytes, &bars[stage]);
+            tma_load_1d(dst + STAR_TILE, sg.p + b, bytes, &bars[stage]);
+            tma_load_1d(dst + 2 * STAR_TILE, sg.o + b, bytes, &bars[stage]);
         }
     };
     if (tid == 0) {
@@ -295,33 +301,46 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_star_kernel(const __grid
         const u32 stage = it & 1u;
         mbar_wait(&bars[stage], (it >> 1) & 1u);
         const uint4* sS4 = reinterpret_cast<const uint4*>(smem_all + stage * STAGE_WORDS);
-        const uint4* sP4 = sS4 + SCAN_TILE / 4;
-        const uint4* sO4 = sS4 + 2 * (SCAN_TILE / 4);
-        const uint4 s0 = sS4[2 * tid], s1 = sS4[2 * tid + 1];
-        const uint4 p0 = sP4[2 * tid], p1 = sP4[2 * tid + 1];
-        const uint4 o0 = sO4[2 * tid], o1 = sO4[2 * tid + 1];
+        const uint4* sP4 = sS4 + STAR_TILE / 4;
+        const uint4* sO4 = sS4 + 2 * (STAR_TILE / 4);
+        // thread t owns triples [4t, 4t+4) of EACH half of the tile: consecutive threads read consecutive 16-byte words (LDS.128 without
+        // bank conflicts; 8 consecutive triples per thread put two threads of a quarter-warp on the same banks). The rows of a tile
+        // therefore come out in a fixed permutation of store order — fine for tables and for completion-order results; ordered
+        // contexts take the general kernel.
+        constexpr u32 HALF4 = STAR_TILE / 8;  // uint4 words per half column
+        const uint4 s0 = sS4[tid], s1 = sS4[HALF4 + tid];
+        const uint4 p0 = sP4[tid], p1 = sP4[HALF4 + tid];
+        const uint4 o0 = sO4[tid], o1 = sO4[HALF4 + tid];
         const u32 cnt = s_tcnt[stage];
-        const u32 first = (u32)tid * 8u;
-        const u32 vmask = first >= cnt ? 0u : (cnt - first >= 8u ? 0xFFu : ((1u << (cnt - first)) - 1u));
+        const u32 first = (u32)tid * 4u;
+        const u32 lo = first >= cnt ? 0u : (cnt - first >= 4u ? 0xFu : ((1u << (cnt - first)) - 1u));
+        const u32 first2 = (u32)STAR_TILE / 2u + first;
+        const u32 hi = first2 >= cnt ? 0u : (cnt - first2 >= 4u ? 0xFu : ((1u << (cnt - first2)) - 1u));
+        const u32 vmask = lo | (hi << 4);
         u32 mk[K];
 #pragma unroll
         for (int k = 0; k < K; k++) {
             u32 m = eq8(p0, p1, P.pat[k].cp) & vmask;
             if (P.pat[k].f_len != 0u) {  // uniform per pattern: FILTER(?x <cmp> c) on the subject (slot 0) or the object (slot 2)
+                // the launcher canonicalised the comparison to >= or <= (a > c is a >= nextup(c)): one DSETP per triple, no operator switch
                 const FilterOp fo = P.ops[P.pat[k].f_begin];
                 const bool on_s = fo.slot == 0u;
-                const bool flip = fo.cmp == KB_CMP_LT || fo.cmp == KB_CMP_LE;   // a < c  <=>  -a > -c (NaN stays false, -0.0 == 0.0 either way)
-                const bool strict = fo.cmp == KB_CMP_GT || fo.cmp == KB_CMP_LT;
-                const double sg = flip ? -1.0 : 1.0;
-                const double cv = fo.value * sg;
+                const double cv = fo.value;
                 const uint4 x0 = on_s ? s0 : o0, x1 = on_s ? s1 : o1;
-                u32 pass = 0;
+                double a[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const u32 id = KB_ELEM(x0, x1, j);
-                    const double a = (((m >> j) & 1u) && id < P.nt.n_ids) ? __ldg(P.nt.num_or0 + id) * sg : 0.0 * sg;
-                    const bool ok = strict ? (a > cv) : (a >= cv);
-                    pass |= (ok ? 1u : 0u) << j;
+                    a[j] = 0.0;
+                    if (((m >> j) & 1u) && id < P.nt.n_ids) a[j] = __ldg(P.nt.num_or0 + id);
+                }
+                u32 pass = 0;
+                if (fo.cmp == KB_CMP_GE) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) pass |= (a[j] >= cv ? 1u : 0u) << j;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) pass |= (a[j] <= cv ? 1u : 0u) << j;
                 }
                 m &= pass;
             }
@@ -351,62 +370,56 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_star_kernel(const __grid
         }
         __syncthreads();
         const u32 following = s_nexts[stage ^ 1u];
-        if (tid == SCAN_THREADS - 1) issue_next(stage);  // every thread holds its triples in registers: the stage takes the tile after next
+        if (tid == STAR_THREADS - 1) issue_next(stage);  // every thread holds its triples in registers: the stage takes the tile after next
         if (warp < K) {
-            const u32 c = lane < SCAN_THREADS / 32 ? s_wcnt[lane][warp] : 0u;
+            const u32 c = lane < STAR_THREADS / 32 ? s_wcnt[lane][warp] : 0u;
             u32 incl = c;
 #pragma unroll
-            for (int o = 1; o < SCAN_THREADS / 32; o <<= 1) {
+            for (int o = 1; o < STAR_THREADS / 32; o <<= 1) {
                 const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
                 if (lane >= o) incl += y;
             }
-            const u32 total = __shfl_sync(0xffffffffu, incl, SCAN_THREADS / 32 - 1);
-            if (lane < SCAN_THREADS / 32) s_wcnt[lane][warp] = incl - c;
+            const u32 total = __shfl_sync(0xffffffffu, incl, STAR_THREADS / 32 - 1);
+            if (lane < STAR_THREADS / 32) s_wcnt[lane][warp] = incl - c;
             const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, (u32)warp, P.epoch, total, P.totals_in, P.totals_out, P.ordered, lane);
             if (lane == 0) s_excl[warp] = ex;
         }
         __syncthreads();
-        // ---- table outputs: every triple is CLASSIFIED once (the patterns' predicates are distinct, so it matches at most one) and
-        // takes one store path whose table / key base / range / key position are fetched from the parameter block by class index;
-        // class K (no match, or a pair-output pattern, whose range is 0) stores nothing
-        {
-            u32 filt_fail = 0;  // bit j: triple j matched the predicate of a filtered pattern but failed its FILTER
-#pragma unroll
-            for (int k = 0; k < K; k++) if (P.pat[k].f_len != 0u) filt_fail |= eq8(p0, p1, P.pat[k].cp) & ~mk[k];
-            auto table_stores = [&](auto with_cshift) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const u32 pj = KB_ELEM(p0, p1, j);
-                    u32 c = (u32)K;
-#pragma unroll
-                    for (int k = K - 1; k >= 0; k--) c = pj == P.pat[k].cp ? (u32)k : c;
-                    const bool live = ((vmask & ~filt_fail) >> j) & 1u;
-                    const ScanPat& sp = P.pat[c];
-                    const u32 krange = sp.co;
-                    const bool key_o = (sp.flags & SP_TKEY_O) != 0u;
-                    const u32 sj = KB_ELEM(s0, s1, j), oj = KB_ELEM(o0, o1, j);
-                    const u32 key = key_o ? oj : sj, val = key_o ? sj : oj;
-                    const u32 off = (with_cshift.value ? compact_key(key, P.cshift) : key) - sp.cs;
-                    const bool in = off < krange;
-                    if (live && in) sp.outp[0][off] = val;
-                    bad_any |= (live && !in && krange != 0u) ? (1u << c) : 0u;
-                }
-            };
-            if (P.cshift == 0u) table_stores(std::false_type{});
-            else table_stores(std::true_type{});
-        }
-        // ---- pair outputs (the probe side of the join): ranked, predicated 8-byte stores
 #pragma unroll
         for (int k = 0; k < K; k++) {
-            if (P.pat[k].flags & SP_TABLE) continue;  // uniform
             const u32 m = mk[k];
-            u32 pos = s_excl[k] + s_wcnt[warp][k] + wex[k];
-            uint2* out = reinterpret_cast<uint2*>(P.pat[k].outp[0]);
+            if (P.pat[k].flags & SP_TABLE) {  // uniform: the matches go straight into this pattern's direct table
+                u32* tab = P.pat[k].outp[0];
+                const u32 kbase = P.pat[k].cs, krange = P.pat[k].co;
+                auto stores = [&](const uint4& k0, const uint4& k1, const uint4& v0, const uint4& v1, auto with_cshift) {
+                    u32 worst = 0;  // largest offset of a matching triple: one range test per pattern and tile instead of one flag update per triple
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const bool on = (m >> j) & 1u;
-                if (on) out[pos] = make_uint2(KB_ELEM(s0, s1, j), KB_ELEM(o0, o1, j));
-                pos += on ? 1u : 0u;
+                    for (int j = 0; j < 8; j++) {
+                        const u32 key = KB_ELEM(k0, k1, j);
+                        const u32 off = (with_cshift.value ? compact_key(key, P.cshift) : key) - kbase;
+                        const bool on = (m >> j) & 1u;  // (the compiler folds this with the predicate comparison the bit came from)
+                        if (on && off < krange) tab[off] = KB_ELEM(v0, v1, j);
+                        worst = max(worst, on ? off : 0u);
+                    }
+                    bad_any |= worst >= krange ? (1u << k) : 0u;
+                };
+                const bool key_o = (P.pat[k].flags & SP_TKEY_O) != 0u;
+                if (P.cshift == 0u) {
+                    if (key_o) stores(o0, o1, s0, s1, std::false_type{});
+                    else stores(s0, s1, o0, o1, std::false_type{});
+                } else {
+                    if (key_o) stores(o0, o1, s0, s1, std::true_type{});
+                    else stores(s0, s1, o0, o1, std::true_type{});
+                }
+            } else {
+                u32 pos = s_excl[k] + s_wcnt[warp][k] + wex[k];
+                uint2* out = reinterpret_cast<uint2*>(P.pat[k].outp[0]);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const bool on = (m >> j) & 1u;
+                    if (on) out[pos] = make_uint2(KB_ELEM(s0, s1, j), KB_ELEM(o0, o1, j));
+                    pos += on ? 1u : 0u;
+                }
             }
         }
         tile = following;
@@ -420,9 +433,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 4) scan_star_kernel(const __grid
 
 // does the star-shape kernel apply?
 static bool scan_is_star(const ScanParams& p) {
-    if (p.K > 4) return false;
-    for (u32 a = 0; a < p.K; a++)
-        for (u32 b = a + 1; b < p.K; b++) if (p.pat[a].cp == p.pat[b].cp) return false;  // a triple must match at most one pattern
+    if (p.K > 4 || p.ordered) return false;  // store-order output (KOLIBRIE_ORDERED, legacy FFI): the general kernel
     for (u32 k = 0; k < p.K; k++) {
         const ScanPat& sp = p.pat[k];
         const u32 shape = sp.flags & ~(SP_TABLE | SP_TKEY_O | SP_TTRUSTED | SP_PAIR);
@@ -440,20 +451,29 @@ static bool scan_is_star(const ScanParams& p) {
 template <int K>
 static void launch_scan_star_k(const ScanParams& p_in, int n_sms, cudaStream_t st) {
     ScanParams p = p_in;
-    for (u32 k = 0; k <= (u32)K; k++) {  // classes that store nothing: pair-output patterns and the no-match class K have range 0
-        if (k == (u32)K || !(p.pat[k].flags & SP_TABLE)) { p.pat[k].co = 0u; p.pat[k].cs = 0u; p.pat[k].outp[0] = k == (u32)K ? nullptr : p.pat[k].outp[0]; }
-        if (k == (u32)K) p.pat[k].flags = 0u;
+    for (u32 k = 0; k < (u32)K; k++) {
+        if (p.pat[k].f_len != 1u) continue;
+        // strict comparisons become non-strict ones against the neighbouring double: a > c <=> a >= nextup(c) (c = +inf: never true -> NaN)
+        FilterOp& fo = p.ops[p.pat[k].f_begin];
+        if (fo.cmp == KB_CMP_GT) { fo.value = fo.value == HUGE_VAL ? NAN : nextafter(fo.value, HUGE_VAL); fo.cmp = KB_CMP_GE; }
+        else if (fo.cmp == KB_CMP_LT) { fo.value = fo.value == -HUGE_VAL ? NAN : nextafter(fo.value, -HUGE_VAL); fo.cmp = KB_CMP_LE; }
     }
-    const size_t smem = 2 * 3 * SCAN_TILE * sizeof(u32);
+    // the kernel walks the store in STAR_TILE-triple tiles: renumber the segments' first tiles
+    p.n_tiles = 0;
+    for (u32 g = 0; g < p.n_seg; g++) {
+        p.seg[g].tile0 = p.n_tiles;
+        p.n_tiles += (p.seg[g].n + (u32)STAR_TILE - 1u) / (u32)STAR_TILE;
+    }
+    const size_t smem = 2 * 3 * STAR_TILE * sizeof(u32);
     static int grid_max = 0;
     if (grid_max == 0) {
         cudaFuncSetAttribute(scan_star_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_star_kernel<K>, SCAN_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_star_kernel<K>, STAR_THREADS, smem);
         grid_max = (per_sm < 1 ? 1 : per_sm) * n_sms;
     }
     const int grid = (int)umin64((u64)grid_max, (u64)p.n_tiles);
-    scan_star_kernel<K><<<grid, SCAN_THREADS, smem, st>>>(p);
+    scan_star_kernel<K><<<grid, STAR_THREADS, smem, st>>>(p);
 }
 
 template <int K>

@@ -81,8 +81,58 @@ class Constant:
     id: int
 
 
-Term = Union[Variable, Constant]
+@dataclass(frozen=True)
+class QuotedTriple:
+    """Term::QuotedTriple(Box<(Term, Term, Term)>) (shared/src/terms.rs:19): an RDF-star pattern `<< s p o >>` in subject or object position"""
+    s: object
+    p: object
+    o: object
+
+
+Term = Union[Variable, Constant, QuotedTriple]
 TriplePattern = Tuple[Term, Term, Term]
+
+QUOTED_TRIPLE_ID_BIT = 0x8000_0000  # shared/src/quoted_triple_store.rs:17
+
+
+def is_quoted_triple_id(i: int) -> bool:
+    return (i & QUOTED_TRIPLE_ID_BIT) != 0
+
+
+class QuotedTripleStore:
+    """shared/src/quoted_triple_store.rs:28-80: quoted triples as u32 ids with bit 31 set, bidirectional, deduplicating; components
+    may themselves be quoted-triple ids (nesting)."""
+
+    def __init__(self):
+        self.id_to_components: Dict[int, Tuple[int, int, int]] = {}
+        self.components_to_id: Dict[Tuple[int, int, int], int] = {}
+        self.next_qt_id = QUOTED_TRIPLE_ID_BIT
+
+    def encode(self, subject: int, predicate: int, obj: int) -> int:
+        key = (int(subject), int(predicate), int(obj))
+        i = self.components_to_id.get(key)
+        if i is not None:
+            return i
+        i = self.next_qt_id
+        self.next_qt_id += 1
+        self.id_to_components[i] = key
+        self.components_to_id[key] = i
+        return i
+
+    def decode(self, i: int) -> Optional[Tuple[int, int, int]]:
+        return self.id_to_components.get(int(i))
+
+    def __len__(self):
+        return len(self.id_to_components)
+
+    def is_empty(self) -> bool:
+        return not self.id_to_components
+
+    def merge(self, other: "QuotedTripleStore"):
+        for i, comp in other.id_to_components.items():
+            self.id_to_components.setdefault(i, comp)
+            self.components_to_id.setdefault(comp, i)
+        self.next_qt_id = max(self.next_qt_id, other.next_qt_id)
 
 
 def _strip(v: str) -> str:
@@ -104,6 +154,8 @@ class SlotMap:
         return self.slot[name]
 
     def term(self, t: Term) -> c.KbTerm:
+        if isinstance(t, QuotedTriple):
+            raise c.KolibrieError(c.KB_E_UNSUPPORTED, "a quoted-triple term must be resolved on the host first (ExecutionEngine._scan_quoted)")
         return c.V(self.of(t.name)) if isinstance(t, Variable) else c.K(t.id)
 
     def pattern(self, p: TriplePattern) -> c.KbPattern:
@@ -269,10 +321,35 @@ class SparqlDatabase:
 
     def __init__(self, ctx: Optional[c.Context] = None, device: int = 0):
         self.dictionary = Dictionary()
+        self.quoted_triple_store = QuotedTripleStore()  # sparql_database.rs:58
         self.triples: set = set()
         self.ctx = ctx or c.Context(device)
         self._uploaded_version = -1
         self._version = 0
+
+    def encode_term(self, t) -> int:
+        """a term given as a string, or as a nested (s, p, o) tuple for a quoted triple `<< s p o >>` (components encoded first, in
+        s, p, o order, then the quoted triple itself: sparql_database.rs encode_quoted_triple)"""
+        if isinstance(t, (tuple, list)):
+            s, p, o = (self.encode_term(x) for x in t)
+            return self.quoted_triple_store.encode(s, p, o)
+        return self.dictionary.encode(t)
+
+    def decode_term(self, i: int) -> Optional[str]:
+        """Dictionary::decode_term (dictionary.rs:58-68): quoted-triple ids decode recursively to `<< s p o >>`"""
+        if is_quoted_triple_id(i):
+            comp = self.quoted_triple_store.decode(i)
+            if comp is None:
+                return None
+            parts = [self.decode_term(x) for x in comp]
+            if any(x is None for x in parts):
+                return None
+            return "<< " + " ".join(parts) + " >>"
+        return self.dictionary.decode(i)
+
+    def add_statement(self, s, p, o):
+        """add one triple whose terms are strings or nested tuples (quoted triples)"""
+        self.add_triple((self.encode_term(s), self.encode_term(p), self.encode_term(o)))
 
     def add_triple_parts(self, s: str, p: str, o: str):
         t = (self.dictionary.encode(s), self.dictionary.encode(p), self.dictionary.encode(o))
@@ -299,7 +376,7 @@ class SparqlDatabase:
     def _sync(self):
         if self._uploaded_version == self._version:
             return
-        arr = np.array(sorted(self.triples), dtype=np.uint32).reshape(-1, 3)
+        arr = np.array(sorted(self.triples), dtype=np.uint32).reshape(-1, 3)  # (s,p,o) order: the reference's BTreeSet iteration
         self.ctx.store_load(arr[:, 0], arr[:, 1], arr[:, 2])
         num, isn = self.dictionary.numeric_table()
         self.ctx.dict_numeric_load(num, isn)
@@ -314,6 +391,8 @@ class ExecutionEngine:
     def _run(op, db: SparqlDatabase, slots: SlotMap) -> c.Relation:
         ctx = db.ctx
         if isinstance(op, (TableScan, IndexScan)):
+            if any(isinstance(t, QuotedTriple) for t in op.pattern):
+                return ExecutionEngine._scan_quoted(op.pattern, db, slots)
             return ctx.scan([slots.pattern(op.pattern)])[0]
         if isinstance(op, Filter):
             # Selection directly over a star / scan: let the fused operator push conjuncts into its scans
@@ -328,7 +407,10 @@ class ExecutionEngine:
         if isinstance(op, (HashJoin, OptimizedHashJoin, NestedLoopJoin)):
             return ctx.hash_join(ExecutionEngine._run(op.left, db, slots), ExecutionEngine._run(op.right, db, slots))
         if isinstance(op, ParallelJoin):
-            # right side a scan -> bind join (engine.rs:935-937) == natural join of left with the pattern's matches
+            # right side a scan -> bind join (engine.rs:935-937) == natural join of left with the pattern's matches: kb_bind_join looks the
+            # pattern up in the index's persistent tables when it can, and scans + joins otherwise
+            if isinstance(op.right, (TableScan, IndexScan)) and not any(isinstance(t, QuotedTriple) for t in op.right.pattern) and hasattr(ctx, "bind_join"):
+                return ctx.bind_join(ExecutionEngine._run(op.left, db, slots), slots.pattern(op.right.pattern))
             return ctx.hash_join(ExecutionEngine._run(op.left, db, slots), ExecutionEngine._run(op.right, db, slots))
         if isinstance(op, StarJoin):
             return ctx.star_join(slots.of(op.join_var), [slots.pattern(p) for p in op.patterns])
@@ -337,6 +419,50 @@ class ExecutionEngine:
             cols = [np.array([row[k] for row in op.content], dtype=np.uint32) for k in names]
             return ctx.rel_from_host([slots.of(k) for k in names], cols)
         raise c.KolibrieError(c.KB_E_UNSUPPORTED, f"operator {type(op).__name__} stays on the reference's CPU path")
+
+    @staticmethod
+    def _scan_quoted(pattern: TriplePattern, db: SparqlDatabase, slots: SlotMap):
+        """resolve_quoted_triple_scan (engine.rs:1111-1188). The quoted-triple store is a host structure in the reference too: its
+        entries are matched against the `<< s p o >>` term(s) on the host (match_term, engine.rs:1088-1107: constants by id, variables
+        bound on first use and compared afterwards, a nested quoted term only requires a quoted-triple id), which yields one row
+        (quoted id, inner bindings) per matching entry. The reference then runs one index scan per entry with the id substituted and
+        merges the bindings, dropping conflicts; relationally that is the natural join of those rows with ONE scan of the pattern whose
+        quoted position is a fresh variable — which is what runs on the device (kb_scan + kb_rel_from_host + kb_hash_join)."""
+        ctx = db.ctx
+        qt_s, qt_o = isinstance(pattern[0], QuotedTriple), isinstance(pattern[2], QuotedTriple)
+        if isinstance(pattern[1], QuotedTriple):
+            raise c.KolibrieError(c.KB_E_UNSUPPORTED, "quoted triple in predicate position")
+        rows: List[Dict[str, int]] = []
+        for qid, comp in db.quoted_triple_store.id_to_components.items():
+            b: Dict[str, int] = {}
+
+            def match(term, value) -> bool:
+                if isinstance(term, Constant):
+                    return term.id == value
+                if isinstance(term, Variable):
+                    name = _strip(term.name)
+                    if name in b:
+                        return b[name] == value
+                    b[name] = value
+                    return True
+                return is_quoted_triple_id(value)  # nested quoted pattern: engine.rs:1100-1105
+
+            ok = True
+            for term in ([pattern[0]] if qt_s else []) + ([pattern[2]] if qt_o else []):  # the SAME entry serves both positions (engine.rs:1135-1150)
+                ok = ok and match(term.s, comp[0]) and match(term.p, comp[1]) and match(term.o, comp[2])
+            if ok:
+                b["__qt"] = qid
+                rows.append(b)
+        qslot = slots.of("__qt_%d" % len(slots.names))
+        names = sorted({k for r in rows for k in r if k != "__qt"})
+        # the outer pattern with the quoted position(s) replaced by the fresh variable
+        outer = (Variable(slots.names[qslot]) if qt_s else pattern[0], pattern[1], Variable(slots.names[qslot]) if qt_o else pattern[2])
+        outer_rel = ctx.scan([slots.pattern(outer)])[0]
+        cols = [np.array([r["__qt"] for r in rows], dtype=np.uint32)] + [np.array([r[k] for r in rows], dtype=np.uint32) for k in names]
+        inner_rel = ctx.rel_from_host([qslot] + [slots.of(k) for k in names], cols)
+        joined = ctx.hash_join(inner_rel, outer_rel)
+        _, jslots = joined.info()
+        return ctx.project(joined, [s_ for s_ in jslots if s_ != qslot])
 
     @staticmethod
     def execute_with_ids(op, db: SparqlDatabase) -> List[Dict[str, int]]:
@@ -355,7 +481,14 @@ class ExecutionEngine:
         slots = SlotMap()
         rel = ExecutionEngine._run(op, db, slots)
         n, rslots = rel.info()
-        cols = [rel.decode_strings(i) for i in range(len(rslots))]
+        cols = []
+        for i in range(len(rslots)):
+            try:
+                cols.append(rel.decode_strings(i))
+            except c.KolibrieError as e:  # quoted-triple ids (bit 31) are decoded on the host, recursively (dictionary.rs:58-68)
+                if e.status != c.KB_E_UNSUPPORTED:
+                    raise
+                cols.append([db.decode_term(int(x)) or "unknown" for x in rel.column(i)])
         names = [slots.names[s] for s in rslots]
         return [{names[j]: cols[j][i] for j in range(len(names))} for i in range(n)]
 

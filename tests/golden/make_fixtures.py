@@ -91,3 +91,55 @@ dump("rust_parse_f64.json", {
                "Infinity": "inf", "INFINITY": "inf", "nan": "nan", "NaN": "nan", "+nan": "nan", "100000": 100000.0, "0": 0.0, "007": 7.0},
     "reject": ["", " 1", "1 ", "1_000", "0x10", "1e", "e5", ".", "+", "-", "1.2.3", "--1", "infinit", "nane", "1f", "Developer",
                "http://example.org/employee1", "١", "5\n", " 5", "5 ", "5\t", "\n5", "1e5\n"]})
+
+EX = "http://example.org/"
+dump("rdf_star.json", {
+    "source": "/root/reference/kolibrie/tests/rdf_star_test.rs:107-145 (SPARQL-star scans), :281-329 (quoted triple as a bound value), :384-405 (DELETE WHERE); "
+              "/root/reference/shared/src/quoted_triple_store.rs:82-157 (QuotedTripleStore unit tests, replayed by tests/test_rdf_star_rsp_golden.py)",
+    "note": "terms are strings; a nested [s, p, o] list is a quoted triple << s p o >>; '?x' is a variable",
+    "cases": [
+        {"name": "constant_quoted_triple", "line": 107,
+         "data": [[[EX + "emp38", EX + "jobTitle", EX + "AssistantDesigner"], EX + "statedBy", EX + "emp22"]],
+         "pattern": [[EX + "emp38", EX + "jobTitle", EX + "AssistantDesigner"], EX + "statedBy", "?who"],
+         "select": ["who"], "rows": [[EX + "emp22"]]},
+        {"name": "variable_in_quoted_triple", "line": 126,
+         "data": [[[EX + "emp38", EX + "jobTitle", EX + "AssistantDesigner"], EX + "statedBy", EX + "emp22"],
+                  [[EX + "emp39", EX + "jobTitle", EX + "Designer"], EX + "statedBy", EX + "emp23"]],
+         "pattern": [["?emp", EX + "jobTitle", "?title"], EX + "statedBy", "?who"],
+         "select": ["emp", "title", "who"], "n_rows": 2,
+         "rows": [[EX + "emp38", EX + "AssistantDesigner", EX + "emp22"], [EX + "emp39", EX + "Designer", EX + "emp23"]]},
+        {"name": "quoted_triple_bound_to_a_variable", "line": 281,
+         "data": [[[EX + "alice", EX + "knows", EX + "bob"], EX + "source", EX + "doc1"]],
+         "pattern": ["?t", EX + "source", EX + "doc1"],
+         "select": ["t"], "n_rows": 1, "rows": [["<< " + EX + "alice " + EX + "knows " + EX + "bob >>"]], "subject_of_t": EX + "alice"},
+    ],
+    "delete_where": {"line": 384,
+                     "data": [[EX + "alice", EX + "knows", EX + "bob"], [EX + "alice", EX + "knows", EX + "carol"], [EX + "alice", EX + "name", "Alice"]],
+                     "delete_pattern": ["?s", EX + "knows", "?o"], "triples_before": 3, "triples_after": 1}})
+
+T = "http://test/"
+dump("rsp_windows.json", {
+    "source": "/root/reference/kolibrie/tests/rsp_engine_test.rs:24-112 (rsp_ql_istream_semantics), :935-1027 (rsp_ql_istream_range3_step1), "
+              ":1029-1084 (test_window_evicts_old_data), :1103-1200 (rsp_ql_istream_same_sp_diff_object)",
+    "note": "The window operator (S2R) and the stream operator (R2S) are out of the hot path; what the hot path sees per firing is the window's "
+            "content (rsp_engine.rs:94-104: evict the previous window, add the current one) and the query over it. `firings` lists each "
+            "firing's window content exactly as the reference test's comments state it, and the rows its R2S operator emits.",
+    "cases": [
+        {"name": "istream_semantics", "line": 24, "stream": "ISTREAM", "pattern": ["?s", "a", T + "IType"], "select": ["s"],
+         "firings": [{"window": [[T + "subjectA", "a", T + "IType"]], "emit": [[T + "subjectA"]]},
+                     {"window": [[T + "subjectA", "a", T + "IType"], [T + "subjectB", "a", T + "IType"]], "emit": [[T + "subjectB"]]},
+                     {"window": [[T + "subjectA", "a", T + "IType"], [T + "subjectB", "a", T + "IType"], [T + "subjectC", "a", T + "IType"]], "emit": [[T + "subjectC"]]}]},
+        {"name": "istream_range3_step1", "line": 935, "stream": "ISTREAM", "pattern": ["?s", "a", T + "RType"], "select": ["s"],
+         "firings": [{"window": [[T + "subjectA", "a", T + "RType"]], "emit": [[T + "subjectA"]]},
+                     {"window": [[T + "subjectA", "a", T + "RType"], [T + "subjectB", "a", T + "RType"]], "emit": [[T + "subjectB"]]},
+                     {"window": [[T + "subjectA", "a", T + "RType"], [T + "subjectB", "a", T + "RType"], [T + "subjectC", "a", T + "RType"]], "emit": [[T + "subjectC"]]}]},
+        {"name": "window_evicts_old_data", "line": 1029, "stream": "RSTREAM", "pattern": ["?s", "a", EX + "Type"], "select": ["s"],
+         "firings": [{"window": [[EX + "subject1", "a", EX + "Type"]], "emit": [[EX + "subject1"]]},
+                     {"window": [[EX + "subject2", "a", EX + "Type"]], "emit": [[EX + "subject2"]]},
+                     {"window": [[EX + "subject3", "a", EX + "Type"]], "emit": [[EX + "subject3"]]}]},
+        {"name": "istream_same_sp_diff_object", "line": 1103, "stream": "ISTREAM", "pattern": ["?reading", T + "hasTemp", "?temp"], "select": ["reading", "temp"],
+         "firings": [{"window": [[T + "reading1", T + "hasTemp", "\"1\""]], "emit": [[T + "reading1", "\"1\""]]},
+                     {"window": [[T + "reading1", T + "hasTemp", "\"1\""], [T + "reading1", T + "hasTemp", "\"2\""]], "emit": [[T + "reading1", "\"2\""]]},
+                     {"window": [[T + "reading1", T + "hasTemp", "\"1\""], [T + "reading1", T + "hasTemp", "\"2\""], [T + "reading1", T + "hasTemp", "\"3\""]],
+                      "emit": [[T + "reading1", "\"3\""]]}]},
+    ]})

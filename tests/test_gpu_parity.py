@@ -528,3 +528,17 @@ def test_index_kernel_shapes(ctx, n_subj):
     ctx.set_use_index(True)
     got = ctx.star_join(0, cases[1][1], cases[1][2])
     H.assert_same_bag(got.to_numpy(sorted(got.slots)), r.to_numpy(sorted(r.slots)), "index vs scan path")
+
+
+@pytest.mark.parametrize("cmp", [c.CMP_GT, c.CMP_GE, c.CMP_LT, c.CMP_LE])
+def test_star_scan_filter_boundaries(ctx, emp, cmp):
+    """the star-shape scan kernel evaluates a strict comparison as a non-strict one against the neighbouring double: constants that
+    equal stored values, infinities, NaN and signed zeros must still give the oracle's rows (scan path: index off)"""
+    d, db = emp
+    js, pats, _ = datagen.employee_queries(d)["cfg2"]
+    present = float(d.salary_of_employee[7])
+    for value in (present, present + 0.5, 30000.0, 149999.0, 0.0, -0.0, float("inf"), float("-inf"), float("nan"), 1e300, -1e300, 5e-324):
+        filt = [c.fop(c.F_CMP_NUM, slot=2, cmp=cmp, value=value)]
+        got = ctx.star_join(js, pats, filt)
+        want = db.bgp(pats, filt)
+        H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"cmp {cmp} value {value}")
