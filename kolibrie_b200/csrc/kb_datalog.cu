@@ -68,6 +68,8 @@ struct Fix {
     kb_ctx* ctx;
     std::map<u32, PredRel> rels;
     std::vector<Pending> pend;
+    Buf buckets;  // candidate buckets of the radix-partitioned dedup, kept across the derive calls of one fixpoint (a 3 GB allocation
+                  // from the stream-ordered pool can cost milliseconds when the pool has to remap)
 };
 
 kb_status grow_rel(kb_ctx* ctx, PredRel& r, u64 need) {
@@ -358,9 +360,50 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                         D.set_slots = hr.set_slots;
                         // the set may fill up to 3/4 before it has to grow (expected: 1/2)
                         D.budget = (u32)std::min<u64>((u64)hr.set_slots / 4 * 3 - count_before, 0xFFFFFFFFull);
-                        timer_begin(ctx, F_OTHER);
-                        launch_derive(D, ctx->n_sms, ctx->st);
-                        timer_end(ctx);
+                        // Large candidate sets against a table far beyond L2: radix-partition the candidates by the high bits of their
+                        // home slot and probe partition by partition (each slice stays L2-resident) instead of one random DRAM line per
+                        // candidate. Partitions: ~32 MB slices, at least ~1 M candidates each (so that the CTAs of the probe pass sit on
+                        // one or two slices at a time), at most 1024.
+                        u64 n_parts = 0;
+                        {
+                            const u64 set_bytes = (u64)hr.set_slots * sizeof(u64);
+                            u64 want = std::min<u64>(set_bytes / ctx->derive_slice_bytes, std::min<u64>(cur->n / ctx->derive_min_part_rows, 1024));
+                            while (want >= 2 && n_parts * 2 <= want) n_parts = n_parts ? n_parts * 2 : 2;  // power of two
+                            if (ctx->derive_part == 0) n_parts = 0;
+                        }
+                        if (n_parts >= 2) {
+                            DerivePartParams Q{};
+                            Q.d = D;
+                            Q.n_parts = (u32)n_parts;
+                            u32 set_bits = 0;
+                            while ((1ull << set_bits) < hr.set_slots) set_bits++;
+                            u32 part_bits = 0;
+                            while ((1ull << part_bits) < n_parts) part_bits++;
+                            Q.slice_bits = set_bits - part_bits;
+                            Q.bucket_cap = (u32)std::min<u64>(cur->n / n_parts + cur->n / n_parts / 8 + ctx->derive_bucket_slack, 0xFFFFFFF0ull);
+                            Buf ctl;
+                            const size_t bucket_bytes = n_parts * (u64)Q.bucket_cap * sizeof(u64);
+                            if (!fx.buckets || fx.buckets->bytes < bucket_bytes) {
+                                fx.buckets.reset();
+                                KB_TRY(alloc_buf(ctx, bucket_bytes + bucket_bytes / 4, &fx.buckets));
+                            }
+                            Buf buckets = fx.buckets;
+                            KB_TRY(alloc_buf(ctx, (2 * n_parts + 8) * sizeof(u32), &ctl));
+                            KB_CUDA(ctx, cudaMemsetAsync(ctl->p, 0, (2 * n_parts + 8) * sizeof(u32), ctx->st));
+                            Q.buckets = static_cast<u64*>(buckets->p);
+                            Q.cursors = static_cast<u32*>(ctl->p);
+                            Q.tile_start = Q.cursors + n_parts;
+                            Q.tickets = Q.tile_start + n_parts + 1 + ((n_parts + 1) & 1u);
+                            tr.mark(ctx, "    derive: buckets allocated", n_parts);
+                            timer_begin(ctx, F_OTHER, 3);
+                            launch_derive_partitioned(Q, ctx->n_sms, ctx->st);
+                            timer_end(ctx);
+                            ctx->stats.rows_built += cur->n;  // (counted as table traffic: partitioned candidates)
+                        } else {
+                            timer_begin(ctx, F_OTHER);
+                            launch_derive(D, ctx->n_sms, ctx->st);
+                            timer_end(ctx);
+                        }
                         KB_CUDA(ctx, cudaGetLastError());
                         // counts are read immediately: the control arena may be recycled by later joins of this round
                         KB_TRY(ctrl_read(ctx));

@@ -159,6 +159,12 @@ struct kb_ctx {
     std::map<kb::u32, kb::PredSlice> index;  // kb_store_build_index: predicate -> slice; valid while index_version == store_version
     kb::u64 index_version = ~0ull;
     bool csr_join = true;                // KOLIBRIE_CSR_JOIN=0: 1:N joins always use the chained table (A/B switch)
+    // Datalog candidate dedup: radix-partitioned above these sizes (KOLIBRIE_DERIVE_PART=0: never; =1 with KOLIBRIE_DERIVE_SLICE /
+    // KOLIBRIE_DERIVE_MIN_ROWS: tests force it on small inputs)
+    int derive_part = 1;
+    kb::u64 derive_slice_bytes = 32ull << 20;
+    kb::u64 derive_min_part_rows = 1ull << 20;
+    kb::u64 derive_bucket_slack = 8192;  // KOLIBRIE_DERIVE_SLACK: rows a bucket holds beyond 9/8 of its fair share
     bool fast_index_kernel = true;       // KOLIBRIE_INDEX_KERNEL=0: index joins go through the generic probe kernel (A/B switch)
     bool use_index = true;               // KOLIBRIE_USE_INDEX=0 / kb_set_use_index: force the scanning path
     kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject

@@ -6,6 +6,7 @@
 
 #include <math_constants.h>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -2329,6 +2330,218 @@ __global__ void __launch_bounds__(256) derive_kernel(const __grid_constant__ Der
     nd = nd + __shfl_xor_sync(0xffffffffu, nd, 1);
     if (lane == 0 && nd) atomicAdd(P.n_deriv, nd);
 }
+// ---- radix-partitioned variant
+constexpr int DPART_THREADS = 256;
+constexpr int DPART_ITEMS = 16;
+constexpr int DPART_TILE = DPART_THREADS * DPART_ITEMS;  // 4096 candidates: 32 KB of keys + 8 KB of partition ids in shared memory
+constexpr int DPART_MAXP = 1024;
+__device__ __forceinline__ u32 set64_home(u32 n_slots, u32 s, u32 o) { return mix32(mix32(s) * 0x9E3779B1u ^ mix32(o + 0x632BE5ABu)) & (n_slots - 1u); }
+
+// insert + append of ONE candidate outside any warp-cooperative section (bucket overflow path of the partition pass)
+__device__ __noinline__ void derive_one(const DeriveParams& P, u32 s, u32 o) {
+    if (*reinterpret_cast<volatile u32*>(P.out_count) >= P.budget) { *P.overflow = 2u; return; }
+    const u32 r = set64_insert(P.set, P.set_slots, s, o);
+    if (r == 2u) *P.overflow = 2u;
+    if (r == 1u) {
+        const u32 at = atomicAdd(P.out_count, 1u);
+        if (at < P.out_cap) { P.out_s[at] = s; P.out_o[at] = o; }
+        else *P.overflow = 1u;
+    }
+}
+
+__global__ void __launch_bounds__(DPART_THREADS) derive_partition_kernel(const __grid_constant__ DerivePartParams Q) {
+    extern __shared__ __align__(16) u64 sh_keys[];  // [DPART_TILE] keys sorted by partition, then u16 partition ids
+    __shared__ u32 s_cnt[DPART_MAXP], s_off[DPART_MAXP], s_gbase[DPART_MAXP];
+    __shared__ u32 s_tile;
+    const DeriveParams& P = Q.d;
+    unsigned short* s_dest = reinterpret_cast<unsigned short*>(sh_keys + DPART_TILE);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 n_tiles = (P.n + DPART_TILE - 1u) / DPART_TILE;
+    unsigned long long nd = 0;
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(&Q.tickets[0], 1u);
+        for (u32 d = (u32)tid; d < Q.n_parts; d += DPART_THREADS) s_cnt[d] = 0u;
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= n_tiles) break;
+        const u32 row0 = tile * (u32)DPART_TILE;
+        const u32 cnt = min((u32)DPART_TILE, P.n - row0);
+        // ---- 1. head instantiation + rule filters; partition = high bits of the key's home slot; histogram
+        u64 key[DPART_ITEMS];
+        u32 part[DPART_ITEMS];
+#pragma unroll
+        for (int j = 0; j < DPART_ITEMS; j++) {
+            const u32 r = (u32)j * DPART_THREADS + (u32)tid;
+            const u32 i = row0 + r;
+            bool pass = r < cnt && rule_filters_pass(P, i);
+            u32 s = 0, o = 0;
+            if (pass) {
+                nd++;
+                s = P.head_s.is_var ? __ldg(P.bcol[P.head_s.value] + i) : P.head_s.value;
+                o = P.head_o.is_var ? __ldg(P.bcol[P.head_o.value] + i) : P.head_o.value;
+            }
+            key[j] = ((u64)s << 32) | (u64)o;
+            part[j] = pass ? (set64_home(P.set_slots, s, o) >> Q.slice_bits) : 0xFFFFu;
+            if (pass) atomicAdd(&s_cnt[part[j]], 1u);
+        }
+        __syncthreads();
+        // ---- 2. offsets inside the tile (one warp scans the histogram), one range reservation per partition
+        if (warp == 0) {
+            u32 run = 0;
+            for (u32 d0 = 0; d0 < Q.n_parts; d0 += 32u) {
+                const u32 d = d0 + (u32)lane;
+                const u32 c = d < Q.n_parts ? s_cnt[d] : 0u;
+                u32 incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                if (d < Q.n_parts) {
+                    s_off[d] = run + incl - c;
+                    s_gbase[d] = c ? atomicAdd(&Q.cursors[d], c) : 0u;
+                    s_cnt[d] = 0u;  // becomes the fill cursor of step 3
+                }
+                run += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
+        __syncthreads();
+        // ---- 3. keys staged in partition order
+#pragma unroll
+        for (int j = 0; j < DPART_ITEMS; j++) {
+            if (part[j] == 0xFFFFu) continue;
+            const u32 pos = s_off[part[j]] + atomicAdd(&s_cnt[part[j]], 1u);
+            sh_keys[pos] = key[j];
+            s_dest[pos] = (unsigned short)part[j];
+        }
+        __syncthreads();
+        // ---- 4. flush: staged position q belongs to partition s_dest[q]; consecutive q of one partition are consecutive in its bucket
+        const u32 staged = s_off[Q.n_parts - 1u] + s_cnt[Q.n_parts - 1u];
+        for (u32 q = (u32)tid; q < staged; q += DPART_THREADS) {
+            const u32 d = s_dest[q];
+            const u32 at = s_gbase[d] + (q - s_off[d]);
+            const u64 k = sh_keys[q];
+            if (at < Q.bucket_cap) Q.buckets[(u64)d * Q.bucket_cap + at] = k;
+            else derive_one(P, (u32)(k >> 32), (u32)k);  // the bucket is full (skewed hash): probe directly
+        }
+        __syncthreads();
+    }
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 16);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 8);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 4);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 2);
+    nd = nd + __shfl_xor_sync(0xffffffffu, nd, 1);
+    if (lane == 0 && nd) atomicAdd(P.n_deriv, nd);
+}
+
+constexpr int DPROBE_TILE = 2048;
+__global__ void __launch_bounds__(1024) derive_tile_starts_kernel(const __grid_constant__ DerivePartParams Q) {
+    __shared__ u32 s_tiles[DPART_MAXP];
+    const int tid = threadIdx.x;
+    if ((u32)tid < Q.n_parts) s_tiles[tid] = (min(Q.cursors[tid], Q.bucket_cap) + DPROBE_TILE - 1u) / DPROBE_TILE;
+    __syncthreads();
+    if (tid == 0) {
+        u32 run = 0;
+        for (u32 d = 0; d < Q.n_parts; d++) { Q.tile_start[d] = run; run += s_tiles[d]; }
+        Q.tile_start[Q.n_parts] = run;
+    }
+}
+
+__global__ void __launch_bounds__(256) derive_probe_kernel(const __grid_constant__ DerivePartParams Q) {
+    __shared__ u32 s_tile, s_base;
+    __shared__ u32 s_wcnt[8];
+    const DeriveParams& P = Q.d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 n_tiles = Q.tile_start[Q.n_parts];
+    constexpr int R = DPROBE_TILE / 256;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(&Q.tickets[1], 1u);  // tickets are handed out in partition order: the CTAs walk the slices together
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= n_tiles) break;
+        u32 lo = 0, hi = Q.n_parts;  // partition of this tile: last d with tile_start[d] <= tile
+        while (hi - lo > 1u) {
+            const u32 mid = (lo + hi) >> 1;
+            if (Q.tile_start[mid] <= tile) lo = mid; else hi = mid;
+        }
+        const u32 d = lo;
+        const u32 n_keys = min(Q.cursors[d], Q.bucket_cap);
+        const u32 first = (tile - Q.tile_start[d]) * (u32)DPROBE_TILE;
+        const u64* keys = Q.buckets + (u64)d * Q.bucket_cap;
+        // the set must not fill past its budget: checked once per tile (a tile adds at most DPROBE_TILE facts: the budget leaves that room)
+        const bool room = *reinterpret_cast<volatile u32*>(P.out_count) < P.budget;
+        if (!room && tid == 0) *P.overflow = 2u;
+        u64 k[R];
+        u32 fresh = 0;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            const u32 q = first + (u32)j * 256u + (u32)tid;
+            k[j] = (room && q < n_keys) ? __ldg(keys + q) : EMPTY64;
+        }
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if (k[j] == EMPTY64) continue;  // (s = o = 0xFFFFFFFF is the reserved id: never a fact)
+            const u32 r = set64_insert(P.set, P.set_slots, (u32)(k[j] >> 32), (u32)k[j]);
+            if (r == 2u) *P.overflow = 2u;  // table full (the per-tile budget check lets a small table overshoot): grow and run again
+            fresh |= (r == 1u ? 1u : 0u) << j;
+        }
+        // ONE reservation per tile for the facts that were new (a single global cursor serialises: per-warp reservations cost 30 ms on
+        // 1.4e8 new facts), then ranked writes
+        const u32 c = (u32)__popc(fresh);
+        u32 incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) s_wcnt[warp] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            u32 run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { const u32 x = s_wcnt[w]; s_wcnt[w] = run; run += x; }
+            s_base = run ? atomicAdd(P.out_count, run) : 0u;
+        }
+        __syncthreads();
+        u32 pos = s_base + s_wcnt[warp] + incl - c;
+#pragma unroll
+        for (int j = 0; j < R; j++) {
+            if ((fresh >> j) & 1u) {
+                if (pos < P.out_cap) { P.out_s[pos] = (u32)(k[j] >> 32); P.out_o[pos] = (u32)k[j]; }
+                else *P.overflow = 1u;
+                pos++;
+            }
+        }
+    }
+}
+
+void launch_derive_partitioned(const DerivePartParams& p, int n_sms, cudaStream_t st) {
+    if (p.d.n == 0) return;
+    const size_t smem = (size_t)DPART_TILE * (sizeof(u64) + sizeof(unsigned short));
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(derive_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    const u32 n_tiles = (p.d.n + DPART_TILE - 1u) / DPART_TILE;
+    const int grid1 = grid_for((const void*)derive_partition_kernel, DPART_THREADS, smem, n_sms, n_tiles);
+    static const bool trace = getenv("KOLIBRIE_TRACE") != nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    if (trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventRecord(e0, st); }
+    derive_partition_kernel<<<grid1, DPART_THREADS, smem, st>>>(p);
+    if (trace) cudaEventRecord(e1, st);
+    derive_tile_starts_kernel<<<1, 1024, 0, st>>>(p);
+    const int grid2 = grid_for((const void*)derive_probe_kernel, 256, 0, n_sms, (p.d.n + DPROBE_TILE - 1u) / DPROBE_TILE + p.n_parts);
+    derive_probe_kernel<<<grid2, 256, 0, st>>>(p);
+    if (trace) {
+        cudaEventRecord(e2, st);
+        cudaEventSynchronize(e2);
+        float a = 0.f, b = 0.f;
+        cudaEventElapsedTime(&a, e0, e1);
+        cudaEventElapsedTime(&b, e1, e2);
+        fprintf(stderr, "[kb trace]     derive partitioned: %u candidates, %u partitions: partition pass %.3f ms, probe pass %.3f ms\n", p.d.n, p.n_parts, a, b);
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    }
+}
+
 void launch_derive(const DeriveParams& p, int n_sms, cudaStream_t st) {
     if (p.n == 0) return;
     int grid = (int)umin64((u64)n_sms * 8ull, ((u64)p.n + 255ull) / 256ull);

@@ -355,6 +355,22 @@ struct DeriveParams {
     u32* overflow;                // 1: set or output full (error); 2: budget reached, the host grows the set and runs the launch again
 };
 void launch_derive(const DeriveParams& p, int n_sms, cudaStream_t st);
+// RADIX-PARTITIONED candidate dedup (the same work as launch_derive for large candidate sets). The known-fact set is an open-addressing
+// table far larger than L2 (config 4: 8 GB), so a direct probe per candidate is one random DRAM line per candidate. Here the
+// candidates are first partitioned by the HIGH bits of their home slot (tile sorted by partition in shared memory, one range
+// reservation per tile and partition, coalesced runs), so that partition p only touches slice p of the table; the probe pass then walks
+// the partitions in order, every CTA on (nearly) the same slice, which is sized to stay resident in L2.
+struct DerivePartParams {
+    DeriveParams d;            // candidates, head, filters, set, outputs, counters (as for launch_derive)
+    u32 slice_bits;            // log2(slots per slice); partition = home slot >> slice_bits
+    u32 n_parts;               // set_slots >> slice_bits, <= 1024
+    u64* buckets;              // [n_parts][bucket_cap] candidate keys (s << 32 | o)
+    u32 bucket_cap;
+    u32* cursors;              // [n_parts] keys in each bucket (zeroed)
+    u32* tile_start;           // [n_parts + 1] first probe tile of each partition (written by the launch)
+    u32* tickets;              // [2] zeroed: tile counters of the two passes
+};
+void launch_derive_partitioned(const DerivePartParams& p, int n_sms, cudaStream_t st);
 void launch_set64_insert(u64* set, u32 set_slots, const u32* s, const u32* o, u32 n, u32* overflow, int n_sms, cudaStream_t st);
 void launch_set_insert(uint4* set, u32 set_slots, const u32* s, const u32* p /*null: p_const*/, u32 p_const, const u32* o, u32 n, u32* overflow,
                        int n_sms, cudaStream_t st);
