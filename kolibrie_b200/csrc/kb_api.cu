@@ -851,7 +851,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             if (rng == 0 || rng > std::max<u64>(8 * sl[k]->n, 1ull << 16) || rng > (1ull << 31)) ok = false;
             if (ctx->multi_valued.count({pats[k].p.value, key_pos(k)})) ok = false;
         }
-        if (ok && all_persistent && ctx->fast_index_kernel) {
+        if (ok && all_persistent && ctx->fast_index_kernel && sl[probe_k]->chunks.size() <= (size_t)PROBEI_MAXSEG) {
             // every build side is a persistent table: the whole join is one launch of probe_index_kernel
             const PredSlice& PS = *sl[probe_k];
             const u32 T = K - 1;
@@ -885,10 +885,9 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                     for (size_t i = 0; i < pv[probe_k].size(); i++) remap[pv[probe_k][i]] = psrc[probe_k][i] == 0 ? 0u : 1u;
                     std::vector<FilterOp> fo;
                     if (!append_prog(&fo, pf, remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
-                    const bool typed = PS.ynum && PS.ynum_version == ctx->num_version && fo.size() == 1 && fo[0].op == KB_F_CMP_NUM && fo[0].slot == 1u;
+                    const bool typed = PS.typed(ctx->num_version) && fo.size() == 1 && fo[0].op == KB_F_CMP_NUM && fo[0].slot == 1u;
                     if (typed) {
                         P.pre_mode = 1; P.pre_cmp = fo[0].cmp; P.pre_val = fo[0].value;
-                        P.ynum = static_cast<const double*>(PS.ynum->p);
                     } else {
                         P.pre_mode = 2; P.n_pre = (u32)fo.size();
                         for (size_t i = 0; i < fo.size(); i++) P.pre_ops[i] = fo[i];
@@ -905,10 +904,19 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 P.n_ops = (u32)fops.size();
                 for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
             }
-            P.pairs = reinterpret_cast<const uint2*>(PS.pairs.ptr);
+            P.n_seg = 0;
+            P.n_tiles = 0;
+            for (auto& ch : PS.chunks) {  // one chunk per store segment: an RSP window of slides is walked in ONE launch
+                if (ch.n == 0) continue;
+                ProbeISeg& g = P.seg[P.n_seg++];
+                g.pairs = reinterpret_cast<const uint2*>(ch.pairs.ptr);
+                g.ynum = P.pre_mode == 1u ? static_cast<const double*>(ch.ynum->p) : nullptr;
+                g.n = (u32)ch.n;
+                g.tile0 = P.n_tiles;
+                P.n_tiles += (u32)((ch.n + PROBEF_TILE - 1) / PROBEF_TILE);
+            }
             P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
             P.n = (u32)PS.n;
-            P.n_tiles = (u32)((PS.n + PROBEF_TILE - 1) / PROBEF_TILE);
             P.T = T;
             P.cap = (u32)PS.n;
             P.nt = numtab(ctx);
@@ -1020,6 +1028,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             *out = select_cols(*res, all_slots);
             return KB_OK;
         }
+        for (u32 k = 0; k < K && ok; k++) if (!sl[k]->single()) ok = false;  // the build-from-slice path reads one contiguous slice per pattern
         if (plan_only) return fail(ctx, KB_E_UNSUPPORTED, "prepared plans take the one-kernel index path only: every pattern (?s P ?o) over a predicate whose key column has a persistent table in the store index");
         if (ok) {
             const u32 range = (u32)rng;
@@ -1065,7 +1074,7 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                     u32* tab = static_cast<u32*>(tabs[bi]->p);
                     KB_CUDA(ctx, cudaMemsetAsync(tab, 0xFF, (size_t)range * sizeof(u32), bs));
                     BuildPairsParams B{};
-                    B.kv = reinterpret_cast<const uint2*>(sl[k]->pairs.ptr);
+                    B.kv = reinterpret_cast<const uint2*>(sl[k]->single()->pairs.ptr);
                     B.n = (u32)sl[k]->n;
                     B.key_is_y = key_pos(k) == 2 ? 1u : 0u;
                     B.pred = pats[k].p.value;
@@ -1116,9 +1125,9 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 if (!append_prog(&fo, pushdown[probe_k], remap)) return fail(ctx, KB_E_INVALID, "filter uses an unbound variable");
                 P.n_pre = (u32)fo.size();
                 for (size_t i = 0; i < fo.size(); i++) P.pre_ops[i] = fo[i];
-                if (sl[probe_k]->ynum && sl[probe_k]->ynum_version == ctx->num_version) P.pre_num = static_cast<const double*>(sl[probe_k]->ynum->p);
+                if (sl[probe_k]->typed(ctx->num_version)) P.pre_num = static_cast<const double*>(sl[probe_k]->single()->ynum->p);
             }
-            P.pairs = reinterpret_cast<const uint2*>(PS.pairs.ptr);
+            P.pairs = reinterpret_cast<const uint2*>(PS.single()->pairs.ptr);
             P.key_is_y = key_pos((u32)probe_k) == 2 ? 1u : 0u;
             P.n = (u32)PS.n;
             P.n_tiles = (u32)((PS.n + PROBEF_TILE - 1) / PROBEF_TILE);
@@ -1706,6 +1715,7 @@ kb_status kb_ctx_create(int device, kb_ctx** out) {
     if (const char* ui = getenv("KOLIBRIE_USE_INDEX")) ctx->use_index = ui[0] != '0';
     if (const char* fk = getenv("KOLIBRIE_INDEX_KERNEL")) ctx->fast_index_kernel = fk[0] != '0';
     if (const char* cj = getenv("KOLIBRIE_CSR_JOIN")) ctx->csr_join = cj[0] != '0';
+    if (const char* im = getenv("KOLIBRIE_INDEX_MAINTAIN")) ctx->index_maintain = im[0] != '0';
     if (const char* dp = getenv("KOLIBRIE_DERIVE_PART")) ctx->derive_part = dp[0] != '0';
     if (const char* ds = getenv("KOLIBRIE_DERIVE_SLICE")) ctx->derive_slice_bytes = std::max<u64>(64, strtoull(ds, nullptr, 10));
     if (const char* dk = getenv("KOLIBRIE_DERIVE_SLACK")) ctx->derive_bucket_slack = strtoull(dk, nullptr, 10);
@@ -1804,12 +1814,24 @@ static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, cons
                     std::chrono::duration<double, std::milli>(t1 - t0).count(),
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     }
+    const bool maintain = ctx->index_maintain && ctx->index_version == ctx->store_version && !ctx->index.empty();
     ctx->segs.push_back(sg);
     ctx->n_triples += n;
     ctx->store_version++;
     ctx->multi_valued.clear();
     ctx->single_valued.clear();
+    if (maintain) {
+        // the index stays alive across the mutation: the new segment becomes one more chunk of every predicate slice it touches and
+        // its keys are inserted into the persistent tables in place (an RSP window slide keeps the one-kernel index path)
+        bool indexable = true;
+        const kb_status rc = kb::index_add_segment(ctx, ctx->segs.size() - 1, &indexable);
+        if (rc == KB_OK && indexable) { ctx->index_version = ctx->store_version; return KB_OK; }
+        ctx->index.clear();
+        ctx->index_version = ~0ull;
+        return rc;
+    }
     ctx->index.clear();  // the predicate-partitioned index describes the previous store version
+    ctx->index_version = ~0ull;
     return KB_OK;
 }
 
@@ -1825,12 +1847,16 @@ kb_status kb_store_clear(kb_ctx* ctx) {
 }
 kb_status kb_store_load(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n) {
     KB_ENTER(ctx);
+    ctx->index.clear();
+    ctx->index_version = ~0ull;  // a reload replaces the store: nothing to maintain
     ctx->segs.clear();
     ctx->n_triples = 0;
     return store_add_segment(ctx, s, p, o, n, 0, cudaMemcpyHostToDevice);
 }
 kb_status kb_store_load_device(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n) {
     KB_ENTER(ctx);
+    ctx->index.clear();
+    ctx->index_version = ~0ull;  // a reload replaces the store: nothing to maintain
     ctx->segs.clear();
     ctx->n_triples = 0;
     return store_add_segment(ctx, s, p, o, n, 0, cudaMemcpyDeviceToDevice);
@@ -1849,10 +1875,12 @@ kb_status kb_store_evict(kb_ctx* ctx, uint64_t tag) {
             found = true;
         } else i++;
     }
+    const bool maintain = ctx->index_maintain && ctx->index_version == ctx->store_version && !ctx->index.empty();
     ctx->store_version++;
     ctx->multi_valued.clear();
     ctx->single_valued.clear();
-    ctx->index.clear();  // the predicate-partitioned index describes the previous store version
+    if (maintain && found && kb::index_evict_tag(ctx, tag) == KB_OK) ctx->index_version = ctx->store_version;
+    else { ctx->index.clear(); ctx->index_version = ~0ull; }
     return found ? KB_OK : kb::fail(ctx, KB_E_NOT_FOUND, "no segment with tag %llu", (unsigned long long)tag);
 }
 kb_status kb_set_use_index(kb_ctx* ctx, int enabled) {
@@ -1860,6 +1888,185 @@ kb_status kb_set_use_index(kb_ctx* ctx, int enabled) {
     ctx->use_index = enabled != 0;
     return KB_OK;
 }
+
+}  // extern "C"
+
+// ---- store index, one chunk per (predicate, store segment)
+namespace kb {
+// (re)build or extend the persistent table of one column of a slice after `added` (index into ps.chunks; -1: all chunks) arrived.
+// flag_word: control word the insert kernels raise on a duplicate key. Returns through *touched whether a flag has to be read.
+static kb_status slice_table_update(kb_ctx* ctx, PredSlice& ps, u32 y, int added, u32 cshift, u32 flag_off, bool* touched) {
+    Buf& tab = y ? ps.ytab : ps.xtab;
+    u32& tmin = y ? ps.ytab_min : ps.xtab_min;
+    u32& tcap = y ? ps.ytab_range : ps.xtab_range;
+    bool& tried = y ? ps.y_tried : ps.x_tried;
+    bool& unique = y ? ps.y_unique : ps.x_unique;
+    *touched = false;
+    if (tried && !tab) return KB_OK;  // the column was found multi-valued or too sparse: no table, nothing to maintain
+    const u32 cs = y ? 0u : cshift;    // only subjects are sharded
+    const u32 lo = compact_key(y ? ps.ymin : ps.xmin, cs), hi = compact_key(y ? ps.ymax : ps.xmax, cs);
+    const u64 range = (u64)hi - lo + 1;
+    const bool fits = tab && lo >= tmin && (u64)hi < (u64)tmin + tcap && (y || ps.tab_cshift == cshift);
+    if (!fits) {
+        // (re)build over every chunk, with headroom above the largest key: dictionary ids grow, so appended segments bring larger ones
+        tab.reset();
+        tried = true;
+        unique = false;
+        if (range > std::max<u64>(4 * ps.n + 65536, 1ull << 16) || range > (1ull << 28)) return KB_OK;  // not dense: keep no table
+        const u64 cap = std::min<u64>(range + range / 2 + 65536, 1ull << 29);
+        KB_TRY(alloc_buf(ctx, cap * sizeof(u32), &tab));
+        KB_CUDA(ctx, cudaMemsetAsync(tab->p, 0xFF, cap * sizeof(u32), ctx->st));
+        tmin = lo;
+        tcap = (u32)cap;
+        if (!y) ps.tab_cshift = cshift;
+        added = -1;
+        unique = true;  // until a flag says otherwise
+    }
+    for (size_t c = 0; c < ps.chunks.size(); c++) {
+        if (added >= 0 && (int)c != added) continue;
+        const SliceChunk& ch = ps.chunks[c];
+        if (!ch.n) continue;
+        launch_build_direct_pairs(reinterpret_cast<const uint2*>(ch.pairs.ptr), y, (u32)ch.n, static_cast<u32*>(tab->p), tmin, tcap, cs, ctx->ctrl + flag_off, 0u,
+                                  ctx->n_sms, ctx->st);
+        ctx->stats.kernel_launches++;
+        *touched = true;
+    }
+    return KB_OK;
+}
+
+// index the triples of ONE store segment: a chunk per predicate it carries, ranges, persistent tables, typed literal columns
+kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable) {
+    *indexable = true;
+    Segment sg = ctx->segs[seg_idx];
+    if (sg.n == 0) return KB_OK;
+    // 1. distinct predicates of the segment
+    const u32 set_slots = 8192;
+    Buf set;
+    KB_TRY(alloc_buf(ctx, set_slots * sizeof(u32), &set));
+    KB_CUDA(ctx, cudaMemsetAsync(set->p, 0xFF, set_slots * sizeof(u32), ctx->st));
+    const u32 off = ctrl_alloc(ctx, 4);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, 4 * sizeof(u32), ctx->st));
+    timer_begin(ctx, F_OTHER);
+    launch_distinct(sg.p.ptr, (u32)sg.n, static_cast<u32*>(set->p), set_slots, ctx->ctrl + off, ctx->n_sms, ctx->st);
+    timer_end(ctx);
+    std::vector<u32> hset(set_slots);
+    KB_CUDA(ctx, cudaMemcpyAsync(hset.data(), set->p, set_slots * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+    KB_TRY(ctrl_read(ctx));
+    std::vector<u32> preds;
+    for (u32 v : hset) if (v != EMPTY32) preds.push_back(v);
+    std::sort(preds.begin(), preds.end());
+    {
+        std::set<u32> all(preds.begin(), preds.end());
+        for (auto& kv : ctx->index) all.insert(kv.first);
+        if (ctx->h_ctrl[off] || all.size() > 4096) { *indexable = false; return KB_OK; }  // too many predicates: keep scanning
+    }
+    if (!sg.has_stats || sg.stats_world != ctx->shard_world) { KB_TRY(segment_stats(ctx, &ctx->segs[seg_idx])); sg = ctx->segs[seg_idx]; }
+    u32 cshift = 0;  // subject-sharded store: compact the subject keys (see compact_key)
+    {
+        bool sharded = ctx->shard_world > 1 && (ctx->shard_world & (ctx->shard_world - 1)) == 0;
+        for (auto& g : ctx->segs) if (g.n && g.has_stats && !g.sharded_ok) sharded = false;
+        if (sharded) while ((1u << cshift) < ctx->shard_world) cshift++;
+    }
+    // 2. one fused scan of THIS segment per 8 predicates, pair output, shrunk to a chunk; id ranges of both halves
+    std::vector<Segment> one{sg}, saved;
+    const u64 saved_n = ctx->n_triples;
+    for (size_t b = 0; b < preds.size(); b += MAXP) {
+        const u32 k = (u32)std::min<size_t>(MAXP, preds.size() - b);
+        kb_pattern pats[MAXP];
+        for (u32 i = 0; i < k; i++) { pats[i].s = kb_term{1, 0}; pats[i].p = kb_term{0, preds[b + i]}; pats[i].o = kb_term{1, 1}; }
+        std::vector<std::unique_ptr<kb_rel>> rels;
+        std::vector<FilterProg> none;
+        ctx->segs.swap(one);
+        ctx->n_triples = sg.n;
+        const kb_status rc = scan_impl(ctx, pats, k, none, false, true, &rels);
+        ctx->segs.swap(one);
+        ctx->n_triples = saved_n;
+        if (rc != KB_OK) return rc;
+        const u32 soff = ctrl_alloc(ctx, 4 * MAXP);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff, 0, 4 * MAXP * sizeof(u32), ctx->st));
+        for (u32 i = 0; i < k; i++) KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff + 4 * i, 0xFF, 2 * sizeof(u32), ctx->st));
+        std::vector<int> chunk_of(k, -1);
+        for (u32 i = 0; i < k; i++) {
+            if (rels[i]->n == 0) continue;
+            PredSlice& ps = ctx->index[preds[b + i]];
+            SliceChunk ch;
+            ch.tag = sg.tag;
+            ch.n = rels[i]->n;
+            KB_TRY(alloc_col(ctx, 2 * ch.n, &ch.pairs));
+            KB_CUDA(ctx, cudaMemcpyAsync(ch.pairs.ptr, rels[i]->cols[0].ptr, ch.n * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->st));
+            launch_pair_minmax(reinterpret_cast<const uint2*>(ch.pairs.ptr), (u32)ch.n, ctx->ctrl + soff + 4 * i, ctx->n_sms, ctx->st);
+            ctx->stats.kernel_launches++;
+            chunk_of[i] = (int)ps.chunks.size();
+            ps.chunks.push_back(ch);
+            ps.n += ch.n;
+        }
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(ctrl_read(ctx));
+        // 3. persistent tables (inserted in place; a duplicate key or a key outside the table ends / rebuilds it) and the typed literal
+        //    column of the new chunk: the f64 value of every object, so that FILTER(?o <cmp> c) reads it sequentially instead of
+        //    gathering num_or0[object] at random
+        const u32 uoff = ctrl_alloc(ctx, 2 * MAXP);
+        const u32 noff = ctrl_alloc(ctx, MAXP);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + uoff, 0, 2 * MAXP * sizeof(u32), ctx->st));
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + noff, 0, MAXP * sizeof(u32), ctx->st));
+        std::vector<char> touched(2 * k, 0);
+        for (u32 i = 0; i < k; i++) {
+            if (chunk_of[i] < 0) continue;
+            PredSlice& ps = ctx->index[preds[b + i]];
+            ps.xmin = std::min(ps.xmin, ctx->h_ctrl[soff + 4 * i]); ps.ymin = std::min(ps.ymin, ctx->h_ctrl[soff + 4 * i + 1]);
+            ps.xmax = std::max(ps.xmax, ctx->h_ctrl[soff + 4 * i + 2]); ps.ymax = std::max(ps.ymax, ctx->h_ctrl[soff + 4 * i + 3]);
+            for (u32 y = 0; y < 2; y++) {
+                bool t = false;
+                KB_TRY(slice_table_update(ctx, ps, y, chunk_of[i], cshift, uoff + 2 * i + y, &t));
+                touched[2 * i + y] = t ? 1 : 0;
+            }
+            if (ctx->n_ids) {
+                SliceChunk& ch = ps.chunks[chunk_of[i]];
+                KB_TRY(alloc_buf(ctx, ch.n * sizeof(double), &ch.ynum));
+                launch_pair_numcol(reinterpret_cast<const uint2*>(ch.pairs.ptr), (u32)ch.n, numtab(ctx), static_cast<double*>(ch.ynum->p), ctx->ctrl + noff + i,
+                                   ctx->n_sms, ctx->st);
+                ctx->stats.kernel_launches++;
+            }
+        }
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(ctrl_read(ctx));
+        for (u32 i = 0; i < k; i++) {
+            if (chunk_of[i] < 0) continue;
+            PredSlice& ps = ctx->index[preds[b + i]];
+            SliceChunk& ch = ps.chunks[chunk_of[i]];
+            if (ch.ynum && ctx->h_ctrl[noff + i] > 0) ch.ynum_version = ctx->num_version;
+            else ch.ynum.reset();
+            if (touched[2 * i] && ctx->h_ctrl[uoff + 2 * i]) { ps.x_unique = false; ps.xtab.reset(); }      // a subject occurs twice
+            if (touched[2 * i + 1] && ctx->h_ctrl[uoff + 2 * i + 1]) { ps.y_unique = false; ps.ytab.reset(); }
+        }
+    }
+    return KB_OK;
+}
+
+// eviction of the segment(s) tagged `tag`: their chunks leave the slices, their keys leave the persistent tables
+kb_status index_evict_tag(kb_ctx* ctx, u64 tag) {
+    for (auto it = ctx->index.begin(); it != ctx->index.end();) {
+        PredSlice& ps = it->second;
+        for (size_t c = 0; c < ps.chunks.size();) {
+            SliceChunk& ch = ps.chunks[c];
+            if (ch.tag != tag) { c++; continue; }
+            if (ps.xtab) launch_clear_direct_pairs(reinterpret_cast<const uint2*>(ch.pairs.ptr), 0u, (u32)ch.n, static_cast<u32*>(ps.xtab->p), ps.xtab_min, ps.xtab_range,
+                                                   ps.tab_cshift, ctx->n_sms, ctx->st);
+            if (ps.ytab) launch_clear_direct_pairs(reinterpret_cast<const uint2*>(ch.pairs.ptr), 1u, (u32)ch.n, static_cast<u32*>(ps.ytab->p), ps.ytab_min, ps.ytab_range, 0u,
+                                                   ctx->n_sms, ctx->st);
+            ctx->stats.kernel_launches += (ps.xtab ? 1 : 0) + (ps.ytab ? 1 : 0);
+            ps.n -= ch.n;
+            ps.chunks.erase(ps.chunks.begin() + c);  // the chunk's buffers are released stream-ordered, after the clears above
+        }
+        if (ps.chunks.empty()) it = ctx->index.erase(it);
+        else ++it;
+    }
+    KB_CUDA(ctx, cudaGetLastError());
+    return KB_OK;
+}
+}  // namespace kb
+
+extern "C" {
 
 kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* build_ms) {
     KB_ENTER(ctx);
@@ -1870,113 +2077,22 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
     if (ctx->n_triples == 0) return KB_OK;
     kb::ScopedEvent e0, e1;
     cudaEventRecord(e0, ctx->st);
-    // 1. distinct predicates
-    const u32 set_slots = 8192;
-    kb::Buf set;
-    KB_TRY(kb::alloc_buf(ctx, set_slots * sizeof(u32), &set));
-    KB_CUDA(ctx, cudaMemsetAsync(set->p, 0xFF, set_slots * sizeof(u32), ctx->st));
-    const u32 off = kb::ctrl_alloc(ctx, 4);
-    kb::timer_begin(ctx, kb::F_OTHER, (int)ctx->segs.size());
-    for (auto& sg : ctx->segs) kb::launch_distinct(sg.p.ptr, (u32)sg.n, static_cast<u32*>(set->p), set_slots, ctx->ctrl + off, ctx->n_sms, ctx->st);
-    kb::timer_end(ctx);
-    std::vector<u32> hset(set_slots);
-    KB_CUDA(ctx, cudaMemcpyAsync(hset.data(), set->p, set_slots * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
-    KB_TRY(kb::ctrl_read(ctx));
-    std::vector<u32> preds;
-    for (u32 v : hset) if (v != kb::EMPTY32) preds.push_back(v);
-    std::sort(preds.begin(), preds.end());
-    if (ctx->h_ctrl[off] || preds.size() > 4096) return KB_OK;  // too many predicates: keep scanning
-    // 2. one fused scan per 8 predicates, pair output, then shrink each slice to its size and take its id ranges
-    for (size_t b = 0; b < preds.size(); b += kb::MAXP) {
-        const u32 k = (u32)std::min<size_t>(kb::MAXP, preds.size() - b);
-        kb_pattern pats[kb::MAXP];
-        for (u32 i = 0; i < k; i++) { pats[i].s = kb_term{1, 0}; pats[i].p = kb_term{0, preds[b + i]}; pats[i].o = kb_term{1, 1}; }
-        std::vector<std::unique_ptr<kb_rel>> rels;
-        std::vector<kb::FilterProg> none;
-        KB_TRY(kb::scan_impl(ctx, pats, k, none, false, true, &rels));
-        const u32 soff = kb::ctrl_alloc(ctx, 4 * kb::MAXP);
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff, 0, 4 * kb::MAXP * sizeof(u32), ctx->st));
-        for (u32 i = 0; i < k; i++) KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + soff + 4 * i, 0xFF, 2 * sizeof(u32), ctx->st));
-        for (u32 i = 0; i < k; i++) {
-            kb::PredSlice ps;
-            ps.n = rels[i]->n;
-            KB_TRY(kb::alloc_col(ctx, 2 * ps.n, &ps.pairs));
-            if (ps.n) KB_CUDA(ctx, cudaMemcpyAsync(ps.pairs.ptr, rels[i]->cols[0].ptr, ps.n * sizeof(uint2), cudaMemcpyDeviceToDevice, ctx->st));
-            kb::launch_pair_minmax(reinterpret_cast<const uint2*>(ps.pairs.ptr), (u32)ps.n, ctx->ctrl + soff + 4 * i, ctx->n_sms, ctx->st);
-            ctx->stats.kernel_launches++;
-            ctx->index[preds[b + i]] = ps;
-        }
-        KB_CUDA(ctx, cudaGetLastError());
-        KB_TRY(kb::ctrl_read(ctx));
-        for (u32 i = 0; i < k; i++) {
-            kb::PredSlice& ps = ctx->index[preds[b + i]];
-            ps.xmin = ctx->h_ctrl[soff + 4 * i]; ps.ymin = ctx->h_ctrl[soff + 4 * i + 1];
-            ps.xmax = ctx->h_ctrl[soff + 4 * i + 2]; ps.ymax = ctx->h_ctrl[soff + 4 * i + 3];
-        }
-        // 3. key uniqueness per slice and position (one trial direct build each): joins keyed on a unique column skip duplicate detection
-        const u32 uoff = kb::ctrl_alloc(ctx, 2 * kb::MAXP);
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + uoff, 0, 2 * kb::MAXP * sizeof(u32), ctx->st));
-        std::vector<int> tried(2 * k, 0);
-        u32 cshift = 0;  // subject-sharded store: compact the subject keys (see compact_key)
-        {
-            bool sharded = ctx->shard_world > 1 && (ctx->shard_world & (ctx->shard_world - 1)) == 0;
-            for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world)) KB_TRY(kb::segment_stats(ctx, &sg));
-            for (auto& sg : ctx->segs) if (sg.n && !sg.sharded_ok) sharded = false;
-            if (sharded) while ((1u << cshift) < ctx->shard_world) cshift++;
-        }
-        for (u32 i = 0; i < k; i++) {
-            kb::PredSlice& ps = ctx->index[preds[b + i]];
-            if (ps.n == 0) continue;
-            ps.tab_cshift = cshift;
-            for (u32 y = 0; y < 2; y++) {
-                const u32 cs = y ? 0u : cshift;  // only subjects are sharded
-                const u32 lo = kb::compact_key(y ? ps.ymin : ps.xmin, cs), hi = kb::compact_key(y ? ps.ymax : ps.xmax, cs);
-                const u64 range = (u64)hi - lo + 1;
-                if (range > std::max<u64>(8 * ps.n, 1ull << 16) || range > (1ull << 28)) continue;
-                kb::Buf tab;
-                KB_TRY(kb::alloc_buf(ctx, range * sizeof(u32), &tab));
-                KB_CUDA(ctx, cudaMemsetAsync(tab->p, 0xFF, range * sizeof(u32), ctx->st));
-                kb::launch_build_direct_pairs(reinterpret_cast<const uint2*>(ps.pairs.ptr), y, (u32)ps.n, static_cast<u32*>(tab->p), lo, (u32)range, cs,
-                                              ctx->ctrl + uoff + 2 * i + y, 0u, ctx->n_sms, ctx->st);
-                ctx->stats.kernel_launches++;
-                tried[2 * i + y] = 1;
-                if (y) { ps.ytab = tab; ps.ytab_min = lo; ps.ytab_range = (u32)range; }
-                else { ps.xtab = tab; ps.xtab_min = lo; ps.xtab_range = (u32)range; }
-            }
-        }
-        KB_CUDA(ctx, cudaGetLastError());
-        KB_TRY(kb::ctrl_read(ctx));
-        // 4. typed literal column: the f64 value of every object, for slices that have numeric objects at all (FILTER(?o <cmp> c) then
-        //    reads it sequentially instead of gathering num_or0[object] at random)
-        std::vector<kb::Buf> ynum(k);
-        const u32 noff = kb::ctrl_alloc(ctx, kb::MAXP);
-        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + noff, 0, kb::MAXP * sizeof(u32), ctx->st));
-        if (ctx->n_ids) for (u32 i = 0; i < k; i++) {
-            kb::PredSlice& ps = ctx->index[preds[b + i]];
-            if (ps.n == 0) continue;
-            KB_TRY(kb::alloc_buf(ctx, ps.n * sizeof(double), &ynum[i]));
-            kb::launch_pair_numcol(reinterpret_cast<const uint2*>(ps.pairs.ptr), (u32)ps.n, kb::numtab(ctx), static_cast<double*>(ynum[i]->p), ctx->ctrl + noff + i,
-                                   ctx->n_sms, ctx->st);
-            ctx->stats.kernel_launches++;
-        }
-        KB_CUDA(ctx, cudaGetLastError());
-        KB_TRY(kb::ctrl_read(ctx));
-        for (u32 i = 0; i < k; i++) {
-            kb::PredSlice& ps = ctx->index[preds[b + i]];
-            if (ynum[i] && ctx->h_ctrl[noff + i] > 0) { ps.ynum = ynum[i]; ps.ynum_version = ctx->num_version; }
-            ps.x_unique = tried[2 * i] && ctx->h_ctrl[uoff + 2 * i] == 0;
-            ps.y_unique = tried[2 * i + 1] && ctx->h_ctrl[uoff + 2 * i + 1] == 0;
-            if (!ps.x_unique || ps.xtab_range > 4 * ps.n + 65536) ps.xtab.reset();  // keep only tables of unique, dense columns
-            if (!ps.y_unique || ps.ytab_range > 4 * ps.n + 65536) ps.ytab.reset();
+    for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world)) KB_TRY(kb::segment_stats(ctx, &sg));
+    for (size_t g = 0; g < ctx->segs.size(); g++) {
+        bool indexable = true;
+        const kb_status rc = kb::index_add_segment(ctx, g, &indexable);
+        if (rc != KB_OK || !indexable) {
+            ctx->index.clear();
+            if (rc != KB_OK) return rc;
+            return KB_OK;  // too many predicates: keep scanning (n_predicates = 0)
         }
     }
-    for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world)) KB_TRY(kb::segment_stats(ctx, &sg));
     cudaEventRecord(e1, ctx->st);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     ctx->index_version = ctx->store_version;
-    if (n_predicates) *n_predicates = (uint32_t)preds.size();
+    if (n_predicates) *n_predicates = (uint32_t)ctx->index.size();
     if (build_ms) *build_ms = ms;
     return KB_OK;
 }

@@ -93,19 +93,33 @@ struct Segment {
 }  // namespace kb
 
 namespace kb {
-struct PredSlice {  // one predicate's (subject, object) rows of the store, interleaved — the device analogue of pos[P] (index_manager.rs:18-26)
+struct SliceChunk {  // the rows of ONE store segment that carry the predicate: interleaved (subject, object)
+    u64 tag = 0;           // the segment's tag (kb_store_append): evicting the segment drops the chunk
     Col pairs;
     u64 n = 0;
-    u32 xmin = 0xFFFFFFFFu, xmax = 0, ymin = 0xFFFFFFFFu, ymax = 0;  // id range of subjects (x) and objects (y)
-    // persistent direct tables built with the index when the column is unique and dense: xtab[subject - xtab_min] = object (what
-    // the reference's spo[s][P] lookup answers, index_manager.rs:18-26) and ytab[object - ytab_min] = subject (pos[P][o])
+    Buf ynum;              // typed literal column: f64 value of every object (num_or0), kept when the chunk has numeric objects
+    u64 ynum_version = 0;  // numeric side table version it was built from
+};
+struct PredSlice {  // one predicate's (subject, object) rows of the store — the device analogue of pos[P] (index_manager.rs:18-26) — as one
+                    // chunk per store segment, so that an RSP window slide (append one segment, evict another) maintains the index
+                    // instead of dropping it (rsp_engine.rs:94-104; simple_r2r.rs:95-142)
+    std::vector<SliceChunk> chunks;
+    u64 n = 0;  // rows over all chunks
+    u32 xmin = 0xFFFFFFFFu, xmax = 0, ymin = 0xFFFFFFFFu, ymax = 0;  // id range of subjects (x) and objects (y); never shrunk by evictions
+    // persistent direct tables kept while the column is unique and dense: xtab[subject - xtab_min] = object (what the reference's
+    // spo[s][P] lookup answers, index_manager.rs:18-26) and ytab[object - ytab_min] = subject (pos[P][o]). *_range is the table's
+    // CAPACITY in slots: it is allocated with headroom above the largest key (dictionary ids grow), appended chunks are inserted in
+    // place, evicted chunks are cleared in place, and the table is rebuilt only when a key falls outside it.
     Buf xtab, ytab;
     u32 xtab_min = 0, xtab_range = 0, ytab_min = 0, ytab_range = 0, tab_cshift = 0;
-    Buf ynum;  // typed literal column: f64 value of every object (num_or0), kept when the slice has numeric objects; valid for the
-               // numeric side table version it was built from (ynum_version)
-    u64 ynum_version = 0;
-    bool x_unique = false, y_unique = false;  // verified at index build: no subject (object) occurs twice -> builds keyed on it need no
-                                              // duplicate detection (functional / inverse-functional predicate in this store)
+    bool x_unique = false, y_unique = false;  // no subject (object) occurs twice -> builds keyed on it need no duplicate detection
+                                              // (functional / inverse-functional predicate in this store)
+    bool x_tried = false, y_tried = false;    // a table for the column was attempted (false: never dense enough)
+    const SliceChunk* single() const { return chunks.size() == 1 ? &chunks[0] : nullptr; }
+    bool typed(u64 num_version) const {
+        for (auto& c : chunks) if (!c.ynum || c.ynum_version != num_version) return false;
+        return !chunks.empty();
+    }
 };
 }  // namespace kb
 
@@ -167,6 +181,7 @@ struct kb_ctx {
     kb::u64 derive_bucket_slack = 8192;  // KOLIBRIE_DERIVE_SLACK: rows a bucket holds beyond 9/8 of its fair share
     bool fast_index_kernel = true;       // KOLIBRIE_INDEX_KERNEL=0: index joins go through the generic probe kernel (A/B switch)
     bool use_index = true;               // KOLIBRIE_USE_INDEX=0 / kb_set_use_index: force the scanning path
+    bool index_maintain = true;          // KOLIBRIE_INDEX_MAINTAIN=0: append / evict drop the index instead of maintaining it (A/B switch)
     kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject
     int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges
 };
@@ -254,6 +269,8 @@ void groups_from_host_table(const char* hb, const GroupTable& t, u32 n_group, co
 // the same from a dense record list (launch_group_compact)
 void groups_from_records(const GroupRecord* recs, u64 n, u32 n_group, const kb_agg* aggs, u32 n_aggs, kb_groups* g);
 kb_status segment_stats(kb_ctx* ctx, Segment* sg);
+kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable);
+kb_status index_evict_tag(kb_ctx* ctx, u64 tag);
 kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r);
 kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);
 kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const FilterProg* post, std::unique_ptr<kb_rel>* out);

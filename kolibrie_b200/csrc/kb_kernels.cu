@@ -756,6 +756,20 @@ __global__ void __launch_bounds__(256) count_nonempty_kernel(const uint4* __rest
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
+__global__ void __launch_bounds__(256) clear_direct_pairs_kernel(const uint2* __restrict__ kv, u32 key_is_y, u32 n, u32* __restrict__ table, u32 kmin, u32 range,
+                                                                 u32 cshift) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 v = kv[i];
+        const u32 off = compact_key(key_is_y ? v.y : v.x, cshift) - kmin;
+        if (off < range) table[off] = EMPTY32;
+    }
+}
+void launch_clear_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32 cshift, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    clear_direct_pairs_kernel<<<grid, 256, 0, st>>>(kv, key_is_y, n, table, kmin, range, cshift);
+}
 void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, cudaStream_t st) {
     if (n == 0) return;
     const u32 n4 = n / 4;
@@ -1015,15 +1029,20 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
             a_val[i] = P.akind == KB_AGG_MIN ? CUDART_INF : (P.akind == KB_AGG_MAX ? -CUDART_INF : 0.0);
         }
     }
+    __shared__ u32 s_tcnt[2];  // rows in the staged tile
     auto issue = [&](u32 t, u32 stage) {
         u32* smem = smem_all + stage * STAGE_WORDS;
         u64& bar = bars[stage];
-        const u32 b = t * TILE;
-        const u32 c = min(TILE, P.n - b);
+        u32 g = 0;  // the chunk (store segment) this tile belongs to
+        while (g + 1u < P.n_seg && t >= P.seg[g + 1u].tile0) g++;
+        const ProbeISeg& sg = P.seg[g];
+        const u32 b = (t - sg.tile0) * TILE;
+        const u32 c = min(TILE, sg.n - b);
         const u32 bytes = (c * 8u + 15u) & ~15u;
+        s_tcnt[stage] = c;
         mbar_arrive_expect_tx(&bar, PRE == 1 ? 2u * bytes : bytes);
-        tma_load_1d(smem, P.pairs + b, bytes, &bar);
-        if (PRE == 1) tma_load_1d(smem + 2 * TILE, P.ynum + b, bytes, &bar);
+        tma_load_1d(smem, sg.pairs + b, bytes, &bar);
+        if (PRE == 1) tma_load_1d(smem + 2 * TILE, sg.ynum + b, bytes, &bar);
     };
     // two shared stages: tile i+1 is in flight while tile i is processed, and the stage of tile i is refilled (tile i+2) right after
     // the first compaction barrier — by then every thread has its rows in registers, so no barrier is spent on the hand-over
@@ -1043,9 +1062,8 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
     while (tile < P.n_tiles) {
         const u32 stage = it & 1u;
         const u32* smem = smem_all + stage * STAGE_WORDS;
-        const u32 base = tile * TILE;
-        const u32 cnt = min(TILE, P.n - base);
         mbar_wait(&bars[stage], (it >> 1) & 1u);
+        const u32 cnt = s_tcnt[stage];
         u32 rx[R], ry[R];
         double pa[R];
         // striped: row j of this thread is row (warp*128 + j*32 + lane) of the tile, so one warp instruction touches 32 CONSECUTIVE

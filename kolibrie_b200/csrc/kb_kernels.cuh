@@ -161,10 +161,16 @@ void launch_probe_fast(const ProbeFParams& p, int n_sms, cudaStream_t st);
 // Output layout is fixed: column 0 = x, 1 = y, 2+t = value found in table t. The launch owns a 4-word control block
 // {ticket, total, zero, done} that the last CTA to finish resets to zero after publishing the row count to pinned host memory: a
 // query is ONE device operation (no memset before, no copy after).
-struct ProbeIParams {
+constexpr int PROBEI_MAXSEG = 16;  // chunks of the probe slice one launch can walk (one per store segment: an RSP window of slides)
+struct ProbeISeg {
     const uint2* pairs;
-    const double* ynum;  // typed literal column of the slice (non-null iff pre_mode == 1)
-    u32 key_is_y, n, n_tiles, T;
+    const double* ynum;  // typed literal column of the chunk (non-null iff pre_mode == 1)
+    u32 n, tile0;        // rows; first tile of this chunk in the launch's tile numbering
+};
+struct ProbeIParams {
+    ProbeISeg seg[PROBEI_MAXSEG];
+    u32 n_seg;
+    u32 key_is_y, n, n_tiles, T;  // n = rows over all chunks
     DirectTab tab[MAXT];
     u32* out[2 + MAXT];
     u32 cap;
@@ -210,6 +216,8 @@ void launch_pair_numcol(const uint2* kv, u32 n, NumTab nt, double* out, u32* n_n
 void launch_pair_minmax(const uint2* kv, u32 n, u32* out4, int n_sms, cudaStream_t st);
 // number of occupied (non-EMPTY32) slots of a direct table: equals the number of inserted rows iff the keys were single-valued
 void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, cudaStream_t st);
+// eviction of a chunk: the table entries of its keys go back to EMPTY32 (keys are unique while a persistent table exists)
+void launch_clear_direct_pairs(const uint2* kv, u32 key_is_y, u32 n, u32* table, u32 kmin, u32 range, u32 cshift, int n_sms, cudaStream_t st);
 // number of keys that do NOT belong to shard `rank` of `world` (kb_shard_of): 0 for a correctly sharded column
 void launch_count_foreign(const u32* col, u32 n, u32 rank, u32 world, u32* out, int n_sms, cudaStream_t st);
 void launch_col_minmax(const u32* col, u32 n, u32* out_min, u32* out_max, int n_sms, cudaStream_t st);

@@ -57,3 +57,55 @@ def test_window_with_reasoning(ctx):
         q = ctx.scan([c.pattern(c.V(0), c.K(t.ids["rdf:type"]), c.V(1))])[0]
         assert q.n_rows == step + int((want["facts"][:, 1] == t.ids["rdf:type"]).sum())
         ctx.store_evict(c.KB_TAG_INFERRED)  # next firing re-materialises from scratch (simple_r2r.rs:103-128)
+
+
+@pytest.mark.parametrize("q", ["cfg2", "cfg3", "star3"])
+def test_window_slides_keep_the_index_path(ctx, q):
+    """the store index is MAINTAINED across kb_store_append / kb_store_evict (one chunk per segment in every predicate slice, keys
+    inserted into / cleared from the persistent tables in place): after every slide the star join still takes the one-kernel index
+    path and still returns the oracle's rows for the live window; replays simple_r2r.rs:95-142 / rsp_engine.rs:94-104"""
+    d = datagen.employee_dataset(14000)
+    js, pats, filt = datagen.employee_queries(d)[q]
+    ctx.dict_numeric_load(d.num_or0, d.is_num)
+    ctx.store_clear()
+    n_slides, width = 14, 5
+    per = d.n_triples // n_slides // 6 * 6
+    live = []
+    # the window is built up from an indexed first slide; every later slide is an append (+ an eviction once the window is full)
+    for t in range(n_slides):
+        lo, hi = t * per, (t + 1) * per
+        if len(live) == width:
+            ctx.store_evict(live.pop(0))
+        ctx.store_append(d.s[lo:hi], d.p[lo:hi], d.o[lo:hi], tag=500 + t)
+        live.append(500 + t)
+        if t == 0:
+            ctx.build_index()  # SparqlDatabase::build_all_indexes once; never again
+        a, b = (t - len(live) + 1) * per, hi
+        n0 = ctx.get_stats()["index_joins"]
+        got = ctx.star_join(js, pats, filt)
+        assert ctx.get_stats()["index_joins"] == n0 + 1, f"slide {t}: the query left the index path"
+        want = O.Db(d.s[a:b], d.p[a:b], d.o[a:b], d.num_or0, d.is_num).bgp(pats, filt)
+        H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"slide {t}")
+        # the fused GROUP BY and a prepared plan see the maintained index too
+        if t in (3, 9):
+            g, n_rows = ctx.star_join_aggregate(js, pats, filt, [1], [(c.AGG_COUNT, 0)])
+            assert n_rows == want.n_rows and int(g["counts"].sum()) == want.n_rows
+            plan = ctx.prepare_star_join(js, pats, filt, ring=2)
+            assert plan.collect(plan.submit()) == want.n_rows
+            plan.free()
+    # a subject that re-appears in a later segment makes its predicates multi-valued: the tables go, the answers stay right
+    ctx.store_append(d.s[a:a + 600], d.p[a:a + 600], d.o[a:a + 600], tag=999)
+    got = ctx.star_join(js, pats, filt)
+    s2 = np.concatenate([d.s[a:b], d.s[a:a + 600]]); p2 = np.concatenate([d.p[a:b], d.p[a:a + 600]]); o2 = np.concatenate([d.o[a:b], d.o[a:a + 600]])
+    want = O.Db(s2, p2, o2, d.num_or0, d.is_num).bgp(pats, filt)
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), "duplicate subjects across segments")
+    # evicting the duplicate segment leaves a correct (if table-less) index; a rebuild restores the fast path
+    ctx.store_evict(999)
+    got = ctx.star_join(js, pats, filt)
+    want = O.Db(d.s[a:b], d.p[a:b], d.o[a:b], d.num_or0, d.is_num).bgp(pats, filt)
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), "after evicting the duplicates")
+    ctx.build_index()
+    n0 = ctx.get_stats()["index_joins"]
+    got = ctx.star_join(js, pats, filt)
+    assert ctx.get_stats()["index_joins"] == n0 + 1
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), "after the rebuild")
