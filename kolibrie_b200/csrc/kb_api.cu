@@ -318,9 +318,134 @@ kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r) {
     return KB_OK;
 }
 
+// IndexScan proper (engine.rs:1192-1407, the 8-case lookup of index_manager.rs:253-340 for a constant predicate): with a valid store
+// index a pattern whose predicate is constant is answered from the predicate's slice — (c P ?o) from the subject table / directory,
+// (?s P c) from the object table / directory, (?s P ?o) is the slice itself — without touching the 12-byte/triple store.
+// *out stays null when the index cannot answer the pattern (the caller scans).
+static kb_status index_lookup(kb_ctx* ctx, const kb_pattern& pt, std::unique_ptr<kb_rel>* out) {
+    out->reset();
+    if (!ctx->use_index || ctx->index_version != ctx->store_version || pt.p.is_var) return KB_OK;
+    std::vector<u32> slots, src;
+    pattern_vars(pt, &slots, &src);
+    auto it = ctx->index.find(pt.p.value);
+    auto rel = std::make_unique<kb_rel>();
+    rel->slots = slots;
+    if (it == ctx->index.end() || it->second.n == 0) {  // the predicate does not occur: empty answer
+        for (size_t c = 0; c < slots.size(); c++) { Col col; KB_TRY(alloc_col(ctx, 0, &col)); rel->cols.push_back(col); }
+        *out = std::move(rel);
+        return KB_OK;
+    }
+    const PredSlice& ps = it->second;
+    if (pt.s.is_var && pt.o.is_var) {
+        if (pt.s.value == pt.o.value) return KB_OK;  // ?x P ?x: the scan enforces the equality
+        Col x, y;  // the slice itself, de-interleaved (all chunks)
+        KB_TRY(alloc_col(ctx, ps.n, &x));
+        KB_TRY(alloc_col(ctx, ps.n, &y));
+        u64 at = 0;
+        timer_begin(ctx, F_SCAN, (int)ps.chunks.size());
+        for (auto& ch : ps.chunks) {
+            // (chunk boundaries keep 16-byte alignment only by luck: unpair writes element-wise, no TMA on the output side)
+            launch_unpair(reinterpret_cast<const uint2*>(ch.pairs.ptr), (u32)ch.n, x.ptr + at, y.ptr + at, ctx->st);
+            at += ch.n;
+        }
+        timer_end(ctx);
+        KB_CUDA(ctx, cudaGetLastError());
+        rel->cols = {x, y};
+        rel->n = ps.n;
+        ctx->stats.index_joins++;
+        *out = std::move(rel);
+        return KB_OK;
+    }
+    if (pt.s.is_var == pt.o.is_var) return KB_OK;  // both constant: left to the scan
+    const bool by_y = !pt.o.is_var;                // the bound position is the object
+    const u32 key = by_y ? pt.o.value : pt.s.value;
+    const Buf& tab = by_y ? ps.ytab : ps.xtab;
+    const Buf& off = by_y ? ps.yoff : ps.xoff;
+    const Buf& val = by_y ? ps.yval : ps.xval;
+    if (tab) {  // unique column: one table slot
+        const u32 cs = by_y ? 0u : ps.tab_cshift;
+        if (cs != 0u && shard_of(key, ctx->shard_world) != ctx->shard_rank) {  // a key of another shard: not in this store
+            Col col; KB_TRY(alloc_col(ctx, 0, &col)); rel->cols.push_back(col);
+            *out = std::move(rel);
+            return KB_OK;
+        }
+        const u32 o = compact_key(key, cs) - (by_y ? ps.ytab_min : ps.xtab_min);
+        u32 v = EMPTY32;
+        if (o < (by_y ? ps.ytab_range : ps.xtab_range)) {
+            KB_CUDA(ctx, cudaMemcpyAsync(&v, static_cast<const u32*>(tab->p) + o, sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+            KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+            ctx->stats.d2h_bytes += 4;
+        }
+        Col col;
+        KB_TRY(alloc_col(ctx, v == EMPTY32 ? 0 : 1, &col));
+        if (v != EMPTY32) KB_CUDA(ctx, cudaMemcpyAsync(col.ptr, &v, sizeof(u32), cudaMemcpyHostToDevice, ctx->st));
+        KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+        rel->cols.push_back(col);
+        rel->n = v == EMPTY32 ? 0 : 1;
+        ctx->stats.index_joins++;
+        *out = std::move(rel);
+        return KB_OK;
+    }
+    if (off && val) {  // multi-valued column: the key's run in the directory
+        const u32 kmin = by_y ? ps.ycsr_min : ps.xcsr_min, range = by_y ? ps.ycsr_range : ps.xcsr_range;
+        u32 be[2] = {0, 0};
+        if (key >= kmin && key - kmin < range) {
+            KB_CUDA(ctx, cudaMemcpyAsync(be, static_cast<const u32*>(off->p) + (key - kmin), 2 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->st));
+            KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+            ctx->stats.d2h_bytes += 8;
+        }
+        const u64 n = be[1] - be[0];
+        Col col;
+        if ((be[0] & 3u) == 0 && n) {  // 16-byte aligned run: a view of the directory's values, no copy
+            col.buf = val;
+            col.ptr = static_cast<u32*>(val->p) + be[0];
+        } else {
+            KB_TRY(alloc_col(ctx, n, &col));
+            if (n) KB_CUDA(ctx, cudaMemcpyAsync(col.ptr, static_cast<const u32*>(val->p) + be[0], n * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+        }
+        rel->cols.push_back(col);
+        rel->n = n;
+        ctx->stats.index_joins++;
+        *out = std::move(rel);
+        return KB_OK;
+    }
+    return KB_OK;
+}
+
 kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vector<FilterProg>& pushdown, bool want_index, bool pairs,
                     std::vector<std::unique_ptr<kb_rel>>* out, const std::vector<ScanTable>* tables) {
     if (K == 0 || K > (u32)MAXP) return fail(ctx, KB_E_LIMIT, "a fused scan takes 1..%d patterns (got %u)", MAXP, K);
+    if (!want_index && !pairs && !tables && ctx->use_index && ctx->index_version == ctx->store_version && !ctx->in_index_build) {
+        // patterns the index answers are not scanned; the rest (if any) go through one fused scan
+        std::vector<std::unique_ptr<kb_rel>> got(K);
+        std::vector<u32> rest;
+        for (u32 k = 0; k < K; k++) {
+            KB_TRY(check_pattern(ctx, pats[k]));
+            KB_TRY(index_lookup(ctx, pats[k], &got[k]));
+            if (!got[k]) { rest.push_back(k); continue; }
+            if (k < pushdown.size() && !pushdown[k].ops.empty()) {  // the pattern's own FILTER, applied to the looked-up rows
+                std::unique_ptr<kb_rel> f;
+                KB_TRY(filter_impl(ctx, *got[k], pushdown[k], &f));
+                got[k] = std::move(f);
+            }
+        }
+        if (rest.size() < K) {
+            if (!rest.empty()) {
+                std::vector<kb_pattern> rp;
+                std::vector<FilterProg> rf;
+                for (u32 k : rest) { rp.push_back(pats[k]); rf.push_back(k < pushdown.size() ? pushdown[k] : FilterProg{}); }
+                std::vector<std::unique_ptr<kb_rel>> sub;
+                ctx->in_index_build = true;  // (re-entrancy guard: the remaining patterns are scanned, not looked up again)
+                const kb_status rc = scan_impl(ctx, rp.data(), (u32)rp.size(), rf, false, false, &sub, nullptr);
+                ctx->in_index_build = false;
+                if (rc != KB_OK) return rc;
+                for (size_t i = 0; i < rest.size(); i++) got[rest[i]] = std::move(sub[i]);
+            }
+            out->clear();
+            for (u32 k = 0; k < K; k++) out->push_back(std::move(got[k]));
+            return KB_OK;
+        }
+    }
     const u64 N = ctx->n_triples;
     if (N >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "store holds %llu triples; row positions are 32-bit", (unsigned long long)N);
     ScanParams P{};
@@ -1999,6 +2124,7 @@ kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable) {
             chunk_of[i] = (int)ps.chunks.size();
             ps.chunks.push_back(ch);
             ps.n += ch.n;
+            if (ps.chunks.size() > 1) { ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset(); }  // the directories describe one chunk
         }
         KB_CUDA(ctx, cudaGetLastError());
         KB_TRY(ctrl_read(ctx));
@@ -2057,6 +2183,7 @@ kb_status index_evict_tag(kb_ctx* ctx, u64 tag) {
             ctx->stats.kernel_launches += (ps.xtab ? 1 : 0) + (ps.ytab ? 1 : 0);
             ps.n -= ch.n;
             ps.chunks.erase(ps.chunks.begin() + c);  // the chunk's buffers are released stream-ordered, after the clears above
+            ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset();
         }
         if (ps.chunks.empty()) it = ctx->index.erase(it);
         else ++it;
@@ -2087,6 +2214,33 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
             return KB_OK;  // too many predicates: keep scanning (n_predicates = 0)
         }
     }
+    // key-grouped directories (counting sort by the dense key) for the columns that did not get a direct table
+    for (auto& kv : ctx->index) {
+        kb::PredSlice& ps = kv.second;
+        const kb::SliceChunk* ch = ps.single();
+        if (!ch || ch->n == 0) continue;
+        for (u32 y = 0; y < 2; y++) {
+            if (y ? (bool)ps.ytab : (bool)ps.xtab) continue;  // unique column: the direct table answers the lookup
+            const u32 lo = y ? ps.ymin : ps.xmin, hi = y ? ps.ymax : ps.xmax;
+            const u64 range = (u64)hi - lo + 1;
+            if (range > std::max<u64>(8 * ps.n, 1ull << 20) || range > (1ull << 28)) continue;  // sparse ids: no directory
+            kb::Buf off, val, cursor, scratch;
+            KB_TRY(kb::alloc_buf(ctx, (range + 1) * sizeof(u32), &off));
+            KB_TRY(kb::alloc_buf(ctx, ch->n * sizeof(u32), &val));
+            KB_TRY(kb::alloc_buf(ctx, range * sizeof(u32), &cursor));
+            KB_TRY(kb::alloc_buf(ctx, ((range + 1) / 2048 + 4) * sizeof(u32), &scratch));
+            KB_CUDA(ctx, cudaMemsetAsync(off->p, 0, (range + 1) * sizeof(u32), ctx->st));
+            const uint2* pairs = reinterpret_cast<const uint2*>(ch->pairs.ptr);
+            kb::launch_csr_count_pairs(pairs, y, (u32)ch->n, lo, static_cast<u32*>(off->p), ctx->n_sms, ctx->st);
+            kb::launch_exclusive_scan_u32(static_cast<u32*>(off->p), (u32)range + 1, static_cast<u32*>(scratch->p), ctx->st);
+            KB_CUDA(ctx, cudaMemcpyAsync(cursor->p, off->p, range * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            kb::launch_csr_fill_pairs(pairs, y, (u32)ch->n, lo, static_cast<u32*>(cursor->p), static_cast<u32*>(val->p), ctx->n_sms, ctx->st);
+            ctx->stats.kernel_launches += 5;
+            if (y) { ps.yoff = off; ps.yval = val; ps.ycsr_min = lo; ps.ycsr_range = (u32)range; }
+            else { ps.xoff = off; ps.xval = val; ps.xcsr_min = lo; ps.xcsr_range = (u32)range; }
+        }
+    }
+    KB_CUDA(ctx, cudaGetLastError());
     cudaEventRecord(e1, ctx->st);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     float ms = 0.f;

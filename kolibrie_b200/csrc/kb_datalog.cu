@@ -240,7 +240,12 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
             for (u32 i = 0; i < k; i++) { pats[i].s = kb_term{1, 0}; pats[i].p = kb_term{0, preds[b + i]}; pats[i].o = kb_term{1, 1}; }
             std::vector<std::unique_ptr<kb_rel>> out;
             std::vector<FilterProg> none;
-            KB_TRY(scan_impl(ctx, pats, k, none, false, false, &out));
+            // the predicate relations are append-only buffers with the capacity of a whole-store scan output: take the scan, not the
+            // (exactly sized) index slices
+            ctx->in_index_build = true;
+            const kb_status src = scan_impl(ctx, pats, k, none, false, false, &out);
+            ctx->in_index_build = false;
+            KB_TRY(src);
             for (u32 i = 0; i < k; i++) {
                 PredRel& r = fx.rels[preds[b + i]];
                 r.s = out[i]->cols[0];

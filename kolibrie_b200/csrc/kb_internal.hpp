@@ -115,6 +115,12 @@ struct PredSlice {  // one predicate's (subject, object) rows of the store — t
     bool x_unique = false, y_unique = false;  // no subject (object) occurs twice -> builds keyed on it need no duplicate detection
                                               // (functional / inverse-functional predicate in this store)
     bool x_tried = false, y_tried = false;    // a table for the column was attempted (false: never dense enough)
+    // key-grouped directories for the columns that are NOT unique (multi-valued predicates, objects shared by many subjects): the
+    // slice sorted by that column — a counting sort, the ids being dense — as off[key - min .. ] + the other half in key order. What the
+    // reference's spo[s][P] -> {o} and pos[P][o] -> {s} sets are (index_manager.rs:18-26, 253-340): a bound subject / object is a range
+    // of val, not a scan. Built by kb_store_build_index for single-chunk slices; dropped when the predicate's slice is appended to.
+    Buf xoff, xval, yoff, yval;
+    u32 xcsr_min = 0, xcsr_range = 0, ycsr_min = 0, ycsr_range = 0;
     const SliceChunk* single() const { return chunks.size() == 1 ? &chunks[0] : nullptr; }
     bool typed(u64 num_version) const {
         for (auto& c : chunks) if (!c.ynum || c.ynum_version != num_version) return false;
@@ -181,6 +187,7 @@ struct kb_ctx {
     kb::u64 derive_bucket_slack = 8192;  // KOLIBRIE_DERIVE_SLACK: rows a bucket holds beyond 9/8 of its fair share
     bool fast_index_kernel = true;       // KOLIBRIE_INDEX_KERNEL=0: index joins go through the generic probe kernel (A/B switch)
     bool use_index = true;               // KOLIBRIE_USE_INDEX=0 / kb_set_use_index: force the scanning path
+    bool in_index_build = false;         // scan_impl must read the store itself (index build in progress / remaining patterns of a mixed scan)
     bool index_maintain = true;          // KOLIBRIE_INDEX_MAINTAIN=0: append / evict drop the index instead of maintaining it (A/B switch)
     kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject
     int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges

@@ -1695,6 +1695,33 @@ void launch_csr_fill(const u32* keys, u32 n, u32 kmin, u32* cursor, const u32* c
     csr_fill_kernel<<<grid, 256, 0, st>>>(P);
 }
 
+__global__ void __launch_bounds__(256) csr_count_pairs_kernel(const uint2* __restrict__ kv, u32 key_is_y, u32 n, u32 kmin, u32* __restrict__ counts) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 v = kv[i];
+        atomicAdd(&counts[(key_is_y ? v.y : v.x) - kmin], 1u);
+    }
+}
+void launch_csr_count_pairs(const uint2* kv, u32 key_is_y, u32 n, u32 kmin, u32* counts, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    csr_count_pairs_kernel<<<grid, 256, 0, st>>>(kv, key_is_y, n, kmin, counts);
+}
+__global__ void __launch_bounds__(256) csr_fill_pairs_kernel(const uint2* __restrict__ kv, u32 key_is_y, u32 n, u32 kmin, u32* __restrict__ cursor,
+                                                             u32* __restrict__ val_out) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 v = kv[i];
+        const u32 pos = atomicAdd(&cursor[(key_is_y ? v.y : v.x) - kmin], 1u);
+        val_out[pos] = key_is_y ? v.x : v.y;
+    }
+}
+void launch_csr_fill_pairs(const uint2* kv, u32 key_is_y, u32 n, u32 kmin, u32* cursor, u32* val_out, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    csr_fill_pairs_kernel<<<grid, 256, 0, st>>>(kv, key_is_y, n, kmin, cursor, val_out);
+}
+
 __global__ void __launch_bounds__(256) csr_total_kernel(const u32* __restrict__ pk, u32 n, const u32* __restrict__ off, u32 kmin, u32 range,
                                                         unsigned long long* total) {
     const u32 stride = gridDim.x * blockDim.x;

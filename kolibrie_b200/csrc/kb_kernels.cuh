@@ -269,6 +269,9 @@ void launch_csr_count(const u32* keys, u32 n, u32 kmin, u32* counts, int n_sms, 
 void launch_exclusive_scan_u32(u32* a, u32 n, u32* scratch, cudaStream_t st);
 void launch_csr_fill(const u32* keys, u32 n, u32 kmin, u32* cursor, const u32* const* pay_in, u32* const* pay_out, u32 n_pay, int n_sms, cudaStream_t st);
 void launch_csr_total(const u32* pkeys, u32 n, const CsrTab& tab, unsigned long long* total, int n_sms, cudaStream_t st);
+// the same directory built from an interleaved (subject, object) slice of the store index: key = one half, payload = the other half
+void launch_csr_count_pairs(const uint2* kv, u32 key_is_y, u32 n, u32 kmin, u32* counts, int n_sms, cudaStream_t st);
+void launch_csr_fill_pairs(const uint2* kv, u32 key_is_y, u32 n, u32 kmin, u32* cursor, u32* val_out, int n_sms, cudaStream_t st);
 constexpr int PROBEG_THREADS = 256;
 constexpr int PROBEG_ITEMS = 4;
 constexpr int PROBEG_TILE = PROBEG_THREADS * PROBEG_ITEMS;

@@ -547,3 +547,56 @@ def test_star_scan_filter_boundaries(ctx, emp, cmp):
         got = ctx.star_join(js, pats, filt)
         want = db.bgp(pats, filt)
         H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), f"cmp {cmp} value {value}")
+
+
+def test_index_lookups_replace_scans(ctx):
+    """IndexScan with a bound subject or object (index_manager.rs:253-340 cases; engine.rs:1248-1407): with the store index valid,
+    (c P ?o), (?s P c) and (?s P ?o) are answered from the predicate's slice — direct table for unique columns, key-grouped directory
+    for multi-valued ones — and must not launch a scan kernel; answers = the oracle's scan"""
+    rng = np.random.default_rng(21)
+    n = 60000
+    # predicate 100: functional (unique subjects); 101: multi-valued both ways; 102: sparse object ids (no directory -> scan)
+    s100 = rng.permutation(20000)[:15000].astype(np.uint32) + 1000
+    t100 = np.stack([s100, np.full(len(s100), 100), rng.integers(500, 900, len(s100))], axis=1)
+    t101 = np.unique(np.stack([rng.integers(1000, 6000, n), np.full(n, 101), rng.integers(2000, 7000, n)], axis=1), axis=0)
+    t102 = np.unique(np.stack([rng.integers(1000, 3000, 4000), np.full(4000, 102), rng.integers(0, 1 << 30, 4000)], axis=1), axis=0)
+    tr = np.concatenate([t100, t101, t102]).astype(np.uint32)
+    tr = tr[rng.permutation(len(tr))]
+    ctx.store_load(tr[:, 0], tr[:, 1], tr[:, 2])
+    db = O.Db(tr[:, 0], tr[:, 1], tr[:, 2])
+    ctx.build_index()
+    X, Y = 0, 1
+    some_s100, some_s101, some_o101, some_o100 = int(s100[7]), int(t101[5, 0]), int(t101[9, 2]), int(t100[3, 2])
+    cases = [("functional, bound subject", c.pattern(c.K(some_s100), c.K(100), c.V(Y)), True),
+             ("functional, bound subject absent", c.pattern(c.K(999999), c.K(100), c.V(Y)), True),
+             ("functional predicate, bound object (many subjects)", c.pattern(c.V(X), c.K(100), c.K(some_o100)), True),
+             ("multi-valued, bound subject", c.pattern(c.K(some_s101), c.K(101), c.V(Y)), True),
+             ("multi-valued, bound object", c.pattern(c.V(X), c.K(101), c.K(some_o101)), True),
+             ("multi-valued, bound object absent", c.pattern(c.V(X), c.K(101), c.K(1)), True),
+             ("whole slice", c.pattern(c.V(X), c.K(101), c.V(Y)), True),
+             ("predicate absent", c.pattern(c.V(X), c.K(555), c.V(Y)), True),
+             ("sparse objects, bound subject", c.pattern(c.K(int(t102[0, 0])), c.K(102), c.V(Y)), True),
+             ("sparse objects, bound object: no directory", c.pattern(c.V(X), c.K(102), c.K(int(t102[0, 2]))), False),
+             ("variable predicate", c.pattern(c.K(some_s101), c.V(Y), c.V(X)), False)]
+    for what, pat, by_index in cases:
+        scans0 = ctx.get_stats()["scan_launches"]
+        got = ctx.scan([pat])[0]
+        want = db.scan(pat)
+        H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), what)
+        launched = ctx.get_stats()["scan_launches"] - scans0
+        if by_index and "whole slice" not in what:
+            assert launched == 0, f"{what}: a scan kernel ran"
+        if not by_index:
+            assert launched >= 1, what
+    # several patterns in one call: looked-up and scanned patterns mix; a pushed-down FILTER applies to looked-up rows too
+    pats = [c.pattern(c.K(some_s101), c.K(101), c.V(Y)), c.pattern(c.V(X), c.V(2), c.K(some_o101)), c.pattern(c.V(X), c.K(100), c.V(Y))]
+    flt = [None, None, [c.fop(c.F_NE_ID, slot=Y, id=some_o100)]]
+    got = ctx.scan(pats, flt)
+    for k in range(3):
+        want = db.scan(pats[k], flt[k])
+        H.assert_same_bag(got[k].to_numpy(sorted(got[k].slots)), want.to_numpy(sorted(want.slots)), f"mixed {k}")
+    # a BGP whose patterns do not share one variable (left-deep joins over looked-up inputs)
+    bgp = [c.pattern(c.K(some_s101), c.K(101), c.V(Y)), c.pattern(c.V(X), c.K(101), c.V(Y))]
+    got = ctx.bgp_execute(bgp)
+    want = db.bgp(bgp)
+    H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), "path BGP")
