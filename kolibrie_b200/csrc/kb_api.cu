@@ -1029,9 +1029,22 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 P.n_ops = (u32)fops.size();
                 for (size_t i = 0; i < fops.size(); i++) P.ops[i] = fops[i];
             }
+            // table mode: the probe pattern's own subject table is the probe stream (keys ascending whatever the store / id order)
+            const bool tab_mode = ctx->probe_table_mode && !ctx->ordered && persistent((u32)probe_k) && key_pos((u32)probe_k) == 0 &&
+                                  (P.pre_mode != 1u || (PS.xnum && PS.xnum_version == ctx->num_version));
             P.n_seg = 0;
             P.n_tiles = 0;
+            if (tab_mode) {
+                P.ptab = static_cast<const u32*>(PS.xtab->p);
+                P.pnum = P.pre_mode == 1u ? static_cast<const double*>(PS.xnum->p) : nullptr;
+                P.ptab_min = PS.xtab_min;
+                P.ptab_range = PS.xtab_range;
+                P.ptab_cshift = PS.tab_cshift;
+                P.shard_rank = ctx->shard_rank;
+                P.n_tiles = (u32)(((u64)PS.xtab_range + PROBEF_TILE - 1) / PROBEF_TILE);
+            }
             for (auto& ch : PS.chunks) {  // one chunk per store segment: an RSP window of slides is walked in ONE launch
+                if (tab_mode) break;
                 if (ch.n == 0) continue;
                 ProbeISeg& g = P.seg[P.n_seg++];
                 g.pairs = reinterpret_cast<const uint2*>(ch.pairs.ptr);
@@ -1841,6 +1854,7 @@ kb_status kb_ctx_create(int device, kb_ctx** out) {
     if (const char* fk = getenv("KOLIBRIE_INDEX_KERNEL")) ctx->fast_index_kernel = fk[0] != '0';
     if (const char* cj = getenv("KOLIBRIE_CSR_JOIN")) ctx->csr_join = cj[0] != '0';
     if (const char* im = getenv("KOLIBRIE_INDEX_MAINTAIN")) ctx->index_maintain = im[0] != '0';
+    if (const char* tm = getenv("KOLIBRIE_PROBE_TABLE")) ctx->probe_table_mode = tm[0] != '0';
     if (const char* dp = getenv("KOLIBRIE_DERIVE_PART")) ctx->derive_part = dp[0] != '0';
     if (const char* ds = getenv("KOLIBRIE_DERIVE_SLICE")) ctx->derive_slice_bytes = std::max<u64>(64, strtoull(ds, nullptr, 10));
     if (const char* dk = getenv("KOLIBRIE_DERIVE_SLACK")) ctx->derive_bucket_slack = strtoull(dk, nullptr, 10);
@@ -2035,6 +2049,7 @@ static kb_status slice_table_update(kb_ctx* ctx, PredSlice& ps, u32 y, int added
     if (!fits) {
         // (re)build over every chunk, with headroom above the largest key: dictionary ids grow, so appended segments bring larger ones
         tab.reset();
+        if (!y) ps.xnum.reset();
         tried = true;
         unique = false;
         if (range > std::max<u64>(4 * ps.n + 65536, 1ull << 16) || range > (1ull << 28)) return KB_OK;  // not dense: keep no table
@@ -2125,6 +2140,7 @@ kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable) {
             ps.chunks.push_back(ch);
             ps.n += ch.n;
             if (ps.chunks.size() > 1) { ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset(); }  // the directories describe one chunk
+            if (!ctx->in_full_index_build) ps.xnum.reset();  // (kept in table order by the full build only)
         }
         KB_CUDA(ctx, cudaGetLastError());
         KB_TRY(ctrl_read(ctx));
@@ -2183,7 +2199,7 @@ kb_status index_evict_tag(kb_ctx* ctx, u64 tag) {
             ctx->stats.kernel_launches += (ps.xtab ? 1 : 0) + (ps.ytab ? 1 : 0);
             ps.n -= ch.n;
             ps.chunks.erase(ps.chunks.begin() + c);  // the chunk's buffers are released stream-ordered, after the clears above
-            ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset();
+            ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset(); ps.xnum.reset();
         }
         if (ps.chunks.empty()) it = ctx->index.erase(it);
         else ++it;
@@ -2207,12 +2223,27 @@ kb_status kb_store_build_index(kb_ctx* ctx, uint32_t* n_predicates, double* buil
     for (auto& sg : ctx->segs) if (sg.n && (!sg.has_stats || sg.stats_world != ctx->shard_world)) KB_TRY(kb::segment_stats(ctx, &sg));
     for (size_t g = 0; g < ctx->segs.size(); g++) {
         bool indexable = true;
+        ctx->in_full_index_build = true;
         const kb_status rc = kb::index_add_segment(ctx, g, &indexable);
+        ctx->in_full_index_build = false;
         if (rc != KB_OK || !indexable) {
             ctx->index.clear();
             if (rc != KB_OK) return rc;
             return KB_OK;  // too many predicates: keep scanning (n_predicates = 0)
         }
+    }
+    // typed values in table order for subject tables whose slice is numeric: the table-mode probe reads FILTER operands sequentially
+    for (auto& kv : ctx->index) {
+        kb::PredSlice& ps = kv.second;
+        if (!ps.xtab || !ctx->n_ids || !ps.typed(ctx->num_version)) continue;
+        KB_TRY(kb::alloc_buf(ctx, (size_t)ps.xtab_range * sizeof(double), &ps.xnum));
+        KB_CUDA(ctx, cudaMemsetAsync(ps.xnum->p, 0, (size_t)ps.xtab_range * sizeof(double), ctx->st));
+        for (auto& ch : ps.chunks) {
+            kb::launch_pair_numtab(reinterpret_cast<const uint2*>(ch.pairs.ptr), (u32)ch.n, kb::numtab(ctx), static_cast<double*>(ps.xnum->p), ps.xtab_min, ps.xtab_range,
+                                   ps.tab_cshift, ctx->n_sms, ctx->st);
+            ctx->stats.kernel_launches++;
+        }
+        ps.xnum_version = ctx->num_version;
     }
     // key-grouped directories (counting sort by the dense key) for the columns that did not get a direct table
     for (auto& kv : ctx->index) {

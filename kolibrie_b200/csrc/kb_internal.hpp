@@ -119,6 +119,8 @@ struct PredSlice {  // one predicate's (subject, object) rows of the store — t
     // slice sorted by that column — a counting sort, the ids being dense — as off[key - min .. ] + the other half in key order. What the
     // reference's spo[s][P] -> {o} and pos[P][o] -> {s} sets are (index_manager.rs:18-26, 253-340): a bound subject / object is a range
     // of val, not a scan. Built by kb_store_build_index for single-chunk slices; dropped when the predicate's slice is appended to.
+    Buf xnum;                // typed values in TABLE order: xnum[compact(subject) - xtab_min] = num_or0[object] (built with xtab by kb_store_build_index
+    u64 xnum_version = 0;    // when the slice has numeric objects; the table-mode probe filters on it sequentially)
     Buf xoff, xval, yoff, yval;
     u32 xcsr_min = 0, xcsr_range = 0, ycsr_min = 0, ycsr_range = 0;
     const SliceChunk* single() const { return chunks.size() == 1 ? &chunks[0] : nullptr; }
@@ -188,6 +190,8 @@ struct kb_ctx {
     bool fast_index_kernel = true;       // KOLIBRIE_INDEX_KERNEL=0: index joins go through the generic probe kernel (A/B switch)
     bool use_index = true;               // KOLIBRIE_USE_INDEX=0 / kb_set_use_index: force the scanning path
     bool in_index_build = false;         // scan_impl must read the store itself (index build in progress / remaining patterns of a mixed scan)
+    bool in_full_index_build = false;
+    bool probe_table_mode = true;        // KOLIBRIE_PROBE_TABLE=0: the index probe always streams the slice (A/B switch)
     bool index_maintain = true;          // KOLIBRIE_INDEX_MAINTAIN=0: append / evict drop the index instead of maintaining it (A/B switch)
     kb::u32 shard_rank = 0, shard_world = 1;  // kb_set_sharding: the store is shard `rank` of `world`, sharded by subject
     int upload_stats_off = -1;  // chunked upload in flight: control words where the copy stream accumulates the column ranges

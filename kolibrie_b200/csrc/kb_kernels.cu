@@ -711,6 +711,19 @@ __global__ void __launch_bounds__(256) pair_numcol_kernel(const uint2* __restric
     c = warp_sum(c);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_numeric, c);
 }
+__global__ void __launch_bounds__(256) pair_numtab_kernel(const uint2* __restrict__ kv, u32 n, NumTab nt, double* __restrict__ out, u32 kmin, u32 range, u32 cshift) {
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint2 v = kv[i];
+        const u32 off = compact_key(v.x, cshift) - kmin;
+        if (off < range) out[off] = num_of(nt, v.y);
+    }
+}
+void launch_pair_numtab(const uint2* kv, u32 n, NumTab nt, double* out, u32 kmin, u32 range, u32 cshift, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    pair_numtab_kernel<<<grid, 256, 0, st>>>(kv, n, nt, out, kmin, range, cshift);
+}
 void launch_pair_numcol(const uint2* kv, u32 n, NumTab nt, double* out, u32* n_numeric, int n_sms, cudaStream_t st) {
     if (n == 0) return;
     int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
@@ -1007,12 +1020,17 @@ constexpr int PI_GROUP_SMEM = 64;
 __device__ void group_update_global(const GroupParams& P, const u32* k, unsigned long long cnt, const double* val);
 __device__ void atomic_min_f64(double* addr, double v);
 __device__ void atomic_max_f64(double* addr, double v);
-template <int T, int PRE, bool AGG>
+// TAB = true: the probe stream is not the slice but the probe pattern's own persistent TABLE, walked slot by slot: slot i holds the
+// other half of the triple whose key is (table base + i), EMPTY32 where no triple has that key. The keys then come in ascending order
+// whatever the order of the store and of the dictionary ids, so the lookups into the other patterns' tables are sequential too — a
+// direct table over dense ids IS the slice sorted by that column (with the gaps of the id space). With a FILTER on the other half's
+// numeric value the typed column is read from a second table in the same order.
+template <int T, int PRE, bool AGG, bool TAB>
 __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel(const __grid_constant__ ProbeIParams P, const __grid_constant__ GroupParams G) {
     constexpr int R = 4;  // rows per thread (striped over the warp's 128-row chunk, see below)
     constexpr u32 TILE = PROBEF_THREADS * R;
     extern __shared__ __align__(128) u32 smem_all[];  // per stage: TILE pairs [+ TILE doubles]
-    constexpr u32 STAGE_WORDS = (PRE == 1 ? 4u : 2u) * TILE;
+    constexpr u32 STAGE_WORDS = TAB ? (PRE == 1 ? 3u : 1u) * TILE : (PRE == 1 ? 4u : 2u) * TILE;  // TAB: TILE values [+ TILE doubles]
     __shared__ __align__(8) u64 bars[2];
     __shared__ u32 s_nexts[2];
     __shared__ u32 s_wcnt[PROBEF_THREADS / 32];
@@ -1033,6 +1051,16 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
     auto issue = [&](u32 t, u32 stage) {
         u32* smem = smem_all + stage * STAGE_WORDS;
         u64& bar = bars[stage];
+        if constexpr (TAB) {
+            const u32 b = t * TILE;
+            const u32 c = min(TILE, P.ptab_range - b);
+            const u32 bytes = (c * 4u + 15u) & ~15u;
+            s_tcnt[stage] = c;
+            mbar_arrive_expect_tx(&bar, PRE == 1 ? 3u * bytes : bytes);
+            tma_load_1d(smem, P.ptab + b, bytes, &bar);
+            if (PRE == 1) tma_load_1d(smem + TILE, P.pnum + b, 2u * bytes, &bar);
+            return;
+        }
         u32 g = 0;  // the chunk (store segment) this tile belongs to
         while (g + 1u < P.n_seg && t >= P.seg[g + 1u].tile0) g++;
         const ProbeISeg& sg = P.seg[g];
@@ -1069,16 +1097,31 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
         // striped: row j of this thread is row (warp*128 + j*32 + lane) of the tile, so one warp instruction touches 32 CONSECUTIVE
         // rows: lookups into a table indexed by a sorted key hit 4 sectors instead of 16, and the compacted stores of one j are
         // one contiguous run
-#pragma unroll
-        for (int j = 0; j < R; j++) {
-            const u32 idx = (u32)warp * (32u * R) + (u32)j * 32u + (u32)lane;
-            const uint2 v = reinterpret_cast<const uint2*>(smem)[idx];
-            rx[j] = v.x; ry[j] = v.y;
-            if (PRE == 1) pa[j] = reinterpret_cast<const double*>(smem + 2 * TILE)[idx];
-        }
         u32 vmask = 0;
+        if constexpr (TAB) {
 #pragma unroll
-        for (int j = 0; j < R; j++) vmask |= (((u32)warp * (32u * R) + (u32)j * 32u + (u32)lane) < cnt ? 1u : 0u) << j;
+            for (int j = 0; j < R; j++) {
+                const u32 idx = (u32)warp * (32u * R) + (u32)j * 32u + (u32)lane;
+                const u32 v = smem[idx];
+                // the key of slot (tile base + idx): the inverse of compact_key for this shard's keys
+                const u32 ck = P.ptab_min + tile * TILE + idx;
+                const u32 key = P.ptab_cshift ? (((((ck >> SHARD_B) << P.ptab_cshift) | P.shard_rank) << SHARD_B) | (ck & ((1u << SHARD_B) - 1u))) : ck;
+                rx[j] = P.key_is_y ? v : key;
+                ry[j] = P.key_is_y ? key : v;
+                if (PRE == 1) pa[j] = reinterpret_cast<const double*>(smem + TILE)[idx];
+                vmask |= ((idx < cnt && v != EMPTY32) ? 1u : 0u) << j;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+                const u32 idx = (u32)warp * (32u * R) + (u32)j * 32u + (u32)lane;
+                const uint2 v = reinterpret_cast<const uint2*>(smem)[idx];
+                rx[j] = v.x; ry[j] = v.y;
+                if (PRE == 1) pa[j] = reinterpret_cast<const double*>(smem + 2 * TILE)[idx];
+            }
+#pragma unroll
+            for (int j = 0; j < R; j++) vmask |= (((u32)warp * (32u * R) + (u32)j * 32u + (u32)lane) < cnt ? 1u : 0u) << j;
+        }
         if (PRE == 1) {
             u32 pass = 0;
 #pragma unroll
@@ -1260,36 +1303,45 @@ __global__ void __launch_bounds__(PROBEF_THREADS, KB_PI_MINB) probe_index_kernel
     }
 }
 
-template <int T, int PRE, bool AGG>
+template <int T, int PRE, bool AGG, bool TAB>
 static void launch_probe_index_tp(const ProbeIParams& p, const GroupParams& g, int n_sms, cudaStream_t st) {
     static int per_sm = 0;  // occupancy is a property of the kernel image: asked once per instantiation
-    const size_t smem = (size_t)PROBEF_THREADS * 4 * (PRE == 1 ? 16 : 8) * 2;
+    const size_t smem = TAB ? (size_t)PROBEF_THREADS * 4 * (PRE == 1 ? 12 : 4) * 2 : (size_t)PROBEF_THREADS * 4 * (PRE == 1 ? 16 : 8) * 2;
     if (per_sm == 0) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_index_kernel<T, PRE, AGG>, PROBEF_THREADS, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_index_kernel<T, PRE, AGG, TAB>, PROBEF_THREADS, smem);
         if (per_sm < 1) per_sm = 1;
     }
     long long grid = (long long)per_sm * n_sms;
     if (grid > (long long)p.n_tiles) grid = p.n_tiles;
-    probe_index_kernel<T, PRE, AGG><<<(int)grid, PROBEF_THREADS, smem, st>>>(p, g);
+    probe_index_kernel<T, PRE, AGG, TAB><<<(int)grid, PROBEF_THREADS, smem, st>>>(p, g);
 }
-template <int T>
+template <int T, bool TAB>
 static void launch_probe_index_t(const ProbeIParams& p, const GroupParams* g, int n_sms, cudaStream_t st) {
     static const GroupParams none{};
     if (g) {
-        if (p.pre_mode == 1u) launch_probe_index_tp<T, 1, true>(p, *g, n_sms, st);
-        else launch_probe_index_tp<T, 0, true>(p, *g, n_sms, st);
+        if (p.pre_mode == 1u) launch_probe_index_tp<T, 1, true, TAB>(p, *g, n_sms, st);
+        else launch_probe_index_tp<T, 0, true, TAB>(p, *g, n_sms, st);
     } else {
-        if (p.pre_mode == 1u) launch_probe_index_tp<T, 1, false>(p, none, n_sms, st);
-        else launch_probe_index_tp<T, 0, false>(p, none, n_sms, st);
+        if (p.pre_mode == 1u) launch_probe_index_tp<T, 1, false, TAB>(p, none, n_sms, st);
+        else launch_probe_index_tp<T, 0, false, TAB>(p, none, n_sms, st);
     }
 }
 void launch_probe_index(const ProbeIParams& p, const GroupParams* agg, int n_sms, cudaStream_t st) {
     if (p.n == 0) return;
+    if (p.ptab) {
+        switch (p.T) {
+            case 1: launch_probe_index_t<1, true>(p, agg, n_sms, st); break;
+            case 2: launch_probe_index_t<2, true>(p, agg, n_sms, st); break;
+            case 3: launch_probe_index_t<3, true>(p, agg, n_sms, st); break;
+            default: launch_probe_index_t<4, true>(p, agg, n_sms, st); break;
+        }
+        return;
+    }
     switch (p.T) {
-        case 1: launch_probe_index_t<1>(p, agg, n_sms, st); break;
-        case 2: launch_probe_index_t<2>(p, agg, n_sms, st); break;
-        case 3: launch_probe_index_t<3>(p, agg, n_sms, st); break;
-        default: launch_probe_index_t<4>(p, agg, n_sms, st); break;
+        case 1: launch_probe_index_t<1, false>(p, agg, n_sms, st); break;
+        case 2: launch_probe_index_t<2, false>(p, agg, n_sms, st); break;
+        case 3: launch_probe_index_t<3, false>(p, agg, n_sms, st); break;
+        default: launch_probe_index_t<4, false>(p, agg, n_sms, st); break;
     }
 }
 

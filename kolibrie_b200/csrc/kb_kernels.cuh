@@ -170,6 +170,12 @@ struct ProbeISeg {
 struct ProbeIParams {
     ProbeISeg seg[PROBEI_MAXSEG];
     u32 n_seg;
+    // table mode (ptab != nullptr): the probe stream is the probe pattern's own persistent table, slot by slot (keys ascending), and
+    // pnum the numeric value of the slot's other half (pre_mode == 1); keys are rebuilt from the slot number (ptab_min + slot, then
+    // the inverse of the shard compaction)
+    const u32* ptab;
+    const double* pnum;
+    u32 ptab_min, ptab_range, ptab_cshift, shard_rank;
     u32 key_is_y, n, n_tiles, T;  // n = rows over all chunks
     DirectTab tab[MAXT];
     u32* out[2 + MAXT];
@@ -213,6 +219,8 @@ void launch_distinct(const u32* col, u32 n, u32* set, u32 set_slots, u32* overfl
 // min/max of both halves of a pair relation: out[0..3] = min x, min y, max x, max y
 // typed literal column of a predicate slice: out[i] = num_or0[kv[i].y]; *n_numeric += rows whose object is numeric
 void launch_pair_numcol(const uint2* kv, u32 n, NumTab nt, double* out, u32* n_numeric, int n_sms, cudaStream_t st);
+// the same values laid out like the subject-keyed direct table: out[compact(subject) - kmin] = num_or0[object]
+void launch_pair_numtab(const uint2* kv, u32 n, NumTab nt, double* out, u32 kmin, u32 range, u32 cshift, int n_sms, cudaStream_t st);
 void launch_pair_minmax(const uint2* kv, u32 n, u32* out4, int n_sms, cudaStream_t st);
 // number of occupied (non-EMPTY32) slots of a direct table: equals the number of inserted rows iff the keys were single-valued
 void launch_count_nonempty(const u32* table, u32 n, u32* out_count, int n_sms, cudaStream_t st);

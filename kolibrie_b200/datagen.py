@@ -313,3 +313,40 @@ def row_checksums(a: np.ndarray):
             h *= np.uint64(0xC4CEB9FE1A85EC53)
             h ^= h >> np.uint64(33)
         return int(a.shape[0]), int(h.sum(dtype=np.uint64)), int(np.bitwise_xor.reduce(h)) if len(h) else 0
+
+
+def permuted_dataset(d: EmployeeData, seed: int = 5):
+    """The same dataset under a random relabelling of ALL dictionary ids and a random order of the triples: what a store looks like
+    whose dictionary was not filled in document order (ids of one employee's terms far apart, subjects in no order). Returns
+    (s, p, o, num_or0, is_num, pi) with pi[old id] = new id."""
+    rng = np.random.default_rng(seed)
+    pi = rng.permutation(d.n_ids).astype(np.uint32)
+    order = rng.permutation(d.n_triples)
+    num = np.zeros_like(d.num_or0)
+    isn = np.zeros_like(d.is_num)
+    num[pi] = d.num_or0
+    isn[pi] = d.is_num
+    return pi[d.s][order], pi[d.p][order], pi[d.o][order], num, isn, pi
+
+
+def multivalued_dataset(n_subjects: int, per_subject: int = 3, seed: int = 9):
+    """A store with one MULTI-VALUED predicate: subject k (id 100 + k) has `per_subject` distinct `tag` objects, one functional
+    `score` literal and one functional `name`. ids: tag = 1, score = 2, name = 3; tag objects 10 .. 10 + 50; subjects from 100; score
+    literals after the subjects (value v has id lit0 + v, v in [0, 1000)). Returns (s, p, o, num_or0, is_num, meta)."""
+    n = int(n_subjects)
+    subj = (np.arange(n, dtype=np.uint32) + np.uint32(100))
+    k = np.arange(n, dtype=np.uint64)
+    lit0 = 100 + n
+    score = (splitmix64_at(seed, k) % np.uint64(1000)).astype(np.uint32)
+    tag0 = (splitmix64_at(seed + 1, k) % np.uint64(50)).astype(np.uint32)
+    assert 1 <= per_subject <= 7  # (tag0 + 7 j) mod 50 are distinct for j < 50 / 7
+    tags = [tag0 + np.uint32(10)] + [((tag0 + np.uint32(j * 7)) % np.uint32(50)) + np.uint32(10) for j in range(1, per_subject)]
+    s = np.concatenate([np.repeat(subj, per_subject), subj, subj])
+    p = np.concatenate([np.full(n * per_subject, 1, np.uint32), np.full(n, 2, np.uint32), np.full(n, 3, np.uint32)])
+    o = np.concatenate([np.stack(tags, axis=1).reshape(-1), score + np.uint32(lit0), subj])
+    n_ids = lit0 + 1000
+    num = np.zeros(n_ids, dtype=np.float64)
+    isn = np.zeros(n_ids, dtype=np.uint8)
+    num[lit0:] = np.arange(1000, dtype=np.float64)
+    isn[lit0:] = 1
+    return s.astype(np.uint32), p, o.astype(np.uint32), num, isn, {"subj": subj, "score": score, "tags": tags, "lit0": lit0, "per_subject": per_subject}
