@@ -1038,10 +1038,11 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 P.ptab = static_cast<const u32*>(PS.xtab->p);
                 P.pnum = P.pre_mode == 1u ? static_cast<const double*>(PS.xnum->p) : nullptr;
                 P.ptab_min = PS.xtab_min;
-                P.ptab_range = PS.xtab_range;
+                // walk the slots that can hold a key (up to the largest subject), not the table's growth headroom
+                P.ptab_range = std::min<u32>(PS.xtab_range, compact_key(PS.xmax, PS.tab_cshift) - PS.xtab_min + 1u);
                 P.ptab_cshift = PS.tab_cshift;
                 P.shard_rank = ctx->shard_rank;
-                P.n_tiles = (u32)(((u64)PS.xtab_range + PROBEF_TILE - 1) / PROBEF_TILE);
+                P.n_tiles = (u32)(((u64)P.ptab_range + PROBEF_TILE - 1) / PROBEF_TILE);
             }
             for (auto& ch : PS.chunks) {  // one chunk per store segment: an RSP window of slides is walked in ONE launch
                 if (tab_mode) break;
