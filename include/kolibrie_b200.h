@@ -82,8 +82,18 @@ enum kb_filter_opcode {
     KB_F_MUL = 11,
     KB_F_DIV = 12,      /* divisor == 0.0 -> whole expression invalid (shared/src/query.rs:47-53) */
     KB_F_TRUTHY = 13,   /* pop number, push ( valid && v != 0.0 )            types.rs:168 */
-    KB_F_IS_TRIPLE = 14 /* push ( row[slot] has bit 31 )                      types.rs:170-183 */
+    KB_F_IS_TRIPLE = 14, /* push ( row[slot] has bit 31 )                      types.rs:170-183 */
+    /* the LEGACY executor's comparison (SparqlDatabase::apply_filters_simd, kolibrie/src/sparql_database.rs:1381-1669; the path
+     * execute_query takes, execute_query.rs:311): when the bound term AND the constant both parse as i32 the comparison is an integer
+     * one (all six operators); otherwise it is a byte-wise string comparison where only = and != can hold. Fields: `cmp` = kb_cmp,
+     * OR-ed with KB_LEGACY_CONST_IS_I32 when the constant parses as i32, `value` = that integer, `id` = dictionary id of the constant
+     * string (KB_ID_NONE when the dictionary does not hold it: no term equals it). Needs kb_dict_legacy_i32_load. */
+    KB_F_CMP_LEGACY = 15
 };
+#define KB_LEGACY_CONST_IS_I32 0x100u  /* the constant parses as a number (i32; f64 in nested mode) */
+/* a comparison NESTED inside AND / OR / NOT is evaluated by evaluate_filter_expression instead (sparql_database.rs:1784-1836): both sides
+ * parsed as f64 (`value` = the constant), all six operators when both are numbers, string = / != otherwise */
+#define KB_LEGACY_NESTED_F64 0x200u
 enum kb_cmp { KB_CMP_GT = 1, KB_CMP_GE = 2, KB_CMP_LT = 3, KB_CMP_LE = 4, KB_CMP_EQ = 5, KB_CMP_NE = 6 };
 
 typedef struct kb_filter_op {
@@ -179,6 +189,10 @@ KB_API kb_status kb_store_size(kb_ctx* ctx, uint64_t* n_triples, uint32_t* n_seg
 /* id -> f64 side table computed by the host with Rust `str::parse::<f64>` acceptance:
  * num_or0[id] = parse().unwrap_or(0.0); is_num[id] = parse().is_ok(). ids >= n_ids read as (0.0, not numeric). */
 KB_API kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t* is_num, uint32_t n_ids);
+
+/* id -> i32 side table of the legacy executor's filter (KB_F_CMP_LEGACY): val[id] = the term parsed with Rust `str::parse::<i32>`,
+ * is_i32[id] = whether it parses. ids >= n_ids are not integers. */
+KB_API kb_status kb_dict_legacy_i32_load(kb_ctx* ctx, const int32_t* val, const uint8_t* is_i32, uint32_t n_ids);
 
 /* Dictionary strings on the device + result decode: the id -> string step that ends ExecutionEngine::execute
  * (kolibrie/src/streamertail_optimizer/execution/engine.rs:27-51) and Dictionary::decode (shared/src/dictionary.rs:50-52).

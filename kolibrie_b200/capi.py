@@ -25,7 +25,9 @@ KB_MAX_COLS = 16
 KB_TAG_INFERRED = 0xFFFFFFFFFFFFFFF0
 
 # filter opcodes / comparisons / aggregates (mirror the header)
-F_CMP_NUM, F_EQ_ID, F_NE_ID, F_AND, F_OR, F_NOT, F_PUSH_VAR, F_PUSH_CONST, F_ADD, F_SUB, F_MUL, F_DIV, F_TRUTHY, F_IS_TRIPLE = range(1, 15)
+F_CMP_NUM, F_EQ_ID, F_NE_ID, F_AND, F_OR, F_NOT, F_PUSH_VAR, F_PUSH_CONST, F_ADD, F_SUB, F_MUL, F_DIV, F_TRUTHY, F_IS_TRIPLE, F_CMP_LEGACY = range(1, 16)
+LEGACY_CONST_IS_I32 = 0x100
+LEGACY_NESTED_F64 = 0x200
 CMP_GT, CMP_GE, CMP_LT, CMP_LE, CMP_EQ, CMP_NE = range(1, 7)
 AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_AVG = range(5)
 SEMI_NAIVE, NAIVE, SEMI_NAIVE_PARALLEL = 0, 1, 2
@@ -158,6 +160,7 @@ def lib() -> C.CDLL:
         "kb_store_download": (i32, [vp, vp, vp, vp, u64, P(u64)]),
         "kb_dict_numeric_load": (i32, [vp, vp, vp, u32]),
         "kb_dict_strings_load": (i32, [vp, vp, vp, u32]),
+        "kb_dict_legacy_i32_load": (i32, [vp, vp, vp, u32]),
         "kb_rel_decode": (i32, [vp, vp, u32, P(vp)]),
         "kb_strings_info": (i32, [vp, P(u64), P(u64)]),
         "kb_strings_download": (i32, [vp, vp, vp, vp]),
@@ -214,7 +217,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "kb_version", "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_set_timing", "kb_get_stats", "kb_synchronize",
     "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
-    "kb_store_download", "kb_dict_numeric_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
+    "kb_store_download", "kb_dict_numeric_load", "kb_dict_legacy_i32_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_bind_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_groups_pack", "kb_groups_merge", "kb_star_join_aggregate",
     "kb_star_join_prepare", "kb_plan_submit", "kb_plan_collect", "kb_plan_info", "kb_plan_free", "kb_plan_peer_scratch_bytes", "kb_plan_attach_peers",
@@ -385,6 +388,13 @@ class Context:
         isn = np.ascontiguousarray(is_num, dtype=np.uint8)
         assert len(num) == len(isn)
         self._check(lib().kb_dict_numeric_load(self.h, _ptr(num), _ptr(isn), len(num)))
+
+    def dict_legacy_i32_load(self, val, is_i32):
+        """kb_dict_legacy_i32_load: the i32 view of the terms the legacy executor's FILTER compares with (apply_filters_simd)"""
+        v = np.ascontiguousarray(val, dtype=np.int32)
+        f = np.ascontiguousarray(is_i32, dtype=np.uint8)
+        assert len(v) == len(f)
+        self._check(lib().kb_dict_legacy_i32_load(self.h, _ptr(v), _ptr(f), len(v)))
 
     def dict_strings_load(self, strings: Sequence[str]):
         """kb_dict_strings_load: string i = the term with dictionary id i (Dictionary::id_to_string, dictionary.rs:17-21)"""

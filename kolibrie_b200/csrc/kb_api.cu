@@ -110,6 +110,9 @@ NumTab numtab(const kb_ctx* ctx) {
     nt.num_or0 = ctx->num ? static_cast<const double*>(ctx->num->p) : nullptr;
     nt.is_num = ctx->isnum ? static_cast<const u8*>(ctx->isnum->p) : nullptr;
     nt.n_ids = ctx->n_ids;
+    nt.i32_val = ctx->i32val ? static_cast<const int*>(ctx->i32val->p) : nullptr;
+    nt.is_i32 = ctx->isi32 ? static_cast<const u8*>(ctx->isi32->p) : nullptr;
+    nt.n_i32 = ctx->n_i32;
     return nt;
 }
 
@@ -177,14 +180,14 @@ void timers_flush(kb_ctx* ctx) {
 // FILTER program helpers
 static int op_arity(u32 op) {
     switch (op) {
-        case KB_F_CMP_NUM: case KB_F_EQ_ID: case KB_F_NE_ID: case KB_F_PUSH_VAR: case KB_F_PUSH_CONST: case KB_F_IS_TRIPLE: return 0;
+        case KB_F_CMP_NUM: case KB_F_EQ_ID: case KB_F_NE_ID: case KB_F_PUSH_VAR: case KB_F_PUSH_CONST: case KB_F_IS_TRIPLE: case KB_F_CMP_LEGACY: return 0;
         case KB_F_NOT: case KB_F_TRUTHY: return 1;
         case KB_F_AND: case KB_F_OR: case KB_F_ADD: case KB_F_SUB: case KB_F_MUL: case KB_F_DIV: return 2;
         default: return -1;
     }
 }
 static bool op_has_slot(u32 op) {
-    return op == KB_F_CMP_NUM || op == KB_F_EQ_ID || op == KB_F_NE_ID || op == KB_F_PUSH_VAR || op == KB_F_IS_TRIPLE;
+    return op == KB_F_CMP_NUM || op == KB_F_EQ_ID || op == KB_F_NE_ID || op == KB_F_PUSH_VAR || op == KB_F_IS_TRIPLE || op == KB_F_CMP_LEGACY;
 }
 
 kb_status validate_filter(kb_ctx* ctx, const kb_filter_op* ops, u32 n) {
@@ -1880,6 +1883,8 @@ void kb_ctx_destroy(kb_ctx* ctx) {
     ctx->index.clear();
     ctx->num.reset();
     ctx->isnum.reset();
+    ctx->i32val.reset();
+    ctx->isi32.reset();
     ctx->dict_off.reset();
     ctx->dict_bytes.reset();
     ctx->tile_state.reset();
@@ -2388,6 +2393,23 @@ kb_status kb_dict_numeric_load(kb_ctx* ctx, const double* num_or0, const uint8_t
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     ctx->n_ids = n_ids;
     ctx->num_version++;
+    return KB_OK;
+}
+
+kb_status kb_dict_legacy_i32_load(kb_ctx* ctx, const int32_t* val, const uint8_t* is_i32, uint32_t n_ids) {
+    KB_ENTER(ctx);
+    ctx->i32val.reset();
+    ctx->isi32.reset();
+    ctx->n_i32 = 0;
+    if (n_ids == 0) return KB_OK;
+    if (!val || !is_i32) return kb::fail(ctx, KB_E_INVALID, "NULL table");
+    KB_TRY(kb::alloc_buf(ctx, (size_t)n_ids * sizeof(int32_t), &ctx->i32val));
+    KB_TRY(kb::alloc_buf(ctx, (size_t)n_ids, &ctx->isi32));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->i32val->p, val, (size_t)n_ids * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaMemcpyAsync(ctx->isi32->p, is_i32, (size_t)n_ids, cudaMemcpyHostToDevice, ctx->st));
+    KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
+    ctx->stats.h2d_bytes += (u64)n_ids * 5;
+    ctx->n_i32 = n_ids;
     return KB_OK;
 }
 

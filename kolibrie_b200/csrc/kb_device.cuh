@@ -292,6 +292,9 @@ struct NumTab {
     const double* num_or0;
     const u8* is_num;
     u32 n_ids;
+    const int* i32_val;  // legacy executor: the term parsed as i32 (kb_dict_legacy_i32_load); null when not loaded
+    const u8* is_i32;
+    u32 n_i32;
 };
 __device__ __forceinline__ double num_of(const NumTab& nt, u32 id) { return id < nt.n_ids ? __ldg(nt.num_or0 + id) : 0.0; }
 __device__ __forceinline__ bool isnum_of(const NumTab& nt, u32 id) { return id < nt.n_ids ? __ldg(nt.is_num + id) != 0 : false; }
@@ -339,6 +342,24 @@ static __device__ __noinline__ bool eval_filter_general(const FilterOp* ops, u32
             } break;
             case KB_F_TRUTHY: st[sp - 1] = (((okm >> (sp - 1)) & 1u) && st[sp - 1] != 0.0) ? 1.0 : 0.0; okm |= 1u << (sp - 1); break;
             case KB_F_IS_TRIPLE: st[sp] = (vals[op.slot] & 0x80000000u) ? 1.0 : 0.0; okm |= 1u << sp; sp++; break;
+            case KB_F_CMP_LEGACY: {  // sparql_database.rs:1420-1620: i32 comparison when both sides are integers, else string equality
+                const u32 id = vals[op.slot];
+                const u32 cmp = op.cmp & 0xFFu;
+                const bool nested = (op.cmp & KB_LEGACY_NESTED_F64) != 0u;
+                const bool both_int = !nested && (op.cmp & KB_LEGACY_CONST_IS_I32) && nt.is_i32 != nullptr && id < nt.n_i32 && __ldg(nt.is_i32 + id) != 0;
+                bool r;
+                if (nested && (op.cmp & KB_LEGACY_CONST_IS_I32) && isnum_of(nt, id)) {
+                    const double a = num_of(nt, id), b = op.value;
+                    r = cmp == KB_CMP_EQ ? a == b : cmp == KB_CMP_NE ? a != b : cmp == KB_CMP_GT ? a > b : cmp == KB_CMP_GE ? a >= b : cmp == KB_CMP_LT ? a < b : cmp == KB_CMP_LE ? a <= b : false;
+                } else if (both_int) {
+                    const int a = __ldg(nt.i32_val + id), b = (int)op.value;
+                    r = cmp == KB_CMP_EQ ? a == b : cmp == KB_CMP_NE ? a != b : cmp == KB_CMP_GT ? a > b : cmp == KB_CMP_GE ? a >= b : cmp == KB_CMP_LT ? a < b : cmp == KB_CMP_LE ? a <= b : false;
+                } else {
+                    const bool same = op.id != EMPTY32 && id == op.id;  // byte-wise equal strings <=> the same dictionary id
+                    r = cmp == KB_CMP_EQ ? same : cmp == KB_CMP_NE ? !same : false;
+                }
+                st[sp] = r ? 1.0 : 0.0; okm |= 1u << sp; sp++;
+            } break;
             default: return false;
         }
         if (sp > 11) return false;

@@ -142,6 +142,8 @@ struct kb_ctx {
     std::vector<kb::Segment> segs;
     kb::u64 n_triples = 0;
     kb::Buf num, isnum;
+    kb::Buf i32val, isi32;  // kb_dict_legacy_i32_load: the legacy executor's integer view of the terms
+    kb::u32 n_i32 = 0;
     kb::Buf dict_off, dict_bytes;  // kb_dict_strings_load: u64 offsets [dict_ids + 1] + UTF-8 bytes
     kb::u32 dict_ids = 0;
     kb::u32 n_ids = 0;

@@ -594,3 +594,118 @@ class Reasoner:
         cols = {s: rel.column(i) for i, s in enumerate(slots)}
         fixed = [None if v is None else self.dictionary.encode(v) for v in (subject, predicate, obj)]
         return [tuple(int(cols[k][i]) if fixed[k] is None else fixed[k] for k in range(3)) for i in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The LEGACY executor's BGP + FILTER stage (kolibrie/src/execute_query.rs:151-341 — the path `execute_query` takes: CLI, criterion bench,
+# README): patterns are joined one by one by perform_join_par_simd_with_strict_filter_1 (sparql_database.rs:2056-2213) over rows of
+# STRING bindings, then apply_filters_simd (sparql_database.rs:1381-1669). Its quirks, kept here because they decide the answer:
+#   * a pattern's predicate is compared as a string: a variable predicate ("?p") equals no predicate, the pattern matches nothing;
+#   * a constant SUBJECT is not enforced: the constant's text is used as a binding NAME, so it behaves like a variable (that joins with
+#     other occurrences of the same constant); a constant OBJECT is enforced (literal_filter) and bound under its own text as well;
+#   * FILTER comparison at the top level: i32 comparison when the bound term and the constant both parse as i32, byte-wise string
+#     = / != otherwise; the same comparison nested under AND / OR / NOT parses f64 instead (evaluate_filter_expression);
+#   * an operand containing + - * / goes to the reference's arithmetic-expression parser: not evaluated on the device (UNSUPPORTED).
+_I32 = re.compile(r"[+-]?[0-9]+")
+
+
+def rust_parse_i32(s: str) -> Optional[int]:
+    """`str::parse::<i32>()` acceptance: optional sign, ASCII digits, in range; nothing else"""
+    if not isinstance(s, str) or not _I32.fullmatch(s):
+        return None
+    v = int(s)
+    return v if -(1 << 31) <= v < (1 << 31) else None
+
+
+def _has_arith(s: str) -> bool:
+    return any(ch in s for ch in "+-*/")
+
+
+class LegacyExecutor:
+    def __init__(self, db: "SparqlDatabase"):
+        self.db = db
+        self._i32_loaded = -1
+
+    def _sync(self):
+        db = self.db
+        db._sync()
+        n = len(db.dictionary.id_to_string)
+        if n != self._i32_loaded and hasattr(db.ctx, "dict_legacy_i32_load"):
+            val = np.zeros(n, dtype=np.int32)
+            isi = np.zeros(n, dtype=np.uint8)
+            for i, st in enumerate(db.dictionary.id_to_string):
+                v = rust_parse_i32(st)
+                if v is not None:
+                    val[i] = v
+                    isi[i] = 1
+            db.ctx.dict_legacy_i32_load(val, isi)
+            self._i32_loaded = n
+
+    def _compile_filter(self, e, slots: SlotMap, nested: bool, ops: List[c.KbFilterOp]):
+        d = self.db.dictionary
+        if isinstance(e, Comparison):
+            if _has_arith(e.var) or _has_arith(e.value):
+                raise c.KolibrieError(c.KB_E_UNSUPPORTED, "operands with + - * / go through the reference's arithmetic-expression parser")
+            if not e.var.startswith("?") or e.value.startswith("?"):
+                raise c.KolibrieError(c.KB_E_UNSUPPORTED, "legacy FILTER: variable <op> constant only")
+            cmpc = {">": c.CMP_GT, ">=": c.CMP_GE, "<": c.CMP_LT, "<=": c.CMP_LE, "=": c.CMP_EQ, "!=": c.CMP_NE}.get(e.op)
+            if cmpc is None:
+                raise c.KolibrieError(c.KB_E_UNSUPPORTED, f"operator {e.op!r}: the reference evaluates it to false")
+            name = _strip(e.var)
+            if name not in slots.slot:
+                raise c.KolibrieError(c.KB_E_UNSUPPORTED, "FILTER on an unbound variable: the reference evaluates it to false")
+            lit = d.lookup(e.value)
+            num = rust_parse_f64(e.value) if nested else rust_parse_i32(e.value)
+            flags = (c.LEGACY_CONST_IS_I32 if num is not None else 0) | (c.LEGACY_NESTED_F64 if nested else 0)
+            ops.append(c.fop(c.F_CMP_LEGACY, slot=slots.slot[name], cmp=cmpc | flags, id=c.KB_ID_NONE if lit is None else lit, value=float(num) if num is not None else 0.0))
+        elif isinstance(e, And):
+            self._compile_filter(e.left, slots, True, ops); self._compile_filter(e.right, slots, True, ops); ops.append(c.fop(c.F_AND))
+        elif isinstance(e, Or):
+            self._compile_filter(e.left, slots, True, ops); self._compile_filter(e.right, slots, True, ops); ops.append(c.fop(c.F_OR))
+        elif isinstance(e, Not):
+            self._compile_filter(e.inner, slots, True, ops); ops.append(c.fop(c.F_NOT))
+        elif isinstance(e, FunctionCall) and e.name == "isTRIPLE" and e.args and e.args[0].startswith("?") and _strip(e.args[0]) in slots.slot:
+            ops.append(c.fop(c.F_IS_TRIPLE, slot=slots.slot[_strip(e.args[0])]))
+        else:
+            raise c.KolibrieError(c.KB_E_UNSUPPORTED, f"legacy FILTER construct {type(e).__name__}")
+
+    def execute_bgp(self, patterns: Sequence[Tuple[str, str, str]], filters: Sequence[object] = (), select: Optional[Sequence[str]] = None) -> List[Dict[str, str]]:
+        """patterns: (subject, predicate, object) as RESOLVED strings, variables start with '?'. Returns rows of string bindings for the
+        variables (pseudo-bindings named after constants are dropped unless selected)."""
+        db = self.db
+        self._sync()
+        d = db.dictionary
+        slots = SlotMap()
+        pats, eqs = [], []
+        for s_, p_, o_ in patterns:
+            if p_.startswith("?"):
+                return []  # the predicate string "?p" equals no predicate (sparql_database.rs:2136)
+            pid = d.lookup(p_)
+            if pid is None:
+                return []
+            # a constant subject / object is a binding NAME in the legacy join: one slot per distinct text
+            st = c.V(slots.of(s_ if s_.startswith("?") else "?\x00" + s_))  # "\x00<text>": a name no variable can have
+            ot = c.V(slots.of(o_ if o_.startswith("?") else "?\x00" + o_))
+            if not o_.startswith("?"):  # literal_filter: the object string must equal the constant
+                oid = d.lookup(o_)
+                if oid is None:
+                    return []
+                eqs.append(c.fop(c.F_EQ_ID, slot=ot.value, id=oid))
+            pats.append(c.pattern(st, c.K(pid), ot))
+        ops: List[c.KbFilterOp] = []
+        for i, e in enumerate(eqs):
+            ops.append(e)
+            if i:
+                ops.append(c.fop(c.F_AND))
+        for f in filters:  # filters.iter().all(...): a conjunction of top-level expressions
+            had = bool(ops)
+            self._compile_filter(f, slots, False, ops)
+            if had:
+                ops.append(c.fop(c.F_AND))
+        rel = db.ctx.bgp_execute(pats, ops or None)
+        n, rslots = rel.info()
+        names = [slots.names[s_] for s_ in rslots]
+        keep = [j for j, nm in enumerate(names) if (select is None and any(nm == _strip(t) for pt in patterns for t in (pt[0], pt[2]) if t.startswith("?")))
+                or (select is not None and ("?" + nm) in select)]
+        cols = {j: rel.column(j) for j in keep}
+        return [{"?" + names[j]: db.decode_term(int(cols[j][i])) for j in keep} for i in range(n)]
