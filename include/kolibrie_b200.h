@@ -336,6 +336,18 @@ KB_API kb_status kb_rel_wrap_device(kb_ctx* ctx, const uint32_t* slots, uint32_t
 KB_API kb_status kb_rel_from_device(kb_ctx* ctx, const uint32_t* slots, uint32_t n_cols, const uint32_t* const* d_cols, uint64_t n_rows, kb_rel** out);
 KB_API kb_status kb_store_download(kb_ctx* ctx, uint32_t* s, uint32_t* p, uint32_t* o, uint64_t cap, uint64_t* n);
 
+/* ------------------------------------------------------------------ on-disk columnar segments (the device store's layout on disk; the
+ * reference persists SSTables of triples, kolibrie/src/disk_storage/sstable.rs:40-85). File = one 4096-byte header (triple count, tag,
+ * id range and checksum of each column) + the s, p, o columns, each starting at a 4096-byte boundary.
+ * kb_segment_write / kb_segment_info are host-only (no device needed). kb_segment_save writes the store segment(s) tagged `tag` (or
+ * the whole store when whole_store != 0). kb_store_append_file streams a file into a NEW store segment tagged `tag` through two
+ * pinned staging buffers (file reads overlap the host->device copies); the header's column ranges replace the load-time statistics
+ * kernels; verify != 0 checks the column checksums while reading. The store index is maintained as for kb_store_append. */
+KB_API kb_status kb_segment_write(const char* path, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint64_t tag);
+KB_API kb_status kb_segment_info(const char* path, uint64_t* n_triples, uint64_t* tag, uint32_t* cmin /* [3] or NULL */, uint32_t* cmax /* [3] or NULL */);
+KB_API kb_status kb_segment_save(kb_ctx* ctx, uint64_t tag, int whole_store, const char* path);
+KB_API kb_status kb_store_append_file(kb_ctx* ctx, const char* path, uint64_t tag, int verify);
+
 /* ------------------------------------------------------------------ one-shot host-buffer entries (end-to-end measurement and the
  * reference's per-call GPU usage, sparql_database.rs:3193-3353): upload (chunked, overlapped with the scan), star-join, download.
  * The store of ctx is REPLACED by the uploaded triples (and is left empty when the call fails). Patterns and filter are validated

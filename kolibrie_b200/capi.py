@@ -200,6 +200,10 @@ def lib() -> C.CDLL:
         "kb_partition": (i32, [vp, vp, u32, u32, P(vp), P(u64)]),
         "kb_partition_counts": (i32, [vp, vp, u32, u32, P(u64)]),
         "kb_shuffle_scatter": (i32, [vp, vp, u32, u32, P(vp), P(u64), u64]),
+        "kb_segment_write": (i32, [C.c_char_p, vp, vp, vp, u64, u64]),
+        "kb_segment_info": (i32, [C.c_char_p, P(u64), P(u64), P(u32), P(u32)]),
+        "kb_segment_save": (i32, [vp, u64, C.c_int, C.c_char_p]),
+        "kb_store_append_file": (i32, [vp, C.c_char_p, u64, C.c_int]),
         "kb_shuffle_push": (i32, [vp, vp, u32, u32, P(vp), P(vp), u64]),
         "kb_rel_wrap_device": (i32, [vp, P(u32), u32, P(vp), u64, P(vp)]),
         "kb_star_join_host": (i32, [vp, vp, vp, vp, u64, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), P(u32), P(vp), P(u64)]),
@@ -221,7 +225,7 @@ EXPORTED_SYMBOLS = [
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_bind_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_groups_pack", "kb_groups_merge", "kb_star_join_aggregate",
     "kb_star_join_prepare", "kb_plan_submit", "kb_plan_collect", "kb_plan_info", "kb_plan_free", "kb_plan_peer_scratch_bytes", "kb_plan_attach_peers",
-    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_shuffle_scatter", "kb_shuffle_push", "kb_rel_wrap_device", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
+    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_segment_write", "kb_segment_info", "kb_segment_save", "kb_store_append_file", "kb_shuffle_scatter", "kb_shuffle_push", "kb_rel_wrap_device", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
 ]
 
 
@@ -361,6 +365,14 @@ class Context:
 
     def store_clear(self):
         self._check(lib().kb_store_clear(self.h))
+
+    def segment_save(self, path: str, tag: Optional[int] = None):
+        """kb_segment_save: the segment(s) tagged `tag` — or the whole store when tag is None — as one columnar segment file"""
+        self._check(lib().kb_segment_save(self.h, 0 if tag is None else tag, 1 if tag is None else 0, path.encode()))
+
+    def store_append_file(self, path: str, tag: int, verify: bool = True):
+        """kb_store_append_file: stream a columnar segment file into a new store segment"""
+        self._check(lib().kb_store_append_file(self.h, path.encode(), tag, 1 if verify else 0))
 
     def build_index(self):
         """SparqlDatabase::build_all_indexes on the device: partition the store by predicate. Returns (n_predicates, build_ms)."""
@@ -756,3 +768,21 @@ def legacy_hash_join_cuda(subjects, predicates, objects, predicate_filter: int, 
     if idx:
         libc.free(C.cast(idx, C.c_void_p))  # the Rust side frees it through Vec's drop = libc free
     return out
+
+
+def segment_write(path: str, s, p, o, tag: int = 0):
+    """kb_segment_write (host only): three u32 columns as a columnar segment file"""
+    s, p, o = _u32(s), _u32(p), _u32(o)
+    rc = lib().kb_segment_write(path.encode(), _ptr(s), _ptr(p), _ptr(o), len(s), tag)
+    if rc != KB_OK:
+        raise KolibrieError(rc, f"cannot write {path}")
+
+
+def segment_info(path: str):
+    """kb_segment_info (host only): (n_triples, tag, cmin[3], cmax[3]) of a segment file"""
+    n, tag = C.c_uint64(), C.c_uint64()
+    lo, hi = (C.c_uint32 * 3)(), (C.c_uint32 * 3)()
+    rc = lib().kb_segment_info(path.encode(), C.byref(n), C.byref(tag), lo, hi)
+    if rc != KB_OK:
+        raise KolibrieError(rc, f"{path} is not a segment file")
+    return n.value, tag.value, list(lo), list(hi)

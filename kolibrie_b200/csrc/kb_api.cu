@@ -1959,6 +1959,15 @@ static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, cons
                     std::chrono::duration<double, std::milli>(t1 - t0).count(),
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
     }
+    return kb::store_add_device_segment(ctx, sg);
+}
+
+}  // extern "C"
+namespace kb {
+// a segment whose columns are already in HBM joins the store: version bump, cached knowledge dropped, index maintained (or dropped)
+kb_status store_add_device_segment(kb_ctx* ctx, Segment& sg) {
+    if (sg.n && !sg.has_stats) KB_TRY(segment_stats(ctx, &sg));
+    const u64 n = sg.n;
     const bool maintain = ctx->index_maintain && ctx->index_version == ctx->store_version && !ctx->index.empty();
     ctx->segs.push_back(sg);
     ctx->n_triples += n;
@@ -1979,6 +1988,8 @@ static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, cons
     ctx->index_version = ~0ull;
     return KB_OK;
 }
+}  // namespace kb
+extern "C" {
 
 kb_status kb_store_clear(kb_ctx* ctx) {
     KB_ENTER(ctx);

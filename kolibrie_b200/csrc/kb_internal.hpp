@@ -284,6 +284,7 @@ void groups_from_records(const GroupRecord* recs, u64 n, u32 n_group, const kb_a
 kb_status segment_stats(kb_ctx* ctx, Segment* sg);
 kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable);
 kb_status index_evict_tag(kb_ctx* ctx, u64 tag);
+kb_status store_add_device_segment(kb_ctx* ctx, Segment& sg);
 kb_status unpair_rel(kb_ctx* ctx, std::unique_ptr<kb_rel>* r);
 kb_status filter_impl(kb_ctx* ctx, const kb_rel& in, const FilterProg& f, std::unique_ptr<kb_rel>* out);
 kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const FilterProg* post, std::unique_ptr<kb_rel>* out);
