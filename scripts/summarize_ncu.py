@@ -77,7 +77,7 @@ if __name__ == "__main__":
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    for fam in ("scan", "build", "probe", "probe_index", "derive"):
+    for fam in ("scan", "build", "probe", "probe_index", "derive", "derivepart"):
         rep = os.path.join(ROOT, "gpurun_out", f"prof_{fam}_{tag}.ncu-rep")
         if os.path.exists(rep):
             summarize(rep, f"{fam}_{tag}", fam, traffic)
