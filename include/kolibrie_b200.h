@@ -175,6 +175,9 @@ KB_API kb_status kb_store_load(kb_ctx* ctx, const uint32_t* s, const uint32_t* p
 /* same, columns already in device memory of ctx's device (copied device-to-device) */
 KB_API kb_status kb_store_load_device(kb_ctx* ctx, const uint32_t* d_s, const uint32_t* d_p, const uint32_t* d_o, uint64_t n);
 KB_API kb_status kb_store_append(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint64_t segment_tag);
+/* kb_store_append for a slide whose columns are already in device memory of ctx's device (the receive side of kb_shuffle_push, a
+ * producer kernel): copied device-to-device into a new segment; the store index is maintained exactly as for kb_store_append */
+KB_API kb_status kb_store_append_device(kb_ctx* ctx, const uint32_t* d_s, const uint32_t* d_p, const uint32_t* d_o, uint64_t n, uint64_t segment_tag);
 KB_API kb_status kb_store_evict(kb_ctx* ctx, uint64_t segment_tag);
 /* set-difference by value (SparqlDatabase::delete_triple, sparql_database.rs:229-242) */
 KB_API kb_status kb_store_delete(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n);

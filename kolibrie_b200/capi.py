@@ -150,6 +150,7 @@ def lib() -> C.CDLL:
         "kb_synchronize": (i32, [vp]),
         "kb_store_load": (i32, [vp, vp, vp, vp, u64]),
         "kb_store_load_device": (i32, [vp, vp, vp, vp, u64]),
+        "kb_store_append_device": (i32, [vp, vp, vp, vp, u64, u64]),
         "kb_store_append": (i32, [vp, vp, vp, vp, u64, u64]),
         "kb_store_evict": (i32, [vp, u64]),
         "kb_store_delete": (i32, [vp, vp, vp, vp, u64]),
@@ -220,7 +221,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "kb_version", "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_set_timing", "kb_get_stats", "kb_synchronize",
-    "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
+    "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_append_device", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
     "kb_store_download", "kb_dict_numeric_load", "kb_dict_legacy_i32_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_bind_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_groups_pack", "kb_groups_merge", "kb_star_join_aggregate",
@@ -355,6 +356,10 @@ class Context:
     def store_append(self, s, p, o, tag: int):
         s, p, o = _u32(s), _u32(p), _u32(o)
         self._check(lib().kb_store_append(self.h, _ptr(s), _ptr(p), _ptr(o), len(s), tag))
+
+    def store_append_device(self, d_s: int, d_p: int, d_o: int, n: int, tag: int):
+        """a slide whose columns are already in this device's memory (copied device-to-device; index maintained as store_append)"""
+        self._check(lib().kb_store_append_device(self.h, C.c_void_p(d_s), C.c_void_p(d_p), C.c_void_p(d_o), n, tag))
 
     def store_evict(self, tag: int):
         self._check(lib().kb_store_evict(self.h, tag))

@@ -43,7 +43,29 @@ kb_status alloc_buf(kb_ctx* ctx, size_t bytes, Buf* out) {
     b->bytes = round256(bytes) + 256;  // every column can be over-read to the next 16-byte boundary by the TMA tile loads
     b->st = ctx->st;
     b->life = ctx->life;
+    if (b->bytes >= Life::MIN_BYTES) {  // best fit among the recycled buffers (at most 25 % larger than asked)
+        Life& L = *ctx->life;
+        int best = -1;
+        for (size_t i = 0; i < L.cache.size(); i++)
+            if (L.cache[i].bytes >= b->bytes && L.cache[i].bytes <= b->bytes + b->bytes / 4 && (best < 0 || L.cache[i].bytes < L.cache[best].bytes)) best = (int)i;
+        if (best >= 0) {
+            b->p = L.cache[best].p;
+            b->bytes = L.cache[best].bytes;
+            L.cached_bytes -= b->bytes;
+            L.cache.erase(L.cache.begin() + best);
+            *out = b;
+            return KB_OK;
+        }
+    }
     cudaError_t e = cudaMallocAsync(&b->p, b->bytes, ctx->st);
+    if (e != cudaSuccess && !ctx->life->cache.empty()) {  // out of memory with buffers parked in the cache: give them back and try once more
+        cudaGetLastError();
+        for (auto& cb : ctx->life->cache) cudaFreeAsync(cb.p, ctx->st);
+        ctx->life->cache.clear();
+        ctx->life->cached_bytes = 0;
+        cudaStreamSynchronize(ctx->st);
+        e = cudaMallocAsync(&b->p, b->bytes, ctx->st);
+    }
     if (e != cudaSuccess) {
         b->p = nullptr;
         cudaGetLastError();
@@ -287,18 +309,25 @@ kb_status check_pattern(kb_ctx* ctx, const kb_pattern& pt) {
 // scan
 kb_status segment_stats(kb_ctx* ctx, Segment* sg) {
     if ((sg->has_stats && sg->stats_world == ctx->shard_world) || sg->n == 0) { sg->has_stats = true; sg->stats_world = ctx->shard_world; return KB_OK; }
-    const u32 off = ctrl_alloc(ctx, 8);
-    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0xFF, 4 * sizeof(u32), ctx->st));
-    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off + 4, 0, 4 * sizeof(u32), ctx->st));
-    const u32* cols[3] = {sg->s.ptr, sg->p.ptr, sg->o.ptr};
-    timer_begin(ctx, F_OTHER, 3);
-    for (int c = 0; c < 3; c++) launch_col_minmax(cols[c], (u32)sg->n, ctx->ctrl + off + c, ctx->ctrl + off + 4 + c, ctx->n_sms, ctx->st);
-    if (ctx->shard_world > 1) launch_count_foreign(sg->s.ptr, (u32)sg->n, ctx->shard_rank, ctx->shard_world, ctx->ctrl + off + 7, ctx->n_sms, ctx->st);
+    // one pass: column ranges, foreign subjects, distinct predicates + their row counts (segment_profile_kernel)
+    const u32 off = ctrl_alloc(ctx, SEGP_WORDS);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0xFF, SEGP_MAX * sizeof(u32), ctx->st));
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off + SEGP_MAX, 0, (SEGP_WORDS - SEGP_MAX) * sizeof(u32), ctx->st));
+    timer_begin(ctx, F_OTHER);
+    launch_segment_profile(sg->s.ptr, sg->p.ptr, sg->o.ptr, (u32)sg->n, ctx->shard_rank, ctx->shard_world, ctx->ctrl + off, ctx->n_sms, ctx->st);
     timer_end(ctx);
     KB_CUDA(ctx, cudaGetLastError());
     KB_TRY(ctrl_read(ctx));
-    for (int c = 0; c < 3; c++) { sg->cmin[c] = ctx->h_ctrl[off + c]; sg->cmax[c] = ctx->h_ctrl[off + 4 + c]; }
-    sg->sharded_ok = ctx->h_ctrl[off + 7] == 0;  // key compaction is only sound when every subject is ours
+    const u32* h = ctx->h_ctrl + off;
+    for (int c = 0; c < 3; c++) { sg->cmin[c] = h[SEGP_MIN + c]; sg->cmax[c] = h[SEGP_MAX + c]; }
+    sg->sharded_ok = h[SEGP_FOREIGN] == 0;  // key compaction is only sound when every subject is ours
+    sg->pred_rows.clear();
+    sg->preds_overflow = h[SEGP_OVERFLOW] != 0;
+    sg->has_preds = true;
+    if (!sg->preds_overflow) {
+        for (u32 i = 0; i < SEGP_SLOTS; i++) if (h[SEGP_SLOT + i] != EMPTY32) sg->pred_rows.push_back({h[SEGP_SLOT + i], h[SEGP_COUNT + i]});
+        std::sort(sg->pred_rows.begin(), sg->pred_rows.end());
+    }
     sg->stats_world = ctx->shard_world;
     sg->has_stats = true;
     return KB_OK;
@@ -1038,11 +1067,14 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
             P.n_seg = 0;
             P.n_tiles = 0;
             if (tab_mode) {
-                P.ptab = static_cast<const u32*>(PS.xtab->p);
-                P.pnum = P.pre_mode == 1u ? static_cast<const double*>(PS.xnum->p) : nullptr;
-                P.ptab_min = PS.xtab_min;
-                // walk the slots that can hold a key (up to the largest subject), not the table's growth headroom
-                P.ptab_range = std::min<u32>(PS.xtab_range, compact_key(PS.xmax, PS.tab_cshift) - PS.xtab_min + 1u);
+                // walk the slots that can hold a key (smallest to largest live subject), not the table's growth headroom nor the
+                // slots an evicted past has left empty; the first slot stays 128-byte aligned for the bulk loads
+                const u32 lo = ((compact_key(PS.xmin, PS.tab_cshift) - PS.xtab_min) / 32u) * 32u;
+                const u32 hi = std::min<u32>(PS.xtab_range, compact_key(PS.xmax, PS.tab_cshift) - PS.xtab_min + 1u);
+                P.ptab = static_cast<const u32*>(PS.xtab->p) + lo;
+                P.pnum = P.pre_mode == 1u ? static_cast<const double*>(PS.xnum->p) + lo : nullptr;
+                P.ptab_min = PS.xtab_min + lo;
+                P.ptab_range = hi > lo ? hi - lo : 0u;
                 P.ptab_cshift = PS.tab_cshift;
                 P.shard_rank = ctx->shard_rank;
                 P.n_tiles = (u32)(((u64)P.ptab_range + PROBEF_TILE - 1) / PROBEF_TILE);
@@ -1889,6 +1921,9 @@ void kb_ctx_destroy(kb_ctx* ctx) {
     ctx->dict_bytes.reset();
     ctx->tile_state.reset();
     ctx->block_state.reset();
+    for (auto& cb : ctx->life->cache) cudaFreeAsync(cb.p, ctx->st);
+    ctx->life->cache.clear();
+    ctx->life->cached_bytes = 0;
     cudaStreamSynchronize(ctx->st);
     ctx->life->alive = false;  // buffers still referenced by live relations fall back to cudaFree
     for (auto e : ctx->ev_pool) cudaEventDestroy(e);
@@ -1950,9 +1985,11 @@ static kb_status store_add_segment(kb_ctx* ctx, const u32* s, const u32* p, cons
         KB_CUDA(ctx, cudaMemcpyAsync(sg.s.ptr, s, n * sizeof(u32), kind, ctx->st));
         KB_CUDA(ctx, cudaMemcpyAsync(sg.p.ptr, p, n * sizeof(u32), kind, ctx->st));
         KB_CUDA(ctx, cudaMemcpyAsync(sg.o.ptr, o, n * sizeof(u32), kind, ctx->st));
-        KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));  // the caller's buffers are borrowed for this call only
+        if (trace) KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
         const auto t1 = std::chrono::steady_clock::now();
         if (kind == cudaMemcpyHostToDevice) ctx->stats.h2d_bytes += 3 * n * sizeof(u32);
+        // the statistics pass ends with a read-back on the same stream: when it returns the copies are done too (the caller's
+        // buffers are borrowed for this call only)
         KB_TRY(kb::segment_stats(ctx, &sg));
         if (trace)
             fprintf(stderr, "[kb trace] segment of %llu triples: copies %.3f ms, statistics %.3f ms\n", (unsigned long long)n,
@@ -2020,6 +2057,10 @@ kb_status kb_store_load_device(kb_ctx* ctx, const uint32_t* s, const uint32_t* p
 kb_status kb_store_append(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint64_t tag) {
     KB_ENTER(ctx);
     return store_add_segment(ctx, s, p, o, n, tag, cudaMemcpyHostToDevice);
+}
+kb_status kb_store_append_device(kb_ctx* ctx, const uint32_t* s, const uint32_t* p, const uint32_t* o, uint64_t n, uint64_t tag) {
+    KB_ENTER(ctx);
+    return store_add_segment(ctx, s, p, o, n, tag, cudaMemcpyDeviceToDevice);
 }
 kb_status kb_store_evict(kb_ctx* ctx, uint64_t tag) {
     KB_ENTER(ctx);
@@ -2092,10 +2133,112 @@ static kb_status slice_table_update(kb_ctx* ctx, PredSlice& ps, u32 y, int added
 }
 
 // index the triples of ONE store segment: a chunk per predicate it carries, ranges, persistent tables, typed literal columns
+// the slide-sized case of index_add_segment: the segment's predicates and their row counts are known from its profile pass, so the
+// chunks are allocated exactly and ONE kernel files every triple (segment_split_kernel); one read-back
+static kb_status index_add_segment_split(kb_ctx* ctx, const Segment& sg, u32 cshift) {
+    const u32 k = (u32)sg.pred_rows.size();
+    SplitParams P{};
+    P.s = sg.s.ptr; P.p = sg.p.ptr; P.o = sg.o.ptr;
+    P.n = (u32)sg.n;
+    P.k = k;
+    P.nt = numtab(ctx);
+    const u32 off = ctrl_alloc(ctx, k * SPLIT_WORDS);
+    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0, k * SPLIT_WORDS * sizeof(u32), ctx->st));
+    P.ctrl = ctx->ctrl + off;
+    std::vector<SliceChunk> chs(k);
+    bool rebuild[MAXP][2];
+    for (u32 i = 0; i < k; i++) {
+        PredSlice& ps = ctx->index[sg.pred_rows[i].first];
+        SliceChunk& ch = chs[i];
+        ch.tag = sg.tag;
+        ch.n = sg.pred_rows[i].second;
+        KB_TRY(alloc_col(ctx, 2 * ch.n, &ch.pairs));
+        if (ctx->n_ids) KB_TRY(alloc_buf(ctx, ch.n * sizeof(double), &ch.ynum));
+        SplitEntry& e = P.e[i];
+        e.pred = sg.pred_rows[i].first;
+        e.n = (u32)ch.n;
+        e.pairs = reinterpret_cast<uint2*>(ch.pairs.ptr);
+        e.ynum = ch.ynum ? static_cast<double*>(ch.ynum->p) : nullptr;
+        const bool xok = ps.xtab && ps.tab_cshift == cshift;
+        rebuild[i][0] = ps.xtab ? !xok : !ps.x_tried;
+        rebuild[i][1] = !ps.ytab && !ps.y_tried;
+        if (xok) { e.xtab = static_cast<u32*>(ps.xtab->p); e.xtab_min = ps.xtab_min; e.xtab_range = ps.xtab_range; e.cshift = cshift; }
+        if (xok && ps.xnum && ps.xnum_version == ctx->num_version && ctx->n_ids) e.xnum = static_cast<double*>(ps.xnum->p);
+        else ps.xnum.reset();
+        if (ps.ytab) { e.ytab = static_cast<u32*>(ps.ytab->p); e.ytab_min = ps.ytab_min; e.ytab_range = ps.ytab_range; }
+    }
+    timer_begin(ctx, F_OTHER);
+    launch_segment_split(P, ctx->n_sms, ctx->st);
+    timer_end(ctx);
+    ctx->stats.kernel_launches++;
+    KB_CUDA(ctx, cudaGetLastError());
+    KB_TRY(ctrl_read(ctx));
+    const u32 uoff = ctrl_alloc(ctx, 2 * MAXP);
+    bool any_touched = false;
+    std::vector<char> touched(2 * k, 0);
+    std::vector<int> chunk_of(k, -1);
+    for (u32 i = 0; i < k; i++) {
+        const u32* h = ctx->h_ctrl + off + i * SPLIT_WORDS;
+        PredSlice& ps = ctx->index[sg.pred_rows[i].first];
+        SliceChunk& ch = chs[i];
+        if (h[SPLIT_CURSOR] != ch.n) return fail(ctx, KB_E_CUDA, "index maintenance: predicate %u has %u rows, its profile said %llu", sg.pred_rows[i].first,
+                                                  h[SPLIT_CURSOR], (unsigned long long)ch.n);
+        ch.xmin = ~h[SPLIT_XMIN]; ch.ymin = ~h[SPLIT_YMIN]; ch.xmax = h[SPLIT_XMAX]; ch.ymax = h[SPLIT_YMAX];
+        if (ch.ynum && h[SPLIT_NNUM] > 0) ch.ynum_version = ctx->num_version;
+        else { ch.ynum.reset(); ps.xnum.reset(); }
+        ps.xmin = std::min(ps.xmin, ch.xmin); ps.ymin = std::min(ps.ymin, ch.ymin);
+        ps.xmax = std::max(ps.xmax, ch.xmax); ps.ymax = std::max(ps.ymax, ch.ymax);
+        chunk_of[i] = (int)ps.chunks.size();
+        ps.chunks.push_back(ch);
+        ps.n += ch.n;
+        if (ps.chunks.size() > 1) { ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset(); }  // the directories describe one chunk
+        if (h[SPLIT_XDUP]) { ps.x_unique = false; ps.xtab.reset(); ps.xnum.reset(); }  // a subject occurs twice
+        if (h[SPLIT_YDUP]) { ps.y_unique = false; ps.ytab.reset(); }
+        if (h[SPLIT_XOUT] && ps.xtab) rebuild[i][0] = true;  // a key outside the table: rebuild it over every chunk, with new headroom
+        if (h[SPLIT_YOUT] && ps.ytab) rebuild[i][1] = true;
+    }
+    for (u32 i = 0; i < k; i++) {
+        PredSlice& ps = ctx->index[sg.pred_rows[i].first];
+        for (u32 y = 0; y < 2; y++) {
+            if (!rebuild[i][y]) continue;
+            if (!any_touched) { KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + uoff, 0, 2 * MAXP * sizeof(u32), ctx->st)); any_touched = true; }
+            Buf& tab = y ? ps.ytab : ps.xtab;
+            tab.reset();  // slice_table_update sees no table: a rebuild over all chunks (the new one included)
+            if (y) ps.y_tried = false; else ps.x_tried = false;
+            bool t = false;
+            KB_TRY(slice_table_update(ctx, ps, y, chunk_of[i], cshift, uoff + 2 * i + y, &t));
+            touched[2 * i + y] = t ? 1 : 0;
+        }
+    }
+    if (any_touched) {
+        KB_CUDA(ctx, cudaGetLastError());
+        KB_TRY(ctrl_read(ctx));
+        for (u32 i = 0; i < k; i++) {
+            PredSlice& ps = ctx->index[sg.pred_rows[i].first];
+            if (touched[2 * i] && ctx->h_ctrl[uoff + 2 * i]) { ps.x_unique = false; ps.xtab.reset(); }
+            if (touched[2 * i + 1] && ctx->h_ctrl[uoff + 2 * i + 1]) { ps.y_unique = false; ps.ytab.reset(); }
+        }
+    }
+    return KB_OK;
+}
+
 kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable) {
     *indexable = true;
     Segment sg = ctx->segs[seg_idx];
     if (sg.n == 0) return KB_OK;
+    static const bool split_ok = !(getenv("KOLIBRIE_INDEX_SPLIT") && getenv("KOLIBRIE_INDEX_SPLIT")[0] == '0');
+    if (split_ok && !ctx->in_full_index_build && sg.has_stats && sg.stats_world == ctx->shard_world && sg.has_preds && !sg.preds_overflow &&
+        sg.pred_rows.size() <= MAXP) {
+        size_t n_new = 0;
+        for (auto& pr : sg.pred_rows) n_new += ctx->index.count(pr.first) ? 0 : 1;
+        if (ctx->index.size() + n_new <= 4096) {
+            u32 cshift = 0;  // subject-sharded store: compact the subject keys (see compact_key)
+            bool sharded = ctx->shard_world > 1 && (ctx->shard_world & (ctx->shard_world - 1)) == 0;
+            for (auto& g : ctx->segs) if (g.n && g.has_stats && !g.sharded_ok) sharded = false;
+            if (sharded) while ((1u << cshift) < ctx->shard_world) cshift++;
+            return index_add_segment_split(ctx, sg, cshift);
+        }
+    }
     // 1. distinct predicates of the segment
     const u32 set_slots = 8192;
     Buf set;
@@ -2172,8 +2315,13 @@ kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable) {
         for (u32 i = 0; i < k; i++) {
             if (chunk_of[i] < 0) continue;
             PredSlice& ps = ctx->index[preds[b + i]];
-            ps.xmin = std::min(ps.xmin, ctx->h_ctrl[soff + 4 * i]); ps.ymin = std::min(ps.ymin, ctx->h_ctrl[soff + 4 * i + 1]);
-            ps.xmax = std::max(ps.xmax, ctx->h_ctrl[soff + 4 * i + 2]); ps.ymax = std::max(ps.ymax, ctx->h_ctrl[soff + 4 * i + 3]);
+            {
+                SliceChunk& ch = ps.chunks[chunk_of[i]];
+                ch.xmin = ctx->h_ctrl[soff + 4 * i]; ch.ymin = ctx->h_ctrl[soff + 4 * i + 1];
+                ch.xmax = ctx->h_ctrl[soff + 4 * i + 2]; ch.ymax = ctx->h_ctrl[soff + 4 * i + 3];
+                ps.xmin = std::min(ps.xmin, ch.xmin); ps.ymin = std::min(ps.ymin, ch.ymin);
+                ps.xmax = std::max(ps.xmax, ch.xmax); ps.ymax = std::max(ps.ymax, ch.ymax);
+            }
             for (u32 y = 0; y < 2; y++) {
                 bool t = false;
                 KB_TRY(slice_table_update(ctx, ps, y, chunk_of[i], cshift, uoff + 2 * i + y, &t));
@@ -2204,23 +2352,45 @@ kb_status index_add_segment(kb_ctx* ctx, size_t seg_idx, bool* indexable) {
 
 // eviction of the segment(s) tagged `tag`: their chunks leave the slices, their keys leave the persistent tables
 kb_status index_evict_tag(kb_ctx* ctx, u64 tag) {
+    ClearParams C{};
+    std::vector<SliceChunk> dying;  // kept until the clears are queued: their buffers are released stream-ordered behind them
+    auto flush = [&]() {
+        if (C.k) { launch_clear_chunks(C, ctx->n_sms, ctx->st); ctx->stats.kernel_launches++; }
+        C.k = 0;
+    };
     for (auto it = ctx->index.begin(); it != ctx->index.end();) {
         PredSlice& ps = it->second;
+        bool hit = false;
         for (size_t c = 0; c < ps.chunks.size();) {
             SliceChunk& ch = ps.chunks[c];
             if (ch.tag != tag) { c++; continue; }
-            if (ps.xtab) launch_clear_direct_pairs(reinterpret_cast<const uint2*>(ch.pairs.ptr), 0u, (u32)ch.n, static_cast<u32*>(ps.xtab->p), ps.xtab_min, ps.xtab_range,
-                                                   ps.tab_cshift, ctx->n_sms, ctx->st);
-            if (ps.ytab) launch_clear_direct_pairs(reinterpret_cast<const uint2*>(ch.pairs.ptr), 1u, (u32)ch.n, static_cast<u32*>(ps.ytab->p), ps.ytab_min, ps.ytab_range, 0u,
-                                                   ctx->n_sms, ctx->st);
-            ctx->stats.kernel_launches += (ps.xtab ? 1 : 0) + (ps.ytab ? 1 : 0);
+            hit = true;
+            if ((ps.xtab || ps.ytab) && ch.n) {
+                ClearEntry& e = C.e[C.k++];
+                e = ClearEntry{};
+                e.pairs = reinterpret_cast<const uint2*>(ch.pairs.ptr);
+                e.n = (u32)ch.n;
+                if (ps.xtab) { e.xtab = static_cast<u32*>(ps.xtab->p); e.xtab_min = ps.xtab_min; e.xtab_range = ps.xtab_range; e.cshift = ps.tab_cshift; }
+                if (ps.ytab) { e.ytab = static_cast<u32*>(ps.ytab->p); e.ytab_min = ps.ytab_min; e.ytab_range = ps.ytab_range; }
+                if (C.k == CLEAR_MAX) flush();
+            }
             ps.n -= ch.n;
-            ps.chunks.erase(ps.chunks.begin() + c);  // the chunk's buffers are released stream-ordered, after the clears above
-            ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset(); ps.xnum.reset();
+            dying.push_back(ch);
+            ps.chunks.erase(ps.chunks.begin() + c);
+            ps.xoff.reset(); ps.xval.reset(); ps.yoff.reset(); ps.yval.reset();  // (xnum stays: its slots are only read where xtab holds a key)
+        }
+        if (hit) {  // the slice's id ranges shrink to the surviving chunks': a long-running window does not walk its whole past
+            ps.xmin = ps.ymin = 0xFFFFFFFFu;
+            ps.xmax = ps.ymax = 0u;
+            for (auto& ch : ps.chunks) {
+                ps.xmin = std::min(ps.xmin, ch.xmin); ps.ymin = std::min(ps.ymin, ch.ymin);
+                ps.xmax = std::max(ps.xmax, ch.xmax); ps.ymax = std::max(ps.ymax, ch.ymax);
+            }
         }
         if (ps.chunks.empty()) it = ctx->index.erase(it);
         else ++it;
     }
+    flush();
     KB_CUDA(ctx, cudaGetLastError());
     return KB_OK;
 }

@@ -14,6 +14,14 @@ namespace kb {
 
 struct Life {  // shared by a context and every buffer it handed out: relations may outlive their context (bindings' GC order)
     bool alive = true;
+    // Large buffers are recycled here instead of going back to the stream-ordered pool: a freed 267 MB result buffer that the pool has
+    // to re-map for the next query costs ~0.5 ms (measured at N = 2: 0.69 ms per synchronous query instead of 0.12), a closure's
+    // multi-GB join outputs several ms. Everything is allocated and released on the context's one stream, so a recycled buffer is
+    // ordered behind its previous user exactly like a pool allocation would be.
+    struct Cached { void* p; size_t bytes; };
+    std::vector<Cached> cache;
+    size_t cached_bytes = 0;
+    static constexpr size_t MIN_BYTES = 1u << 20, MAX_ENTRIES = 48, MAX_BYTES = 24ull << 30;
 };
 struct DevBuf {
     void* p = nullptr;
@@ -22,8 +30,14 @@ struct DevBuf {
     std::shared_ptr<Life> life;
     ~DevBuf() {
         if (!p) return;
-        if (life && life->alive) cudaFreeAsync(p, st);  // stream-ordered: kernels still queued on st may be using it
-        else cudaFree(p);                               // the context (and its stream) is gone
+        if (life && life->alive) {
+            if (bytes >= Life::MIN_BYTES && life->cache.size() < Life::MAX_ENTRIES && life->cached_bytes + bytes <= Life::MAX_BYTES) {
+                life->cache.push_back({p, bytes});
+                life->cached_bytes += bytes;
+                return;
+            }
+            cudaFreeAsync(p, st);  // stream-ordered: kernels still queued on st may be using it
+        } else cudaFree(p);         // the context (and its stream) is gone
     }
 };
 using Buf = std::shared_ptr<DevBuf>;
@@ -89,6 +103,10 @@ struct Segment {
     bool has_stats = false;
     u32 stats_world = 0;   // sharding the statistics were checked against
     bool sharded_ok = true;  // every subject belongs to this context's shard (checked when kb_set_sharding is in effect)
+    // distinct predicates of the segment with their row counts, from the same pass as the ranges (empty + preds_overflow when it
+    // carries more than SEGP_SLOTS of them): what the index maintenance of a window slide allocates its chunks from
+    std::vector<std::pair<u32, u32>> pred_rows;
+    bool has_preds = false, preds_overflow = false;
 };
 }  // namespace kb
 
@@ -99,13 +117,14 @@ struct SliceChunk {  // the rows of ONE store segment that carry the predicate: 
     u64 n = 0;
     Buf ynum;              // typed literal column: f64 value of every object (num_or0), kept when the chunk has numeric objects
     u64 ynum_version = 0;  // numeric side table version it was built from
+    u32 xmin = 0xFFFFFFFFu, xmax = 0, ymin = 0xFFFFFFFFu, ymax = 0;  // id ranges of the chunk (an eviction re-derives the slice's from the survivors)
 };
 struct PredSlice {  // one predicate's (subject, object) rows of the store — the device analogue of pos[P] (index_manager.rs:18-26) — as one
                     // chunk per store segment, so that an RSP window slide (append one segment, evict another) maintains the index
                     // instead of dropping it (rsp_engine.rs:94-104; simple_r2r.rs:95-142)
     std::vector<SliceChunk> chunks;
     u64 n = 0;  // rows over all chunks
-    u32 xmin = 0xFFFFFFFFu, xmax = 0, ymin = 0xFFFFFFFFu, ymax = 0;  // id range of subjects (x) and objects (y); never shrunk by evictions
+    u32 xmin = 0xFFFFFFFFu, xmax = 0, ymin = 0xFFFFFFFFu, ymax = 0;  // id range of subjects (x) and objects (y) over the live chunks
     // persistent direct tables kept while the column is unique and dense: xtab[subject - xtab_min] = object (what the reference's
     // spo[s][P] lookup answers, index_manager.rs:18-26) and ytab[object - ytab_min] = subject (pos[P][o]). *_range is the table's
     // CAPACITY in slots: it is allocated with headroom above the largest key (dictionary ids grow), appended chunks are inserted in

@@ -690,6 +690,175 @@ void launch_distinct(const u32* col, u32 n, u32* set, u32 set_slots, u32* overfl
     distinct_kernel<<<grid, 256, 0, st>>>(col, n, set, set_slots, overflow);
 }
 
+// One pass over a new segment: id range of the three columns, subjects that belong to another shard, and the segment's distinct
+// predicates with their row counts (32 open-addressing slots in the control words; a 33rd predicate raises the overflow word and the
+// caller takes the batched scan path). Predicates come in short runs (one employee = six consecutive triples), so a warp holds a
+// handful of distinct values: one probe sequence and one count atomic per (warp, value).
+__global__ void __launch_bounds__(256) segment_profile_kernel(const u32* __restrict__ s, const u32* __restrict__ p, const u32* __restrict__ o, u32 n, u32 rank,
+                                                              u32 world, u32* ctrl) {
+    // per CTA: its own 32-slot table (value, rows) in shared memory, merged into the control words once at the end — the global table
+    // sees one probe sequence and one add per (CTA, predicate) instead of one per (warp, predicate) and iteration
+    __shared__ u32 s_key[SEGP_SLOTS], s_cnt[SEGP_SLOTS];
+    __shared__ u32 s_over;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < SEGP_SLOTS) { s_key[threadIdx.x] = EMPTY32; s_cnt[threadIdx.x] = 0u; }
+    if (threadIdx.x == 0) s_over = 0u;
+    __syncthreads();
+    u32 mn[3] = {EMPTY32, EMPTY32, EMPTY32}, mx[3] = {0u, 0u, 0u}, foreign = 0u;
+    const u32 n_round = (n + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        const bool valid = i < n;
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (!valid) continue;
+        const u32 vs = s[i], vp = p[i], vo = o[i];
+        mn[0] = min(mn[0], vs); mx[0] = max(mx[0], vs);
+        mn[1] = min(mn[1], vp); mx[1] = max(mx[1], vp);
+        mn[2] = min(mn[2], vo); mx[2] = max(mx[2], vo);
+        if (world > 1u) foreign += shard_of(vs, world) != rank;
+        const unsigned peers = __match_any_sync(act, vp);
+        if (lane != __ffs(peers) - 1) continue;
+        u32 slot = mix32(vp) & (SEGP_SLOTS - 1u);
+        for (u32 probes = 0;; probes++) {
+            if (probes >= SEGP_SLOTS) { s_over = 1u; break; }
+            u32 cur = *reinterpret_cast<volatile u32*>(&s_key[slot]);
+            if (cur == EMPTY32) cur = atomicCAS(&s_key[slot], EMPTY32, vp);
+            if (cur == EMPTY32 || cur == vp) { atomicAdd(&s_cnt[slot], (u32)__popc(peers)); break; }
+            slot = (slot + 1u) & (SEGP_SLOTS - 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < SEGP_SLOTS && s_key[threadIdx.x] != EMPTY32) {
+        const u32 vp = s_key[threadIdx.x];
+        u32 slot = mix32(vp) & (SEGP_SLOTS - 1u);
+        for (u32 probes = 0;; probes++) {
+            if (probes >= SEGP_SLOTS) { ctrl[SEGP_OVERFLOW] = 1u; break; }
+            u32 cur = *reinterpret_cast<volatile u32*>(&ctrl[SEGP_SLOT + slot]);
+            if (cur == EMPTY32) cur = atomicCAS(&ctrl[SEGP_SLOT + slot], EMPTY32, vp);
+            if (cur == EMPTY32 || cur == vp) { atomicAdd(&ctrl[SEGP_COUNT + slot], s_cnt[threadIdx.x]); break; }
+            slot = (slot + 1u) & (SEGP_SLOTS - 1u);
+        }
+    }
+    if (threadIdx.x == 0 && s_over) ctrl[SEGP_OVERFLOW] = 1u;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        mn[c] = __reduce_min_sync(0xffffffffu, mn[c]);
+        mx[c] = __reduce_max_sync(0xffffffffu, mx[c]);
+    }
+    foreign = warp_sum(foreign);
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { atomicMin(&ctrl[SEGP_MIN + c], mn[c]); atomicMax(&ctrl[SEGP_MAX + c], mx[c]); }
+        if (foreign) atomicAdd(&ctrl[SEGP_FOREIGN], foreign);
+    }
+}
+void launch_segment_profile(const u32* s, const u32* p, const u32* o, u32 n, u32 rank, u32 world, u32* ctrl, int n_sms, cudaStream_t st) {
+    if (n == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + 255ull) / 256ull);
+    segment_profile_kernel<<<grid, 256, 0, st>>>(s, p, o, n, rank, world, ctrl);
+}
+
+// One pass over a new segment that files every triple under its predicate's slice: the (subject, object) pair goes to the slice's new
+// chunk (one cursor reservation per warp and predicate), the object's f64 value to the chunk's typed column, both ids into the slice's
+// persistent tables (atomicExch: a previous occupant = the column is not unique; a key outside the table = the table has to be
+// rebuilt; both reported through control words), id ranges reduced per CTA in shared memory. Replaces, per slide, a scan + copy + range
+// pass + two table builds + a typed column pass PER PREDICATE (~30 launches and 4 host round trips for six predicates).
+__global__ void __launch_bounds__(256) segment_split_kernel(const __grid_constant__ SplitParams P) {
+    __shared__ u32 s_mm[MAXP][4];
+    __shared__ u32 s_flag[MAXP][4];
+    __shared__ u32 s_nnum[MAXP];
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < MAXP) {
+        s_mm[threadIdx.x][0] = EMPTY32; s_mm[threadIdx.x][1] = EMPTY32; s_mm[threadIdx.x][2] = 0u; s_mm[threadIdx.x][3] = 0u;
+        s_flag[threadIdx.x][0] = 0u; s_flag[threadIdx.x][1] = 0u; s_flag[threadIdx.x][2] = 0u; s_flag[threadIdx.x][3] = 0u;
+        s_nnum[threadIdx.x] = 0u;
+    }
+    __syncthreads();
+    const u32 n_round = (P.n + 31u) & ~31u;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        u32 vs = 0u, vo = 0u, which = EMPTY32;
+        if (i < P.n) {
+            const u32 vp = P.p[i];
+            vs = P.s[i]; vo = P.o[i];
+#pragma unroll
+            for (u32 j = 0; j < MAXP; j++) if (j < P.k && P.e[j].pred == vp) which = j;
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, which != EMPTY32);
+        if (which == EMPTY32) continue;
+        const SplitEntry& E = P.e[which];
+        const unsigned peers = __match_any_sync(act, which);
+        const int leader = __ffs(peers) - 1;
+        u32 base = 0;
+        if (lane == leader) base = atomicAdd(&P.ctrl[which * SPLIT_WORDS + SPLIT_CURSOR], (u32)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const u32 pos = base + (u32)__popc(peers & ((1u << lane) - 1u));
+        const u32 xlo = __reduce_min_sync(peers, vs), ylo = __reduce_min_sync(peers, vo), xhi = __reduce_max_sync(peers, vs), yhi = __reduce_max_sync(peers, vo);
+        if (lane == leader) { atomicMin(&s_mm[which][0], xlo); atomicMin(&s_mm[which][1], ylo); atomicMax(&s_mm[which][2], xhi); atomicMax(&s_mm[which][3], yhi); }
+        const unsigned nm = __ballot_sync(peers, E.ynum != nullptr && isnum_of(P.nt, vo));
+        if (lane == leader && nm) atomicAdd(&s_nnum[which], (u32)__popc(nm));
+        if (pos < E.n) {  // (always: the capacities are the profile pass's exact counts)
+            E.pairs[pos] = make_uint2(vs, vo);
+            if (E.ynum) E.ynum[pos] = num_of(P.nt, vo);
+        }
+        if (E.xtab) {
+            const u32 off = compact_key(vs, E.cshift) - E.xtab_min;
+            if (off < E.xtab_range) {
+                if (atomicExch(&E.xtab[off], vo) != EMPTY32) s_flag[which][0] = 1u;
+                if (E.xnum) E.xnum[off] = num_of(P.nt, vo);
+            } else s_flag[which][2] = 1u;
+        }
+        if (E.ytab) {
+            const u32 off = vo - E.ytab_min;
+            if (off < E.ytab_range) {
+                if (atomicExch(&E.ytab[off], vs) != EMPTY32) s_flag[which][1] = 1u;
+            } else s_flag[which][3] = 1u;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < P.k) {
+        const u32 j = threadIdx.x;
+        u32* c = P.ctrl + j * SPLIT_WORDS;
+        if (s_mm[j][0] != EMPTY32 || s_mm[j][2] != 0u) {  // minima are kept complemented so that every control word starts at 0
+            atomicMax(&c[SPLIT_XMIN], ~s_mm[j][0]); atomicMax(&c[SPLIT_YMIN], ~s_mm[j][1]);
+            atomicMax(&c[SPLIT_XMAX], s_mm[j][2]); atomicMax(&c[SPLIT_YMAX], s_mm[j][3]);
+        }
+        if (s_nnum[j]) atomicAdd(&c[SPLIT_NNUM], s_nnum[j]);
+        if (s_flag[j][0]) c[SPLIT_XDUP] = 1u;
+        if (s_flag[j][1]) c[SPLIT_YDUP] = 1u;
+        if (s_flag[j][2]) c[SPLIT_XOUT] = 1u;
+        if (s_flag[j][3]) c[SPLIT_YOUT] = 1u;
+    }
+}
+void launch_segment_split(const SplitParams& p, int n_sms, cudaStream_t st) {
+    if (p.n == 0 || p.k == 0) return;
+    const int grid = (int)umin64((u64)n_sms * 4ull, ((u64)p.n + 255ull) / 256ull);
+    segment_split_kernel<<<grid, 256, 0, st>>>(p);
+}
+
+// the keys of up to CLEAR_MAX evicted chunks leave their slices' persistent tables in one launch (blockIdx.y = chunk)
+__global__ void __launch_bounds__(256) clear_chunks_kernel(const __grid_constant__ ClearParams P) {
+    const ClearEntry& E = P.e[blockIdx.y];
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < E.n; i += stride) {
+        const uint2 v = E.pairs[i];
+        if (E.xtab) {
+            const u32 off = compact_key(v.x, E.cshift) - E.xtab_min;
+            if (off < E.xtab_range) E.xtab[off] = EMPTY32;
+        }
+        if (E.ytab) {
+            const u32 off = v.y - E.ytab_min;
+            if (off < E.ytab_range) E.ytab[off] = EMPTY32;
+        }
+    }
+}
+void launch_clear_chunks(const ClearParams& p, int n_sms, cudaStream_t st) {
+    if (p.k == 0) return;
+    u32 n_max = 0;
+    for (u32 j = 0; j < p.k; j++) n_max = p.e[j].n > n_max ? p.e[j].n : n_max;
+    if (n_max == 0) return;
+    const u32 gx = (u32)umin64((u64)n_sms * 8ull / p.k + 1ull, ((u64)n_max + 255ull) / 256ull);
+    clear_chunks_kernel<<<dim3(gx, p.k), 256, 0, st>>>(p);
+}
+
 __global__ void __launch_bounds__(256) pair_minmax_kernel(const uint2* __restrict__ kv, u32 n, u32* out4) {
     u32 mnx = EMPTY32, mny = EMPTY32, mxx = 0u, mxy = 0u;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -2803,7 +2972,7 @@ void launch_part_scatter(const u32* key, u32 n, u32 n_parts, u32* cursors, const
 constexpr int SHUF_THREADS = 256;
 __global__ void __launch_bounds__(SHUF_THREADS) shuffle_scatter_kernel(const __grid_constant__ ShuffleParams P) {
     extern __shared__ __align__(16) u32 sh_stage[];  // [n_cols][tile] staged columns, then tile bytes of destinations
-    __shared__ u32 s_cnt[64], s_off[64], s_gbase[64];
+    __shared__ u32 s_cnt[64], s_off[64], s_fill[64], s_gbase[64];
     __shared__ u32 s_tile;
     const u32 TILE = P.tile;
     unsigned char* s_dest = reinterpret_cast<unsigned char*>(sh_stage + (size_t)P.n_cols * TILE);
@@ -2811,28 +2980,22 @@ __global__ void __launch_bounds__(SHUF_THREADS) shuffle_scatter_kernel(const __g
     const u32 items = TILE / SHUF_THREADS;
     for (;;) {
         if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
-        if (tid < 64) s_cnt[tid] = 0u;
+        if (tid < 64) { s_cnt[tid] = 0u; s_fill[tid] = 0u; }
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= P.n_tiles) break;
         const u32 row0 = tile * TILE;
         const u32 cnt = min(TILE, P.n - row0);
-        // ---- 1. destinations + histogram (one shared atomic per warp and destination); the atomic's return value is the row's RANK
-        // among the tile's rows for that destination, kept for step 3
-        unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_dest + TILE);
+        // ---- 1. destinations + histogram (one shared atomic per warp and destination)
         for (u32 j = 0; j < items; j++) {
             const u32 r = j * SHUF_THREADS + (u32)tid;
             const bool valid = r < cnt;
             const u32 part = valid ? shard_of(__ldg(P.key + row0 + r), P.n_parts) : 0xFFu;
+            if (valid) s_dest[r] = (unsigned char)part;
             const unsigned act = __ballot_sync(0xffffffffu, valid);
             if (valid) {
                 const unsigned peers = __match_any_sync(act, part);
-                const int leader = __ffs(peers) - 1;
-                u32 b = 0;
-                if (lane == leader) b = atomicAdd(&s_cnt[part], (u32)__popc(peers));
-                b = __shfl_sync(peers, b, leader);
-                s_dest[r] = (unsigned char)part;
-                s_rank[r] = (unsigned short)(b + (u32)__popc(peers & ((1u << lane) - 1u)));
+                if (lane == __ffs(peers) - 1) atomicAdd(&s_cnt[part], (u32)__popc(peers));
             }
         }
         __syncthreads();
@@ -2859,11 +3022,20 @@ __global__ void __launch_bounds__(SHUF_THREADS) shuffle_scatter_kernel(const __g
             }
         }
         __syncthreads();
-        // ---- 3. stage the columns sorted by destination (position = destination's offset in the tile + the rank taken in step 1)
+        // ---- 3. stage the columns sorted by destination (taking the rank here, with a second round of warp-aggregated shared
+        // atomics, measured faster than keeping the returned ranks of step 1: 0.36 vs 0.42 ms at N = 2)
         for (u32 j = 0; j < items; j++) {
             const u32 r = j * SHUF_THREADS + (u32)tid;
-            if (r >= cnt) continue;
-            const u32 pos = s_off[s_dest[r]] + (u32)s_rank[r];
+            const bool valid = r < cnt;
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (!valid) continue;
+            const u32 part = s_dest[r];
+            const unsigned peers = __match_any_sync(act, part);
+            const int leader = __ffs(peers) - 1;
+            u32 b = 0;
+            if (lane == leader) b = atomicAdd(&s_fill[part], (u32)__popc(peers));
+            b = __shfl_sync(peers, b, leader);
+            const u32 pos = s_off[part] + b + (u32)__popc(peers & ((1u << lane) - 1u));
             for (u32 c = 0; c < P.n_cols; c++) sh_stage[c * TILE + pos] = __ldg(P.in[c] + row0 + r);
         }
         __syncthreads();
@@ -2891,7 +3063,7 @@ void launch_shuffle_scatter(const ShuffleParams& p_in, int n_sms, cudaStream_t s
     ShuffleParams p = p_in;
     p.tile = p.n_cols <= 4 ? 4096u : (p.n_cols <= 8 ? 2048u : 1024u);
     p.n_tiles = (p.n + p.tile - 1u) / p.tile;
-    const size_t smem = (size_t)p.n_cols * p.tile * sizeof(u32) + 3 * (size_t)p.tile;  // staged columns, destination bytes, rank halfwords
+    const size_t smem = (size_t)p.n_cols * p.tile * sizeof(u32) + p.tile;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(shuffle_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024); attr = true; }
     const int grid = grid_for((const void*)shuffle_scatter_kernel, SHUF_THREADS, smem, n_sms, p.n_tiles);

@@ -216,6 +216,46 @@ struct BuildPairsParams {
 void launch_build_direct_pairs_filtered(const BuildPairsParams& p, int n_sms, cudaStream_t st);
 // distinct values of a column into a small open-addressing set (EMPTY32 = free); *overflow set when it fills up
 void launch_distinct(const u32* col, u32 n, u32* set, u32 set_slots, u32* overflow, int n_sms, cudaStream_t st);
+
+// ---- window-slide maintenance of the store index: ONE pass profiles a new segment (column ranges, foreign subjects, its distinct
+// predicates with their row counts), ONE pass splits it into the predicate slices' new chunks — pairs, id ranges, typed literal
+// column, in-place inserts into the persistent tables — and ONE pass clears an evicted segment's keys from all of its slices' tables.
+constexpr u32 SEGP_SLOTS = 32;  // open-addressing slots for a segment's distinct predicates (more than that: the batched scan path)
+// control words of segment_profile: [0..2] min s/p/o, [3] unused, [4 .. 4+SLOTS) predicate slots (all 0xFF at launch);
+// then (all 0 at launch) [P_MAX .. +3) max s/p/o, P_FOREIGN, P_OVERFLOW, [P_COUNT .. +SLOTS) rows per slot
+constexpr u32 SEGP_MIN = 0, SEGP_SLOT = 4, SEGP_MAX = 4 + SEGP_SLOTS, SEGP_FOREIGN = SEGP_MAX + 3, SEGP_OVERFLOW = SEGP_MAX + 4, SEGP_COUNT = SEGP_MAX + 8,
+              SEGP_WORDS = SEGP_COUNT + SEGP_SLOTS;
+void launch_segment_profile(const u32* s, const u32* p, const u32* o, u32 n, u32 rank, u32 world, u32* ctrl, int n_sms, cudaStream_t st);
+
+struct SplitEntry {
+    u32 pred;
+    u32 n;              // rows of the predicate in the segment (capacity of pairs / ynum)
+    uint2* pairs;       // the new chunk
+    double* ynum;       // its typed literal column (null: no numeric side table loaded)
+    u32* xtab; u32 xtab_min, xtab_range, cshift;   // subject table to insert into (null: none)
+    double* xnum;       // typed values in table order, maintained with xtab (null: none)
+    u32* ytab; u32 ytab_min, ytab_range;           // object table (null: none)
+};
+// control words per entry (all 0 at launch): cursor, n_numeric, xdup, ydup, xout, yout, pad, pad, ~xmin, ~ymin, xmax, ymax
+constexpr u32 SPLIT_CURSOR = 0, SPLIT_NNUM = 1, SPLIT_XDUP = 2, SPLIT_YDUP = 3, SPLIT_XOUT = 4, SPLIT_YOUT = 5, SPLIT_XMIN = 8, SPLIT_YMIN = 9, SPLIT_XMAX = 10,
+              SPLIT_YMAX = 11, SPLIT_WORDS = 12;
+struct SplitParams {
+    const u32 *s, *p, *o;
+    u32 n, k;
+    SplitEntry e[MAXP];
+    u32* ctrl;  // k * SPLIT_WORDS words
+    NumTab nt;
+};
+void launch_segment_split(const SplitParams& p, int n_sms, cudaStream_t st);
+
+constexpr u32 CLEAR_MAX = 16;
+struct ClearEntry {
+    const uint2* pairs; u32 n;
+    u32* xtab; u32 xtab_min, xtab_range, cshift;
+    u32* ytab; u32 ytab_min, ytab_range;
+};
+struct ClearParams { ClearEntry e[CLEAR_MAX]; u32 k; };
+void launch_clear_chunks(const ClearParams& p, int n_sms, cudaStream_t st);
 // min/max of both halves of a pair relation: out[0..3] = min x, min y, max x, max y
 // typed literal column of a predicate slice: out[i] = num_or0[kv[i].y]; *n_numeric += rows whose object is numeric
 void launch_pair_numcol(const uint2* kv, u32 n, NumTab nt, double* out, u32* n_numeric, int n_sms, cudaStream_t st);

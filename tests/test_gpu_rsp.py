@@ -109,3 +109,86 @@ def test_window_slides_keep_the_index_path(ctx, q):
     got = ctx.star_join(js, pats, filt)
     assert ctx.get_stats()["index_joins"] == n0 + 1
     H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), "after the rebuild")
+
+
+def test_slide_maintenance_corner_cases(ctx):
+    """the one-kernel slide maintenance (segment_profile_kernel + segment_split_kernel) against the oracle where it has to leave its
+    straight path: a slide that brings a NEW predicate, ids BELOW the persistent tables' first slot (rebuild), a subject repeated
+    INSIDE a slide (the subject table goes), more than 8 predicates in one slide (batched scan path), a device-resident slide
+    (kb_store_append_device), evictions in between — rsp_engine.rs:94-104 with arbitrary window contents"""
+    import torch
+
+    rng = np.random.default_rng(11)
+    P = [50, 51, 52]
+    js = 0
+    pats = [c.pattern(c.V(0), c.K(50), c.V(1)), c.pattern(c.V(0), c.K(51), c.V(2)), c.pattern(c.V(0), c.K(52), c.V(3))]
+
+    def slide(subj, preds=P, repeat=0):
+        s = np.repeat(subj, len(preds)).astype(np.uint32)
+        p = np.tile(np.array(preds, dtype=np.uint32), len(subj))
+        o = (10_000 + rng.integers(0, 40, size=len(s))).astype(np.uint32)
+        if repeat:
+            s = np.concatenate([s, s[:repeat]]); p = np.concatenate([p, p[:repeat]]); o = np.concatenate([o, o[:repeat] + 1])
+        return s, p, o
+
+    ctx.store_clear()
+    live = {}
+
+    def check(label, expect_index=True):
+        s = np.concatenate([v[0] for v in live.values()]); p = np.concatenate([v[1] for v in live.values()]); o = np.concatenate([v[2] for v in live.values()])
+        n0 = ctx.get_stats()["index_joins"]
+        got = ctx.star_join(js, pats, None)
+        if expect_index:
+            assert ctx.get_stats()["index_joins"] == n0 + 1, f"{label}: left the index path"
+        want = O.Db(s, p, o).bgp(pats, None)
+        H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), label)
+        for k, pt in enumerate(pats):  # single-pattern lookups through the maintained slices
+            g1 = ctx.scan([pt])[0]
+            w1 = O.Db(s, p, o).bgp([pt], None)
+            H.assert_same_bag(g1.to_numpy(sorted(g1.slots)), w1.to_numpy(sorted(w1.slots)), f"{label} pattern {k}")
+
+    def add(tag, sl, device=False):
+        live[tag] = sl
+        if device:
+            d = [torch.from_numpy(x).cuda() for x in sl]
+            ctx.store_append_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr(), len(sl[0]), tag)
+        else:
+            ctx.store_append(*sl, tag=tag)
+
+    add(1, slide(np.arange(5000, 6000)))
+    ctx.build_index()
+    check("first slide")
+    add(2, slide(np.arange(6000, 7000)))
+    check("second slide")
+    add(3, slide(np.arange(7000, 7500), preds=P + [53]))  # a predicate the index has not seen
+    check("new predicate")
+    g = ctx.scan([c.pattern(c.V(0), c.K(53), c.V(1))])[0]
+    assert g.n_rows == 500
+    add(4, slide(np.arange(100, 600)))  # ids below every table's first slot: the tables are rebuilt over all live chunks
+    check("ids below the tables")
+    ctx.store_evict(1); live.pop(1)
+    check("after evicting the first slide")
+    add(5, slide(np.arange(8000, 8400)), device=True)
+    check("device-resident slide")
+    add(6, slide(np.arange(9000, 9300), preds=list(range(50, 62))))  # 12 predicates: the batched scan path
+    check("twelve predicates in a slide")
+    ctx.store_evict(4); live.pop(4)
+    ctx.store_evict(2); live.pop(2)
+    check("after two more evictions")
+    add(7, slide(np.arange(9500, 9800), repeat=30))  # subjects repeated inside the slide: predicate 50.. become multi-valued
+    check("repeated subjects inside a slide", expect_index=False)
+    ctx.store_evict(7); live.pop(7)
+    check("after evicting the repeated subjects", expect_index=False)
+    ctx.build_index()
+    check("after the rebuild")
+    # a window that slides far: the slices' id ranges follow the live chunks (the table walk does not cover the evicted past)
+    tags = []
+    for t in range(12):
+        add(100 + t, slide(np.arange(20_000 + 1000 * t, 20_000 + 1000 * t + 700)))
+        tags.append(100 + t)
+        if len(tags) > 3:
+            old = tags.pop(0)
+            ctx.store_evict(old); live.pop(old)
+    for tag in (3, 5, 6):
+        ctx.store_evict(tag); live.pop(tag)
+    check("long slide")
