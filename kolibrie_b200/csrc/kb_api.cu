@@ -2111,7 +2111,9 @@ static kb_status slice_table_update(kb_ctx* ctx, PredSlice& ps, u32 y, int added
         tried = true;
         unique = false;
         if (range > std::max<u64>(4 * ps.n + 65536, 1ull << 16) || range > (1ull << 28)) return KB_OK;  // not dense: keep no table
-        const u64 cap = std::min<u64>(range + range / 2 + 65536, 1ull << 29);
+        // headroom: half the range for large tables, twice the range for small ones (a sliding window's ids move up by a slide per
+        // slide: a 10-slide window then re-bases its tables every ~20 slides instead of every ~5)
+        const u64 cap = std::min<u64>(range + (range <= (4ull << 20) ? 2 * range : range / 2) + 65536, 1ull << 29);
         KB_TRY(alloc_buf(ctx, cap * sizeof(u32), &tab));
         KB_CUDA(ctx, cudaMemsetAsync(tab->p, 0xFF, cap * sizeof(u32), ctx->st));
         tmin = lo;
@@ -2128,6 +2130,17 @@ static kb_status slice_table_update(kb_ctx* ctx, PredSlice& ps, u32 y, int added
                                   ctx->n_sms, ctx->st);
         ctx->stats.kernel_launches++;
         *touched = true;
+    }
+    // a subject table rebuilt outside the full build takes its typed column along (the table-mode probe filters on it)
+    if (!y && !fits && !ctx->in_full_index_build && ctx->n_ids && ps.typed(ctx->num_version)) {
+        KB_TRY(alloc_buf(ctx, (size_t)tcap * sizeof(double), &ps.xnum));
+        KB_CUDA(ctx, cudaMemsetAsync(ps.xnum->p, 0, (size_t)tcap * sizeof(double), ctx->st));
+        for (auto& ch : ps.chunks) {
+            if (!ch.n) continue;
+            launch_pair_numtab(reinterpret_cast<const uint2*>(ch.pairs.ptr), (u32)ch.n, numtab(ctx), static_cast<double*>(ps.xnum->p), tmin, tcap, cs, ctx->n_sms, ctx->st);
+            ctx->stats.kernel_launches++;
+        }
+        ps.xnum_version = ctx->num_version;
     }
     return KB_OK;
 }
