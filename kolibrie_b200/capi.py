@@ -31,6 +31,7 @@ LEGACY_NESTED_F64 = 0x200
 CMP_GT, CMP_GE, CMP_LT, CMP_LE, CMP_EQ, CMP_NE = range(1, 7)
 AGG_COUNT, AGG_SUM, AGG_MIN, AGG_MAX, AGG_AVG = range(5)
 SEMI_NAIVE, NAIVE, SEMI_NAIVE_PARALLEL = 0, 1, 2
+SEMI_NAIVE_OLD_DELTA = 3  # textbook OLD/delta scheme: same facts, rounds and per-round counts, fewer candidates (include/kolibrie_b200.h)
 
 
 class KbTerm(C.Structure):

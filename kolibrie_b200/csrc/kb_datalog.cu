@@ -172,7 +172,9 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev_dev};
     KB_TRY(begin_call(ctx));
     if ((n_rules && !rules) || !inferred) return fail(ctx, KB_E_INVALID, "NULL argument");
-    if (strategy != KB_SEMI_NAIVE && strategy != KB_NAIVE && strategy != KB_SEMI_NAIVE_PARALLEL) return fail(ctx, KB_E_INVALID, "unknown strategy %u", strategy);
+    if (strategy != KB_SEMI_NAIVE && strategy != KB_NAIVE && strategy != KB_SEMI_NAIVE_PARALLEL && strategy != KB_SEMI_NAIVE_OLD_DELTA)
+        return fail(ctx, KB_E_INVALID, "unknown strategy %u", strategy);
+    const bool old_delta = strategy == KB_SEMI_NAIVE_OLD_DELTA;
     const bool strict = strategy == KB_SEMI_NAIVE_PARALLEL;
     kb_fixpoint_stats st{};
     ScopedEvent ev0, ev1;
@@ -302,9 +304,11 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                 for (u32 j = 0; j < np && cur->n; j++) {
                     if (j == i) continue;
                     const PredRel& pr = fx.rels[pl.prem[j].pred];
-                    if (pr.snapshot == 0) { cur->n = 0; break; }
+                    // KB_SEMI_NAIVE_OLD_DELTA: a premise before the delta premise sees only the facts older than its delta
+                    const u64 visible = old_delta && j < i ? pr.delta_start : pr.snapshot;
+                    if (visible == 0) { cur->n = 0; break; }
                     std::unique_ptr<kb_rel> all, joined;
-                    KB_TRY(make_view(ctx, pr, 0, pr.snapshot, (u32)pl.prem[j].s_var, (u32)pl.prem[j].o_var, &all));
+                    KB_TRY(make_view(ctx, pr, 0, visible, (u32)pl.prem[j].s_var, (u32)pl.prem[j].o_var, &all));
                     if (strict) KB_TRY(enforce_constants(ctx, pl.prem[j], &all));
                     tr.mark(ctx, "  views");
                     KB_TRY(hash_join_impl(ctx, *cur, *all, nullptr, &joined));

@@ -448,7 +448,7 @@ struct ShuffleParams {
     u32 capacity;
     u32* overflow;
     u32* ticket;               // zeroed tile counter
-    u32 tile, n_tiles;         // set by the launcher
+    u32 tile, n_tiles, stride, pow2_mask;  // set by the launcher
 };
 void launch_shuffle_scatter(const ShuffleParams& p, int n_sms, cudaStream_t st);
 

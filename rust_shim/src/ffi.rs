@@ -29,7 +29,7 @@ pub const KB_F_NOT: u32 = 6; pub const KB_F_PUSH_VAR: u32 = 7; pub const KB_F_PU
 pub const KB_F_MUL: u32 = 11; pub const KB_F_DIV: u32 = 12; pub const KB_F_TRUTHY: u32 = 13; pub const KB_F_IS_TRIPLE: u32 = 14;
 pub const KB_CMP_GT: u32 = 1; pub const KB_CMP_GE: u32 = 2; pub const KB_CMP_LT: u32 = 3; pub const KB_CMP_LE: u32 = 4; pub const KB_CMP_EQ: u32 = 5; pub const KB_CMP_NE: u32 = 6;
 pub const KB_AGG_COUNT: u32 = 0; pub const KB_AGG_SUM: u32 = 1; pub const KB_AGG_MIN: u32 = 2; pub const KB_AGG_MAX: u32 = 3; pub const KB_AGG_AVG: u32 = 4;
-pub const KB_SEMI_NAIVE: u32 = 0; pub const KB_NAIVE: u32 = 1; pub const KB_SEMI_NAIVE_PARALLEL: u32 = 2;
+pub const KB_SEMI_NAIVE: u32 = 0; pub const KB_NAIVE: u32 = 1; pub const KB_SEMI_NAIVE_PARALLEL: u32 = 2; pub const KB_SEMI_NAIVE_OLD_DELTA: u32 = 3;
 
 pub enum KbCtx {} pub enum KbRel {} pub enum KbGroups {} pub enum KbStrings {} pub enum KbPlan {}
 

@@ -183,3 +183,34 @@ def test_partitioned_candidate_dedup_vs_oracle(monkeypatch, strategy, slack):
         assert int(st.derivations) == int(want["derivations"])
     finally:
         cx.close()
+
+
+def test_old_delta_scheme_same_facts_fewer_candidates(ctx):
+    """KB_SEMI_NAIVE_OLD_DELTA (premises before the delta premise read only OLD facts): the inferred facts, the rounds and the new facts
+    per round are those of semi_naive.rs:17-85 (= the oracle's); only the number of candidate derivations is smaller"""
+    t = datagen.taxonomy_dataset(fanout=3, depth=5, n_instances=20000)
+    rules = datagen.taxonomy_rules(t)
+    ctx.store_load(t.s, t.p, t.o)
+    rel, st = ctx.datalog_fixpoint(rules, c.SEMI_NAIVE_OLD_DELTA)
+    want = O.Db(t.s, t.p, t.o).fixpoint(rules, c.SEMI_NAIVE)
+    H.assert_same_bag(rel.to_numpy([0, 1, 2]), want["facts"], "old/delta closure")
+    assert st.rounds == len(want["round_new"]) and st.inferred == len(want["facts"])
+    assert [int(x) for x in st.round_new[:st.rounds]] == [int(x) for x in want["round_new"][:st.rounds]]
+    assert 0 < st.derivations < want["derivations"]
+    # the reference's fixtures with joins inside a rule: sibling / uncle shapes (reasoning_tests.rs:107-135, 362-404)
+    rng = np.random.default_rng(5)
+    n = 3000
+    PARENT, SIB, UNCLE = 1, 2, 3
+    kids = np.arange(10, 10 + n, dtype=np.uint32)
+    par = (10 + n + rng.integers(0, n // 3, size=n)).astype(np.uint32)
+    s = np.concatenate([kids, par[: n // 2]]); o = np.concatenate([par, (10 + 2 * n + rng.integers(0, 50, size=n // 2)).astype(np.uint32)])
+    p = np.full(len(s), PARENT, dtype=np.uint32)
+    sib = {"premise": [c.pattern(c.V(0), c.K(PARENT), c.V(2)), c.pattern(c.V(1), c.K(PARENT), c.V(2))], "conclusion": [c.pattern(c.V(0), c.K(SIB), c.V(1))],
+           "filters": [c.KbRuleFilter(0, c.CMP_NE, 1, 1, 0.0)]}
+    uncle = {"premise": [c.pattern(c.V(0), c.K(SIB), c.V(1)), c.pattern(c.V(2), c.K(PARENT), c.V(1))], "conclusion": [c.pattern(c.V(0), c.K(UNCLE), c.V(2))],
+             "filters": []}
+    ctx.store_load(s, p, o)
+    rel, st = ctx.datalog_fixpoint([sib, uncle], c.SEMI_NAIVE_OLD_DELTA)
+    want = O.Db(s, p, o).fixpoint([sib, uncle], c.SEMI_NAIVE)
+    H.assert_same_bag(rel.to_numpy([0, 1, 2]), want["facts"], "sibling / uncle")
+    assert st.rounds == len(want["round_new"]) and st.derivations <= want["derivations"]
