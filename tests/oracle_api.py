@@ -97,9 +97,12 @@ class Rel:
         return out
 
     def __del__(self):
-        if self.h:
-            lib().ko_rel_free(self.h)
-            self.h = None
+        try:
+            if self.h:
+                lib().ko_rel_free(self.h)
+                self.h = None
+        except Exception:  # interpreter shutdown: module globals may already be gone
+            pass
 
 
 class Db:
@@ -157,9 +160,12 @@ class Db:
             lib().ko_fix_free(f)
 
     def __del__(self):
-        if self.h:
-            lib().ko_db_free(self.h)
-            self.h = None
+        try:
+            if self.h:
+                lib().ko_db_free(self.h)
+                self.h = None
+        except Exception:
+            pass
 
 
 def rel_from_host(slots, cols) -> Rel:
