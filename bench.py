@@ -690,7 +690,7 @@ def other_configs(args, ctx, c, datagen, torch, peak, which=("cfg3", "cfg4", "cf
         t = datagen.taxonomy_dataset(10, 6, n_inst, seed=43)
         rules = datagen.taxonomy_rules(t)
         times, st = [], None
-        for rep in range(4):  # one warm-up closure, then three timed ones, each on a freshly loaded store
+        for rep in range(6):  # one warm-up closure, then five timed ones (median), each on a freshly loaded store
             ctx.store_load(t.s, t.p, t.o)
             ctx.synchronize()
             t0 = time.perf_counter()
@@ -699,7 +699,7 @@ def other_configs(args, ctx, c, datagen, torch, peak, which=("cfg3", "cfg4", "cf
             if rep:
                 times.append(time.perf_counter() - t0)
             rel.free()
-        dt = sorted(times)[1]
+        dt = sorted(times)[len(times) // 2]
         inferred, deriv = int(st.inferred), int(st.derivations)
         lvl = np.repeat(np.arange(7), [10 ** k for k in range(7)])
         cls = t.o[t.p == t.ids["rdf:type"]].astype(np.int64) - 2

@@ -43,7 +43,9 @@ kb_status alloc_buf(kb_ctx* ctx, size_t bytes, Buf* out) {
     b->bytes = round256(bytes) + 256;  // every column can be over-read to the next 16-byte boundary by the TMA tile loads
     b->st = ctx->st;
     b->life = ctx->life;
-    if (b->bytes >= Life::MIN_BYTES) {  // best fit among the recycled buffers (at most 25 % larger than asked)
+    static const bool cache_on = !(getenv("KOLIBRIE_BUF_CACHE") && getenv("KOLIBRIE_BUF_CACHE")[0] == '0');
+    if (!cache_on) ctx->life->cache_off = true;
+    if (b->bytes >= Life::MIN_BYTES && cache_on) {  // best fit among the recycled buffers (at most 25 % larger than asked)
         Life& L = *ctx->life;
         int best = -1;
         for (size_t i = 0; i < L.cache.size(); i++)

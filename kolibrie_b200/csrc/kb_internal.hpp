@@ -21,6 +21,7 @@ struct Life {  // shared by a context and every buffer it handed out: relations 
     struct Cached { void* p; size_t bytes; };
     std::vector<Cached> cache;
     size_t cached_bytes = 0;
+    bool cache_off = false;  // KOLIBRIE_BUF_CACHE=0
     static constexpr size_t MIN_BYTES = 1u << 20, MAX_ENTRIES = 48, MAX_BYTES = 24ull << 30;
 };
 struct DevBuf {
@@ -31,7 +32,7 @@ struct DevBuf {
     ~DevBuf() {
         if (!p) return;
         if (life && life->alive) {
-            if (bytes >= Life::MIN_BYTES && life->cache.size() < Life::MAX_ENTRIES && life->cached_bytes + bytes <= Life::MAX_BYTES) {
+            if (!life->cache_off && bytes >= Life::MIN_BYTES && life->cache.size() < Life::MAX_ENTRIES && life->cached_bytes + bytes <= Life::MAX_BYTES) {
                 life->cache.push_back({p, bytes});
                 life->cached_bytes += bytes;
                 return;
