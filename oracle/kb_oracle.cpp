@@ -8,6 +8,11 @@
 // /root/reference/datalog/tests/reasoning_tests.rs:28-404, replayed in tests/test_oracle_golden.py) and for
 // scan/filter (kolibrie/tests/integration_test.rs:19-76,131-299 fixture counts; 4-employee dataset of
 // kolibrie/examples/sparql_syntax/simple_select/simple_select_synth_data.rs:16-52).
+// Round 2 added, through the host mirror driven by this oracle (tests/test_rdf_star_rsp_golden.py, tests/golden/*.json, generator
+// tests/golden/make_fixtures.py): the RDF-star scans, SUBJECT(?t) / isTRIPLE and DELETE WHERE of kolibrie/tests/rdf_star_test.rs
+// (:107-145, :281-329, :384-405), the per-firing window contents and ISTREAM / RSTREAM emissions of kolibrie/tests/rsp_engine_test.rs
+// (:24-112, :935-1027, :1103-1200), the unit tests of shared/src/quoted_triple_store.rs:82-157, the 4-row answer of
+// benches/my_benchmark.rs:29-41, and Rust's str::parse::<f64> acceptance table (tests/golden/rust_parse_f64.json).
 // Multi-pattern BGP joins: pinned only by the two joins whose answers kolibrie/tests/integration_test.rs asserts (:286-299 a
 // 2-pattern join, :302-342 a 3-pattern join + numeric FILTER; tests/test_oracle_golden.py, both oracle modes). No reference test
 // asserts the rows of larger joins through the executor (SURVEY.md §4 "Gap that matters"): beyond those two, parity is UNPINNED and
