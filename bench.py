@@ -107,13 +107,17 @@ class ClockSampler(threading.Thread):
             return n.nvmlDeviceGetHandleByIndex(cuda_index)
 
     def _sample_nvml(self):
+        # two queries per GPU and sample (the maximum clock is asked once): every NVML query takes driver locks next to the ranks'
+        # stream synchronisations — legs that synchronise every step lost up to ~10 ms to one unlucky sample (0.65 instead of
+        # 0.12 ms/step over 20 steps at N = 4), the launch-only headline loop does not notice
         n = self.nvml
-        for h in self.handles:
+        if not hasattr(self, "max_mhz"):
+            self.max_mhz = [float(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)) for h in self.handles]
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        for h, mx in zip(self.handles, self.max_mhz):
             sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
-            mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
-            get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
             mask = int(get(h))
-            self.samples.append((float(sm), float(mx), [k for k, b in self.BITS.items() if mask & b]))
+            self.samples.append((float(sm), mx, [k for k, b in self.BITS.items() if mask & b]))
 
     def _sample_smi(self):
         out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", ",".join(str(i) for i in self.indices)],
@@ -390,9 +394,19 @@ def main():
     rows_step, dt, st = timed(head_fn, K)
     # the same K steps through the synchronous operator (one host round trip per step)
     sync_leg = None
+    def timed_best(fn, k, reps=3):
+        """secondary legs that synchronise with the host every step: best of `reps` repetitions of k steps (a clock sample that lands
+        inside a 2 ms leg costs it several ms; the headline leg is ONE k-step measurement as the contract says)"""
+        best = None
+        for _ in range(reps):
+            r = timed(fn, k)
+            if best is None or r[1] < best[1]:
+                best = r
+        return best
+
     if plan:
         sync_loop(3)
-        rows_sync, dt_sync, st_sync = timed(sync_loop, K)
+        rows_sync, dt_sync, st_sync = timed_best(sync_loop, K)
         assert rows_sync == rows_step
         sync_leg = (dt_sync, st_sync)
     # the same K steps on the store-SCANNING path (index switched off): the K_scan / K_build / K_probe numbers of SURVEY.md §8(d)
@@ -400,7 +414,7 @@ def main():
     if not args.no_index:
         ctx.set_use_index(False)
         sync_loop(3)
-        rows_scan, dts, st_scan = timed(sync_loop, K)
+        rows_scan, dts, st_scan = timed_best(sync_loop, K)
         assert rows_scan == rows_step
         scan_leg = (dts, st_scan)
         ctx.set_use_index(True)
@@ -595,11 +609,11 @@ def main():
     if sync_leg:
         line["sync_path"] = {"value": rows_all / (dt_sync_m / K), "unit": UNIT, "ms_per_step": dt_sync_m / K * 1e3, "gpu_launches": int(sync_leg[1]["kernel_launches"]),
                              "device_ms_per_step": sync_leg[1]["total_ms"] / K,
-                             "note": "same K steps through the synchronous kb_star_join (result allocation + stream synchronisation every step)"}
+                             "note": "same K steps through the synchronous kb_star_join (result allocation + stream synchronisation every step); best of 3 repetitions of K steps"}
     if scan_leg:
         st_scan = scan_leg[1]
         line["scan_path"] = {"value": rows_all / (dts_m / K), "unit": UNIT, "ms_per_step": dts_m / K * 1e3, "gpu_launches": int(st_scan["kernel_launches"]),
-                             "protocol": "SURVEY.md 8(d): R / (t_scan + t_build + t_probe), every step scans the 12-byte/triple store",
+                             "protocol": "SURVEY.md 8(d): R / (t_scan + t_build + t_probe), every step scans the 12-byte/triple store; best of 3 repetitions of K steps",
                              "roofline": roof(families(st_scan, False), st_scan)}
     if multi:
         line["multi_gpu"] = multi
