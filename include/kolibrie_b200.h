@@ -210,6 +210,17 @@ typedef struct kb_strings kb_strings; /* device-resident decoded column: offsets
 /* Decodes column `col` of `r`: row i becomes the string of its id; an id the dictionary does not hold becomes "unknown" (engine.rs:44).
  * Quoted-triple ids (bit 31, shared/src/quoted_triple_store.rs:28-55) -> KB_E_UNSUPPORTED. At most 2^32-1 bytes per call. */
 KB_API kb_status kb_rel_decode(kb_ctx* ctx, const kb_rel* r, uint32_t col, kb_strings** out);
+/* Dictionary::encode (shared/src/dictionary.rs:32-48) for a BATCH of terms — the load-time encode of sparql_database.rs:1000-1013 — on
+ * the device: term i = bytes[offsets[i] .. offsets[i+1]) (host memory, offsets[0] = 0). A term the device dictionary already holds
+ * (kb_dict_strings_load, earlier kb_dict_encode calls) gets its id; every other distinct string gets the next id in FIRST-SEEN order
+ * over the batch — exactly the ids n_terms sequential Dictionary::encode calls hand out — and is appended to the device dictionary
+ * (kb_rel_decode sees it). out_ids[n_terms]; *n_new = number of new strings; new_first_pos (may be NULL, room for n_terms entries):
+ * new_first_pos[k] = index in the batch of the term that introduced id (ids before the call) + k, so the host dictionary can add the
+ * same strings without a lookup of its own. Limits: < 2^32-16 terms and bytes per call (split larger loads); ids stay below bit 31. */
+KB_API kb_status kb_dict_encode(kb_ctx* ctx, const uint64_t* offsets /* [n_terms + 1] */, const uint8_t* bytes, uint64_t n_terms, uint32_t* out_ids,
+                                uint32_t* n_new, uint64_t* new_first_pos);
+/* ids and bytes the device dictionary holds */
+KB_API kb_status kb_dict_strings_info(kb_ctx* ctx, uint32_t* n_ids, uint64_t* n_bytes);
 KB_API kb_status kb_strings_info(const kb_strings* s, uint64_t* n_strings, uint64_t* total_bytes);
 KB_API kb_status kb_strings_download(kb_ctx* ctx, const kb_strings* s, uint64_t* offsets /* [n + 1] */, uint8_t* bytes /* total_bytes */);
 KB_API void kb_strings_free(kb_ctx* ctx, kb_strings* s);

@@ -10,7 +10,7 @@ import atexit
 import ctypes as C
 import os
 import weakref
-from typing import List, Iterable, Optional, Sequence
+from typing import List, Iterable, Optional, Sequence, Tuple, Union
 
 import numpy as np
 
@@ -162,6 +162,8 @@ def lib() -> C.CDLL:
         "kb_store_download": (i32, [vp, vp, vp, vp, u64, P(u64)]),
         "kb_dict_numeric_load": (i32, [vp, vp, vp, u32]),
         "kb_dict_strings_load": (i32, [vp, vp, vp, u32]),
+        "kb_dict_encode": (i32, [vp, vp, vp, u64, vp, P(u32), vp]),
+        "kb_dict_strings_info": (i32, [vp, P(u32), P(u64)]),
         "kb_dict_legacy_i32_load": (i32, [vp, vp, vp, u32]),
         "kb_rel_decode": (i32, [vp, vp, u32, P(vp)]),
         "kb_strings_info": (i32, [vp, P(u64), P(u64)]),
@@ -223,7 +225,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "kb_version", "kb_ctx_create", "kb_ctx_destroy", "kb_last_error", "kb_set_timing", "kb_get_stats", "kb_synchronize",
     "kb_store_load", "kb_store_load_device", "kb_store_append", "kb_store_append_device", "kb_store_evict", "kb_store_delete", "kb_store_clear", "kb_store_build_index", "kb_set_use_index", "kb_store_size",
-    "kb_store_download", "kb_dict_numeric_load", "kb_dict_legacy_i32_load", "kb_dict_strings_load", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
+    "kb_store_download", "kb_dict_numeric_load", "kb_dict_legacy_i32_load", "kb_dict_strings_load", "kb_dict_encode", "kb_dict_strings_info", "kb_rel_decode", "kb_strings_info", "kb_strings_download", "kb_strings_free", "kb_rel_info", "kb_rel_download", "kb_rel_device_col", "kb_rel_from_host",
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_bind_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_groups_pack", "kb_groups_merge", "kb_star_join_aggregate",
     "kb_star_join_prepare", "kb_plan_submit", "kb_plan_collect", "kb_plan_info", "kb_plan_free", "kb_plan_peer_scratch_bytes", "kb_plan_attach_peers",
@@ -423,6 +425,27 @@ class Context:
         data = np.frombuffer(b"".join(enc), dtype=np.uint8) if enc else np.empty(0, np.uint8)
         data = np.ascontiguousarray(data)
         self._check(lib().kb_dict_strings_load(self.h, _ptr(off), _ptr(data) if len(data) else None, len(enc)))
+
+    def dict_encode(self, terms: Sequence[Union[str, bytes]]):
+        """kb_dict_encode: Dictionary::encode of a batch of terms on the device. Returns (ids uint32[n], first_pos uint64[n_new]):
+        first_pos[k] = index in `terms` of the term that introduced id (ids before the call) + k."""
+        enc = [x.encode("utf-8") if isinstance(x, str) else bytes(x) for x in terms]
+        n = len(enc)
+        ids = np.empty(n, dtype=np.uint32)
+        if n == 0:
+            return ids, np.empty(0, np.uint64)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(np.fromiter((len(b) for b in enc), dtype=np.uint64, count=n), dtype=np.uint64)
+        data = np.ascontiguousarray(np.frombuffer(b"".join(enc), dtype=np.uint8)) if off[-1] else np.empty(0, np.uint8)
+        first = np.empty(n, dtype=np.uint64)
+        n_new = C.c_uint32(0)
+        self._check(lib().kb_dict_encode(self.h, _ptr(off), _ptr(data) if len(data) else None, n, _ptr(ids), C.byref(n_new), _ptr(first)))
+        return ids, first[: n_new.value].copy()
+
+    def dict_strings_info(self) -> Tuple[int, int]:
+        n, b = C.c_uint32(0), C.c_uint64(0)
+        self._check(lib().kb_dict_strings_info(self.h, C.byref(n), C.byref(b)))
+        return int(n.value), int(b.value)
 
     # ---- operators
     def scan(self, pats: Sequence[KbPattern], pushdown: Optional[Sequence[Optional[Sequence[KbFilterOp]]]] = None):

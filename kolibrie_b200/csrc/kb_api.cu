@@ -2614,6 +2614,9 @@ kb_status kb_dict_strings_load(kb_ctx* ctx, const uint64_t* offsets, const uint8
     ctx->dict_off.reset();
     ctx->dict_bytes.reset();
     ctx->dict_ids = 0;
+    ctx->dict_index.reset();  // (kb_dict_encode rebuilds its string -> id index lazily)
+    ctx->dict_index_slots = 0;
+    ctx->dict_indexed = 0;
     if (n_ids == 0) return KB_OK;
     if (!offsets) return kb::fail(ctx, KB_E_INVALID, "NULL offsets");
     const uint64_t total = offsets[n_ids];

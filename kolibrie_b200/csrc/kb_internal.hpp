@@ -164,8 +164,11 @@ struct kb_ctx {
     kb::Buf num, isnum;
     kb::Buf i32val, isi32;  // kb_dict_legacy_i32_load: the legacy executor's integer view of the terms
     kb::u32 n_i32 = 0;
-    kb::Buf dict_off, dict_bytes;  // kb_dict_strings_load: u64 offsets [dict_ids + 1] + UTF-8 bytes
+    kb::Buf dict_off, dict_bytes;  // kb_dict_strings_load / kb_dict_encode: u64 offsets [dict_ids + 1] + UTF-8 bytes
     kb::u32 dict_ids = 0;
+    kb::Buf dict_index;            // kb_dict_encode: open-addressing index string -> id (hash tag << 32 | id), built lazily
+    kb::u64 dict_index_slots = 0;
+    kb::u32 dict_indexed = 0;      // ids [0, dict_indexed) are in the index
     kb::u32 n_ids = 0;
     kb::u64 num_version = 1;  // bumped by kb_dict_numeric_load: typed literal columns of the index are tied to it
     // tile-state buffer of the look-back prefix (never cleared: words carry the launch epoch)

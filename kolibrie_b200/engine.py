@@ -52,6 +52,21 @@ class Dictionary:
             self.id_to_string.append(value)
         return i
 
+    def encode_bulk(self, ctx, terms: Sequence[str]) -> np.ndarray:
+        """the load-time encode of a whole batch (sparql_database.rs:1000-1013 calls encode once per term) on the device: kb_dict_encode
+        hands out the ids the sequential loop would, and this dictionary learns the new strings from the positions that introduced them.
+        The device dictionary must mirror this one (it does when every string entered through encode_bulk / dict_strings_load)."""
+        n_dev, _ = ctx.dict_strings_info()
+        if n_dev != len(self.id_to_string):
+            ctx.dict_strings_load(self.id_to_string)
+        ids, first = ctx.dict_encode(terms)
+        for pos in first:
+            t = terms[int(pos)]
+            assert len(self.id_to_string) < 0x8000_0000, "Dictionary ID space exhausted"  # dictionary.rs:36-40
+            self.string_to_id[t] = len(self.id_to_string)
+            self.id_to_string.append(t)
+        return ids
+
     def lookup(self, value: str) -> Optional[int]:
         return self.string_to_id.get(value)
 
@@ -354,6 +369,15 @@ class SparqlDatabase:
     def add_triple_parts(self, s: str, p: str, o: str):
         t = (self.dictionary.encode(s), self.dictionary.encode(p), self.dictionary.encode(o))
         self.add_triple(t)
+
+    def add_triples_bulk(self, statements: Sequence[Tuple[str, str, str]]):
+        """bulk load of parsed (s, p, o) STRING triples (what parse_ntriples / parse_rdf hand to the per-term encode loop,
+        sparql_database.rs:1000-1013): one device encode of all 3n terms in s, p, o order per triple — the ids are those of the
+        sequential loop (dictionary.rs:32-48) — then the triples join the set"""
+        terms = [t for st in statements for t in st]
+        ids = self.dictionary.encode_bulk(self.ctx, terms).reshape(-1, 3)
+        for row in ids:
+            self.add_triple((int(row[0]), int(row[1]), int(row[2])))
 
     def add_triple(self, t: Tuple[int, int, int]):  # sparql_database.rs:215-226
         if t not in self.triples:

@@ -49,6 +49,9 @@ extern "C" {
     pub fn kb_store_size(ctx: *mut KbCtx, n_triples: *mut u64, n_segments: *mut u32) -> kb_status;
     pub fn kb_dict_numeric_load(ctx: *mut KbCtx, num_or0: *const c_double, is_num: *const u8, n_ids: u32) -> kb_status;
     pub fn kb_dict_strings_load(ctx: *mut KbCtx, offsets: *const u64, bytes: *const u8, n_ids: u32) -> kb_status;
+    pub fn kb_dict_encode(ctx: *mut KbCtx, offsets: *const u64, bytes: *const u8, n_terms: u64, out_ids: *mut u32, n_new: *mut u32, new_first_pos: *mut u64) -> kb_status;
+    pub fn kb_dict_strings_info(ctx: *mut KbCtx, n_ids: *mut u32, n_bytes: *mut u64) -> kb_status;
+    pub fn kb_store_append_device(ctx: *mut KbCtx, d_s: *const u32, d_p: *const u32, d_o: *const u32, n: u64, tag: u64) -> kb_status;
     // relations
     pub fn kb_rel_info(r: *const KbRel, n_rows: *mut u64, n_cols: *mut u32, slots: *mut u32) -> kb_status;
     pub fn kb_rel_download(ctx: *mut KbCtx, r: *const KbRel, col: u32, dst: *mut u32) -> kb_status;

@@ -85,6 +85,26 @@ impl DeviceStore {
     }
 
     pub fn invalidate(&mut self) { self.synced_triples = usize::MAX; self.synced_dict = usize::MAX; }
+
+    /// The per-term `Dictionary::encode` loop of a bulk load (sparql_database.rs:1000-1013) as one device call. Returns the ids of
+    /// `terms` (those the sequential loop would hand out, dictionary.rs:32-48) and, for every NEW string in id order, the index of the
+    /// term that introduced it: the caller replays `dict.encode(terms[p])` for those positions only. The device dictionary must hold
+    /// the host dictionary's strings (`sync` uploads them; afterwards the two grow in lock step through this call).
+    pub fn encode_bulk(&mut self, terms: &[&str]) -> Result<(Vec<u32>, Vec<u64>), String> {
+        let n = terms.len();
+        let mut offs = Vec::with_capacity(n + 1);
+        let mut bytes = Vec::new();
+        offs.push(0u64);
+        for t in terms { bytes.extend_from_slice(t.as_bytes()); offs.push(bytes.len() as u64); }
+        let mut ids = vec![0u32; n];
+        let mut first = vec![0u64; n];
+        let mut n_new = 0u32;
+        let rc = unsafe { kb_dict_encode(self.ctx, offs.as_ptr(), bytes.as_ptr(), n as u64, ids.as_mut_ptr(), &mut n_new, first.as_mut_ptr()) };
+        if rc != KB_OK { return Err(self.last_error()); }
+        first.truncate(n_new as usize);
+        if self.synced_dict != usize::MAX { self.synced_dict += n_new as usize; }
+        Ok((ids, first))
+    }
 }
 
 impl Drop for DeviceStore {
