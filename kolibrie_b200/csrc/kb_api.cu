@@ -719,7 +719,7 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
     // ---- grouped (CSR) join: one key column with a dense id range and no join filter
     if (ctx->csr_join && common.size() == 1 && (!post || post->ops.empty())) {
         const u32* bk = B.cols[B.col_of(common[0])].ptr;
-        const u32 off = ctrl_alloc(ctx, 8);  // [0] min, [1] max, [2..3] u64 output rows, [4] ticket, [5] total, [6] zero
+        const u32 off = ctrl_alloc(ctx, 8);  // [0] min, [1] max, [2..3] u64 output rows, [4] ticket, [5] total, [6] zero, [7] heavy tiles
         KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off, 0xFF, sizeof(u32), ctx->st));
         KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off + 1, 0, 7 * sizeof(u32), ctx->st));
         timer_begin(ctx, F_BUILD);
@@ -792,9 +792,15 @@ kb_status hash_join_impl(kb_ctx* ctx, const kb_rel& L, const kb_rel& R, const Fi
             G.total = ctx->ctrl + off + 5;
             G.zero_word = ctx->ctrl + off + 6;
             G.epoch = ctx->epoch++;
+            Buf heavy;  // tiles whose expansion is spread over the grid by the second launch (skewed keys)
+            if (total > PROBEG_HEAVY) {
+                KB_TRY(alloc_buf(ctx, (size_t)G.n_tiles * sizeof(ProbeGParams::Heavy), &heavy));
+                G.heavy = static_cast<ProbeGParams::Heavy*>(heavy->p);
+                G.heavy_count = ctx->ctrl + off + 7;
+            }
             ctx->stats.rows_probed += Pr.n;
             if (total) {
-                timer_begin(ctx, F_PROBE);
+                timer_begin(ctx, F_PROBE, G.heavy ? 2 : 1);
                 launch_probe_grouped(G, ctx->n_sms, ctx->st);
                 timer_end(ctx);
                 KB_CUDA(ctx, cudaGetLastError());

@@ -96,8 +96,9 @@ kb_status ensure_set(Fix& fx, PredRel& r, u64 extra, bool must_grow = false) {
     const u64 expect = std::min<u64>(extra, std::max<u64>(r.set_count / 2, 1u << 20));
     const u64 need = (r.set_count + expect) * 2;
     if (r.set && need <= r.set_slots && !must_grow) return KB_OK;
+    static const u64 slack = getenv("KOLIBRIE_SET_SLACK") ? std::max(1, atoi(getenv("KOLIBRIE_SET_SLACK"))) : 2;
     u64 slots = 1024;
-    while (slots < need * 2) slots <<= 1;
+    while (slots < need * slack) slots <<= 1;
     if (must_grow) slots = std::max<u64>(slots, (u64)r.set_slots * 2);
     if (slots > (1ull << 31)) slots = 1ull << 31;
     if (slots < need || (must_grow && r.set && slots <= r.set_slots))

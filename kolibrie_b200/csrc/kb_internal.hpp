@@ -22,7 +22,10 @@ struct Life {  // shared by a context and every buffer it handed out: relations 
     std::vector<Cached> cache;
     size_t cached_bytes = 0;
     bool cache_off = false;  // KOLIBRIE_BUF_CACHE=0
-    static constexpr size_t MIN_BYTES = 1u << 20, MAX_ENTRIES = 48, MAX_BYTES = 24ull << 30;
+    // Sized for the working set of the largest workload (a config-4 closure releases ~30 GB of buffers when it ends and asks for the
+    // same sizes in the same order the next time): with 24 GB / 48 entries the 8 GB known-fact set fell out of the cache, and one
+    // closure in seven then waited 0.3-1.2 s for the pool to re-map it. When the cache is full the OLDEST entries go back to the pool.
+    static constexpr size_t MIN_BYTES = 1u << 20, MAX_ENTRIES = 256, MAX_BYTES = 56ull << 30;
 };
 struct DevBuf {
     void* p = nullptr;
@@ -32,7 +35,12 @@ struct DevBuf {
     ~DevBuf() {
         if (!p) return;
         if (life && life->alive) {
-            if (!life->cache_off && bytes >= Life::MIN_BYTES && life->cache.size() < Life::MAX_ENTRIES && life->cached_bytes + bytes <= Life::MAX_BYTES) {
+            if (!life->cache_off && bytes >= Life::MIN_BYTES && bytes <= Life::MAX_BYTES / 2) {
+                while (!life->cache.empty() && (life->cache.size() >= Life::MAX_ENTRIES || life->cached_bytes + bytes > Life::MAX_BYTES)) {
+                    cudaFreeAsync(life->cache.front().p, st);  // (entries are in release order: the front is the oldest)
+                    life->cached_bytes -= life->cache.front().bytes;
+                    life->cache.erase(life->cache.begin());
+                }
                 life->cache.push_back({p, bytes});
                 life->cached_bytes += bytes;
                 return;

@@ -1852,13 +1852,58 @@ void launch_probe_chained(const ProbeCParams& p, int n_sms, cudaStream_t st) {
 
 // =================================================================================================================
 // K_build / K_probe (grouped by key, CSR directory)
+// Directory builds (count, then fill) go tile by tile through a shared-memory hash of the tile's keys: the rows of a tile that carry the
+// same key are counted / ranked with SHARED atomics and the global counter of a key is touched once per (tile, key). A Datalog
+// closure's subClassOf facts name the root class a million times, in no particular order: one global atomic per row (and per warp-level
+// group of equal keys, which random order leaves at size one) made the 2 M-row build of the transitive rule's join take 3-7 ms —
+// more than the 331 M-row join next to it.
+constexpr u32 CSR_ITEMS = 8, CSR_TILE = 256 * CSR_ITEMS, CSR_HASH = 4096;
+struct CsrTileHash {
+    u32 key[CSR_HASH], cnt[CSR_HASH], base[CSR_HASH];
+};
+// slot of k in the tile's table (claimed when absent); the table is at most half full (2048 rows, 4096 slots)
+__device__ __forceinline__ u32 csr_slot(CsrTileHash& H, u32 k) {
+    u32 slot = mix32(k) & (CSR_HASH - 1u);
+    for (;;) {
+        u32 cur = *reinterpret_cast<volatile u32*>(&H.key[slot]);
+        if (cur == EMPTY32) cur = atomicCAS(&H.key[slot], EMPTY32, k);
+        if (cur == EMPTY32 || cur == k) return slot;
+        slot = (slot + 1u) & (CSR_HASH - 1u);
+    }
+}
 __global__ void __launch_bounds__(256) csr_count_kernel(const u32* __restrict__ keys, u32 n, u32 kmin, u32* __restrict__ counts) {
-    const u32 stride = gridDim.x * blockDim.x;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&counts[keys[i] - kmin], 1u);
+    __shared__ CsrTileHash H;
+    for (u32 i = threadIdx.x; i < CSR_HASH; i += 256u) { H.key[i] = EMPTY32; H.cnt[i] = 0u; }
+    __syncthreads();
+    const u32 n_tiles = (n + CSR_TILE - 1u) / CSR_TILE;
+    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u32 row0 = tile * CSR_TILE;
+        u32 k[CSR_ITEMS], slot[CSR_ITEMS];
+        bool lead[CSR_ITEMS];
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) {
+            const u32 i = row0 + j * 256u + threadIdx.x;
+            k[j] = i < n ? keys[i] - kmin : EMPTY32;
+        }
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) {
+            lead[j] = false;
+            if (k[j] == EMPTY32) continue;
+            slot[j] = csr_slot(H, k[j]);
+            lead[j] = atomicAdd(&H.cnt[slot[j]], 1u) == 0u;  // the first row of the key in this tile speaks for it
+        }
+        __syncthreads();
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) if (lead[j]) atomicAdd(&counts[k[j]], H.cnt[slot[j]]);
+        __syncthreads();
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) if (lead[j]) { H.key[slot[j]] = EMPTY32; H.cnt[slot[j]] = 0u; }
+        __syncthreads();
+    }
 }
 void launch_csr_count(const u32* keys, u32 n, u32 kmin, u32* counts, int n_sms, cudaStream_t st) {
     if (n == 0) return;
-    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    const int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + CSR_TILE - 1ull) / CSR_TILE);
     csr_count_kernel<<<grid, 256, 0, st>>>(keys, n, kmin, counts);
 }
 
@@ -1947,11 +1992,42 @@ struct CsrFillParams {
     const u32* pay_in[KB_MAX_COLS];
     u32* pay_out[KB_MAX_COLS];
 };
-__global__ void __launch_bounds__(256) csr_fill_kernel(const CsrFillParams P) {
-    const u32 stride = gridDim.x * blockDim.x;
-    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) {
-        const u32 pos = atomicAdd(&P.cursor[P.keys[i] - P.kmin], 1u);
-        for (u32 c = 0; c < P.n_pay; c++) P.pay_out[c][pos] = P.pay_in[c][i];
+__global__ void __launch_bounds__(256) csr_fill_kernel(const __grid_constant__ CsrFillParams P) {
+    __shared__ CsrTileHash H;
+    for (u32 i = threadIdx.x; i < CSR_HASH; i += 256u) { H.key[i] = EMPTY32; H.cnt[i] = 0u; }
+    __syncthreads();
+    const u32 n_tiles = (P.n + CSR_TILE - 1u) / CSR_TILE;
+    for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const u32 row0 = tile * CSR_TILE;
+        u32 k[CSR_ITEMS], slot[CSR_ITEMS], rank[CSR_ITEMS];
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) {
+            const u32 i = row0 + j * 256u + threadIdx.x;
+            k[j] = i < P.n ? P.keys[i] - P.kmin : EMPTY32;
+        }
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) {
+            rank[j] = EMPTY32;
+            if (k[j] == EMPTY32) continue;
+            slot[j] = csr_slot(H, k[j]);
+            rank[j] = atomicAdd(&H.cnt[slot[j]], 1u);
+        }
+        __syncthreads();
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++)  // one range of the key's run per (tile, key)
+            if (rank[j] == 0u) H.base[slot[j]] = atomicAdd(&P.cursor[k[j]], H.cnt[slot[j]]);
+        __syncthreads();
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) {
+            if (rank[j] == EMPTY32) continue;
+            const u32 i = row0 + j * 256u + threadIdx.x;
+            const u32 pos = H.base[slot[j]] + rank[j];
+            for (u32 c = 0; c < P.n_pay; c++) P.pay_out[c][pos] = P.pay_in[c][i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (u32 j = 0; j < CSR_ITEMS; j++) if (rank[j] == 0u) { H.key[slot[j]] = EMPTY32; H.cnt[slot[j]] = 0u; }
+        __syncthreads();
     }
 }
 void launch_csr_fill(const u32* keys, u32 n, u32 kmin, u32* cursor, const u32* const* pay_in, u32* const* pay_out, u32 n_pay, int n_sms, cudaStream_t st) {
@@ -1959,7 +2035,7 @@ void launch_csr_fill(const u32* keys, u32 n, u32 kmin, u32* cursor, const u32* c
     CsrFillParams P{};
     P.keys = keys; P.n = n; P.kmin = kmin; P.n_pay = n_pay; P.cursor = cursor;
     for (u32 c = 0; c < n_pay; c++) { P.pay_in[c] = pay_in[c]; P.pay_out[c] = pay_out[c]; }
-    const int grid = (int)umin64((u64)n_sms * 8ull, ((u64)n + 255ull) / 256ull);
+    const int grid = (int)umin64((u64)n_sms * 4ull, ((u64)n + CSR_TILE - 1ull) / CSR_TILE);
     csr_fill_kernel<<<grid, 256, 0, st>>>(P);
 }
 
@@ -2032,6 +2108,11 @@ void launch_csr_total(const u32* pkeys, u32 n, const CsrTab& tab, unsigned long 
 // One tile = 1024 probe rows staged by TMA. Pass 1: every row reads its directory entry (begin, count); the counts are scanned over the
 // tile. Pass 2: output row r of the tile belongs to the probe row whose prefix range holds r (binary search in shared memory), so
 // consecutive threads write consecutive output rows and read consecutive payload rows.
+// Skew: a probe row may match 10^5 build rows (the closure of a class tree joined on the ancestor), and a tile of such rows used to be
+// expanded by the ONE CTA that scanned it — the 2 M x 5 M-row join of the transitive rule took 6 ms for 5 M output rows. A tile whose
+// expansion exceeds PROBEG_HEAVY rows is now only recorded by the first launch (HEAVY = false); the second launch (HEAVY = true) walks
+// the recorded tiles, every CTA re-stages the tile and expands its share of PROBEG_CHUNK-row pieces.
+template <bool HEAVY>
 __global__ void __launch_bounds__(PROBEG_THREADS) probe_grouped_kernel(const __grid_constant__ ProbeGParams P) {
     extern __shared__ __align__(128) u32 smem[];  // n_pcols tiles, then begin[TILE], pref[TILE]
     u32* s_begin = smem + P.n_pcols * PROBEG_TILE;
@@ -2047,22 +2128,31 @@ __global__ void __launch_bounds__(PROBEG_THREADS) probe_grouped_kernel(const __g
     }
     u32 parity = 0;
     const u32* sKey = smem + P.pkey * PROBEG_TILE;
+    const u32 n_heavy = HEAVY ? *reinterpret_cast<volatile u32*>(P.heavy_count) : 0u;
+    u32 h_next = 0;  // HEAVY: next recorded tile to look at
     for (;;) {
         __syncthreads();  // the previous tile's expansion has finished reading shared memory
-        if (tid == 0) {
-            const u32 t = atomicAdd(P.ticket, 1u);
-            s_tile = t;
-            if (t < P.n_tiles) {
-                const u32 b = t * (u32)PROBEG_TILE;
-                const u32 c = min((u32)PROBEG_TILE, P.n - b);
-                const u32 bytes = (c * 4u + 15u) & ~15u;
-                mbar_arrive_expect_tx(&bar, bytes * P.n_pcols);
-                for (u32 q = 0; q < P.n_pcols; q++) tma_load_1d(smem + q * PROBEG_TILE, P.pcol[q] + b, bytes, &bar);
+        u32 h_gbase = 0, h_total = 0;
+        if constexpr (HEAVY) {
+            // the recorded tiles in list order; a CTA takes part in a tile when it has at least one piece of it
+            u32 t = EMPTY32;
+            while (h_next < n_heavy) {
+                const ProbeGParams::Heavy e = P.heavy[h_next++];
+                const u32 pieces = (e.total + PROBEG_CHUNK - 1u) / PROBEG_CHUNK;
+                if (blockIdx.x < pieces) { t = e.tile; h_gbase = e.gbase; h_total = e.total; break; }
             }
-        }
+            if (tid == 0) s_tile = t;
+        } else if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= P.n_tiles) break;
+        if (tid == 0) {
+            const u32 b = tile * (u32)PROBEG_TILE;
+            const u32 c = min((u32)PROBEG_TILE, P.n - b);
+            const u32 bytes = (c * 4u + 15u) & ~15u;
+            mbar_arrive_expect_tx(&bar, bytes * P.n_pcols);
+            for (u32 q = 0; q < P.n_pcols; q++) tma_load_1d(smem + q * PROBEG_TILE, P.pcol[q] + b, bytes, &bar);
+        }
         const u32 cnt = min((u32)PROBEG_TILE, P.n - tile * (u32)PROBEG_TILE);
         mbar_wait(&bar, parity);
         parity ^= 1u;
@@ -2104,8 +2194,17 @@ __global__ void __launch_bounds__(PROBEG_THREADS) probe_grouped_kernel(const __g
             const u32 total = __shfl_sync(0xffffffffu, wi, PROBEG_THREADS / 32 - 1);
             if (lane < PROBEG_THREADS / 32) s_w[lane] = wi - w;
             if (lane == 0) s_w[PROBEG_THREADS / 32] = total;
-            const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
-            if (lane == 0) s_base = ex;
+            if (!HEAVY) {
+                const u32 ex = tile_prefix_2level(P.tile_state, P.block_state, tile, P.n_tiles, 0u, P.epoch, total, P.zero_word, P.total, P.ordered, lane);
+                if (lane == 0) {
+                    s_base = ex;
+                    if (P.heavy && total > PROBEG_HEAVY) {  // recorded for the second launch
+                        ProbeGParams::Heavy e;
+                        e.tile = tile; e.gbase = ex; e.total = total; e.pad = 0u;
+                        P.heavy[atomicAdd(P.heavy_count, 1u)] = e;
+                    }
+                }
+            }
         }
         __syncthreads();
         {
@@ -2116,20 +2215,26 @@ __global__ void __launch_bounds__(PROBEG_THREADS) probe_grouped_kernel(const __g
         __syncthreads();
         // pass 2: load-balanced expansion
         const u32 total = s_w[PROBEG_THREADS / 32];
-        const u32 gbase = s_base;
-        for (u32 r = (u32)tid; r < total; r += PROBEG_THREADS) {
-            u32 lo = 0, hi = PROBEG_TILE - 1;  // largest idx with pref[idx] <= r
+        const u32 gbase = HEAVY ? h_gbase : s_base;
+        if (!HEAVY && P.heavy && total > PROBEG_HEAVY) continue;
+        const u32 pieces = HEAVY ? (h_total + PROBEG_CHUNK - 1u) / PROBEG_CHUNK : 1u;
+        for (u32 piece = HEAVY ? blockIdx.x : 0u; piece < pieces; piece += gridDim.x) {
+            const u32 r0 = HEAVY ? piece * PROBEG_CHUNK : 0u;
+            const u32 r1 = HEAVY ? min(total, r0 + PROBEG_CHUNK) : total;
+            for (u32 r = r0 + (u32)tid; r < r1; r += PROBEG_THREADS) {
+                u32 lo = 0, hi = PROBEG_TILE - 1;  // largest idx with pref[idx] <= r
 #pragma unroll
-            for (int step = 0; step < 10; step++) {
-                const u32 mid = (lo + hi + 1u) >> 1;
-                if (s_pref[mid] <= r) lo = mid; else hi = mid - 1u;
-            }
-            const u32 src = lo;
-            const u32 brow = s_begin[src] + (r - s_pref[src]);
-            const u32 pos = gbase + r;
-            if (pos < P.cap) {
-                for (u32 q = 0; q < P.n_pcols; q++) P.out[q][pos] = smem[q * PROBEG_TILE + src];
-                for (u32 q = 0; q < P.tab.n_pay; q++) P.out[P.n_pcols + q][pos] = __ldg(P.tab.pay[q] + brow);
+                for (int step = 0; step < 10; step++) {
+                    const u32 mid = (lo + hi + 1u) >> 1;
+                    if (s_pref[mid] <= r) lo = mid; else hi = mid - 1u;
+                }
+                const u32 src = lo;
+                const u32 brow = s_begin[src] + (r - s_pref[src]);
+                const u32 pos = gbase + r;
+                if (pos < P.cap) {
+                    for (u32 q = 0; q < P.n_pcols; q++) P.out[q][pos] = smem[q * PROBEG_TILE + src];
+                    for (u32 q = 0; q < P.tab.n_pay; q++) P.out[P.n_pcols + q][pos] = __ldg(P.tab.pay[q] + brow);
+                }
             }
         }
     }
@@ -2137,9 +2242,16 @@ __global__ void __launch_bounds__(PROBEG_THREADS) probe_grouped_kernel(const __g
 void launch_probe_grouped(const ProbeGParams& p, int n_sms, cudaStream_t st) {
     if (p.n == 0) return;
     const size_t smem = (size_t)(p.n_pcols + 2) * PROBEG_TILE * sizeof(u32);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(probe_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int grid = grid_for((const void*)probe_grouped_kernel, PROBEG_THREADS, smem, n_sms, p.n_tiles);
-    probe_grouped_kernel<<<grid, PROBEG_THREADS, smem, st>>>(p);
+    if (smem > 48 * 1024) {
+        cudaFuncSetAttribute(probe_grouped_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(probe_grouped_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    const int grid = grid_for((const void*)probe_grouped_kernel<false>, PROBEG_THREADS, smem, n_sms, p.n_tiles);
+    probe_grouped_kernel<false><<<grid, PROBEG_THREADS, smem, st>>>(p);
+    if (p.heavy) {  // the recorded heavy tiles (usually none: the launch then finds an empty list and ends)
+        const int grid2 = grid_for((const void*)probe_grouped_kernel<true>, PROBEG_THREADS, smem, n_sms, 1u << 20);
+        probe_grouped_kernel<true><<<grid2, PROBEG_THREADS, smem, st>>>(p);
+    }
 }
 
 // cartesian product: output row (i*nr + j) = left row i ++ right row j (engine.rs:1054-1071)

@@ -337,7 +337,13 @@ struct ProbeGParams {
     u64 epoch;
     u32* total;
     const u32* zero_word;
+    // tiles whose expansion exceeds PROBEG_HEAVY output rows are not expanded by the CTA that scanned them: it appends them here
+    // (heavy_count[0] entries) and a second launch spreads each one's output range over the whole grid in PROBEG_CHUNK-row pieces
+    struct Heavy { u32 tile, gbase, total, pad; };
+    Heavy* heavy;        // room for n_tiles entries (null: no splitting)
+    u32* heavy_count;    // zeroed control word
 };
+constexpr u32 PROBEG_HEAVY = 32768, PROBEG_CHUNK = 4096;
 void launch_probe_grouped(const ProbeGParams& p, int n_sms, cudaStream_t st);
 
 // cartesian product (engine.rs:1054-1071) — small inputs only
