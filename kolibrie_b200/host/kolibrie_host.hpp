@@ -10,6 +10,8 @@
 //   Condition                 kolibrie/src/streamertail_optimizer/types.rs:110-186
 //   SparqlDatabase            kolibrie/src/sparql_database.rs:49-60, 215-258, 3364-3394
 //   ExecutionEngine           kolibrie/src/streamertail_optimizer/execution/engine.rs:27, 54
+//   PreparedStarJoin          (new) a StarJoin resolved once, submitted asynchronously: kb_star_join_prepare / kb_plan_submit / kb_plan_collect
+//   WindowStore               the R2R store maintenance of kolibrie/src/rsp/simple_r2r.rs:95-142 on the device (append / evict by tag)
 //
 // All data-touching work happens in libkolibrie_b200.so; a kb_status other than KB_OK becomes a kolibrie::GpuError whose
 // `unsupported()` tells the caller to take the reference's CPU path (KB_E_UNSUPPORTED).
@@ -212,8 +214,12 @@ class Reasoner {
 
   private:
     static uint32_t cmp_of(const std::string& op) {
-        if (op == ">") return KB_CMP_GT; if (op == ">=") return KB_CMP_GE; if (op == "<") return KB_CMP_LT;
-        if (op == "<=") return KB_CMP_LE; if (op == "=") return KB_CMP_EQ; if (op == "!=") return KB_CMP_NE;
+        if (op == ">") return KB_CMP_GT;
+        if (op == ">=") return KB_CMP_GE;
+        if (op == "<") return KB_CMP_LT;
+        if (op == "<=") return KB_CMP_LE;
+        if (op == "=") return KB_CMP_EQ;
+        if (op == "!=") return KB_CMP_NE;
         return 0;  // e.g. "OR:>" is a no-op in the reference (rules.rs:133-165)
     }
     void sync() {
@@ -343,10 +349,85 @@ class SparqlDatabase {
         uploaded_ = version_;
     }
     const Device& device() const { return *dev_; }
+    // the per-term encode loop of a bulk load (sparql_database.rs:1000-1013 -> dictionary.rs:32-48) as one device call: `terms` holds
+    // three strings per triple in document order; the ids are those of the sequential loop, the host dictionary learns the new strings
+    // from the positions that introduced them, the triples join the set
+    void add_triples_bulk(const std::vector<std::string>& terms) {
+        if (terms.size() % 3) throw std::invalid_argument("three terms per triple");
+        uint32_t n_dev = 0;
+        dev_->check(kb_dict_strings_info(dev_->get(), &n_dev, nullptr));
+        if (n_dev != dictionary.id_to_string.size()) upload_strings();
+        std::vector<uint64_t> off(terms.size() + 1, 0);
+        std::string bytes;
+        for (size_t i = 0; i < terms.size(); i++) { bytes += terms[i]; off[i + 1] = bytes.size(); }
+        std::vector<uint32_t> ids(terms.size());
+        std::vector<uint64_t> first(terms.size());
+        uint32_t n_new = 0;
+        dev_->check(kb_dict_encode(dev_->get(), off.data(), reinterpret_cast<const uint8_t*>(bytes.data()), terms.size(), ids.data(), &n_new, first.data()));
+        for (uint32_t k = 0; k < n_new; k++) dictionary.encode(terms[first[k]]);  // same order => same ids
+        for (size_t i = 0; i + 2 < ids.size(); i += 3) add_triple(Triple{ids[i], ids[i + 1], ids[i + 2]});
+    }
+
+  private:
+    void upload_strings() {
+        std::vector<uint64_t> off(dictionary.id_to_string.size() + 1, 0);
+        std::string bytes;
+        for (size_t i = 0; i < dictionary.id_to_string.size(); i++) { bytes += dictionary.id_to_string[i]; off[i + 1] = bytes.size(); }
+        dev_->check(kb_dict_strings_load(dev_->get(), off.data(), reinterpret_cast<const uint8_t*>(bytes.data()), (uint32_t)dictionary.id_to_string.size()));
+    }
+    std::shared_ptr<Device> dev_;
+    long version_ = 0, uploaded_ = -1;
+};
+
+// A StarJoin resolved once and submitted asynchronously (the headline path of bench.py): submit() is one kernel launch, collect() waits
+// for that ticket only; up to `ring` tickets may be in flight. The plan is bound to the store / index version it was prepared on.
+class PreparedStarJoin {
+  public:
+    PreparedStarJoin(SparqlDatabase& db, const std::string& join_var, const std::vector<TriplePattern>& patterns, const Condition* filter = nullptr, uint32_t ring = 4)
+        : dev_(&db.device()) {
+        db.build_all_indexes();
+        std::vector<kb_pattern> ps;
+        for (auto& p : patterns) ps.push_back(sm_.pattern(p));
+        std::vector<kb_filter_op> ops;
+        if (filter) filter->compile(filter->expression, sm_, db.dictionary, &ops);
+        dev_->check(kb_star_join_prepare(dev_->get(), sm_.of(join_var), ps.data(), (uint32_t)ps.size(), ops.data(), (uint32_t)ops.size(), nullptr, 0, nullptr, 0, ring, &plan_));
+    }
+    ~PreparedStarJoin() { if (plan_) kb_plan_free(dev_->get(), plan_); }
+    PreparedStarJoin(const PreparedStarJoin&) = delete;
+    PreparedStarJoin& operator=(const PreparedStarJoin&) = delete;
+    uint64_t submit() { uint64_t t = 0; dev_->check(kb_plan_submit(dev_->get(), plan_, &t)); return t; }
+    uint64_t collect(uint64_t ticket) { uint64_t n = 0; dev_->check(kb_plan_collect(dev_->get(), plan_, ticket, &n, nullptr, nullptr)); return n; }  // rows of that step
+    const SlotMap& slots() const { return sm_; }
+
+  private:
+    const Device* dev_;
+    SlotMap sm_;
+    kb_plan* plan_ = nullptr;
+};
+
+// SimpleR2R::add / remove (kolibrie/src/rsp/simple_r2r.rs:95-128) for whole window slides: a slide is a store segment with a tag; the
+// store index built once stays valid across slides (kb_store_append / kb_store_evict maintain it in place).
+class WindowStore {
+  public:
+    explicit WindowStore(std::shared_ptr<Device> dev) : dev_(std::move(dev)) {}
+    void append_slide(uint64_t tag, const std::vector<Triple>& slide) {
+        std::vector<uint32_t> s, p, o;
+        for (auto& t : slide) { s.push_back(t.subject); p.push_back(t.predicate); o.push_back(t.object); }
+        dev_->check(kb_store_append(dev_->get(), s.data(), p.data(), o.data(), s.size(), tag));
+    }
+    void evict_slide(uint64_t tag) { dev_->check(kb_store_evict(dev_->get(), tag)); }
+    void build_index() { dev_->check(kb_store_build_index(dev_->get(), nullptr, nullptr)); }
+    uint64_t star_join_rows(uint32_t join_slot, const std::vector<kb_pattern>& ps) {
+        kb_rel* out = nullptr;
+        dev_->check(kb_star_join(dev_->get(), join_slot, ps.data(), (uint32_t)ps.size(), nullptr, 0, &out));
+        uint64_t n = 0;
+        kb_rel_info(out, &n, nullptr, nullptr);
+        kb_rel_free(dev_->get(), out);
+        return n;
+    }
 
   private:
     std::shared_ptr<Device> dev_;
-    long version_ = 0, uploaded_ = -1;
 };
 
 struct ExecutionEngine {
@@ -377,8 +458,22 @@ struct ExecutionEngine {
                 for (auto& v : op.variables) slots.push_back(sm.of(v));
                 dev.check(kb_project(dev.get(), in->r, slots.data(), (uint32_t)slots.size(), &out));
             } break;
-            case PhysicalOperator::HashJoin: case PhysicalOperator::OptimizedHashJoin: case PhysicalOperator::NestedLoopJoin:
-            case PhysicalOperator::ParallelJoin: {  // ParallelJoin with a scan on the right = bind join (engine.rs:935-937) = natural join
+            case PhysicalOperator::ParallelJoin:
+                // ParallelJoin with a scan on the right = bind join (engine.rs:926-949 -> 840-885): every left row is substituted into the
+                // right pattern and looked up in the index; relationally the natural join of the two (the fallback when the device says
+                // the pattern's shape has no lookup)
+                if (op.right->kind == PhysicalOperator::TableScan || op.right->kind == PhysicalOperator::IndexScan) {
+                    Rel l = run(*op.left, db, sm);
+                    kb_pattern p = sm.pattern(op.right->pattern);
+                    const kb_status st = kb_bind_join(dev.get(), l->r, &p, &out);
+                    if (st == KB_OK) break;
+                    if (st != KB_E_UNSUPPORTED) dev.check(st);
+                    Rel r = run(*op.right, db, sm);
+                    dev.check(kb_hash_join(dev.get(), l->r, r->r, &out));
+                    break;
+                }
+                [[fallthrough]];
+            case PhysicalOperator::HashJoin: case PhysicalOperator::OptimizedHashJoin: case PhysicalOperator::NestedLoopJoin: {
                 Rel l = run(*op.left, db, sm), r = run(*op.right, db, sm);
                 dev.check(kb_hash_join(dev.get(), l->r, r->r, &out));
             } break;

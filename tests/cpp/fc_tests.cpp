@@ -1,6 +1,7 @@
 // fc_tests.cpp — the reference's forward-chaining tests (datalog/tests/reasoning_tests.rs:28-404) and two executor queries
 // (kolibrie/tests/integration_test.rs fixture; simple_select_synth_data.rs), written against the C++ host mirror so they read like
 // the reference's own tests. Built and run by tests/test_gpu_cpp_host.py on the GPU box. Exit code = number of failed checks.
+#include <array>
 #include <cstdio>
 #include <string>
 
@@ -143,11 +144,64 @@ static void executor_employee4() {
     for (auto& r : rows) CHECK(r.size() == 2 && std::stod(r.at("salary")) > 80000, "projection + filter");
 }
 
+// round 2: prepared plan, bulk encode, window slides through the C++ mirror
+static void prepared_plan_bulk_load_and_slides() {
+    SparqlDatabase db(g_dev);
+    // bulk load = one device encode of all terms; must equal the per-term loop
+    SparqlDatabase seq(g_dev);
+    std::vector<std::string> terms;
+    for (int e = 0; e < 500; e++) {
+        const std::string s = "http://example.org/employee" + std::to_string(e);
+        const std::string sal = std::to_string(60000 + (e * 7919) % 50000);
+        const char* title = e % 3 ? "Developer" : "Manager";
+        for (auto& t : {std::array<std::string, 3>{s, "foaf:name", s}, {s, "foaf:title", title}, {s, "ds:annual_salary", sal}}) {
+            terms.insert(terms.end(), t.begin(), t.end());
+            seq.add_triple_parts(t[0], t[1], t[2]);
+        }
+    }
+    db.add_triples_bulk(terms);
+    CHECK(db.dictionary.id_to_string == seq.dictionary.id_to_string, "bulk encode == sequential encode (dictionary)");
+    CHECK(db.triples == seq.triples, "bulk encode == sequential encode (triples)");
+    // the same star + FILTER through a prepared plan (asynchronous submit / collect) and through the synchronous operator
+    auto K = [&](const char* s) { return C(db.dictionary.encode(s)); };
+    std::vector<TriplePattern> pats = {{V("?employee"), K("foaf:title"), V("?t")}, {V("?employee"), K("ds:annual_salary"), V("?salary")},
+                                       {V("?employee"), K("foaf:name"), V("?n")}};
+    Condition cond{FilterExpression::Cmp("?salary", ">", "90000")};
+    auto rows = ExecutionEngine::execute_with_ids(PhysicalOperator::FilterOf(PhysicalOperator::Star("?employee", pats), cond), db);
+    size_t want = 0;
+    for (int e = 0; e < 500; e++) want += (60000 + (e * 7919) % 50000) > 90000;
+    CHECK(rows.size() == want, "synchronous star join rows");
+    PreparedStarJoin plan(db, "?employee", pats, &cond, 4);
+    uint64_t t[3] = {plan.submit(), plan.submit(), plan.submit()};
+    for (uint64_t tk : t) CHECK(plan.collect(tk) == want, "prepared plan rows");
+    // window slides: index built once, maintained by append / evict
+    WindowStore w(g_dev);
+    g_dev->check(kb_store_clear(g_dev->get()));
+    const uint32_t P1 = 7, P2 = 8;
+    auto slide = [&](uint32_t first, uint32_t n) {
+        std::vector<Triple> v;
+        for (uint32_t i = 0; i < n; i++) { v.push_back(Triple{1000 + first + i, P1, 50}); v.push_back(Triple{1000 + first + i, P2, 60 + i % 5}); }
+        return v;
+    };
+    w.append_slide(1, slide(0, 300));
+    w.build_index();
+    std::vector<kb_pattern> ps = {kb_pattern{{1, 0}, {0, P1}, {1, 1}}, kb_pattern{{1, 0}, {0, P2}, {1, 2}}};
+    CHECK(w.star_join_rows(0, ps) == 300, "first slide");
+    w.append_slide(2, slide(300, 200));
+    CHECK(w.star_join_rows(0, ps) == 500, "two slides");
+    w.evict_slide(1);
+    CHECK(w.star_join_rows(0, ps) == 200, "after evicting the first slide");
+    kb_stats st{};
+    g_dev->check(kb_get_stats(g_dev->get(), &st, 0));
+    CHECK(st.index_joins >= 3, "the slides stayed on the index path");
+}
+
 int main() {
     try {
         g_dev = std::make_shared<Device>(0);
         fc_1hop_base(); fc_3hop_transitive(); fc_sibling_three_children(); fc_three_premise_rule(); fc_multi_conclusion_and_cascade();
         fc_diamond_and_disconnected(); fc_no_matching_and_idempotent(); fc_uncle_derived(); executor_employee4();
+        prepared_plan_bulk_load_and_slides();
     } catch (const GpuError& e) {
         std::fprintf(stderr, "GpuError %d: %s\n", e.status, e.what());
         return 100;

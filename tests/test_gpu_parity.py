@@ -600,3 +600,27 @@ def test_index_lookups_replace_scans(ctx):
     got = ctx.bgp_execute(bgp)
     want = db.bgp(bgp)
     H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), "path BGP")
+
+
+def test_join_heavy_hitters_spread_over_the_grid(ctx):
+    """1:N join whose fan-out is concentrated on a few probe rows (the transitive rule's join on the ancestor column, join_algorithm.rs:
+    499-677 over a class tree): tiles whose expansion exceeds 32 768 rows are recorded and expanded by a second launch in pieces
+    (probe_grouped_kernel<HEAVY>); same bag as the oracle, heavy keys adjacent, scattered, and mixed with ordinary rows"""
+    rng = np.random.default_rng(23)
+    n_build = 300_000
+    bkey = rng.integers(100, 4000, n_build).astype(np.uint32)
+    bkey[:120_000] = 7            # one key carried by 120 000 build rows
+    bkey[120_000:170_000] = 9     # another by 50 000
+    rng.shuffle(bkey)
+    bpay = np.arange(n_build, dtype=np.uint32)
+    for label, pkey in (("adjacent heavy rows", np.concatenate([np.full(20, 7), np.full(10, 9), rng.integers(100, 4000, 5000)])),
+                        ("scattered heavy rows", rng.permutation(np.concatenate([np.full(12, 7), np.full(25, 9), rng.integers(0, 4000, 40000)]))),
+                        ("one heavy row", np.concatenate([rng.integers(100, 4000, 2000), [7], rng.integers(100, 4000, 2000)]))):
+        pkey = pkey.astype(np.uint32)
+        ppay = np.arange(len(pkey), dtype=np.uint32) + 1_000_000
+        gl, ol = ctx.rel_from_host([0, 1], [ppay, pkey]), O.rel_from_host([0, 1], [ppay, pkey])
+        gr, orr = ctx.rel_from_host([1, 2], [bkey, bpay]), O.rel_from_host([1, 2], [bkey, bpay])
+        got = ctx.hash_join(gl, gr)
+        want = O.hash_join(ol, orr)
+        assert got.n_rows == want.n_rows and got.n_rows > 200_000, label
+        H.assert_same_bag(got.to_numpy(sorted(got.slots)), want.to_numpy(sorted(want.slots)), label)
