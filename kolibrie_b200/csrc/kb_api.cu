@@ -568,6 +568,11 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
     u64 index_base = 0;
     u32 n_launched = 0;
     u32 g = 0;
+    // tables that still have to be set to 0xFF: by the first launch itself when it is the star-shape kernel, else by memsets here
+    std::vector<std::pair<u32*, u32>> pending_clear;
+    if (tables) for (auto& tb : *tables) if (tb.tab && tb.clear) pending_clear.push_back({tb.tab, tb.range});
+    u32 off_clear = 0;
+    bool clear_folded = false;
     while (g < n_seg) {
         P.n_seg = 0;
         P.n_tiles = 0;
@@ -597,14 +602,31 @@ kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 K, const std::vecto
         n_launched++;
         P.epoch = ctx->epoch++;
         if (ctx->epoch >= (1ull << 30)) ctx->epoch = 1;
+        P.n_clear = 0;
+        if (!pending_clear.empty()) {
+            if (pending_clear.size() <= 4 && scan_clears_tables(P)) {
+                off_clear = ctrl_alloc(ctx, 4);
+                KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + off_clear, 0, 4 * sizeof(u32), ctx->st));
+                for (auto& pc : pending_clear) { P.clear_tab[P.n_clear] = pc.first; P.clear_words[P.n_clear] = pc.second; P.n_clear++; }
+                P.clear_barrier = ctx->ctrl + off_clear;
+                clear_folded = true;
+            } else {
+                timer_begin(ctx, F_BUILD, 0);
+                for (auto& pc : pending_clear) KB_CUDA(ctx, cudaMemsetAsync(pc.first, 0xFF, (size_t)pc.second * sizeof(u32), ctx->st));
+                timer_end(ctx);
+            }
+            pending_clear.clear();
+        }
         if (wait_ev) KB_CUDA(ctx, cudaStreamWaitEvent(ctx->st, wait_ev, 0));  // chunked upload: start as soon as this chunk landed
         timer_begin(ctx, F_SCAN);
         launch_scan(P, ctx->n_sms, ctx->st);
         timer_end(ctx);
     }
+    for (auto& pc : pending_clear) KB_CUDA(ctx, cudaMemsetAsync(pc.first, 0xFF, (size_t)pc.second * sizeof(u32), ctx->st));  // (nothing was launched)
     KB_CUDA(ctx, cudaGetLastError());
     ctx->stats.rows_scanned += N;
     KB_TRY(ctrl_read(ctx));
+    if (clear_folded && ctx->h_ctrl[off_clear + 1]) return fail(ctx, KB_E_CUDA, "scan: the grid did not meet at the table-clear barrier (another kernel holds SMs?)");
     for (u32 k = 0; k < K; k++) (*out)[k]->n = ctx->h_ctrl[off_tot + (ctx->ordered ? (n_launched & 1u) * MAXP : 0u) + k];
     return KB_OK;
 }
@@ -1405,9 +1427,9 @@ kb_status star_join_impl2(kb_ctx* ctx, u32 join_slot, const kb_pattern* pats, u3
                 if ((int)k == probe_k) continue;
                 Buf b;
                 KB_TRY(alloc_buf(ctx, (size_t)range * sizeof(u32), &b));
-                KB_CUDA(ctx, cudaMemsetAsync(b->p, 0xFF, (size_t)range * sizeof(u32), ctx->st));
                 tabs.push_back(b);
                 st[k].tab = static_cast<u32*>(b->p);
+                st[k].clear = true;  // cleared by the scan (scan_impl)
                 st[k].kmin = kmn; st[k].range = range; st[k].cshift = cshift;
                 st[k].key_is_o = key_pos(k) == 2 ? 1u : 0u;
                 st[k].trusted = (!pats[k].p.is_var && ctx->single_valued.count({pats[k].p.value, key_pos(k)})) ? 1u : 0u;

@@ -271,6 +271,7 @@ struct ScanTable {  // scan+build fusion: pattern k inserts its matches into thi
     u32 cshift = 0;
     u32 key_is_o = 0, trusted = 0;
     u32* dup_flag = nullptr;
+    bool clear = false;  // the table has not been set to 0xFF yet: scan_impl clears it (inside the scan kernel when it can)
 };
 kb_status scan_impl(kb_ctx* ctx, const kb_pattern* pats, u32 n_pats, const std::vector<FilterProg>& pushdown, bool want_index, bool pairs,
                     std::vector<std::unique_ptr<kb_rel>>* out, const std::vector<ScanTable>* tables = nullptr);

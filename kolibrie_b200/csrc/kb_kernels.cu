@@ -294,6 +294,28 @@ __global__ void __launch_bounds__(STAR_THREADS, 1024 / STAR_THREADS) scan_star_k
         issue_next(0);
         issue_next(1);
     }
+    if (P.n_clear) {
+        // the tables this scan inserts into are cleared by the grid itself while the first tiles are in flight, then every CTA waits
+        // until all have finished (the grid is sized to residency, so all of them are running)
+        const uint4 ones = make_uint4(EMPTY32, EMPTY32, EMPTY32, EMPTY32);
+        for (u32 t = 0; t < P.n_clear; t++) {
+            uint4* t4 = reinterpret_cast<uint4*>(P.clear_tab[t]);
+            const u32 n4 = P.clear_words[t] >> 2;
+            for (u32 i = blockIdx.x * STAR_THREADS + (u32)tid; i < n4; i += gridDim.x * STAR_THREADS) t4[i] = ones;
+            if (blockIdx.x == 0) for (u32 i = (n4 << 2) + (u32)tid; i < P.clear_words[t]; i += STAR_THREADS) P.clear_tab[t][i] = EMPTY32;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(P.clear_barrier, 1u);
+            u32 spins = 0;
+            while (*reinterpret_cast<volatile u32*>(P.clear_barrier) < gridDim.x) {
+                __nanosleep(100);
+                if (++spins > (1u << 24)) { P.clear_barrier[1] = 1u; break; }  // ~2 s: reported by the host as an error
+            }
+            __threadfence();
+        }
+    }
     __syncthreads();
     u32 tile = s_nexts[0];
     u32 it = 0;
@@ -484,10 +506,17 @@ static void launch_scan_k(const ScanParams& p, int n_sms, cudaStream_t st) {
     const int grid = grid_for((const void*)scan_kernel<K>, SCAN_THREADS, smem, n_sms, p.n_tiles);
     scan_kernel<K><<<grid, SCAN_THREADS, smem, st>>>(p);
 }
+static bool scan_star_enabled() {
+    static const bool star_off = getenv("KOLIBRIE_SCAN_STAR") && getenv("KOLIBRIE_SCAN_STAR")[0] == '0';  // A/B switch
+    return !star_off;
+}
+bool scan_clears_tables(const ScanParams& p) {
+    static const bool fold_off = getenv("KOLIBRIE_SCAN_CLEAR_FOLD") && getenv("KOLIBRIE_SCAN_CLEAR_FOLD")[0] == '0';  // A/B switch
+    return !fold_off && p.n_tiles != 0 && scan_star_enabled() && scan_is_star(p);
+}
 void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st) {
     if (p.n_tiles == 0) return;
-    static const bool star_off = getenv("KOLIBRIE_SCAN_STAR") && getenv("KOLIBRIE_SCAN_STAR")[0] == '0';  // A/B switch
-    if (!star_off && scan_is_star(p)) {
+    if (scan_star_enabled() && scan_is_star(p)) {
         switch (p.K) {
             case 1: launch_scan_star_k<1>(p, n_sms, st); return;
             case 2: launch_scan_star_k<2>(p, n_sms, st); return;

@@ -48,6 +48,13 @@ struct ScanParams {
     ScanPat pat[MAXP];
     FilterOp ops[KB_MAX_FILTER_OPS];
     NumTab nt;
+    // direct tables the FIRST launch of a scan clears itself (scan_star_kernel: every CTA fills a slice with 0xFF, then the grid meets
+    // at clear_barrier[0] before any insert; clear_barrier[1] is raised when the meeting timed out) — two 67 MB cudaMemsetAsync calls
+    // in front of a 0.32 ms kernel cost 45 us + two launch gaps, the same bytes written by the resident grid ~25 us
+    u32* clear_tab[4];
+    u32 clear_words[4];
+    u32 n_clear;
+    u32* clear_barrier;
     u64* tile_state;   // level 1: [n_tiles][MAXP]
     u64* block_state;  // level 2: [ceil(n_tiles/32)][MAXP]
     u32 ordered;       // 1: output in store order (two-level prefix)  0: tile completion order (atomic cursor)
@@ -57,6 +64,7 @@ struct ScanParams {
     u32* totals_out;       // [MAXP] rows written so far (ordered: a different array than totals_in; unordered: the same, used as atomic cursor)
 };
 void launch_scan(const ScanParams& p, int n_sms, cudaStream_t st);
+bool scan_clears_tables(const ScanParams& p);  // true when launch_scan(p) runs the kernel that honours clear_tab / n_clear
 
 // ---------------------------------------------------------------------------------------------------------------
 // K_build
