@@ -60,3 +60,44 @@ def test_employee_shard_closed_form_tail():
         keep = shard_of(full.s, 2) == r
         assert np.array_equal(part.s, full.s[keep]) and np.array_equal(part.p, full.p[keep]) and np.array_equal(part.o, full.o[keep])
     assert sum(p.n_employees for p in parts) == E
+
+
+def test_closed_form_helpers_agree_with_the_sequential_dataset():
+    """the closed forms bench.py asserts its multi-GPU legs against (subject id / title id of a global employee number, the employees
+    of a shard, the reports_to companion relation) against the sequentially generated dataset"""
+    E = 2_300_000
+    full = datagen.employee_dataset(E)
+    title_p = full.ids["foaf:title"]
+    subj_of = full.s[full.p == title_p]      # subject of employee k, in generation order
+    title_of = full.o[full.p == title_p]
+    for world in (1, 2, 4):
+        seen = []
+        for r in range(world):
+            part = datagen.employee_shard(E, r, world, prefix=2_000_000)
+            idx = datagen.employee_indices_of_shard(part, r, world)
+            seen.append(idx)
+            assert np.array_equal(datagen.employee_subject_ids(part, idx), subj_of[idx])
+            assert np.array_equal(datagen.employee_title_ids(part, idx), title_of[idx])
+            assert np.array_equal(np.unique(part.s), np.sort(subj_of[idx]))            # exactly the shard's employees
+            e, m, t = datagen.reports_to_relation(part, r, world)
+            assert np.array_equal(e, subj_of[idx]) and len(m) == len(e)
+            pos = {int(s): k for k, s in enumerate(subj_of[:50_000])}                  # spot check: m's title from the full dataset
+            for k in np.nonzero(np.isin(m, subj_of[:50_000]))[0][:200]:
+                assert int(title_of[pos[int(m[k])]]) == int(t[k])
+        assert np.array_equal(np.sort(np.concatenate(seen)), np.arange(E))
+
+
+def test_permuted_and_multivalued_datasets():
+    d = datagen.employee_dataset(3000)
+    s, p, o, num, isn, pi = datagen.permuted_dataset(d)
+    assert sorted(pi.tolist()) == list(range(d.n_ids))                                 # a permutation of all ids
+    inv = np.empty_like(pi); inv[pi] = np.arange(d.n_ids, dtype=np.uint32)
+    back = datagen.canonical_rows(np.stack([inv[s], inv[p], inv[o]], axis=1))
+    assert np.array_equal(back, datagen.canonical_rows(np.stack([d.s, d.p, d.o], axis=1)))  # same triples, relabelled and shuffled
+    assert np.array_equal(num[pi], d.num_or0) and np.array_equal(isn[pi], d.is_num)
+    s, p, o, num, isn, meta = datagen.multivalued_dataset(5000, per_subject=3)
+    tag = p == 1
+    assert tag.sum() == 15000 and (p == 2).sum() == 5000 and (p == 3).sum() == 5000
+    pairs = np.unique(np.stack([s[tag], o[tag]], axis=1), axis=0)
+    assert len(pairs) == 15000                                                          # three DISTINCT tags per subject
+    assert np.array_equal(num[o[p == 2]], meta["score"].astype(np.float64)) and isn[o[p == 2]].all()
