@@ -91,10 +91,10 @@ kb_status grow_rel(kb_ctx* ctx, PredRel& r, u64 need) {
 // `extra` counts candidates, most of which are usually known already (cfg4: 1.25e9 candidates for 2.9e8 new facts), so the
 // expectation is capped at half the set's size (and at least 2^20 facts); derive_kernel enforces the real bound (budget) and the launch is repeated on a
 // larger table when the cap was too optimistic. A rebuild re-inserts every known fact, so every (re)build allocates twice the need.
-kb_status ensure_set(Fix& fx, PredRel& r, u64 extra, bool must_grow = false) {
+kb_status ensure_set(Fix& fx, PredRel& r, u64 extra, bool must_grow = false, bool exact_expectation = false) {
     kb_ctx* ctx = fx.ctx;
-    const u64 expect = std::min<u64>(extra, std::max<u64>(r.set_count / 2, 1u << 20));
-    const u64 need = (r.set_count + expect) * 2;
+    const u64 expect = exact_expectation ? extra : std::min<u64>(extra, std::max<u64>(r.set_count / 2, 1u << 20));
+    const u64 need = exact_expectation ? r.set_count + expect : (r.set_count + expect) * 2;  // (a known final size: load <= 1/2 is enough)
     if (r.set && need <= r.set_slots && !must_grow) return KB_OK;
     static const u64 slack = getenv("KOLIBRIE_SET_SLACK") ? std::max(1, atoi(getenv("KOLIBRIE_SET_SLACK"))) : 2;
     u64 slots = 1024;
@@ -273,7 +273,12 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     tr.mark(ctx, "split store by predicate");
     for (auto& kv : fx.rels) if (kv.second.is_head) {
         kv.second.set_count = kv.second.n;
-        KB_TRY(ensure_set(fx, kv.second, 1024));
+        // A window that re-materialises the same rules every firing (simple_r2r.rs:103-128) ends with about as many facts as last time:
+        // the set is built for that size at once (config 4: the 2^28 -> 2^30 rebuild in the middle of round 0 cost 6.7 ms of 64)
+        u64 expect = 1024;
+        auto hint = ctx->fix_hint.find(kv.first);
+        if (hint != ctx->fix_hint.end() && hint->second > kv.second.n) expect = std::min<u64>(hint->second - kv.second.n, 0x7FFFFFFFull);
+        KB_TRY(ensure_set(fx, kv.second, expect, false, /*exact_expectation=*/expect > 1024));
     }
     tr.mark(ctx, "initial known-fact sets");
 
@@ -479,6 +484,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
         off += cnt;
     }
     res->cols = {cs, cp, co};
+    for (auto& kv : fx.rels) if (kv.second.is_head) ctx->fix_hint[kv.first] = kv.second.n;
     if (st.inferred) {
         Segment sg;
         sg.tag = KB_TAG_INFERRED;
