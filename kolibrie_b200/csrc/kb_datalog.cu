@@ -97,8 +97,10 @@ kb_status ensure_set(Fix& fx, PredRel& r, u64 extra, bool must_grow = false, boo
     const u64 need = exact_expectation ? r.set_count + expect : (r.set_count + expect) * 2;  // (a known final size: load <= 1/2 is enough)
     if (r.set && need <= r.set_slots && !must_grow) return KB_OK;
     static const u64 slack = getenv("KOLIBRIE_SET_SLACK") ? std::max(1, atoi(getenv("KOLIBRIE_SET_SLACK"))) : 2;
+    static const u64 tight = getenv("KOLIBRIE_SET_TIGHT") ? (u64)atoi(getenv("KOLIBRIE_SET_TIGHT")) : 0;  // experiment: known final size at load <= 2/3
     u64 slots = 1024;
-    while (slots < need * slack) slots <<= 1;
+    if (exact_expectation && tight) { while (slots * 2 < need * 3) slots <<= 1; }
+    else while (slots < need * slack) slots <<= 1;
     if (must_grow) slots = std::max<u64>(slots, (u64)r.set_slots * 2);
     if (slots > (1ull << 31)) slots = 1ull << 31;
     if (slots < need || (must_grow && r.set && slots <= r.set_slots))
