@@ -2843,7 +2843,7 @@ __global__ void __launch_bounds__(DPART_THREADS) derive_partition_kernel(const _
         const u32 cnt = min((u32)DPART_TILE, P.n - row0);
         // ---- 1. head instantiation + rule filters; partition = high bits of the key's home slot; histogram
         u64 key[DPART_ITEMS];
-        u32 part[DPART_ITEMS];
+        u32 part[DPART_ITEMS], rank[DPART_ITEMS];
 #pragma unroll
         for (int j = 0; j < DPART_ITEMS; j++) {
             const u32 r = (u32)j * DPART_THREADS + (u32)tid;
@@ -2857,7 +2857,7 @@ __global__ void __launch_bounds__(DPART_THREADS) derive_partition_kernel(const _
             }
             key[j] = ((u64)s << 32) | (u64)o;
             part[j] = pass ? (set64_home(P.set_slots, s, o) >> Q.slice_bits) : 0xFFFFu;
-            if (pass) atomicAdd(&s_cnt[part[j]], 1u);
+            rank[j] = pass ? atomicAdd(&s_cnt[part[j]], 1u) : 0u;  // the key's place among the tile's keys of its partition (kept for step 3)
         }
         __syncthreads();
         // ---- 2. offsets inside the tile (one warp scans the histogram), one range reservation per partition
@@ -2875,7 +2875,6 @@ __global__ void __launch_bounds__(DPART_THREADS) derive_partition_kernel(const _
                 if (d < Q.n_parts) {
                     s_off[d] = run + incl - c;
                     s_gbase[d] = c ? atomicAdd(&Q.cursors[d], c) : 0u;
-                    s_cnt[d] = 0u;  // becomes the fill cursor of step 3
                 }
                 run += __shfl_sync(0xffffffffu, incl, 31);
             }
@@ -2885,7 +2884,7 @@ __global__ void __launch_bounds__(DPART_THREADS) derive_partition_kernel(const _
 #pragma unroll
         for (int j = 0; j < DPART_ITEMS; j++) {
             if (part[j] == 0xFFFFu) continue;
-            const u32 pos = s_off[part[j]] + atomicAdd(&s_cnt[part[j]], 1u);
+            const u32 pos = s_off[part[j]] + rank[j];
             sh_keys[pos] = key[j];
             s_dest[pos] = (unsigned short)part[j];
         }
