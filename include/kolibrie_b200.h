@@ -321,6 +321,16 @@ KB_API kb_status kb_plan_attach_peers(kb_ctx* ctx, kb_plan* plan, uint32_t rank,
 #define KB_TAG_INFERRED 0xFFFFFFFFFFFFFFF0ull
 KB_API kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy,
                                      kb_rel** inferred, kb_fixpoint_stats* stats);
+/* Incremental materialisation. The store is closed under `rules` already (an earlier kb_datalog_fixpoint[_seed] with the same rules, and
+ * nothing deleted since); `seed` (3 columns, slots 0,1,2 = s,p,o; not yet in the store) are facts to ADD. The seed facts the store does
+ * not hold yet are accepted and become the first delta; everything the store held is OLD, so the rounds join the delta alone against
+ * the store instead of the store against itself — the closure Reasoner::add_abox_triple + infer_new_facts_semi_naive reach by
+ * starting over (semi_naive.rs:89; per window slide: simple_r2r.rs:95-128). `*out` = the *n_seed_new accepted seed facts, then the
+ * facts inferred from them (stats->inferred); both are appended to the store (tag KB_TAG_INFERRED). Duplicates inside the seed are
+ * accepted once. Seed facts whose predicate no rule mentions are not looked at (load them with kb_store_append). The sharded
+ * fixpoint (kolibrie_b200/dist.py) feeds the facts derived on other ranks through this call. */
+KB_API kb_status kb_datalog_fixpoint_seed(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy, const kb_rel* seed,
+                                          kb_rel** out, uint64_t* n_seed_new, kb_fixpoint_stats* stats);
 
 /* ------------------------------------------------------------------ multi-GPU helpers (one process per GPU; the host layer
  * runs the NCCL all-to-all between kb_partition and kb_rel_from_device) */

@@ -199,6 +199,7 @@ def lib() -> C.CDLL:
         "kb_plan_attach_peers": (i32, [vp, vp, u32, u32, P(vp)]),
         "kb_star_join_aggregate": (i32, [vp, u32, P(KbPattern), u32, P(KbFilterOp), u32, P(u32), u32, P(KbAgg), u32, P(vp), P(u64)]),
         "kb_datalog_fixpoint": (i32, [vp, P(KbRule), u32, u32, P(vp), P(KbFixpointStats)]),
+        "kb_datalog_fixpoint_seed": (i32, [vp, P(KbRule), u32, u32, vp, P(vp), P(u64), P(KbFixpointStats)]),
         "kb_shard_of": (u32, [u32, u32]),
         "kb_set_sharding": (i32, [vp, u32, u32]),
         "kb_partition": (i32, [vp, vp, u32, u32, P(vp), P(u64)]),
@@ -229,7 +230,7 @@ EXPORTED_SYMBOLS = [
     "kb_rel_from_device", "kb_rel_free", "kb_scan", "kb_filter", "kb_project", "kb_hash_join", "kb_bind_join", "kb_star_join", "kb_bgp_execute",
     "kb_group_aggregate", "kb_groups_info", "kb_groups_keys", "kb_groups_values", "kb_groups_counts", "kb_groups_free", "kb_groups_pack", "kb_groups_merge", "kb_star_join_aggregate",
     "kb_star_join_prepare", "kb_plan_submit", "kb_plan_collect", "kb_plan_info", "kb_plan_free", "kb_plan_peer_scratch_bytes", "kb_plan_attach_peers",
-    "kb_datalog_fixpoint", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_segment_write", "kb_segment_info", "kb_segment_save", "kb_store_append_file", "kb_shuffle_scatter", "kb_shuffle_push", "kb_rel_wrap_device", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
+    "kb_datalog_fixpoint", "kb_datalog_fixpoint_seed", "kb_shard_of", "kb_set_sharding", "kb_partition", "kb_partition_counts", "kb_segment_write", "kb_segment_info", "kb_segment_save", "kb_store_append_file", "kb_shuffle_scatter", "kb_shuffle_push", "kb_rel_wrap_device", "kb_star_join_host", "kb_star_join_host_into", "perform_hash_join_cuda",
 ]
 
 
@@ -614,6 +615,16 @@ class Context:
         st = KbFixpointStats()
         self._check(lib().kb_datalog_fixpoint(self.h, arr, len(rules), strategy, C.byref(out), C.byref(st)))
         return Relation(self, out), st
+
+    def datalog_fixpoint_seed(self, rules: Sequence[dict], seed: Relation, strategy: int = SEMI_NAIVE):
+        """kb_datalog_fixpoint_seed: the store is closed under `rules` already; `seed` (slots 0,1,2 = s,p,o) are facts to add. Returns
+        (relation = the accepted seed facts followed by the facts inferred from them, number of accepted seed facts, stats)."""
+        arr, keep = make_rules(rules)
+        out = C.c_void_p()
+        n_new = C.c_uint64()
+        st = KbFixpointStats()
+        self._check(lib().kb_datalog_fixpoint_seed(self.h, arr, len(rules), strategy, seed.h, C.byref(out), C.byref(n_new), C.byref(st)))
+        return Relation(self, out), int(n_new.value), st
 
     def partition(self, rel: Relation, key_slot: int, n_parts: int):
         out = C.c_void_p()

@@ -24,7 +24,8 @@ struct PredRel {
     u32 pred = 0;
     Col s, o;
     u64 n = 0, cap = 0;
-    u64 base_n = 0;       // facts present before inference
+    u64 base_n = 0;       // facts present before inference (with a seed: after the seed's new facts were accepted)
+    u64 seed_from = 0;    // kb_datalog_fixpoint_seed: rows [seed_from, base_n) are the seed facts that were new
     u64 delta_start = 0;  // facts [delta_start, snapshot) were added by the previous round
     u64 snapshot = 0;
     bool is_head = false;
@@ -166,8 +167,10 @@ kb_status enforce_constants(kb_ctx* ctx, const Premise& pr, std::unique_ptr<kb_r
 
 }  // namespace
 
-extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy, kb_rel** inferred,
-                                         kb_fixpoint_stats* stats) {
+// `seed` == nullptr: kb_datalog_fixpoint (every fact of the store is the first delta). With a seed (kb_datalog_fixpoint_seed): the store
+// is taken as closed under the rules already, the seed facts the store does not hold yet are accepted into it and form the first delta.
+static kb_status fixpoint_impl(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy, bool seeded, const kb_rel* seed,
+                               kb_rel** inferred, uint64_t* n_seed_new, kb_fixpoint_stats* stats) {
     if (!ctx) return KB_E_INVALID;
     int prev_dev = -1;
     cudaGetDevice(&prev_dev);
@@ -177,6 +180,10 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     if ((n_rules && !rules) || !inferred) return fail(ctx, KB_E_INVALID, "NULL argument");
     if (strategy != KB_SEMI_NAIVE && strategy != KB_NAIVE && strategy != KB_SEMI_NAIVE_PARALLEL && strategy != KB_SEMI_NAIVE_OLD_DELTA)
         return fail(ctx, KB_E_INVALID, "unknown strategy %u", strategy);
+    if (seeded && !seed) return fail(ctx, KB_E_INVALID, "NULL seed");
+    if (seed && (seed->pair || seed->cols.size() != 3 || seed->col_of(0) != 0 || seed->col_of(1) != 1 || seed->col_of(2) != 2))
+        return fail(ctx, KB_E_INVALID, "the seed must be a 3-column relation with slots 0,1,2 = s,p,o");
+    if (seed && seed->n >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "seed too large");
     const bool old_delta = strategy == KB_SEMI_NAIVE_OLD_DELTA;
     const bool strict = strategy == KB_SEMI_NAIVE_PARALLEL;
     kb_fixpoint_stats st{};
@@ -234,6 +241,8 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
             if (rule.filters[f].cmp > KB_CMP_NE) return fail(ctx, KB_E_INVALID, "rule %u filter %u: bad comparison", r, f);
         }
     }
+    // a seed fact may belong to any predicate of the rules: each of them needs its known-fact set (to tell the new seed facts from the old)
+    if (seed) for (auto& kv : fx.rels) kv.second.is_head = true;
 
     // ---- split the store by predicate: one fused scan per 8 predicates
     {
@@ -284,6 +293,162 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     }
     tr.mark(ctx, "initial known-fact sets");
 
+    // ---- one head of one rule over the joined bindings `cur`: filters + instantiate + dedup against the known facts + append to the
+    // round's pending facts (`rule_p` == nullptr: no rule filters — the seed facts of kb_datalog_fixpoint_seed take the same way in)
+    auto derive_head = [&](const kb_rel* cur, const kb_pattern& h, const kb_rule* rule_p) -> kb_status {
+        DeriveParams D{};
+        for (size_t k = 0; k < cur->cols.size(); k++) D.bcol[k] = cur->cols[k].ptr;
+        D.n = (u32)cur->n;
+        auto term = [&](const kb_term& t) {
+            HeadTerm ht;
+            ht.is_var = t.is_var;
+            ht.value = t.is_var ? (u32)cur->col_of(t.value) : t.value;
+            return ht;
+        };
+        D.head_s = term(h.s);
+        D.head_o = term(h.o);
+        D.n_filt = 0;
+        for (u32 f = 0; f < (strict || !rule_p ? 0u : rule_p->n_filters); f++) {  // the parallel variant never evaluates the rule filters
+            const kb_rule_filter& rf = rule_p->filters[f];
+            const int lc = cur->col_of(rf.lhs_slot);
+            if (lc < 0 || rf.cmp == 0) continue;  // unbound lhs: the reference skips the filter (rules.rs:139)
+            RuleFilterDev d;
+            d.lhs_col = (u32)lc;
+            d.cmp = rf.cmp;
+            d.rhs_value = rf.rhs_value;
+            d.rhs_is_var = 0; d.rhs_col = 0;
+            if (rf.rhs_is_var) {
+                const int rc = cur->col_of(rf.rhs_slot);
+                if (rc >= 0) { d.rhs_is_var = 1; d.rhs_col = (u32)rc; }
+                // rhs names an unbound variable: the reference falls to the numeric branch with value.parse() (rules.rs:148-151)
+            }
+            D.filt[D.n_filt++] = d;
+        }
+        D.nt = numtab(ctx);
+        PredRel& hr = fx.rels[h.p.value];
+        KB_TRY(ensure_set(fx, hr, cur->n));
+        tr.mark(ctx, "  ensure_set", hr.set_slots);
+        Pending pd;
+        pd.pred = h.p.value;
+        pd.count = 0;
+        KB_TRY(alloc_col(ctx, cur->n, &pd.s));
+        KB_TRY(alloc_col(ctx, cur->n, &pd.o));
+        const u32 coff = ctrl_alloc(ctx, 8);
+        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff, 0, 8 * sizeof(u32), ctx->st));
+        D.out_s = pd.s.ptr; D.out_o = pd.o.ptr;
+        D.out_cap = (u32)cur->n;
+        D.out_count = ctx->ctrl + coff;
+        D.overflow = ctx->ctrl + coff + 1;
+        D.n_deriv = reinterpret_cast<unsigned long long*>(ctx->ctrl + coff + 4);
+        const u64 count_before = hr.set_count;
+        for (;;) {
+            D.set = static_cast<u64*>(hr.set->p);
+            D.set_slots = hr.set_slots;
+            // the set may fill up to 3/4 before it has to grow (expected: 1/2)
+            D.budget = (u32)std::min<u64>((u64)hr.set_slots / 4 * 3 - count_before, 0xFFFFFFFFull);
+            // Large candidate sets against a table far beyond L2: radix-partition the candidates by the high bits of their
+            // home slot and probe partition by partition (each slice stays L2-resident) instead of one random DRAM line per
+            // candidate. Partitions: ~32 MB slices, at least ~1 M candidates each (so that the CTAs of the probe pass sit on
+            // one or two slices at a time), at most 1024.
+            u64 n_parts = 0;
+            {
+                const u64 set_bytes = (u64)hr.set_slots * sizeof(u64);
+                u64 want = std::min<u64>(set_bytes / ctx->derive_slice_bytes, std::min<u64>(cur->n / ctx->derive_min_part_rows, 1024));
+                while (want >= 2 && n_parts * 2 <= want) n_parts = n_parts ? n_parts * 2 : 2;  // power of two
+                if (ctx->derive_part == 0) n_parts = 0;
+            }
+            if (n_parts >= 2) {
+                DerivePartParams Q{};
+                Q.d = D;
+                Q.n_parts = (u32)n_parts;
+                u32 set_bits = 0;
+                while ((1ull << set_bits) < hr.set_slots) set_bits++;
+                u32 part_bits = 0;
+                while ((1ull << part_bits) < n_parts) part_bits++;
+                Q.slice_bits = set_bits - part_bits;
+                Q.bucket_cap = (u32)std::min<u64>(cur->n / n_parts + cur->n / n_parts / 8 + ctx->derive_bucket_slack, 0xFFFFFFF0ull);
+                Buf ctl;
+                const size_t bucket_bytes = n_parts * (u64)Q.bucket_cap * sizeof(u64);
+                if (!fx.buckets || fx.buckets->bytes < bucket_bytes) {
+                    fx.buckets.reset();
+                    KB_TRY(alloc_buf(ctx, bucket_bytes + bucket_bytes / 4, &fx.buckets));
+                }
+                Buf buckets = fx.buckets;
+                KB_TRY(alloc_buf(ctx, (2 * n_parts + 8) * sizeof(u32), &ctl));
+                KB_CUDA(ctx, cudaMemsetAsync(ctl->p, 0, (2 * n_parts + 8) * sizeof(u32), ctx->st));
+                Q.buckets = static_cast<u64*>(buckets->p);
+                Q.cursors = static_cast<u32*>(ctl->p);
+                Q.tile_start = Q.cursors + n_parts;
+                Q.tickets = Q.tile_start + n_parts + 1 + ((n_parts + 1) & 1u);
+                tr.mark(ctx, "    derive: buckets allocated", n_parts);
+                timer_begin(ctx, F_OTHER, 3);
+                launch_derive_partitioned(Q, ctx->n_sms, ctx->st);
+                timer_end(ctx);
+                ctx->stats.rows_built += cur->n;  // (counted as table traffic: partitioned candidates)
+            } else {
+                timer_begin(ctx, F_OTHER);
+                launch_derive(D, ctx->n_sms, ctx->st);
+                timer_end(ctx);
+            }
+            KB_CUDA(ctx, cudaGetLastError());
+            // counts are read immediately: the control arena may be recycled by later joins of this round
+            KB_TRY(ctrl_read(ctx));
+            pd.count = ctx->h_ctrl[coff];
+            if (ctx->h_ctrl[coff + 1] == 1u) return fail(ctx, KB_E_LIMIT, "known-fact set overflow");
+            if (ctx->h_ctrl[coff + 1] == 0u) break;
+            // budget reached: rebuild the set larger WITH the facts appended so far, then repeat the launch (facts already
+            // inserted are found present and are not appended twice; the derivation count is the last, complete pass's)
+            fx.pend.push_back(pd);
+            const kb_status gs = ensure_set(fx, hr, cur->n, true);
+            fx.pend.pop_back();
+            if (gs != KB_OK) return gs;
+            KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff + 1, 0, sizeof(u32), ctx->st));
+            KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff + 4, 0, 2 * sizeof(u32), ctx->st));
+        }
+        unsigned long long nd;
+        memcpy(&nd, ctx->h_ctrl + coff + 4, sizeof nd);
+        st.derivations += nd;
+        hr.set_count = count_before;
+        hr.set_count += pd.count;
+        if (pd.count) fx.pend.push_back(pd);
+        tr.mark(ctx, "  derive", pd.count);
+        return KB_OK;
+    };
+
+    // ---- seed: its facts take the way of derived heads (dedup against the known facts); the winners become visible now and are the
+    // first delta, everything the store held is OLD
+    u64 seed_new = 0;
+    if (seed) {
+        for (auto& kv : fx.rels) kv.second.snapshot = kv.second.seed_from = kv.second.n;
+        for (auto& kv : fx.rels) {
+            if (seed->n == 0) break;
+            FilterProg f;
+            kb_filter_op op{};
+            op.op = KB_F_EQ_ID; op.slot = 1; op.id = kv.first;
+            f.ops.push_back(op);
+            std::unique_ptr<kb_rel> sub;
+            KB_TRY(filter_impl(ctx, *seed, f, &sub));
+            if (sub->n == 0) continue;
+            kb_pattern h{};
+            h.s = kb_term{1, 0}; h.p = kb_term{0, kv.first}; h.o = kb_term{1, 2};
+            KB_TRY(derive_head(sub.get(), h, nullptr));
+        }
+        for (auto& kv : fx.rels) kv.second.delta_start = kv.second.snapshot;
+        for (auto& pd : fx.pend) {
+            PredRel& r = fx.rels[pd.pred];
+            const u64 cnt = pd.count;
+            KB_TRY(grow_rel(ctx, r, r.n + cnt));
+            KB_CUDA(ctx, cudaMemcpyAsync(r.s.ptr + r.n, pd.s.ptr, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            KB_CUDA(ctx, cudaMemcpyAsync(r.o.ptr + r.n, pd.o.ptr, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            r.n += cnt;
+            seed_new += cnt;
+        }
+        fx.pend.clear();
+        for (auto& kv : fx.rels) kv.second.base_n = kv.second.n;
+        st.derivations = 0;  // (the seed's facts are not derivations)
+        tr.mark(ctx, "seed accepted", seed_new);
+    }
+
     // ---- rounds
     for (u32 round = 0;; round++) {
         for (auto& kv : fx.rels) kv.second.snapshot = kv.second.n;
@@ -326,123 +491,7 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
                 if (cur->n == 0) continue;
                 // heads: filters + instantiate + dedup against known facts + append
                 for (u32 c = 0; c < rule.n_conclusion; c++) {
-                    const kb_pattern& h = rule.conclusion[c];
-                    DeriveParams D{};
-                    for (size_t k = 0; k < cur->cols.size(); k++) D.bcol[k] = cur->cols[k].ptr;
-                    D.n = (u32)cur->n;
-                    auto term = [&](const kb_term& t) {
-                        HeadTerm ht;
-                        ht.is_var = t.is_var;
-                        ht.value = t.is_var ? (u32)cur->col_of(t.value) : t.value;
-                        return ht;
-                    };
-                    D.head_s = term(h.s);
-                    D.head_o = term(h.o);
-                    D.n_filt = 0;
-                    for (u32 f = 0; f < (strict ? 0u : rule.n_filters); f++) {  // the parallel variant never evaluates rule.filters
-                        const kb_rule_filter& rf = rule.filters[f];
-                        const int lc = cur->col_of(rf.lhs_slot);
-                        if (lc < 0 || rf.cmp == 0) continue;  // unbound lhs: the reference skips the filter (rules.rs:139)
-                        RuleFilterDev d;
-                        d.lhs_col = (u32)lc;
-                        d.cmp = rf.cmp;
-                        d.rhs_value = rf.rhs_value;
-                        d.rhs_is_var = 0; d.rhs_col = 0;
-                        if (rf.rhs_is_var) {
-                            const int rc = cur->col_of(rf.rhs_slot);
-                            if (rc >= 0) { d.rhs_is_var = 1; d.rhs_col = (u32)rc; }
-                            // rhs names an unbound variable: the reference falls to the numeric branch with value.parse() (rules.rs:148-151)
-                        }
-                        D.filt[D.n_filt++] = d;
-                    }
-                    D.nt = numtab(ctx);
-                    PredRel& hr = fx.rels[h.p.value];
-                    KB_TRY(ensure_set(fx, hr, cur->n));
-                    tr.mark(ctx, "  ensure_set", hr.set_slots);
-                    Pending pd;
-                    pd.pred = h.p.value;
-                    pd.count = 0;
-                    KB_TRY(alloc_col(ctx, cur->n, &pd.s));
-                    KB_TRY(alloc_col(ctx, cur->n, &pd.o));
-                    const u32 coff = ctrl_alloc(ctx, 8);
-                    KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff, 0, 8 * sizeof(u32), ctx->st));
-                    D.out_s = pd.s.ptr; D.out_o = pd.o.ptr;
-                    D.out_cap = (u32)cur->n;
-                    D.out_count = ctx->ctrl + coff;
-                    D.overflow = ctx->ctrl + coff + 1;
-                    D.n_deriv = reinterpret_cast<unsigned long long*>(ctx->ctrl + coff + 4);
-                    const u64 count_before = hr.set_count;
-                    for (;;) {
-                        D.set = static_cast<u64*>(hr.set->p);
-                        D.set_slots = hr.set_slots;
-                        // the set may fill up to 3/4 before it has to grow (expected: 1/2)
-                        D.budget = (u32)std::min<u64>((u64)hr.set_slots / 4 * 3 - count_before, 0xFFFFFFFFull);
-                        // Large candidate sets against a table far beyond L2: radix-partition the candidates by the high bits of their
-                        // home slot and probe partition by partition (each slice stays L2-resident) instead of one random DRAM line per
-                        // candidate. Partitions: ~32 MB slices, at least ~1 M candidates each (so that the CTAs of the probe pass sit on
-                        // one or two slices at a time), at most 1024.
-                        u64 n_parts = 0;
-                        {
-                            const u64 set_bytes = (u64)hr.set_slots * sizeof(u64);
-                            u64 want = std::min<u64>(set_bytes / ctx->derive_slice_bytes, std::min<u64>(cur->n / ctx->derive_min_part_rows, 1024));
-                            while (want >= 2 && n_parts * 2 <= want) n_parts = n_parts ? n_parts * 2 : 2;  // power of two
-                            if (ctx->derive_part == 0) n_parts = 0;
-                        }
-                        if (n_parts >= 2) {
-                            DerivePartParams Q{};
-                            Q.d = D;
-                            Q.n_parts = (u32)n_parts;
-                            u32 set_bits = 0;
-                            while ((1ull << set_bits) < hr.set_slots) set_bits++;
-                            u32 part_bits = 0;
-                            while ((1ull << part_bits) < n_parts) part_bits++;
-                            Q.slice_bits = set_bits - part_bits;
-                            Q.bucket_cap = (u32)std::min<u64>(cur->n / n_parts + cur->n / n_parts / 8 + ctx->derive_bucket_slack, 0xFFFFFFF0ull);
-                            Buf ctl;
-                            const size_t bucket_bytes = n_parts * (u64)Q.bucket_cap * sizeof(u64);
-                            if (!fx.buckets || fx.buckets->bytes < bucket_bytes) {
-                                fx.buckets.reset();
-                                KB_TRY(alloc_buf(ctx, bucket_bytes + bucket_bytes / 4, &fx.buckets));
-                            }
-                            Buf buckets = fx.buckets;
-                            KB_TRY(alloc_buf(ctx, (2 * n_parts + 8) * sizeof(u32), &ctl));
-                            KB_CUDA(ctx, cudaMemsetAsync(ctl->p, 0, (2 * n_parts + 8) * sizeof(u32), ctx->st));
-                            Q.buckets = static_cast<u64*>(buckets->p);
-                            Q.cursors = static_cast<u32*>(ctl->p);
-                            Q.tile_start = Q.cursors + n_parts;
-                            Q.tickets = Q.tile_start + n_parts + 1 + ((n_parts + 1) & 1u);
-                            tr.mark(ctx, "    derive: buckets allocated", n_parts);
-                            timer_begin(ctx, F_OTHER, 3);
-                            launch_derive_partitioned(Q, ctx->n_sms, ctx->st);
-                            timer_end(ctx);
-                            ctx->stats.rows_built += cur->n;  // (counted as table traffic: partitioned candidates)
-                        } else {
-                            timer_begin(ctx, F_OTHER);
-                            launch_derive(D, ctx->n_sms, ctx->st);
-                            timer_end(ctx);
-                        }
-                        KB_CUDA(ctx, cudaGetLastError());
-                        // counts are read immediately: the control arena may be recycled by later joins of this round
-                        KB_TRY(ctrl_read(ctx));
-                        pd.count = ctx->h_ctrl[coff];
-                        if (ctx->h_ctrl[coff + 1] == 1u) return fail(ctx, KB_E_LIMIT, "known-fact set overflow");
-                        if (ctx->h_ctrl[coff + 1] == 0u) break;
-                        // budget reached: rebuild the set larger WITH the facts appended so far, then repeat the launch (facts already
-                        // inserted are found present and are not appended twice; the derivation count is the last, complete pass's)
-                        fx.pend.push_back(pd);
-                        const kb_status gs = ensure_set(fx, hr, cur->n, true);
-                        fx.pend.pop_back();
-                        if (gs != KB_OK) return gs;
-                        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff + 1, 0, sizeof(u32), ctx->st));
-                        KB_CUDA(ctx, cudaMemsetAsync(ctx->ctrl + coff + 4, 0, 2 * sizeof(u32), ctx->st));
-                    }
-                    unsigned long long nd;
-                    memcpy(&nd, ctx->h_ctrl + coff + 4, sizeof nd);
-                    st.derivations += nd;
-                    hr.set_count = count_before;
-                    hr.set_count += pd.count;
-                    if (pd.count) fx.pend.push_back(pd);
-                    tr.mark(ctx, "  derive", pd.count);
+                    KB_TRY(derive_head(cur.get(), rule.conclusion[c], &rule));
                 }
             }
         }
@@ -470,36 +519,42 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     // ---- result: inferred facts as (s,p,o) columns; also appended to the store (infer_generic.rs:46 index_manager.insert)
     auto res = std::make_unique<kb_rel>();
     res->slots = {0, 1, 2};
-    res->n = st.inferred;
+    // (with a seed: the accepted seed facts first, then the inferred ones)
+    const u64 total = seed_new + st.inferred;
+    if (total >= 0xFFFFFFF0ull || ctx->n_triples + total >= 0xFFFFFFF0ull) return fail(ctx, KB_E_LIMIT, "the closure exceeds 2^32 - 16 triples");
+    res->n = total;
     Col cs, cp, co;
-    KB_TRY(alloc_col(ctx, st.inferred, &cs));
-    KB_TRY(alloc_col(ctx, st.inferred, &cp));
-    KB_TRY(alloc_col(ctx, st.inferred, &co));
+    KB_TRY(alloc_col(ctx, total, &cs));
+    KB_TRY(alloc_col(ctx, total, &cp));
+    KB_TRY(alloc_col(ctx, total, &co));
     u64 off = 0;
-    for (auto& kv : fx.rels) {
-        PredRel& r = kv.second;
-        const u64 cnt = r.n - r.base_n;
-        if (!cnt) continue;
-        KB_CUDA(ctx, cudaMemcpyAsync(cs.ptr + off, r.s.ptr + r.base_n, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
-        KB_CUDA(ctx, cudaMemcpyAsync(co.ptr + off, r.o.ptr + r.base_n, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
-        launch_fill_u32(cp.ptr + off, r.pred, cnt, ctx->st);
-        off += cnt;
+    for (int pass = seed ? 0 : 1; pass < 2; pass++) {
+        for (auto& kv : fx.rels) {
+            PredRel& r = kv.second;
+            const u64 from = pass == 0 ? r.seed_from : r.base_n, to = pass == 0 ? r.base_n : r.n;
+            const u64 cnt = to - from;
+            if (!cnt) continue;
+            KB_CUDA(ctx, cudaMemcpyAsync(cs.ptr + off, r.s.ptr + from, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            KB_CUDA(ctx, cudaMemcpyAsync(co.ptr + off, r.o.ptr + from, cnt * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->st));
+            launch_fill_u32(cp.ptr + off, r.pred, cnt, ctx->st);
+            off += cnt;
+        }
     }
     res->cols = {cs, cp, co};
     for (auto& kv : fx.rels) if (kv.second.is_head) ctx->fix_hint[kv.first] = kv.second.n;
-    if (st.inferred) {
+    if (total) {
         Segment sg;
         sg.tag = KB_TAG_INFERRED;
-        sg.n = st.inferred;
+        sg.n = total;
         sg.s = cs; sg.p = cp; sg.o = co;
         ctx->segs.push_back(sg);
-        ctx->n_triples += st.inferred;
+        ctx->n_triples += total;
         ctx->store_version++;
         ctx->multi_valued.clear();
         ctx->single_valued.clear();
         ctx->index.clear();
     }
-    tr.mark(ctx, "result assembly", st.inferred);
+    tr.mark(ctx, "result assembly", total);
     cudaEventRecord(ev1, ctx->st);
     KB_CUDA(ctx, cudaStreamSynchronize(ctx->st));
     timers_flush(ctx);
@@ -507,7 +562,21 @@ extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint
     cudaEventElapsedTime(&ms, ev0, ev1);
     st.device_ms = ms;
     if (stats) *stats = st;
+    if (n_seed_new) *n_seed_new = seed_new;
     ctx->stats.rows_out = st.inferred;
     *inferred = res.release();
     return KB_OK;
+}
+
+extern "C" kb_status kb_datalog_fixpoint(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy, kb_rel** inferred,
+                                         kb_fixpoint_stats* stats) {
+    return fixpoint_impl(ctx, rules, n_rules, strategy, false, nullptr, inferred, nullptr, stats);
+}
+
+// Incremental materialisation: what Reasoner::add_abox_triple + infer_new_facts_semi_naive (reasoning.rs, semi_naive.rs:89) reach by
+// starting over, reached from the delta alone. Used per window slide (simple_r2r.rs:95-128 adds the slide's triples and materialises
+// again) and by the sharded fixpoint (kolibrie_b200/dist.py: facts derived on another rank arrive as seeds).
+extern "C" kb_status kb_datalog_fixpoint_seed(kb_ctx* ctx, const kb_rule* rules, uint32_t n_rules, uint32_t strategy, const kb_rel* seed,
+                                              kb_rel** out, uint64_t* n_seed_new, kb_fixpoint_stats* stats) {
+    return fixpoint_impl(ctx, rules, n_rules, strategy, true, seed, out, n_seed_new, stats);
 }

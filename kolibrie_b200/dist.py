@@ -302,3 +302,198 @@ def datalog_fixpoint_sharded(local_fixpoint, s, p, o, rules, replicated_preds, d
     inferred = np.asarray(local_fixpoint(S, P, O), dtype=np.uint32).reshape(-1, 3)
     is_rep = np.isin(inferred[:, 1], np.asarray(list(replicated_preds), dtype=np.uint32))
     return inferred[~is_rep] if rank != 0 else inferred
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Datalog across ranks, general case (SURVEY.md §8e "Datalog fixpoint": local delta joins, derived facts routed to their owners, the
+# owner dedups, termination by an all-reduce of the number of facts sent). Rules may join TWO premises over sharded predicates.
+#
+# Placement. A fact (s, P, o) lives on owner(s) = kb_shard_of(s, world) — its home, the rank that reports it. When a rule joins two
+# sharded premises on a variable v that sits in the OBJECT position of a premise over P, facts of P are kept on owner(o) as well
+# ("object-homed"): every fact that mentions the value v in a join position is then on owner(v), so the join for that value is
+# complete there and nowhere else has to see both sides. Replicated predicates (small ones: the TBox) are on every rank.
+# Super-steps. (0) base facts travel to their second homes; (1) every rank closes its local facts under the rules
+# (kb_datalog_fixpoint) and sends each derived fact to its homes; (k >= 2) the facts that arrived are the SEED of an incremental
+# closure (kb_datalog_fixpoint_seed: the known-fact set tells which of them are new, those alone are the first delta, the store is
+# OLD); what that derives is sent on. The loop ends when no rank sent anything. A rank that holds a fact it does not own may derive
+# from it too: sound (every stored fact is in the closure), redundant at worst — the owners' known-fact sets drop the repeats.
+def exchange_plan(rules: Sequence[dict], replicated_preds: Sequence[int] = ()):
+    """Returns (object_homed, replicated): the predicates whose facts need a second home on owner(object) for `rules` (compiled
+    rules: kolibrie_b200.engine.compile_rule), and the replicated ones. Raises ValueError for a rule the placement cannot serve:
+    more than two premises over sharded predicates, two that share no variable, or a sharded premise under a replicated head."""
+    rep = set(int(x) for x in replicated_preds)
+    homed = set()
+    for ri, r in enumerate(rules):
+        if any(p.p.is_var for p in r["premise"]):
+            continue  # a variable predicate never matches (join_algorithm.rs:515-521): the rule derives nothing
+        sharded = [p for p in r["premise"] if int(p.p.value) not in rep]
+        for h in r["conclusion"]:
+            if h.p.is_var:
+                raise ValueError(f"rule {ri}: variable head predicate")
+            if sharded and int(h.p.value) in rep:
+                raise ValueError(f"rule {ri}: a rule with a sharded premise must not derive a replicated predicate")
+        if len(sharded) > 2:
+            raise ValueError(f"rule {ri}: {len(sharded)} premises over sharded predicates (at most two: their join needs one exchange per extra premise)")
+        if len(sharded) == 2:
+            a, b = sharded
+            best = None
+            for pos_a, ta in (("s", a.s), ("o", a.o)):
+                for pos_b, tb in (("s", b.s), ("o", b.o)):
+                    if ta.is_var and tb.is_var and ta.value == tb.value:
+                        need = set()
+                        if pos_a == "o":
+                            need.add(int(a.p.value))
+                        if pos_b == "o":
+                            need.add(int(b.p.value))
+                        if best is None or len(need - homed) < len(best - homed):
+                            best = need
+            if best is None:
+                raise ValueError(f"rule {ri}: its two sharded premises share no variable")
+            homed |= best
+    return homed, rep
+
+
+class ShardedFixpoint:
+    """One rank of the exchange scheme above. `engine` does the data work on this rank's facts:
+    `load(rows)`, `closure() -> inferred rows`, `closure_seed(rows) -> (accepted rows, inferred rows)` — `DeviceFixpointEngine` on a
+    GPU, an oracle-backed stand-in in the CPU tests. Rows are [n, 3] uint32 arrays (s, p, o). Drive it with `run_sharded_fixpoint`."""
+
+    def __init__(self, engine, rank: int, world: int, rules: Sequence[dict], replicated_preds: Sequence[int] = ()):
+        self.engine, self.rank, self.world = engine, int(rank), int(world)
+        self.homed, self.rep = exchange_plan(rules, replicated_preds)
+        self.mine: List[np.ndarray] = []  # the inferred facts this rank reports
+        self.steps = 0
+        self.sent_rows = 0
+        self._loaded = False
+        self._base: Optional[np.ndarray] = None
+
+    def _isin(self, preds: np.ndarray, which: set) -> np.ndarray:
+        return np.isin(preds, np.fromiter(which, dtype=np.uint32, count=len(which))) if which else np.zeros(len(preds), dtype=bool)
+
+    def _route(self, rows: np.ndarray, base: bool) -> List[np.ndarray]:
+        """per destination rank, the rows to send there (never to this rank itself)"""
+        parts = [np.empty((0, 3), np.uint32) for _ in range(self.world)]
+        if len(rows) == 0 or self.world == 1:
+            return parts
+        is_rep = self._isin(rows[:, 1], self.rep)
+        home_s = shard_of(rows[:, 0], self.world)
+        home_o = np.where(self._isin(rows[:, 1], self.homed), shard_of(rows[:, 2], self.world), home_s)
+        for d in range(self.world):
+            if d == self.rank:
+                continue
+            # base facts: this rank is their subject home, so only the second home and the replicas are missing;
+            # derived facts of replicated predicates are derived on every rank alike (exchange_plan) and never travel
+            to_d = ((home_s == d) | (home_o == d)) & ~is_rep
+            if base:
+                to_d |= is_rep
+            parts[d] = np.ascontiguousarray(rows[to_d])
+        return parts
+
+    def _report(self, rows: np.ndarray):
+        if len(rows) == 0:
+            return
+        is_rep = self._isin(rows[:, 1], self.rep)
+        keep = np.where(is_rep, self.rank == 0, shard_of(rows[:, 0], self.world) == self.rank)
+        if keep.any():
+            self.mine.append(rows[keep])
+
+    def start(self, s: np.ndarray, p: np.ndarray, o: np.ndarray) -> List[np.ndarray]:
+        """super-step 0: `s, p, o` = this rank's subject shard of the base facts; returns what the other ranks need of it"""
+        rows = np.stack([np.asarray(s, np.uint32), np.asarray(p, np.uint32), np.asarray(o, np.uint32)], axis=1)
+        if self.world > 1 and not (shard_of(rows[:, 0], self.world) == self.rank).all():
+            raise ValueError("the base facts of a rank must be its subject shard (dist.shard_triples)")
+        self._base = rows
+        parts = self._route(rows, base=True)
+        self.sent_rows += sum(len(x) for x in parts)
+        return parts
+
+    def step(self, received: np.ndarray) -> List[np.ndarray]:
+        """one super-step: takes what arrived, runs the engine, returns the derived facts per destination"""
+        received = np.asarray(received, np.uint32).reshape(-1, 3)
+        self.steps += 1
+        if not self._loaded:
+            self.engine.load(np.concatenate([self._base, received], axis=0))
+            self._base = None
+            self._loaded = True
+            inferred = self.engine.closure()
+        else:
+            accepted, inferred = self.engine.closure_seed(received)
+            self._report(accepted)
+        self._report(inferred)
+        parts = self._route(inferred, base=False)
+        self.sent_rows += sum(len(x) for x in parts)
+        return parts
+
+    def result(self) -> np.ndarray:
+        """the inferred facts this rank reports: those whose subject it owns; replicated predicates on rank 0 only"""
+        return np.concatenate(self.mine, axis=0) if self.mine else np.empty((0, 3), np.uint32)
+
+
+class DeviceFixpointEngine:
+    """ShardedFixpoint's engine on one GPU: the closures are kb_datalog_fixpoint / kb_datalog_fixpoint_seed over the context's store."""
+
+    def __init__(self, ctx, rules: Sequence[dict], strategy: int = 0):
+        self.ctx, self.rules, self.strategy = ctx, list(rules), strategy
+        self.device_ms = 0.0
+
+    def load(self, rows: np.ndarray):
+        self.ctx.store_load(rows[:, 0], rows[:, 1], rows[:, 2])
+
+    def closure(self) -> np.ndarray:
+        rel, st = self.ctx.datalog_fixpoint(self.rules, self.strategy)
+        self.device_ms += st.device_ms
+        out = rel.to_numpy([0, 1, 2])
+        rel.free()
+        return out
+
+    def closure_seed(self, rows: np.ndarray):
+        if len(rows) == 0:
+            e = np.empty((0, 3), np.uint32)
+            return e, e
+        seed = self.ctx.rel_from_host([0, 1, 2], [np.ascontiguousarray(rows[:, k]) for k in range(3)])
+        rel, n_new, st = self.ctx.datalog_fixpoint_seed(self.rules, seed, self.strategy)
+        self.device_ms += st.device_ms
+        out = rel.to_numpy([0, 1, 2])
+        rel.free()
+        seed.free()
+        return out[:n_new], out[n_new:]
+
+
+def exchange_rows(parts: Sequence[np.ndarray], device=None, group=None) -> np.ndarray:
+    """variable-size all-to-all of [n, 3] uint32 row blocks: parts[d] goes to rank d; returns what arrived (source-rank order)"""
+    world = dist.get_world_size(group)
+    dev = device or torch.device("cpu")
+    offs = [0]
+    for r in range(world):
+        offs.append(offs[-1] + len(parts[r]))
+    flat = np.concatenate([np.asarray(x, np.uint32).reshape(-1, 3) for x in parts], axis=0) if offs[-1] else np.empty((0, 3), np.uint32)
+    cols = [torch.from_numpy(np.ascontiguousarray(flat[:, k]).view(np.int32)).to(dev) for k in range(3)]
+    recv = all_to_all_relation(cols, offs, group)
+    return np.stack([t.cpu().numpy().view(np.uint32) for t in recv], axis=1) if len(recv[0]) else np.empty((0, 3), np.uint32)
+
+
+def run_sharded_fixpoint(node: ShardedFixpoint, s, p, o, device=None, group=None) -> np.ndarray:
+    """Drives one rank's `ShardedFixpoint` with torch.distributed (NCCL on the GPU box, gloo in the CPU tests): exchange, step, and an
+    all-reduce of the rows sent per super-step as the termination test. Returns this rank's share of the inferred facts."""
+    parts = node.start(s, p, o)
+    parts = node.step(exchange_rows(parts, device, group))
+    while sum_over_ranks(sum(len(x) for x in parts), device, group) > 0:
+        parts = node.step(exchange_rows(parts, device, group))
+    return node.result()
+
+
+def run_sharded_fixpoint_local(nodes: Sequence[ShardedFixpoint], shards: Sequence[tuple]) -> List[np.ndarray]:
+    """The same loop for `world` nodes living in ONE process (one context per node on the same GPU, or oracle engines): the exchange is
+    a transpose of the outgoing lists. Used by the single-GPU tests of the scheme; `shards[r]` = (s, p, o) of rank r."""
+    world = len(nodes)
+
+    def transpose(out):
+        return [np.concatenate([out[src][dst] for src in range(world)], axis=0) for dst in range(world)]
+
+    out = [nodes[r].start(*shards[r]) for r in range(world)]
+    inbox = transpose(out)
+    out = [nodes[r].step(inbox[r]) for r in range(world)]
+    while sum(len(x) for parts in out for x in parts) > 0:
+        inbox = transpose(out)
+        out = [nodes[r].step(inbox[r]) for r in range(world)]
+    return [n.result() for n in nodes]

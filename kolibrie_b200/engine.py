@@ -565,6 +565,8 @@ class Reasoner:
         self._fact_set: set = set()
         self._dirty = True
         self.last_stats = None
+        self._n_in_store: Optional[int] = None  # facts of self._facts the device store holds, once a fixpoint has closed it
+        self._closed_rules = -1                 # len(self.rules) at that fixpoint
 
     def add_abox_triple(self, subject: str, predicate: str, obj: str):
         t = (self.dictionary.encode(subject), self.dictionary.encode(predicate), self.dictionary.encode(obj))
@@ -581,6 +583,8 @@ class Reasoner:
             arr = np.array(self._facts, dtype=np.uint32).reshape(-1, 3)
             self.ctx.store_load(arr[:, 0], arr[:, 1], arr[:, 2])
             self._dirty = False
+            if self._n_in_store is not None and self._n_in_store != len(self._facts):
+                self._n_in_store = None  # the reloaded store holds triples no fixpoint has seen: it is not a closed store plus a seed
         num, isn = self.dictionary.numeric_table()
         self.ctx.dict_numeric_load(num, isn)
 
@@ -593,6 +597,35 @@ class Reasoner:
         for t in out:  # the device already appended them to its store (infer_generic.rs:46)
             self._fact_set.add(t)
             self._facts.append(t)
+        self._n_in_store, self._closed_rules = len(self._facts), len(self.rules)
+        return out
+
+    def infer_new_facts_incremental(self, strategy: int = c.SEMI_NAIVE):
+        """`add_abox_triple` after a fixpoint, then infer again WITHOUT starting over (the reference starts over: semi_naive.rs:89 sets
+        the delta to every fact): the triples added since the last fixpoint are the seed of kb_datalog_fixpoint_seed — they alone are
+        the first delta, the closed store is OLD. Returns the facts inferred from them, the same set a fresh
+        infer_new_facts_semi_naive() would add. Falls back to the full fixpoint when there is no closed store to extend."""
+        if self._n_in_store is None or self._closed_rules != len(self.rules) or self._n_in_store > len(self._facts):
+            return self._infer(strategy)
+        rules = [compile_rule(r) for r in self.rules]
+        rule_preds = {int(x.p.value) for r in rules for x in list(r["premise"]) + list(r["conclusion"]) if not x.p.is_var}
+        added = np.array(self._facts[self._n_in_store:], dtype=np.uint32).reshape(-1, 3)
+        num, isn = self.dictionary.numeric_table()
+        self.ctx.dict_numeric_load(num, isn)
+        in_rules = np.isin(added[:, 1], np.fromiter(rule_preds, np.uint32, len(rule_preds))) if len(added) else np.zeros(0, bool)
+        other = added[~in_rules]
+        if len(other):  # predicates no rule mentions: plain store rows
+            self.ctx.store_append(other[:, 0], other[:, 1], other[:, 2], 0)
+        sd = added[in_rules]
+        seed = self.ctx.rel_from_host([0, 1, 2], [np.ascontiguousarray(sd[:, k]) for k in range(3)])
+        rel, n_new, st = self.ctx.datalog_fixpoint_seed(rules, seed, strategy)
+        self.last_stats = st
+        rows = rel.to_numpy([0, 1, 2])[n_new:]
+        out = [tuple(int(x) for x in r) for r in rows]
+        for t in out:
+            self._fact_set.add(t)
+            self._facts.append(t)
+        self._n_in_store, self._dirty = len(self._facts), False
         return out
 
     def infer_new_facts_semi_naive(self):

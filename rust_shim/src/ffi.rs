@@ -84,6 +84,9 @@ extern "C" {
     pub fn kb_plan_free(ctx: *mut KbCtx, plan: *mut KbPlan);
     // Datalog
     pub fn kb_datalog_fixpoint(ctx: *mut KbCtx, rules: *const KbRule, n: u32, strategy: u32, out: *mut *mut KbRel, stats: *mut KbFixpointStats) -> kb_status;
+    // incremental: the store is closed under the rules already, `seed` (s, p, o) are the triples added since
+    pub fn kb_datalog_fixpoint_seed(ctx: *mut KbCtx, rules: *const KbRule, n: u32, strategy: u32, seed: *const KbRel, out: *mut *mut KbRel, n_seed_new: *mut u64,
+                                    stats: *mut KbFixpointStats) -> kb_status;
     // multi-GPU helpers
     pub fn kb_shard_of(key: u32, n_shards: u32) -> u32;
     pub fn kb_set_sharding(ctx: *mut KbCtx, rank: u32, world: u32) -> kb_status;
