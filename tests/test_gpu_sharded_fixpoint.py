@@ -154,3 +154,46 @@ def test_reasoner_mirror_incremental_inference():
     assert r.infer_new_facts_incremental() == [], "nothing added since: nothing inferred"
     r.ctx.close()
     fresh.ctx.close()
+
+
+@pytest.mark.parametrize("state", ["1", "0"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_a_run_of_seeds_with_and_without_the_kept_state(name, state, monkeypatch):
+    """six seeds in a row (a growing window): with KOLIBRIE_FIX_STATE=1 (default) every call after the first continues from the relations
+    and known-fact sets its predecessor left in the context; with 0 every call splits the store again. Same answers, call by call."""
+    monkeypatch.setenv("KOLIBRIE_FIX_STATE", state)
+    rows, rules, numeric, _ = CASES[name]()
+    rng = np.random.default_rng(23)
+    order = rng.permutation(len(rows))
+    chunks = np.array_split(order, 8)
+    base = rows[np.concatenate(chunks[:2])]
+    eng = S.OracleEngine(rules, numeric)
+    eng.load(base)
+    want0 = eng.closure()
+    cx = c.Context(0)
+    try:
+        cx.store_load(base[:, 0], base[:, 1], base[:, 2])
+        rel, st = cx.datalog_fixpoint(rules)
+        H.assert_same_bag(rel.to_numpy([0, 1, 2]), want0, f"{name}: first closure")
+        for k in range(2, 8):
+            sd = rows[chunks[k]]
+            if k == 5:
+                sd = np.concatenate([sd, rows[chunks[3]][:7]], axis=0)  # some triples the store has seen already
+            want_acc, want_inf = eng.closure_seed(sd)
+            seed_rel = cx.rel_from_host([0, 1, 2], [np.ascontiguousarray(sd[:, j]) for j in range(3)])
+            out, n_new, st2 = cx.datalog_fixpoint_seed(rules, seed_rel)
+            got = out.to_numpy([0, 1, 2])
+            assert n_new == len(want_acc), (name, state, k)
+            H.assert_same_bag(got[:n_new], want_acc, f"{name} state {state} seed {k}: accepted")
+            H.assert_same_bag(got[n_new:], want_inf, f"{name} state {state} seed {k}: inferred")
+            if k == 4:  # a store mutation between two seeds: the kept state is stale and must not be used
+                extra = np.array([[123_456, 999_999, 7]], np.uint32)
+                cx.store_append(extra[:, 0], extra[:, 1], extra[:, 2], 77)
+                eng.rows = np.concatenate([eng.rows, extra], axis=0)
+        s, p, o = cx.store_download()
+        H.assert_same_bag(np.stack([s, p, o], axis=1), eng.rows, f"{name} state {state}: store at the end")
+        st_full, want_full = S.closure_of(rows, rules, numeric)
+        n_inferred_total = len(eng.rows) - len(rows) - 1
+        assert n_inferred_total == len(want_full), "the closure reached seed by seed == the closure of all the triples at once"
+    finally:
+        cx.close()
