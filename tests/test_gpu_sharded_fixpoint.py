@@ -197,3 +197,18 @@ def test_a_run_of_seeds_with_and_without_the_kept_state(name, state, monkeypatch
         assert n_inferred_total == len(want_full), "the closure reached seed by seed == the closure of all the triples at once"
     finally:
         cx.close()
+
+
+def test_seed_closure_through_the_partitioned_dedup(monkeypatch):
+    """the same comparison with the radix-partitioned candidate dedup forced onto small inputs (the seed's facts and the heads derived
+    from them both go through derive_partition_kernel / derive_probe_kernel)"""
+    monkeypatch.setenv("KOLIBRIE_DERIVE_PART", "1")
+    monkeypatch.setenv("KOLIBRIE_DERIVE_SLICE", "2048")
+    monkeypatch.setenv("KOLIBRIE_DERIVE_MIN_ROWS", "16")
+    cx = c.Context(0)
+    try:
+        for name in sorted(CASES):
+            rows, rules, numeric, _ = CASES[name]()
+            check_seed_call(cx, rows, rules, numeric, c.SEMI_NAIVE, f"{name}/partitioned")
+    finally:
+        cx.close()
