@@ -17,7 +17,8 @@ dataset has N x that, sharded by kb_shard_of(subject, N); a subject-star join ne
              and the download of the binding columns are all inside the timed region
   roofline   algorithmic bytes (SURVEY.md §8d formulas) / CUDA-event time of the dominant kernel family, vs the measured HBM peak
   multi_gpu  (N > 1) the legs that exercise the real multi-GPU path, each parity-asserted against closed-form digests of the generator:
-             cfg3 = 4-pattern star + GROUP BY ?t COUNT with the cross-rank merge of the partial groups (all-gather + kb_groups_merge);
+             cfg3 = 4-pattern star + GROUP BY ?t COUNT with the cross-rank merge of the partial groups inside the prepared plan
+             (peer-memory tables, device-side barrier, one merge kernel over NVLink), the NCCL all-gather + kb_groups_merge variant beside it;
              shuffle_join = a path join on a NON-subject key through the fused peer-memory shuffle (kb_shuffle_push over NVLink);
              strong = the 100 M-triple store of BASELINE configs[2] split over the N GPUs (strong scaling)
   cfg2_10M   (N = 1) the same query on BASELINE configs[1]'s own 10 M-triple store: the size the CPU arm runs
