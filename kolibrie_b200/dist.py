@@ -11,7 +11,12 @@
   - `shuffle_relation`: `kb_partition` (device) splits a relation into `world` contiguous ranges, `all_to_all_relation` exchanges
     the range sizes and then the columns with `torch.distributed.all_to_all_single` — NCCL on the GPU box, gloo in the CPU tests.
 
-Only plumbing lives here; all data-touching work is in libkolibrie_b200.so.
+* Datalog over a sharded store: the broadcast plan (`datalog_fixpoint_sharded`) and, for rules that join two sharded predicates, the
+  super-step scheme at the end of this file (`exchange_plan`, `ShardedFixpoint`, `run_sharded_fixpoint`): closures and dedup on the
+  device (`kb_datalog_fixpoint`, `kb_datalog_fixpoint_seed`), the derived facts of a super-step routed to their home ranks here.
+
+Plumbing lives here; the data-touching work is in libkolibrie_b200.so — with one exception, said where it stands: the routing of a
+super-step's derived facts (which rank is home to which row) is numpy on the host, the rows travel as host arrays.
 """
 from __future__ import annotations
 
