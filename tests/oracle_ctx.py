@@ -90,5 +90,45 @@ class OracleCtx:
     def rel_from_host(self, slots, cols):
         return self._wrap(O.rel_from_host(list(slots), [np.asarray(x, np.uint32) for x in cols]))
 
+    # ---- Datalog (Reasoner mirror on CPU): the contracts of kb_datalog_fixpoint / kb_datalog_fixpoint_seed restated with the oracle
+    class _Stats:
+        def __init__(self, w=None):
+            self.rounds = len(w["round_new"]) if w else 0
+            self.round_new = list(w["round_new"]) + [0] * 64 if w else [0] * 64
+            self.inferred = len(w["facts"]) if w else 0
+            self.derivations = int(w["derivations"]) if w else 0
+            self.device_ms = 0.0
+
+    def store_append(self, s, p, o, tag):
+        self._spo = tuple(np.concatenate([a, np.asarray(b, np.uint32)]) for a, b in zip(self._spo, (s, p, o)))
+        self._make()
+
+    def _rows(self):
+        return np.stack(self._spo, axis=1)
+
+    def datalog_fixpoint(self, rules, strategy=0):
+        from kolibrie_b200 import capi as c
+
+        w = self.db.fixpoint(rules, strategy)
+        if w["status"] != 0:
+            raise c.KolibrieError(c.KB_E_UNSUPPORTED, "the oracle declines this rule set")
+        f = w["facts"]
+        if len(f):  # infer_generic.rs:46: inferred facts join the store
+            self.store_append(f[:, 0], f[:, 1], f[:, 2], 0)
+        return self.rel_from_host([0, 1, 2], [f[:, k].copy() for k in range(3)]), OracleCtx._Stats(w)
+
+    def datalog_fixpoint_seed(self, rules, seed, strategy=0):
+        """accepted = seed facts (of rule predicates) the store does not hold; inferred = closure(store + accepted) beyond that"""
+        sd = seed.to_numpy([0, 1, 2])
+        preds = {int(x.p.value) for r in rules for x in list(r["premise"]) + list(r["conclusion"]) if not x.p.is_var}
+        sd = sd[np.isin(sd[:, 1], np.fromiter(preds, np.uint32, len(preds)))] if len(sd) else sd
+        have = set(map(tuple, self._rows().tolist()))
+        acc = np.array([t for t in dict.fromkeys(map(tuple, sd.tolist())) if t not in have], np.uint32).reshape(-1, 3)
+        if len(acc):
+            self.store_append(acc[:, 0], acc[:, 1], acc[:, 2], 0)
+        rel, st = self.datalog_fixpoint(rules, strategy) if len(acc) else (self.rel_from_host([0, 1, 2], [np.empty(0, np.uint32)] * 3), OracleCtx._Stats())
+        out = np.concatenate([acc, rel.to_numpy([0, 1, 2])], axis=0)
+        return self.rel_from_host([0, 1, 2], [out[:, k].copy() for k in range(3)]), len(acc), st
+
     def close(self):
         self.db = None
