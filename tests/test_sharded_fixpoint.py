@@ -135,6 +135,15 @@ def _worker(rank, world, port, q):
             st, want = S.closure_of(rows, rules, numeric)
             H.assert_same_bag(allf, want, f"{name} over gloo")
             assert kd.sum_over_ranks(node.sent_rows) > 0
+        # the config-4 way: TBox replicated, only its base facts travel; rank 0 reports the replicated predicate
+        rows, rules, numeric, ids = S.taxonomy_case()
+        sc = ids["rdfs:subClassOf"]
+        s, p, o = kd.shard_triples(rows[:, 0], rows[:, 1], rows[:, 2], rank, world)
+        node = kd.ShardedFixpoint(S.OracleEngine(rules, numeric), rank, world, rules, [sc])
+        mine = kd.run_sharded_fixpoint(node, s, p, o)
+        assert rank == 0 or (mine[:, 1] != sc).all()
+        H.assert_same_bag(kd._allgather_rows(mine), S.closure_of(rows, rules, numeric)[1], "replicated TBox over gloo")
+        assert kd.sum_over_ranks(node.sent_rows) == int((rows[:, 1] == sc).sum()) * (world - 1)
         q.put((rank, "ok"))
     except Exception:  # pragma: no cover
         import traceback
@@ -144,10 +153,10 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_two_ranks_over_gloo():
+@pytest.mark.parametrize("world", [2, 3])
+def test_ranks_over_gloo(world):
     import torch.multiprocessing as mp
 
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -157,4 +166,4 @@ def test_two_ranks_over_gloo():
     res = [q.get(timeout=240) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
-    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
