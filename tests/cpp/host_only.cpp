@@ -26,5 +26,21 @@ int main() {
     size_t n_num = 0;
     for (auto b : isn) n_num += b;
     std::printf("N %zu %zu\n", dict.id_to_string.size(), n_num);
+    // FILTER compilation (types.rs:110-186 contract): the same expressions tests/test_cpp_host_cpu.py compiles with the Python mirror
+    using FE = kolibrie::FilterExpression;
+    const std::string lit = dict.id_to_string.empty() ? std::string("x") : dict.id_to_string[0];
+    std::vector<FE> exprs = {
+        FE::Cmp("?s", ">", "100000"),
+        FE::AndOf(FE::Cmp("?s", ">=", "5."), FE::Cmp("?t", "=", lit)),
+        FE::OrOf(FE::NotOf(FE::Cmp("?n", "!=", "a literal no triple mentions")), FE::Cmp("?s", "<", "abc")),
+        FE::Cmp("?s", "<=", "?t"),
+        FE::AndOf(FE::OrOf(FE::Cmp("t", "=", lit), FE::Cmp("?t", "!=", lit)), FE::NotOf(FE::Cmp("?s", ">", "-1e3"))),
+    };
+    for (size_t k = 0; k < exprs.size(); k++) {
+        kolibrie::SlotMap sm;
+        std::vector<kb_filter_op> ops;
+        kolibrie::Condition{exprs[k]}.compile(exprs[k], sm, dict, &ops);
+        for (auto& op : ops) std::printf("F %zu %u %u %u %u %a\n", k, op.op, op.slot, op.cmp, op.id, op.value);
+    }
     return 0;
 }

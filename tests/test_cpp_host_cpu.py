@@ -24,11 +24,13 @@ def run(strings):
     r = subprocess.run([BIN], input=inp, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0, r.stdout
     lines = r.stdout.splitlines()
+    progs = [tuple(x.split()[1:]) for x in lines if x.startswith("F ")]
+    lines = [x for x in lines if not x.startswith("F ")]
     assert len(lines) == 2 * len(strings) + 1
     parsed = [None if lines[2 * i] == "0" else float.fromhex(lines[2 * i].split()[1]) for i in range(len(strings))]
     ids = [int(lines[2 * i + 1].split()[1]) for i in range(len(strings))]
     n_ids, n_num = (int(x) for x in lines[-1].split()[1:])
-    return parsed, ids, n_ids, n_num
+    return parsed, ids, n_ids, n_num, progs
 
 
 def same(a, b):
@@ -44,7 +46,7 @@ def test_cpp_mirror_parses_f64_like_rust_and_like_the_python_mirror():
     fuzz = ["".join(rng.choice(alphabet, size=int(rng.integers(0, 9)))) for _ in range(4000)]
     fuzz = [s for s in fuzz if "\x00" not in s]
     strings = list(table["accept"]) + list(table["reject"]) + fuzz
-    parsed, ids, n_ids, n_num = run(strings)
+    parsed, ids, n_ids, n_num, progs = run(strings)
     for s, v in zip(strings[: len(table["accept"])], parsed):
         assert v is not None, f"C++ mirror rejects {s!r}, Rust accepts it"
     for s, v in zip(table["reject"], parsed[len(table["accept"]):]):
@@ -56,3 +58,20 @@ def test_cpp_mirror_parses_f64_like_rust_and_like_the_python_mirror():
     d = Dictionary()
     assert ids == [d.encode(s) for s in strings] and n_ids == len(d.id_to_string)
     assert n_num == sum(rust_parse_f64(s) is not None for s in d.id_to_string)
+    # FILTER programs: the expressions tests/cpp/host_only.cpp compiles, through the Python mirror
+    from kolibrie_b200.engine import And, Comparison, Condition, Not, Or, SlotMap
+
+    lit = d.id_to_string[0]
+    exprs = [
+        Comparison("?s", ">", "100000"),
+        And(Comparison("?s", ">=", "5."), Comparison("?t", "=", lit)),
+        Or(Not(Comparison("?n", "!=", "a literal no triple mentions")), Comparison("?s", "<", "abc")),
+        Comparison("?s", "<=", "?t"),
+        And(Or(Comparison("t", "=", lit), Comparison("?t", "!=", lit)), Not(Comparison("?s", ">", "-1e3"))),
+    ]
+    want = []
+    for k, e in enumerate(exprs):
+        for op in Condition(e).compile(SlotMap(), d):
+            want.append((str(k), str(op.op), str(op.slot), str(op.cmp), str(op.id), float(op.value).hex()))
+    got = [(a, b, cc, dd, e, float.fromhex(f).hex()) for a, b, cc, dd, e, f in progs]
+    assert got == want
