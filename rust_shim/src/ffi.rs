@@ -21,6 +21,10 @@ pub const KB_TAG_INFERRED: u64 = 0xFFFF_FFFF_FFFF_FFF0;
 #[repr(C)] #[derive(Clone, Copy, Debug, Default)] pub struct KbRuleFilter { pub lhs_slot: u32, pub cmp: u32, pub rhs_is_var: u32, pub rhs_slot: u32, pub rhs_value: c_double }
 #[repr(C)] pub struct KbRule { pub premise: *const KbPattern, pub n_premise: u32, pub filters: *const KbRuleFilter, pub n_filters: u32,
                               pub conclusion: *const KbPattern, pub n_conclusion: u32 }
+#[repr(C)] #[derive(Clone, Copy, Debug, Default)] pub struct KbStats { pub scan_ms: c_double, pub build_ms: c_double, pub probe_ms: c_double, pub filter_ms: c_double,
+    pub group_ms: c_double, pub other_ms: c_double, pub total_ms: c_double, pub scan_launches: u64, pub build_launches: u64, pub probe_launches: u64,
+    pub filter_launches: u64, pub group_launches: u64, pub other_launches: u64, pub rows_scanned: u64, pub rows_built: u64, pub rows_probed: u64,
+    pub rows_out: u64, pub h2d_bytes: u64, pub d2h_bytes: u64, pub kernel_launches: u64, pub fused_scan_builds: u64, pub index_joins: u64 }
 #[repr(C)] pub struct KbFixpointStats { pub rounds: u32, pub inferred: u64, pub derivations: u64, pub round_new: [u64; 64], pub device_ms: c_double }
 
 // kb_filter_opcode / kb_cmp / kb_agg_kind / kb_strategy
@@ -93,5 +97,32 @@ extern "C" {
     pub fn kb_shuffle_push(ctx: *mut KbCtx, r: *const KbRel, key_slot: u32, n_parts: u32, peer_cols: *const *mut u32, peer_cursors: *const *mut u32, capacity_rows: u64) -> kb_status;
     pub fn kb_rel_wrap_device(ctx: *mut KbCtx, slots: *const u32, n_cols: u32, d_cols: *const *mut u32, n_rows: u64, out: *mut *mut KbRel) -> kb_status;
     pub fn kb_groups_pack(g: *const KbGroups, dst: *mut c_void, capacity_bytes: u64, bytes: *mut u64) -> kb_status;
+    // the rest of the header (timing, device-resident loads, the legacy executor's i32 view, BGP execution, plan introspection and the
+    // cross-rank GROUP BY attachment, the count-matrix shuffle, store download, on-disk segments, the one-shot host-buffer joins)
+    pub fn kb_set_timing(ctx: *mut KbCtx, enabled: c_int) -> kb_status;
+    pub fn kb_get_stats(ctx: *mut KbCtx, out: *mut KbStats, reset: c_int) -> kb_status;
+    pub fn kb_store_load_device(ctx: *mut KbCtx, d_s: *const u32, d_p: *const u32, d_o: *const u32, n: u64) -> kb_status;
+    pub fn kb_set_use_index(ctx: *mut KbCtx, enabled: c_int) -> kb_status;
+    pub fn kb_dict_legacy_i32_load(ctx: *mut KbCtx, val: *const i32, is_i32: *const u8, n_ids: u32) -> kb_status;
+    pub fn kb_rel_device_col(r: *const KbRel, col: u32, d_ptr: *mut *const u32) -> kb_status;
+    pub fn kb_bgp_execute(ctx: *mut KbCtx, pats: *const KbPattern, n_pats: u32, filter: *const KbFilterOp, n_filter_ops: u32, project_slots: *const u32, n_project: u32,
+                          out: *mut *mut KbRel) -> kb_status;
+    pub fn kb_plan_info(plan: *const KbPlan, ring: *mut u32, capacity_rows: *mut u64, n_cols: *mut u32, slots: *mut u32, grouped: *mut u32) -> kb_status;
+    pub fn kb_plan_peer_scratch_bytes(plan: *const KbPlan) -> u64;
+    pub fn kb_plan_attach_peers(ctx: *mut KbCtx, plan: *mut KbPlan, rank: u32, world: u32, peer_scratch: *const *mut c_void) -> kb_status;
+    pub fn kb_partition(ctx: *mut KbCtx, r: *const KbRel, key_slot: u32, n_parts: u32, out: *mut *mut KbRel, part_offsets: *mut u64) -> kb_status;
+    pub fn kb_partition_counts(ctx: *mut KbCtx, r: *const KbRel, key_slot: u32, n_parts: u32, counts: *mut u64) -> kb_status;
+    pub fn kb_shuffle_scatter(ctx: *mut KbCtx, r: *const KbRel, key_slot: u32, n_parts: u32, peer_cols: *const *mut u32, base: *const u64, capacity_rows: u64) -> kb_status;
+    pub fn kb_rel_from_device(ctx: *mut KbCtx, slots: *const u32, n_cols: u32, d_cols: *const *const u32, n_rows: u64, out: *mut *mut KbRel) -> kb_status;
+    pub fn kb_store_download(ctx: *mut KbCtx, s: *mut u32, p: *mut u32, o: *mut u32, cap: u64, n: *mut u64) -> kb_status;
+    pub fn kb_segment_write(path: *const c_char, s: *const u32, p: *const u32, o: *const u32, n: u64, tag: u64) -> kb_status;
+    pub fn kb_segment_info(path: *const c_char, n_triples: *mut u64, tag: *mut u64, cmin: *mut u32, cmax: *mut u32) -> kb_status;
+    pub fn kb_segment_save(ctx: *mut KbCtx, tag: u64, whole_store: c_int, path: *const c_char) -> kb_status;
+    pub fn kb_store_append_file(ctx: *mut KbCtx, path: *const c_char, tag: u64, verify: c_int) -> kb_status;
+    pub fn kb_star_join_host(ctx: *mut KbCtx, s: *const u32, p: *const u32, o: *const u32, n: u64, join_slot: u32, pats: *const KbPattern, n_pats: u32,
+                             filter: *const KbFilterOp, n_filter_ops: u32, n_cols: *mut u32, slots: *mut u32, cols: *mut *mut u32, n_rows: *mut u64) -> kb_status;
+    pub fn kb_star_join_host_into(ctx: *mut KbCtx, s: *const u32, p: *const u32, o: *const u32, n: u64, join_slot: u32, pats: *const KbPattern, n_pats: u32,
+                                  filter: *const KbFilterOp, n_filter_ops: u32, n_cols: *mut u32, slots: *mut u32, cols: *const *mut u32, capacity_rows: u64,
+                                  n_rows: *mut u64) -> kb_status;
     pub fn kb_groups_merge(ctx: *mut KbCtx, parts: *const *const c_void, part_bytes: *const u64, n_parts: u32, out: *mut *mut KbGroups) -> kb_status;
 }
