@@ -70,3 +70,34 @@ def test_every_entry_point_is_documented_for_the_integrator():
             names.add(fam[0] + tail)
     missing = [f for f in fns if f not in names]
     assert not missing, missing
+
+
+def test_ctypes_signatures_match_the_header():
+    """every kb_* function the Python binding declares (capi.lib(): argtypes / restype) against the header: same number of parameters,
+    the same scalar width where the header passes a scalar, a pointer where it passes a pointer — a 32-bit argument where the callee
+    reads 64 bits (or the reverse) is the ABI bug this guards against"""
+    from tests.test_rust_shim_ffi import header_functions
+
+    L = capi.lib()
+    hdr = header_functions()
+    scalars = {"u32": (C.c_uint32,), "u64": (C.c_uint64,), "i32": (C.c_int32, C.c_int), "f64": (C.c_double,), "u8": (C.c_uint8,)}
+    checked = 0
+    for name, (ret, args) in sorted(hdr.items()):
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            continue  # not declared by the binding (it declares what it calls)
+        assert len(fn.argtypes) == len(args), f"{name}: {len(fn.argtypes)} argtypes, {len(args)} parameters in the header"
+        for i, (at, (base, levels)) in enumerate(zip(fn.argtypes, args)):
+            if levels:
+                assert at is C.c_void_p or at is C.c_char_p or hasattr(at, "contents") or issubclass(at, C._Pointer), f"{name} parameter {i}: {at} for a pointer"
+            else:
+                assert at in scalars[base], f"{name} parameter {i}: {at} for a {base}"
+        rbase, rlevels = ret
+        if rlevels:
+            assert fn.restype in (C.c_void_p, C.c_char_p) or issubclass(fn.restype, C._Pointer), f"{name}: result {fn.restype}"
+        elif rbase == "void":
+            assert fn.restype is None, f"{name}: result {fn.restype} for void"
+        else:
+            assert fn.restype in scalars[rbase], f"{name}: result {fn.restype} for {rbase}"
+        checked += 1
+    assert checked >= 60, checked
