@@ -124,3 +124,34 @@ def test_legacy_header_is_the_signature_kolibrie_binds():
     assert [x.split(":")[0].strip() for x in rust] == [re.findall(r"\w+", x)[-1] for x in ours]
     depth = lambda t: t.count("*")
     assert [depth(x.split(":")[1]) for x in rust] == [depth(x) for x in ours], "pointer depth per parameter as Rust passes it"
+
+
+def test_the_product_never_touches_the_oracle():
+    """the oracle is test infrastructure: nothing under kolibrie_b200/ imports it or the tests package, the shared library neither links
+    it nor carries its symbols nor any math / BLAS / thrust dependency beyond the C++ runtime, and bench.py reaches it only from inside the
+    functions of its CPU legs (cpu baseline, reference arm, the other configs' CPU samples) — never at module level"""
+    import ast
+    import subprocess
+
+    pkg = os.path.join(ROOT, "kolibrie_b200")
+    for d, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith(".py"):
+                tree = ast.parse(open(os.path.join(d, f)).read())
+                for node in ast.walk(tree):
+                    names = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""] if isinstance(node, ast.ImportFrom) else []
+                    for n in names:
+                        assert not re.match(r"^(tests|oracle)(\.|$)", n), f"{f} imports {n}"
+            if f.endswith((".cu", ".cuh", ".hpp", ".h")):
+                text = open(os.path.join(d, f), errors="replace").read()
+                assert not re.search(r'#include\s+[<"][^>"]*oracle', text), f
+    needed = subprocess.run(["readelf", "-d", capi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    libs = set(re.findall(r"NEEDED\)\s+Shared library: \[([^\]]+)\]", needed))
+    assert libs <= {"libstdc++.so.6", "libm.so.6", "libgcc_s.so.1", "libc.so.6", "ld-linux-x86-64.so.2", "libdl.so.2", "libpthread.so.0", "librt.so.1"}, libs
+    syms = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert not re.search(r"\bko_\w+", syms), "oracle symbols inside the product library"
+    bench = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    for node in bench.body:  # module level only
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            mod = node.module if isinstance(node, ast.ImportFrom) else ",".join(a.name for a in node.names)
+            assert "oracle" not in (mod or "") and not (mod or "").startswith("tests"), mod
